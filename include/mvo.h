@@ -1,0 +1,223 @@
+/*
+ * mvo.h — C ABI of libmvo.so: the B200 (sm_100a) implementation of the per-frame
+ * hot path of felixchenfy/Monocular-Visual-Odometry.
+ *
+ * The reference has no FFI of its own: its "operator API" is a set of free C++
+ * functions in my_slam::geometry / my_slam::optimization plus one inline OpenCV
+ * call in the VO layer.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).
+ * The C++ adapters with the reference's exact signatures live in
+ * include/my_slam/ and forward to these functions.
+ *
+ * Conventions
+ *  - All pointers in the mvo_* (non-_dev) functions are HOST pointers owned by
+ *    the caller; outputs are caller-allocated with an explicit capacity.
+ *  - *_dev functions take DEVICE pointers (resident in HBM) and are enqueued on
+ *    the context's stream without synchronising; they exist so that a pipeline
+ *    can keep a frame on the GPU between stages (and so bench.py can time the
+ *    kernels with inputs already resident).
+ *  - Return value: 0 = MVO_OK, negative = error (mvo_status).  mvo_last_error()
+ *    returns a human-readable message for the last failure on that context.
+ *  - A context is bound to one GPU and one stream; calls on one context must be
+ *    serialised by the caller (the reference is single-threaded, non-reentrant).
+ *  - No CPU fallback exists: if no CUDA device is usable mvo_create fails with
+ *    MVO_ERR_NO_DEVICE.
+ */
+#ifndef MVO_H_
+#define MVO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVO_VERSION 100
+
+typedef enum mvo_status {
+  MVO_OK = 0,
+  MVO_ERR_INVALID_ARG = -1,   /* null pointer, bad size, bad method index (reference throws
+                                 std::runtime_error at src/geometry/feature_match.cpp:225) */
+  MVO_ERR_NO_DEVICE = -2,     /* no usable CUDA device / wrong architecture */
+  MVO_ERR_CUDA = -3,          /* a CUDA runtime call or kernel failed */
+  MVO_ERR_CAPACITY = -4,      /* caller-provided output capacity too small */
+  MVO_ERR_UNSUPPORTED = -5,   /* size beyond a documented limit */
+  MVO_ERR_DEGENERATE = -6     /* numerically degenerate problem (e.g. < 4 PnP points) */
+} mvo_status;
+
+/* cv::KeyPoint, 28 bytes, same field order as OpenCV (features2d). */
+typedef struct mvo_keypoint {
+  float x, y;       /* pt, pixels in level-0 coordinates */
+  float size;       /* 31 * level scale */
+  float angle;      /* degrees [0,360) */
+  float response;   /* Harris response */
+  int32_t octave;   /* pyramid level */
+  int32_t class_id; /* always -1 */
+} mvo_keypoint;
+
+/* cv::DMatch, 16 bytes. */
+typedef struct mvo_dmatch {
+  int32_t query_idx;
+  int32_t train_idx;
+  int32_t img_idx;  /* reference leaves OpenCV's default: 0 from the matchers, -1 from DMatch(i,j,d) */
+  float distance;
+} mvo_dmatch;
+
+/* Parameters the hot path latches from config/config.yaml.
+ * mvo_default_params() fills the shipped values (with max_number_of_keypoints
+ * raised to the BASELINE's 2000 only if the caller does so explicitly). */
+typedef struct mvo_params {
+  /* ORB — src/geometry/feature_match.cpp:16-23 */
+  int32_t orb_nfeatures;      /* number_of_keypoints_to_extract = 8000 */
+  float orb_scale_factor;     /* scale_factor = 1.2 */
+  int32_t orb_nlevels;        /* level_pyramid = 4 (<= 8 supported) */
+  int32_t orb_fast_threshold; /* score_threshold = 20 */
+  /* grid NMS — feature_match.cpp:56-59 */
+  int32_t max_keypoints;      /* max_number_of_keypoints = 1500 */
+  int32_t grid_size;          /* kpts_uniform_selection_grid_size = 16 */
+  int32_t max_pts_per_grid;   /* kpts_uniform_selection_max_pts_per_grid = 8 */
+  /* matching — feature_match.cpp:137-139 (values after the reference's get<int> rounding) */
+  double xiang_gao_ratio;     /* xiang_gao_method_match_ratio = 2 */
+  double lowe_ratio;          /* lowe_method_dist_ratio: 0.8 read as int -> 1 */
+  /* PnP — src/vo/vo.cpp:314-317 (hard-coded in the reference) */
+  int32_t pnp_hypotheses;     /* batched hypothesis count (reference: <=100 adaptive); default 4096 */
+  float pnp_reproj_error;     /* 2.0 px */
+  uint64_t pnp_seed;          /* counter-based RNG seed for minimal sets */
+  int32_t pnp_refine_iters;   /* LM iterations of the final refit on inliers; default 20 */
+  /* BA — src/optimization/g2o_ba.cpp:275, g2o defaults */
+  int32_t ba_iterations;      /* reference: 50; BASELINE config 4: 10 */
+  double ba_huber_delta;      /* 1.0 */
+  int32_t ba_fix_first_pose;  /* 0 = reference behaviour (no pose fixed, g2o_ba.cpp:210-211) */
+} mvo_params;
+
+typedef struct mvo_ctx mvo_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+void mvo_default_params(mvo_params *p);
+/* Replaces the reference's process-global state (function-local static ORB objects, matchers
+ * and latched config values, feature_match.cpp:16-23,42-45,56-62,137-141). */
+int mvo_create(mvo_ctx **out, int device, const mvo_params *params /* NULL = defaults */);
+void mvo_destroy(mvo_ctx *ctx);
+const char *mvo_last_error(const mvo_ctx *ctx);
+int mvo_get_params(const mvo_ctx *ctx, mvo_params *out);
+int mvo_set_params(mvo_ctx *ctx, const mvo_params *p);
+/* Use an externally created cudaStream_t (e.g. torch's current stream) for all work. */
+int mvo_set_stream(mvo_ctx *ctx, void *cuda_stream);
+int mvo_synchronize(mvo_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t mvo_kernel_launches(const mvo_ctx *ctx);
+
+/* ---- ORB extraction --------------------------------------------------------------------
+ * mvo_calc_keypoints  == geometry::calcKeyPoints   (src/geometry/feature_match.cpp:11-36):
+ *     cv::ORB(8000,1.2,4,31,0,2,HARRIS,31,20)->detect + selectUniformKptsByGrid (:51-84).
+ * mvo_calc_descriptors == geometry::calcDescriptors (feature_match.cpp:38-49):
+ *     cv::ORB(8000,1.2,4)->compute on caller keypoints (level-sorted, as produced above).
+ * mvo_orb_extract      == both, fused (one upload, keypoints never leave the GPU in between);
+ *     this is what vo::Frame::calcKeyPoints + calcDescriptors (include/my_slam/vo/frame.h:73-86)
+ *     amount to per frame.
+ * image: rows x cols, `channels` = 3 (BGR, as cv::imread gives run_vo.cpp:114) or 1 (gray),
+ * `stride` bytes per row.  Keypoint order, coordinates, angle, response and descriptor bytes
+ * are bit-exact with OpenCV 4.13's cv::ORB.
+ * *n_kpts: in = capacity of kpts (and rows of desc), out = number written. */
+int mvo_calc_keypoints(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels,
+                       size_t stride, mvo_keypoint *kpts, int *n_kpts);
+int mvo_calc_descriptors(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels,
+                         size_t stride, const mvo_keypoint *kpts, int n_kpts,
+                         uint8_t *desc /* n_kpts x 32 */);
+int mvo_orb_extract(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels,
+                    size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);
+/* geometry::selectUniformKptsByGrid (feature_match.cpp:51-84) on host data (tiny, sequential).
+ * Unlike the reference, the grid dimensions are taken from THIS call's image size rather than
+ * latched from the first call. */
+int mvo_select_uniform_kpts_by_grid(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts,
+                                    int image_rows, int image_cols);
+
+/* Batched, device-resident extraction for throughput (extraction does not depend on VO state,
+ * SURVEY.md §8e): d_images = B frames, each rows x cols x channels with `stride` bytes per row
+ * and `frame_stride` bytes per frame.  Outputs are device arrays with `cap` entries per frame:
+ * d_kpts[B][cap], d_desc[B][cap][32], d_counts[B].  Asynchronous on the context stream. */
+int mvo_orb_extract_batch_dev(mvo_ctx *ctx, const uint8_t *d_images, int batch, int rows,
+                              int cols, int channels, size_t stride, size_t frame_stride,
+                              mvo_keypoint *d_kpts, uint8_t *d_desc, int32_t *d_counts, int cap);
+
+/* ---- descriptor matching ---------------------------------------------------------------
+ * Raw all-pairs kernels.  d1: n1 x 32 bytes (query), d2: n2 x 32 bytes (train).
+ * n1, n2 <= 65535.  Ties are broken towards the lowest train index (OpenCV BFMatcher rule).
+ *  mvo_match_hamming_nn   == cv::BFMatcher(NORM_HAMMING).match    (the exact search that
+ *      FLANN-LSH, feature_match.cpp:140,162, approximates): out[i] = best train for query i.
+ *  mvo_match_hamming_knn2 == matcher_bf->knnMatch(d1,d2,knn,2)    (feature_match.cpp:208):
+ *      out[2*i], out[2*i+1] = best and second best (n2 >= 2 required).
+ *  mvo_match_radius_sad   == geometry::matchByRadiusAndBruteForce (feature_match.cpp:86-124):
+ *      xy1/xy2 = keypoint pt (x,y) pairs; distance = sum|a-b| / 32 (double -> float);
+ *      queries with no train inside the radius are omitted.  *n_out receives the count. */
+int mvo_match_hamming_nn(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+                         mvo_dmatch *out /* n1 */);
+int mvo_match_hamming_knn2(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+                           mvo_dmatch *out /* 2*n1 */);
+int mvo_match_radius_sad(mvo_ctx *ctx, const uint8_t *d1, const float *xy1, int n1,
+                         const uint8_t *d2, const float *xy2, int n2, float radius,
+                         mvo_dmatch *out /* n1 */, int *n_out);
+/* geometry::matchFeatures (feature_match.cpp:126-239) end to end: method 1 (exact Hamming NN
+ * in place of FLANN-LSH), 2 (knn2 + Lowe ratio) or 3 (radius-gated SAD), the
+ * max(min_dis*ratio, 30) threshold (:187-196) and removeDuplicatedMatches (:241-260).
+ * xy1/xy2/radius are only read for method 3.  out capacity >= n1. */
+int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+                       int method_index, const float *xy1, const float *xy2, float radius,
+                       mvo_dmatch *out, int *n_out);
+/* geometry::removeDuplicatedMatches (feature_match.cpp:241-260): libstdc++ std::sort by
+ * trainIdx (unstable, like the reference) then keep the first of each run.  Host only. */
+int mvo_remove_duplicated_matches(mvo_dmatch *matches, int *n);
+
+/* Device-resident raw matcher: packed result keys, one (mode 0,2) or two (mode 1) per query:
+ * key = (distance << 16) | train_idx, 0xFFFFFFFF = no match.  mode: 0 = Hamming NN,
+ * 1 = Hamming knn2, 2 = radius SAD (d_xy1/d_xy2 required).  Asynchronous. */
+int mvo_match_dev(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                  const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
+                  uint32_t *d_keys);
+
+/* ---- PnP -------------------------------------------------------------------------------
+ * Replaces the inline call cv::solvePnPRansac(pts_3d, pts_2d, K, noArray(), rvec, t, false,
+ * 100, 2.0, 0.999, inliers) at src/vo/vo.cpp:318-320.
+ * pts3d: n x 3 float (cv::Point3f), pts2d: n x 2 float (cv::Point2f), K: 3x3 row-major double.
+ * Outputs: rvec[3] (Rodrigues), tvec[3], inliers (indices into the input, ascending; the
+ * consensus set of the best minimal model, as OpenCV returns), *n_inliers in = capacity,
+ * out = count.  Returns MVO_ERR_DEGENERATE if n < 4 or no hypothesis has >= 4 inliers. */
+int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n,
+                         const double *K, double *rvec, double *tvec, int32_t *inliers,
+                         int *n_inliers);
+/* Debug/parity hook: the hypotheses of the last mvo_solve_pnp_ransac call.
+ * poses: H x 12 doubles (R row-major 3x3, then t), counts: H inlier counts (-1 = invalid). */
+int mvo_pnp_last_hypotheses(mvo_ctx *ctx, double *poses, int32_t *counts, int cap, int *n_hyp);
+/* Final refit only: LM on the reprojection error over all n points from (rvec,tvec) in/out —
+ * the deterministic part of solvePnPRansac. */
+int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, const double *K,
+                   double *rvec, double *tvec);
+
+/* ---- bundle adjustment -----------------------------------------------------------------
+ * Replaces optimization::bundleAdjustment (src/optimization/g2o_ba.cpp:172-317), flattened:
+ *   poses_T_w_c : F x 16 doubles, row-major 4x4 camera->world (Frame::T_w_c_), in/out.
+ *   points      : P x 3 floats (MapPoint::pos_), in/out (written only if update_points).
+ *   edges       : E observations; edge e = (frame edge_frame[e], point edge_point[e],
+ *                 pixel obs[2e], obs[2e+1]) — the flattening of v_pts_2d/v_pts_2d_to_3d_idx.
+ *   K           : 3x3 row-major; only K[0] (fx), K[2], K[5] are used, like g2o's
+ *                 CameraParameters at g2o_ba.cpp:219-220.
+ *   information : 2x2 row-major (config information_matrix).
+ * g2o semantics restated in SURVEY.md App. B: LM (tau 1e-5, <=10 trials), Huber(delta),
+ * Schur complement over points when they are free, dense 6F x 6F solve.  F <= 16.
+ * stats (optional, 4 doubles): initial robust chi2, final robust chi2, LM iterations run,
+ * final lambda. */
+int mvo_bundle_adjustment(mvo_ctx *ctx, double *poses_T_w_c, int n_frames, float *points,
+                          int n_points, const int32_t *edge_frame, const int32_t *edge_point,
+                          const float *obs, int n_edges, const double *K,
+                          const double *information, int fix_points, int update_points,
+                          double *stats);
+/* optimization::optimizeSingleFrame (g2o_ba.cpp:34-145): one pose + its points, identity
+ * information, NO robust kernel, 50 iterations in the reference (ctx ba_iterations here). */
+int mvo_optimize_single_frame(mvo_ctx *ctx, double *pose_T_w_c, float *points, const float *obs,
+                              int n_points, const double *K, int fix_points, int update_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVO_H_ */

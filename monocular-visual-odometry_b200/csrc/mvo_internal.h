@@ -1,0 +1,106 @@
+// Internal declarations shared by the CUDA translation units of libmvo.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "mvo.h"
+
+#define MVO_MAX_LEVELS 8
+#define MVO_DESC_BYTES 32
+
+struct mvo_ctx;
+
+// ---- error plumbing -------------------------------------------------------------------
+int mvo_fail(mvo_ctx *ctx, int code, const char *fmt, ...);
+#define MVO_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return mvo_fail((ctx), MVO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,  \
+                      cudaGetErrorString(e__));                                          \
+  } while (0)
+#define MVO_CHECK_LAUNCH(ctx)                                                            \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      return mvo_fail((ctx), MVO_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__,        \
+                      __LINE__, cudaGetErrorString(e__));                                \
+  } while (0)
+#define MVO_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != MVO_OK) return rc__; \
+  } while (0)
+
+// Growable device / pinned-host scratch buffers owned by the context.
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+// ---- ORB per-level geometry -------------------------------------------------------------
+struct OrbLevel {
+  int w, h;          // level size (unbordered)
+  int pitch;         // bytes per row of the level planes (multiple of 128)
+  size_t img_off;    // offset of the gray plane inside a frame slot
+  size_t blur_off;   // offset of the blurred plane
+  float scale;       // (float)pow((double)scaleFactor_f32, level)
+  int cap;           // featuresPerLevel (OpenCV distribution)
+  int band_first;    // index of this level's first FAST band
+  int nbands;
+};
+
+struct OrbLayout {
+  int rows = 0, cols = 0, nlevels = 0;
+  OrbLevel lv[MVO_MAX_LEVELS];
+  size_t slot_bytes = 0;   // bytes of image planes per frame
+  int total_bands = 0;
+  int band_cap = 0;        // staging capacity (candidates) per band
+};
+
+struct mvo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  mvo_params prm;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 0;
+
+  // generic scratch
+  DevBuf d_a, d_b, d_c, d_d, d_e, d_f;
+  PinBuf h_a, h_b;
+
+  // ORB workspace (sized for `orb_batch` frames of the current layout)
+  OrbLayout orb;
+  int orb_batch = 0;
+  DevBuf orb_planes, orb_cand, orb_bandcnt, orb_sel, orb_misc, orb_in;
+  DevBuf orb_kpts, orb_desc, orb_counts;
+  PinBuf orb_h;
+
+  // match
+  DevBuf match_part, match_tickets, match_in, match_keys;
+  PinBuf match_h;
+
+  // PnP
+  DevBuf pnp_pts, pnp_hyp, pnp_cnt, pnp_out;
+  int pnp_last_h = 0;
+  // BA
+  DevBuf ba_buf;
+};
+
+int mvo_reserve(mvo_ctx *ctx, DevBuf &b, size_t bytes);
+int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes);
+
+// ---- stage entry points (host-side launchers, all asynchronous on ctx->stream) -----------
+// match.cu
+int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                     const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
+                     uint32_t *d_keys);

@@ -1,0 +1,297 @@
+"""ctypes binding of libmvo.so (include/mvo.h) — test/bench harness only.
+
+The product is the C ABI; this file is the thinnest possible Python view of it so that
+pytest and bench.py can drive the library with numpy (host) buffers or raw device pointers
+(``tensor.data_ptr()``).  There is NO fallback: if libmvo.so is missing or no B200 is
+visible, loading / ``Context()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(os.environ.get("MVO_LIB", _PKG_DIR / "libmvo.so"))
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")], align=False)
+DMATCH_DTYPE = np.dtype(
+    [("query_idx", "<i4"), ("train_idx", "<i4"), ("img_idx", "<i4"), ("distance", "<f4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16
+
+MVO_OK = 0
+ERR_NAMES = {0: "MVO_OK", -1: "MVO_ERR_INVALID_ARG", -2: "MVO_ERR_NO_DEVICE", -3: "MVO_ERR_CUDA",
+             -4: "MVO_ERR_CAPACITY", -5: "MVO_ERR_UNSUPPORTED", -6: "MVO_ERR_DEGENERATE"}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("orb_nfeatures", C.c_int32), ("orb_scale_factor", C.c_float), ("orb_nlevels", C.c_int32),
+        ("orb_fast_threshold", C.c_int32), ("max_keypoints", C.c_int32), ("grid_size", C.c_int32),
+        ("max_pts_per_grid", C.c_int32), ("xiang_gao_ratio", C.c_double), ("lowe_ratio", C.c_double),
+        ("pnp_hypotheses", C.c_int32), ("pnp_reproj_error", C.c_float), ("pnp_seed", C.c_uint64),
+        ("pnp_refine_iters", C.c_int32), ("ba_iterations", C.c_int32), ("ba_huber_delta", C.c_double),
+        ("ba_fix_first_pose", C.c_int32),
+    ]
+
+
+class MvoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+# Every exported symbol of include/mvo.h with its signature (also used by the CPU-side
+# "library loads and exports everything" test).
+_vp, _i, _sz, _f = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+_pi = C.POINTER(C.c_int)
+SIGNATURES = {
+    "mvo_default_params": (None, [C.POINTER(Params)]),
+    "mvo_create": (_i, [C.POINTER(_vp), _i, C.POINTER(Params)]),
+    "mvo_destroy": (None, [_vp]),
+    "mvo_last_error": (C.c_char_p, [_vp]),
+    "mvo_get_params": (_i, [_vp, C.POINTER(Params)]),
+    "mvo_set_params": (_i, [_vp, C.POINTER(Params)]),
+    "mvo_set_stream": (_i, [_vp, _vp]),
+    "mvo_synchronize": (_i, [_vp]),
+    "mvo_kernel_launches": (C.c_uint64, [_vp]),
+    "mvo_calc_keypoints": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _pi]),
+    "mvo_calc_descriptors": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _i, _vp]),
+    "mvo_orb_extract": (_i, [_vp, _vp, _i, _i, _i, _sz, _vp, _pi, _vp]),
+    "mvo_select_uniform_kpts_by_grid": (_i, [_vp, _vp, _pi, _i, _i]),
+    "mvo_orb_extract_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _i]),
+    "mvo_match_hamming_nn": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "mvo_match_hamming_knn2": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "mvo_match_radius_sad": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _f, _vp, _pi]),
+    "mvo_match_features": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _pi]),
+    "mvo_remove_duplicated_matches": (_i, [_vp, _pi]),
+    "mvo_match_dev": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _vp]),
+    "mvo_solve_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _pi]),
+    "mvo_pnp_last_hypotheses": (_i, [_vp, _vp, _vp, _i, _pi]),
+    "mvo_pnp_refine": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "mvo_bundle_adjustment": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "mvo_optimize_single_frame": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmvo.so and attach signatures.  Raises if the library is not built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(no CPU fallback exists)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().mvo_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One mvo_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0, params: Params | None = None, **overrides):
+        self.lib = load_library()
+        p = params or default_params()
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        h = C.c_void_p()
+        rc = self.lib.mvo_create(C.byref(h), device, C.byref(p))
+        if rc != MVO_OK:
+            raise MvoError(rc, "mvo_create failed (no usable sm_100 GPU? this library has no CPU path)")
+        self.h = h
+        self.params = p
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mvo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != MVO_OK:
+            raise MvoError(rc, self.lib.mvo_last_error(self.h).decode())
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        self._chk(self.lib.mvo_set_params(self.h, C.byref(self.params)))
+
+    def set_stream(self, cuda_stream: int):
+        self._chk(self.lib.mvo_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._chk(self.lib.mvo_synchronize(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.mvo_kernel_launches(self.h))
+
+    # ---- ORB ---------------------------------------------------------------------------
+    @staticmethod
+    def _img(image):
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        rows, cols, ch = img.shape
+        return img, rows, cols, ch
+
+    def calc_keypoints(self, image, cap: int = 16384):
+        img, rows, cols, ch = self._img(image)
+        kp = np.zeros(cap, KEYPOINT_DTYPE)
+        n = C.c_int(cap)
+        self._chk(self.lib.mvo_calc_keypoints(self.h, _ptr(img), rows, cols, ch, cols * ch, _ptr(kp), C.byref(n)))
+        return kp[: n.value].copy()
+
+    def calc_descriptors(self, image, kpts):
+        img, rows, cols, ch = self._img(image)
+        kp = _c(kpts, KEYPOINT_DTYPE)
+        desc = np.zeros((len(kp), 32), np.uint8)
+        self._chk(self.lib.mvo_calc_descriptors(self.h, _ptr(img), rows, cols, ch, cols * ch, _ptr(kp), len(kp), _ptr(desc)))
+        return desc
+
+    def orb_extract(self, image, cap: int = 16384):
+        img, rows, cols, ch = self._img(image)
+        kp = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(cap)
+        self._chk(self.lib.mvo_orb_extract(self.h, _ptr(img), rows, cols, ch, cols * ch, _ptr(kp), C.byref(n), _ptr(desc)))
+        return kp[: n.value].copy(), desc[: n.value].copy()
+
+    def select_uniform_kpts_by_grid(self, kpts, rows, cols):
+        kp = _c(kpts, KEYPOINT_DTYPE).copy()
+        n = C.c_int(len(kp))
+        self._chk(self.lib.mvo_select_uniform_kpts_by_grid(self.h, _ptr(kp), C.byref(n), rows, cols))
+        return kp[: n.value].copy()
+
+    def orb_extract_batch_dev(self, d_images, batch, rows, cols, ch, stride, frame_stride, d_kpts, d_desc, d_counts, cap):
+        self._chk(self.lib.mvo_orb_extract_batch_dev(self.h, _ptr(d_images), batch, rows, cols, ch, stride,
+                                                     frame_stride, _ptr(d_kpts), _ptr(d_desc), _ptr(d_counts), cap))
+
+    # ---- matching ----------------------------------------------------------------------
+    def match_hamming_nn(self, d1, d2):
+        d1, d2 = _c(d1, np.uint8), _c(d2, np.uint8)
+        out = np.zeros(len(d1), DMATCH_DTYPE)
+        self._chk(self.lib.mvo_match_hamming_nn(self.h, _ptr(d1), len(d1), _ptr(d2), len(d2), _ptr(out)))
+        return out
+
+    def match_hamming_knn2(self, d1, d2):
+        d1, d2 = _c(d1, np.uint8), _c(d2, np.uint8)
+        out = np.zeros((len(d1), 2), DMATCH_DTYPE)
+        self._chk(self.lib.mvo_match_hamming_knn2(self.h, _ptr(d1), len(d1), _ptr(d2), len(d2), _ptr(out)))
+        return out
+
+    def match_radius_sad(self, d1, xy1, d2, xy2, radius):
+        d1, d2 = _c(d1, np.uint8), _c(d2, np.uint8)
+        xy1, xy2 = _c(xy1, np.float32), _c(xy2, np.float32)
+        out = np.zeros(len(d1), DMATCH_DTYPE)
+        n = C.c_int(0)
+        self._chk(self.lib.mvo_match_radius_sad(self.h, _ptr(d1), _ptr(xy1), len(d1), _ptr(d2), _ptr(xy2), len(d2),
+                                                 C.c_float(radius), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def match_features(self, d1, d2, method_index=1, xy1=None, xy2=None, radius=0.0):
+        d1, d2 = _c(d1, np.uint8), _c(d2, np.uint8)
+        if xy1 is not None:
+            xy1, xy2 = _c(xy1, np.float32), _c(xy2, np.float32)
+        out = np.zeros(max(len(d1), 1), DMATCH_DTYPE)
+        n = C.c_int(0)
+        self._chk(self.lib.mvo_match_features(self.h, _ptr(d1), len(d1), _ptr(d2), len(d2), method_index,
+                                               _ptr(xy1), _ptr(xy2), C.c_float(radius), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def match_dev(self, mode, d_d1, d_xy1, n1, d_d2, d_xy2, n2, radius, d_keys):
+        self._chk(self.lib.mvo_match_dev(self.h, mode, _ptr(d_d1), _ptr(d_xy1), n1, _ptr(d_d2), _ptr(d_xy2), n2,
+                                          C.c_float(radius), _ptr(d_keys)))
+
+    # ---- PnP ---------------------------------------------------------------------------
+    def solve_pnp_ransac(self, pts3d, pts2d, K):
+        p3, p2, K = _c(pts3d, np.float32), _c(pts2d, np.float32), _c(K, np.float64)
+        rvec, tvec = np.zeros(3), np.zeros(3)
+        inl = np.zeros(len(p3), np.int32)
+        n = C.c_int(len(p3))
+        self._chk(self.lib.mvo_solve_pnp_ransac(self.h, _ptr(p3), _ptr(p2), len(p3), _ptr(K), _ptr(rvec), _ptr(tvec),
+                                                 _ptr(inl), C.byref(n)))
+        return rvec, tvec, inl[: n.value].copy()
+
+    def pnp_last_hypotheses(self):
+        cap = int(self.params.pnp_hypotheses)
+        poses = np.zeros((cap, 12))
+        counts = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        self._chk(self.lib.mvo_pnp_last_hypotheses(self.h, _ptr(poses), _ptr(counts), cap, C.byref(n)))
+        return poses[: n.value].copy(), counts[: n.value].copy()
+
+    def pnp_refine(self, pts3d, pts2d, K, rvec, tvec):
+        p3, p2, K = _c(pts3d, np.float32), _c(pts2d, np.float32), _c(K, np.float64)
+        rvec, tvec = _c(rvec, np.float64).copy().reshape(3), _c(tvec, np.float64).copy().reshape(3)
+        self._chk(self.lib.mvo_pnp_refine(self.h, _ptr(p3), _ptr(p2), len(p3), _ptr(K), _ptr(rvec), _ptr(tvec)))
+        return rvec, tvec
+
+    # ---- BA ----------------------------------------------------------------------------
+    def bundle_adjustment(self, poses_T_w_c, points, edge_frame, edge_point, obs, K, information=None,
+                          fix_points=False, update_points=True):
+        poses = _c(poses_T_w_c, np.float64).copy().reshape(-1, 16)
+        pts = _c(points, np.float32).copy().reshape(-1, 3)
+        ef, ep = _c(edge_frame, np.int32), _c(edge_point, np.int32)
+        ob = _c(obs, np.float32).reshape(-1, 2)
+        K = _c(K, np.float64)
+        info = _c(np.eye(2) if information is None else information, np.float64)
+        stats = np.zeros(4)
+        self._chk(self.lib.mvo_bundle_adjustment(self.h, _ptr(poses), len(poses), _ptr(pts), len(pts), _ptr(ef), _ptr(ep),
+                                                  _ptr(ob), len(ef), _ptr(K), _ptr(info), int(fix_points),
+                                                  int(update_points), _ptr(stats)))
+        return poses.reshape(-1, 4, 4), pts, stats
+
+    def optimize_single_frame(self, pose_T_w_c, points, obs, K, fix_points=False, update_points=True):
+        pose = _c(pose_T_w_c, np.float64).copy().reshape(16)
+        pts = _c(points, np.float32).copy().reshape(-1, 3)
+        ob = _c(obs, np.float32).reshape(-1, 2)
+        K = _c(K, np.float64)
+        self._chk(self.lib.mvo_optimize_single_frame(self.h, _ptr(pose), _ptr(pts), _ptr(ob), len(pts), _ptr(K),
+                                                      int(fix_points), int(update_points)))
+        return pose.reshape(4, 4), pts
+
+
+def remove_duplicated_matches(matches):
+    m = _c(matches, DMATCH_DTYPE).copy()
+    n = C.c_int(len(m))
+    rc = load_library().mvo_remove_duplicated_matches(_ptr(m), C.byref(n))
+    if rc != MVO_OK:
+        raise MvoError(rc, "mvo_remove_duplicated_matches")
+    return m[: n.value].copy()
