@@ -99,6 +99,8 @@ struct mvo_ctx {
 int mvo_reserve(mvo_ctx *ctx, DevBuf &b, size_t bytes);
 int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes);
 
+void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
+
 // ---- stage entry points (host-side launchers, all asynchronous on ctx->stream) -----------
 // match.cu
 int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,

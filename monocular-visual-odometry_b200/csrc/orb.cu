@@ -1,0 +1,765 @@
+// ORB extraction kernels for sm_100a — bit-exact with OpenCV 4.13's cv::ORB as the reference
+// calls it (src/geometry/feature_match.cpp:22-23,34,45,48) followed by the reference's own
+// first-come grid selection (feature_match.cpp:51-84).  Algorithm: SURVEY.md Appendix A.
+//
+// HBM layout per frame slot: for every pyramid level one gray plane and one blurred plane,
+// rows padded to a multiple of 128 B (16-byte vector / TMA-legal strides).  No 32-px border is
+// materialised: with edgeThreshold 31 no bit-exact result ever depends on it (FAST needs 3+1 px,
+// Harris 4, the orientation disc 15, rotated BRIEF samples <= 19 px from the keypoint).
+//
+// Kernels (all batched over frames in grid.y / grid.z):
+//   k_gray        BGR -> gray, fixed point (3735 B + 19235 G + 9798 R + 16384) >> 15
+//   k_resize      level l from level l-1, INTER_LINEAR_EXACT (8.8 x 8.8 fixed point, host tables)
+//   k_fast        one CTA per 8-row band: image rows staged in shared memory, quick 4-point
+//                 reject, cornerScore<16> only for survivors, 3x3 NMS, raster-ordered emit
+//   k_select      one CTA per frame: candidate compaction + first-come grid selection, restated
+//                 as rank-in-cell < max_per_cell and an ordered prefix count (deterministic)
+//   k_blur        7x7 sigma-2 Gaussian, float separable, round-half-even (ORB's descriptor blur)
+//   k_describe    one warp per keypoint: Harris response, intensity-centroid angle, 256 steered
+//                 BRIEF tests (lane i produces descriptor byte i)
+// Float formulas that OpenCV evaluates without FMA use __fmul_rn/__fadd_rn explicitly.
+#include <cooperative_groups.h>
+#include "orb.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+#include "orb_pattern.inc"   // __constant__-free table: static const signed char kOrbPattern[512][2]
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------ gray
+__global__ void __launch_bounds__(128)
+k_gray(OrbPlanDev plan, const uint8_t *__restrict__ in, int channels, size_t stride, size_t frame_stride,
+       uint8_t *__restrict__ planes) {
+  const int y = blockIdx.y, f = blockIdx.z;
+  const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int w = plan.lv[0].w, pitch = plan.lv[0].pitch;
+  if (x4 >= pitch) return;
+  const uint8_t *row = in + (size_t)f * frame_stride + (size_t)y * stride;
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i;
+    uint32_t g = 0;
+    if (x < w) {
+      if (channels == 3) {
+        const uint32_t b = row[3 * x], gg = row[3 * x + 1], r = row[3 * x + 2];
+        g = (3735u * b + 19235u * gg + 9798u * r + 16384u) >> 15;
+      } else {
+        g = row[x];
+      }
+    }
+    out |= g << (8 * i);
+  }
+  uint8_t *dst = planes + (size_t)f * plan.slot_bytes + plan.lv[0].img_off + (size_t)y * pitch;
+  *reinterpret_cast<uint32_t *>(dst + x4) = out;
+}
+
+// ---------------------------------------------------------------------------------- resize
+__global__ void __launch_bounds__(128)
+k_resize(OrbPlanDev plan, int level, const int32_t *__restrict__ tables, uint8_t *__restrict__ planes) {
+  const OrbLevelDev &L = plan.lv[level];
+  const OrbLevelDev &S = plan.lv[level - 1];
+  const int y = blockIdx.y, f = blockIdx.z;
+  const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (x4 >= L.pitch) return;
+  const int32_t *xofs = tables + L.tab_off, *xw1 = xofs + L.w, *yofs = xw1 + L.w, *yw1 = yofs + L.h;
+  uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
+  const int oy = yofs[y], wy1 = yw1[y], wy0 = 256 - wy1;
+  const int oy1 = min(oy + 1, S.h - 1);
+  const uint8_t *r0 = slot + S.img_off + (size_t)oy * S.pitch;
+  const uint8_t *r1 = slot + S.img_off + (size_t)oy1 * S.pitch;
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i;
+    uint32_t v = 0;
+    if (x < L.w) {
+      const int ox = xofs[x], wx1 = xw1[x], wx0 = 256 - wx1;
+      const int ox1 = min(ox + 1, S.w - 1);
+      const int h0 = r0[ox] * wx0 + r0[ox1] * wx1;
+      const int h1 = r1[ox] * wx0 + r1[ox1] * wx1;
+      v = (uint32_t)(h0 * wy0 + h1 * wy1 + 32768) >> 16;
+    }
+    out |= v << (8 * i);
+  }
+  *reinterpret_cast<uint32_t *>(slot + L.img_off + (size_t)y * L.pitch + x4) = out;
+}
+
+// ------------------------------------------------------------------------------------ FAST
+// cornerScore<16> (OpenCV fast_score.cpp) == max(t, A, B) - 1 with
+//   A = max over the 16 arcs of 9 contiguous ring pixels of min(d), B the same for -d,
+//   d[k] = centre - ring[k]; the pixel is a FAST-9 corner iff max(A, B) > t.
+__device__ __forceinline__ int fast_score(const uint8_t *__restrict__ p, int stride, int t) {
+  const int c = p[0];
+  int d[16];
+  d[0] = c - p[3 * stride];      d[1] = c - p[3 * stride + 1];   d[2] = c - p[2 * stride + 2];
+  d[3] = c - p[stride + 3];      d[4] = c - p[3];                d[5] = c - p[-stride + 3];
+  d[6] = c - p[-2 * stride + 2]; d[7] = c - p[-3 * stride + 1];  d[8] = c - p[-3 * stride];
+  d[9] = c - p[-3 * stride - 1]; d[10] = c - p[-2 * stride - 2]; d[11] = c - p[-stride - 3];
+  d[12] = c - p[-3];             d[13] = c - p[stride - 3];      d[14] = c - p[2 * stride - 2];
+  d[15] = c - p[3 * stride - 1];
+  int mn3[16], mx3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mn3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
+    mx3[k] = max(max(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
+  }
+  int A = -1000, B = 1000;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    A = max(A, min(min(mn3[k], mn3[(k + 3) & 15]), mn3[(k + 6) & 15]));
+    B = min(B, max(max(mx3[k], mx3[(k + 3) & 15]), mx3[(k + 6) & 15]));
+  }
+  const int m = max(A, -B);
+  return m > t ? m - 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict__ staging,
+       int32_t *__restrict__ bandcnt) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int band = blockIdx.x, f = blockIdx.y;
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < plan.nlevels && band >= plan.lv[l + 1].band_first) ++l;
+  const OrbLevelDev &L = plan.lv[l];
+  const int w = L.w, h = L.h, pitch = L.pitch;
+  const int t = plan.fast_threshold;
+  const int y0 = ORB_EDGE + (band - L.band_first) * ORB_BAND_H;     // first NMS row
+  const int nms_rows = min(ORB_BAND_H, h - ORB_EDGE - y0);
+  const int sstride = pitch + 16;                                    // de-alias rows across banks
+  const int img_rows = nms_rows + 8;                                 // rows y0-4 .. y0+nms_rows+3
+  const int sc_rows = nms_rows + 2;                                  // rows y0-1 .. y0+nms_rows
+  const int w32 = (w + 31) >> 5;
+
+  uint8_t *s_img = smem;                                             // [ORB_BAND_H+8][sstride]
+  uint8_t *s_sc = s_img + (ORB_BAND_H + 8) * sstride;                // [ORB_BAND_H+2][sstride]
+  uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_sc + (ORB_BAND_H + 2) * sstride);   // [ORB_BAND_H][w32]
+  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_bits + ORB_BAND_H * w32);           // [(ORB_BAND_H+2)*w]
+  __shared__ int s_cnt;
+  __shared__ int s_wsum[8];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t *img = planes + (size_t)f * plan.slot_bytes + L.img_off;
+
+  // stage image rows (whole padded rows, 16-byte vectors), clear score rows and the keep bitmap
+  {
+    const int vec_per_row = pitch >> 4;
+    for (int i = tid; i < img_rows * vec_per_row; i += 256) {
+      const int r = i / vec_per_row, v = i - r * vec_per_row;
+      const uint4 val = *reinterpret_cast<const uint4 *>(img + (size_t)(y0 - 4 + r) * pitch + v * 16);
+      *reinterpret_cast<uint4 *>(s_img + r * sstride + v * 16) = val;
+    }
+    const int svec = (sc_rows * sstride) >> 4;
+    for (int i = tid; i < svec; i += 256) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < ORB_BAND_H * w32; i += 256) s_bits[i] = 0;
+    if (tid == 0) s_cnt = 0;
+  }
+  __syncthreads();
+
+  // phase 1: quick reject on the 4 compass points; survivors go to a shared list.
+  // An arc of 9 contiguous ring pixels always contains one of {0,8} and one of {4,12}.
+  {
+    const int xspan = w - 2 * (ORB_EDGE - 1);                        // columns 30 .. w-31
+    const int nseg = (xspan + 31) >> 5;
+    for (int s = warp; s < sc_rows * nseg; s += 8) {
+      const int r = s / nseg, seg = s - r * nseg;                    // r: score row (image row y0-1+r)
+      const int x = (ORB_EDGE - 1) + seg * 32 + lane;
+      bool pass = false;
+      if (x < w - (ORB_EDGE - 1)) {
+        const uint8_t *p = s_img + (r + 3) * sstride + x;            // s_img row of image row y0-1+r
+        const int c = p[0], hi = c + t, lo = c - t;
+        const int a = p[3 * sstride], b = p[-3 * sstride], e = p[3], g = p[-3];
+        const bool bright = (a > hi || b > hi) && (e > hi || g > hi);
+        const bool dark = (a < lo || b < lo) && (e < lo || g < lo);
+        pass = bright || dark;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_cnt, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) s_list[base + __popc(m & lanemask_lt())] = (uint16_t)((r << 12) | x);
+      }
+    }
+  }
+  __syncthreads();
+  const int ncand = s_cnt;
+
+  // phase 2: exact corner score for the survivors
+  for (int i = tid; i < ncand; i += 256) {
+    const int e = s_list[i], r = e >> 12, x = e & 0xFFF;
+    const int sc = fast_score(s_img + (r + 3) * sstride + x, sstride, t);
+    if (sc) s_sc[r * sstride + x] = (uint8_t)sc;
+  }
+  __syncthreads();
+
+  // phase 3: 3x3 non-maximum suppression (strictly greater than all 8 neighbours), border filter
+  for (int i = tid; i < ncand; i += 256) {
+    const int e = s_list[i], r = e >> 12, x = e & 0xFFF;
+    if (r < 1 || r > nms_rows || x < ORB_EDGE || x >= w - ORB_EDGE) continue;
+    const uint8_t *q = s_sc + r * sstride + x;
+    const int sc = q[0];
+    if (sc == 0) continue;
+    const bool keep = sc > q[-1] && sc > q[1] && sc > q[-sstride - 1] && sc > q[-sstride] && sc > q[-sstride + 1] &&
+                      sc > q[sstride - 1] && sc > q[sstride] && sc > q[sstride + 1];
+    if (keep) atomicOr(&s_bits[(r - 1) * w32 + (x >> 5)], 1u << (x & 31));
+  }
+  __syncthreads();
+
+  // phase 4: raster-ordered emit.  Thread i owns a contiguous run of bitmap words.
+  {
+    const int nwords = nms_rows * w32;
+    const int wpt = (nwords + 255) >> 8;
+    const int wb = tid * wpt, we = min(wb + wpt, nwords);
+    int mine = 0;
+    for (int i = wb; i < we; ++i) mine += __popc(s_bits[i]);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int off = incl - mine, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < warp) off += s_wsum[k];
+      total += s_wsum[k];
+    }
+    uint32_t *out = staging + ((size_t)f * plan.total_bands + band) * plan.band_cap;
+    for (int i = wb; i < we; ++i) {
+      uint32_t bits = s_bits[i];
+      const int r = i / w32, xb = (i - r * w32) << 5;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int x = xb + b;
+        out[off++] = orb_pack(x, y0 + r, s_sc[(r + 1) * sstride + x]);
+      }
+    }
+    if (tid == 0) bandcnt[(size_t)f * plan.total_bands + band] = total;
+  }
+}
+
+// ---------------------------------------------------------------------------------- select
+// Restates feature_match.cpp:68-81: walking keypoints in order, a keypoint is kept iff fewer than
+// max_per_cell earlier keypoints fell into its 16x16 cell, and the walk stops right after the
+// (max_kpts+1)-th kept keypoint.  Equivalent closed form: kept0 = (rank in cell < max_per_cell),
+// kept = kept0 && (#kept0 before it) <= max_kpts.
+__global__ void __launch_bounds__(1024)
+k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *__restrict__ bandcnt,
+         uint32_t *__restrict__ cand, uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncell = plan.grid_rows * plan.grid_cols;
+  const int cap = plan.cand_cap, scap = plan.sel_cap;
+  int32_t *s_boff = reinterpret_cast<int32_t *>(smem);            // [total_bands + 1]
+  int32_t *s_cellcnt = s_boff + ORB_MAX_BANDS + 1;                // [ncell + 1]  start offsets after scan
+  int32_t *s_cursor = s_cellcnt + ncell + 1;                      // [ncell]
+  uint16_t *s_cell = reinterpret_cast<uint16_t *>(s_cursor + ncell);   // [cap] cell of candidate i
+  uint16_t *s_bucket = s_cell + scap;                             // [cap] candidate ids grouped by cell
+  uint8_t *s_keep = reinterpret_cast<uint8_t *>(s_bucket + scap);  // [cap]
+  __shared__ int s_lvl_off[MVO_MAX_LEVELS + 1];
+  __shared__ int s_warp[32];
+  __shared__ int s_overflow;
+
+  const int nb = plan.total_bands;
+  const int32_t *bc = bandcnt + (size_t)f * nb;
+  // exclusive scan of band counts (nb <= 1024): one element per thread
+  {
+    const int v = tid < nb ? bc[tid] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = incl - v;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    if (tid < nb) s_boff[tid] = off;
+    if (tid == nb - 1) s_boff[nb] = off + v;
+  }
+  __syncthreads();
+  const int n = s_boff[nb];
+  if (tid == 0) {
+    int ovf = 0;
+    for (int l = 0; l < plan.nlevels; ++l) {
+      const int b0 = plan.lv[l].band_first;
+      s_lvl_off[l] = s_boff[b0];
+      const int cnt = s_boff[b0 + plan.lv[l].nbands] - s_boff[b0];
+      meta[f].lvl_count[l] = cnt;
+      if (cnt > plan.lv[l].cap) ovf = 1;          // OpenCV would call retainBest -> host path
+    }
+    s_lvl_off[plan.nlevels] = n;
+    if (n > cap || n > scap) ovf = 1;
+    s_overflow = ovf;
+    meta[f].overflow = ovf;
+    meta[f].n_cand = n;
+    if (ovf) meta[f].n_sel = 0;
+  }
+  for (int i = tid; i <= ncell; i += 1024) s_cellcnt[i] = 0;
+  __syncthreads();
+  const bool ovf = s_overflow != 0;
+
+  // gather the band staging into the compact, level-major raster-ordered candidate array
+  uint32_t *cf = cand + (size_t)f * cap;
+  for (int b = warp; b < nb; b += 32) {
+    const int o = s_boff[b], c = s_boff[b + 1] - o;
+    const uint32_t *src = staging + ((size_t)f * nb + b) * plan.band_cap;
+    int l = 0;
+    while (l + 1 < plan.nlevels && b >= plan.lv[l + 1].band_first) ++l;
+    const float scale = plan.lv[l].scale;
+    for (int i = lane; i < c; i += 32) {
+      const uint32_t p = src[i];
+      if (o + i < cap) {
+        cf[o + i] = p;
+        if (!ovf) {
+          // feature_match.cpp:70: row = ((int)kpt.pt.y) / grid, col = ((int)kpt.pt.x) / grid
+          const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
+          const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
+          int row = ((int)fy) / plan.grid_size, col = ((int)fx) / plan.grid_size;
+          row = min(row, plan.grid_rows - 1);
+          col = min(col, plan.grid_cols - 1);
+          const int cell = row * plan.grid_cols + col;
+          s_cell[o + i] = (uint16_t)cell;
+          atomicAdd(&s_cellcnt[cell], 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (ovf) return;
+
+  // exclusive scan over cells (ncell <= 65535): chunked per thread
+  {
+    const int per = (ncell + 1023) >> 10;
+    const int b = tid * per, e = min(b + per, ncell);
+    int mine = 0;
+    for (int i = b; i < e; ++i) mine += s_cellcnt[i];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    for (int i = b; i < e; ++i) {
+      const int c = s_cellcnt[i];
+      s_cellcnt[i] = off;
+      s_cursor[i] = off;
+      off += c;
+    }
+    if (tid == 1023) s_cellcnt[ncell] = n;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) s_bucket[atomicAdd(&s_cursor[s_cell[i]], 1)] = (uint16_t)i;
+  __syncthreads();
+  // rank of candidate i inside its cell = number of smaller candidate ids in the same bucket
+  for (int i = tid; i < n; i += 1024) {
+    const int c = s_cell[i];
+    int rank = 0;
+    for (int k = s_cellcnt[c]; k < s_cellcnt[c + 1]; ++k) rank += (s_bucket[k] < i);
+    s_keep[i] = rank < plan.max_per_cell;
+  }
+  __syncthreads();
+  // ordered prefix count of kept0 (contiguous chunk per thread), cut after max_kpts + 1
+  {
+    const int per = (n + 1023) >> 10;
+    const int b = tid * per, e = min(b + per, n);
+    int mine = 0;
+    for (int i = b; i < e; ++i) mine += s_keep[i];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int pos = incl - mine, total = 0;
+    for (int k = 0; k < 32; ++k) {
+      if (k < warp) pos += s_warp[k];
+      total += s_warp[k];
+    }
+    uint2 *sf = sel + (size_t)f * (plan.max_kpts + 1);
+    for (int i = b; i < e; ++i) {
+      if (s_keep[i]) {
+        if (pos <= plan.max_kpts) {
+          int l = 0;
+          while (l + 1 < plan.nlevels && i >= s_lvl_off[l + 1]) ++l;
+          sf[pos] = make_uint2(cf[i], (uint32_t)l);
+        }
+        ++pos;
+      }
+    }
+    if (tid == 0) meta[f].n_sel = min(total, plan.max_kpts + 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------ blur
+// cv::GaussianBlur(7x7, 2, 2, BORDER_REFLECT_101) as ORB applies it to a pyramid level: float
+// separable filter, row pass taps in ascending order, symmetric column pass, saturate_cast<uchar>
+// (round half to even).  kernel = getGaussianKernel(7, 2, CV_32F).
+__constant__ float c_gauss7[7];
+
+constexpr int BLUR_TW = 128, BLUR_TH = 16;
+
+__global__ void __launch_bounds__(256)
+k_blur(OrbPlanDev plan, int level, uint8_t *__restrict__ planes) {
+  __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
+  __shared__ float s_row[BLUR_TH + 6][BLUR_TW + 1];
+  const OrbLevelDev &L = plan.lv[level];
+  const int f = blockIdx.z, tx0 = blockIdx.x * BLUR_TW, ty0 = blockIdx.y * BLUR_TH;
+  const int w = L.w, h = L.h;
+  const uint8_t *img = planes + (size_t)f * plan.slot_bytes + L.img_off;
+  uint8_t *out = planes + (size_t)f * plan.slot_bytes + L.blur_off;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+    const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+    int y = ty0 + r - 3, x = tx0 + c - 3;
+    y = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);        // BORDER_REFLECT_101
+    x = x < 0 ? -x : (x >= w ? 2 * w - 2 - x : x);
+    y = max(0, min(y, h - 1));
+    x = max(0, min(x, w - 1));
+    s_in[r][c] = img[(size_t)y * L.pitch + x];
+  }
+  __syncthreads();
+  for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+    const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+    float s = __fmul_rn(c_gauss7[0], (float)s_in[r][c]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) s = __fadd_rn(s, __fmul_rn(c_gauss7[k], (float)s_in[r][c + k]));
+    s_row[r][c] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+    const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
+    const int y = ty0 + r;
+    if (y >= h || tx0 + c4 >= L.pitch) continue;
+    uint32_t pk = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c4 + j;
+      float s = __fmul_rn(c_gauss7[3], s_row[r + 3][c]);
+#pragma unroll
+      for (int k = 1; k <= 3; ++k)
+        s = __fadd_rn(s, __fmul_rn(c_gauss7[3 + k], __fadd_rn(s_row[r + 3 + k][c], s_row[r + 3 - k][c])));
+      int v = __float2int_rn(s);
+      v = max(0, min(255, v));
+      pk |= (uint32_t)v << (8 * j);
+    }
+    *reinterpret_cast<uint32_t *>(out + (size_t)y * L.pitch + tx0 + c4) = pk;
+  }
+}
+
+// -------------------------------------------------------------------------------- describe
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// cv::fastAtan2 scalar path (degrees); every product/sum rounded separately, like the C++ build.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  // OpenCV: static const float atan2_p1 = 0.9997878412794807f*(float)(180/CV_PI); ... (float x float)
+  constexpr float r2d = (float)(180.0 / 3.1415926535897932384626433832795);
+  constexpr float p1 = 0.9997878412794807f * r2d, p3 = -0.3258083974640975f * r2d;
+  constexpr float p5 = 0.1555786518463281f * r2d, p7 = -0.04432655554792128f * r2d;
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  const float eps = 2.2204460492503131e-16f;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__device__ __forceinline__ float harris_warp(const uint8_t *__restrict__ img, int pitch, int x0, int y0, int lane) {
+  // OpenCV HarrisResponses: 7x7 block, Sobel-like 3x3 gradients, integer sums.
+  int a = 0, b = 0, c = 0;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int k = lane + 32 * rep;
+    if (k < 49) {
+      const int i = k / 7, j = k - 7 * i;
+      const uint8_t *p = img + (size_t)(y0 - 3 + i) * pitch + (x0 - 3 + j);
+      const int Ix = (p[1] - p[-1]) * 2 + (p[-pitch + 1] - p[-pitch - 1]) + (p[pitch + 1] - p[pitch - 1]);
+      const int Iy = (p[pitch] - p[-pitch]) * 2 + (p[pitch - 1] - p[-pitch - 1]) + (p[pitch + 1] - p[-pitch + 1]);
+      a += Ix * Ix;
+      b += Iy * Iy;
+      c += Ix * Iy;
+    }
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  c = warp_sum(c);
+  const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));            // 1.f/((1<<2)*7*255.f)
+  const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+  const float fa = (float)a, fb = (float)b, fc = (float)c;
+  const float ab = __fadd_rn(fa, fb);
+  return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, ab), ab)), s4);
+}
+
+__device__ __forceinline__ float ic_angle_warp(const uint8_t *__restrict__ img, int pitch, int x0, int y0, int lane) {
+  // intensity centroid over the radius-15 disc (umax table of OpenCV's ORB)
+  const int u = lane - ORB_HALF_PATCH;      // lanes 0..30 -> u = -15..15
+  const unsigned long long umax_lo = 0x0D0E0E0E0F0F0F0FULL;   // umax[0..7]  = 15,15,15,15,14,14,14,13
+  const unsigned long long umax_hi = 0x030608090A0B0C0DULL;   // umax[8..15] = 13,12,11,10,9,8,6,3
+  int m10 = 0, m01 = 0;
+  for (int v = -ORB_HALF_PATCH; v <= ORB_HALF_PATCH; ++v) {
+    const int av = v < 0 ? -v : v;
+    const int um = (int)(((av < 8 ? umax_lo >> (8 * av) : umax_hi >> (8 * (av - 8)))) & 0xFF);
+    if (lane < 31 && u >= -um && u <= um) {
+      const int val = img[(size_t)(y0 + v) * pitch + x0 + u];
+      m10 += u * val;
+      m01 += v * val;
+    }
+  }
+  m10 = warp_sum(m10);
+  m01 = warp_sum(m01);
+  return fast_atan2_deg((float)m01, (float)m10);
+}
+
+__device__ __forceinline__ uint32_t brief_byte(const uint8_t *__restrict__ blur, int pitch, int cx, int cy,
+                                               float angle_deg, int lane, const char2 *__restrict__ s_pat) {
+  // orb.cpp computeOrbDescriptors: angle *= (float)(CV_PI/180.f); a = (float)cos(angle), b = (float)sin(angle)
+  const float th = __fmul_rn(angle_deg, 0.017453292519943295f);
+  const float a = (float)cos((double)th), b = (float)sin((double)th);
+  const uint8_t *center = blur + (size_t)cy * pitch + cx;
+  uint32_t byte = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const char2 p0 = s_pat[(lane * 8 + j) * 2], p1 = s_pat[(lane * 8 + j) * 2 + 1];
+    const float x0 = __fsub_rn(__fmul_rn((float)p0.x, a), __fmul_rn((float)p0.y, b));
+    const float y0 = __fadd_rn(__fmul_rn((float)p0.x, b), __fmul_rn((float)p0.y, a));
+    const float x1 = __fsub_rn(__fmul_rn((float)p1.x, a), __fmul_rn((float)p1.y, b));
+    const float y1 = __fadd_rn(__fmul_rn((float)p1.x, b), __fmul_rn((float)p1.y, a));
+    const int t0 = center[__float2int_rn(y0) * pitch + __float2int_rn(x0)];
+    const int t1 = center[__float2int_rn(y1) * pitch + __float2int_rn(x1)];
+    byte |= (uint32_t)(t0 < t1) << j;
+  }
+  return byte;
+}
+
+constexpr int DESC_WARPS = 8;
+
+// MODE 0: keypoints from the selection list (level coordinates) -> mvo_keypoint (+ descriptor)
+// MODE 1: descriptors for caller-supplied keypoints
+template <int MODE>
+__global__ void __launch_bounds__(DESC_WARPS * 32)
+k_describe(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__restrict__ sel,
+           const OrbFrameMeta *__restrict__ meta, const int32_t *__restrict__ n_override,
+           const mvo_keypoint *__restrict__ kin, int n_in, mvo_keypoint *__restrict__ kout,
+           uint8_t *__restrict__ desc, int32_t *__restrict__ counts, int out_cap, int with_desc,
+           int32_t *__restrict__ bad_flag) {
+  __shared__ char2 s_pat[512];
+  const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_pat[i] = make_char2(kOrbPattern[i][0], kOrbPattern[i][1]);
+  __syncthreads();
+  int n;
+  if (MODE == 0) {
+    n = n_override ? n_override[f] : meta[f].n_sel;
+    n = min(n, out_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counts) counts[f] = n;
+  } else {
+    n = n_in;
+  }
+  const uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
+  for (int k = blockIdx.x * DESC_WARPS + warp; k < n; k += gridDim.x * DESC_WARPS) {
+    int l, x, y;
+    float angle;
+    if (MODE == 0) {
+      const uint2 s = sel[(size_t)f * (plan.max_kpts + 1) + k];
+      l = (int)s.y;
+      x = orb_px(s.x);
+      y = orb_py(s.x);
+      const OrbLevelDev &L = plan.lv[l];
+      const uint8_t *img = slot + L.img_off;
+      const float resp = harris_warp(img, L.pitch, x, y, lane);
+      angle = ic_angle_warp(img, L.pitch, x, y, lane);
+      if (lane == 0) {
+        mvo_keypoint kp;
+        kp.x = l ? __fmul_rn((float)x, L.scale) : (float)x;
+        kp.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+        kp.size = __fmul_rn(31.f, L.scale);
+        kp.angle = angle;
+        kp.response = resp;
+        kp.octave = l;
+        kp.class_id = -1;
+        kout[(size_t)f * out_cap + k] = kp;
+      }
+    } else {
+      const mvo_keypoint kp = kin[k];
+      l = kp.octave;
+      if (l < 0 || l >= plan.nlevels) {
+        if (lane == 0) atomicExch(bad_flag, 1);
+        continue;
+      }
+      const OrbLevelDev &L = plan.lv[l];
+      const float s = __fdiv_rn(1.f, L.scale);
+      x = __float2int_rn(__fmul_rn(kp.x, s));
+      y = __float2int_rn(__fmul_rn(kp.y, s));
+      angle = kp.angle;
+      // rotated samples reach at most round(13*sqrt(2)) = 19 px from the centre
+      if (x < 20 || y < 20 || x >= L.w - 20 || y >= L.h - 20) {
+        if (lane == 0) atomicExch(bad_flag, 2);
+        continue;
+      }
+    }
+    if (MODE == 1 || with_desc) {
+      const OrbLevelDev &L = plan.lv[l];
+      const uint32_t byte = brief_byte(slot + L.blur_off, L.pitch, x, y, angle, lane, s_pat);
+      desc[((size_t)f * (MODE == 0 ? out_cap : n_in) + k) * 32 + lane] = (uint8_t)byte;
+    }
+  }
+}
+
+// Harris response for every compact candidate (host retainBest path only).
+__global__ void __launch_bounds__(256)
+k_harris_all(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint32_t *__restrict__ cand,
+             const OrbFrameMeta *__restrict__ meta, float *__restrict__ harris) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min(meta[f].n_cand, plan.cand_cap);
+  const uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
+  for (int k = blockIdx.x * 8 + warp; k < n; k += gridDim.x * 8) {
+    int l = 0, acc = meta[f].lvl_count[0];
+    while (l + 1 < plan.nlevels && k >= acc) acc += meta[f].lvl_count[++l];
+    const uint32_t p = cand[(size_t)f * plan.cand_cap + k];
+    const float r = harris_warp(slot + plan.lv[l].img_off, plan.lv[l].pitch, orb_px(p), orb_py(p), lane);
+    if (lane == 0) harris[(size_t)f * plan.cand_cap + k] = r;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ launchers
+static bool g_gauss_uploaded[64] = {false};
+
+static int upload_gauss(mvo_ctx *ctx) {
+  if (ctx->device < 64 && g_gauss_uploaded[ctx->device]) return MVO_OK;
+  // cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2/(2 sigma^2)) normalised in double, stored as float
+  double k[7], s = 0;
+  for (int i = 0; i < 7; ++i) { const double x = i - 3; k[i] = exp(-x * x / 8.0); s += k[i]; }
+  float kf[7];
+  for (int i = 0; i < 7; ++i) kf[i] = (float)(k[i] / s);
+  MVO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gauss7, kf, sizeof kf, 0, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->device < 64) g_gauss_uploaded[ctx->device] = true;
+  return MVO_OK;
+}
+
+int orb_launch_gray(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, int channels, size_t stride,
+                    size_t frame_stride, uint8_t *planes, int batch) {
+  dim3 grid((plan.lv[0].pitch / 4 + 127) / 128, plan.rows, batch);
+  k_gray<<<grid, 128, 0, ctx->stream>>>(plan, d_in, channels, stride, frame_stride, planes);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_launch_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const int32_t *tables, uint8_t *planes, int batch) {
+  for (int l = 1; l < plan.nlevels; ++l) {
+    dim3 grid((plan.lv[l].pitch / 4 + 127) / 128, plan.lv[l].h, batch);
+    k_resize<<<grid, 128, 0, ctx->stream>>>(plan, l, tables, planes);
+    MVO_CHECK_LAUNCH(ctx);
+  }
+  return MVO_OK;
+}
+
+static size_t fast_smem_bytes(const OrbPlanDev &plan) {
+  size_t m = 0;
+  for (int l = 0; l < plan.nlevels; ++l) {
+    const size_t sstride = plan.lv[l].pitch + 16, w32 = (plan.lv[l].w + 31) / 32;
+    const size_t b = (ORB_BAND_H + 8) * sstride + (ORB_BAND_H + 2) * sstride + ORB_BAND_H * w32 * 4 +
+                     (size_t)(ORB_BAND_H + 2) * plan.lv[l].w * 2 + 64;
+    if (b > m) m = b;
+  }
+  return m;
+}
+
+int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, uint32_t *staging,
+                    int32_t *bandcnt, int batch) {
+  const size_t smem = fast_smem_bytes(plan);
+  if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "image too wide for the FAST band kernel");
+  if (smem > 48 * 1024)
+    MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(plan.total_bands, batch);
+  k_fast<<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *staging, const int32_t *bandcnt,
+                      uint32_t *cand, uint2 *sel, OrbFrameMeta *meta, int batch) {
+  const int ncell = plan.grid_rows * plan.grid_cols;
+  const size_t smem = (size_t)(ORB_MAX_BANDS + 1) * 4 + (size_t)(ncell + 1) * 4 + (size_t)ncell * 4 +
+                      (size_t)plan.sel_cap * 2 * 2 + plan.sel_cap + 64;
+  if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "selection grid too large");
+  if (smem > 48 * 1024)
+    MVO_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_select<<<batch, 1024, smem, ctx->stream>>>(plan, staging, bandcnt, cand, sel, meta);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int batch) {
+  MVO_TRY(upload_gauss(ctx));
+  for (int l = 0; l < plan.nlevels; ++l) {
+    dim3 grid((plan.lv[l].w + BLUR_TW - 1) / BLUR_TW, (plan.lv[l].h + BLUR_TH - 1) / BLUR_TH, batch);
+    k_blur<<<grid, 256, 0, ctx->stream>>>(plan, l, planes);
+    MVO_CHECK_LAUNCH(ctx);
+  }
+  return MVO_OK;
+}
+
+int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint32_t *cand,
+                          const OrbFrameMeta *meta, float *harris, int batch) {
+  dim3 grid(2 * ctx->sm_count, batch);
+  k_harris_all<<<grid, 256, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_launch_describe_sel(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint2 *sel,
+                            const OrbFrameMeta *meta, const int32_t *n_override, mvo_keypoint *kpts, uint8_t *desc,
+                            int32_t *counts, int out_cap, int with_desc, int batch) {
+  const int blocks = (plan.max_kpts + 1 + DESC_WARPS - 1) / DESC_WARPS;
+  dim3 grid(blocks < 1 ? 1 : blocks, batch);
+  k_describe<0><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, sel, meta, n_override, nullptr, 0, kpts,
+                                                           desc, counts, out_cap, with_desc, nullptr);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_launch_describe_kpts(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const mvo_keypoint *kpts,
+                             int n, uint8_t *desc, int32_t *bad_flag) {
+  if (n <= 0) return MVO_OK;
+  dim3 grid((n + DESC_WARPS - 1) / DESC_WARPS, 1);
+  k_describe<1><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, nullptr, nullptr, nullptr, kpts, n, nullptr,
+                                                           desc, nullptr, 0, 1, bad_flag);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}

@@ -3,11 +3,6 @@
 #include "mvo_internal.h"
 #define TODO(ctx, name) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, name ": not implemented yet")
 extern "C" {
-int mvo_calc_keypoints(mvo_ctx *ctx, const uint8_t *, int, int, int, size_t, mvo_keypoint *, int *) { TODO(ctx, "mvo_calc_keypoints"); }
-int mvo_calc_descriptors(mvo_ctx *ctx, const uint8_t *, int, int, int, size_t, const mvo_keypoint *, int, uint8_t *) { TODO(ctx, "mvo_calc_descriptors"); }
-int mvo_orb_extract(mvo_ctx *ctx, const uint8_t *, int, int, int, size_t, mvo_keypoint *, int *, uint8_t *) { TODO(ctx, "mvo_orb_extract"); }
-int mvo_select_uniform_kpts_by_grid(mvo_ctx *ctx, mvo_keypoint *, int *, int, int) { TODO(ctx, "mvo_select_uniform_kpts_by_grid"); }
-int mvo_orb_extract_batch_dev(mvo_ctx *ctx, const uint8_t *, int, int, int, int, size_t, size_t, mvo_keypoint *, uint8_t *, int32_t *, int) { TODO(ctx, "mvo_orb_extract_batch_dev"); }
 int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *, const float *, int, const double *, double *, double *, int32_t *, int *) { TODO(ctx, "mvo_solve_pnp_ransac"); }
 int mvo_pnp_last_hypotheses(mvo_ctx *ctx, double *, int32_t *, int, int *) { TODO(ctx, "mvo_pnp_last_hypotheses"); }
 int mvo_pnp_refine(mvo_ctx *ctx, const float *, const float *, int, const double *, double *, double *) { TODO(ctx, "mvo_pnp_refine"); }

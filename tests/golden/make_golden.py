@@ -30,6 +30,27 @@ def make_match():
                         cv_version=cv2.__version__)
 
 
+def make_orb():
+    """cv::ORB detect (feature_match.cpp:22-23,34) -> selectUniformKptsByGrid restatement -> compute (:45,48)."""
+    import cv2
+    import mvo_synth
+    from oracle import oracle_lib
+    scenes = {"rect0": mvo_synth.gray_to_bgr(mvo_synth.rect_scene(0)), "color1": mvo_synth.color_scene(1),
+              "noise0": mvo_synth.gray_to_bgr(mvo_synth.noise_scene(0))}
+    for name, img in scenes.items():
+        kps = cv2.ORB_create(8000, 1.2, 4, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20).detect(img, None)
+        det = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id) for k in kps],
+                       oracle_lib.KEYPOINT_DTYPE)
+        sel = oracle_lib.select_uniform_kpts_by_grid(det, img.shape[0], img.shape[1], 2000, 16, 8)
+        ck = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]),
+                           int(k["octave"]), int(k["class_id"])) for k in sel]
+        ck2, desc = cv2.ORB_create(8000, 1.2, 4).compute(img, ck)
+        assert len(ck2) == len(sel)
+        extra = {} if name == "noise0" else {"image": img}      # the noise image is regenerated from its seed
+        np.savez_compressed(OUT / f"orb_{name}.npz", detect=det, selected=sel, descriptors=desc,
+                            cv_version=cv2.__version__, **extra)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):

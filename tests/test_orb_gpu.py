@@ -1,0 +1,128 @@
+"""GPU parity of ORB extraction through the C ABI: keypoints (order, coordinates, angle, response)
+and descriptor bytes must be BIT-EXACT with OpenCV's cv::ORB + the reference's grid selection
+(reference src/geometry/feature_match.cpp:11-84).  Checked against cv2 live (when importable),
+the numpy oracle, and the committed golden vectors."""
+import numpy as np
+import pytest
+from conftest import GOLDEN, have_cv2
+
+import mvo_synth
+from oracle import oracle_lib, orb_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def _assert_kp_equal(got, ref):
+    assert len(got) == len(ref), (len(got), len(ref))
+    for f in FIELDS:
+        bad = np.nonzero(got[f] != ref[f])[0]
+        assert bad.size == 0, f"{f}: {bad.size} mismatches, first at {bad[:5]}: {got[f][bad[:5]]} vs {ref[f][bad[:5]]}"
+
+
+def _cv_reference(img, max_kpts):
+    import cv2
+    kps = cv2.ORB_create(8000, 1.2, 4, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20).detect(img, None)
+    det = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id) for k in kps], oo.KEYPOINT_DTYPE)
+    sel = oracle_lib.select_uniform_kpts_by_grid(det, img.shape[0], img.shape[1], max_kpts, 16, 8)
+    ck = [cv2.KeyPoint(float(k["x"]), float(k["y"]), float(k["size"]), float(k["angle"]), float(k["response"]),
+                       int(k["octave"]), int(k["class_id"])) for k in sel]
+    _, desc = cv2.ORB_create(8000, 1.2, 4).compute(img, ck)
+    return sel, desc
+
+
+SCENES = {
+    "rect0": lambda: mvo_synth.gray_to_bgr(mvo_synth.rect_scene(0)),
+    "rect1_gray": lambda: mvo_synth.rect_scene(1),                        # 1-channel input
+    "color1": lambda: mvo_synth.color_scene(1),                           # levels 0-1 above the Harris cap
+    "noise0": lambda: mvo_synth.gray_to_bgr(mvo_synth.noise_scene(0)),    # every level above 2x cap
+    "odd": lambda: mvo_synth.gray_to_bgr(mvo_synth.rect_scene(5, 517, 389)),
+    "flat": lambda: np.full((480, 640, 3), 77, np.uint8),                  # no corners at all
+    "sparse": lambda: mvo_synth.gray_to_bgr(mvo_synth.rect_scene(9, n_rect=12)),
+}
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("max_kpts", [2000, 1500])
+def test_extract_vs_cv2(ctx, name, max_kpts):
+    img = SCENES[name]()
+    ctx.set_params(max_keypoints=max_kpts)
+    ref_kp, ref_desc = _cv_reference(img, max_kpts)
+    kp, desc = ctx.orb_extract(img)
+    _assert_kp_equal(kp, ref_kp)
+    if len(ref_kp):
+        assert np.array_equal(desc, ref_desc), f"{int(np.any(desc != ref_desc, axis=1).sum())} descriptor rows differ"
+    # the two separate reference entry points give the same answers as the fused call
+    kp2 = ctx.calc_keypoints(img)
+    _assert_kp_equal(kp2, ref_kp)
+    if len(kp2):
+        assert np.array_equal(ctx.calc_descriptors(img, kp2), ref_desc)
+
+
+@pytest.mark.parametrize("name", ["rect0", "color1", "noise0"])
+def test_extract_vs_golden(ctx, name):
+    g = np.load(GOLDEN / f"orb_{name}.npz")
+    img = g["image"] if "image" in g else SCENES[name]()
+    ctx.set_params(max_keypoints=2000)
+    kp, desc = ctx.orb_extract(img)
+    _assert_kp_equal(kp, g["selected"])
+    assert np.array_equal(desc, g["descriptors"])
+
+
+def test_extract_vs_numpy_oracle(ctx):
+    img = mvo_synth.gray_to_bgr(mvo_synth.rect_scene(11))
+    ctx.set_params(max_keypoints=2000)
+    det = oo.detect(img)
+    sel = oracle_lib.select_uniform_kpts_by_grid(det, 480, 640, 2000, 16, 8)
+    kp, desc = ctx.orb_extract(img)
+    _assert_kp_equal(kp, sel)
+    assert np.array_equal(desc, oo.compute(img, sel))
+
+
+def test_grid_select_host_entry(ctx):
+    rng = np.random.default_rng(0)
+    import mvo_b200
+    kp = np.zeros(6000, mvo_b200.KEYPOINT_DTYPE)
+    kp["x"] = rng.uniform(31, 608, 6000)
+    kp["y"] = rng.uniform(31, 448, 6000)
+    ctx.set_params(max_keypoints=1500)
+    got = ctx.select_uniform_kpts_by_grid(kp, 480, 640)
+    ref = oracle_lib.select_uniform_kpts_by_grid(kp, 480, 640, 1500, 16, 8)
+    assert got.tobytes() == ref.tobytes() and len(got) == 1501     # the reference's off-by-one (feature_match.cpp:77)
+
+
+def test_batch_dev_matches_single(ctx):
+    import torch
+    ctx.set_params(max_keypoints=2000)
+    imgs = [mvo_synth.gray_to_bgr(mvo_synth.rect_scene(s)) for s in (0, 1, 2)] + [mvo_synth.color_scene(1)]
+    B, cap = len(imgs), 2001
+    d_img = torch.from_numpy(np.stack(imgs)).cuda()
+    d_kp = torch.zeros(B * cap * 28, dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros(B * cap * 32, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.orb_extract_batch_dev(d_img.data_ptr(), B, 480, 640, 3, 640 * 3, 480 * 640 * 3, d_kp.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap)
+    ctx.synchronize()
+    cnt = d_cnt.cpu().numpy()
+    import mvo_b200
+    kp_all = d_kp.cpu().numpy().view(mvo_b200.KEYPOINT_DTYPE).reshape(B, cap)
+    desc_all = d_desc.cpu().numpy().reshape(B, cap, 32)
+    for f, img in enumerate(imgs):
+        kp, desc = ctx.orb_extract(img)
+        assert cnt[f] == len(kp)
+        _assert_kp_equal(kp_all[f, : cnt[f]], kp)
+        assert np.array_equal(desc_all[f, : cnt[f]], desc)
+
+
+def test_errors(ctx):
+    import mvo_b200
+    with pytest.raises(mvo_b200.MvoError):
+        ctx.orb_extract(np.zeros((40, 40, 3), np.uint8))            # smaller than the ORB border
+    with pytest.raises(mvo_b200.MvoError):
+        ctx.orb_extract(np.zeros((480, 640, 2), np.uint8))          # bad channel count
+    kp = np.zeros(1, mvo_b200.KEYPOINT_DTYPE)
+    kp["x"], kp["y"], kp["octave"] = 5, 5, 0
+    with pytest.raises(mvo_b200.MvoError):
+        ctx.calc_descriptors(mvo_synth.rect_scene(0), kp)           # inside the border band
