@@ -1,0 +1,657 @@
+// Batched RANSAC PnP for sm_100a — replaces the inline cv::solvePnPRansac call at reference
+// src/vo/vo.cpp:318-320 (iterationsCount 100, reprojectionError 2.0, confidence 0.999,
+// useExtrinsicGuess false, default SOLVEPNP_ITERATIVE).  Structure kept from OpenCV (SURVEY.md
+// App. C): hypotheses from minimal sets -> consensus set of the best hypothesis (returned as
+// ascending indices) -> iterative least-squares refit on exactly those inliers.  What differs by
+// design: all H hypotheses (default 4096, not <=100 adaptive) are generated and scored in one
+// batch; the minimal solver is a P3P (3 points + 1 to disambiguate) instead of 5-point EPnP.
+//
+//   k_pnp_hypotheses  one thread per hypothesis: counter-based sampling (splitmix64), P3P by
+//                     intersecting the two distance-ratio conics through their degenerate
+//                     pencil member, pose from the three depths, 4th point picks the root.
+//   k_pnp_score       persistent grid, one warp per hypothesis at a time, the N correspondences
+//                     staged once per CTA in shared memory; fp64 reprojection, count(err^2<=thr^2).
+//   k_pnp_finish      one CTA: arg-max (ties -> lowest hypothesis), ordered inlier compaction,
+//                     damped Gauss-Newton on SE(3) over the inliers (fp64).
+// All arithmetic fp64: the stage is latency-bound (N*H = 8.2e6 reprojections), not FLOP-bound.
+#include <string.h>
+#include "mvo_internal.h"
+
+namespace {
+
+struct PnpCam { double fx, fy, cx, cy; };
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ V3 unit(V3 a) { return rsqrt(dot(a, a)) * a; }
+
+// symmetric 3x3 stored as m00 m01 m02 m11 m12 m22
+struct S3 { double a, b, c, d, e, f; };
+__device__ __forceinline__ S3 adj(const S3 &m) {   // adjugate (also symmetric)
+  S3 r;
+  r.a = m.d * m.f - m.e * m.e;
+  r.b = m.c * m.e - m.b * m.f;
+  r.c = m.b * m.e - m.c * m.d;
+  r.d = m.a * m.f - m.c * m.c;
+  r.e = m.b * m.c - m.a * m.e;
+  r.f = m.a * m.d - m.b * m.b;
+  return r;
+}
+__device__ __forceinline__ double det(const S3 &m) {
+  return m.a * (m.d * m.f - m.e * m.e) - m.b * (m.b * m.f - m.c * m.e) + m.c * (m.b * m.e - m.c * m.d);
+}
+__device__ __forceinline__ double trprod(const S3 &p, const S3 &q) {   // trace(P Q)
+  return p.a * q.a + p.d * q.d + p.f * q.f + 2.0 * (p.b * q.b + p.c * q.c + p.e * q.e);
+}
+
+// real roots of c3 x^3 + c2 x^2 + c1 x + c0; returns count (1..3), Newton-polished
+__device__ int cubic_roots(double c3, double c2, double c1, double c0, double *r) {
+  int n = 0;
+  const double scale = fabs(c3) + fabs(c2) + fabs(c1) + fabs(c0);
+  if (!(scale > 0)) return 0;
+  if (fabs(c3) < 1e-14 * scale) {            // quadratic / linear
+    if (fabs(c2) < 1e-14 * scale) {
+      if (fabs(c1) < 1e-14 * scale) return 0;
+      r[0] = -c0 / c1;
+      return 1;
+    }
+    const double disc = c1 * c1 - 4 * c2 * c0;
+    if (disc < 0) return 0;
+    const double q = -0.5 * (c1 + copysign(sqrt(disc), c1));
+    r[n++] = q / c2;
+    if (q != 0) r[n++] = c0 / q;
+    return n;
+  }
+  const double a = c2 / c3, b = c1 / c3, c = c0 / c3;
+  const double Q = (a * a - 3 * b) / 9, R = (2 * a * a * a - 9 * a * b + 27 * c) / 54;
+  if (R * R < Q * Q * Q) {
+    const double th = acos(fmax(-1.0, fmin(1.0, R / sqrt(Q * Q * Q)))), sq = -2 * sqrt(Q);
+    r[0] = sq * cos(th / 3) - a / 3;
+    r[1] = sq * cos((th + 6.283185307179586) / 3) - a / 3;
+    r[2] = sq * cos((th - 6.283185307179586) / 3) - a / 3;
+    n = 3;
+  } else {
+    const double A = -copysign(cbrt(fabs(R) + sqrt(fmax(R * R - Q * Q * Q, 0.0))), R);
+    const double B = A != 0 ? Q / A : 0;
+    r[0] = A + B - a / 3;
+    n = 1;
+  }
+  for (int i = 0; i < n; ++i) {
+    double x = r[i];
+    for (int it = 0; it < 3; ++it) {
+      const double fx = ((c3 * x + c2) * x + c1) * x + c0, dfx = (3 * c3 * x + 2 * c2) * x + c1;
+      if (dfx != 0) x -= fx / dfx;
+    }
+    r[i] = x;
+  }
+  return n;
+}
+
+struct Pose { double R[9]; double t[3]; };
+
+__device__ __forceinline__ double reproj_err2(const Pose &P, const PnpCam &cam, V3 X, double u, double v) {
+  const double x = P.R[0] * X.x + P.R[1] * X.y + P.R[2] * X.z + P.t[0];
+  const double y = P.R[3] * X.x + P.R[4] * X.y + P.R[5] * X.z + P.t[1];
+  const double z = P.R[6] * X.x + P.R[7] * X.y + P.R[8] * X.z + P.t[2];
+  if (!(z > 1e-9)) return 1e300;       // behind the camera never counts as an inlier
+  const double iz = 1.0 / z;
+  const double du = cam.fx * x * iz + cam.cx - u, dv = cam.fy * y * iz + cam.cy - v;
+  return du * du + dv * dv;
+}
+
+// P3P: up to 4 poses mapping world X[0..2] onto unit bearings f[0..2]
+__device__ int p3p(const V3 *X, const V3 *f, Pose *out) {
+  const double a = dot(X[1] - X[2], X[1] - X[2]), b = dot(X[0] - X[2], X[0] - X[2]), c = dot(X[0] - X[1], X[0] - X[1]);
+  const double ca = dot(f[1], f[2]), cb = dot(f[0], f[2]), cg = dot(f[0], f[1]);
+  if (!(a > 1e-18 && b > 1e-18 && c > 1e-18)) return 0;
+  // conics in (u, v, 1) with u = s2/s1, v = s3/s1 (depth ratios):
+  //   C1: b(u^2 + v^2 - 2uv ca) - a(1 + v^2 - 2v cb) = 0
+  //   C2: b(1 + u^2 - 2u cg)    - c(1 + v^2 - 2v cb) = 0
+  S3 C1, C2;
+  C1.a = b;  C1.b = -b * ca; C1.c = 0;       C1.d = b - a; C1.e = a * cb; C1.f = -a;
+  C2.a = b;  C2.b = 0;       C2.c = -b * cg; C2.d = -c;    C2.e = c * cb; C2.f = b - c;
+  const S3 A1 = adj(C1), A2 = adj(C2);
+  double roots[3];
+  const int nr = cubic_roots(det(C2), trprod(C1, A2), trprod(A1, C2), det(C1), roots);
+  // pick the pencil member that is the best-conditioned REAL line pair
+  S3 D, AD;
+  double best = 0;
+  int bi = -1;
+  for (int i = 0; i < nr; ++i) {
+    const double g = roots[i];
+    S3 Di;
+    Di.a = C1.a + g * C2.a; Di.b = C1.b + g * C2.b; Di.c = C1.c + g * C2.c;
+    Di.d = C1.d + g * C2.d; Di.e = C1.e + g * C2.e; Di.f = C1.f + g * C2.f;
+    const S3 Ai = adj(Di);
+    const double nrm = fabs(Di.a) + fabs(Di.b) + fabs(Di.c) + fabs(Di.d) + fabs(Di.e) + fabs(Di.f);
+    const double m = fmax(fmax(-Ai.a, -Ai.d), -Ai.f) / (nrm * nrm + 1e-300);
+    if (m > best) { best = m; bi = i; D = Di; AD = Ai; }
+  }
+  if (bi < 0) return 0;
+  // p = l x m from adj(D) = -(p p^T)
+  double p0, p1, p2;
+  if (-AD.a >= -AD.d && -AD.a >= -AD.f) { const double s = sqrt(-AD.a); p0 = -AD.a / s; p1 = -AD.b / s; p2 = -AD.c / s; }
+  else if (-AD.d >= -AD.f)              { const double s = sqrt(-AD.d); p0 = -AD.b / s; p1 = -AD.d / s; p2 = -AD.e / s; }
+  else                                   { const double s = sqrt(-AD.f); p0 = -AD.c / s; p1 = -AD.e / s; p2 = -AD.f / s; }
+  // N = D + [p]_x = 2 m l^T : rows are multiples of one line, columns of the other
+  const double N[3][3] = {{D.a, D.b - p2, D.c + p1}, {D.b + p2, D.d, D.e - p0}, {D.c - p1, D.e + p0, D.f}};
+  int ri = 0, cj = 0;
+  double bm = -1;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      if (fabs(N[i][j]) > bm) { bm = fabs(N[i][j]); ri = i; cj = j; }
+  if (!(bm > 0)) return 0;
+  const double lines[2][3] = {{N[ri][0], N[ri][1], N[ri][2]}, {N[0][cj], N[1][cj], N[2][cj]}};
+  int ns = 0;
+  for (int li = 0; li < 2; ++li) {
+    const double L0 = lines[li][0], L1 = lines[li][1], L2 = lines[li][2];
+    const bool solve_v = fabs(L0) >= fabs(L1);      // u = al*v + be   (else v = al*u + be)
+    const double den = solve_v ? L0 : L1;
+    if (!(fabs(den) > 0)) continue;
+    const double al = -(solve_v ? L1 : L0) / den, be = -L2 / den;
+    // substitute into C2
+    double q2, q1, q0;
+    if (solve_v) {
+      q2 = C2.a * al * al + 2 * C2.b * al + C2.d;
+      q1 = 2 * (C2.a * al * be + C2.b * be + C2.c * al + C2.e);
+      q0 = C2.a * be * be + 2 * C2.c * be + C2.f;
+    } else {
+      q2 = C2.d * al * al + 2 * C2.b * al + C2.a;
+      q1 = 2 * (C2.d * al * be + C2.b * be + C2.e * al + C2.c);
+      q0 = C2.d * be * be + 2 * C2.e * be + C2.f;
+    }
+    double w[2];
+    int nw = 0;
+    if (fabs(q2) < 1e-14 * (fabs(q1) + fabs(q0))) { if (q1 != 0) w[nw++] = -q0 / q1; }
+    else {
+      const double disc = q1 * q1 - 4 * q2 * q0;
+      if (disc >= 0) {
+        const double q = -0.5 * (q1 + copysign(sqrt(disc), q1));
+        w[nw++] = q / q2;
+        if (q != 0) w[nw++] = q0 / q;
+      }
+    }
+    for (int k = 0; k < nw && ns < 4; ++k) {
+      const double u = solve_v ? al * w[k] + be : w[k];
+      const double v = solve_v ? w[k] : al * w[k] + be;
+      if (!(u > 0 && v > 0)) continue;
+      const double dn = 1 + v * v - 2 * v * cb;
+      if (!(dn > 1e-18)) continue;
+      const double s1 = sqrt(b / dn), s2 = u * s1, s3 = v * s1;
+      const V3 P1 = s1 * f[0], P2 = s2 * f[1], P3 = s3 * f[2];
+      // rigid transform from the two orthonormal triads
+      const V3 e1 = unit(X[1] - X[0]), e3 = unit(cross(e1, X[2] - X[0])), e2 = cross(e3, e1);
+      const V3 g1 = unit(P2 - P1), g3 = unit(cross(g1, P3 - P1)), g2 = cross(g3, g1);
+      Pose &T = out[ns];
+      T.R[0] = g1.x * e1.x + g2.x * e2.x + g3.x * e3.x; T.R[1] = g1.x * e1.y + g2.x * e2.y + g3.x * e3.y; T.R[2] = g1.x * e1.z + g2.x * e2.z + g3.x * e3.z;
+      T.R[3] = g1.y * e1.x + g2.y * e2.x + g3.y * e3.x; T.R[4] = g1.y * e1.y + g2.y * e2.y + g3.y * e3.y; T.R[5] = g1.y * e1.z + g2.y * e2.z + g3.y * e3.z;
+      T.R[6] = g1.z * e1.x + g2.z * e2.x + g3.z * e3.x; T.R[7] = g1.z * e1.y + g2.z * e2.y + g3.z * e3.y; T.R[8] = g1.z * e1.z + g2.z * e2.z + g3.z * e3.z;
+      T.t[0] = P1.x - (T.R[0] * X[0].x + T.R[1] * X[0].y + T.R[2] * X[0].z);
+      T.t[1] = P1.y - (T.R[3] * X[0].x + T.R[4] * X[0].y + T.R[5] * X[0].z);
+      T.t[2] = P1.z - (T.R[6] * X[0].x + T.R[7] * X[0].y + T.R[8] * X[0].z);
+      bool ok = true;
+      for (int q = 0; q < 9; ++q) ok = ok && isfinite(T.R[q]);
+      for (int q = 0; q < 3; ++q) ok = ok && isfinite(T.t[q]);
+      if (ok) ++ns;
+    }
+  }
+  return ns;
+}
+
+__global__ void __launch_bounds__(128)
+k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, uint64_t seed,
+                 int H, double *__restrict__ poses, int32_t *__restrict__ valid) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  int idx[4];
+  uint64_t ctr = 0;
+  for (int k = 0; k < 4; ++k) {
+    for (int attempt = 0; attempt < 64; ++attempt) {
+      const uint64_t r = splitmix64(seed ^ splitmix64(((uint64_t)h << 20) ^ ctr++));
+      int cand = (int)(r % (uint64_t)n);
+      bool dup = false;
+      for (int q = 0; q < k; ++q) dup |= idx[q] == cand;
+      idx[k] = cand;
+      if (!dup) break;
+    }
+  }
+  V3 X[4], f[3];
+  double u4 = 0, v4 = 0;
+  for (int k = 0; k < 4; ++k) {
+    X[k] = v3(p3[3 * idx[k]], p3[3 * idx[k] + 1], p3[3 * idx[k] + 2]);
+    const double u = p2[2 * idx[k]], v = p2[2 * idx[k] + 1];
+    if (k < 3) f[k] = unit(v3((u - cam.cx) / cam.fx, (v - cam.cy) / cam.fy, 1.0));
+    else { u4 = u; v4 = v; }
+  }
+  Pose sol[4];
+  const int ns = p3p(X, f, sol);
+  int bi = -1;
+  double be = 1e300;
+  for (int s = 0; s < ns; ++s) {
+    // all three sample points must be in front of the camera and reproject onto themselves
+    const double e4 = reproj_err2(sol[s], cam, X[3], u4, v4);
+    if (e4 < be) { be = e4; bi = s; }
+  }
+  double *o = poses + (size_t)h * 12;
+  if (bi >= 0 && be < 1e299) {
+    for (int q = 0; q < 9; ++q) o[q] = sol[bi].R[q];
+    for (int q = 0; q < 3; ++q) o[9 + q] = sol[bi].t[q];
+    valid[h] = 1;
+  } else {
+    for (int q = 0; q < 12; ++q) o[q] = 0;
+    valid[h] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, double thr2, int H,
+            const double *__restrict__ poses, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
+  extern __shared__ float s_pts[];      // [n][5]: X Y Z u v
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s_pts[5 * i] = p3[3 * i]; s_pts[5 * i + 1] = p3[3 * i + 1]; s_pts[5 * i + 2] = p3[3 * i + 2];
+    s_pts[5 * i + 3] = p2[2 * i]; s_pts[5 * i + 4] = p2[2 * i + 1];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int h = blockIdx.x * wpb + warp; h < H; h += gridDim.x * wpb) {
+    if (!valid[h]) { if (lane == 0) counts[h] = -1; continue; }
+    Pose P;
+    const double *o = poses + (size_t)h * 12;
+    for (int q = 0; q < 9; ++q) P.R[q] = o[q];
+    for (int q = 0; q < 3; ++q) P.t[q] = o[9 + q];
+    int c = 0;
+    for (int i = lane; i < n; i += 32) {
+      const float *s = s_pts + 5 * i;
+      c += reproj_err2(P, cam, v3(s[0], s[1], s[2]), s[3], s[4]) <= thr2;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) counts[h] = c;
+  }
+}
+
+// ---- refinement helpers (one CTA) -------------------------------------------------------
+__device__ __forceinline__ void rot_exp(const double *w, double *R) {   // Rodrigues
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+  double A, B;
+  if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
+  else { A = sin(th) / th; B = (1 - cos(th)) / th2; }
+  const double wx = w[0], wy = w[1], wz = w[2];
+  R[0] = 1 - B * (wy * wy + wz * wz); R[1] = -A * wz + B * wx * wy;       R[2] = A * wy + B * wx * wz;
+  R[3] = A * wz + B * wx * wy;        R[4] = 1 - B * (wx * wx + wz * wz); R[5] = -A * wx + B * wy * wz;
+  R[6] = -A * wy + B * wx * wz;       R[7] = A * wx + B * wy * wz;        R[8] = 1 - B * (wx * wx + wy * wy);
+}
+
+// 6x6 SPD solve by Cholesky (in place on the lower triangle of a 6x6 row-major copy)
+__device__ bool solve6(const double *Hm, const double *g, double lambda, double *x) {
+  double L[36];
+  for (int i = 0; i < 36; ++i) L[i] = Hm[i];
+  for (int i = 0; i < 6; ++i) L[i * 6 + i] += lambda * fmax(Hm[i * 6 + i], 1e-12);
+  for (int j = 0; j < 6; ++j) {
+    double d = L[j * 6 + j];
+    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+    if (!(d > 0)) return false;
+    d = sqrt(d);
+    L[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double s = L[i * 6 + j];
+      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+      L[i * 6 + j] = s / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = g[i];
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
+    y[i] = s / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
+    x[i] = s / L[i * 6 + i];
+  }
+  return true;
+}
+
+constexpr int FIN_T = 1024;
+
+// block-wide sum of NV doubles per thread -> result in s_out[0..NV) (valid for all threads after return)
+template <int NV>
+__device__ void block_sum(double *v, double *s_red /* [32][NV] */, double *s_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) s_red[warp * NV + k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < FIN_T / 32; ++w) s += s_red[w * NV + threadIdx.x];
+    s_out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// out: [0..8] R, [9..11] t, then int32 n_inliers at out_i[0], best hypothesis at out_i[1],
+// iterations at out_i[2]; inlier indices in inl[].  mode 0: full finish; mode 1: refine only
+// (all n points are inliers, pose_io holds the start pose).
+__global__ void __launch_bounds__(FIN_T)
+k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, double thr2, int H,
+             const double *__restrict__ poses, const int32_t *__restrict__ counts, int mode, int max_iters,
+             double *__restrict__ pose_io, int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
+  __shared__ double s_red[32 * 28];
+  __shared__ double s_sum[28];
+  __shared__ double s_pose[12], s_try[12], s_delta[6];
+  __shared__ int s_best, s_cnt[32], s_state;
+  __shared__ double s_lambda;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n_in = 0;
+  if (mode == 0) {
+    // arg-max of the inlier count, ties -> lowest hypothesis index
+    long long best = -1;
+    for (int h = tid; h < H; h += FIN_T) {
+      const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
+      best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
+    long long *s_k = reinterpret_cast<long long *>(s_red);
+    if (lane == 0) s_k[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      long long b = -1;
+      for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
+      const int cnt = (int)(b >> 20);
+      s_best = cnt >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
+    }
+    __syncthreads();
+    if (s_best < 0) {
+      if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
+      return;
+    }
+    if (tid < 12) s_pose[tid] = poses[(size_t)s_best * 12 + tid];
+    __syncthreads();
+    // ordered compaction of the consensus set (contiguous chunk per thread)
+    Pose P;
+    for (int q = 0; q < 9; ++q) P.R[q] = s_pose[q];
+    for (int q = 0; q < 3; ++q) P.t[q] = s_pose[9 + q];
+    const int per = (n + FIN_T - 1) / FIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+    int mine = 0;
+    for (int i = b0; i < e0; ++i)
+      mine += reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_cnt[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+    for (int i = b0; i < e0; ++i)
+      if (reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2) inl[off++] = i;
+    __syncthreads();     // inl[] visible to the whole block (global memory, same CTA)
+  } else {
+    n_in = n;
+    if (tid < 12) s_pose[tid] = pose_io[tid];
+    __syncthreads();
+  }
+
+  // damped Gauss-Newton on SE(3), left-multiplicative update T <- exp(delta) T, delta = (w, v)
+  if (tid == 0) { s_lambda = 1e-4; s_state = 0; }
+  __syncthreads();
+  double cost_cur = -1;
+  int it = 0;
+  for (; it < max_iters; ++it) {
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0;
+    for (int j = tid; j < n_in; j += FIN_T) {
+      const int i = mode == 0 ? inl[j] : j;
+      const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
+      const double x = s_pose[0] * X + s_pose[1] * Y + s_pose[2] * Z + s_pose[9];
+      const double y = s_pose[3] * X + s_pose[4] * Y + s_pose[5] * Z + s_pose[10];
+      const double z = s_pose[6] * X + s_pose[7] * Y + s_pose[8] * Z + s_pose[11];
+      const double iz = 1.0 / z;
+      const double ru = cam.fx * x * iz + cam.cx - p2[2 * i], rv = cam.fy * y * iz + cam.cy - p2[2 * i + 1];
+      // d(proj)/d(delta) for p' = p + w x p + v
+      const double a = cam.fx * iz, bq = cam.fy * iz, xz = x * iz, yz = y * iz;
+      const double Ju[6] = {-a * xz * y, a * (z + x * xz), -a * y, a, 0, -a * xz};
+      const double Jv[6] = {-bq * (z + y * yz), bq * yz * x, bq * x, 0, bq, -bq * yz};
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) acc[q++] += Ju[r] * Ju[c] + Jv[r] * Jv[c];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[21 + r] += Ju[r] * ru + Jv[r] * rv;
+      acc[27] += ru * ru + rv * rv;
+    }
+    block_sum<28>(acc, s_red, s_sum);
+    cost_cur = s_sum[27];
+    // try steps with increasing damping until the cost goes down
+    bool accepted = false;
+    for (int trial = 0; trial < 8 && !accepted; ++trial) {
+      if (tid == 0) {
+        double Hm[36], g[6];
+        int q = 0;
+        for (int r = 0; r < 6; ++r)
+          for (int c = r; c < 6; ++c) { Hm[r * 6 + c] = s_sum[q]; Hm[c * 6 + r] = s_sum[q]; ++q; }
+        for (int r = 0; r < 6; ++r) g[r] = -s_sum[21 + r];
+        double d[6];
+        if (solve6(Hm, g, s_lambda, d)) {
+          double Rw[9];
+          rot_exp(d, Rw);
+          for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c)
+              s_try[r * 3 + c] = Rw[r * 3] * s_pose[c] + Rw[r * 3 + 1] * s_pose[3 + c] + Rw[r * 3 + 2] * s_pose[6 + c];
+            s_try[9 + r] = Rw[r * 3] * s_pose[9] + Rw[r * 3 + 1] * s_pose[10] + Rw[r * 3 + 2] * s_pose[11] + d[3 + r];
+          }
+          for (int r = 0; r < 6; ++r) s_delta[r] = d[r];
+          s_state = 1;
+        } else {
+          s_state = 0;
+        }
+      }
+      __syncthreads();
+      if (s_state == 0) {               // singular even with damping: raise lambda
+        if (tid == 0) s_lambda *= 10;
+        __syncthreads();
+        continue;
+      }
+      double c1[1] = {0};
+      for (int j = tid; j < n_in; j += FIN_T) {
+        const int i = mode == 0 ? inl[j] : j;
+        const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
+        const double x = s_try[0] * X + s_try[1] * Y + s_try[2] * Z + s_try[9];
+        const double y = s_try[3] * X + s_try[4] * Y + s_try[5] * Z + s_try[10];
+        const double z = s_try[6] * X + s_try[7] * Y + s_try[8] * Z + s_try[11];
+        const double iz = 1.0 / z;
+        const double ru = cam.fx * x * iz + cam.cx - p2[2 * i], rv = cam.fy * y * iz + cam.cy - p2[2 * i + 1];
+        c1[0] += ru * ru + rv * rv;
+      }
+      block_sum<1>(c1, s_red, s_sum + 27);     // keeps s_sum[0..26] (H, g) intact for re-damping
+      const double cost_new = s_sum[27];
+      if (cost_new <= cost_cur) {
+        accepted = true;
+        __syncthreads();
+        if (tid < 12) s_pose[tid] = s_try[tid];
+        if (tid == 0) s_lambda = fmax(s_lambda * 0.1, 1e-15);
+      } else {
+        if (tid == 0) s_lambda *= 10;
+      }
+      __syncthreads();
+    }
+    if (!accepted) break;
+    const double dn = fabs(s_delta[0]) + fabs(s_delta[1]) + fabs(s_delta[2]) + fabs(s_delta[3]) + fabs(s_delta[4]) + fabs(s_delta[5]);
+    if (dn < 1e-13) { ++it; break; }
+  }
+  if (tid < 12) pose_io[tid] = s_pose[tid];
+  if (tid == 0) { out_i[0] = n_in; out_i[1] = mode == 0 ? s_best : -1; out_i[2] = it; }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------- host entry
+static void rotation_to_rvec(const double *R, double *rvec) {
+  // via the unit quaternion: robust for every angle in [0, pi]
+  double q[4];
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) { double s = sqrt(tr + 1.0) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+  if (q[0] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double vn = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (vn < 1e-15) { rvec[0] = rvec[1] = rvec[2] = 0; return; }
+  const double th = 2 * atan2(vn, q[0]);
+  for (int i = 0; i < 3; ++i) rvec[i] = th * q[1 + i] / vn;
+}
+
+static void rvec_to_rotation(const double *w, double *R) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+  double A, B;
+  if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
+  else { A = sin(th) / th; B = (1 - cos(th)) / th2; }
+  const double wx = w[0], wy = w[1], wz = w[2];
+  R[0] = 1 - B * (wy * wy + wz * wz); R[1] = -A * wz + B * wx * wy;       R[2] = A * wy + B * wx * wz;
+  R[3] = A * wz + B * wx * wy;        R[4] = 1 - B * (wx * wx + wz * wz); R[5] = -A * wx + B * wy * wz;
+  R[6] = -A * wy + B * wx * wz;       R[7] = A * wx + B * wy * wz;        R[8] = 1 - B * (wx * wx + wy * wy);
+}
+
+struct PnpWs { float *p3, *p2; double *poses, *pose_io; int32_t *valid, *counts, *out_i, *inl; };
+
+static int pnp_ws(mvo_ctx *ctx, int n, int H, PnpWs *w) {
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_p3 = 0, o_p2 = al(o_p3 + (size_t)n * 12), o_inl = al(o_p2 + (size_t)n * 8), o_end = al(o_inl + (size_t)n * 4);
+  MVO_TRY(mvo_reserve(ctx, ctx->pnp_pts, o_end));
+  MVO_TRY(mvo_reserve(ctx, ctx->pnp_hyp, (size_t)H * 12 * 8 + 256));
+  MVO_TRY(mvo_reserve(ctx, ctx->pnp_cnt, (size_t)H * 8 + 512));
+  MVO_TRY(mvo_reserve(ctx, ctx->pnp_out, 1024));
+  uint8_t *b = (uint8_t *)ctx->pnp_pts.p;
+  w->p3 = (float *)(b + o_p3); w->p2 = (float *)(b + o_p2); w->inl = (int32_t *)(b + o_inl);
+  w->poses = (double *)ctx->pnp_hyp.p;
+  w->valid = (int32_t *)ctx->pnp_cnt.p;
+  w->counts = w->valid + ((H + 63) & ~63);
+  w->pose_io = (double *)ctx->pnp_out.p;
+  w->out_i = (int32_t *)((uint8_t *)ctx->pnp_out.p + 256);
+  return MVO_OK;
+}
+
+static int pnp_cam(mvo_ctx *ctx, const double *K, PnpCam *cam) {
+  if (!K) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null K");
+  cam->fx = K[0]; cam->fy = K[4]; cam->cx = K[2]; cam->cy = K[5];
+  if (!(cam->fx > 0 && cam->fy > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "K: focal lengths must be positive");
+  return MVO_OK;
+}
+
+extern "C" {
+
+int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, const double *K,
+                         double *rvec, double *tvec, int32_t *inliers, int *n_inliers) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!pts3d || !pts2d || !rvec || !tvec || !n_inliers || (*n_inliers > 0 && !inliers))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "solvePnPRansac: null pointer");
+  if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: %d correspondences (< 4)", n);
+  PnpCam cam;
+  MVO_TRY(pnp_cam(ctx, K, &cam));
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int H = ctx->prm.pnp_hypotheses;
+  PnpWs w;
+  MVO_TRY(pnp_ws(ctx, n, H, &w));
+  const size_t smem = (size_t)n * 5 * sizeof(float);
+  if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
+  const size_t hb = (size_t)n * 20 + (size_t)n * 4 + 1024;
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, hb));
+  float *h3 = (float *)ctx->h_b.p, *h2 = h3 + (size_t)n * 3;
+  memcpy(h3, pts3d, (size_t)n * 12);
+  memcpy(h2, pts2d, (size_t)n * 8);
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
+  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, cam, ctx->prm.pnp_seed, H, w.poses, w.valid);
+  MVO_CHECK_LAUNCH(ctx);
+  if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pnp_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (H + 7) / 8;
+  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.valid, w.counts);
+  MVO_CHECK_LAUNCH(ctx);
+  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
+                                             w.pose_io, w.out_i, w.inl);
+  MVO_CHECK_LAUNCH(ctx);
+  ctx->pnp_last_h = H;
+  uint8_t *hout = (uint8_t *)ctx->h_b.p + (size_t)n * 20;
+  double *h_pose = (double *)hout;
+  int32_t *h_i = (int32_t *)(hout + 128), *h_inl = (int32_t *)(hout + 256);
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_i, w.out_i, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, w.inl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int ni = h_i[0];
+  if (ni < 4) { *n_inliers = 0; return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: no hypothesis reached 4 inliers"); }
+  if (ni > *n_inliers) return mvo_fail(ctx, MVO_ERR_CAPACITY, "inlier capacity %d < %d", *n_inliers, ni);
+  rotation_to_rvec(h_pose, rvec);
+  tvec[0] = h_pose[9]; tvec[1] = h_pose[10]; tvec[2] = h_pose[11];
+  memcpy(inliers, h_inl, (size_t)ni * 4);
+  *n_inliers = ni;
+  return MVO_OK;
+}
+
+int mvo_pnp_last_hypotheses(mvo_ctx *ctx, double *poses, int32_t *counts, int cap, int *n_hyp) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!poses || !counts || !n_hyp) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null pointer");
+  const int H = ctx->pnp_last_h;
+  if (H <= 0) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "no PnP call yet");
+  if (cap < H) return mvo_fail(ctx, MVO_ERR_CAPACITY, "capacity %d < %d", cap, H);
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int32_t *d_counts = (int32_t *)ctx->pnp_cnt.p + ((H + 63) & ~63);
+  MVO_CUDA(ctx, cudaMemcpyAsync(poses, ctx->pnp_hyp.p, (size_t)H * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_hyp = H;
+  return MVO_OK;
+}
+
+int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, const double *K, double *rvec,
+                   double *tvec) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!pts3d || !pts2d || !rvec || !tvec) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_refine: null pointer");
+  if (n < 3) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "pnp_refine: %d correspondences (< 3)", n);
+  PnpCam cam;
+  MVO_TRY(pnp_cam(ctx, K, &cam));
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  PnpWs w;
+  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, (size_t)n * 20 + 1024));
+  float *h3 = (float *)ctx->h_b.p, *h2 = h3 + (size_t)n * 3;
+  double *h_pose = (double *)((uint8_t *)ctx->h_b.p + (size_t)n * 20);
+  memcpy(h3, pts3d, (size_t)n * 12);
+  memcpy(h2, pts2d, (size_t)n * 8);
+  rvec_to_rotation(rvec, h_pose);
+  h_pose[9] = tvec[0]; h_pose[10] = tvec[1]; h_pose[11] = tvec[2];
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.pose_io, h_pose, 96, cudaMemcpyHostToDevice, ctx->stream));
+  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, 0.0, 0, nullptr, nullptr, 1, ctx->prm.pnp_refine_iters,
+                                             w.pose_io, w.out_i, w.inl);
+  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  rotation_to_rvec(h_pose, rvec);
+  tvec[0] = h_pose[9]; tvec[1] = h_pose[10]; tvec[2] = h_pose[11];
+  return MVO_OK;
+}
+
+}  // extern "C"

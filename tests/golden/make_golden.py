@@ -51,6 +51,21 @@ def make_orb():
                             cv_version=cv2.__version__, **extra)
 
 
+def make_pnp():
+    """cv::solvePnPRansac exactly as called at src/vo/vo.cpp:318-320 on the config-3 instance."""
+    import cv2
+    import mvo_synth
+    P, uv, rvec_true, tvec_true, is_out = mvo_synth.pnp_problem(0)
+    K = mvo_synth.K_DEFAULT
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(P, uv, K, None, None, None, False, 100, 2.0, 0.999)
+    assert ok
+    inl = inl.ravel().astype(np.int32)
+    ok2, r2, t2 = cv2.solvePnP(P[inl], uv[inl], K, None, flags=cv2.SOLVEPNP_ITERATIVE)
+    np.savez_compressed(OUT / "pnp_config3.npz", P=P, uv=uv, K=K, rvec=rvec.ravel(), tvec=tvec.ravel(), inliers=inl,
+                        rvec_refit=r2.ravel(), tvec_refit=t2.ravel(), rvec_true=rvec_true, tvec_true=tvec_true,
+                        cv_version=cv2.__version__)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):

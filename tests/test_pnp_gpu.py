@@ -1,0 +1,113 @@
+"""GPU parity of the batched RANSAC PnP (C ABI mvo_solve_pnp_ransac, replacing cv::solvePnPRansac
+at reference src/vo/vo.cpp:318-320).
+
+Tolerances (stated per SURVEY.md App. C):
+  * scoring: inlier counts of every hypothesis equal the fp64 oracle's exactly, except hypotheses
+    that have a point within 1e-7 px^2 of the threshold (summation-order noise);
+  * refit on a FIXED inlier set: pose within 1e-6 (rad / length units) of cv2.solvePnP(ITERATIVE)
+    and 1e-8 of the converged least-squares optimum;
+  * end to end vs cv2.solvePnPRansac: rotation within 5e-4 rad, translation within 2e-3 units,
+    inlier sets overlapping >= 99 % (different minimal sets -> different borderline points)."""
+import numpy as np
+import pytest
+from conftest import GOLDEN, have_cv2
+
+import mvo_synth
+from oracle import pnp_oracle as po
+
+pytestmark = pytest.mark.gpu
+K = mvo_synth.K_DEFAULT
+
+
+def test_config3_vs_golden_and_truth(ctx):
+    g = np.load(GOLDEN / "pnp_config3.npz")
+    rvec, tvec, inl = ctx.solve_pnp_ransac(g["P"], g["uv"], g["K"])
+    assert np.abs(rvec - g["rvec"]).max() < 5e-4, rvec - g["rvec"]
+    assert np.abs(tvec - g["tvec"]).max() < 2e-3, tvec - g["tvec"]
+    a, b = set(inl.tolist()), set(g["inliers"].tolist())
+    assert len(a & b) / len(a | b) >= 0.99
+    assert len(inl) >= len(g["inliers"]) - 5           # 4096 hypotheses should not find a worse model
+    assert np.all(np.diff(inl) > 0)                     # ascending indices
+    assert np.abs(rvec - g["rvec_true"]).max() < 2e-3 and np.abs(tvec - g["tvec_true"]).max() < 1e-2
+
+
+def test_hypothesis_scoring_bit_level(ctx):
+    P, uv, *_ = mvo_synth.pnp_problem(1, n=1500)
+    rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, K)
+    poses, counts = ctx.pnp_last_hypotheses()
+    assert len(poses) == 4096
+    valid = counts >= 0
+    assert valid.mean() > 0.95                                   # P3P almost always has a real solution
+    ref, margin = po.count_inliers(P, uv, K, poses[valid], 2.0)
+    clear = margin > 1e-7
+    assert clear.mean() > 0.99
+    assert np.array_equal(counts[valid][clear], ref[clear])
+    # rotations are proper
+    R = poses[valid][:, :9].reshape(-1, 3, 3)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 1e-9 and np.abs(np.linalg.det(R) - 1).max() < 1e-9
+    # best model = highest count, lowest index on ties; its consensus set is what is returned
+    best = int(np.flatnonzero(counts == counts.max())[0])
+    e = po.reproj_err2(P, uv, K, poses[best][:9].reshape(3, 3), poses[best][9:])
+    assert np.array_equal(inl, np.flatnonzero(e <= 4.0))
+    # with 30 % outliers about 0.7^4 = 24 % of the minimal sets are all-inlier: they must agree with the truth
+    good = counts > 0.6 * 0.7 * len(P)
+    assert good.mean() > 0.10
+
+
+def test_refit_parity(ctx):
+    g = np.load(GOLDEN / "pnp_config3.npz")
+    inl = g["inliers"]
+    P, uv = g["P"][inl], g["uv"][inl]
+    r0 = g["rvec"] + np.array([2e-3, -1e-3, 1.5e-3])
+    t0 = g["tvec"] + np.array([5e-3, -4e-3, 8e-3])
+    r, t = ctx.pnp_refine(P, uv, g["K"], r0, t0)
+    assert np.abs(r - g["rvec_refit"]).max() < 1e-6 and np.abs(t - g["tvec_refit"]).max() < 1e-6
+    ro, to = po.refine(P, uv, g["K"], r0, t0)
+    assert np.abs(r - ro).max() < 1e-8 and np.abs(t - to).max() < 1e-8
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("seed,n,outl", [(2, 2000, 0.3), (3, 500, 0.5), (4, 60, 0.2), (5, 2000, 0.0)])
+def test_vs_cv2_live(ctx, seed, n, outl):
+    import cv2
+    P, uv, rt, tt, _ = mvo_synth.pnp_problem(seed, n=n, outlier_frac=outl)
+    ok, rc, tc, ic = cv2.solvePnPRansac(P, uv, K, None, None, None, False, 100, 2.0, 0.999)
+    assert ok
+    rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, K)
+    tol_r, tol_t = (5e-4, 2e-3) if n >= 500 else (5e-3, 2e-2)     # few points -> borderline inliers weigh more
+    assert np.abs(rvec - rc.ravel()).max() < tol_r and np.abs(tvec - tc.ravel()).max() < tol_t
+    a, b = set(inl.tolist()), set(ic.ravel().tolist())
+    assert len(a & b) / len(a | b) >= (0.99 if n >= 500 else 0.9)
+    # refit parity on OUR inlier set: cv2.solvePnP(ITERATIVE) must land on our pose
+    ok, r2, t2 = cv2.solvePnP(P[inl], uv[inl], K, None, flags=cv2.SOLVEPNP_ITERATIVE)
+    assert np.abs(rvec - r2.ravel()).max() < 1e-6 and np.abs(tvec - t2.ravel()).max() < 1e-6
+
+
+def test_deterministic_and_seeded(ctx):
+    P, uv, *_ = mvo_synth.pnp_problem(7, n=800)
+    a = ctx.solve_pnp_ransac(P, uv, K)
+    b = ctx.solve_pnp_ransac(P, uv, K)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    old = ctx.params.pnp_seed
+    ctx.set_params(pnp_seed=12345)
+    c = ctx.solve_pnp_ransac(P, uv, K)
+    ctx.set_params(pnp_seed=old)
+    assert np.abs(c[0] - a[0]).max() < 5e-4
+
+
+def test_edge_cases(ctx):
+    import mvo_b200
+    P, uv, rt, tt, _ = mvo_synth.pnp_problem(8, n=4, outlier_frac=0.0, noise=0.0)
+    with pytest.raises(mvo_b200.MvoError) as e:
+        ctx.solve_pnp_ransac(P[:3], uv[:3], K)
+    assert e.value.code == -6
+    rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, K)               # exactly 4 noise-free points
+    assert len(inl) == 4 and np.abs(rvec - rt).max() < 1e-4 and np.abs(tvec - tt).max() < 1e-3
+    # planar object (all Z equal in its own frame)
+    rng = np.random.default_rng(0)
+    Pp = np.stack([rng.uniform(-1, 1, 300), rng.uniform(-1, 1, 300), np.zeros(300)], 1).astype(np.float32)
+    R = mvo_synth.rodrigues([0.2, -0.1, 0.05])
+    pc = Pp @ R.T + np.array([0.1, 0.0, 4.0])
+    uvp = (pc[:, :2] / pc[:, 2:3] * 615 + np.array([320, 240])).astype(np.float32)
+    rvec, tvec, inl = ctx.solve_pnp_ransac(Pp, uvp, K)
+    assert len(inl) >= 295 and np.abs(rvec - [0.2, -0.1, 0.05]).max() < 1e-3 and np.abs(tvec - [0.1, 0, 4.0]).max() < 5e-3
