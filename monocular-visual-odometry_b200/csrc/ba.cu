@@ -1,0 +1,684 @@
+// Local bundle adjustment for sm_100a — replaces optimization::bundleAdjustment
+// (reference src/optimization/g2o_ba.cpp:172-317) and optimizeSingleFrame (:34-145), i.e. g2o's
+// OptimizationAlgorithmLevenberg + BlockSolver<6,3> (Schur on the points) + LinearSolverDense
+// + RobustKernelHuber over VertexSE3Expmap / VertexSBAPointXYZ / EdgeProjectXYZ2UV
+// (semantics: SURVEY.md Appendix B).
+//
+// The problem is tiny (F <= 16 poses, ~2000 points, ~10^4 edges) and every LM step is a chain
+// of dependent phases, so the whole optimisation is ONE kernel launched as ONE thread-block
+// cluster (8 CTAs on 8 SMs of a GPC): phases are separated by cluster barriers (~0.3 us instead
+// of a ~3 us grid sync or a kernel boundary), and cross-CTA reductions go through distributed
+// shared memory: every CTA leaves its partial sums in its own shared memory and, after the
+// barrier, every CTA reads all 8 partials in rank order.  All CTAs therefore hold bit-identical
+// copies of Hpp, b, the Schur system, its solution and the LM control state, take the same
+// accept/reject decisions without any broadcast, and the result is deterministic.
+//
+// Work split: points (with their edges, CSR by point, edges of a point sorted by frame) are
+// partitioned over the CTAs.  Per LM iteration:
+//   A  linearise: thread per point walks its edges; Hll, bl, W(point,frame) to global; Hpp/bp of
+//      each frame by a warp-shuffle reduction (the "segmented" reduce: segments = frames)
+//   B  reduce partials over the cluster, lambda init (first iteration)
+//   C  Schur partials  S_part = sum_l Y_l W_l^T,  Y_l = W_l (Hll+lambda I)^-1   (staged in smem)
+//   D  S = Hpp + lambda I - sum S_part; block-parallel LDL^T; pose step
+//   E  point steps, trial state, new robust chi2 and the gain denominator
+//   F  gain ratio, accept/reject, lambda update  (g2o's rule, <= 10 trials)
+// fp64 throughout (g2o is double); no tensor cores: ~15 MFLOP per iteration, latency-bound.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "mvo_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int BA_T = 256;
+constexpr int BA_CLUSTER = 8;
+constexpr int BA_MAXF = 16;
+constexpr int BA_NW = BA_T / 32;
+
+struct BaArgs {
+  int F, P, E, iters, fix_points, fix_first, use_huber, pc;
+  double f, cx, cy, i00, i01, i10, i11, huber;
+  const int32_t *pt_start;
+  const int32_t *e_frame;
+  const double *obs;
+  double *pts_a, *pts_b, *Hll, *bl, *Hinv, *Wd;
+  double *poses;     // F x 12 (R row-major, t), world->camera, in/out
+  double *stats;     // 4
+  int32_t *pts_sel;  // [1]: which of pts_a / pts_b holds the final points
+};
+
+struct Lin {
+  double e0, e1, chi, w;
+  double A[6], B[12];
+};
+
+__device__ __forceinline__ void edge_residual(const double *Rt, const double *X, double ou, double ov, const BaArgs &a,
+                                              double &x, double &y, double &z, double &e0, double &e1) {
+  x = Rt[0] * X[0] + Rt[1] * X[1] + Rt[2] * X[2] + Rt[9];
+  y = Rt[3] * X[0] + Rt[4] * X[1] + Rt[5] * X[2] + Rt[10];
+  z = Rt[6] * X[0] + Rt[7] * X[1] + Rt[8] * X[2] + Rt[11];
+  e0 = ou - (a.f * x / z + a.cx);
+  e1 = ov - (a.f * y / z + a.cy);
+}
+
+__device__ __forceinline__ double robust_rho(double chi, const BaArgs &a) {
+  const double d2 = a.huber * a.huber;
+  return (a.use_huber && chi > d2) ? 2 * sqrt(chi) * a.huber - d2 : chi;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exp of a g2o SE3 update (omega, upsilon) applied on the left of (R, t): out = exp(d) * in
+__device__ void se3_update(const double *d, const double *in, double *out) {
+  const double wx = d[0], wy = d[1], wz = d[2];
+  const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+  double a, b, c;
+  if (th < 0.00001) { a = 1; b = 1; c = 1; }        // g2o's small-angle branch: R = V = I + O + O^2
+  else { a = sin(th) / th; b = (1 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
+  const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  double O2[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+  double Rd[9], V[9];
+  for (int i = 0; i < 9; ++i) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    Rd[i] = I + a * O[i] + b * O2[i];
+    V[i] = (th < 0.00001) ? Rd[i] : I + b * O[i] + c * O2[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) out[i * 3 + j] = Rd[i * 3] * in[j] + Rd[i * 3 + 1] * in[3 + j] + Rd[i * 3 + 2] * in[6 + j];
+    out[9 + i] = Rd[i * 3] * in[9] + Rd[i * 3 + 1] * in[10] + Rd[i * 3 + 2] * in[11] +
+                 V[i * 3] * d[3] + V[i * 3 + 1] * d[4] + V[i * 3 + 2] * d[5];
+  }
+}
+
+__device__ __forceinline__ bool inv3_sym(const double *h, double lam, double *o) {   // h: 00 01 02 11 12 22
+  const double a = h[0] + lam, b = h[1], c = h[2], d = h[3] + lam, e = h[4], f = h[5] + lam;
+  const double c0 = d * f - e * e, c1 = c * e - b * f, c2 = b * e - c * d;
+  const double det = a * c0 + b * c1 + c * c2;
+  if (!(fabs(det) > 0)) return false;
+  const double id = 1.0 / det;
+  o[0] = c0 * id; o[1] = c1 * id; o[2] = c2 * id;
+  o[3] = (a * f - c * c) * id; o[4] = (b * c - a * e) * id; o[5] = (a * d - b * b) * id;
+  return true;
+}
+
+__global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = a.F;
+  extern __shared__ __align__(16) double sm[];
+
+  // active pose blocks
+  __shared__ int s_pidx[BA_MAXF], s_act[BA_MAXF];
+  __shared__ int s_nact;
+  __shared__ double s_ctl[8];     // 0 lambda, 1 ni, 2 chi_cur, 3 rho, 4 ok, 5 temp chi, 6 swap flag
+  if (tid == 0) {
+    int na = 0;
+    for (int f = 0; f < F; ++f) {
+      if (a.fix_first && f == 0) s_pidx[f] = -1;
+      else { s_pidx[f] = na; s_act[na] = f; ++na; }
+    }
+    s_nact = na;
+    s_ctl[6] = 0;
+  }
+  __syncthreads();
+  const int n = 6 * s_nact;
+  const int NA = F * 27 + 2;                 // per-frame (21 Hpp + 6 bp), chi2, max diag(Hll)
+  const int NC = n * n + n;
+  // shared carve-up (doubles)
+  double *s_pose = sm;                        // F*12
+  double *s_try = s_pose + F * 12;            // F*12
+  double *s_full = s_try + F * 12;            // NA   reduced Hpp/bp/chi/maxdiag
+  double *s_partA = s_full + NA;              // NA   this CTA's partial (read remotely)
+  double *s_partE = s_partA + NA;             // 4
+  double *s_dp = s_partE + 4;                 // n (+pad)
+  double *s_partC = s_dp + ((n + 3) & ~3) + 4;   // NC  (read remotely)
+  double *s_u = s_partC + ((NC + 3) & ~3);    // union: warp partials (A) | staging (C) | S + rhs (D)
+  double *s_wred = s_u;                       // BA_NW * NA
+  double *s_S = s_u;                          // n*n
+  double *s_rhs = s_u + n * n;                // n
+
+  for (int i = tid; i < F * 12; i += BA_T) s_pose[i] = a.poses[i];
+  // this CTA's points
+  const int per = (a.P + (int)csize - 1) / (int)csize;
+  const int p0 = min((int)rank * per, a.P), p1 = min(p0 + per, a.P);
+  const bool freep = !a.fix_points;
+  double chi_init = 0;
+  int it = 0;
+  bool terminate = false;
+
+  for (; it < a.iters && !terminate; ++it) {
+    __syncthreads();
+    const double *pts = (s_ctl[6] != 0) ? a.pts_b : a.pts_a;
+    double *pts_try = (s_ctl[6] != 0) ? a.pts_a : a.pts_b;
+    // ---------------- phase A: linearise ----------------
+    for (int i = tid; i < BA_NW * NA; i += BA_T) s_wred[i] = 0;
+    __syncthreads();
+    double chi_t = 0, md_t = 0;
+    for (int base = p0; base < p1; base += BA_T) {
+      const int l = base + tid;
+      const bool act = l < p1;
+      double X[3] = {0, 0, 0};
+      int k = 0, kend = 0;
+      if (act) { X[0] = pts[3 * l]; X[1] = pts[3 * l + 1]; X[2] = pts[3 * l + 2]; k = a.pt_start[l]; kend = a.pt_start[l + 1]; }
+      double hl[6] = {0, 0, 0, 0, 0, 0}, blv[3] = {0, 0, 0};
+      for (int f = 0; f < F; ++f) {
+        double hp[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) hp[q] = 0;
+        double wlf[18];
+#pragma unroll
+        for (int q = 0; q < 18; ++q) wlf[q] = 0;
+        const double *Rt = s_pose + 12 * f;
+        const bool pose_act = s_pidx[f] >= 0;
+        while (k < kend && a.e_frame[k] == f) {
+          double x, y, z, e0, e1;
+          edge_residual(Rt, X, a.obs[2 * k], a.obs[2 * k + 1], a, x, y, z, e0, e1);
+          const double iz = 1.0 / z, z2 = z * z, fl = a.f;
+          // EdgeProjectXYZ2UV::linearizeOplus
+          const double t0 = -x * iz * fl, t1 = -y * iz * fl;
+          double A[6];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            A[c] = -iz * (fl * Rt[c] + t0 * Rt[6 + c]);
+            A[3 + c] = -iz * (fl * Rt[3 + c] + t1 * Rt[6 + c]);
+          }
+          const double B[12] = {x * y / z2 * fl, -(1 + (x * x / z2)) * fl, y * iz * fl, -iz * fl, 0, x / z2 * fl,
+                                (1 + y * y / z2) * fl, -x * y / z2 * fl, -x * iz * fl, 0, -iz * fl, y / z2 * fl};
+          const double Oe0 = a.i00 * e0 + a.i01 * e1, Oe1 = a.i10 * e0 + a.i11 * e1;
+          const double chi = e0 * Oe0 + e1 * Oe1;
+          chi_t += robust_rho(chi, a);
+          double w = 1.0;
+          if (a.use_huber && chi > a.huber * a.huber) w = a.huber / sqrt(chi);
+          const double o00 = w * a.i00, o01 = w * a.i01, o10 = w * a.i10, o11 = w * a.i11;
+          const double r0 = -w * Oe0, r1 = -w * Oe1;
+          double OA[6];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { OA[c] = o00 * A[c] + o01 * A[3 + c]; OA[3 + c] = o10 * A[c] + o11 * A[3 + c]; }
+          if (freep) {
+            blv[0] += A[0] * r0 + A[3] * r1; blv[1] += A[1] * r0 + A[4] * r1; blv[2] += A[2] * r0 + A[5] * r1;
+            hl[0] += A[0] * OA[0] + A[3] * OA[3]; hl[1] += A[0] * OA[1] + A[3] * OA[4]; hl[2] += A[0] * OA[2] + A[3] * OA[5];
+            hl[3] += A[1] * OA[1] + A[4] * OA[4]; hl[4] += A[1] * OA[2] + A[4] * OA[5]; hl[5] += A[2] * OA[2] + A[5] * OA[5];
+            if (pose_act) {
+#pragma unroll
+              for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) wlf[r * 3 + c] += B[r] * OA[c] + B[6 + r] * OA[3 + c];
+            }
+          }
+          if (pose_act) {
+            double OB[12];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { OB[c] = o00 * B[c] + o01 * B[6 + c]; OB[6 + c] = o10 * B[c] + o11 * B[6 + c]; }
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+              for (int c = r; c < 6; ++c) hp[q++] += B[r] * OB[c] + B[6 + r] * OB[6 + c];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) hp[21 + r] += B[r] * r0 + B[6 + r] * r1;
+          }
+          ++k;
+        }
+        if (freep && act && pose_act) {
+          double *wd = a.Wd + ((size_t)l * F + f) * 18;
+#pragma unroll
+          for (int q = 0; q < 18; ++q) wd[q] = wlf[q];
+        }
+        if (pose_act) {
+#pragma unroll
+          for (int q = 0; q < 27; ++q) {
+            const double s = warp_sum_d(hp[q]);
+            if (lane == 0) s_wred[warp * NA + f * 27 + q] += s;
+          }
+        }
+      }
+      if (freep && act) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a.Hll[(size_t)l * 6 + q] = hl[q];
+        a.bl[3 * l] = blv[0]; a.bl[3 * l + 1] = blv[1]; a.bl[3 * l + 2] = blv[2];
+        if (kend > a.pt_start[l]) md_t = fmax(md_t, fmax(fabs(hl[0]), fmax(fabs(hl[3]), fabs(hl[5]))));
+      }
+    }
+    {
+      const double cs = warp_sum_d(chi_t);
+      double m = md_t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) { s_wred[warp * NA + F * 27] = cs; s_wred[warp * NA + F * 27 + 1] = m; }
+    }
+    __syncthreads();
+    for (int i = tid; i < NA; i += BA_T) {
+      double s = 0;
+      if (i == NA - 1) { for (int w = 0; w < BA_NW; ++w) s = fmax(s, s_wred[w * NA + i]); }
+      else { for (int w = 0; w < BA_NW; ++w) s += s_wred[w * NA + i]; }
+      s_partA[i] = s;
+    }
+    cluster.sync();                                                         // ---- barrier 1
+    // ---------------- phase B: cluster reduction ----------------
+    for (int i = tid; i < NA; i += BA_T) {
+      double s = 0;
+      for (unsigned r = 0; r < csize; ++r) {
+        const double v = *cluster.map_shared_rank(s_partA + i, r);
+        s = (i == NA - 1) ? fmax(s, v) : s + v;
+      }
+      s_full[i] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_ctl[2] = s_full[F * 27];
+      if (it == 0) {
+        // computeLambdaInit: tau * max |diag| over all non-fixed vertices, tau = 1e-5
+        double md = freep ? s_full[F * 27 + 1] : 0;
+        for (int f = 0; f < F; ++f)
+          if (s_pidx[f] >= 0) {
+            const double *h = s_full + f * 27;
+            md = fmax(md, fmax(fmax(fabs(h[0]), fabs(h[6])), fmax(fmax(fabs(h[11]), fabs(h[15])), fmax(fabs(h[18]), fabs(h[20])))));
+          }
+        s_ctl[0] = 1e-5 * md;
+        s_ctl[1] = 2;
+      }
+    }
+    __syncthreads();
+    if (it == 0) chi_init = s_ctl[2];
+
+    // ---------------- LM trials ----------------
+    int qmax = 0;
+    double rho = 0;
+    do {
+      const double lambda = s_ctl[0];
+      // ---- phase C: Schur partials (free points only) ----
+      for (int i = tid; i < NC; i += BA_T) s_partC[i] = 0;
+      bool inv_ok = true;
+      if (freep) {
+        double *s_Y = s_u;                                   // [pc][F][18]
+        double *s_W = s_Y + (size_t)a.pc * F * 18;           // [pc][F][18]
+        double *s_b = s_W + (size_t)a.pc * F * 18;           // [pc][3]
+        for (int c0 = p0; c0 < p1; c0 += a.pc) {
+          const int cn = min(a.pc, p1 - c0);
+          __syncthreads();
+          for (int i = tid; i < cn * F; i += BA_T) {
+            const int li = i / F, f = i - li * F, l = c0 + li;
+            double *Ys = s_Y + (size_t)i * 18, *Ws = s_W + (size_t)i * 18;
+            const bool has = a.pt_start[l + 1] > a.pt_start[l];
+            double hi[6] = {0, 0, 0, 0, 0, 0};
+            if (has) { if (!inv3_sym(a.Hll + (size_t)l * 6, lambda, hi)) { inv_ok = false; } }
+            if (f == 0) {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) a.Hinv[(size_t)l * 6 + q] = hi[q];
+              s_b[li * 3] = a.bl[3 * l]; s_b[li * 3 + 1] = a.bl[3 * l + 1]; s_b[li * 3 + 2] = a.bl[3 * l + 2];
+            }
+            if (has && s_pidx[f] >= 0) {
+              const double *wd = a.Wd + ((size_t)l * F + f) * 18;
+#pragma unroll
+              for (int r = 0; r < 6; ++r) {
+                const double w0 = wd[r * 3], w1 = wd[r * 3 + 1], w2 = wd[r * 3 + 2];
+                Ws[r * 3] = w0; Ws[r * 3 + 1] = w1; Ws[r * 3 + 2] = w2;
+                Ys[r * 3] = w0 * hi[0] + w1 * hi[1] + w2 * hi[2];
+                Ys[r * 3 + 1] = w0 * hi[1] + w1 * hi[3] + w2 * hi[4];
+                Ys[r * 3 + 2] = w0 * hi[2] + w1 * hi[4] + w2 * hi[5];
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 18; ++q) { Ws[q] = 0; Ys[q] = 0; }
+            }
+          }
+          __syncthreads();
+          for (int o = tid; o < NC; o += BA_T) {
+            double acc = 0;
+            if (o < n * n) {
+              const int i = o / n, j = o - i * n;
+              const int fa = s_act[i / 6], ra = i % 6, fb = s_act[j / 6], rb = j % 6;
+              const double *yp = s_Y + ((size_t)fa * 18 + ra * 3), *wp = s_W + ((size_t)fb * 18 + rb * 3);
+              for (int li = 0; li < cn; ++li) {
+                const double *y = yp + (size_t)li * F * 18, *w = wp + (size_t)li * F * 18;
+                acc += y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
+              }
+            } else {
+              const int i = o - n * n, fa = s_act[i / 6], ra = i % 6;
+              const double *yp = s_Y + ((size_t)fa * 18 + ra * 3);
+              for (int li = 0; li < cn; ++li) {
+                const double *y = yp + (size_t)li * F * 18, *b = s_b + li * 3;
+                acc += y[0] * b[0] + y[1] * b[1] + y[2] * b[2];
+              }
+            }
+            s_partC[o] += acc;
+          }
+        }
+      }
+      if (tid == 0) s_partE[2] = 1.0;
+      __syncthreads();
+      if (!inv_ok) s_partE[2] = 0.0;                      // any thread that saw a singular Hll block
+      cluster.sync();                                                       // ---- barrier 2
+      // ---- phase D: assemble and solve the pose system (every CTA, identically) ----
+      for (int o = tid; o < NC; o += BA_T) {
+        double s = 0;
+        if (freep) for (unsigned r = 0; r < csize; ++r) s += *cluster.map_shared_rank(s_partC + o, r);
+        if (o < n * n) {
+          const int i = o / n, j = o - i * n;
+          double h = 0;
+          if (i / 6 == j / 6) {
+            const int f = s_act[i / 6], r = min(i % 6, j % 6), c = max(i % 6, j % 6);
+            h = s_full[f * 27 + (r * (13 - r)) / 2 + (c - r)];        // upper-triangular packing
+            if (i == j) h += lambda;
+          }
+          s_S[o] = h - s;
+        } else {
+          const int i = o - n * n, f = s_act[i / 6];
+          s_rhs[i] = s_full[f * 27 + 21 + i % 6] - s;
+        }
+      }
+      double okf = 1.0;
+      for (unsigned r = 0; r < csize; ++r) okf *= *cluster.map_shared_rank(s_partE + 2, r);
+      __syncthreads();
+      bool ok = okf != 0.0;
+      // LDL^T, right-looking, in place (lower triangle holds L, diagonal holds D)
+      for (int j = 0; j < n && ok; ++j) {
+        const double d = s_S[j * n + j];
+        if (!(fabs(d) > 0) || !isfinite(d)) { ok = false; break; }      // uniform: every thread reads the same d
+        for (int i = j + 1 + tid; i < n; i += BA_T) s_S[i * n + j] /= d;
+        __syncthreads();
+        const int m = n - j - 1;
+        for (int o = tid; o < m * m; o += BA_T) {
+          const int i = j + 1 + o / m, k = j + 1 + o % m;
+          if (k <= i) s_S[i * n + k] -= s_S[i * n + j] * s_S[k * n + j] * d;
+        }
+        __syncthreads();
+      }
+      if (ok) {
+        for (int j = 0; j < n; ++j) {           // forward: L y = b
+          const double bj = s_rhs[j];
+          __syncthreads();
+          for (int i = j + 1 + tid; i < n; i += BA_T) s_rhs[i] -= s_S[i * n + j] * bj;
+          __syncthreads();
+        }
+        for (int i = tid; i < n; i += BA_T) s_rhs[i] /= s_S[i * n + i];
+        __syncthreads();
+        for (int j = n - 1; j >= 0; --j) {      // backward: L^T x = y
+          const double bj = s_rhs[j];
+          __syncthreads();
+          for (int i = tid; i < j; i += BA_T) s_rhs[i] -= s_S[j * n + i] * bj;
+          __syncthreads();
+        }
+        for (int i = tid; i < n; i += BA_T) s_dp[i] = s_rhs[i];
+      } else {
+        for (int i = tid; i < n; i += BA_T) s_dp[i] = 0;
+      }
+      __syncthreads();
+      // ---- phase E: trial state, new chi2, gain denominator ----
+      for (int f = tid; f < F; f += BA_T) {
+        if (s_pidx[f] >= 0 && ok) se3_update(s_dp + 6 * s_pidx[f], s_pose + 12 * f, s_try + 12 * f);
+        else for (int q = 0; q < 12; ++q) s_try[12 * f + q] = s_pose[12 * f + q];
+      }
+      __syncthreads();
+      double chi_n = 0, scale_t = 0;
+      for (int l = p0 + tid; l < p1; l += BA_T) {
+        double X[3] = {pts[3 * l], pts[3 * l + 1], pts[3 * l + 2]};
+        const int kb = a.pt_start[l], ke = a.pt_start[l + 1];
+        if (freep && ok && ke > kb) {
+          double c[3] = {a.bl[3 * l], a.bl[3 * l + 1], a.bl[3 * l + 2]};
+          const double b0 = c[0], b1 = c[1], b2 = c[2];
+          for (int f = 0; f < F; ++f) {
+            const int pa = s_pidx[f];
+            if (pa < 0) continue;
+            const double *wd = a.Wd + ((size_t)l * F + f) * 18, *dp = s_dp + 6 * pa;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { c[0] -= wd[q * 3] * dp[q]; c[1] -= wd[q * 3 + 1] * dp[q]; c[2] -= wd[q * 3 + 2] * dp[q]; }
+          }
+          const double *hi = a.Hinv + (size_t)l * 6;
+          const double d0 = hi[0] * c[0] + hi[1] * c[1] + hi[2] * c[2];
+          const double d1 = hi[1] * c[0] + hi[3] * c[1] + hi[4] * c[2];
+          const double d2 = hi[2] * c[0] + hi[4] * c[1] + hi[5] * c[2];
+          X[0] += d0; X[1] += d1; X[2] += d2;
+          scale_t += d0 * (lambda * d0 + b0) + d1 * (lambda * d1 + b1) + d2 * (lambda * d2 + b2);
+        }
+        if (freep) { pts_try[3 * l] = X[0]; pts_try[3 * l + 1] = X[1]; pts_try[3 * l + 2] = X[2]; }
+        for (int k = kb; k < ke; ++k) {
+          double x, y, z, e0, e1;
+          edge_residual(s_try + 12 * a.e_frame[k], X, a.obs[2 * k], a.obs[2 * k + 1], a, x, y, z, e0, e1);
+          chi_n += robust_rho(e0 * (a.i00 * e0 + a.i01 * e1) + e1 * (a.i10 * e0 + a.i11 * e1), a);
+        }
+      }
+      {
+        const double c = warp_sum_d(chi_n), s = warp_sum_d(scale_t);
+        __syncthreads();                     // s_u (S, rhs) is dead from here on: reuse as scratch
+        if (lane == 0) { s_u[warp * 2] = c; s_u[warp * 2 + 1] = s; }
+        __syncthreads();
+        if (tid == 0) {
+          double cc = 0, ss = 0;
+          for (int w = 0; w < BA_NW; ++w) { cc += s_u[w * 2]; ss += s_u[w * 2 + 1]; }
+          s_partE[0] = cc; s_partE[1] = ss;
+        }
+      }
+      cluster.sync();                                                       // ---- barrier 3
+      // ---- phase F: gain ratio and LM control (g2o OptimizationAlgorithmLevenberg::solve) ----
+      if (tid == 0) {
+        double temp = 0, scale = 0;
+        for (unsigned r = 0; r < csize; ++r) {
+          temp += *cluster.map_shared_rank(s_partE + 0, r);
+          scale += *cluster.map_shared_rank(s_partE + 1, r);
+        }
+        for (int i = 0; i < n; ++i) {
+          const int f = s_act[i / 6];
+          scale += s_dp[i] * (lambda * s_dp[i] + s_full[f * 27 + 21 + i % 6]);
+        }
+        if (!ok) temp = 1.7976931348623157e308;
+        const double cur = s_ctl[2];
+        double r_ = (cur - temp) / (scale + 1e-3);
+        if (r_ > 0 && isfinite(temp)) {
+          double alpha = 1. - pow(2 * r_ - 1, 3);
+          alpha = fmin(alpha, 2. / 3.);
+          s_ctl[0] = lambda * fmax(1. / 3., alpha);
+          s_ctl[1] = 2;
+          s_ctl[2] = temp;
+          s_ctl[4] = 1;
+        } else {
+          s_ctl[0] = lambda * s_ctl[1];
+          s_ctl[1] *= 2;
+          s_ctl[4] = 0;
+        }
+        s_ctl[3] = r_;
+      }
+      __syncthreads();
+      rho = s_ctl[3];
+      if (s_ctl[4] != 0) {              // accepted: trial state becomes current
+        for (int i = tid; i < F * 12; i += BA_T) s_pose[i] = s_try[i];
+        if (freep) {
+          __syncthreads();
+          if (tid == 0) s_ctl[6] = (s_ctl[6] != 0) ? 0.0 : 1.0;
+        }
+      }
+      __syncthreads();
+      ++qmax;
+      // the trial loop re-reads s_ctl / pts pointers only on acceptance, which ends the loop
+    } while (rho < 0 && qmax < 10);
+    if (qmax == 10 || rho == 0) terminate = true;
+    // Each CTA reads remote s_partE / s_partC only between the barriers above; a trailing barrier
+    // keeps a fast CTA from overwriting its partials while a slow one is still in phase F.
+    cluster.sync();
+  }
+  if (rank == 0) {
+    for (int i = tid; i < F * 12; i += BA_T) a.poses[i] = s_pose[i];
+    if (tid == 0) {
+      a.stats[0] = chi_init; a.stats[1] = s_ctl[2]; a.stats[2] = it; a.stats[3] = s_ctl[0];
+      a.pts_sel[0] = s_ctl[6] != 0 ? 1 : 0;
+    }
+  }
+}
+
+size_t ba_smem_doubles(int F, int nact, int pc) {
+  const size_t n = 6 * (size_t)nact, NA = (size_t)F * 27 + 2, NC = n * n + n;
+  size_t u = (size_t)BA_NW * NA;
+  u = std::max(u, n * n + n + 8);
+  u = std::max(u, (size_t)pc * F * 36 + (size_t)pc * 3 + 8);
+  return (size_t)F * 24 + 2 * NA + 4 + ((n + 3) & ~(size_t)3) + 4 + ((NC + 3) & ~(size_t)3) + u + 16;
+}
+
+}  // namespace
+
+// Shared driver for bundleAdjustment and optimizeSingleFrame.
+static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P, const int32_t *edge_frame,
+                  const int32_t *edge_point, const float *obs, int E, const double *K, const double *info,
+                  int fix_points, int update_points, int iterations, int use_huber, double *stats) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!poses_T_w_c || !K || !info || (P > 0 && !points) || (E > 0 && (!edge_frame || !edge_point || !obs)))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "bundleAdjustment: null pointer");
+  if (F < 1 || F > BA_MAXF) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "bundleAdjustment: %d frames (supported 1..%d)", F, BA_MAXF);
+  if (P < 0 || E < 0) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "bundleAdjustment: negative size");
+  for (int k = 0; k < E; ++k)
+    if (edge_frame[k] < 0 || edge_frame[k] >= F || edge_point[k] < 0 || edge_point[k] >= P)
+      return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "bundleAdjustment: edge %d references frame %d / point %d", k, edge_frame[k], edge_point[k]);
+  if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  const int fix_first = ctx->prm.ba_fix_first_pose ? 1 : 0;
+  const int nact = F - fix_first;
+  if (E == 0 || iterations == 0 || (nact == 0 && fix_points)) return MVO_OK;      // nothing to optimise
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  // CSR by point, edges of a point ordered by frame (stable in the caller's order otherwise)
+  std::vector<int32_t> pt_start(P + 2, 0), e_fr(E);
+  std::vector<double> e_obs(2 * (size_t)E);
+  {
+    std::vector<int32_t> order(E);
+    for (int k = 0; k < E; ++k) pt_start[edge_point[k] + 1]++;
+    for (int p = 0; p < P; ++p) pt_start[p + 1] += pt_start[p];
+    std::vector<int32_t> cur(pt_start.begin(), pt_start.begin() + P + 1);
+    for (int k = 0; k < E; ++k) order[cur[edge_point[k]]++] = k;
+    for (int p = 0; p < P; ++p)
+      std::stable_sort(order.begin() + pt_start[p], order.begin() + pt_start[p + 1],
+                       [&](int32_t x, int32_t y) { return edge_frame[x] < edge_frame[y]; });
+    for (int i = 0; i < E; ++i) {
+      e_fr[i] = edge_frame[order[i]];
+      e_obs[2 * i] = obs[2 * order[i]];
+      e_obs[2 * i + 1] = obs[2 * order[i] + 1];
+    }
+  }
+  // g2o_ba.cpp:183-190: world->camera = (T_w_c)^-1
+  std::vector<double> pose12((size_t)F * 12), pts_d(3 * (size_t)std::max(P, 1));
+  for (int f = 0; f < F; ++f) {
+    const double *T = poses_T_w_c + 16 * f;
+    double *o = pose12.data() + 12 * f;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) o[i * 3 + j] = T[j * 4 + i];
+      o[9 + i] = -(T[0 * 4 + i] * T[3] + T[1 * 4 + i] * T[7] + T[2 * 4 + i] * T[11]);
+    }
+  }
+  for (int i = 0; i < 3 * P; ++i) pts_d[i] = points[i];
+
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  const size_t o_start = o; o = al(o + (size_t)(P + 1) * 4);
+  const size_t o_fr = o;    o = al(o + (size_t)E * 4);
+  const size_t o_obs = o;   o = al(o + (size_t)E * 16);
+  const size_t o_pose = o;  o = al(o + (size_t)F * 96);
+  const size_t o_pa = o;    o = al(o + (size_t)P * 24 + 24);
+  const size_t in_end = o;
+  const size_t o_pb = o;    o = al(o + (size_t)P * 24 + 24);
+  const size_t o_hll = o;   o = al(o + (size_t)P * 48 + 48);
+  const size_t o_bl = o;    o = al(o + (size_t)P * 24 + 24);
+  const size_t o_hinv = o;  o = al(o + (size_t)P * 48 + 48);
+  const size_t o_wd = o;    o = al(o + (fix_points ? 8 : (size_t)P * F * 144 + 144));
+  const size_t o_stats = o; o = al(o + 64);
+  MVO_TRY(mvo_reserve(ctx, ctx->ba_buf, o));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, in_end + 4096));
+  uint8_t *h = (uint8_t *)ctx->h_a.p, *d = (uint8_t *)ctx->ba_buf.p;
+  memcpy(h + o_start, pt_start.data(), (size_t)(P + 1) * 4);
+  memcpy(h + o_fr, e_fr.data(), (size_t)E * 4);
+  memcpy(h + o_obs, e_obs.data(), (size_t)E * 16);
+  memcpy(h + o_pose, pose12.data(), (size_t)F * 96);
+  memcpy(h + o_pa, pts_d.data(), (size_t)P * 24);
+  MVO_CUDA(ctx, cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, ctx->stream));
+
+  BaArgs a;
+  a.F = F; a.P = P; a.E = E; a.iters = iterations; a.fix_points = fix_points ? 1 : 0; a.fix_first = fix_first;
+  a.use_huber = use_huber && ctx->prm.ba_huber_delta > 0;
+  a.f = K[0]; a.cx = K[2]; a.cy = K[5];                      // g2o_ba.cpp:219-220: fy is ignored
+  a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
+  a.huber = ctx->prm.ba_huber_delta;
+  a.pt_start = (const int32_t *)(d + o_start); a.e_frame = (const int32_t *)(d + o_fr); a.obs = (const double *)(d + o_obs);
+  a.poses = (double *)(d + o_pose); a.pts_a = (double *)(d + o_pa); a.pts_b = (double *)(d + o_pb);
+  a.Hll = (double *)(d + o_hll); a.bl = (double *)(d + o_bl); a.Hinv = (double *)(d + o_hinv); a.Wd = (double *)(d + o_wd);
+  a.stats = (double *)(d + o_stats); a.pts_sel = (int32_t *)(d + o_stats + 32);
+  // staging chunk for the Schur products: <= 64 KB of shared memory
+  int pc = (int)(65536 / ((size_t)F * 36 * 8 + 24));
+  pc = std::max(1, std::min(pc, 64));
+  a.pc = pc;
+  const size_t smem = ba_smem_doubles(F, nact, pc) * sizeof(double);
+  if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "bundleAdjustment: shared memory %zu B", smem);
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(BA_CLUSTER);
+  cfg.blockDim = dim3(BA_T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = BA_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_ba, a));
+  ctx->launches++;
+  // results
+  double *h_pose = (double *)(h + o_pose), *h_stats = (double *)(h + in_end);
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, a.poses, (size_t)F * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_stats, a.stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!fix_points && update_points && P > 0) {
+    const int sel = *(int32_t *)((uint8_t *)h_stats + 32);
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_pa, sel ? a.pts_b : a.pts_a, (size_t)P * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double *pd = (const double *)(h + o_pa);
+    for (int i = 0; i < 3 * P; ++i) points[i] = (float)pd[i];      // g2o_ba.cpp:313-315
+  }
+  for (int f = 0; f < F; ++f) {                                     // g2o_ba.cpp:298-305: back to camera->world
+    const double *p = h_pose + 12 * f;
+    double *T = poses_T_w_c + 16 * f;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) T[i * 4 + j] = p[j * 3 + i];
+      T[i * 4 + 3] = -(p[i] * p[9] + p[3 + i] * p[10] + p[6 + i] * p[11]);
+    }
+    T[12] = T[13] = T[14] = 0;
+    T[15] = 1;
+  }
+  if (stats) memcpy(stats, h_stats, 32);
+  return MVO_OK;
+}
+
+extern "C" {
+
+int mvo_bundle_adjustment(mvo_ctx *ctx, double *poses_T_w_c, int n_frames, float *points, int n_points,
+                          const int32_t *edge_frame, const int32_t *edge_point, const float *obs, int n_edges,
+                          const double *K, const double *information, int fix_points, int update_points, double *stats) {
+  return run_ba(ctx, poses_T_w_c, n_frames, points, n_points, edge_frame, edge_point, obs, n_edges, K, information,
+                fix_points, update_points, ctx ? ctx->prm.ba_iterations : 0, 1, stats);
+}
+
+int mvo_optimize_single_frame(mvo_ctx *ctx, double *pose_T_w_c, float *points, const float *obs, int n_points,
+                              const double *K, int fix_points, int update_points) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (n_points < 0) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "optimizeSingleFrame: negative size");
+  // g2o_ba.cpp:82-98: one edge per (point i, pose 0), identity information, no robust kernel
+  std::vector<int32_t> ef(n_points, 0), ep(n_points);
+  for (int i = 0; i < n_points; ++i) ep[i] = i;
+  const double I2[4] = {1, 0, 0, 1};
+  mvo_params saved = ctx->prm;
+  ctx->prm.ba_fix_first_pose = 0;
+  const int rc = run_ba(ctx, pose_T_w_c, 1, points, n_points, ef.data(), ep.data(), obs, n_points, K, I2, fix_points,
+                        update_points, ctx->prm.ba_iterations, 0, nullptr);
+  ctx->prm = saved;
+  return rc;
+}
+
+}  // extern "C"

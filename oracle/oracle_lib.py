@@ -98,3 +98,26 @@ def retain_best(response, n_points):
     idx = np.arange(len(r), dtype=np.int32)
     n = lib().orc_retain_best(_p(r), _p(idx), len(r), int(n_points))
     return idx[:n].copy()
+
+
+def bundle_adjustment(poses_T_w_c, points, edge_frame, edge_point, obs, K, information=None, fix_points=False,
+                      update_points=True, iterations=50, huber_delta=1.0, fix_first_pose=False):
+    """oracle/ba_oracle.c — restated g2o LM (parity vs real g2o unpinned).  Returns (poses, points, stats)."""
+    L = lib()
+    L.orc_bundle_adjustment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.c_int, C.c_void_p]
+    poses = np.ascontiguousarray(poses_T_w_c, np.float64).copy().reshape(-1, 16)
+    pts = np.ascontiguousarray(points, np.float32).copy().reshape(-1, 3)
+    ef = np.ascontiguousarray(edge_frame, np.int32)
+    ep = np.ascontiguousarray(edge_point, np.int32)
+    ob = np.ascontiguousarray(obs, np.float32).reshape(-1, 2)
+    Kc = np.ascontiguousarray(K, np.float64)
+    info = np.ascontiguousarray(np.eye(2) if information is None else information, np.float64)
+    stats = np.zeros(4)
+    rc = L.orc_bundle_adjustment(_p(poses), len(poses), _p(pts), len(pts), _p(ef), _p(ep), _p(ob), len(ef), _p(Kc),
+                                 _p(info), int(fix_points), int(update_points), int(iterations), float(huber_delta),
+                                 int(fix_first_pose), _p(stats))
+    if rc != 0:
+        raise RuntimeError(f"orc_bundle_adjustment failed ({rc})")
+    return poses.reshape(-1, 4, 4), pts, stats

@@ -1,0 +1,109 @@
+"""GPU parity of the bundle adjustment (C ABI mvo_bundle_adjustment / mvo_optimize_single_frame,
+replacing optimization::bundleAdjustment / optimizeSingleFrame, reference
+src/optimization/g2o_ba.cpp:172-317, :34-145) against the C oracle that restates g2o's algorithm.
+
+Stated tolerances (fp64 on both sides, different summation order): robust chi2 relative 1e-9;
+poses |dT| < 1e-8 with fixed points, < 1e-6 with free points (the undamped gauge directions
+amplify rounding); refined points |dX| < 2e-6 (they are written back as float32)."""
+import numpy as np
+import pytest
+
+import mvo_synth
+from oracle import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(ctx, pb, fix, iters, fix_first=False):
+    ctx.set_params(ba_iterations=iters, ba_fix_first_pose=int(fix_first))
+    g = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"],
+                              fix_points=fix, update_points=not fix)
+    o = oracle_lib.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"],
+                                     fix_points=fix, update_points=not fix, iterations=iters, fix_first_pose=fix_first)
+    ctx.set_params(ba_iterations=50, ba_fix_first_pose=0)
+    return g, o
+
+
+@pytest.mark.parametrize("fix", [True, False])
+@pytest.mark.parametrize("F,P,iters", [(5, 2000, 10), (5, 300, 10), (1, 100, 10), (3, 37, 5), (8, 500, 10), (16, 200, 4)])
+def test_ba_vs_oracle(ctx, fix, F, P, iters):
+    pb = mvo_synth.ba_problem(F * 7 + P, n_frames=F, n_points=P, visibility=1.0 if P != 300 else 0.7)
+    (gp, gx, gs), (op, ox, os_) = _run_both(ctx, pb, fix, iters)
+    assert gs[2] == os_[2], (gs, os_)                                    # same number of LM iterations
+    assert abs(gs[0] - os_[0]) <= 1e-9 * os_[0] and abs(gs[1] - os_[1]) <= 1e-9 * os_[1], (gs, os_)
+    assert abs(gs[3] - os_[3]) <= 1e-6 * os_[3]                          # same lambda trajectory
+    assert gs[1] < gs[0]
+    assert np.abs(gp - op).max() < (1e-8 if fix else 1e-6), np.abs(gp - op).max()
+    if fix:
+        assert np.array_equal(gx, pb["points"])                          # g2o_ba.cpp:308: points untouched
+    else:
+        assert np.abs(gx - ox).max() < 2e-6, np.abs(gx - ox).max()
+
+
+def test_fix_first_pose_and_50_iterations(ctx):
+    pb = mvo_synth.ba_problem(3, n_frames=5, n_points=400)
+    (gp, gx, gs), (op, ox, os_) = _run_both(ctx, pb, False, 50, fix_first=True)
+    assert np.array_equal(gp[0], op[0]) and np.abs(gp[0] - pb["T_w_c"][0]).max() < 1e-12
+    assert gs[2] == os_[2] and abs(gs[1] - os_[1]) <= 1e-8 * os_[1]
+    assert np.abs(gp - op).max() < 1e-6 and np.abs(gx - ox).max() < 2e-6
+
+
+def test_information_matrix_and_duplicates(ctx):
+    pb = mvo_synth.ba_problem(4, n_frames=4, n_points=250)
+    info = np.array([[2.0, 0.3], [0.3, 0.5]])
+    # duplicate some observations (same point seen twice in one frame) and shuffle the edge order
+    rng = np.random.default_rng(0)
+    dup = rng.choice(len(pb["obs"]), 60, replace=False)
+    ef = np.concatenate([pb["edge_frame"], pb["edge_frame"][dup]])
+    ep = np.concatenate([pb["edge_point"], pb["edge_point"][dup]])
+    ob = np.concatenate([pb["obs"], pb["obs"][dup] + 0.25])
+    perm = rng.permutation(len(ef))
+    ef, ep, ob = ef[perm], ep[perm], ob[perm]
+    ctx.set_params(ba_iterations=8)
+    gp, gx, gs = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], ef, ep, ob, pb["K"], information=info, fix_points=False)
+    ctx.set_params(ba_iterations=50)
+    op, ox, os_ = oracle_lib.bundle_adjustment(pb["T_w_c"], pb["points"], ef, ep, ob, pb["K"], information=info,
+                                               fix_points=False, iterations=8)
+    assert gs[2] == os_[2] and abs(gs[1] - os_[1]) <= 1e-9 * os_[1]
+    assert np.abs(gp - op).max() < 1e-6 and np.abs(gx - ox).max() < 2e-6
+
+
+def test_optimize_single_frame(ctx):
+    pb = mvo_synth.ba_problem(5, n_frames=1, n_points=300, outlier_frac=0.0)
+    ctx.set_params(ba_iterations=12)
+    for fix in (True, False):
+        gp, gx = ctx.optimize_single_frame(pb["T_w_c"][0], pb["points"], pb["obs"], pb["K"], fix_points=fix, update_points=not fix)
+        op, ox, _ = oracle_lib.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"],
+                                                 fix_points=fix, update_points=not fix, iterations=12, huber_delta=0.0)
+        assert np.abs(gp - op[0]).max() < (1e-8 if fix else 1e-6)
+        assert np.abs(gx - ox).max() < 2e-6
+    ctx.set_params(ba_iterations=50)
+
+
+def test_degenerate_inputs(ctx):
+    import mvo_b200
+    pb = mvo_synth.ba_problem(6, n_frames=2, n_points=20)
+    # no edges: poses and points come back unchanged
+    gp, gx, gs = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], np.zeros(0, np.int32), np.zeros(0, np.int32),
+                                       np.zeros((0, 2), np.float32), pb["K"])
+    assert np.array_equal(gp, pb["T_w_c"]) and np.array_equal(gx, pb["points"])
+    with pytest.raises(mvo_b200.MvoError):
+        ctx.bundle_adjustment(pb["T_w_c"], pb["points"], np.array([5], np.int32), np.array([0], np.int32),
+                              np.zeros((1, 2), np.float32), pb["K"])           # frame index out of range
+    big = mvo_synth.ba_problem(7, n_frames=17, n_points=5)
+    with pytest.raises(mvo_b200.MvoError):
+        ctx.bundle_adjustment(big["T_w_c"], big["points"], big["edge_frame"], big["edge_point"], big["obs"], big["K"])
+
+
+def test_properties_full_size(ctx):
+    """Config 4 size: determinism, monotone cost, and the pose error against ground truth shrinks."""
+    pb = mvo_synth.ba_problem(11, n_frames=5, n_points=2000)
+    ctx.set_params(ba_iterations=10)
+    a = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"], fix_points=True, update_points=False)
+    b = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"], fix_points=True, update_points=False)
+    ctx.set_params(ba_iterations=50)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert a[2][1] < a[2][0]
+    e0 = np.abs(pb["T_w_c"] - pb["T_w_c_true"]).max()
+    e1 = np.abs(a[0] - pb["T_w_c_true"]).max()
+    assert e1 < 0.5 * e0
