@@ -19,11 +19,12 @@ def test_refit_reproduces_golden_pose():
 
 def test_inlier_rule_matches_golden_consensus_size():
     g = np.load(GOLDEN / "pnp_config3.npz")
-    pose = np.concatenate([po.rodrigues(g["rvec"]).ravel(), g["tvec"]])[None]
-    cnt, _ = po.count_inliers(g["P"], g["uv"], g["K"], pose, 2.0)
-    # the returned list is the best MINIMAL model's consensus set; the refit pose's own set differs
-    # by a handful of borderline points
-    assert abs(int(cnt[0]) - len(g["inliers"])) <= 8
+    R = po.rodrigues(g["rvec"])
+    e = po.reproj_err2(g["P"], g["uv"], g["K"], R, g["tvec"])
+    # the returned list is the best MINIMAL model's consensus set; the refit pose
+    # explains those points even better, so nearly all of them stay within 2 px of it and it gains a few
+    assert (e[g["inliers"]] <= 4.0).mean() > 0.99
+    assert int((e <= 4.0).sum()) >= len(g["inliers"])
 
 
 @pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
