@@ -217,6 +217,73 @@ int mvo_bundle_adjustment(mvo_ctx *ctx, double *poses_T_w_c, int n_frames, float
 int mvo_optimize_single_frame(mvo_ctx *ctx, double *pose_T_w_c, float *points, const float *obs,
                               int n_points, const double *K, int fix_points, int update_points);
 
+/* ---- tracking step ---------------------------------------------------------------------
+ * The DOING_TRACKING branch of vo::VisualOdometry::addFrame (src/vo/vo_addFrame.cpp:71-91) over
+ * flat arrays, host logic in C++ like the reference:
+ *   Frame::calcKeyPoints + calcDescriptors        include/my_slam/vo/frame.h:73-86
+ *   getMappointsInCurrentView_                    src/vo/vo.cpp:16-49   (project every map point
+ *                                                 with the guess pose, keep z >= 0 and inside image)
+ *   matchFeatures(map descriptors, frame)         src/vo/vo.cpp:283-289
+ *   poseEstimationPnP_                            src/vo/vo.cpp:293-381 (>= 5 pairs, PnP, T_w_c =
+ *                                                 [R|t]^-1, reject if it jumps >= 0.3 from prev)
+ *   callBundleAdjustment_                         src/vo/vo.cpp:384-478 (newest <= 5 frames of the
+ *                                                 buffer that have >= 3 map links)
+ * The map (3-D points + descriptors) is supplied by the caller: keyframe insertion, triangulation
+ * and map culling (vo_addFrame.cpp:93-124) are outside the hot path.  The pose
+ * guess is the reference keyframe's pose, moved forward whenever the camera has travelled more
+ * than min_dist_between_two_keyframes from it (checkLargeMoveForAddKeyFrame_, vo.cpp:247-265). */
+typedef struct mvo_tracker mvo_tracker;
+
+typedef struct mvo_track_params {
+  int32_t match_method;        /* feature_match_method_index_pnp = 1 (config.yaml:75) */
+  float match_radius;          /* max_matching_pixel_dist_in_pnp = 50 (:91) */
+  int32_t min_pnp_points;      /* kMinPtsForPnP = 5 (vo.cpp:304) */
+  double max_dist_to_prev;     /* max_possible_dist_to_prev_keyframe = 0.3 (config.yaml:107 region) */
+  double min_dist_keyframe;    /* min_dist_between_two_keyframes = 0.03 */
+  int32_t ba_enable;           /* is_enable_ba "true" (:120) */
+  int32_t ba_window;           /* num_prev_frames_to_opti_by_ba = 5 (:121) */
+  int32_t ba_fix_points;       /* is_ba_fix_map_points "true" (:123) */
+  double information[4];       /* information_matrix "1 0 0 1" (:122) */
+  int32_t buffer_size;         /* kBuffSize_ = 20 (include/my_slam/vo/vo.h:77) */
+} mvo_track_params;
+
+typedef struct mvo_track_result {
+  int32_t n_keypoints;         /* keypoints extracted from the frame */
+  int32_t n_candidates;        /* map points projected into the view */
+  int32_t n_matches;           /* 3d-2d pairs after matchFeatures */
+  int32_t n_inliers;           /* PnP consensus set */
+  int32_t pnp_ok;              /* poseEstimationPnP_ return value */
+  int32_t ba_frames;           /* frames that entered bundle adjustment */
+  int32_t ba_edges;
+  int32_t pad;
+  double T_w_c_pnp[16];        /* pose right after PnP (before BA) */
+} mvo_track_result;
+
+void mvo_default_track_params(mvo_track_params *p);
+int mvo_tracker_create(mvo_ctx *ctx, const double *K /* 3x3 */, int rows, int cols,
+                       const mvo_track_params *params /* NULL = defaults */, mvo_tracker **out);
+void mvo_tracker_destroy(mvo_tracker *t);
+/* Replace the map: n points (x,y,z float) with their 32-byte descriptors (MapPoint::pos_,
+ * MapPoint::descriptor_).  Copied.  Point index = map point id for the BA graph. */
+int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc, int n);
+/* Clear the frame buffer and set the reference keyframe pose (camera->world 4x4 row-major). */
+int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref);
+/* Track one frame.  image: rows x cols x channels, host memory, or device memory when
+ * image_on_device != 0.  T_w_c_out receives the frame's pose after PnP (+ BA). */
+int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t stride,
+                      int image_on_device, double *T_w_c_out, mvo_track_result *res);
+/* Pose of the k-th newest buffered frame (k = 0 is the last tracked one) after BA updates. */
+int mvo_tracker_frame_pose(const mvo_tracker *t, int k, double *T_w_c);
+
+/* ---- per-kernel timing (CUDA events on the context stream) ------------------------------
+ * mask bit i enables event pairs around every launch of kernel class i (see mvo_kernel_name).
+ * mvo_timing_read synchronises the stream and ADDS the elapsed milliseconds / launch counts
+ * since the last read into ms[] / counts[] (arrays of mvo_kernel_classes() entries). */
+int mvo_kernel_classes(void);
+const char *mvo_kernel_name(int kernel_class);
+int mvo_timing_enable(mvo_ctx *ctx, uint32_t mask);
+int mvo_timing_read(mvo_ctx *ctx, double *ms, uint64_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

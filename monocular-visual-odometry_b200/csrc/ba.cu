@@ -615,8 +615,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   const size_t smem = ba_smem_doubles(F, nact, pc) * sizeof(double);
   if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "bundleAdjustment: shared memory %zu B", smem);
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_ba, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(BA_CLUSTER);
   cfg.blockDim = dim3(BA_T);
   cfg.dynamicSmemBytes = smem;
@@ -628,7 +627,10 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_ba, a));
+  {
+    KTimer kt(ctx, KC_BA);
+    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_ba, a));
+  }
   ctx->launches++;
   // results
   double *h_pose = (double *)(h + o_pose), *h_stats = (double *)(h + in_end);

@@ -42,7 +42,49 @@ int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes) {
   return MVO_OK;
 }
 
+KTimer::KTimer(mvo_ctx *ctx, int kernel_class) : c(ctx), id(kernel_class) {
+  if (!c || !(c->timing_mask & (1u << id))) { c = nullptr; return; }
+  for (cudaEvent_t *e : {&a, &b}) {
+    if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else if (cudaEventCreate(e) != cudaSuccess) { c = nullptr; return; }
+  }
+  cudaEventRecord(a, c->stream);
+}
+
+KTimer::~KTimer() {
+  if (!c) return;
+  cudaEventRecord(b, c->stream);
+  c->ev_pending.push_back(MvoEvPair{id, a, b});
+}
+
+static const char *kKernelNames[KC_COUNT] = {"k_gray", "k_resize", "k_fast", "k_select", "k_blur", "k_describe",
+                                              "k_harris_all", "match_kernel", "k_pnp_hypotheses", "k_pnp_score",
+                                              "k_pnp_finish", "k_ba"};
+
 extern "C" {
+
+int mvo_kernel_classes(void) { return KC_COUNT; }
+const char *mvo_kernel_name(int k) { return (k >= 0 && k < KC_COUNT) ? kKernelNames[k] : "?"; }
+
+int mvo_timing_enable(mvo_ctx *ctx, uint32_t mask) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  ctx->timing_mask = mask;
+  return MVO_OK;
+}
+
+int mvo_timing_read(mvo_ctx *ctx, double *ms, uint64_t *counts) {
+  if (!ctx || !ms || !counts) return MVO_ERR_INVALID_ARG;
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (const MvoEvPair &p : ctx->ev_pending) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { ctx->t_ms[p.id] += t; ctx->t_cnt[p.id]++; }
+    ctx->ev_pool.push_back(p.a);
+    ctx->ev_pool.push_back(p.b);
+  }
+  ctx->ev_pending.clear();
+  for (int i = 0; i < KC_COUNT; ++i) { ms[i] += ctx->t_ms[i]; counts[i] += ctx->t_cnt[i]; ctx->t_ms[i] = 0; ctx->t_cnt[i] = 0; }
+  return MVO_OK;
+}
 
 void mvo_default_params(mvo_params *p) {
   if (!p) return;
@@ -135,6 +177,8 @@ void mvo_destroy(mvo_ctx *ctx) {
   PinBuf *pbs[] = {&ctx->h_a, &ctx->h_b, &ctx->orb_h, &ctx->match_h};
   for (PinBuf *b : pbs)
     if (b->p) cudaFreeHost(b->p);
+  for (const MvoEvPair &p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

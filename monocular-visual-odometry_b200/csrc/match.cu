@@ -188,6 +188,7 @@ int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d
   dim3 grid(qtiles, nsplit), block(kQ);
   const uint4 *a = (const uint4 *)d_d1, *b = (const uint4 *)d_d2;
   const float2 *xa = (const float2 *)d_xy1, *xb = (const float2 *)d_xy2;
+  KTimer kt(ctx, KC_MATCH);
   if (mode == 0)
     match_kernel<0><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys);
   else if (mode == 1)

@@ -12,6 +12,11 @@
 
 struct mvo_ctx;
 
+// kernel classes for the optional CUDA-event timing (mvo_timing_*)
+enum MvoKernelClass { KC_GRAY = 0, KC_RESIZE, KC_FAST, KC_SELECT, KC_BLUR, KC_DESCRIBE, KC_HARRIS, KC_MATCH,
+                      KC_PNP_HYP, KC_PNP_SCORE, KC_PNP_FINISH, KC_BA, KC_COUNT };
+struct MvoEvPair { int id; cudaEvent_t a, b; };
+
 // ---- error plumbing -------------------------------------------------------------------
 int mvo_fail(mvo_ctx *ctx, int code, const char *fmt, ...);
 #define MVO_CUDA(ctx, call)                                                              \
@@ -89,6 +94,13 @@ struct mvo_ctx {
   DevBuf match_part, match_tickets, match_in, match_keys;
   PinBuf match_h;
 
+  // timing
+  uint32_t timing_mask = 0;
+  std::vector<MvoEvPair> ev_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double t_ms[KC_COUNT] = {0};
+  uint64_t t_cnt[KC_COUNT] = {0};
+
   // PnP
   DevBuf pnp_pts, pnp_hyp, pnp_cnt, pnp_out;
   int pnp_last_h = 0;
@@ -96,10 +108,22 @@ struct mvo_ctx {
   DevBuf ba_buf;
 };
 
+// RAII event pair around the launches of one kernel class (no-op unless enabled in timing_mask)
+struct KTimer {
+  mvo_ctx *c;
+  int id;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KTimer(mvo_ctx *ctx, int kernel_class);
+  ~KTimer();
+};
+
 int mvo_reserve(mvo_ctx *ctx, DevBuf &b, size_t bytes);
 int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
+// mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)
+int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
+                       int on_device, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);
 
 // ---- stage entry points (host-side launchers, all asynchronous on ctx->stream) -----------
 // match.cu

@@ -675,6 +675,7 @@ static int upload_gauss(mvo_ctx *ctx) {
 int orb_launch_gray(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, int channels, size_t stride,
                     size_t frame_stride, uint8_t *planes, int batch) {
   dim3 grid((plan.lv[0].pitch / 4 + 127) / 128, plan.rows, batch);
+  KTimer kt(ctx, KC_GRAY);
   k_gray<<<grid, 128, 0, ctx->stream>>>(plan, d_in, channels, stride, frame_stride, planes);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
@@ -683,6 +684,7 @@ int orb_launch_gray(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, i
 int orb_launch_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const int32_t *tables, uint8_t *planes, int batch) {
   for (int l = 1; l < plan.nlevels; ++l) {
     dim3 grid((plan.lv[l].pitch / 4 + 127) / 128, plan.lv[l].h, batch);
+    KTimer kt(ctx, KC_RESIZE);
     k_resize<<<grid, 128, 0, ctx->stream>>>(plan, l, tables, planes);
     MVO_CHECK_LAUNCH(ctx);
   }
@@ -707,6 +709,7 @@ int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes,
   if (smem > 48 * 1024)
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(plan.total_bands, batch);
+  KTimer kt(ctx, KC_FAST);
   k_fast<<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
@@ -720,6 +723,7 @@ int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *stag
   if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "selection grid too large");
   if (smem > 48 * 1024)
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KTimer kt(ctx, KC_SELECT);
   k_select<<<batch, 1024, smem, ctx->stream>>>(plan, staging, bandcnt, cand, sel, meta);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
@@ -729,6 +733,7 @@ int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int b
   MVO_TRY(upload_gauss(ctx));
   for (int l = 0; l < plan.nlevels; ++l) {
     dim3 grid((plan.lv[l].w + BLUR_TW - 1) / BLUR_TW, (plan.lv[l].h + BLUR_TH - 1) / BLUR_TH, batch);
+    KTimer kt(ctx, KC_BLUR);
     k_blur<<<grid, 256, 0, ctx->stream>>>(plan, l, planes);
     MVO_CHECK_LAUNCH(ctx);
   }
@@ -738,6 +743,7 @@ int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int b
 int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint32_t *cand,
                           const OrbFrameMeta *meta, float *harris, int batch) {
   dim3 grid(2 * ctx->sm_count, batch);
+  KTimer kt(ctx, KC_HARRIS);
   k_harris_all<<<grid, 256, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
@@ -748,6 +754,7 @@ int orb_launch_describe_sel(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t 
                             int32_t *counts, int out_cap, int with_desc, int batch) {
   const int blocks = (plan.max_kpts + 1 + DESC_WARPS - 1) / DESC_WARPS;
   dim3 grid(blocks < 1 ? 1 : blocks, batch);
+  KTimer kt(ctx, KC_DESCRIBE);
   k_describe<0><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, sel, meta, n_override, nullptr, 0, kpts,
                                                            desc, counts, out_cap, with_desc, nullptr);
   MVO_CHECK_LAUNCH(ctx);
@@ -758,6 +765,7 @@ int orb_launch_describe_kpts(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t
                              int n, uint8_t *desc, int32_t *bad_flag) {
   if (n <= 0) return MVO_OK;
   dim3 grid((n + DESC_WARPS - 1) / DESC_WARPS, 1);
+  KTimer kt(ctx, KC_DESCRIBE);
   k_describe<1><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, nullptr, nullptr, nullptr, kpts, n, nullptr,
                                                            desc, nullptr, 0, 1, bad_flag);
   MVO_CHECK_LAUNCH(ctx);

@@ -288,7 +288,7 @@ int upload_image(mvo_ctx *ctx, const uint8_t *image, int rows, size_t stride, ui
 
 // detect (+ optionally describe) one host image; results to host arrays
 int extract_host(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
-                 mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, bool with_desc) {
+                 mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, bool with_desc, bool on_device = false) {
   MVO_TRY(check_image(ctx, image, rows, cols, channels, stride));
   if (!n_kpts || (*n_kpts > 0 && !kpts) || (with_desc && *n_kpts > 0 && !desc))
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
@@ -303,7 +303,8 @@ int extract_host(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int cha
   const size_t img_bytes = ((size_t)rows * stride + 255) & ~(size_t)255;
   const size_t out_bytes = (size_t)out_cap * (sizeof(mvo_keypoint) + 32) + 256;
   MVO_TRY(mvo_reserve_pinned(ctx, ctx->orb_h, img_bytes + out_bytes + 512));
-  MVO_TRY(upload_image(ctx, image, rows, stride, &d_in));
+  if (on_device) d_in = const_cast<uint8_t *>(image);
+  else MVO_TRY(upload_image(ctx, image, rows, stride, &d_in));
   MVO_TRY(mvo_reserve(ctx, ctx->orb_kpts, (size_t)out_cap * sizeof(mvo_keypoint) + (size_t)out_cap * 32 + 512));
   mvo_keypoint *d_k = (mvo_keypoint *)ctx->orb_kpts.p;
   uint8_t *d_d = (uint8_t *)ctx->orb_kpts.p + (((size_t)out_cap * sizeof(mvo_keypoint) + 255) & ~(size_t)255);
@@ -343,6 +344,11 @@ int extract_host(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int cha
 }
 
 }  // namespace
+
+int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
+                       int on_device, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
+  return extract_host(ctx, image, rows, cols, channels, stride, kpts, n_kpts, desc, true, on_device != 0);
+}
 
 void orb_state_free(mvo_ctx *ctx) {
   for (size_t i = 0; i < g_states.size(); ++i)

@@ -581,15 +581,18 @@ int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, i
   MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
-  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, cam, ctx->prm.pnp_seed, H, w.poses, w.valid);
+  { KTimer kt(ctx, KC_PNP_HYP);
+  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
   MVO_CHECK_LAUNCH(ctx);
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pnp_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (H + 7) / 8;
   if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
-  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.valid, w.counts);
+  { KTimer kt(ctx, KC_PNP_SCORE);
+  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.valid, w.counts); }
   MVO_CHECK_LAUNCH(ctx);
+  { KTimer kt(ctx, KC_PNP_FINISH);
   k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
-                                             w.pose_io, w.out_i, w.inl);
+                                             w.pose_io, w.out_i, w.inl); }
   MVO_CHECK_LAUNCH(ctx);
   ctx->pnp_last_h = H;
   uint8_t *hout = (uint8_t *)ctx->h_b.p + (size_t)n * 20;
@@ -644,8 +647,9 @@ int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, 
   MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(w.pose_io, h_pose, 96, cudaMemcpyHostToDevice, ctx->stream));
+  { KTimer kt(ctx, KC_PNP_FINISH);
   k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, 0.0, 0, nullptr, nullptr, 1, ctx->prm.pnp_refine_iters,
-                                             w.pose_io, w.out_i, w.inl);
+                                             w.pose_io, w.out_i, w.inl); }
   MVO_CHECK_LAUNCH(ctx);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -39,6 +39,19 @@ class Params(C.Structure):
     ]
 
 
+class TrackParams(C.Structure):
+    _fields_ = [("match_method", C.c_int32), ("match_radius", C.c_float), ("min_pnp_points", C.c_int32),
+                ("max_dist_to_prev", C.c_double), ("min_dist_keyframe", C.c_double), ("ba_enable", C.c_int32),
+                ("ba_window", C.c_int32), ("ba_fix_points", C.c_int32), ("information", C.c_double * 4),
+                ("buffer_size", C.c_int32)]
+
+
+class TrackResult(C.Structure):
+    _fields_ = [("n_keypoints", C.c_int32), ("n_candidates", C.c_int32), ("n_matches", C.c_int32),
+                ("n_inliers", C.c_int32), ("pnp_ok", C.c_int32), ("ba_frames", C.c_int32), ("ba_edges", C.c_int32),
+                ("pad", C.c_int32), ("T_w_c_pnp", C.c_double * 16)]
+
+
 class MvoError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
@@ -75,6 +88,17 @@ SIGNATURES = {
     "mvo_pnp_refine": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "mvo_bundle_adjustment": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "mvo_optimize_single_frame": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
+    "mvo_default_track_params": (None, [C.POINTER(TrackParams)]),
+    "mvo_tracker_create": (_i, [_vp, _vp, _i, _i, C.POINTER(TrackParams), C.POINTER(_vp)]),
+    "mvo_tracker_destroy": (None, [_vp]),
+    "mvo_tracker_set_map": (_i, [_vp, _vp, _vp, _i]),
+    "mvo_tracker_reset": (_i, [_vp, _vp]),
+    "mvo_tracker_track": (_i, [_vp, _vp, _i, _sz, _i, _vp, C.POINTER(TrackResult)]),
+    "mvo_tracker_frame_pose": (_i, [_vp, _i, _vp]),
+    "mvo_kernel_classes": (_i, []),
+    "mvo_kernel_name": (C.c_char_p, [_i]),
+    "mvo_timing_enable": (_i, [_vp, C.c_uint32]),
+    "mvo_timing_read": (_i, [_vp, _vp, _vp]),
 }
 
 _lib = None
@@ -286,6 +310,85 @@ class Context:
         self._chk(self.lib.mvo_optimize_single_frame(self.h, _ptr(pose), _ptr(pts), _ptr(ob), len(pts), _ptr(K),
                                                       int(fix_points), int(update_points)))
         return pose.reshape(4, 4), pts
+
+
+class Tracker:
+    """mvo_tracker: the per-frame tracking step (extract -> match map -> PnP -> BA)."""
+
+    def __init__(self, ctx: Context, K, rows, cols, **overrides):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        p = TrackParams()
+        self.lib.mvo_default_track_params(C.byref(p))
+        for k, v in overrides.items():
+            if k == "information":
+                for i, x in enumerate(np.asarray(v, np.float64).ravel()):
+                    p.information[i] = float(x)
+            else:
+                if not hasattr(p, k):
+                    raise AttributeError(k)
+                setattr(p, k, v)
+        self.params = p
+        self.rows, self.cols = rows, cols
+        K = _c(K, np.float64)
+        h = C.c_void_p()
+        ctx._chk(self.lib.mvo_tracker_create(ctx.h, _ptr(K), rows, cols, C.byref(p), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mvo_tracker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, pts3d, desc):
+        p, d = _c(pts3d, np.float32), _c(desc, np.uint8)
+        self.ctx._chk(self.lib.mvo_tracker_set_map(self.h, _ptr(p), _ptr(d), len(p)))
+
+    def reset(self, T_w_c_ref):
+        T = _c(T_w_c_ref, np.float64)
+        self.ctx._chk(self.lib.mvo_tracker_reset(self.h, _ptr(T)))
+
+    def track(self, image, channels=None, stride=None, on_device=False):
+        """image: numpy array (host) or an integer device pointer (with channels/stride given)."""
+        T = np.zeros(16)
+        res = TrackResult()
+        if on_device:
+            ptr = C.c_void_p(int(image))
+        else:
+            img = np.ascontiguousarray(image, np.uint8)
+            channels = 1 if img.ndim == 2 else img.shape[2]
+            stride = img.shape[1] * channels
+            ptr = _ptr(img)
+        self.ctx._chk(self.lib.mvo_tracker_track(self.h, ptr, channels, stride, int(on_device), _ptr(T), C.byref(res)))
+        return T.reshape(4, 4), res
+
+    def frame_pose(self, k=0):
+        T = np.zeros(16)
+        self.ctx._chk(self.lib.mvo_tracker_frame_pose(self.h, k, _ptr(T)))
+        return T.reshape(4, 4)
+
+
+def kernel_names():
+    lib = load_library()
+    return [lib.mvo_kernel_name(i).decode() for i in range(lib.mvo_kernel_classes())]
+
+
+def timing_enable(ctx: Context, mask: int):
+    ctx._chk(ctx.lib.mvo_timing_enable(ctx.h, mask))
+
+
+def timing_read(ctx: Context):
+    n = ctx.lib.mvo_kernel_classes()
+    ms = np.zeros(n)
+    cnt = np.zeros(n, np.uint64)
+    ctx._chk(ctx.lib.mvo_timing_read(ctx.h, _ptr(ms), _ptr(cnt)))
+    return ms, cnt
 
 
 def remove_duplicated_matches(matches):
