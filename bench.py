@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the per-frame VO hot path on B200.
+
+A STEP is one tracked frame: ORB extract + grid-NMS (640x480, max 2000+1 keypoints) -> Hamming
+match of the visible map points against the frame -> batched RANSAC PnP (4096 hypotheses) ->
+bundle adjustment over the newest 5 frames (10 LM iterations), i.e. mvo_tracker_track().
+
+  value   frames/s with the frame images already resident in HBM (160 device copies = 147 MB,
+          larger than the 126 MB L2, cycled so no frame is re-read from cache)
+  e2e     the same metric through the C ABI with HOST images: the H2D copy of every frame and
+          the D2H read of its pose are inside the timed region
+  --impl reference   the reference's own CPU path on the host cores: cv2 (the OpenCV the
+          reference calls) for ORB / matching / solvePnPRansac + oracle/ba_oracle.c (g2o
+          restated); the reference binary itself cannot be built here (no OpenCV C++/g2o/...)
+
+One JSON line on stdout (rank 0).  Launch for N > 1:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P bench.py --gpus N --steps K --warmup W
+Multi-GPU = independent sequences per GPU (replicas only): NCCL only carries the
+per-rank timings (all_reduce MAX).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python"))
+sys.path.insert(0, str(ROOT))
+
+W, H = 640, 480
+N_DISTINCT = 16          # distinct rendered frames per sequence (ping-pong trajectory)
+N_DEVICE_COPIES = 160    # device-resident frame slots: 160 x 921,600 B = 147 MB > L2 (126 MB)
+MAX_KPTS = 2000
+BA_ITERS = 10
+METRIC = "VO frames/sec @ 640x480, 2000 kpts, 5-frame BA"
+WORKLOAD = ("tracked frame: ORB extract+grid-NMS 640x480 (<=2001 kpts) + Hamming match vs map + RANSAC PnP "
+            "(4096 hyp, 2 px) + 5-frame BA (10 LM it, Huber, fixed map points as shipped)")
+
+# Algorithmic bytes per launch of each kernel class for ONE 640x480 frame (DESIGN.md §Kernels;
+# SURVEY.md §8d gives the per-frame ORB figure 1,041,660 B = BGR in + keypoints + descriptors out).
+PYR_PX = 640 * 480 + 533 * 400 + 444 * 333 + 370 * 278          # 771,112 gray pixels over 4 levels
+ALGO_BYTES = {
+    "k_gray": 640 * 480 * 3 + 640 * 480,
+    "k_resize": None,                                            # 3 launches of different size: see DESIGN.md
+    "k_fast": PYR_PX + 4 * 7300,                                  # read every level once + packed candidates out
+    "k_select": 2 * 4 * 7300 + 8 * 2001,
+    "k_blur": None,
+    "k_describe": 2001 * (31 * 31 + 512) + 2001 * (28 + 32),
+    "match_kernel": 32 * (2001 + 2001) + 4 * 2001,
+    "k_pnp_hypotheses": 20 * 2000 + 96 * 4096,
+    "k_pnp_score": 20 * 2000 + 100 * 4096,
+    "k_pnp_finish": 20 * 2000 + 4 * 4096,
+    "k_ba": 10000 * 16 + 2000 * 24 + 5 * 96,
+}
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def nvml_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    ids = [v for v in vis.split(",") if v.strip()]
+    if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+        return int(ids[local_rank])
+    return local_rank
+
+
+def build_sequence(seed):
+    """16 distinct frames of a textured plane + ground-truth poses; visiting order is a ping-pong."""
+    import mvo_synth
+    frames, T_c_w, _ = mvo_synth.planar_sequence(seed, n_frames=N_DISTINCT, plane_z=4.0)
+    imgs = [mvo_synth.gray_to_bgr(f) for f in frames]
+    order = list(range(1, N_DISTINCT)) + list(range(N_DISTINCT - 2, 0, -1))      # 1..15,14..1 then repeat
+    return imgs, [np.linalg.inv(T) for T in T_c_w], order
+
+
+def map_from_first_frame(kp, plane_z=4.0):
+    import mvo_synth
+    Ki = np.linalg.inv(mvo_synth.K_DEFAULT)
+    rays = (Ki @ np.stack([kp["x"], kp["y"], np.ones(len(kp))]).astype(np.float64)).T
+    return (rays * (plane_z / rays[:, 2:3])).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU path (cv2 + restated g2o) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import cv2
+    import mvo_synth
+    from oracle import vo_oracle
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    imgs, T_true, order = build_sequence(0)
+    trk = vo_oracle.CpuTracker(mvo_synth.K_DEFAULT, H, W, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
+    kp0, desc0 = trk.extract(imgs[0])
+    trk.set_map(map_from_first_frame(kp0), desc0)
+    trk.reset(np.eye(4))
+    for i in range(args.warmup):
+        trk.track(imgs[order[i % len(order)]])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        trk.track(imgs[order[(args.warmup + i) % len(order)]])
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = (f"{args.steps} tracked frames of sequence seed 0 (cv2 {cv2.__version__} ORB detect/compute, exact Hamming "
+              f"matcher restated in C++, cv2.solvePnPRansac(100 it, 2 px, 0.999), oracle/ba_oracle.c g2o restatement, "
+              f"5-frame window, {BA_ITERS} LM it); reference binary not buildable here")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": 1, "image": "640x480 BGR u8"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cv2.getNumThreads(), "host_cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- own arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import mvo_b200
+    import mvo_synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = mvo_b200.Context(local_rank, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
+    ctx.set_stream(stream.cuda_stream)
+    K = mvo_synth.K_DEFAULT
+
+    imgs, T_true, order = build_sequence(rank)          # one independent sequence per rank / GPU
+    kp0, desc0 = ctx.orb_extract(imgs[0])
+    map_pts = map_from_first_frame(kp0)
+    trk = mvo_b200.Tracker(ctx, K, H, W)
+    trk.set_map(map_pts, desc0)
+    trk.reset(np.eye(4))
+
+    # device-resident frame slots (> L2) and pinned host frames
+    d_frames = torch.empty((N_DEVICE_COPIES, H, W, 3), dtype=torch.uint8, device="cuda")
+    h_frames = [torch.from_numpy(im).pin_memory() for im in imgs]
+    for s in range(N_DEVICE_COPIES):
+        d_frames[s].copy_(h_frames[order[s % len(order)]], non_blocking=True)
+    torch.cuda.synchronize()
+    frame_bytes = H * W * 3
+
+    def step_dev(i):
+        s = i % N_DEVICE_COPIES
+        return trk.track(d_frames[s].data_ptr(), channels=3, stride=W * 3, on_device=True)
+
+    def step_host(i):
+        return trk.track(h_frames[order[i % len(order)]].numpy())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, n, first):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = None
+        for i in range(n):
+            last = step_fn(first + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    # warm-up (>= 3), then a calibration pass with every kernel class timed to find the dominant one
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step_dev(i)
+    names = mvo_b200.kernel_names()
+    mvo_b200.timing_enable(ctx, (1 << len(names)) - 1)
+    mvo_b200.timing_read(ctx)
+    ncal = min(32, max(8, args.steps))
+    for i in range(ncal):
+        step_dev(warm + i)
+    ms_k, cnt_k = mvo_b200.timing_read(ctx)
+    stages = {names[k]: {"us_per_frame": 1e3 * ms_k[k] / ncal, "launches_per_frame": float(cnt_k[k]) / ncal}
+              for k in range(len(names)) if cnt_k[k]}
+    dominant = max(stages, key=lambda k: stages[k]["us_per_frame"])
+    mvo_b200.timing_enable(ctx, 1 << names.index(dominant))
+
+    # ---- timed region: K steps, images resident in HBM ----
+    sampler = ClockSampler(nvml_index(local_rank))
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    first = warm + ncal
+    ms, (T_last, res_last) = timed(step_dev, args.steps, first)
+    launches = ctx.kernel_launches - launches0
+    ms_d, cnt_d = mvo_b200.timing_read(ctx)
+    kd = names.index(dominant)
+    dom_us = 1e3 * ms_d[kd] / max(int(cnt_d[kd]), 1)
+    mvo_b200.timing_enable(ctx, 0)
+    clocks = sampler.stop()
+
+    # ---- e2e: host images through the C ABI, H2D + D2H inside the timed region ----
+    trk.reset(np.eye(4))
+    for i in range(warm):
+        step_host(i)
+    ms_e2e, _ = timed(step_host, args.steps, warm)
+
+    # sanity: the pipeline is really tracking (not timing failures)
+    ok = bool(res_last.pnp_ok) and res_last.n_inliers > 100
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        fps = world * args.steps / (ms / 1e3)
+        fps_e2e = world * args.steps / (ms_e2e / 1e3)
+        ab = ALGO_BYTES.get(dominant)
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get(dominant)
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": (ab / (dom_us * 1e-6) / 1e9) if ab else None,
+                "peak": peak, "unit": "GB/s", "frac": (ab / (dom_us * 1e-6) / 1e9 / peak) if ab else None,
+                "traffic": traffic, "us_per_launch": dom_us, "algorithmic_bytes_per_launch": ab, "peak_source": peak_src,
+                "note": "single-frame launches are latency/issue-bound, not HBM-bound (DESIGN.md §Roofline)"}
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": 1, "image": "640x480 BGR u8",
+                       "sequences": "one independent synthetic sequence per GPU (seed = rank)",
+                       "l2": f"{N_DEVICE_COPIES} device-resident frame slots = {N_DEVICE_COPIES * frame_bytes / 1e6:.0f} MB > 126 MB L2, cycled",
+                       "tracking_ok": ok, "last_frame": {"keypoints": res_last.n_keypoints, "matches": res_last.n_matches,
+                                                         "inliers": res_last.n_inliers, "ba_frames": res_last.ba_frames}},
+            "clocks": clocks,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 16 * 8 + 160,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "stages": stages,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    trk.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(n_frames=100):
+    """The same workload on the host cores (bounded sample), rank 0 / N=1 only."""
+    import cv2
+    import mvo_synth
+    from oracle import vo_oracle
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    imgs, _, order = build_sequence(0)
+    trk = vo_oracle.CpuTracker(mvo_synth.K_DEFAULT, H, W, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
+    kp0, desc0 = trk.extract(imgs[0])
+    trk.set_map(map_from_first_frame(kp0), desc0)
+    trk.reset(np.eye(4))
+    for i in range(3):
+        trk.track(imgs[order[i]])
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        trk.track(imgs[order[(3 + i) % len(order)]])
+    dt = time.perf_counter() - t0
+    return {"value": n_frames / dt, "unit": "frames/s", "cores": cv2.getNumThreads(), "host_cores": cores, "kind": "port",
+            "sample": f"{n_frames} tracked frames of sequence seed 0: cv2 {cv2.__version__} ORB/solvePnPRansac (the OpenCV routines "
+                      f"the reference calls), exact Hamming matcher + g2o BA restated in C (oracle/), {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

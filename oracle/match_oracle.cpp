@@ -132,6 +132,22 @@ int orc_match_features(const uint8_t *d1, int n1, const uint8_t *d2, int n2, int
   return orc_remove_duplicated_matches(out, n);
 }
 
+// feature_match.cpp:179-196 + :229 applied to an externally computed nearest-neighbour list
+// (lets the CPU baseline use cv::BFMatcher — bit-identical to orc_hamming_nn — for the search).
+int orc_threshold_and_dedup(OrcDMatch *all, int na, double xiang_gao_ratio) {
+  double min_dis = 9999999, max_dis = 0;
+  for (int i = 0; i < na; i++) {
+    double dist = all[i].distance;
+    if (dist < min_dis) min_dis = dist;
+    if (dist > max_dis) max_dis = dist;
+  }
+  double distance_threshold = std::max<float>(min_dis * xiang_gao_ratio, 30.0);
+  int n = 0;
+  for (int i = 0; i < na; i++)
+    if (all[i].distance < distance_threshold) all[n++] = all[i];
+  return orc_remove_duplicated_matches(all, n);
+}
+
 // feature_match.cpp:51-84 (grid dims from this call's image size).
 int orc_select_uniform_kpts_by_grid(OrcKeyPoint *kp, int n, int image_rows, int image_cols,
                                     int max_num_keypoints, int grid_size, int max_pts_per_grid) {

@@ -80,6 +80,13 @@ def match_features(d1, d2, method_index, xy1=None, xy2=None, radius=0.0, xiang_g
     return out[:n].copy()
 
 
+def threshold_and_dedup(all_matches, xiang_gao_ratio=2.0):
+    m = np.ascontiguousarray(all_matches, DMATCH_DTYPE).copy()
+    lib().orc_threshold_and_dedup.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    n = lib().orc_threshold_and_dedup(_p(m), len(m), xiang_gao_ratio)
+    return m[:n].copy()
+
+
 def remove_duplicated_matches(m):
     m = np.ascontiguousarray(m, DMATCH_DTYPE).copy()
     n = lib().orc_remove_duplicated_matches(_p(m), len(m))

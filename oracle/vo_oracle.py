@@ -74,7 +74,14 @@ class CpuTracker:
             self.frames.pop(0)
         cand_idx, cand_xy = self.candidates(frame["T"])
         kp_xy = np.stack([kp["x"], kp["y"]], 1) if len(kp) else np.zeros((0, 2), np.float32)
-        if len(cand_idx) and len(kp):
+        if len(cand_idx) and len(kp) and self.match_method == 1:
+            # cv::BFMatcher(NORM_HAMMING).match is the exact search the reference's FLANN-LSH approximates; it is
+            # bit-identical to oracle_lib.hamming_nn (tests/test_match_oracle.py) and SIMD-optimised like the
+            # matcher the reference links, so the CPU baseline is not handicapped by a scalar loop
+            ms = self.bf.match(self.map_desc[cand_idx], desc)
+            allm = np.array([(x.queryIdx, x.trainIdx, x.imgIdx, x.distance) for x in ms], oracle_lib.DMATCH_DTYPE)
+            m = oracle_lib.threshold_and_dedup(allm)
+        elif len(cand_idx) and len(kp):
             m = oracle_lib.match_features(self.map_desc[cand_idx], desc, self.match_method, cand_xy, kp_xy, self.match_radius)
         else:
             m = np.zeros(0, oracle_lib.DMATCH_DTYPE)
