@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "mvo_internal.h"
@@ -82,7 +83,7 @@ __device__ void se3_update(const double *d, const double *in, double *out) {
   const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
   double a, b, c;
   if (th < 0.00001) { a = 1; b = 1; c = 1; }        // g2o's small-angle branch: R = V = I + O + O^2
-  else { a = sin(th) / th; b = (1 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
+  else { double sn, cs; sincos(th, &sn, &cs); const double ith = 1.0 / th; a = sn * ith; b = (1 - cs) * ith * ith; c = (th - sn) * ith * ith * ith; }
   const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
   double O2[9];
   for (int i = 0; i < 3; ++i)
@@ -156,6 +157,9 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
   double chi_init = 0;
   int it = 0;
   bool terminate = false;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // cycles per phase (thread 0), debug only
+  long long tmark = clock64();
+#define BA_MARK(i) do { const long long t_ = clock64(); ph[i] += t_ - tmark; tmark = t_; } while (0)
 
   for (; it < a.iters && !terminate; ++it) {
     __syncthreads();
@@ -264,7 +268,9 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
       else { for (int w = 0; w < BA_NW; ++w) s += s_wred[w * NA + i]; }
       s_partA[i] = s;
     }
+    BA_MARK(0);
     cluster.sync();                                                         // ---- barrier 1
+    BA_MARK(6);
     // ---------------- phase B: cluster reduction ----------------
     for (int i = tid; i < NA; i += BA_T) {
       double s = 0;
@@ -291,6 +297,7 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
     }
     __syncthreads();
     if (it == 0) chi_init = s_ctl[2];
+    BA_MARK(1);
 
     // ---------------- LM trials ----------------
     int qmax = 0;
@@ -359,7 +366,9 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
       if (tid == 0) s_partE[2] = 1.0;
       __syncthreads();
       if (!inv_ok) s_partE[2] = 0.0;                      // any thread that saw a singular Hll block
+      BA_MARK(2);
       cluster.sync();                                                       // ---- barrier 2
+      BA_MARK(6);
       // ---- phase D: assemble and solve the pose system (every CTA, identically) ----
       for (int o = tid; o < NC; o += BA_T) {
         double s = 0;
@@ -415,6 +424,7 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
         for (int i = tid; i < n; i += BA_T) s_dp[i] = 0;
       }
       __syncthreads();
+      BA_MARK(3);
       // ---- phase E: trial state, new chi2, gain denominator ----
       for (int f = tid; f < F; f += BA_T) {
         if (s_pidx[f] >= 0 && ok) se3_update(s_dp + 6 * s_pidx[f], s_pose + 12 * f, s_try + 12 * f);
@@ -460,7 +470,9 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
           s_partE[0] = cc; s_partE[1] = ss;
         }
       }
+      BA_MARK(4);
       cluster.sync();                                                       // ---- barrier 3
+      BA_MARK(6);
       // ---- phase F: gain ratio and LM control (g2o OptimizationAlgorithmLevenberg::solve) ----
       if (tid == 0) {
         double temp = 0, scale = 0;
@@ -500,6 +512,8 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
       }
       __syncthreads();
       ++qmax;
+      ph[7]++;
+      BA_MARK(5);
       // the trial loop re-reads s_ctl / pts pointers only on acceptance, which ends the loop
     } while (rho < 0 && qmax < 10);
     if (qmax == 10 || rho == 0) terminate = true;
@@ -512,6 +526,7 @@ __global__ void __launch_bounds__(BA_T, 1) k_ba(BaArgs a) {
     if (tid == 0) {
       a.stats[0] = chi_init; a.stats[1] = s_ctl[2]; a.stats[2] = it; a.stats[3] = s_ctl[0];
       a.pts_sel[0] = s_ctl[6] != 0 ? 1 : 0;
+      for (int q = 0; q < 8; ++q) a.stats[8 + q] = (double)ph[q];
     }
   }
 }
@@ -524,7 +539,327 @@ size_t ba_smem_doubles(int F, int nact, int pc) {
   return (size_t)F * 24 + 2 * NA + 4 + ((n + 3) & ~(size_t)3) + 4 + ((NC + 3) & ~(size_t)3) + u + 16;
 }
 
+// =========================================================================================
+// Pose-only variant (all map points fixed: the shipped is_ba_fix_map_points "true", and the final
+// refit of solvePnPRansac).  With the points fixed g2o's system is block diagonal: F independent
+// 6x6 pose blocks that share only the LM damping and the accept/reject decision.  Edge-parallel:
+// edges are stored frame-major with their (fixed) 3-D point, every thread of the cluster takes
+// edges e = gtid, gtid + 4096, ...; the 27 sums per frame (21 Hessian + 6 gradient) and the robust
+// chi2 are reduced by a warp shuffle tree per frame segment, then across warps in shared memory,
+// then across the 8 CTAs through distributed shared memory (every CTA reads all partials in rank
+// order, so all CTAs hold identical state and decide identically).  The pass that evaluates a trial
+// step also linearises at the trial point, so an accepted step needs no second pass: one pass and
+// one cluster barrier per LM trial.
+constexpr int PF_T = 512;
+constexpr int PF_NW = PF_T / 32;
+constexpr int PF_V = 28;                      // 21 H + 6 b + chi2 per frame
+
+struct PoseArgs {
+  int F, E, iters, fix_first, use_huber, chunk;    // E = padded edge count (multiple of chunk)
+  double fx, fy, cx, cy, i00, i01, i10, i11, huber, step_tol;
+  const int32_t *e_frame;   // [E] frame-major
+  const double *X;          // [E][3]
+  const double *obs;        // [E][2]
+  double *poses;            // F x 12 in/out
+  double *stats;            // 16
+};
+
+__device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/, const double *g, double lambda, double *x) {
+  // Cholesky with reciprocal diagonal (one rsqrt per column, no divisions on the dependent chain)
+  double L[21], inv[6];     // lower triangle, row-major packed: L[i*(i+1)/2 + j]
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double v = h[(j * (13 - j)) / 2 + (i - j)];
+      if (i == j) v += lambda;
+      L[i * (i + 1) / 2 + j] = v;
+    }
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = L[j * (j + 1) / 2 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+    if (!(d > 0) || !isfinite(d)) { ok = false; d = 1; }
+    double id = rsqrt(d);
+    id = id * (1.5 - 0.5 * d * id * id);          // one Newton step: full double accuracy
+    inv[j] = id;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s2 = L[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s2 -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      L[i * (i + 1) / 2 + j] = s2 * id;
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s2 = g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s2 -= L[i * (i + 1) / 2 + k] * y[k];
+    y[i] = s2 * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s2 = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s2 -= L[k * (k + 1) / 2 + i] * x[k];
+    x[i] = s2 * inv[i];
+  }
+  return ok;
+}
+
+// one pass over this CTA's edge chunks at poses `P` -> s_part[f*PF_V + q] (this CTA's partial sums).
+// Thread (rank, tid) owns chunk rank*PF_T + tid (+ k*csize*PF_T): `chunk` consecutive edges that all
+// belong to ONE frame (the host pads every frame's edge run to a multiple of `chunk` with frame -1),
+// so a thread accumulates its edges in registers and a warp does a single reduction per pass.
+__device__ void pose_pass(const PoseArgs &a, const double *P, double *s_wacc /*[PF_NW][F*PF_V]*/, double *s_part,
+                          unsigned rank, unsigned csize) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, F = a.F;
+  const int NV = F * PF_V;
+  for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
+  __syncthreads();
+  const int nchunks = a.E / a.chunk;                 // E is padded to a multiple of chunk
+  const int stride = (int)csize * PF_T;
+  for (int cbase = (int)rank * PF_T; cbase < nchunks; cbase += stride) {      // uniform trip count per CTA
+    const int c = cbase + tid;
+    double v[PF_V];
+#pragma unroll
+    for (int q = 0; q < PF_V; ++q) v[q] = 0;
+    int f = -1;
+    if (c < nchunks) {
+      const int e0 = c * a.chunk;
+      f = a.e_frame[e0];                              // -1: padding / masked chunk
+      if (f >= 0) {
+        const double *Rt = P + 12 * f;
+        for (int e = e0; e < e0 + a.chunk; ++e) {
+          if (a.e_frame[e] < 0) break;                // padding at the end of a frame's run
+          const double X0 = a.X[3 * e], X1 = a.X[3 * e + 1], X2 = a.X[3 * e + 2];
+          const double x = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+          const double y = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+          const double z = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+          const double iz = 1.0 / z;                  // the only division per edge
+          const double xz = x * iz, yz = y * iz;
+          const double e0r = a.obs[2 * e] - (a.fx * xz + a.cx), e1r = a.obs[2 * e + 1] - (a.fy * yz + a.cy);
+          const double Oe0 = a.i00 * e0r + a.i01 * e1r, Oe1 = a.i10 * e0r + a.i11 * e1r;
+          const double chi = e0r * Oe0 + e1r * Oe1;
+          double w = 1.0, rho = chi;
+          if (a.use_huber && chi > a.huber * a.huber) { const double sq = sqrt(chi); w = a.huber / sq; rho = 2 * sq * a.huber - a.huber * a.huber; }
+          v[27] += rho;
+          // EdgeProjectXYZ2UV::linearizeOplus, pose block (rows scaled by fx / fy)
+          const double fxz = a.fx * iz, fyz = a.fy * iz;
+          const double B[12] = {xz * yz * a.fx, -(1 + xz * xz) * a.fx, yz * a.fx, -fxz, 0, xz * fxz,
+                                (1 + yz * yz) * a.fy, -xz * yz * a.fy, -xz * a.fy, 0, -fyz, yz * fyz};
+          const double o00 = w * a.i00, o01 = w * a.i01, o10 = w * a.i10, o11 = w * a.i11;
+          const double r0 = -w * Oe0, r1 = -w * Oe1;
+          double OB[12];
+#pragma unroll
+          for (int q2 = 0; q2 < 6; ++q2) { OB[q2] = o00 * B[q2] + o01 * B[6 + q2]; OB[6 + q2] = o10 * B[q2] + o11 * B[6 + q2]; }
+          int q = 0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = r; cc < 6; ++cc) v[q++] += B[r] * OB[cc] + B[6 + r] * OB[6 + cc];
+#pragma unroll
+          for (int r = 0; r < 6; ++r) v[21 + r] += B[r] * r0 + B[6 + r] * r1;
+        }
+      }
+    }
+    // frame-segmented warp reduction: chunks are frame-major, so a warp spans one frame (rarely two)
+    unsigned todo = __ballot_sync(0xffffffffu, f >= 0);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int fl = __shfl_sync(0xffffffffu, f, leader);
+      const bool mine = f == fl;
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+      for (int q = 0; q < PF_V; ++q) {
+        double x = mine ? v[q] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == (q & 31)) s_wacc[warp * NV + fl * PF_V + q] += x;      // spread the smem updates over lanes
+      }
+      todo &= ~m;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < NV; i += PF_T) {
+    double s2 = 0;
+    for (int w = 0; w < PF_NW; ++w) s2 += s_wacc[w * NV + i];
+    s_part[i] = s2;
+  }
+}
+
+__global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
+  const int tid = threadIdx.x, F = a.F, NV = F * PF_V;
+  extern __shared__ __align__(16) double sm[];
+  double *s_pose = sm;                       // F*12
+  double *s_try = s_pose + F * 12;           // F*12
+  double *s_cur = s_try + F * 12;            // NV  linearisation at the current state
+  double *s_new = s_cur + NV;                // NV  linearisation at the trial state
+  double *s_part0 = s_new + NV;              // NV  partials, ping
+  double *s_part1 = s_part0 + NV;            // NV  partials, pong
+  double *s_dp = s_part1 + NV;               // F*6
+  double *s_wacc = s_dp + F * 6 + 2;         // PF_NW * NV
+  __shared__ double s_c[8];                  // 0 lambda 1 ni 2 chi 3 rho 4 accepted 5 ok 6 max step
+  __shared__ int s_okf[BA_MAXF];
+  for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i];
+  __syncthreads();
+  int parity = 0;
+  auto gather = [&](double *dst) {           // after the barrier: sum the partials of all CTAs in rank order
+    double *mine = parity ? s_part1 : s_part0;
+    cluster.sync();
+    for (int i = tid; i < NV; i += PF_T) {
+      double v[BA_CLUSTER];
+#pragma unroll
+      for (unsigned r = 0; r < BA_CLUSTER; ++r) v[r] = r < csize ? *cluster.map_shared_rank(mine + i, r) : 0.0;
+      double s2 = 0;
+#pragma unroll
+      for (unsigned r = 0; r < BA_CLUSTER; ++r) s2 += v[r];     // fixed rank order: identical in every CTA
+      dst[i] = s2;
+    }
+    parity ^= 1;
+    __syncthreads();
+  };
+  pose_pass(a, s_pose, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+  gather(s_cur);
+  if (tid == 0) {
+    double chi = 0, md = 0;
+    for (int f = 0; f < F; ++f) {
+      chi += s_cur[f * PF_V + 27];
+      if (!(a.fix_first && f == 0)) {
+        const double *h = s_cur + f * PF_V;
+        md = fmax(md, fmax(fmax(fabs(h[0]), fabs(h[6])), fmax(fmax(fabs(h[11]), fabs(h[15])), fmax(fabs(h[18]), fabs(h[20])))));
+      }
+    }
+    s_c[2] = chi;
+    s_c[0] = 1e-5 * md;        // computeLambdaInit
+    s_c[1] = 2;
+  }
+  __syncthreads();
+  const double chi_init = s_c[2];
+  int it = 0, trials = 0;
+  bool terminate = false;
+  long long ph[4] = {0, 0, 0, 0}, tmark = clock64();
+#define PF_MARK(i) do { const long long t_ = clock64(); ph[i] += t_ - tmark; tmark = t_; } while (0)
+  for (; it < a.iters && !terminate; ++it) {
+    int qmax = 0;
+    double rho = 0;
+    do {
+      const double lambda = s_c[0];
+      // per-frame 6x6 solve + trial pose (every CTA, identically)
+      if (tid < F) {
+        const int f = tid;
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        bool ok = true;
+        if (!(a.fix_first && f == 0)) {
+          ok = chol6_solve(s_cur + f * PF_V, s_cur + f * PF_V + 21, lambda, d);
+          if (ok) se3_update(d, s_pose + 12 * f, s_try + 12 * f);
+        }
+        if (!ok || (a.fix_first && f == 0))
+          for (int q = 0; q < 12; ++q) s_try[12 * f + q] = s_pose[12 * f + q];
+        for (int q = 0; q < 6; ++q) s_dp[6 * f + q] = ok ? d[q] : 0.0;
+        s_okf[f] = ok;
+      }
+      __syncthreads();
+      PF_MARK(0);
+      pose_pass(a, s_try, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+      PF_MARK(1);
+      gather(s_new);
+      PF_MARK(2);
+      if (tid == 0) {
+        bool ok = true;
+        double temp = 0, scale = 0, mstep = 0;
+        for (int f = 0; f < F; ++f) {
+          ok = ok && s_okf[f];
+          temp += s_new[f * PF_V + 27];
+          if (a.fix_first && f == 0) continue;
+          for (int q = 0; q < 6; ++q) {
+            const double dq = s_dp[6 * f + q];
+            scale += dq * (lambda * dq + s_cur[f * PF_V + 21 + q]);     // computeScale with the CURRENT b
+            mstep = fmax(mstep, fabs(dq));
+          }
+        }
+        if (!ok) temp = 1.7976931348623157e308;
+        const double r_ = (s_c[2] - temp) / (scale + 1e-3);
+        if (r_ > 0 && isfinite(temp)) {
+          const double tr = 2 * r_ - 1;
+          double alpha = 1. - tr * tr * tr;
+          alpha = fmin(alpha, 2. / 3.);
+          s_c[0] = lambda * fmax(1. / 3., alpha);
+          s_c[1] = 2;
+          s_c[2] = temp;
+          s_c[4] = 1;
+        } else {
+          s_c[0] = lambda * s_c[1];
+          s_c[1] *= 2;
+          s_c[4] = 0;
+        }
+        s_c[3] = r_;
+        s_c[6] = mstep;
+      }
+      __syncthreads();
+      rho = s_c[3];
+      if (s_c[4] != 0) {
+        for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = s_try[i];
+        for (int i = tid; i < NV; i += PF_T) s_cur[i] = s_new[i];
+      }
+      __syncthreads();
+      ++qmax;
+      ++trials;
+      PF_MARK(3);
+    } while (rho < 0 && qmax < 10);
+    if (qmax == 10 || rho == 0) terminate = true;
+    if (a.step_tol > 0 && s_c[4] != 0 && s_c[6] < a.step_tol) terminate = true;    // optional early exit (PnP refit)
+  }
+  cluster.sync();       // nobody leaves while a neighbour may still read its partials
+  if (rank == 0) {
+    for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = s_pose[i];
+    if (tid == 0) { a.stats[0] = chi_init; a.stats[1] = s_c[2]; a.stats[2] = it; a.stats[3] = s_c[0]; a.stats[15] = trials; for (int q = 0; q < 4; ++q) a.stats[8 + q] = (double)ph[q]; }
+  }
+}
+
+size_t pose_smem_doubles(int F) { return (size_t)F * 24 + 4 * (size_t)F * PF_V + (size_t)F * 6 + 2 + (size_t)PF_NW * F * PF_V + 8; }
+
 }  // namespace
+
+// Launch the pose-only LM on device-resident edge arrays (also used by the PnP refit).
+int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_eframe, const double *d_X, const double *d_obs, double fx, double fy,
+                       double cx, double cy, const double *info, int iters, int use_huber, double huber, int fix_first,
+                       double step_tol, double *d_poses, double *d_stats) {
+  PoseArgs a;
+  a.chunk = chunk;
+  a.F = F; a.E = E; a.iters = iters; a.fix_first = fix_first; a.use_huber = use_huber;
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+  a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
+  a.huber = huber; a.step_tol = step_tol;
+  a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
+  const size_t smem = pose_smem_doubles(F) * sizeof(double);
+  if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: shared memory %zu B", smem);
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_ba_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(BA_CLUSTER);
+  cfg.blockDim = dim3(PF_T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = BA_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    KTimer kt(ctx, KC_BA);
+    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_ba_pose, a));
+  }
+  ctx->launches++;
+  return MVO_OK;
+}
 
 // Shared driver for bundleAdjustment and optimizeSingleFrame.
 static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P, const int32_t *edge_frame,
@@ -543,6 +878,77 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   const int nact = F - fix_first;
   if (E == 0 || iterations == 0 || (nact == 0 && fix_points)) return MVO_OK;      // nothing to optimise
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  if (fix_points) {
+    // ---- pose-only LM: edges frame-major (stable), each with its fixed 3-D point ----
+    std::vector<int32_t> order(E), fstart(F + 1, 0);
+    for (int k = 0; k < E; ++k) fstart[edge_frame[k] + 1]++;
+    for (int f = 0; f < F; ++f) fstart[f + 1] += fstart[f];
+    {
+      std::vector<int32_t> cur(fstart.begin(), fstart.begin() + F);
+      for (int k = 0; k < E; ++k) order[cur[edge_frame[k]]++] = k;
+    }
+    // chunk = edges per thread so that all chunks fit one sweep of the 8 x 512 threads
+    int chunk = 1;
+    while ((long)(E + (long)F * (chunk - 1)) > (long)chunk * BA_CLUSTER * PF_T && chunk < 64) ++chunk;
+    int Ep = 0;
+    for (int f = 0; f < F; ++f) Ep += ((fstart[f + 1] - fstart[f] + chunk - 1) / chunk) * chunk;
+    auto al2 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t o_fr = o;   o = al2(o + (size_t)Ep * 4 + 4);
+    const size_t o_X = o;    o = al2(o + (size_t)Ep * 24 + 24);
+    const size_t o_obs = o;  o = al2(o + (size_t)Ep * 16 + 16);
+    const size_t o_pose = o; o = al2(o + (size_t)F * 96);
+    const size_t in_end = o;
+    const size_t o_stats = o; o = al2(o + 256);
+    MVO_TRY(mvo_reserve(ctx, ctx->ba_buf, o));
+    MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, o + 256));
+    uint8_t *h = (uint8_t *)ctx->h_a.p, *d = (uint8_t *)ctx->ba_buf.p;
+    int32_t *hf = (int32_t *)(h + o_fr);
+    double *hX = (double *)(h + o_X), *hobs = (double *)(h + o_obs), *hpose = (double *)(h + o_pose);
+    {
+      int w = 0;
+      for (int f = 0; f < F; ++f) {
+        for (int i = fstart[f]; i < fstart[f + 1]; ++i, ++w) {
+          const int k = order[i];
+          hf[w] = f;
+          const float *p = points + 3 * (size_t)edge_point[k];
+          hX[3 * w] = p[0]; hX[3 * w + 1] = p[1]; hX[3 * w + 2] = p[2];
+          hobs[2 * w] = obs[2 * k]; hobs[2 * w + 1] = obs[2 * k + 1];
+        }
+        for (; w % chunk; ++w) { hf[w] = -1; hX[3 * w] = hX[3 * w + 1] = 0; hX[3 * w + 2] = 1; hobs[2 * w] = hobs[2 * w + 1] = 0; }
+      }
+    }
+    for (int f = 0; f < F; ++f) {                                 // g2o_ba.cpp:183-190: world->camera = (T_w_c)^-1
+      const double *T = poses_T_w_c + 16 * f;
+      double *q = hpose + 12 * f;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) q[i * 3 + j] = T[j * 4 + i];
+        q[9 + i] = -(T[0 * 4 + i] * T[3] + T[1 * 4 + i] * T[7] + T[2 * 4 + i] * T[11]);
+      }
+    }
+    MVO_CUDA(ctx, cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_TRY(mvo_ba_pose_launch(ctx, F, Ep, chunk, (const int32_t *)(d + o_fr), (const double *)(d + o_X), (const double *)(d + o_obs),
+                               K[0], K[0], K[2], K[5], info, iterations, use_huber && ctx->prm.ba_huber_delta > 0,
+                               ctx->prm.ba_huber_delta, fix_first, 0.0, (double *)(d + o_pose), (double *)(d + o_stats)));
+    double *h_stats = (double *)(h + o_stats);
+    MVO_CUDA(ctx, cudaMemcpyAsync(hpose, d + o_pose, (size_t)F * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h_stats, d + o_stats, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < F; ++f) {                                 // g2o_ba.cpp:298-305
+      const double *p = hpose + 12 * f;
+      double *T = poses_T_w_c + 16 * f;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[i * 4 + j] = p[j * 3 + i];
+        T[i * 4 + 3] = -(p[i] * p[9] + p[3 + i] * p[10] + p[6 + i] * p[11]);
+      }
+      T[12] = T[13] = T[14] = 0;
+      T[15] = 1;
+    }
+    if (stats) memcpy(stats, h_stats, 32);
+    if (getenv("MVO_BA_DEBUG")) fprintf(stderr, "k_ba_pose: F=%d E=%d it=%.0f trials=%.0f cycles solve=%.0f pass=%.0f gather=%.0f decide=%.0f\n", F, E, h_stats[2], h_stats[15], h_stats[8], h_stats[9], h_stats[10], h_stats[11]);
+    return MVO_OK;
+  }
 
   // CSR by point, edges of a point ordered by frame (stable in the caller's order otherwise)
   std::vector<int32_t> pt_start(P + 2, 0), e_fr(E);
@@ -587,7 +993,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   const size_t o_bl = o;    o = al(o + (size_t)P * 24 + 24);
   const size_t o_hinv = o;  o = al(o + (size_t)P * 48 + 48);
   const size_t o_wd = o;    o = al(o + (fix_points ? 8 : (size_t)P * F * 144 + 144));
-  const size_t o_stats = o; o = al(o + 64);
+  const size_t o_stats = o; o = al(o + 256);
   MVO_TRY(mvo_reserve(ctx, ctx->ba_buf, o));
   MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, in_end + 4096));
   uint8_t *h = (uint8_t *)ctx->h_a.p, *d = (uint8_t *)ctx->ba_buf.p;
@@ -607,7 +1013,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   a.pt_start = (const int32_t *)(d + o_start); a.e_frame = (const int32_t *)(d + o_fr); a.obs = (const double *)(d + o_obs);
   a.poses = (double *)(d + o_pose); a.pts_a = (double *)(d + o_pa); a.pts_b = (double *)(d + o_pb);
   a.Hll = (double *)(d + o_hll); a.bl = (double *)(d + o_bl); a.Hinv = (double *)(d + o_hinv); a.Wd = (double *)(d + o_wd);
-  a.stats = (double *)(d + o_stats); a.pts_sel = (int32_t *)(d + o_stats + 32);
+  a.stats = (double *)(d + o_stats); a.pts_sel = (int32_t *)(d + o_stats + 32);   // stats[8..15]: phase cycles (debug)
   // staging chunk for the Schur products: <= 64 KB of shared memory
   int pc = (int)(65536 / ((size_t)F * 36 * 8 + 24));
   pc = std::max(1, std::min(pc, 64));
@@ -635,7 +1041,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
   // results
   double *h_pose = (double *)(h + o_pose), *h_stats = (double *)(h + in_end);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, a.poses, (size_t)F * 96, cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaMemcpyAsync(h_stats, a.stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_stats, a.stats, 128, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (!fix_points && update_points && P > 0) {
     const int sel = *(int32_t *)((uint8_t *)h_stats + 32);
@@ -655,6 +1061,10 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
     T[15] = 1;
   }
   if (stats) memcpy(stats, h_stats, 32);
+  if (getenv("MVO_BA_DEBUG")) {
+    fprintf(stderr, "k_ba: F=%d P=%d E=%d it=%.0f trials=%.0f cycles A=%.0f B=%.0f C=%.0f D=%.0f E=%.0f F=%.0f sync=%.0f\n", F, P, E,
+            h_stats[2], h_stats[15], h_stats[8], h_stats[9], h_stats[10], h_stats[11], h_stats[12], h_stats[13], h_stats[14]);
+  }
   return MVO_OK;
 }
 

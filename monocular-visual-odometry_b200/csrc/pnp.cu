@@ -281,83 +281,19 @@ k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, P
   }
 }
 
-// ---- refinement helpers (one CTA) -------------------------------------------------------
-__device__ __forceinline__ void rot_exp(const double *w, double *R) {   // Rodrigues
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
-  double A, B;
-  if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
-  else { A = sin(th) / th; B = (1 - cos(th)) / th2; }
-  const double wx = w[0], wy = w[1], wz = w[2];
-  R[0] = 1 - B * (wy * wy + wz * wz); R[1] = -A * wz + B * wx * wy;       R[2] = A * wy + B * wx * wz;
-  R[3] = A * wz + B * wx * wy;        R[4] = 1 - B * (wx * wx + wz * wz); R[5] = -A * wx + B * wy * wz;
-  R[6] = -A * wy + B * wx * wz;       R[7] = A * wx + B * wy * wz;        R[8] = 1 - B * (wx * wx + wy * wy);
-}
-
-// 6x6 SPD solve by Cholesky (in place on the lower triangle of a 6x6 row-major copy)
-__device__ bool solve6(const double *Hm, const double *g, double lambda, double *x) {
-  double L[36];
-  for (int i = 0; i < 36; ++i) L[i] = Hm[i];
-  for (int i = 0; i < 6; ++i) L[i * 6 + i] += lambda * fmax(Hm[i * 6 + i], 1e-12);
-  for (int j = 0; j < 6; ++j) {
-    double d = L[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
-    if (!(d > 0)) return false;
-    d = sqrt(d);
-    L[j * 6 + j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = L[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      L[i * 6 + j] = s / d;
-    }
-  }
-  double y[6];
-  for (int i = 0; i < 6; ++i) {
-    double s = g[i];
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k];
-    y[i] = s / L[i * 6 + i];
-  }
-  for (int i = 5; i >= 0; --i) {
-    double s = y[i];
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * x[k];
-    x[i] = s / L[i * 6 + i];
-  }
-  return true;
-}
-
 constexpr int FIN_T = 1024;
 
-// block-wide sum of NV doubles per thread -> result in s_out[0..NV) (valid for all threads after return)
-template <int NV>
-__device__ void block_sum(double *v, double *s_red /* [32][NV] */, double *s_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double x = v[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    if (lane == 0) s_red[warp * NV + k] = x;
-  }
-  __syncthreads();
-  if (threadIdx.x < NV) {
-    double s = 0;
-    for (int w = 0; w < FIN_T / 32; ++w) s += s_red[w * NV + threadIdx.x];
-    s_out[threadIdx.x] = s;
-  }
-  __syncthreads();
-}
-
 // out: [0..8] R, [9..11] t, then int32 n_inliers at out_i[0], best hypothesis at out_i[1],
-// iterations at out_i[2]; inlier indices in inl[].  mode 0: full finish; mode 1: refine only
-// (all n points are inliers, pose_io holds the start pose).
+// inlier indices in inl[] and the one-frame edge list (ex, eo, ef) for the pose-only LM refit.
+// mode 0: arg-max + consensus set; mode 1: every point is an inlier, pose_io holds the start pose.
 __global__ void __launch_bounds__(FIN_T)
 k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, double thr2, int H,
              const double *__restrict__ poses, const int32_t *__restrict__ counts, int mode, int max_iters,
-             double *__restrict__ pose_io, int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
+             double *__restrict__ pose_io, int32_t *__restrict__ out_i, int32_t *__restrict__ inl,
+             double *__restrict__ ex, double *__restrict__ eo, int32_t *__restrict__ ef) {
   __shared__ double s_red[32 * 28];
-  __shared__ double s_sum[28];
-  __shared__ double s_pose[12], s_try[12], s_delta[6];
-  __shared__ int s_best, s_cnt[32], s_state;
-  __shared__ double s_lambda;
+  __shared__ double s_pose[12];
+  __shared__ int s_best, s_cnt[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int n_in = 0;
   if (mode == 0) {
@@ -381,6 +317,8 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     __syncthreads();
     if (s_best < 0) {
       if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
+      for (int j = tid; j < n; j += FIN_T) ef[j] = -1;
+      if (tid < 12) pose_io[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
       return;
     }
     if (tid < 12) s_pose[tid] = poses[(size_t)s_best * 12 + tid];
@@ -409,95 +347,15 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     __syncthreads();
   }
 
-  // damped Gauss-Newton on SE(3), left-multiplicative update T <- exp(delta) T, delta = (w, v)
-  if (tid == 0) { s_lambda = 1e-4; s_state = 0; }
-  __syncthreads();
-  double cost_cur = -1;
-  int it = 0;
-  for (; it < max_iters; ++it) {
-    double acc[28];
-#pragma unroll
-    for (int k = 0; k < 28; ++k) acc[k] = 0;
-    for (int j = tid; j < n_in; j += FIN_T) {
-      const int i = mode == 0 ? inl[j] : j;
-      const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
-      const double x = s_pose[0] * X + s_pose[1] * Y + s_pose[2] * Z + s_pose[9];
-      const double y = s_pose[3] * X + s_pose[4] * Y + s_pose[5] * Z + s_pose[10];
-      const double z = s_pose[6] * X + s_pose[7] * Y + s_pose[8] * Z + s_pose[11];
-      const double iz = 1.0 / z;
-      const double ru = cam.fx * x * iz + cam.cx - p2[2 * i], rv = cam.fy * y * iz + cam.cy - p2[2 * i + 1];
-      // d(proj)/d(delta) for p' = p + w x p + v
-      const double a = cam.fx * iz, bq = cam.fy * iz, xz = x * iz, yz = y * iz;
-      const double Ju[6] = {-a * xz * y, a * (z + x * xz), -a * y, a, 0, -a * xz};
-      const double Jv[6] = {-bq * (z + y * yz), bq * yz * x, bq * x, 0, bq, -bq * yz};
-      int q = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int c = r; c < 6; ++c) acc[q++] += Ju[r] * Ju[c] + Jv[r] * Jv[c];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) acc[21 + r] += Ju[r] * ru + Jv[r] * rv;
-      acc[27] += ru * ru + rv * rv;
-    }
-    block_sum<28>(acc, s_red, s_sum);
-    cost_cur = s_sum[27];
-    // try steps with increasing damping until the cost goes down
-    bool accepted = false;
-    for (int trial = 0; trial < 8 && !accepted; ++trial) {
-      if (tid == 0) {
-        double Hm[36], g[6];
-        int q = 0;
-        for (int r = 0; r < 6; ++r)
-          for (int c = r; c < 6; ++c) { Hm[r * 6 + c] = s_sum[q]; Hm[c * 6 + r] = s_sum[q]; ++q; }
-        for (int r = 0; r < 6; ++r) g[r] = -s_sum[21 + r];
-        double d[6];
-        if (solve6(Hm, g, s_lambda, d)) {
-          double Rw[9];
-          rot_exp(d, Rw);
-          for (int r = 0; r < 3; ++r) {
-            for (int c = 0; c < 3; ++c)
-              s_try[r * 3 + c] = Rw[r * 3] * s_pose[c] + Rw[r * 3 + 1] * s_pose[3 + c] + Rw[r * 3 + 2] * s_pose[6 + c];
-            s_try[9 + r] = Rw[r * 3] * s_pose[9] + Rw[r * 3 + 1] * s_pose[10] + Rw[r * 3 + 2] * s_pose[11] + d[3 + r];
-          }
-          for (int r = 0; r < 6; ++r) s_delta[r] = d[r];
-          s_state = 1;
-        } else {
-          s_state = 0;
-        }
-      }
-      __syncthreads();
-      if (s_state == 0) {               // singular even with damping: raise lambda
-        if (tid == 0) s_lambda *= 10;
-        __syncthreads();
-        continue;
-      }
-      double c1[1] = {0};
-      for (int j = tid; j < n_in; j += FIN_T) {
-        const int i = mode == 0 ? inl[j] : j;
-        const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
-        const double x = s_try[0] * X + s_try[1] * Y + s_try[2] * Z + s_try[9];
-        const double y = s_try[3] * X + s_try[4] * Y + s_try[5] * Z + s_try[10];
-        const double z = s_try[6] * X + s_try[7] * Y + s_try[8] * Z + s_try[11];
-        const double iz = 1.0 / z;
-        const double ru = cam.fx * x * iz + cam.cx - p2[2 * i], rv = cam.fy * y * iz + cam.cy - p2[2 * i + 1];
-        c1[0] += ru * ru + rv * rv;
-      }
-      block_sum<1>(c1, s_red, s_sum + 27);     // keeps s_sum[0..26] (H, g) intact for re-damping
-      const double cost_new = s_sum[27];
-      if (cost_new <= cost_cur) {
-        accepted = true;
-        __syncthreads();
-        if (tid < 12) s_pose[tid] = s_try[tid];
-        if (tid == 0) s_lambda = fmax(s_lambda * 0.1, 1e-15);
-      } else {
-        if (tid == 0) s_lambda *= 10;
-      }
-      __syncthreads();
-    }
-    if (!accepted) break;
-    const double dn = fabs(s_delta[0]) + fabs(s_delta[1]) + fabs(s_delta[2]) + fabs(s_delta[3]) + fabs(s_delta[4]) + fabs(s_delta[5]);
-    if (dn < 1e-13) { ++it; break; }
+  // hand the consensus set to the pose-only LM (ba.cu: k_ba_pose) as a one-frame edge list
+  for (int j = tid; j < n_in; j += FIN_T) {
+    const int i = mode == 0 ? inl[j] : j;
+    ex[3 * j] = p3[3 * i]; ex[3 * j + 1] = p3[3 * i + 1]; ex[3 * j + 2] = p3[3 * i + 2];
+    eo[2 * j] = p2[2 * i]; eo[2 * j + 1] = p2[2 * i + 1];
+    ef[j] = 0;
   }
+  for (int j = n_in + tid; j < n; j += FIN_T) ef[j] = -1;       // masked out of the refit
+  const int it = 0;
   if (tid < 12) pose_io[tid] = s_pose[tid];
   if (tid == 0) { out_i[0] = n_in; out_i[1] = mode == 0 ? s_best : -1; out_i[2] = it; }
 }
@@ -531,22 +389,30 @@ static void rvec_to_rotation(const double *w, double *R) {
   R[6] = -A * wy + B * wx * wz;       R[7] = A * wx + B * wy * wz;        R[8] = 1 - B * (wx * wx + wy * wy);
 }
 
-struct PnpWs { float *p3, *p2; double *poses, *pose_io; int32_t *valid, *counts, *out_i, *inl; };
+struct PnpWs { float *p3, *p2; double *poses, *pose_io, *ex, *eo, *stats; int32_t *valid, *counts, *out_i, *inl, *ef; };
+
+// ba.cu
+int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_eframe, const double *d_X, const double *d_obs, double fx, double fy,
+                       double cx, double cy, const double *info, int iters, int use_huber, double huber, int fix_first,
+                       double step_tol, double *d_poses, double *d_stats);
 
 static int pnp_ws(mvo_ctx *ctx, int n, int H, PnpWs *w) {
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t o_p3 = 0, o_p2 = al(o_p3 + (size_t)n * 12), o_inl = al(o_p2 + (size_t)n * 8), o_end = al(o_inl + (size_t)n * 4);
+  const size_t o_p3 = 0, o_p2 = al(o_p3 + (size_t)n * 12), o_inl = al(o_p2 + (size_t)n * 8), o_ex = al(o_inl + (size_t)n * 4);
+  const size_t o_eo = al(o_ex + (size_t)n * 24), o_ef = al(o_eo + (size_t)n * 16), o_end = al(o_ef + (size_t)n * 4);
   MVO_TRY(mvo_reserve(ctx, ctx->pnp_pts, o_end));
   MVO_TRY(mvo_reserve(ctx, ctx->pnp_hyp, (size_t)H * 12 * 8 + 256));
   MVO_TRY(mvo_reserve(ctx, ctx->pnp_cnt, (size_t)H * 8 + 512));
   MVO_TRY(mvo_reserve(ctx, ctx->pnp_out, 1024));
   uint8_t *b = (uint8_t *)ctx->pnp_pts.p;
   w->p3 = (float *)(b + o_p3); w->p2 = (float *)(b + o_p2); w->inl = (int32_t *)(b + o_inl);
+  w->ex = (double *)(b + o_ex); w->eo = (double *)(b + o_eo); w->ef = (int32_t *)(b + o_ef);
   w->poses = (double *)ctx->pnp_hyp.p;
   w->valid = (int32_t *)ctx->pnp_cnt.p;
   w->counts = w->valid + ((H + 63) & ~63);
   w->pose_io = (double *)ctx->pnp_out.p;
   w->out_i = (int32_t *)((uint8_t *)ctx->pnp_out.p + 256);
+  w->stats = (double *)((uint8_t *)ctx->pnp_out.p + 512);
   return MVO_OK;
 }
 
@@ -555,6 +421,15 @@ static int pnp_cam(mvo_ctx *ctx, const double *K, PnpCam *cam) {
   cam->fx = K[0]; cam->fy = K[4]; cam->cx = K[2]; cam->cy = K[5];
   if (!(cam->fx > 0 && cam->fy > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "K: focal lengths must be positive");
   return MVO_OK;
+}
+
+// Least-squares refit of the pose on the one-frame edge list written by k_pnp_finish: the same
+// pose-only LM as the fixed-points BA (no robust kernel, identity information, fx/fy), stopping
+// once an accepted step is below 1e-9.  E = n is an upper bound: unused edge slots carry frame -1.
+static int pnp_refit(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
+  static const double I2[4] = {1, 0, 0, 1};
+  return mvo_ba_pose_launch(ctx, 1, n, 1, w.ef, w.ex, w.eo, cam.fx, cam.fy, cam.cx, cam.cy, I2, ctx->prm.pnp_refine_iters, 0, 1.0, 0,
+                            1e-9, w.pose_io, w.stats);
 }
 
 extern "C" {
@@ -592,12 +467,15 @@ int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, i
   MVO_CHECK_LAUNCH(ctx);
   { KTimer kt(ctx, KC_PNP_FINISH);
   k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
-                                             w.pose_io, w.out_i, w.inl); }
+                                             w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
   MVO_CHECK_LAUNCH(ctx);
   ctx->pnp_last_h = H;
   uint8_t *hout = (uint8_t *)ctx->h_b.p + (size_t)n * 20;
   double *h_pose = (double *)hout;
   int32_t *h_i = (int32_t *)(hout + 128), *h_inl = (int32_t *)(hout + 256);
+  // the refit runs on the consensus set whose size only the device knows: launch it for the
+  // worst case E = n with the real count read on the device (edges beyond n_in are masked out)
+  MVO_TRY(pnp_refit(ctx, w, n, cam));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_i, w.out_i, 16, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, w.inl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -649,8 +527,9 @@ int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, 
   MVO_CUDA(ctx, cudaMemcpyAsync(w.pose_io, h_pose, 96, cudaMemcpyHostToDevice, ctx->stream));
   { KTimer kt(ctx, KC_PNP_FINISH);
   k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, 0.0, 0, nullptr, nullptr, 1, ctx->prm.pnp_refine_iters,
-                                             w.pose_io, w.out_i, w.inl); }
+                                             w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
   MVO_CHECK_LAUNCH(ctx);
+  MVO_TRY(pnp_refit(ctx, w, n, cam));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   rotation_to_rvec(h_pose, rvec);
