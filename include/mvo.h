@@ -272,6 +272,12 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref);
  * image_on_device != 0.  T_w_c_out receives the frame's pose after PnP (+ BA). */
 int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t stride,
                       int image_on_device, double *T_w_c_out, mvo_track_result *res);
+/* Optional look-ahead for recorded sequences: enqueue the ORB extraction of a FUTURE frame on a second stream so
+ * that it overlaps the tracking of the current one (at most two frames in flight).  Frames must then be
+ * passed to mvo_tracker_track in the same order, with the same image pointer.  The result is identical to
+ * tracking without prefetch. */
+int mvo_tracker_prefetch(mvo_tracker *t, const uint8_t *image, int channels, size_t stride,
+                         int image_on_device);
 /* Pose of the k-th newest buffered frame (k = 0 is the last tracked one) after BA updates. */
 int mvo_tracker_frame_pose(const mvo_tracker *t, int k, double *T_w_c);
 
@@ -283,6 +289,10 @@ int mvo_kernel_classes(void);
 const char *mvo_kernel_name(int kernel_class);
 int mvo_timing_enable(mvo_ctx *ctx, uint32_t mask);
 int mvo_timing_read(mvo_ctx *ctx, double *ms, uint64_t *counts);
+/* The same over every context a tracker owns (its extraction runs on two internal contexts). */
+int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask);
+int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts);
+uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t);
 
 #ifdef __cplusplus
 }

@@ -550,7 +550,10 @@ size_t ba_smem_doubles(int F, int nact, int pc) {
 // order, so all CTAs hold identical state and decide identically).  The pass that evaluates a trial
 // step also linearises at the trial point, so an accepted step needs no second pass: one pass and
 // one cluster barrier per LM trial.
-constexpr int PF_T = 512;
+#ifndef MVO_PF_T
+#define MVO_PF_T 512
+#endif
+constexpr int PF_T = MVO_PF_T;
 constexpr int PF_NW = PF_T / 32;
 constexpr int PF_V = 28;                      // 21 H + 6 b + chi2 per frame
 
@@ -611,59 +614,111 @@ __device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/,
   return ok;
 }
 
-// one pass over this CTA's edge chunks at poses `P` -> s_part[f*PF_V + q] (this CTA's partial sums).
-// Thread (rank, tid) owns chunk rank*PF_T + tid (+ k*csize*PF_T): `chunk` consecutive edges that all
-// belong to ONE frame (the host pads every frame's edge run to a multiple of `chunk` with frame -1),
-// so a thread accumulates its edges in registers and a warp does a single reduction per pass.
-__device__ void pose_pass(const PoseArgs &a, const double *P, double *s_wacc /*[PF_NW][F*PF_V]*/, double *s_part,
-                          unsigned rank, unsigned csize) {
+// fast double reciprocal / reciprocal square root: float seed + Newton steps (<= 1 ulp), no fp64
+// division or sqrt on the dependent chain
+__device__ __forceinline__ double fast_rcp(double z) {
+  double r = (double)__frcp_rn((float)z);
+  r = r * (2.0 - z * r);
+  r = r * (2.0 - z * r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double c) {
+  double y = (double)rsqrtf((float)c);
+  y = y * (1.5 - 0.5 * c * y * y);
+  y = y * (1.5 - 0.5 * c * y * y);
+  return y;
+}
+
+// 28 contributions of one edge at pose Rt (chi2 in v[27]); v is ACCUMULATED
+__device__ __forceinline__ void edge_terms(const PoseArgs &a, const double *Rt, double X0, double X1, double X2, double ou,
+                                           double ov, double (&v)[32]) {
+  const double x = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
+  const double y = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
+  const double z = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
+  const double iz = fast_rcp(z);
+  const double xz = x * iz, yz = y * iz;
+  const double e0r = ou - (a.fx * xz + a.cx), e1r = ov - (a.fy * yz + a.cy);
+  const double Oe0 = a.i00 * e0r + a.i01 * e1r, Oe1 = a.i10 * e0r + a.i11 * e1r;
+  const double chi = e0r * Oe0 + e1r * Oe1;
+  double w = 1.0, rho = chi;
+  if (a.use_huber && chi > a.huber * a.huber) {     // RobustKernelHuber: rho = 2 sqrt(chi) d - d^2, rho' = d / sqrt(chi)
+    const double ys = fast_rsqrt(chi);
+    w = a.huber * ys;
+    rho = 2 * (chi * ys) * a.huber - a.huber * a.huber;
+  }
+  v[27] += rho;
+  // EdgeProjectXYZ2UV::linearizeOplus, pose block (rows scaled by fx / fy)
+  const double fxz = a.fx * iz, fyz = a.fy * iz;
+  const double B[12] = {xz * yz * a.fx, -(1 + xz * xz) * a.fx, yz * a.fx, -fxz, 0, xz * fxz,
+                        (1 + yz * yz) * a.fy, -xz * yz * a.fy, -xz * a.fy, 0, -fyz, yz * fyz};
+  const double o00 = w * a.i00, o01 = w * a.i01, o10 = w * a.i10, o11 = w * a.i11;
+  const double r0 = -w * Oe0, r1 = -w * Oe1;
+  double OB[12];
+#pragma unroll
+  for (int q2 = 0; q2 < 6; ++q2) { OB[q2] = o00 * B[q2] + o01 * B[6 + q2]; OB[6 + q2] = o10 * B[q2] + o11 * B[6 + q2]; }
+  int q = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int cc = r; cc < 6; ++cc) v[q++] += B[r] * OB[cc] + B[6 + r] * OB[6 + cc];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) v[21 + r] += B[r] * r0 + B[6 + r] * r1;
+}
+
+// warp reduce-scatter of 32 values: afterwards lane L holds the warp-wide sum of v[L]
+// (31 exchanges instead of 32 x 5 for a butterfly per value)
+__device__ __forceinline__ double warp_fold32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const double send = up ? v[i] : v[i + step];
+      const double keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+
+// One pass over this CTA's chunks at poses `P` -> s_part[f*PF_V + q].  Thread (rank, tid) owns chunk
+// rank*PF_T + tid: CH consecutive edges of ONE frame (host pads each frame's run to a multiple of CH with
+// frame -1), cached in shared memory (s_ed, SoA) when CACHED, so the LM trials never touch global memory.
+template <int CH, bool CACHED>
+__device__ void pose_pass(const PoseArgs &a, const double *P, const double *s_ed, const int *s_ef, double *s_wacc /*[PF_NW][NV]*/,
+                          double *s_part, unsigned rank, unsigned csize) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, F = a.F;
   const int NV = F * PF_V;
   for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
   __syncthreads();
-  const int nchunks = a.E / a.chunk;                 // E is padded to a multiple of chunk
+  const int chunk = CACHED ? CH : a.chunk;
+  const int nchunks = a.E / chunk;                   // E is padded to a multiple of chunk
   const int stride = (int)csize * PF_T;
-  for (int cbase = (int)rank * PF_T; cbase < nchunks; cbase += stride) {      // uniform trip count per CTA
+  for (int cbase = (int)rank * PF_T; cbase < nchunks; cbase += stride) {      // one sweep when CACHED
     const int c = cbase + tid;
-    double v[PF_V];
+    double v[32];
 #pragma unroll
-    for (int q = 0; q < PF_V; ++q) v[q] = 0;
+    for (int q = 0; q < 32; ++q) v[q] = 0;
     int f = -1;
-    if (c < nchunks) {
-      const int e0 = c * a.chunk;
-      f = a.e_frame[e0];                              // -1: padding / masked chunk
+    if (CACHED) {
+      f = s_ef[tid];
       if (f >= 0) {
         const double *Rt = P + 12 * f;
-        for (int e = e0; e < e0 + a.chunk; ++e) {
-          if (a.e_frame[e] < 0) break;                // padding at the end of a frame's run
-          const double X0 = a.X[3 * e], X1 = a.X[3 * e + 1], X2 = a.X[3 * e + 2];
-          const double x = Rt[0] * X0 + Rt[1] * X1 + Rt[2] * X2 + Rt[9];
-          const double y = Rt[3] * X0 + Rt[4] * X1 + Rt[5] * X2 + Rt[10];
-          const double z = Rt[6] * X0 + Rt[7] * X1 + Rt[8] * X2 + Rt[11];
-          const double iz = 1.0 / z;                  // the only division per edge
-          const double xz = x * iz, yz = y * iz;
-          const double e0r = a.obs[2 * e] - (a.fx * xz + a.cx), e1r = a.obs[2 * e + 1] - (a.fy * yz + a.cy);
-          const double Oe0 = a.i00 * e0r + a.i01 * e1r, Oe1 = a.i10 * e0r + a.i11 * e1r;
-          const double chi = e0r * Oe0 + e1r * Oe1;
-          double w = 1.0, rho = chi;
-          if (a.use_huber && chi > a.huber * a.huber) { const double sq = sqrt(chi); w = a.huber / sq; rho = 2 * sq * a.huber - a.huber * a.huber; }
-          v[27] += rho;
-          // EdgeProjectXYZ2UV::linearizeOplus, pose block (rows scaled by fx / fy)
-          const double fxz = a.fx * iz, fyz = a.fy * iz;
-          const double B[12] = {xz * yz * a.fx, -(1 + xz * xz) * a.fx, yz * a.fx, -fxz, 0, xz * fxz,
-                                (1 + yz * yz) * a.fy, -xz * yz * a.fy, -xz * a.fy, 0, -fyz, yz * fyz};
-          const double o00 = w * a.i00, o01 = w * a.i01, o10 = w * a.i10, o11 = w * a.i11;
-          const double r0 = -w * Oe0, r1 = -w * Oe1;
-          double OB[12];
 #pragma unroll
-          for (int q2 = 0; q2 < 6; ++q2) { OB[q2] = o00 * B[q2] + o01 * B[6 + q2]; OB[6 + q2] = o10 * B[q2] + o11 * B[6 + q2]; }
-          int q = 0;
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int cc = r; cc < 6; ++cc) v[q++] += B[r] * OB[cc] + B[6 + r] * OB[6 + cc];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) v[21 + r] += B[r] * r0 + B[6 + r] * r1;
+        for (int k = 0; k < CH; ++k) {
+          const double *ed = s_ed + (size_t)k * 5 * PF_T + tid;
+          const double ou = ed[3 * PF_T];
+          if (ou > -1e290) edge_terms(a, Rt, ed[0], ed[PF_T], ed[2 * PF_T], ou, ed[4 * PF_T], v);   // -1e300 marks padding
+        }
+      }
+    } else if (c < nchunks) {
+      const int e0 = c * chunk;
+      f = a.e_frame[e0];
+      if (f >= 0) {
+        const double *Rt = P + 12 * f;
+        for (int e = e0; e < e0 + chunk; ++e) {
+          if (a.e_frame[e] < 0) break;
+          edge_terms(a, Rt, a.X[3 * e], a.X[3 * e + 1], a.X[3 * e + 2], a.obs[2 * e], a.obs[2 * e + 1], v);
         }
       }
     }
@@ -674,24 +729,24 @@ __device__ void pose_pass(const PoseArgs &a, const double *P, double *s_wacc /*[
       const int fl = __shfl_sync(0xffffffffu, f, leader);
       const bool mine = f == fl;
       const unsigned m = __ballot_sync(0xffffffffu, mine);
+      double t[32];
 #pragma unroll
-      for (int q = 0; q < PF_V; ++q) {
-        double x = mine ? v[q] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == (q & 31)) s_wacc[warp * NV + fl * PF_V + q] += x;      // spread the smem updates over lanes
-      }
+      for (int q = 0; q < 32; ++q) t[q] = mine ? v[q] : 0.0;
+      const double tot = warp_fold32(t, lane);
+      if (lane < PF_V) s_wacc[warp * NV + fl * PF_V + lane] += tot;
       todo &= ~m;
     }
   }
   __syncthreads();
   for (int i = tid; i < NV; i += PF_T) {
     double s2 = 0;
+#pragma unroll
     for (int w = 0; w < PF_NW; ++w) s2 += s_wacc[w * NV + i];
     s_part[i] = s2;
   }
 }
 
+template <int CH, bool CACHED>
 __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
@@ -699,15 +754,31 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   extern __shared__ __align__(16) double sm[];
   double *s_pose = sm;                       // F*12
   double *s_try = s_pose + F * 12;           // F*12
-  double *s_cur = s_try + F * 12;            // NV  linearisation at the current state
-  double *s_new = s_cur + NV;                // NV  linearisation at the trial state
-  double *s_part0 = s_new + NV;              // NV  partials, ping
+  double *s_lin0 = s_try + F * 12;           // NV  linearisations (current / trial), ping-pong
+  double *s_lin1 = s_lin0 + NV;              // NV
+  double *s_part0 = s_lin1 + NV;             // NV  partials, ping
   double *s_part1 = s_part0 + NV;            // NV  partials, pong
   double *s_dp = s_part1 + NV;               // F*6
   double *s_wacc = s_dp + F * 6 + 2;         // PF_NW * NV
-  __shared__ double s_c[8];                  // 0 lambda 1 ni 2 chi 3 rho 4 accepted 5 ok 6 max step
+  double *s_ed = s_wacc + PF_NW * NV;        // CH*5*PF_T (CACHED only)
+  __shared__ int s_ef[PF_T];
+  __shared__ double s_c[8];                  // 0 lambda 1 ni 2 chi 3 rho 4 accepted 6 max step
   __shared__ int s_okf[BA_MAXF];
   for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i];
+  if (CACHED) {                              // this thread's chunk -> shared memory, once
+    const int c = (int)rank * PF_T + tid, nchunks = a.E / CH;
+    int f = -1;
+    if (c < nchunks) f = a.e_frame[c * CH];
+    s_ef[tid] = f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      double *ed = s_ed + (size_t)k * 5 * PF_T + tid;
+      const int e = c * CH + k;
+      const bool real = f >= 0 && a.e_frame[e] >= 0;
+      ed[0] = real ? a.X[3 * e] : 0; ed[PF_T] = real ? a.X[3 * e + 1] : 0; ed[2 * PF_T] = real ? a.X[3 * e + 2] : 1;
+      ed[3 * PF_T] = real ? a.obs[2 * e] : -1e300; ed[4 * PF_T] = real ? a.obs[2 * e + 1] : 0;
+    }
+  }
   __syncthreads();
   int parity = 0;
   auto gather = [&](double *dst) {           // after the barrier: sum the partials of all CTAs in rank order
@@ -725,7 +796,8 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     parity ^= 1;
     __syncthreads();
   };
-  pose_pass(a, s_pose, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+  double *s_cur = s_lin0, *s_new = s_lin1;
+  pose_pass<CH, CACHED>(a, s_pose, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
   gather(s_cur);
   if (tid == 0) {
     double chi = 0, md = 0;
@@ -739,6 +811,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     s_c[2] = chi;
     s_c[0] = 1e-5 * md;        // computeLambdaInit
     s_c[1] = 2;
+    s_c[4] = 0;
   }
   __syncthreads();
   const double chi_init = s_c[2];
@@ -746,38 +819,45 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   bool terminate = false;
   long long ph[4] = {0, 0, 0, 0}, tmark = clock64();
 #define PF_MARK(i) do { const long long t_ = clock64(); ph[i] += t_ - tmark; tmark = t_; } while (0)
+  // LM control state lives in registers, replicated in every thread (all compute the same values)
+  double lambda = s_c[0], ni = 2, chi_cur = s_c[2];
   for (; it < a.iters && !terminate; ++it) {
     int qmax = 0;
     double rho = 0;
+    bool accepted = false;
+    double mstep = 0;
     do {
-      const double lambda = s_c[0];
       // per-frame 6x6 solve + trial pose (every CTA, identically)
       if (tid < F) {
         const int f = tid;
         double d[6] = {0, 0, 0, 0, 0, 0};
         bool ok = true;
-        if (!(a.fix_first && f == 0)) {
+        const bool fixed = a.fix_first && f == 0;
+        if (!fixed) {
           ok = chol6_solve(s_cur + f * PF_V, s_cur + f * PF_V + 21, lambda, d);
           if (ok) se3_update(d, s_pose + 12 * f, s_try + 12 * f);
         }
-        if (!ok || (a.fix_first && f == 0))
+        if (!ok || fixed)
           for (int q = 0; q < 12; ++q) s_try[12 * f + q] = s_pose[12 * f + q];
         for (int q = 0; q < 6; ++q) s_dp[6 * f + q] = ok ? d[q] : 0.0;
         s_okf[f] = ok;
       }
       __syncthreads();
       PF_MARK(0);
-      pose_pass(a, s_try, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+      pose_pass<CH, CACHED>(a, s_try, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
       PF_MARK(1);
       gather(s_new);
       PF_MARK(2);
-      if (tid == 0) {
+      // gain ratio and LM control (OptimizationAlgorithmLevenberg::solve), computed by every thread
+      {
         bool ok = true;
-        double temp = 0, scale = 0, mstep = 0;
+        double temp = 0, scale = 0;
+        mstep = 0;
         for (int f = 0; f < F; ++f) {
           ok = ok && s_okf[f];
           temp += s_new[f * PF_V + 27];
           if (a.fix_first && f == 0) continue;
+#pragma unroll
           for (int q = 0; q < 6; ++q) {
             const double dq = s_dp[6 * f + q];
             scale += dq * (lambda * dq + s_cur[f * PF_V + 21 + q]);     // computeScale with the CURRENT b
@@ -785,45 +865,43 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
           }
         }
         if (!ok) temp = 1.7976931348623157e308;
-        const double r_ = (s_c[2] - temp) / (scale + 1e-3);
-        if (r_ > 0 && isfinite(temp)) {
-          const double tr = 2 * r_ - 1;
+        rho = (chi_cur - temp) * fast_rcp(scale + 1e-3);
+        accepted = rho > 0 && isfinite(temp);
+        if (accepted) {
+          const double tr = 2 * rho - 1;
           double alpha = 1. - tr * tr * tr;
           alpha = fmin(alpha, 2. / 3.);
-          s_c[0] = lambda * fmax(1. / 3., alpha);
-          s_c[1] = 2;
-          s_c[2] = temp;
-          s_c[4] = 1;
+          lambda *= fmax(1. / 3., alpha);
+          ni = 2;
+          chi_cur = temp;
         } else {
-          s_c[0] = lambda * s_c[1];
-          s_c[1] *= 2;
-          s_c[4] = 0;
+          lambda *= ni;
+          ni *= 2;
         }
-        s_c[3] = r_;
-        s_c[6] = mstep;
       }
-      __syncthreads();
-      rho = s_c[3];
-      if (s_c[4] != 0) {
+      __syncthreads();                         // everyone has read s_dp / s_okf / s_cur / s_new
+      if (accepted) {
         for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = s_try[i];
-        for (int i = tid; i < NV; i += PF_T) s_cur[i] = s_new[i];
+        double *t = s_cur; s_cur = s_new; s_new = t;
+        __syncthreads();
       }
-      __syncthreads();
       ++qmax;
       ++trials;
       PF_MARK(3);
     } while (rho < 0 && qmax < 10);
     if (qmax == 10 || rho == 0) terminate = true;
-    if (a.step_tol > 0 && s_c[4] != 0 && s_c[6] < a.step_tol) terminate = true;    // optional early exit (PnP refit)
+    if (a.step_tol > 0 && accepted && mstep < a.step_tol) terminate = true;    // optional early exit (PnP refit)
   }
   cluster.sync();       // nobody leaves while a neighbour may still read its partials
   if (rank == 0) {
     for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = s_pose[i];
-    if (tid == 0) { a.stats[0] = chi_init; a.stats[1] = s_c[2]; a.stats[2] = it; a.stats[3] = s_c[0]; a.stats[15] = trials; for (int q = 0; q < 4; ++q) a.stats[8 + q] = (double)ph[q]; }
+    if (tid == 0) { a.stats[0] = chi_init; a.stats[1] = chi_cur; a.stats[2] = it; a.stats[3] = lambda; a.stats[15] = trials; for (int q = 0; q < 4; ++q) a.stats[8 + q] = (double)ph[q]; }
   }
 }
 
-size_t pose_smem_doubles(int F) { return (size_t)F * 24 + 4 * (size_t)F * PF_V + (size_t)F * 6 + 2 + (size_t)PF_NW * F * PF_V + 8; }
+size_t pose_smem_doubles(int F, int cached_ch) {
+  return (size_t)F * 24 + 4 * (size_t)F * PF_V + (size_t)F * 6 + 2 + (size_t)PF_NW * F * PF_V + (size_t)cached_ch * 5 * PF_T + 8;
+}
 
 }  // namespace
 
@@ -838,24 +916,36 @@ int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_e
   a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
   a.huber = huber; a.step_tol = step_tol;
   a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
-  const size_t smem = pose_smem_doubles(F) * sizeof(double);
+  static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
+  const int csz = (env_cluster >= 1 && env_cluster <= BA_CLUSTER) ? env_cluster : BA_CLUSTER;
+  const bool cached = chunk >= 1 && chunk <= 4 && E / chunk <= csz * PF_T;
+  const size_t smem = pose_smem_doubles(F, cached ? chunk : 0) * sizeof(double);
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: shared memory %zu B", smem);
-  MVO_CUDA(ctx, cudaFuncSetAttribute(k_ba_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(PoseArgs) = k_ba_pose<1, false>;
+  if (cached) {
+    switch (chunk) {
+      case 1: kern = k_ba_pose<1, true>; break;
+      case 2: kern = k_ba_pose<2, true>; break;
+      case 3: kern = k_ba_pose<3, true>; break;
+      default: kern = k_ba_pose<4, true>; break;
+    }
+  }
+  MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(BA_CLUSTER);
+  cfg.gridDim = dim3(csz);
   cfg.blockDim = dim3(PF_T);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = BA_CLUSTER;
+  attr[0].val.clusterDim.x = csz;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   {
     KTimer kt(ctx, KC_BA);
-    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_ba_pose, a));
+    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
   }
   ctx->launches++;
   return MVO_OK;
@@ -889,8 +979,10 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
       for (int k = 0; k < E; ++k) order[cur[edge_frame[k]]++] = k;
     }
     // chunk = edges per thread so that all chunks fit one sweep of the 8 x 512 threads
+    static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
+    const int csz = (env_cluster >= 1 && env_cluster <= BA_CLUSTER) ? env_cluster : BA_CLUSTER;
     int chunk = 1;
-    while ((long)(E + (long)F * (chunk - 1)) > (long)chunk * BA_CLUSTER * PF_T && chunk < 64) ++chunk;
+    while ((long)(E + (long)F * (chunk - 1)) > (long)chunk * csz * PF_T && chunk < 64) ++chunk;
     int Ep = 0;
     for (int f = 0; f < F; ++f) Ep += ((fstart[f + 1] - fstart[f] + chunk - 1) / chunk) * chunk;
     auto al2 = [](size_t v) { return (v + 255) & ~(size_t)255; };

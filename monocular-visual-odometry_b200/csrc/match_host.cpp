@@ -9,7 +9,8 @@ namespace {
 // Upload both descriptor sets (+ optional coordinates), run the all-pairs kernel, bring the
 // packed keys back.  Returns a pointer to the keys in pinned memory (valid until next call).
 int run_match(mvo_ctx *ctx, int mode, const uint8_t *d1, const float *xy1, int n1,
-              const uint8_t *d2, const float *xy2, int n2, float radius, const uint32_t **keys_out) {
+              const uint8_t *d2, const float *xy2, int n2, float radius, const uint32_t **keys_out,
+              bool d2_on_device = false) {
   if (!ctx) return MVO_ERR_INVALID_ARG;
   if (n1 < 0 || n2 < 0 || (n1 > 0 && !d1) || (n2 > 0 && !d2))
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "match: null descriptors or negative count");
@@ -19,7 +20,7 @@ int run_match(mvo_ctx *ctx, int mode, const uint8_t *d1, const float *xy1, int n
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "match: method 3 needs keypoint coordinates");
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   const int W = mode == 1 ? 2 : 1;
-  const size_t b1 = (size_t)n1 * 32, b2 = (size_t)n2 * 32;
+  const size_t b1 = (size_t)n1 * 32, b2 = d2_on_device ? 0 : (size_t)n2 * 32;
   const size_t x1 = mode == 2 ? (size_t)n1 * 8 : 0, x2 = mode == 2 ? (size_t)n2 * 8 : 0;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_d1 = 0, o_d2 = al(o_d1 + b1), o_x1 = al(o_d2 + b2), o_x2 = al(o_x1 + x1);
@@ -35,7 +36,7 @@ int run_match(mvo_ctx *ctx, int mode, const uint8_t *d1, const float *xy1, int n
   if (x1) memcpy(h + o_x1, xy1, x1);
   if (x2) memcpy(h + o_x2, xy2, x2);
   if (in_bytes) MVO_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  MVO_TRY(mvo_match_launch(ctx, mode, d + o_d1, (const float *)(d + o_x1), n1, d + o_d2,
+  MVO_TRY(mvo_match_launch(ctx, mode, d + o_d1, (const float *)(d + o_x1), n1, d2_on_device ? d2 : d + o_d2,
                            (const float *)(d + o_x2), n2, radius, (uint32_t *)ctx->match_keys.p));
   uint32_t *hk = (uint32_t *)(h + in_bytes + 256);
   if (key_bytes)
@@ -114,6 +115,14 @@ int mvo_remove_duplicated_matches(mvo_dmatch *matches, int *n) {
 int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
                        int method_index, const float *xy1, const float *xy2, float radius,
                        mvo_dmatch *out, int *n_out) {
+  return mvo_match_features_ex(ctx, d1, n1, d2, n2, 0, method_index, xy1, xy2, radius, out, n_out);
+}
+
+}  // extern "C"
+
+int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
+                          int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out) {
+  const bool dev2 = d2_on_device != 0;
   if (!ctx) return MVO_ERR_INVALID_ARG;
   if (!n_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null n_out");
   *n_out = 0;
@@ -125,7 +134,7 @@ int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d
     const uint32_t *k = nullptr;
     const bool sad = method_index == 3;
     if (!sad && n2 == 0) return MVO_OK;   // BFMatcher on an empty train set returns no matches
-    MVO_TRY(run_match(ctx, sad ? 2 : 0, d1, xy1, n1, d2, xy2, n2, radius, &k));
+    MVO_TRY(run_match(ctx, sad ? 2 : 0, d1, xy1, n1, d2, xy2, n2, radius, &k, dev2));
     // feature_match.cpp:179-187
     double min_dis = 9999999, max_dis = 0;
     for (int i = 0; i < n1; ++i) {
@@ -143,7 +152,7 @@ int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d
   } else {
     if (n2 < 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "method 2 needs >= 2 train descriptors");
     const uint32_t *k = nullptr;
-    MVO_TRY(run_match(ctx, 1, d1, nullptr, n1, d2, nullptr, n2, 0.f, &k));
+    MVO_TRY(run_match(ctx, 1, d1, nullptr, n1, d2, nullptr, n2, 0.f, &k, dev2));
     for (int i = 0; i < n1; ++i) {   // :210-217
       const mvo_dmatch m0 = unpack(i, k[2 * i], 0, false), m1 = unpack(i, k[2 * i + 1], 0, false);
       const double dist = m0.distance;
@@ -154,6 +163,8 @@ int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d
   *n_out = n;
   return MVO_OK;
 }
+
+extern "C" {
 
 int mvo_match_dev(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
                   const uint8_t *d_d2, const float *d_xy2, int n2, float radius, uint32_t *d_keys) {

@@ -125,6 +125,14 @@ void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
                        int on_device, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);
 
+// asynchronous extraction (orb_host.cpp): begin enqueues on ctx->stream and returns; end waits, finishes the
+// rare host retainBest path and copies out; *d_desc = descriptors on the device (valid until the next begin)
+int mvo_orb_extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device);
+int mvo_orb_extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc);
+// mvo_match_features with the train descriptors optionally already on the device (match_host.cpp)
+int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
+                          int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out);
+
 // ---- stage entry points (host-side launchers, all asynchronous on ctx->stream) -----------
 // match.cu
 int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,

@@ -286,64 +286,119 @@ int upload_image(mvo_ctx *ctx, const uint8_t *image, int rows, size_t stride, ui
   return MVO_OK;
 }
 
-// detect (+ optionally describe) one host image; results to host arrays
-int extract_host(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
-                 mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, bool with_desc, bool on_device = false) {
+// ---- asynchronous extraction: begin() enqueues everything and returns, end() waits and finishes ----
+struct OrbPending {
+  bool active = false, with_desc = false;
+  int rows = 0, cols = 0, out_cap = 0;
+  cudaEvent_t done = nullptr;
+  OrbWs ws;
+  mvo_keypoint *d_k = nullptr;
+  uint8_t *d_d = nullptr;
+  OrbFrameMeta *h_meta = nullptr;
+  mvo_keypoint *h_k = nullptr;
+  uint8_t *h_d = nullptr;
+};
+static std::vector<std::pair<mvo_ctx *, OrbPending *>> g_pending;
+OrbPending *pending_of(mvo_ctx *ctx) {
+  for (auto &p : g_pending)
+    if (p.first == ctx) return p.second;
+  g_pending.emplace_back(ctx, new OrbPending());
+  return g_pending.back().second;
+}
+
+int extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, bool with_desc,
+                  bool on_device) {
   MVO_TRY(check_image(ctx, image, rows, cols, channels, stride));
-  if (!n_kpts || (*n_kpts > 0 && !kpts) || (with_desc && *n_kpts > 0 && !desc))
-    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   OrbState *st = state_of(ctx);
-  OrbWs ws;
-  MVO_TRY(ensure_ws(ctx, st, rows, cols, 1, &ws));
+  OrbPending *pd = pending_of(ctx);
+  if (pd->active) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "extract_begin: an extraction is already pending on this context");
+  MVO_TRY(ensure_ws(ctx, st, rows, cols, 1, &pd->ws));
   const OrbPlanDev &pl = st->plan;
-  uint8_t *d_in = nullptr;
-  // the pinned upload buffer doubles as the download buffer (after the image, 256-aligned)
   const int out_cap = pl.max_kpts + 1;
-  const size_t img_bytes = ((size_t)rows * stride + 255) & ~(size_t)255;
-  const size_t out_bytes = (size_t)out_cap * (sizeof(mvo_keypoint) + 32) + 256;
-  MVO_TRY(mvo_reserve_pinned(ctx, ctx->orb_h, img_bytes + out_bytes + 512));
+  // pinned layout: [image (host input only)] [meta 256][kpts][desc]
+  const size_t img_bytes = on_device ? 0 : (((size_t)rows * stride + 255) & ~(size_t)255);
+  const size_t kb = ((size_t)out_cap * sizeof(mvo_keypoint) + 255) & ~(size_t)255;
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->orb_h, img_bytes + 256 + kb + (size_t)out_cap * 32 + 512));
+  uint8_t *d_in = nullptr;
   if (on_device) d_in = const_cast<uint8_t *>(image);
   else MVO_TRY(upload_image(ctx, image, rows, stride, &d_in));
-  MVO_TRY(mvo_reserve(ctx, ctx->orb_kpts, (size_t)out_cap * sizeof(mvo_keypoint) + (size_t)out_cap * 32 + 512));
-  mvo_keypoint *d_k = (mvo_keypoint *)ctx->orb_kpts.p;
-  uint8_t *d_d = (uint8_t *)ctx->orb_kpts.p + (((size_t)out_cap * sizeof(mvo_keypoint) + 255) & ~(size_t)255);
-  MVO_TRY(run_detect(ctx, st, ws, d_in, channels, stride, 0, 1));
-  if (with_desc) MVO_TRY(orb_launch_blur(ctx, pl, ws.planes, 1));
-  // optimistic fast path: describe right away, then look at the overflow flag
-  MVO_TRY(orb_launch_describe_sel(ctx, pl, ws.planes, ws.sel, ws.meta, nullptr, d_k, d_d, nullptr, out_cap, with_desc, 1));
+  MVO_TRY(mvo_reserve(ctx, ctx->orb_kpts, kb + (size_t)out_cap * 32 + 512));
+  pd->d_k = (mvo_keypoint *)ctx->orb_kpts.p;
+  pd->d_d = (uint8_t *)ctx->orb_kpts.p + kb;
   uint8_t *h = (uint8_t *)ctx->orb_h.p + img_bytes;
-  OrbFrameMeta *h_meta = (OrbFrameMeta *)h;
-  mvo_keypoint *h_k = (mvo_keypoint *)(h + 256);
-  uint8_t *h_d = h + 256 + (((size_t)out_cap * sizeof(mvo_keypoint) + 255) & ~(size_t)255);
-  auto download = [&]() -> int {
-    MVO_CUDA(ctx, cudaMemcpyAsync(h_meta, ws.meta, sizeof(OrbFrameMeta), cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(h_k, d_k, (size_t)out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-    if (with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(h_d, d_d, (size_t)out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MVO_OK;
-  };
-  MVO_TRY(download());
-  int n = h_meta->n_sel;
-  if (h_meta->overflow) {
+  pd->h_meta = (OrbFrameMeta *)h;
+  pd->h_k = (mvo_keypoint *)(h + 256);
+  pd->h_d = h + 256 + kb;
+  pd->rows = rows; pd->cols = cols; pd->out_cap = out_cap; pd->with_desc = with_desc;
+  MVO_TRY(run_detect(ctx, st, pd->ws, d_in, channels, stride, 0, 1));
+  if (with_desc) MVO_TRY(orb_launch_blur(ctx, pl, pd->ws.planes, 1));
+  // optimistic fast path: describe right away; end() looks at the overflow flag
+  MVO_TRY(orb_launch_describe_sel(ctx, pl, pd->ws.planes, pd->ws.sel, pd->ws.meta, nullptr, pd->d_k, pd->d_d, nullptr, out_cap, with_desc, 1));
+  MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_meta, pd->ws.meta, sizeof(OrbFrameMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!pd->done) MVO_CUDA(ctx, cudaEventCreateWithFlags(&pd->done, cudaEventDisableTiming));
+  MVO_CUDA(ctx, cudaEventRecord(pd->done, ctx->stream));
+  pd->active = true;
+  return MVO_OK;
+}
+
+// Waits for the pending extraction; on return kpts/desc (host) are filled and *d_desc (optional) points at
+// the descriptors on the device (valid until the next extract_begin on this context).
+int extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc) {
+  OrbPending *pd = pending_of(ctx);
+  if (!pd->active) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "extract_end: nothing pending");
+  pd->active = false;
+  if (!n_kpts || (*n_kpts > 0 && !kpts) || (pd->with_desc && *n_kpts > 0 && !desc))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaEventSynchronize(pd->done));
+  OrbState *st = state_of(ctx);
+  const OrbPlanDev &pl = st->plan;
+  int n = pd->h_meta->n_sel;
+  if (pd->h_meta->overflow) {
     // some level exceeds featuresPerLevel: OpenCV's retainBest (libstdc++ nth_element) decides
     // both the surviving set and its ORDER, which the first-come grid selection depends on.
-    OrbFrameMeta meta = *h_meta;
-    MVO_TRY(orb_launch_harris_all(ctx, pl, ws.planes, ws.cand, ws.meta, ws.harris, 1));
+    OrbFrameMeta meta = *pd->h_meta;
+    MVO_TRY(orb_launch_harris_all(ctx, pl, pd->ws.planes, pd->ws.cand, pd->ws.meta, pd->ws.harris, 1));
     std::vector<uint32_t> cand;
     std::vector<float> harris;
-    MVO_TRY(slow_path_frame(ctx, pl, ws, 0, meta, cand, harris, &n));
-    MVO_TRY(orb_launch_describe_sel(ctx, pl, ws.planes, ws.sel, ws.meta, ws.n_override, d_k, d_d, nullptr, out_cap, with_desc, 1));
-    MVO_TRY(download());
+    MVO_TRY(slow_path_frame(ctx, pl, pd->ws, 0, meta, cand, harris, &n));
+    MVO_TRY(orb_launch_describe_sel(ctx, pl, pd->ws.planes, pd->ws.sel, pd->ws.meta, pd->ws.n_override, pd->d_k, pd->d_d, nullptr,
+                                    pd->out_cap, pd->with_desc, 1));
+    MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)pd->out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pd->with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)pd->out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   if (n > *n_kpts) return mvo_fail(ctx, MVO_ERR_CAPACITY, "keypoint capacity %d < %d", *n_kpts, n);
-  memcpy(kpts, h_k, (size_t)n * sizeof(mvo_keypoint));
-  if (with_desc) memcpy(desc, h_d, (size_t)n * 32);
+  memcpy(kpts, pd->h_k, (size_t)n * sizeof(mvo_keypoint));
+  if (pd->with_desc) memcpy(desc, pd->h_d, (size_t)n * 32);
+  if (d_desc) *d_desc = pd->d_d;
   *n_kpts = n;
   return MVO_OK;
 }
 
+// detect (+ optionally describe) one image synchronously
+int extract_host(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
+                 mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, bool with_desc, bool on_device = false) {
+  if (!n_kpts || (*n_kpts > 0 && !kpts) || (with_desc && *n_kpts > 0 && !desc))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
+  MVO_TRY(extract_begin(ctx, image, rows, cols, channels, stride, with_desc, on_device));
+  return extract_end(ctx, kpts, n_kpts, desc, nullptr);
+}
+
 }  // namespace
+
+int mvo_orb_extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  return extract_begin(ctx, image, rows, cols, channels, stride, true, on_device != 0);
+}
+
+int mvo_orb_extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  return extract_end(ctx, kpts, n_kpts, desc, d_desc);
+}
 
 int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
                        int on_device, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
@@ -351,6 +406,13 @@ int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, i
 }
 
 void orb_state_free(mvo_ctx *ctx) {
+  for (size_t i = 0; i < g_pending.size(); ++i)
+    if (g_pending[i].first == ctx) {
+      if (g_pending[i].second->done) cudaEventDestroy(g_pending[i].second->done);
+      delete g_pending[i].second;
+      g_pending.erase(g_pending.begin() + i);
+      break;
+    }
   for (size_t i = 0; i < g_states.size(); ++i)
     if (g_states[i].first == ctx) {
       delete g_states[i].second;

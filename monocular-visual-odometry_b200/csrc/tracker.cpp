@@ -3,7 +3,9 @@
 // getMappointsInCurrentView_ (src/vo/vo.cpp:16-49), poseEstimationPnP_ (:267-381) and
 // callBundleAdjustment_ (:384-478).  Host logic in C++ like the reference; every numeric stage
 // goes through the C ABI of this library (no CPU fallback anywhere).
+#include <chrono>
 #include <deque>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -34,6 +36,18 @@ struct mvo_tracker {
   std::vector<float> cand_xy, kp_xy, p3, p2;
   std::vector<int32_t> cand_idx, inliers;
   std::vector<mvo_dmatch> matches;
+  // BA assembly scratch (capacity reused across frames)
+  std::vector<double> ba_poses;
+  std::vector<int> ba_which;
+  std::vector<int32_t> ba_ef, ba_ep, ba_used, ba_remap, ba_stamp;
+  std::vector<float> ba_ob, ba_pts;
+  int32_t ba_gen = 0;
+  // extraction runs on two alternating contexts (own stream + workspace each) so that frame i+1 can be
+  // extracted while frame i is being tracked: extraction does not depend on the VO state
+  mvo_ctx *xctx[2] = {nullptr, nullptr};
+  const uint8_t *pend_img[2] = {nullptr, nullptr};
+  bool pend[2] = {false, false};
+  unsigned n_submit = 0, n_consume = 0;
 };
 
 namespace {
@@ -100,11 +114,39 @@ int mvo_tracker_create(mvo_ctx *ctx, const double *K, int rows, int cols, const 
   }
   memset(t->T_ref, 0, sizeof t->T_ref);
   t->T_ref[0] = t->T_ref[5] = t->T_ref[10] = t->T_ref[15] = 1;
+  for (int k = 0; k < 2; ++k) {
+    const int rc = mvo_create(&t->xctx[k], ctx->device, &ctx->prm);
+    if (rc != MVO_OK) {
+      mvo_tracker_destroy(t);
+      return mvo_fail(ctx, rc, "tracker: cannot create the extraction context");
+    }
+  }
   *out = t;
   return MVO_OK;
 }
 
-void mvo_tracker_destroy(mvo_tracker *t) { delete t; }
+void mvo_tracker_destroy(mvo_tracker *t) {
+  if (!t) return;
+  for (int k = 0; k < 2; ++k)
+    if (t->xctx[k]) mvo_destroy(t->xctx[k]);
+  delete t;
+}
+
+int mvo_tracker_prefetch(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device) {
+  if (!t) return MVO_ERR_INVALID_ARG;
+  mvo_ctx *ctx = t->ctx;
+  if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null image");
+  const int slot = t->n_submit & 1;
+  if (t->pend[slot]) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: two frames are already in flight");
+  mvo_ctx *x = t->xctx[slot];
+  MVO_TRY(mvo_set_params(x, &ctx->prm));          // follow parameter changes made on the main context
+  const int rc = mvo_orb_extract_begin(x, image, t->rows, t->cols, channels, stride, image_on_device);
+  if (rc != MVO_OK) return mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(x));
+  t->pend[slot] = true;
+  t->pend_img[slot] = image;
+  ++t->n_submit;
+  return MVO_OK;
+}
 
 int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc, int n) {
   if (!t) return MVO_ERR_INVALID_ARG;
@@ -119,7 +161,37 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref) {
   memcpy(t->T_ref, T_w_c_ref, sizeof t->T_ref);
   t->frames.clear();
   t->has_prev = false;
+  // drop frames that were prefetched but never tracked
+  for (int k = 0; k < 2; ++k)
+    if (t->pend[k]) {
+      const int cap = t->ctx->prm.max_keypoints + 1;
+      t->kpts.resize(cap);
+      t->desc.resize((size_t)cap * 32);
+      int nk = cap;
+      mvo_orb_extract_end(t->xctx[k], t->kpts.data(), &nk, t->desc.data(), nullptr);
+      t->pend[k] = false;
+    }
+  t->n_submit = t->n_consume = 0;
   return MVO_OK;
+}
+
+int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask) {
+  if (!t) return MVO_ERR_INVALID_ARG;
+  MVO_TRY(mvo_timing_enable(t->ctx, mask));
+  for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_enable(t->xctx[k], mask));
+  return MVO_OK;
+}
+
+int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts) {
+  if (!t) return MVO_ERR_INVALID_ARG;
+  MVO_TRY(mvo_timing_read(t->ctx, ms, counts));
+  for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_read(t->xctx[k], ms, counts));
+  return MVO_OK;
+}
+
+uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t) {
+  if (!t) return 0;
+  return mvo_kernel_launches(t->ctx) + mvo_kernel_launches(t->xctx[0]) + mvo_kernel_launches(t->xctx[1]);
 }
 
 int mvo_tracker_frame_pose(const mvo_tracker *t, int k, double *T_w_c) {
@@ -135,6 +207,12 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   if (!image || !T_w_c_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
   mvo_track_result r;
   memset(&r, 0, sizeof r);
+  static const bool dbg = getenv("MVO_TRACK_DEBUG") != nullptr;
+  static double acc[8] = {0};
+  static int nacc = 0;
+  auto tnow = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = dbg ? tnow() : 0;
+#define TMARK(i) do { if (dbg) { const double t_ = tnow(); acc[i] += t_ - t0; t0 = t_; } } while (0)
   const int cap = ctx->prm.max_keypoints + 1;
 
   // pushFrameToBuff_ (vo.h:81-86) + Frame::calcKeyPoints / calcDescriptors
@@ -144,10 +222,21 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   t->kpts.resize(cap);
   t->desc.resize((size_t)cap * 32);
   int nk = cap;
-  int rc = mvo_orb_extract_ex(ctx, image, t->rows, t->cols, channels, stride, image_on_device, t->kpts.data(), &nk,
-                              t->desc.data());
-  if (rc != MVO_OK) { t->frames.pop_back(); return rc; }
+  // take the frame from the prefetch queue, or extract it now
+  const int slot = t->n_consume & 1;
+  if (t->pend[slot] && t->pend_img[slot] != image) { t->frames.pop_back(); return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: frames must be tracked in the order they were prefetched"); }
+  if (!t->pend[slot]) {
+    const int rc0 = mvo_tracker_prefetch(t, image, channels, stride, image_on_device);
+    if (rc0 != MVO_OK) { t->frames.pop_back(); return rc0; }
+  }
+  mvo_ctx *x = t->xctx[slot];
+  const uint8_t *d_desc = nullptr;
+  t->pend[slot] = false;
+  ++t->n_consume;
+  int rc = mvo_orb_extract_end(x, t->kpts.data(), &nk, t->desc.data(), &d_desc);
+  if (rc != MVO_OK) { t->frames.pop_back(); return mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(x)); }
   r.n_keypoints = nk;
+  TMARK(0);
 
   // curr_->T_w_c_ = ref_->T_w_c_.clone()  (vo_addFrame.cpp:74): initial guess = reference keyframe
   memcpy(cur.T_w_c, t->T_ref, sizeof cur.T_w_c);
@@ -156,27 +245,38 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   double Tcw[16];
   inv_rigid(cur.T_w_c, Tcw);
   const int nmap = (int)(t->map_pts.size() / 3);
-  t->cand_idx.clear(); t->cand_xy.clear(); t->cand_desc.clear();
-  for (int i = 0; i < nmap; ++i) {
-    // basics::preTranslatePoint3f: double accumulation of T(row, j) * p[j], result narrowed to float
-    const double p[4] = {t->map_pts[3 * i], t->map_pts[3 * i + 1], t->map_pts[3 * i + 2], 1};
-    double q[3] = {0, 0, 0};
-    for (int row = 0; row < 3; ++row)
-      for (int j = 0; j < 4; ++j) q[row] += Tcw[row * 4 + j] * p[j];
-    const float cx = (float)q[0], cy = (float)q[1], cz = (float)q[2];
-    bool in_frame = !(cz < 0);
-    // geometry::cam2pixel (camera.cpp): K(0,0) * p.x / p.z + K(0,2) in double, narrowed to Point2f
-    const float u = (float)(t->K[0] * cx / cz + t->K[2]), v = (float)(t->K[4] * cy / cz + t->K[5]);
-    if (!(u > 0 && v > 0 && u < t->cols && v < t->rows)) in_frame = false;
-    if (in_frame) {
-      t->cand_idx.push_back(i);
-      t->cand_xy.push_back(u);
-      t->cand_xy.push_back(v);
-      t->cand_desc.insert(t->cand_desc.end(), t->map_desc.begin() + (size_t)i * 32, t->map_desc.begin() + (size_t)i * 32 + 32);
+  t->cand_idx.resize(nmap); t->cand_xy.resize((size_t)nmap * 2); t->cand_desc.resize((size_t)nmap * 32);
+  int ncand = 0;
+  {
+    const float *mp = t->map_pts.data();
+    const uint8_t *md = t->map_desc.data();
+    uint8_t *cd = t->cand_desc.data();
+    const float fcols = (float)t->cols, frows = (float)t->rows;
+    for (int i = 0; i < nmap; ++i) {
+      // basics::preTranslatePoint3f: double accumulation of T(row, j) * p[j] (j = 0..3), narrowed to float
+      const double p0 = mp[3 * i], p1 = mp[3 * i + 1], p2 = mp[3 * i + 2];
+      double q[3];
+      for (int row = 0; row < 3; ++row) {
+        double acc = 0;
+        acc += Tcw[row * 4] * p0; acc += Tcw[row * 4 + 1] * p1; acc += Tcw[row * 4 + 2] * p2; acc += Tcw[row * 4 + 3] * 1.0;
+        q[row] = acc;
+      }
+      const float cx = (float)q[0], cy = (float)q[1], cz = (float)q[2];
+      if (cz < 0) continue;
+      // geometry::cam2pixel (camera.cpp): K(0,0) * p.x / p.z + K(0,2) in double, narrowed to Point2f
+      const float u = (float)(t->K[0] * cx / cz + t->K[2]), v = (float)(t->K[4] * cy / cz + t->K[5]);
+      if (!(u > 0 && v > 0 && u < fcols && v < frows)) continue;
+      t->cand_idx[ncand] = i;
+      t->cand_xy[2 * ncand] = u;
+      t->cand_xy[2 * ncand + 1] = v;
+      memcpy(cd + (size_t)ncand * 32, md + (size_t)i * 32, 32);
+      ++ncand;
     }
   }
+  t->cand_idx.resize(ncand);
   const int nc = (int)t->cand_idx.size();
   r.n_candidates = nc;
+  TMARK(1);
 
   // ---- matchFeatures(map descriptors, frame descriptors) (vo.cpp:283-289) ----
   t->kp_xy.resize((size_t)nk * 2);
@@ -184,11 +284,12 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   t->matches.resize(nc > 0 ? nc : 1);
   int nm = 0;
   if (nc > 0 && nk > 0 && !(t->prm.match_method == 2 && nk < 2)) {
-    rc = mvo_match_features(ctx, t->cand_desc.data(), nc, t->desc.data(), nk, t->prm.match_method, t->cand_xy.data(),
-                            t->kp_xy.data(), t->prm.match_radius, t->matches.data(), &nm);
+    rc = mvo_match_features_ex(ctx, t->cand_desc.data(), nc, d_desc, nk, 1, t->prm.match_method, t->cand_xy.data(),
+                               t->kp_xy.data(), t->prm.match_radius, t->matches.data(), &nm);
     if (rc != MVO_OK) { t->frames.pop_back(); return rc; }
   }
   r.n_matches = nm;
+  TMARK(2);
   t->p3.resize((size_t)nm * 3);
   t->p2.resize((size_t)nm * 2);
   for (int i = 0; i < nm; ++i) {            // vo.cpp:293-301
@@ -226,37 +327,37 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   }
   if (!pnp_ok && t->has_prev) memcpy(cur.T_w_c, t->T_prev, sizeof cur.T_w_c);   // vo.cpp:376-379
   r.pnp_ok = pnp_ok;
+  TMARK(3);
   memcpy(r.T_w_c_pnp, cur.T_w_c, sizeof r.T_w_c_pnp);
 
   // ---- callBundleAdjustment_ (vo.cpp:384-478) ----
   if (pnp_ok && t->prm.ba_enable) {
     const int total = (int)t->frames.size();
     const int nba = std::min(t->prm.ba_window, total - 1);
-    std::vector<double> poses;
-    std::vector<int> which;
-    std::vector<int32_t> ef, ep;
-    std::vector<float> ob;
+    std::vector<double> &poses = t->ba_poses;
+    std::vector<int> &which = t->ba_which;
+    std::vector<int32_t> &ef = t->ba_ef, &ep = t->ba_ep, &used = t->ba_used;
+    std::vector<float> &ob = t->ba_ob, &pts = t->ba_pts;
+    poses.clear(); which.clear(); ef.clear(); ep.clear(); ob.clear(); used.clear();
     for (int b = total - 1; b >= total - nba; --b) {          // newest first (vo.cpp:417-419)
       TrackedFrame &f = t->frames[b];
       if ((int)f.map_idx.size() < 3) continue;                // vo.cpp:423-426
       const int fi = (int)which.size();
       which.push_back(b);
       poses.insert(poses.end(), f.T_w_c, f.T_w_c + 16);
-      for (size_t k = 0; k < f.map_idx.size(); ++k) {
-        ef.push_back(fi);
-        ep.push_back(f.map_idx[k]);
-        ob.push_back(f.obs_xy[2 * k]);
-        ob.push_back(f.obs_xy[2 * k + 1]);
-      }
+      ef.insert(ef.end(), f.map_idx.size(), fi);
+      ep.insert(ep.end(), f.map_idx.begin(), f.map_idx.end());
+      ob.insert(ob.end(), f.obs_xy.begin(), f.obs_xy.end());
     }
     if (!which.empty()) {
       // only the map points that appear in the graph become vertices (um_pts_3d_in_prev_frames)
-      std::vector<int32_t> remap(nmap, -1), used;
+      if ((int)t->ba_remap.size() != nmap) { t->ba_remap.assign(nmap, 0); t->ba_stamp.assign(nmap, 0); t->ba_gen = 0; }
+      const int32_t gen = ++t->ba_gen;
       for (int32_t &e : ep) {
-        if (remap[e] < 0) { remap[e] = (int32_t)used.size(); used.push_back(e); }
-        e = remap[e];
+        if (t->ba_stamp[e] != gen) { t->ba_stamp[e] = gen; t->ba_remap[e] = (int32_t)used.size(); used.push_back(e); }
+        e = t->ba_remap[e];
       }
-      std::vector<float> pts((size_t)used.size() * 3);
+      pts.resize((size_t)used.size() * 3);
       for (size_t k = 0; k < used.size(); ++k) memcpy(&pts[3 * k], &t->map_pts[3 * (size_t)used[k]], 12);
       const int fix = t->prm.ba_fix_points ? 1 : 0;
       rc = mvo_bundle_adjustment(ctx, poses.data(), (int)which.size(), pts.data(), (int)used.size(), ef.data(),
@@ -268,6 +369,11 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
       r.ba_frames = (int)which.size();
       r.ba_edges = (int)ef.size();
     }
+  }
+  TMARK(4);
+  if (dbg && ++nacc % 50 == 0) {
+    fprintf(stderr, "tracker us/frame: extract %.1f candidates %.1f match %.1f pnp %.1f ba %.1f\n", acc[0] / 50, acc[1] / 50, acc[2] / 50, acc[3] / 50, acc[4] / 50);
+    for (double &a : acc) a = 0;
   }
   // checkLargeMoveForAddKeyFrame_ (vo.cpp:247-265), translation part: the guess pose follows the camera
   if (pnp_ok && trans_dist(t->frames.back().T_w_c, t->T_ref) > t->prm.min_dist_keyframe)

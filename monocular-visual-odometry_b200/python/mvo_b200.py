@@ -95,6 +95,10 @@ SIGNATURES = {
     "mvo_tracker_reset": (_i, [_vp, _vp]),
     "mvo_tracker_track": (_i, [_vp, _vp, _i, _sz, _i, _vp, C.POINTER(TrackResult)]),
     "mvo_tracker_frame_pose": (_i, [_vp, _i, _vp]),
+    "mvo_tracker_prefetch": (_i, [_vp, _vp, _i, _sz, _i]),
+    "mvo_tracker_timing_enable": (_i, [_vp, C.c_uint32]),
+    "mvo_tracker_timing_read": (_i, [_vp, _vp, _vp]),
+    "mvo_tracker_kernel_launches": (C.c_uint64, [_vp]),
     "mvo_kernel_classes": (_i, []),
     "mvo_kernel_name": (C.c_char_p, [_i]),
     "mvo_timing_enable": (_i, [_vp, C.c_uint32]),
@@ -361,12 +365,39 @@ class Tracker:
         if on_device:
             ptr = C.c_void_p(int(image))
         else:
-            img = np.ascontiguousarray(image, np.uint8)
+            img = image if (isinstance(image, np.ndarray) and image.flags["C_CONTIGUOUS"] and image.dtype == np.uint8) \
+                else np.ascontiguousarray(image, np.uint8)
             channels = 1 if img.ndim == 2 else img.shape[2]
             stride = img.shape[1] * channels
             ptr = _ptr(img)
         self.ctx._chk(self.lib.mvo_tracker_track(self.h, ptr, channels, stride, int(on_device), _ptr(T), C.byref(res)))
         return T.reshape(4, 4), res
+
+    def prefetch(self, image, channels=None, stride=None, on_device=False):
+        """Enqueue the extraction of a future frame (device pointer, or a numpy array that must stay alive
+        and be passed again, unchanged, to track())."""
+        if on_device:
+            ptr = C.c_void_p(int(image))
+        else:
+            assert image.flags["C_CONTIGUOUS"] and image.dtype == np.uint8
+            channels = 1 if image.ndim == 2 else image.shape[2]
+            stride = image.shape[1] * channels
+            ptr = _ptr(image)
+        self.ctx._chk(self.lib.mvo_tracker_prefetch(self.h, ptr, channels, stride, int(on_device)))
+
+    def timing_enable(self, mask: int):
+        self.ctx._chk(self.lib.mvo_tracker_timing_enable(self.h, mask))
+
+    def timing_read(self):
+        n = self.lib.mvo_kernel_classes()
+        ms = np.zeros(n)
+        cnt = np.zeros(n, np.uint64)
+        self.ctx._chk(self.lib.mvo_tracker_timing_read(self.h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.mvo_tracker_kernel_launches(self.h))
 
     def frame_pose(self, k=0):
         T = np.zeros(16)

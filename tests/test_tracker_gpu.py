@@ -87,6 +87,38 @@ def test_device_image_equals_host_image(ctx):
     ctx.set_params(max_keypoints=1500, ba_iterations=50)
 
 
+def test_prefetch_gives_identical_results(ctx):
+    import mvo_b200
+    ctx.set_params(max_keypoints=2000, ba_iterations=10)
+    imgs, _ = _make_sequence(3, 6)
+    pts, desc = _map_from_frame0(ctx, imgs[0])
+    out = []
+    for look_ahead in (False, True):
+        trk = mvo_b200.Tracker(ctx, K, 480, 640)
+        trk.set_map(pts, desc)
+        trk.reset(np.eye(4))
+        poses = []
+        if look_ahead:
+            trk.prefetch(imgs[1])
+        for i in range(1, 6):
+            if look_ahead and i + 1 < 6:
+                trk.prefetch(imgs[i + 1])
+            T, r = trk.track(imgs[i])
+            poses.append(T)
+        out.append(np.array(poses))
+        trk.close()
+    assert np.array_equal(out[0], out[1])
+    # order violations are reported, not silently accepted
+    trk = mvo_b200.Tracker(ctx, K, 480, 640)
+    trk.set_map(pts, desc)
+    trk.reset(np.eye(4))
+    trk.prefetch(imgs[1])
+    with pytest.raises(mvo_b200.MvoError):
+        trk.track(imgs[2])
+    trk.close()
+    ctx.set_params(max_keypoints=1500, ba_iterations=50)
+
+
 def test_lost_frame_keeps_previous_pose(ctx):
     import mvo_b200
     ctx.set_params(max_keypoints=2000)
