@@ -36,7 +36,8 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int BA_T = 256;
-constexpr int BA_CLUSTER = 8;
+constexpr int BA_CLUSTER = 8;          // k_ba (Schur variant)
+constexpr int PF_MAXC = 16;            // k_ba_pose: up to 16 CTAs (non-portable cluster size)
 constexpr int BA_MAXF = 16;
 constexpr int BA_NW = BA_T / 32;
 
@@ -689,8 +690,7 @@ __device__ void pose_pass(const PoseArgs &a, const double *P, const double *s_ed
                           double *s_part, unsigned rank, unsigned csize) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, F = a.F;
   const int NV = F * PF_V;
-  for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
-  __syncthreads();
+  // s_wacc is all-zero on entry (cleared at kernel start and re-cleared by the reduction below)
   const int chunk = CACHED ? CH : a.chunk;
   const int nchunks = a.E / chunk;                   // E is padded to a multiple of chunk
   const int stride = (int)csize * PF_T;
@@ -741,7 +741,7 @@ __device__ void pose_pass(const PoseArgs &a, const double *P, const double *s_ed
   for (int i = tid; i < NV; i += PF_T) {
     double s2 = 0;
 #pragma unroll
-    for (int w = 0; w < PF_NW; ++w) s2 += s_wacc[w * NV + i];
+    for (int w = 0; w < PF_NW; ++w) { s2 += s_wacc[w * NV + i]; s_wacc[w * NV + i] = 0; }
     s_part[i] = s2;
   }
 }
@@ -762,9 +762,11 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   double *s_wacc = s_dp + F * 6 + 2;         // PF_NW * NV
   double *s_ed = s_wacc + PF_NW * NV;        // CH*5*PF_T (CACHED only)
   __shared__ int s_ef[PF_T];
-  __shared__ double s_c[8];                  // 0 lambda 1 ni 2 chi 3 rho 4 accepted 6 max step
+  __shared__ double s_c[8];                  // 0 lambda, 2 chi (initial)
+  __shared__ double s_fscale[BA_MAXF], s_fstep[BA_MAXF];
   __shared__ int s_okf[BA_MAXF];
   for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i];
+  for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
   if (CACHED) {                              // this thread's chunk -> shared memory, once
     const int c = (int)rank * PF_T + tid, nchunks = a.E / CH;
     int f = -1;
@@ -785,19 +787,20 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     double *mine = parity ? s_part1 : s_part0;
     cluster.sync();
     for (int i = tid; i < NV; i += PF_T) {
-      double v[BA_CLUSTER];
+      double v[PF_MAXC];
 #pragma unroll
-      for (unsigned r = 0; r < BA_CLUSTER; ++r) v[r] = r < csize ? *cluster.map_shared_rank(mine + i, r) : 0.0;
+      for (unsigned r = 0; r < PF_MAXC; ++r) v[r] = r < csize ? *cluster.map_shared_rank(mine + i, r) : 0.0;
       double s2 = 0;
 #pragma unroll
-      for (unsigned r = 0; r < BA_CLUSTER; ++r) s2 += v[r];     // fixed rank order: identical in every CTA
+      for (unsigned r = 0; r < PF_MAXC; ++r) s2 += v[r];        // fixed rank order: identical in every CTA
       dst[i] = s2;
     }
     parity ^= 1;
     __syncthreads();
   };
   double *s_cur = s_lin0, *s_new = s_lin1;
-  pose_pass<CH, CACHED>(a, s_pose, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+  double *p_cur = s_pose, *p_try = s_try;    // poses ping-pong like the linearisations
+  pose_pass<CH, CACHED>(a, p_cur, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
   gather(s_cur);
   if (tid == 0) {
     double chi = 0, md = 0;
@@ -810,8 +813,6 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     }
     s_c[2] = chi;
     s_c[0] = 1e-5 * md;        // computeLambdaInit
-    s_c[1] = 2;
-    s_c[4] = 0;
   }
   __syncthreads();
   const double chi_init = s_c[2];
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     bool accepted = false;
     double mstep = 0;
     do {
-      // per-frame 6x6 solve + trial pose (every CTA, identically)
+      // per-frame 6x6 solve + trial pose + this frame's share of the gain denominator (every CTA, identically)
       if (tid < F) {
         const int f = tid;
         double d[6] = {0, 0, 0, 0, 0, 0};
@@ -835,16 +836,21 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
         const bool fixed = a.fix_first && f == 0;
         if (!fixed) {
           ok = chol6_solve(s_cur + f * PF_V, s_cur + f * PF_V + 21, lambda, d);
-          if (ok) se3_update(d, s_pose + 12 * f, s_try + 12 * f);
+          if (ok) se3_update(d, p_cur + 12 * f, p_try + 12 * f);
         }
         if (!ok || fixed)
-          for (int q = 0; q < 12; ++q) s_try[12 * f + q] = s_pose[12 * f + q];
-        for (int q = 0; q < 6; ++q) s_dp[6 * f + q] = ok ? d[q] : 0.0;
+          for (int q = 0; q < 12; ++q) p_try[12 * f + q] = p_cur[12 * f + q];
+        double sc = 0, ms = 0;
+        if (ok && !fixed)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { sc += d[q] * (lambda * d[q] + s_cur[f * PF_V + 21 + q]); ms = fmax(ms, fabs(d[q])); }   // computeScale, CURRENT b
+        s_fscale[f] = sc;
+        s_fstep[f] = ms;
         s_okf[f] = ok;
       }
       __syncthreads();
       PF_MARK(0);
-      pose_pass<CH, CACHED>(a, s_try, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+      pose_pass<CH, CACHED>(a, p_try, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
       PF_MARK(1);
       gather(s_new);
       PF_MARK(2);
@@ -856,13 +862,8 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
         for (int f = 0; f < F; ++f) {
           ok = ok && s_okf[f];
           temp += s_new[f * PF_V + 27];
-          if (a.fix_first && f == 0) continue;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const double dq = s_dp[6 * f + q];
-            scale += dq * (lambda * dq + s_cur[f * PF_V + 21 + q]);     // computeScale with the CURRENT b
-            mstep = fmax(mstep, fabs(dq));
-          }
+          scale += s_fscale[f];
+          mstep = fmax(mstep, s_fstep[f]);
         }
         if (!ok) temp = 1.7976931348623157e308;
         rho = (chi_cur - temp) * fast_rcp(scale + 1e-3);
@@ -874,17 +875,14 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
           lambda *= fmax(1. / 3., alpha);
           ni = 2;
           chi_cur = temp;
+          double *t = s_cur; s_cur = s_new; s_new = t;      // the trial state becomes current: pointer swaps only
+          t = p_cur; p_cur = p_try; p_try = t;
         } else {
           lambda *= ni;
           ni *= 2;
         }
       }
-      __syncthreads();                         // everyone has read s_dp / s_okf / s_cur / s_new
-      if (accepted) {
-        for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = s_try[i];
-        double *t = s_cur; s_cur = s_new; s_new = t;
-        __syncthreads();
-      }
+      __syncthreads();                         // all threads have read s_fscale / s_okf before the next solve rewrites them
       ++qmax;
       ++trials;
       PF_MARK(3);
@@ -894,7 +892,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   }
   cluster.sync();       // nobody leaves while a neighbour may still read its partials
   if (rank == 0) {
-    for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = s_pose[i];
+    for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = p_cur[i];
     if (tid == 0) { a.stats[0] = chi_init; a.stats[1] = chi_cur; a.stats[2] = it; a.stats[3] = lambda; a.stats[15] = trials; for (int q = 0; q < 4; ++q) a.stats[8 + q] = (double)ph[q]; }
   }
 }
@@ -917,7 +915,7 @@ int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_e
   a.huber = huber; a.step_tol = step_tol;
   a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
   static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
-  const int csz = (env_cluster >= 1 && env_cluster <= BA_CLUSTER) ? env_cluster : BA_CLUSTER;
+  const int csz = (env_cluster >= 1 && env_cluster <= PF_MAXC) ? env_cluster : BA_CLUSTER;
   const bool cached = chunk >= 1 && chunk <= 4 && E / chunk <= csz * PF_T;
   const size_t smem = pose_smem_doubles(F, cached ? chunk : 0) * sizeof(double);
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: shared memory %zu B", smem);
@@ -931,6 +929,7 @@ int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_e
     }
   }
   MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (csz > 8) MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(csz);
   cfg.blockDim = dim3(PF_T);
@@ -980,7 +979,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
     }
     // chunk = edges per thread so that all chunks fit one sweep of the 8 x 512 threads
     static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
-    const int csz = (env_cluster >= 1 && env_cluster <= BA_CLUSTER) ? env_cluster : BA_CLUSTER;
+    const int csz = (env_cluster >= 1 && env_cluster <= PF_MAXC) ? env_cluster : BA_CLUSTER;
     int chunk = 1;
     while ((long)(E + (long)F * (chunk - 1)) > (long)chunk * csz * PF_T && chunk < 64) ++chunk;
     int Ep = 0;

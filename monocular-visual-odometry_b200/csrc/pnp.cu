@@ -425,11 +425,11 @@ static int pnp_cam(mvo_ctx *ctx, const double *K, PnpCam *cam) {
 
 // Least-squares refit of the pose on the one-frame edge list written by k_pnp_finish: the same
 // pose-only LM as the fixed-points BA (no robust kernel, identity information, fx/fy), stopping
-// once an accepted step is below 1e-9.  E = n is an upper bound: unused edge slots carry frame -1.
+// once an accepted step is below 1e-8 (quadratic convergence: the next step would be ~1e-16).  E = n is an upper bound: unused edge slots carry frame -1.
 static int pnp_refit(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
   static const double I2[4] = {1, 0, 0, 1};
   return mvo_ba_pose_launch(ctx, 1, n, 1, w.ef, w.ex, w.eo, cam.fx, cam.fy, cam.cx, cam.cy, I2, ctx->prm.pnp_refine_iters, 0, 1.0, 0,
-                            1e-9, w.pose_io, w.stats);
+                            1e-8, w.pose_io, w.stats);
 }
 
 extern "C" {

@@ -1,0 +1,77 @@
+"""Turns gpurun_out/*.ncu-rep + launches CSV into small tracked summaries under profiles/.
+Usage: python tools/summarize_profiles.py <tag>   (e.g. r1)"""
+import csv, json, subprocess, sys
+from collections import defaultdict
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+G, P = ROOT / "gpurun_out", ROOT / "profiles"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+P.mkdir(exist_ok=True)
+
+def launches():
+    f = G / f"launches_{tag}.csv"
+    if not f.exists():
+        return
+    rows = [r for r in csv.reader(open(f)) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        if r is hdr or len(r) <= vi or r[hdr.index("Metric Name")] != "gpu__time_duration.sum":
+            continue
+        name = r[ki].split("(")[0].replace("<unnamed>::", "")
+        unit = r[hdr.index("Metric Unit")]
+        v = float(r[vi].replace(",", ""))
+        v = v / 1000.0 if unit in ("ns", "nsecond") else (v * 1000.0 if unit in ("ms", "msecond") else v)
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)",
+             f"# command: python tools/dev_track_loop.py 24   (launches 200..600 of the run)", "kernel,launches,total_us,avg_us,share"]
+    for k, (n, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        lines.append(f"{k},{n},{us:.1f},{us / n:.2f},{us / tot:.3f}")
+    (P / f"launch_shares_{tag}.csv").write_text("\n".join(lines) + "\n")
+    print("\n".join(lines[:16]))
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__cluster_size", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__cycles_active.avg",
+        "sm__cycles_elapsed.max", "lts__t_bytes.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+
+def kernel(rep):
+    out = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3:
+        return None
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = dict(zip(hdr, vals))
+    u = dict(zip(hdr, units))
+    res = {"kernel": d.get("Kernel Name"), "metrics": {k: f"{d[k]} {u.get(k, '')}".strip() for k in WANT if k in d}}
+    st = {k.replace("smsp__pcsamp_warps_issue_stalled_", ""): int(v) for k, v in d.items()
+          if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("_not_issued") and v.isdigit()}
+    tot = sum(st.values()) or 1
+    res["stall_samples_pct"] = {k: round(100 * v / tot, 1) for k, v in sorted(st.items(), key=lambda x: -x[1])[:6]}
+    return res
+
+launches()
+traffic = {}
+for rep in sorted(G.glob(f"prof_{tag}_*.ncu-rep")):
+    r = kernel(rep)
+    if not r:
+        continue
+    name = rep.stem.replace(f"prof_{tag}_", "")
+    (P / f"ncu_{tag}_{name}.json").write_text(json.dumps(r, indent=1) + "\n")
+    m = r["metrics"]
+    try:
+        def b(x):
+            v, unit = x.split()[0].replace(",", ""), x.split()[1] if len(x.split()) > 1 else "byte"
+            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        traffic[name] = b(m["dram__bytes_read.sum"]) + b(m["dram__bytes_write.sum"])
+    except Exception as e:
+        pass
+    print(name, m.get("gpu__time_duration.sum"), m.get("dram__bytes_read.sum"), m.get("dram__bytes_write.sum"), r["stall_samples_pct"])
+if traffic:
+    tr = {("k_ba" if k == "k_ba_pose" else k): v for k, v in traffic.items()}
+    (P / "traffic.json").write_text(json.dumps(tr, indent=1) + "\n")
