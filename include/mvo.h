@@ -89,6 +89,10 @@ typedef struct mvo_params {
   int32_t ba_iterations;      /* reference: 50; BASELINE config 4: 10 */
   double ba_huber_delta;      /* 1.0 */
   int32_t ba_fix_first_pose;  /* 0 = reference behaviour (no pose fixed, g2o_ba.cpp:210-211) */
+  double ba_step_tol;         /* 0 = g2o's control flow to the letter (default).  > 0: the pose-only LM (fixed map
+                                 points) stops as soon as a trial step is below this bound — at convergence g2o
+                                 spends up to 10 rejected trials on steps of ~1e-10 that it then restores; the
+                                 poses agree with the full run to within the bound (tests/test_ba_gpu.py) */
 } mvo_params;
 
 typedef struct mvo_ctx mvo_ctx;
@@ -245,6 +249,13 @@ typedef struct mvo_track_params {
   int32_t ba_fix_points;       /* is_ba_fix_map_points "true" (:123) */
   double information[4];       /* information_matrix "1 0 0 1" (:122) */
   int32_t buffer_size;         /* kBuffSize_ = 20 (include/my_slam/vo/vo.h:77) */
+  double ba_step_tol;          /* mvo_params::ba_step_tol used for the tracker's BA calls; default 1e-9 */
+  int32_t device_resident;     /* 1 (default): map, frame buffer and BA graph stay on the GPU between the stages
+                                  (two host synchronisations per frame); 0: every stage through its host-array
+                                  C-ABI entry point, as a caller of the reference functions would.  Same results
+                                  (tests/test_tracker_gpu.py).  Free map points (ba_fix_points = 0) always take the
+                                  host-array path. */
+  int32_t pad;
 } mvo_track_params;
 
 typedef struct mvo_track_result {

@@ -566,6 +566,7 @@ struct PoseArgs {
   const double *obs;        // [E][2]
   double *poses;            // F x 12 in/out
   double *stats;            // 16
+  MvoPoseStore st;          // STORE variant only: the tracker's device-resident frame buffer (F = listed slots)
 };
 
 __device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/, const double *g, double lambda, double *x) {
@@ -686,13 +687,12 @@ __device__ __forceinline__ double warp_fold32(double (&v)[32], int lane) {
 // rank*PF_T + tid: CH consecutive edges of ONE frame (host pads each frame's run to a multiple of CH with
 // frame -1), cached in shared memory (s_ed, SoA) when CACHED, so the LM trials never touch global memory.
 template <int CH, bool CACHED>
-__device__ void pose_pass(const PoseArgs &a, const double *P, const double *s_ed, const int *s_ef, double *s_wacc /*[PF_NW][NV]*/,
-                          double *s_part, unsigned rank, unsigned csize) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, F = a.F;
+__device__ void pose_pass(const PoseArgs &a, int F, int nchunks, const double *P, const double *s_ed, const int *s_ef,
+                          double *s_wacc /*[PF_NW][NV]*/, double *s_part, unsigned rank, unsigned csize) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NV = F * PF_V;
   // s_wacc is all-zero on entry (cleared at kernel start and re-cleared by the reduction below)
   const int chunk = CACHED ? CH : a.chunk;
-  const int nchunks = a.E / chunk;                   // E is padded to a multiple of chunk
   const int stride = (int)csize * PF_T;
   for (int cbase = (int)rank * PF_T; cbase < nchunks; cbase += stride) {      // one sweep when CACHED
     const int c = cbase + tid;
@@ -746,12 +746,48 @@ __device__ void pose_pass(const PoseArgs &a, const double *P, const double *s_ed
   }
 }
 
-template <int CH, bool CACHED>
+template <int CH, bool CACHED, bool STORE>
 __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
-  const int tid = threadIdx.x, F = a.F, NV = F * PF_V;
+  const int tid = threadIdx.x;
   extern __shared__ __align__(16) double sm[];
+  __shared__ int s_ef[PF_T];
+  __shared__ double s_c[8];                  // 0 lambda, 2 chi (initial)
+  __shared__ double s_fscale[BA_MAXF], s_fstep[BA_MAXF];
+  __shared__ int s_okf[BA_MAXF];
+  __shared__ int s_fslot[BA_MAXF], s_fcnt[BA_MAXF], s_cstart[BA_MAXF + 1], s_F;
+  int F = a.F, nchunks = CACHED ? a.E / CH : a.E / a.chunk;
+  if (STORE) {
+    // The window is described by the device-resident frame buffer: listed slots (newest first) that hold at
+    // least min_links observations become the frames of the graph (vo.cpp:423-426); every CTA derives the same
+    // layout from the same counters.  Frame f owns chunks [s_cstart[f], s_cstart[f+1]) of CH edges each.
+    if (tid == 0) {
+      int nf = 0, c = 0;
+      if (*a.st.skip_flag == 0)
+        for (int k = 0; k < a.st.nslots; ++k) {
+          const int n = min(a.st.cnt[a.st.slot[k]], a.st.cap);
+          if (n >= a.st.min_links) { s_fslot[nf] = a.st.slot[k]; s_fcnt[nf] = n; s_cstart[nf] = c; c += (n + CH - 1) / CH; ++nf; }
+        }
+      s_cstart[nf] = c;
+      if (c > (int)csize * PF_T) nf = -1;     // cannot happen: the host sizes CH from upper bounds of the counters
+      s_F = nf;
+    }
+    __syncthreads();
+    F = s_F;
+    nchunks = F > 0 ? s_cstart[F] : 0;
+    if (F <= 0) {                              // nothing to optimise (PnP failed / BA disabled / no frame with links)
+      if (rank == 0 && tid == 0) { a.st.out_info[0] = F; a.st.out_info[1] = 0; a.stats[0] = a.stats[1] = a.stats[2] = a.stats[3] = 0; a.stats[15] = 0; }
+      return;                                  // every CTA of the cluster takes this branch together
+    }
+    if (rank == 0 && tid == 0) {
+      a.st.out_info[0] = F;
+      int E = 0;
+      for (int f = 0; f < F; ++f) { E += s_fcnt[f]; a.st.out_info[2 + f] = s_fslot[f]; }
+      a.st.out_info[1] = E;
+    }
+  }
+  const int NV = F * PF_V;
   double *s_pose = sm;                       // F*12
   double *s_try = s_pose + F * 12;           // F*12
   double *s_lin0 = s_try + F * 12;           // NV  linearisations (current / trial), ping-pong
@@ -761,14 +797,30 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   double *s_dp = s_part1 + NV;               // F*6
   double *s_wacc = s_dp + F * 6 + 2;         // PF_NW * NV
   double *s_ed = s_wacc + PF_NW * NV;        // CH*5*PF_T (CACHED only)
-  __shared__ int s_ef[PF_T];
-  __shared__ double s_c[8];                  // 0 lambda, 2 chi (initial)
-  __shared__ double s_fscale[BA_MAXF], s_fstep[BA_MAXF];
-  __shared__ int s_okf[BA_MAXF];
-  for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i];
+  if (STORE) { for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.st.pose[(size_t)s_fslot[i / 12] * 12 + i % 12]; }
+  else { for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i]; }
   for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
-  if (CACHED) {                              // this thread's chunk -> shared memory, once
-    const int c = (int)rank * PF_T + tid, nchunks = a.E / CH;
+  if (STORE) {                               // this thread's chunk: gather the (fixed) map points of its observations
+    const int c = (int)rank * PF_T + tid;
+    int f = -1;
+    if (c < nchunks) { f = 0; while (c >= s_cstart[f + 1]) ++f; }
+    s_ef[tid] = f;
+    const int e0 = f >= 0 ? (c - s_cstart[f]) * CH : 0;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      double *ed = s_ed + (size_t)k * 5 * PF_T + tid;
+      const bool real = f >= 0 && e0 + k < s_fcnt[f];
+      double X0 = 0, X1 = 0, X2 = 1, ou = -1e300, ov = 0;
+      if (real) {
+        const size_t o = (size_t)s_fslot[f] * a.st.cap + e0 + k;
+        const float *mp = a.st.map_pts + 3 * (size_t)a.st.edge_map[o];
+        const float2 ob = a.st.edge_obs[o];
+        X0 = mp[0]; X1 = mp[1]; X2 = mp[2]; ou = ob.x; ov = ob.y;
+      }
+      ed[0] = X0; ed[PF_T] = X1; ed[2 * PF_T] = X2; ed[3 * PF_T] = ou; ed[4 * PF_T] = ov;
+    }
+  } else if (CACHED) {                       // this thread's chunk -> shared memory, once
+    const int c = (int)rank * PF_T + tid;
     int f = -1;
     if (c < nchunks) f = a.e_frame[c * CH];
     s_ef[tid] = f;
@@ -800,7 +852,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   };
   double *s_cur = s_lin0, *s_new = s_lin1;
   double *p_cur = s_pose, *p_try = s_try;    // poses ping-pong like the linearisations
-  pose_pass<CH, CACHED>(a, p_cur, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+  pose_pass<CH, CACHED>(a, F, nchunks, p_cur, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
   gather(s_cur);
   if (tid == 0) {
     double chi = 0, md = 0;
@@ -825,7 +877,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   for (; it < a.iters && !terminate; ++it) {
     int qmax = 0;
     double rho = 0;
-    bool accepted = false;
+    bool accepted = false, tiny = false;
     double mstep = 0;
     do {
       // per-frame 6x6 solve + trial pose + this frame's share of the gain denominator (every CTA, identically)
@@ -850,7 +902,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
       }
       __syncthreads();
       PF_MARK(0);
-      pose_pass<CH, CACHED>(a, p_try, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
+      pose_pass<CH, CACHED>(a, F, nchunks, p_try, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
       PF_MARK(1);
       gather(s_new);
       PF_MARK(2);
@@ -868,6 +920,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
         if (!ok) temp = 1.7976931348623157e308;
         rho = (chi_cur - temp) * fast_rcp(scale + 1e-3);
         accepted = rho > 0 && isfinite(temp);
+        tiny = a.step_tol > 0 && ok && mstep < a.step_tol;
         if (accepted) {
           const double tr = 2 * rho - 1;
           double alpha = 1. - tr * tr * tr;
@@ -886,13 +939,18 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
       ++qmax;
       ++trials;
       PF_MARK(3);
-    } while (rho < 0 && qmax < 10);
+    } while (rho < 0 && qmax < 10 && !tiny);
     if (qmax == 10 || rho == 0) terminate = true;
-    if (a.step_tol > 0 && accepted && mstep < a.step_tol) terminate = true;    // optional early exit (PnP refit)
+    // Optional early exit (step_tol > 0; the PnP refit and the tracker's BA): once a trial step is below step_tol
+    // the remaining g2o trials can only apply steps that are smaller still (the damping grows after a rejection,
+    // the iteration contracts after an acceptance), so the poses are final to within step_tol.  A rejected tiny
+    // step is not applied, exactly as g2o would restore it.
+    if (tiny) terminate = true;
   }
   cluster.sync();       // nobody leaves while a neighbour may still read its partials
   if (rank == 0) {
-    for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = p_cur[i];
+    if (STORE) { for (int i = tid; i < F * 12; i += PF_T) a.st.pose[(size_t)s_fslot[i / 12] * 12 + i % 12] = p_cur[i]; }
+    else { for (int i = tid; i < F * 12; i += PF_T) a.poses[i] = p_cur[i]; }
     if (tid == 0) { a.stats[0] = chi_init; a.stats[1] = chi_cur; a.stats[2] = it; a.stats[3] = lambda; a.stats[15] = trials; for (int q = 0; q < 4; ++q) a.stats[8 + q] = (double)ph[q]; }
   }
 }
@@ -903,31 +961,13 @@ size_t pose_smem_doubles(int F, int cached_ch) {
 
 }  // namespace
 
-// Launch the pose-only LM on device-resident edge arrays (also used by the PnP refit).
-int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_eframe, const double *d_X, const double *d_obs, double fx, double fy,
-                       double cx, double cy, const double *info, int iters, int use_huber, double huber, int fix_first,
-                       double step_tol, double *d_poses, double *d_stats) {
-  PoseArgs a;
-  a.chunk = chunk;
-  a.F = F; a.E = E; a.iters = iters; a.fix_first = fix_first; a.use_huber = use_huber;
-  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
-  a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
-  a.huber = huber; a.step_tol = step_tol;
-  a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
+static int pose_cluster_size() {
   static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
-  const int csz = (env_cluster >= 1 && env_cluster <= PF_MAXC) ? env_cluster : BA_CLUSTER;
-  const bool cached = chunk >= 1 && chunk <= 4 && E / chunk <= csz * PF_T;
-  const size_t smem = pose_smem_doubles(F, cached ? chunk : 0) * sizeof(double);
+  return (env_cluster >= 1 && env_cluster <= PF_MAXC) ? env_cluster : BA_CLUSTER;
+}
+
+static int pose_launch(mvo_ctx *ctx, void (*kern)(PoseArgs), const PoseArgs &a, int csz, size_t smem) {
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: shared memory %zu B", smem);
-  void (*kern)(PoseArgs) = k_ba_pose<1, false>;
-  if (cached) {
-    switch (chunk) {
-      case 1: kern = k_ba_pose<1, true>; break;
-      case 2: kern = k_ba_pose<2, true>; break;
-      case 3: kern = k_ba_pose<3, true>; break;
-      default: kern = k_ba_pose<4, true>; break;
-    }
-  }
   MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csz > 8) MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -948,6 +988,63 @@ int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_e
   }
   ctx->launches++;
   return MVO_OK;
+}
+
+// Launch the pose-only LM on device-resident edge arrays (also used by the PnP refit).
+int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_eframe, const double *d_X, const double *d_obs, double fx, double fy,
+                       double cx, double cy, const double *info, int iters, int use_huber, double huber, int fix_first,
+                       double step_tol, double *d_poses, double *d_stats) {
+  PoseArgs a;
+  memset(&a, 0, sizeof a);
+  a.chunk = chunk;
+  a.F = F; a.E = E; a.iters = iters; a.fix_first = fix_first; a.use_huber = use_huber;
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+  a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
+  a.huber = huber; a.step_tol = step_tol;
+  a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
+  const int csz = pose_cluster_size();
+  const bool cached = chunk >= 1 && chunk <= 4 && E / chunk <= csz * PF_T;
+  const size_t smem = pose_smem_doubles(F, cached ? chunk : 0) * sizeof(double);
+  void (*kern)(PoseArgs) = k_ba_pose<1, false, false>;
+  if (cached) {
+    switch (chunk) {
+      case 1: kern = k_ba_pose<1, true, false>; break;
+      case 2: kern = k_ba_pose<2, true, false>; break;
+      case 3: kern = k_ba_pose<3, true, false>; break;
+      default: kern = k_ba_pose<4, true, false>; break;
+    }
+  }
+  return pose_launch(ctx, kern, a, csz, smem);
+}
+
+// The same LM over the tracker's device-resident frame buffer (track.cu): the graph is assembled by the kernel
+// from the per-frame observation lists and counters, nothing crosses PCIe.  e_upper = upper bound of the edge
+// count (the host knows every counter except the newest frame's, which is bounded by its match count).
+int mvo_ba_pose_store_launch(mvo_ctx *ctx, const MvoPoseStore &st, int e_upper, double fx, double fy, double cx, double cy,
+                             const double *info, int iters, int use_huber, double huber, double step_tol, double *d_stats) {
+  if (st.nslots < 1 || st.nslots > BA_MAXF) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: %d frames (supported 1..%d)", st.nslots, BA_MAXF);
+  const int csz = pose_cluster_size();
+  int chunk = 1;
+  while ((long)(e_upper + (long)st.nslots * (chunk - 1)) > (long)chunk * csz * PF_T && chunk <= 4) ++chunk;
+  if (chunk > 4) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: %d edges exceed the device-resident path", e_upper);
+  PoseArgs a;
+  memset(&a, 0, sizeof a);
+  a.chunk = chunk;
+  a.F = st.nslots; a.E = 0; a.iters = iters; a.fix_first = 0; a.use_huber = use_huber;
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+  a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
+  a.huber = huber; a.step_tol = step_tol;
+  a.stats = d_stats;
+  a.st = st;
+  const size_t smem = pose_smem_doubles(st.nslots, chunk) * sizeof(double);
+  void (*kern)(PoseArgs) = nullptr;
+  switch (chunk) {
+    case 1: kern = k_ba_pose<1, true, true>; break;
+    case 2: kern = k_ba_pose<2, true, true>; break;
+    case 3: kern = k_ba_pose<3, true, true>; break;
+    default: kern = k_ba_pose<4, true, true>; break;
+  }
+  return pose_launch(ctx, kern, a, csz, smem);
 }
 
 // Shared driver for bundleAdjustment and optimizeSingleFrame.
@@ -978,8 +1075,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
       for (int k = 0; k < E; ++k) order[cur[edge_frame[k]]++] = k;
     }
     // chunk = edges per thread so that all chunks fit one sweep of the 8 x 512 threads
-    static const int env_cluster = getenv("MVO_BA_CLUSTER") ? atoi(getenv("MVO_BA_CLUSTER")) : BA_CLUSTER;
-    const int csz = (env_cluster >= 1 && env_cluster <= PF_MAXC) ? env_cluster : BA_CLUSTER;
+    const int csz = pose_cluster_size();
     int chunk = 1;
     while ((long)(E + (long)F * (chunk - 1)) > (long)chunk * csz * PF_T && chunk < 64) ++chunk;
     int Ep = 0;
@@ -1021,7 +1117,7 @@ static int run_ba(mvo_ctx *ctx, double *poses_T_w_c, int F, float *points, int P
     MVO_CUDA(ctx, cudaMemcpyAsync(d, h, in_end, cudaMemcpyHostToDevice, ctx->stream));
     MVO_TRY(mvo_ba_pose_launch(ctx, F, Ep, chunk, (const int32_t *)(d + o_fr), (const double *)(d + o_X), (const double *)(d + o_obs),
                                K[0], K[0], K[2], K[5], info, iterations, use_huber && ctx->prm.ba_huber_delta > 0,
-                               ctx->prm.ba_huber_delta, fix_first, 0.0, (double *)(d + o_pose), (double *)(d + o_stats)));
+                               ctx->prm.ba_huber_delta, fix_first, ctx->prm.ba_step_tol, (double *)(d + o_pose), (double *)(d + o_stats)));
     double *h_stats = (double *)(h + o_stats);
     MVO_CUDA(ctx, cudaMemcpyAsync(hpose, d + o_pose, (size_t)F * 96, cudaMemcpyDeviceToHost, ctx->stream));
     MVO_CUDA(ctx, cudaMemcpyAsync(h_stats, d + o_stats, 128, cudaMemcpyDeviceToHost, ctx->stream));

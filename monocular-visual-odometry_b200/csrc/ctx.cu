@@ -59,7 +59,7 @@ KTimer::~KTimer() {
 
 static const char *kKernelNames[KC_COUNT] = {"k_gray", "k_resize", "k_fast", "k_select", "k_blur", "k_describe",
                                               "k_harris_all", "match_kernel", "k_pnp_hypotheses", "k_pnp_score",
-                                              "k_pnp_finish", "k_ba"};
+                                              "k_pnp_finish", "k_ba", "k_track_glue"};
 
 extern "C" {
 
@@ -105,6 +105,7 @@ void mvo_default_params(mvo_params *p) {
   p->ba_iterations = 50;         // src/optimization/g2o_ba.cpp:275
   p->ba_huber_delta = 1.0;
   p->ba_fix_first_pose = 0;
+  p->ba_step_tol = 0.0;
 }
 
 static int validate_params(mvo_ctx *ctx, const mvo_params *p) {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kQ)
 match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n1,
              const uint4 *__restrict__ d2, const float2 *__restrict__ xy2, int n2, int chunk,
              float r2, uint32_t *__restrict__ part, unsigned int *__restrict__ tickets,
-             uint32_t *__restrict__ keys) {
+             uint32_t *__restrict__ keys, const uint8_t *__restrict__ qmask) {
   __shared__ uint4 s_t[kMaxChunk * 2];
   __shared__ float2 s_xy[MODE == 2 ? kMaxChunk : 1];
   __shared__ bool s_last;
@@ -114,7 +114,11 @@ match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n
   }
 
   constexpr int W = (MODE == 1) ? 2 : 1;
+  // qmask (optional): queries whose mask byte is 0 report "no match" (the tracker matches the whole resident
+  // map and masks the points outside the current view instead of compacting them first)
+  const bool masked = qmask != nullptr && q < n1 && qmask[q] == 0;
   if (nsplit == 1) {
+    if (masked) b1 = b2 = 0xFFFFFFFFu;
     if (q < n1) {
       keys[(size_t)q * W] = b1;
       if (MODE == 1) keys[(size_t)q * W + 1] = b2;
@@ -148,6 +152,7 @@ match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n
         m1 = min(m1, k1);
       }
     }
+    if (masked) m1 = m2 = 0xFFFFFFFFu;
     keys[(size_t)q * W] = m1;
     if (MODE == 1) keys[(size_t)q * W + 1] = m2;
   }
@@ -158,6 +163,12 @@ match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n
 int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
                      const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
                      uint32_t *d_keys) {
+  return mvo_match_launch_masked(ctx, mode, d_d1, d_xy1, n1, d_d2, d_xy2, n2, radius, d_keys, nullptr);
+}
+
+int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                            const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
+                            uint32_t *d_keys, const uint8_t *d_qmask) {
   if (mode < 0 || mode > 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "match: bad mode %d", mode);
   if (n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535)
     return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "match: n1=%d n2=%d outside [0,65535]", n1, n2);
@@ -190,11 +201,11 @@ int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d
   const float2 *xa = (const float2 *)d_xy1, *xb = (const float2 *)d_xy2;
   KTimer kt(ctx, KC_MATCH);
   if (mode == 0)
-    match_kernel<0><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys);
+    match_kernel<0><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
   else if (mode == 1)
-    match_kernel<1><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys);
+    match_kernel<1><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
   else
-    match_kernel<2><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys);
+    match_kernel<2><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

@@ -14,7 +14,7 @@ struct mvo_ctx;
 
 // kernel classes for the optional CUDA-event timing (mvo_timing_*)
 enum MvoKernelClass { KC_GRAY = 0, KC_RESIZE, KC_FAST, KC_SELECT, KC_BLUR, KC_DESCRIBE, KC_HARRIS, KC_MATCH,
-                      KC_PNP_HYP, KC_PNP_SCORE, KC_PNP_FINISH, KC_BA, KC_COUNT };
+                      KC_PNP_HYP, KC_PNP_SCORE, KC_PNP_FINISH, KC_BA, KC_TRACK, KC_COUNT };
 struct MvoEvPair { int id; cudaEvent_t a, b; };
 
 // ---- error plumbing -------------------------------------------------------------------
@@ -89,6 +89,7 @@ struct mvo_ctx {
   DevBuf orb_planes, orb_cand, orb_bandcnt, orb_sel, orb_misc, orb_in;
   DevBuf orb_kpts, orb_desc, orb_counts;
   PinBuf orb_h;
+  void *orb_state = nullptr, *orb_pending = nullptr;   // orb_host.cpp: OrbState / OrbPending of this context
 
   // match
   DevBuf match_part, match_tickets, match_in, match_keys;
@@ -120,6 +121,42 @@ struct KTimer {
 int mvo_reserve(mvo_ctx *ctx, DevBuf &b, size_t bytes);
 int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes);
 
+// The tracker's device-resident frame buffer as the pose-only LM sees it (ba.cu: k_ba_pose<.., STORE>).
+// A buffered frame lives in one ring slot: its world->camera pose, its observation list (map point index +
+// pixel, in PnP-inlier order = Frame::inliers_to_mappt_connections_) and the length of that list.
+struct MvoPoseStore {
+  const float *map_pts;        // [nmap][3] MapPoint::pos_
+  const int32_t *edge_map;     // [ring][cap]
+  const float2 *edge_obs;      // [ring][cap]
+  const int32_t *cnt;          // [ring]
+  double *pose;                // [ring][12] R row-major, t (world->camera)
+  int cap, nslots, min_links;
+  int slot[16];                // the window, newest first
+  const int32_t *skip_flag;    // device flag: != 0 -> the kernel does nothing (PnP failed)
+  int32_t *out_info;           // [0] frames in the graph (0 = skipped), [1] edges, [2 + f] slot of frame f
+};
+
+// track.cu: glue kernels of the device-resident tracking step
+struct MvoTrackGlue {
+  int mode, slot, cap, ba_enable, has_prev;
+  double max_dist, prev_twc[3], fallback[12];
+  const double *pose_io;
+  const int32_t *out_i, *inl, *pairs;
+  const mvo_keypoint *kpts;
+  int32_t *edge_map;
+  float *edge_obs;
+  int32_t *cnt;
+  double *pose;
+  int32_t *skip_flag, *res_i;
+  double *res_d;
+};
+int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,
+                          int rows, int cols, uint8_t *d_vis, float *d_cxy);
+int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_xy);
+int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const float *d_map_pts, const mvo_keypoint *d_kpts,
+                           float *d_p3, float *d_p2);
+int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g);
+
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 // mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)
 int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
@@ -129,6 +166,9 @@ int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, i
 // rare host retainBest path and copies out; *d_desc = descriptors on the device (valid until the next begin)
 int mvo_orb_extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device);
 int mvo_orb_extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc);
+// the same with keypoints and descriptors left on the device (valid until the next begin on this context)
+int mvo_orb_extract_begin_dev(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device);
+int mvo_orb_extract_end_dev(mvo_ctx *ctx, int *n_kpts, const mvo_keypoint **d_kpts, const uint8_t **d_desc);
 // mvo_match_features with the train descriptors optionally already on the device (match_host.cpp)
 int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
                           int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out);
@@ -138,3 +178,12 @@ int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t
 int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
                      const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
                      uint32_t *d_keys);
+int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                            const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
+                            uint32_t *d_keys, const uint8_t *d_qmask);
+// pnp.cu: device-resident solvePnPRansac replacement (see there)
+int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **pose_io, int32_t **out_i, int32_t **inl);
+int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K);
+// ba.cu: pose-only LM over the tracker's device-resident frame buffer
+int mvo_ba_pose_store_launch(mvo_ctx *ctx, const MvoPoseStore &st, int e_upper, double fx, double fy, double cx, double cy,
+                             const double *info, int iters, int use_huber, double huber, double step_tol, double *d_stats);

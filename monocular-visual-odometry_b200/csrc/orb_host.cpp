@@ -15,14 +15,10 @@ struct OrbState {           // lives in mvo_ctx via the opaque DevBufs; plan kep
   bool valid = false;
 };
 
-// one plan per context, keyed by the ctx pointer (contexts are few and long-lived)
-static std::vector<std::pair<mvo_ctx *, OrbState *>> g_states;
-
+// one plan per context, owned by the context (contexts may be driven from different host threads)
 OrbState *state_of(mvo_ctx *ctx) {
-  for (auto &p : g_states)
-    if (p.first == ctx) return p.second;
-  g_states.emplace_back(ctx, new OrbState());
-  return g_states.back().second;
+  if (!ctx->orb_state) ctx->orb_state = new OrbState();
+  return (OrbState *)ctx->orb_state;
 }
 
 inline int cv_round(double v) { return (int)nearbyint(v); }   // cvRound: round half to even
@@ -288,7 +284,7 @@ int upload_image(mvo_ctx *ctx, const uint8_t *image, int rows, size_t stride, ui
 
 // ---- asynchronous extraction: begin() enqueues everything and returns, end() waits and finishes ----
 struct OrbPending {
-  bool active = false, with_desc = false;
+  bool active = false, with_desc = false, want_host = true;
   int rows = 0, cols = 0, out_cap = 0;
   cudaEvent_t done = nullptr;
   OrbWs ws;
@@ -298,16 +294,14 @@ struct OrbPending {
   mvo_keypoint *h_k = nullptr;
   uint8_t *h_d = nullptr;
 };
-static std::vector<std::pair<mvo_ctx *, OrbPending *>> g_pending;
 OrbPending *pending_of(mvo_ctx *ctx) {
-  for (auto &p : g_pending)
-    if (p.first == ctx) return p.second;
-  g_pending.emplace_back(ctx, new OrbPending());
-  return g_pending.back().second;
+  if (!ctx->orb_pending) ctx->orb_pending = new OrbPending();
+  return (OrbPending *)ctx->orb_pending;
 }
 
+// want_host = false: keypoints and descriptors stay on the device (only the 64-byte frame record comes back)
 int extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, bool with_desc,
-                  bool on_device) {
+                  bool on_device, bool want_host = true) {
   MVO_TRY(check_image(ctx, image, rows, cols, channels, stride));
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   OrbState *st = state_of(ctx);
@@ -330,14 +324,16 @@ int extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int ch
   pd->h_meta = (OrbFrameMeta *)h;
   pd->h_k = (mvo_keypoint *)(h + 256);
   pd->h_d = h + 256 + kb;
-  pd->rows = rows; pd->cols = cols; pd->out_cap = out_cap; pd->with_desc = with_desc;
+  pd->rows = rows; pd->cols = cols; pd->out_cap = out_cap; pd->with_desc = with_desc; pd->want_host = want_host;
   MVO_TRY(run_detect(ctx, st, pd->ws, d_in, channels, stride, 0, 1));
   if (with_desc) MVO_TRY(orb_launch_blur(ctx, pl, pd->ws.planes, 1));
   // optimistic fast path: describe right away; end() looks at the overflow flag
   MVO_TRY(orb_launch_describe_sel(ctx, pl, pd->ws.planes, pd->ws.sel, pd->ws.meta, nullptr, pd->d_k, pd->d_d, nullptr, out_cap, with_desc, 1));
   MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_meta, pd->ws.meta, sizeof(OrbFrameMeta), cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-  if (with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_host) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    if (with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (!pd->done) MVO_CUDA(ctx, cudaEventCreateWithFlags(&pd->done, cudaEventDisableTiming));
   MVO_CUDA(ctx, cudaEventRecord(pd->done, ctx->stream));
   pd->active = true;
@@ -346,11 +342,12 @@ int extract_begin(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int ch
 
 // Waits for the pending extraction; on return kpts/desc (host) are filled and *d_desc (optional) points at
 // the descriptors on the device (valid until the next extract_begin on this context).
-int extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc) {
+int extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, const uint8_t **d_desc,
+                const mvo_keypoint **d_kpts = nullptr) {
   OrbPending *pd = pending_of(ctx);
   if (!pd->active) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "extract_end: nothing pending");
   pd->active = false;
-  if (!n_kpts || (*n_kpts > 0 && !kpts) || (pd->with_desc && *n_kpts > 0 && !desc))
+  if (!n_kpts || (pd->want_host && ((*n_kpts > 0 && !kpts) || (pd->with_desc && *n_kpts > 0 && !desc))))
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   MVO_CUDA(ctx, cudaEventSynchronize(pd->done));
@@ -367,14 +364,19 @@ int extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, co
     MVO_TRY(slow_path_frame(ctx, pl, pd->ws, 0, meta, cand, harris, &n));
     MVO_TRY(orb_launch_describe_sel(ctx, pl, pd->ws.planes, pd->ws.sel, pd->ws.meta, pd->ws.n_override, pd->d_k, pd->d_d, nullptr,
                                     pd->out_cap, pd->with_desc, 1));
-    MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)pd->out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-    if (pd->with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)pd->out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pd->want_host) {
+      MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_k, pd->d_k, (size_t)pd->out_cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+      if (pd->with_desc) MVO_CUDA(ctx, cudaMemcpyAsync(pd->h_d, pd->d_d, (size_t)pd->out_cap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  if (n > *n_kpts) return mvo_fail(ctx, MVO_ERR_CAPACITY, "keypoint capacity %d < %d", *n_kpts, n);
-  memcpy(kpts, pd->h_k, (size_t)n * sizeof(mvo_keypoint));
-  if (pd->with_desc) memcpy(desc, pd->h_d, (size_t)n * 32);
+  if (pd->want_host) {
+    if (n > *n_kpts) return mvo_fail(ctx, MVO_ERR_CAPACITY, "keypoint capacity %d < %d", *n_kpts, n);
+    memcpy(kpts, pd->h_k, (size_t)n * sizeof(mvo_keypoint));
+    if (pd->with_desc) memcpy(desc, pd->h_d, (size_t)n * 32);
+  }
   if (d_desc) *d_desc = pd->d_d;
+  if (d_kpts) *d_kpts = pd->d_k;
   *n_kpts = n;
   return MVO_OK;
 }
@@ -405,20 +407,28 @@ int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, i
   return extract_host(ctx, image, rows, cols, channels, stride, kpts, n_kpts, desc, true, on_device != 0);
 }
 
+// Device-only variant for the tracker: nothing but the frame record crosses PCIe.
+int mvo_orb_extract_begin_dev(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  return extract_begin(ctx, image, rows, cols, channels, stride, true, on_device != 0, false);
+}
+
+int mvo_orb_extract_end_dev(mvo_ctx *ctx, int *n_kpts, const mvo_keypoint **d_kpts, const uint8_t **d_desc) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  return extract_end(ctx, nullptr, n_kpts, nullptr, d_desc, d_kpts);
+}
+
 void orb_state_free(mvo_ctx *ctx) {
-  for (size_t i = 0; i < g_pending.size(); ++i)
-    if (g_pending[i].first == ctx) {
-      if (g_pending[i].second->done) cudaEventDestroy(g_pending[i].second->done);
-      delete g_pending[i].second;
-      g_pending.erase(g_pending.begin() + i);
-      break;
-    }
-  for (size_t i = 0; i < g_states.size(); ++i)
-    if (g_states[i].first == ctx) {
-      delete g_states[i].second;
-      g_states.erase(g_states.begin() + i);
-      return;
-    }
+  if (ctx->orb_pending) {
+    OrbPending *pd = (OrbPending *)ctx->orb_pending;
+    if (pd->done) cudaEventDestroy(pd->done);
+    delete pd;
+    ctx->orb_pending = nullptr;
+  }
+  if (ctx->orb_state) {
+    delete (OrbState *)ctx->orb_state;
+    ctx->orb_state = nullptr;
+  }
 }
 
 extern "C" {

@@ -432,29 +432,12 @@ static int pnp_refit(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
                             1e-8, w.pose_io, w.stats);
 }
 
-extern "C" {
-
-int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, const double *K,
-                         double *rvec, double *tvec, int32_t *inliers, int *n_inliers) {
-  if (!ctx) return MVO_ERR_INVALID_ARG;
-  if (!pts3d || !pts2d || !rvec || !tvec || !n_inliers || (*n_inliers > 0 && !inliers))
-    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "solvePnPRansac: null pointer");
-  if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: %d correspondences (< 4)", n);
-  PnpCam cam;
-  MVO_TRY(pnp_cam(ctx, K, &cam));
-  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+// hypotheses -> scores -> consensus set of the best hypothesis -> least-squares refit, all on ctx->stream;
+// w.p3 / w.p2 hold the n correspondences on the device
+static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
   const int H = ctx->prm.pnp_hypotheses;
-  PnpWs w;
-  MVO_TRY(pnp_ws(ctx, n, H, &w));
   const size_t smem = (size_t)n * 5 * sizeof(float);
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
-  const size_t hb = (size_t)n * 20 + (size_t)n * 4 + 1024;
-  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, hb));
-  float *h3 = (float *)ctx->h_b.p, *h2 = h3 + (size_t)n * 3;
-  memcpy(h3, pts3d, (size_t)n * 12);
-  memcpy(h2, pts2d, (size_t)n * 8);
-  MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-  MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
   { KTimer kt(ctx, KC_PNP_HYP);
   k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
@@ -470,12 +453,57 @@ int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, i
                                              w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
   MVO_CHECK_LAUNCH(ctx);
   ctx->pnp_last_h = H;
+  // the refit runs on the consensus set whose size only the device knows: launch it for the
+  // worst case E = n with the real count read on the device (edges beyond n_in are masked out)
+  return pnp_refit(ctx, w, n, cam);
+}
+
+// Device-resident entry points for the tracker (tracker.cpp): reserve the workspace for n correspondences
+// (the caller gathers them into *p3 / *p2 on ctx->stream), then enqueue the whole solvePnPRansac replacement.
+// Results stay on the device: pose_io = [R|t] world->camera after the refit, out_i[0] = consensus-set size
+// (< 4: no model), inl = its ascending indices.
+int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **pose_io, int32_t **out_i, int32_t **inl) {
+  PnpWs w;
+  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  *p3 = w.p3; *p2 = w.p2; *pose_io = w.pose_io; *out_i = w.out_i; *inl = w.inl;
+  return MVO_OK;
+}
+
+int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K) {
+  if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: %d correspondences (< 4)", n);
+  PnpCam cam;
+  MVO_TRY(pnp_cam(ctx, K, &cam));
+  PnpWs w;
+  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  return pnp_enqueue(ctx, w, n, cam);
+}
+
+extern "C" {
+
+int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, const double *K,
+                         double *rvec, double *tvec, int32_t *inliers, int *n_inliers) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!pts3d || !pts2d || !rvec || !tvec || !n_inliers || (*n_inliers > 0 && !inliers))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "solvePnPRansac: null pointer");
+  if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: %d correspondences (< 4)", n);
+  PnpCam cam;
+  MVO_TRY(pnp_cam(ctx, K, &cam));
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int H = ctx->prm.pnp_hypotheses;
+  PnpWs w;
+  MVO_TRY(pnp_ws(ctx, n, H, &w));
+  if ((size_t)n * 20 > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
+  const size_t hb = (size_t)n * 20 + (size_t)n * 4 + 1024;
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, hb));
+  float *h3 = (float *)ctx->h_b.p, *h2 = h3 + (size_t)n * 3;
+  memcpy(h3, pts3d, (size_t)n * 12);
+  memcpy(h2, pts2d, (size_t)n * 8);
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p3, h3, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_TRY(pnp_enqueue(ctx, w, n, cam));
   uint8_t *hout = (uint8_t *)ctx->h_b.p + (size_t)n * 20;
   double *h_pose = (double *)hout;
   int32_t *h_i = (int32_t *)(hout + 128), *h_inl = (int32_t *)(hout + 256);
-  // the refit runs on the consensus set whose size only the device knows: launch it for the
-  // worst case E = n with the real count read on the device (edges beyond n_in are masked out)
-  MVO_TRY(pnp_refit(ctx, w, n, cam));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_pose, w.pose_io, 96, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_i, w.out_i, 16, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, w.inl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

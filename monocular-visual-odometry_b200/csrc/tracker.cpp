@@ -2,55 +2,57 @@
 // vo::VisualOdometry::addFrame (reference src/vo/vo_addFrame.cpp:71-91) with its callees
 // getMappointsInCurrentView_ (src/vo/vo.cpp:16-49), poseEstimationPnP_ (:267-381) and
 // callBundleAdjustment_ (:384-478).  Host logic in C++ like the reference; every numeric stage
-// goes through the C ABI of this library (no CPU fallback anywhere).
+// runs on the GPU (no CPU fallback anywhere).
+//
+// Two implementations of the same step, selected by mvo_track_params::device_resident:
+//   * device-resident (default, shipped configuration = fixed map points): the map (points + descriptors),
+//     the frame buffer (pose + inlier connections of the newest kBuffSize_ frames) and the BA graph live in
+//     HBM.  Per frame the host synchronises twice: after the match kernel (the reference's duplicate removal
+//     is an unstable libstdc++ std::sort whose result has to be reproduced on the host) and at the end of the
+//     frame (poses and counters, ~3 KB).  Everything in between is launched back to back on one stream.
+//   * host-array: every stage through its public C-ABI entry point (mvo_match_features, mvo_solve_pnp_ransac,
+//     mvo_bundle_adjustment), as a maintainer who only swaps the bodies of the reference functions gets it.
+// ORB extraction does not depend on the VO state: a worker thread owns two extraction contexts
+// (own stream + workspace each) and runs frame i+1 — upload, kernels, the rare host retainBest path — while
+// frame i is tracked.
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
 #include <stdlib.h>
 #include <math.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include "mvo_internal.h"
 
+namespace {
+
 struct TrackedFrame {
   double T_w_c[16];
-  // inliers_to_mappt_connections_: keypoint pixel + map point index, in insertion order
+  // inliers_to_mappt_connections_: keypoint pixel + map point index, in insertion order (host-array path)
   std::vector<float> obs_xy;
   std::vector<int32_t> map_idx;
+  // device-resident path: the same list lives in ring slot `slot` of the device frame buffer
+  int slot = -1;
+  int n_links = 0;
 };
 
-struct mvo_tracker {
-  mvo_ctx *ctx = nullptr;
-  double K[9];
-  int rows = 0, cols = 0;
-  mvo_track_params prm;
-  std::vector<float> map_pts;        // n x 3
-  std::vector<uint8_t> map_desc;     // n x 32
-  std::deque<TrackedFrame> frames;   // frames_buff_ (oldest first)
-  double T_ref[16];                  // reference keyframe pose (initial guess for the next frame)
-  bool has_prev = false;
-  double T_prev[16];
-  // scratch
-  std::vector<mvo_keypoint> kpts;
+// One extraction in flight per slot; the worker thread runs them in submission order.
+struct ExtractJob {
+  std::atomic<int> state{0};           // 0 free, 1 queued, 2 done
+  const uint8_t *image = nullptr;
+  int channels = 0, on_device = 0;
+  size_t stride = 0;
+  bool want_host = false;
+  int rc = MVO_OK, nk = 0;
+  const mvo_keypoint *d_k = nullptr;
+  const uint8_t *d_d = nullptr;
+  std::vector<mvo_keypoint> kpts;      // want_host only
   std::vector<uint8_t> desc;
-  std::vector<uint8_t> cand_desc;
-  std::vector<float> cand_xy, kp_xy, p3, p2;
-  std::vector<int32_t> cand_idx, inliers;
-  std::vector<mvo_dmatch> matches;
-  // BA assembly scratch (capacity reused across frames)
-  std::vector<double> ba_poses;
-  std::vector<int> ba_which;
-  std::vector<int32_t> ba_ef, ba_ep, ba_used, ba_remap, ba_stamp;
-  std::vector<float> ba_ob, ba_pts;
-  int32_t ba_gen = 0;
-  // extraction runs on two alternating contexts (own stream + workspace each) so that frame i+1 can be
-  // extracted while frame i is being tracked: extraction does not depend on the VO state
-  mvo_ctx *xctx[2] = {nullptr, nullptr};
-  const uint8_t *pend_img[2] = {nullptr, nullptr};
-  bool pend[2] = {false, false};
-  unsigned n_submit = 0, n_consume = 0;
 };
-
-namespace {
 
 void inv_rigid(const double *T, double *Ti) {     // [R t; 0 1]^-1 = [R^T, -R^T t]
   for (int i = 0; i < 3; ++i) {
@@ -59,6 +61,22 @@ void inv_rigid(const double *T, double *Ti) {     // [R t; 0 1]^-1 = [R^T, -R^T 
   }
   Ti[12] = Ti[13] = Ti[14] = 0;
   Ti[15] = 1;
+}
+
+// camera->world 4x4  ->  world->camera [R (9) | t (3)], and back (g2o_ba.cpp:183-190, :298-305)
+void Twc_to_Rt12(const double *T, double *q) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) q[i * 3 + j] = T[j * 4 + i];
+    q[9 + i] = -(T[0 * 4 + i] * T[3] + T[1 * 4 + i] * T[7] + T[2 * 4 + i] * T[11]);
+  }
+}
+void Rt12_to_Twc(const double *p, double *T) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T[i * 4 + j] = p[j * 3 + i];
+    T[i * 4 + 3] = -(p[i] * p[9] + p[3 + i] * p[10] + p[6 + i] * p[11]);
+  }
+  T[12] = T[13] = T[14] = 0;
+  T[15] = 1;
 }
 
 void rvec_to_R(const double *w, double *R) {      // cv::Rodrigues
@@ -77,7 +95,227 @@ double trans_dist(const double *Ta, const double *Tb) {
   return sqrt(dx * dx + dy * dy + dz * dz);
 }
 
+double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct MatchPair { int32_t train, map; };   // proxy record for removeDuplicatedMatches (see dedup_pairs)
+
 }  // namespace
+
+struct mvo_tracker {
+  mvo_ctx *ctx = nullptr;
+  double K[9];
+  int rows = 0, cols = 0;
+  mvo_track_params prm;
+  std::vector<float> map_pts;        // n x 3
+  std::vector<uint8_t> map_desc;     // n x 32
+  std::deque<TrackedFrame> frames;   // frames_buff_ (oldest first)
+  double T_ref[16];                  // reference keyframe pose (initial guess for the next frame)
+  bool has_prev = false;
+  double T_prev[16];
+  unsigned frame_counter = 0;
+  // scratch (host-array path)
+  std::vector<uint8_t> cand_desc;
+  std::vector<float> cand_xy, kp_xy, p3, p2;
+  std::vector<int32_t> cand_idx, inliers;
+  std::vector<mvo_dmatch> matches;
+  std::vector<double> ba_poses;
+  std::vector<int> ba_which;
+  std::vector<int32_t> ba_ef, ba_ep, ba_used, ba_remap, ba_stamp;
+  std::vector<float> ba_ob, ba_pts;
+  int32_t ba_gen = 0;
+  std::vector<MatchPair> pairs;      // device-resident path
+  // extraction worker
+  mvo_ctx *xctx[2] = {nullptr, nullptr};
+  ExtractJob job[2];
+  unsigned n_submit = 0, n_consume = 0;
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  bool stop = false;
+  unsigned n_run = 0;                // worker-side cursor
+  // device-resident state (one allocation, carved in dev_alloc)
+  uint8_t *dev = nullptr;
+  size_t dev_bytes = 0;
+  int dev_nmap = -1, dev_cap = 0, dev_ring = 0;
+  float *d_map_pts = nullptr;  uint8_t *d_map_desc = nullptr;
+  uint8_t *d_keysvis = nullptr;        // [keys nmap*2 u32][vis nmap u8] — one D2H after the match
+  float *d_cxy = nullptr, *d_kxy = nullptr;
+  int32_t *d_pairs = nullptr, *d_edge_map = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
+  float *d_edge_obs = nullptr;
+  double *d_pose = nullptr, *d_res = nullptr, *d_stats = nullptr;
+  uint8_t *h_pin = nullptr;            // pinned staging: [keys+vis][pairs][results]
+  size_t h_pin_bytes = 0;
+};
+
+namespace {
+
+void worker_main(mvo_tracker *t) {
+  for (;;) {
+    ExtractJob *j = nullptr;
+    int slot = 0;
+    {
+      std::unique_lock<std::mutex> lk(t->mu);
+      t->cv_job.wait(lk, [&] { return t->stop || t->job[t->n_run & 1].state.load(std::memory_order_acquire) == 1; });
+      if (t->stop) return;
+      slot = t->n_run & 1;
+      j = &t->job[slot];
+    }
+    mvo_ctx *x = t->xctx[slot];
+    int rc, nk = 0;
+    if (j->want_host) {
+      const int cap = x->prm.max_keypoints + 1;
+      j->kpts.resize(cap);
+      j->desc.resize((size_t)cap * 32);
+      nk = cap;
+      rc = mvo_orb_extract_begin(x, j->image, t->rows, t->cols, j->channels, j->stride, j->on_device);
+      if (rc == MVO_OK) rc = mvo_orb_extract_end(x, j->kpts.data(), &nk, j->desc.data(), &j->d_d);
+    } else {
+      rc = mvo_orb_extract_begin_dev(x, j->image, t->rows, t->cols, j->channels, j->stride, j->on_device);
+      if (rc == MVO_OK) rc = mvo_orb_extract_end_dev(x, &nk, &j->d_k, &j->d_d);
+    }
+    j->rc = rc;
+    j->nk = nk;
+    {
+      std::lock_guard<std::mutex> lk(t->mu);
+      ++t->n_run;
+      j->state.store(2, std::memory_order_release);
+    }
+    t->cv_done.notify_all();
+  }
+}
+
+// wait for the extraction in `slot`; spins briefly (the usual case: already done) before sleeping
+void wait_job(mvo_tracker *t, int slot) {
+  ExtractJob &j = t->job[slot];
+  for (int spin = 0; spin < 2000; ++spin)
+    if (j.state.load(std::memory_order_acquire) == 2) return;
+  std::unique_lock<std::mutex> lk(t->mu);
+  t->cv_done.wait(lk, [&] { return j.state.load(std::memory_order_acquire) == 2; });
+}
+
+void drain_jobs(mvo_tracker *t) {
+  while (t->n_consume != t->n_submit) {
+    const int slot = t->n_consume & 1;
+    wait_job(t, slot);
+    t->job[slot].state.store(0, std::memory_order_release);
+    ++t->n_consume;
+  }
+}
+
+bool use_device_path(const mvo_tracker *t) { return t->prm.device_resident && t->prm.ba_fix_points; }
+
+size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// (Re)allocate the device-resident state for the current map size / keypoint capacity / ring size.
+int dev_alloc(mvo_tracker *t) {
+  mvo_ctx *ctx = t->ctx;
+  const int nmap = (int)(t->map_pts.size() / 3), cap = ctx->prm.max_keypoints + 1, ring = t->prm.buffer_size;
+  if (t->dev && nmap == t->dev_nmap && cap == t->dev_cap && ring == t->dev_ring) return MVO_OK;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const bool keep_frames = t->dev && cap == t->dev_cap && ring == t->dev_ring;   // a map swap keeps the frame buffer
+  const int nm1 = std::max(nmap, 1);
+  size_t o = 0;
+  const size_t o_pts = o;   o = al256(o + (size_t)nm1 * 12);
+  const size_t o_desc = o;  o = al256(o + (size_t)nm1 * 32);
+  const size_t o_kv = o;    o = al256(o + (size_t)nm1 * 9);
+  const size_t o_cxy = o;   o = al256(o + (size_t)nm1 * 8);
+  const size_t o_kxy = o;   o = al256(o + (size_t)cap * 8);
+  const size_t o_pairs = o; o = al256(o + (size_t)nm1 * 8);
+  const size_t o_frames = o;
+  const size_t o_emap = o;  o = al256(o + (size_t)ring * cap * 4);
+  const size_t o_eobs = o;  o = al256(o + (size_t)ring * cap * 8);
+  const size_t o_cnt = o;   o = al256(o + (size_t)ring * 4);
+  const size_t o_pose = o;  o = al256(o + (size_t)ring * 96);
+  const size_t o_flags = o; o = al256(o + 256);       // [0] BA skip flag, [8..] res_i (3), [16..] out_info (2 + 16)
+  const size_t o_res = o;   o = al256(o + 256);       // res_d (12 doubles)
+  const size_t o_stats = o; o = al256(o + 256);       // BA stats (16 doubles)
+  uint8_t *nd = nullptr;
+  MVO_CUDA(ctx, cudaMalloc(&nd, o));
+  MVO_CUDA(ctx, cudaMemsetAsync(nd, 0, o, ctx->stream));
+  if (keep_frames) {
+    const size_t old_frames = (uint8_t *)t->d_edge_map - t->dev;
+    MVO_CUDA(ctx, cudaMemcpyAsync(nd + o_frames, t->dev + old_frames, o_flags - o_frames, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (t->dev) cudaFree(t->dev);
+  t->dev = nd; t->dev_bytes = o; t->dev_nmap = nmap; t->dev_cap = cap; t->dev_ring = ring;
+  t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis = nd + o_kv;
+  t->d_cxy = (float *)(nd + o_cxy); t->d_kxy = (float *)(nd + o_kxy); t->d_pairs = (int32_t *)(nd + o_pairs);
+  t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs); t->d_cnt = (int32_t *)(nd + o_cnt);
+  t->d_pose = (double *)(nd + o_pose); t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res);
+  t->d_stats = (double *)(nd + o_stats);
+  const size_t hb = al256((size_t)nm1 * 9) + al256((size_t)nm1 * 8) + al256((size_t)ring * 96) + 1024;
+  if (hb > t->h_pin_bytes) {
+    if (t->h_pin) cudaFreeHost(t->h_pin);
+    t->h_pin = nullptr;
+    MVO_CUDA(ctx, cudaMallocHost(&t->h_pin, hb));
+    t->h_pin_bytes = hb;
+  }
+  if (nmap > 0) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_map_pts, t->map_pts.data(), (size_t)nmap * 12, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_map_desc, t->map_desc.data(), (size_t)nmap * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MVO_OK;
+}
+
+// geometry::removeDuplicatedMatches (feature_match.cpp:241-260) on (train, map) records.  libstdc++'s std::sort
+// decides from comparison results and element COUNTS only, so sorting these 8-byte records with the same
+// comparator applies exactly the permutation it applies to the reference's cv::DMatch array
+// (tests/test_capi_symbols.py::test_dedup_proxy_matches_dmatch_sort).
+void dedup_pairs(std::vector<MatchPair> &v) {
+  std::sort(v.begin(), v.end(), [](const MatchPair &a, const MatchPair &b) { return a.train < b.train; });
+  size_t w = 0;
+  for (size_t i = 0; i < v.size(); ++i)
+    if (i == 0 || v[i].train != v[i - 1].train) v[w++] = v[i];
+  v.resize(w);
+}
+
+}  // namespace
+
+// exported for the CPU-side test of the proxy sort (not part of mvo.h: test hook)
+extern "C" int mvo_test_dedup_pairs(int32_t *train, int32_t *map, int *n) {
+  if (!train || !map || !n) return MVO_ERR_INVALID_ARG;
+  std::vector<MatchPair> v(*n);
+  for (int i = 0; i < *n; ++i) v[i] = MatchPair{train[i], map[i]};
+  dedup_pairs(v);
+  for (size_t i = 0; i < v.size(); ++i) { train[i] = v[i].train; map[i] = v[i].map; }
+  *n = (int)v.size();
+  return MVO_OK;
+}
+
+static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device) {
+  mvo_ctx *ctx = t->ctx;
+  if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null image");
+  if (t->n_submit - t->n_consume >= 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: two frames are already in flight");
+  const int slot = t->n_submit & 1;
+  ExtractJob &j = t->job[slot];
+  mvo_ctx *x = t->xctx[slot];
+  MVO_TRY(mvo_set_params(x, &ctx->prm));          // follow parameter changes made on the main context
+  j.image = image; j.channels = channels; j.stride = stride; j.on_device = image_on_device;
+  j.want_host = !use_device_path(t);
+  j.rc = MVO_OK; j.nk = 0; j.d_k = nullptr; j.d_d = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    j.state.store(1, std::memory_order_release);
+  }
+  t->cv_job.notify_one();
+  ++t->n_submit;
+  return MVO_OK;
+}
+
+// checkLargeMoveForAddKeyFrame_ (vo.cpp:247-265), translation part + bookkeeping shared by both paths
+static void finish_frame(mvo_tracker *t, bool pnp_ok, double *T_w_c_out) {
+  if (pnp_ok && trans_dist(t->frames.back().T_w_c, t->T_ref) > t->prm.min_dist_keyframe)
+    memcpy(t->T_ref, t->frames.back().T_w_c, sizeof t->T_ref);
+  memcpy(t->T_prev, t->frames.back().T_w_c, sizeof t->T_prev);
+  t->has_prev = true;
+  memcpy(T_w_c_out, t->frames.back().T_w_c, 16 * sizeof(double));
+}
+
+static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res);
+static int track_host_arrays(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res);
 
 extern "C" {
 
@@ -94,6 +332,8 @@ void mvo_default_track_params(mvo_track_params *p) {
   p->ba_fix_points = 1;           // :123
   p->information[0] = 1; p->information[1] = 0; p->information[2] = 0; p->information[3] = 1;   // :122
   p->buffer_size = 20;            // include/my_slam/vo/vo.h:77
+  p->ba_step_tol = 1e-9;
+  p->device_resident = 1;
 }
 
 int mvo_tracker_create(mvo_ctx *ctx, const double *K, int rows, int cols, const mvo_track_params *params,
@@ -108,7 +348,8 @@ int mvo_tracker_create(mvo_ctx *ctx, const double *K, int rows, int cols, const 
   t->cols = cols;
   if (params) t->prm = *params;
   else mvo_default_track_params(&t->prm);
-  if (t->prm.match_method < 1 || t->prm.match_method > 3 || t->prm.ba_window < 1 || t->prm.buffer_size < 2) {
+  if (t->prm.match_method < 1 || t->prm.match_method > 3 || t->prm.ba_window < 1 || t->prm.ba_window > 16 ||
+      t->prm.buffer_size < 2 || t->prm.buffer_size > 4096 || !(t->prm.ba_step_tol >= 0)) {
     delete t;
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: bad parameters");
   }
@@ -121,38 +362,41 @@ int mvo_tracker_create(mvo_ctx *ctx, const double *K, int rows, int cols, const 
       return mvo_fail(ctx, rc, "tracker: cannot create the extraction context");
     }
   }
+  t->worker = std::thread(worker_main, t);
   *out = t;
   return MVO_OK;
 }
 
 void mvo_tracker_destroy(mvo_tracker *t) {
   if (!t) return;
+  if (t->worker.joinable()) {
+    drain_jobs(t);
+    {
+      std::lock_guard<std::mutex> lk(t->mu);
+      t->stop = true;
+    }
+    t->cv_job.notify_all();
+    t->worker.join();
+  }
   for (int k = 0; k < 2; ++k)
     if (t->xctx[k]) mvo_destroy(t->xctx[k]);
+  if (t->dev) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); cudaFree(t->dev); }
+  if (t->h_pin) cudaFreeHost(t->h_pin);
   delete t;
 }
 
 int mvo_tracker_prefetch(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device) {
   if (!t) return MVO_ERR_INVALID_ARG;
-  mvo_ctx *ctx = t->ctx;
-  if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null image");
-  const int slot = t->n_submit & 1;
-  if (t->pend[slot]) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: two frames are already in flight");
-  mvo_ctx *x = t->xctx[slot];
-  MVO_TRY(mvo_set_params(x, &ctx->prm));          // follow parameter changes made on the main context
-  const int rc = mvo_orb_extract_begin(x, image, t->rows, t->cols, channels, stride, image_on_device);
-  if (rc != MVO_OK) return mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(x));
-  t->pend[slot] = true;
-  t->pend_img[slot] = image;
-  ++t->n_submit;
-  return MVO_OK;
+  return submit_extraction(t, image, channels, stride, image_on_device);
 }
 
 int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc, int n) {
   if (!t) return MVO_ERR_INVALID_ARG;
   if (n < 0 || (n > 0 && (!pts3d || !desc))) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: null map");
+  if (n > 65535) return mvo_fail(t->ctx, MVO_ERR_UNSUPPORTED, "tracker: more than 65535 map points");
   t->map_pts.assign(pts3d, pts3d + (size_t)n * 3);
   t->map_desc.assign(desc, desc + (size_t)n * 32);
+  t->dev_nmap = -1;                 // the device copy is refreshed by the next tracked frame
   return MVO_OK;
 }
 
@@ -161,22 +405,19 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref) {
   memcpy(t->T_ref, T_w_c_ref, sizeof t->T_ref);
   t->frames.clear();
   t->has_prev = false;
-  // drop frames that were prefetched but never tracked
-  for (int k = 0; k < 2; ++k)
-    if (t->pend[k]) {
-      const int cap = t->ctx->prm.max_keypoints + 1;
-      t->kpts.resize(cap);
-      t->desc.resize((size_t)cap * 32);
-      int nk = cap;
-      mvo_orb_extract_end(t->xctx[k], t->kpts.data(), &nk, t->desc.data(), nullptr);
-      t->pend[k] = false;
-    }
+  t->frame_counter = 0;
+  drain_jobs(t);                    // drop frames that were prefetched but never tracked
   t->n_submit = t->n_consume = 0;
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    t->n_run = 0;
+  }
   return MVO_OK;
 }
 
 int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask) {
   if (!t) return MVO_ERR_INVALID_ARG;
+  if (t->n_submit != t->n_consume) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: timing calls need an idle tracker (frames are in flight)");
   MVO_TRY(mvo_timing_enable(t->ctx, mask));
   for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_enable(t->xctx[k], mask));
   return MVO_OK;
@@ -184,6 +425,7 @@ int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask) {
 
 int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts) {
   if (!t) return MVO_ERR_INVALID_ARG;
+  if (t->n_submit != t->n_consume) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: timing calls need an idle tracker (frames are in flight)");
   MVO_TRY(mvo_timing_read(t->ctx, ms, counts));
   for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_read(t->xctx[k], ms, counts));
   return MVO_OK;
@@ -205,36 +447,230 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   if (!t) return MVO_ERR_INVALID_ARG;
   mvo_ctx *ctx = t->ctx;
   if (!image || !T_w_c_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
+  // take the frame from the prefetch queue, or extract it now
+  if (t->n_submit != t->n_consume && t->job[t->n_consume & 1].image != image)
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: frames must be tracked in the order they were prefetched");
+  if (t->n_submit == t->n_consume) MVO_TRY(submit_extraction(t, image, channels, stride, image_on_device));
+  const int slot = t->n_consume & 1;
+  ExtractJob &job = t->job[slot];
+  const bool dev_path = !job.want_host;
+  if (dev_path) {
+    // the device copy of the map is refreshed while the extraction runs
+    const int rc = dev_alloc(t);
+    if (rc != MVO_OK) { wait_job(t, slot); job.state.store(0, std::memory_order_release); ++t->n_consume; return rc; }
+  }
+  wait_job(t, slot);
+  ++t->n_consume;
+  int rc = job.rc;
+  if (rc != MVO_OK) rc = mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(t->xctx[slot]));
+  else rc = dev_path ? track_device(t, job, T_w_c_out, res) : track_host_arrays(t, job, T_w_c_out, res);
+  job.state.store(0, std::memory_order_release);
+  return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// device-resident path
+// ------------------------------------------------------------------------------------------------------------
+static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res) {
+  mvo_ctx *ctx = t->ctx;
   mvo_track_result r;
   memset(&r, 0, sizeof r);
   static const bool dbg = getenv("MVO_TRACK_DEBUG") != nullptr;
   static double acc[8] = {0};
   static int nacc = 0;
-  auto tnow = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  double t0 = dbg ? tnow() : 0;
-#define TMARK(i) do { if (dbg) { const double t_ = tnow(); acc[i] += t_ - t0; t0 = t_; } } while (0)
-  const int cap = ctx->prm.max_keypoints + 1;
+  double t0 = dbg ? now_us() : 0;
+#define TMARK(i) do { if (dbg) { const double t_ = now_us(); acc[i] += t_ - t0; t0 = t_; } } while (0)
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int nmap = t->dev_nmap, cap = t->dev_cap, nk = job.nk;
+  const int method = t->prm.match_method;
+  r.n_keypoints = nk;
 
-  // pushFrameToBuff_ (vo.h:81-86) + Frame::calcKeyPoints / calcDescriptors
+  // pushFrameToBuff_ (vo.h:81-86)
   t->frames.emplace_back();
   if ((int)t->frames.size() > t->prm.buffer_size) t->frames.pop_front();
   TrackedFrame &cur = t->frames.back();
-  t->kpts.resize(cap);
-  t->desc.resize((size_t)cap * 32);
-  int nk = cap;
-  // take the frame from the prefetch queue, or extract it now
-  const int slot = t->n_consume & 1;
-  if (t->pend[slot] && t->pend_img[slot] != image) { t->frames.pop_back(); return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: frames must be tracked in the order they were prefetched"); }
-  if (!t->pend[slot]) {
-    const int rc0 = mvo_tracker_prefetch(t, image, channels, stride, image_on_device);
-    if (rc0 != MVO_OK) { t->frames.pop_back(); return rc0; }
+  cur.slot = (int)(t->frame_counter++ % (unsigned)t->dev_ring);
+  // curr_->T_w_c_ = ref_->T_w_c_.clone()  (vo_addFrame.cpp:74): initial guess = reference keyframe
+  memcpy(cur.T_w_c, t->T_ref, sizeof cur.T_w_c);
+
+  // ---- getMappointsInCurrentView_ + matchFeatures(map descriptors, frame descriptors) (vo.cpp:16-49, 283-289) ----
+  uint32_t *d_keys = (uint32_t *)t->d_keysvis;
+  uint8_t *d_vis = t->d_keysvis + (size_t)std::max(nmap, 1) * 8;
+  const bool can_match = nmap > 0 && nk > 0 && !(method == 2 && nk < 2);
+  const uint32_t *h_keys = (const uint32_t *)t->h_pin;
+  const uint8_t *h_vis = t->h_pin + (size_t)std::max(nmap, 1) * 8;
+  if (nmap > 0) {
+    double Tcw[12];
+    Twc_to_Rt12(cur.T_w_c, Tcw);
+    int rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
+    if (rc == MVO_OK && can_match) {
+      if (method == 3) rc = mvo_track_kpt_xy(ctx, job.d_k, nk, t->d_kxy);
+      if (rc == MVO_OK)
+        rc = mvo_match_launch_masked(ctx, method == 1 ? 0 : (method == 2 ? 1 : 2), t->d_map_desc, t->d_cxy, nmap, job.d_d, t->d_kxy, nk,
+                                     t->prm.match_radius, d_keys, d_vis);
+    }
+    if (rc != MVO_OK) { t->frames.pop_back(); return rc; }
+    // one D2H: [keys | visibility flags]
+    const size_t off = can_match ? 0 : (size_t)nmap * 8, len = (size_t)nmap * 9 - off;
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->h_pin + off, t->d_keysvis + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  mvo_ctx *x = t->xctx[slot];
-  const uint8_t *d_desc = nullptr;
-  t->pend[slot] = false;
-  ++t->n_consume;
-  int rc = mvo_orb_extract_end(x, t->kpts.data(), &nk, t->desc.data(), &d_desc);
-  if (rc != MVO_OK) { t->frames.pop_back(); return mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(x)); }
+  TMARK(0);
+
+  // thresholds of matchFeatures (feature_match.cpp:179-217) and removeDuplicatedMatches (:241-260), on the host
+  std::vector<MatchPair> &pairs = t->pairs;
+  pairs.clear();
+  int ncand = 0;
+  for (int q = 0; q < nmap; ++q) ncand += h_vis[q];
+  r.n_candidates = ncand;
+  if (can_match && ncand > 0) {
+    if (method == 1 || method == 3) {
+      const bool sad = method == 3;
+      double min_dis = 9999999, max_dis = 0;
+      for (int q = 0; q < nmap; ++q) {
+        if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
+        const uint32_t d = h_keys[q] >> 16;
+        const double dist = sad ? (double)(float)((double)d / 32.0) : (double)(float)d;
+        if (dist < min_dis) min_dis = dist;
+        if (dist > max_dis) max_dis = dist;
+      }
+      const double thr = std::max<float>(min_dis * ctx->prm.xiang_gao_ratio, 30.0);
+      for (int q = 0; q < nmap; ++q) {
+        if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
+        const uint32_t d = h_keys[q] >> 16;
+        const float dist = sad ? (float)((double)d / 32.0) : (float)d;
+        if (dist < thr) pairs.push_back(MatchPair{(int32_t)(h_keys[q] & 0xFFFFu), q});
+      }
+    } else {
+      for (int q = 0; q < nmap; ++q) {
+        if (!h_vis[q]) continue;
+        const uint32_t k0 = h_keys[2 * q], k1 = h_keys[2 * q + 1];
+        const double dist = (float)(k0 >> 16);
+        if (dist < ctx->prm.lowe_ratio * (float)(k1 >> 16)) pairs.push_back(MatchPair{(int32_t)(k0 & 0xFFFFu), q});
+      }
+    }
+    dedup_pairs(pairs);
+  }
+  const int nm = (int)pairs.size();
+  r.n_matches = nm;
+  TMARK(1);
+
+  // ---- poseEstimationPnP_ (vo.cpp:293-381) + callBundleAdjustment_ (:384-478), enqueued back to back ----
+  int32_t *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
+  MvoTrackGlue g;
+  memset(&g, 0, sizeof g);
+  g.mode = nm >= t->prm.min_pnp_points && nm >= 4;
+  g.slot = cur.slot; g.cap = cap; g.ba_enable = t->prm.ba_enable; g.has_prev = t->has_prev;
+  g.max_dist = t->prm.max_dist_to_prev;
+  if (t->has_prev) { g.prev_twc[0] = t->T_prev[3]; g.prev_twc[1] = t->T_prev[7]; g.prev_twc[2] = t->T_prev[11]; }
+  const double *T_fallback = t->has_prev ? t->T_prev : cur.T_w_c;     // vo.cpp:376-379
+  Twc_to_Rt12(T_fallback, g.fallback);
+  g.pairs = t->d_pairs; g.kpts = job.d_k;
+  g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.cnt = t->d_cnt; g.pose = t->d_pose;
+  g.skip_flag = t->d_flags; g.res_i = d_res_i; g.res_d = t->d_res;
+  int rc = MVO_OK;
+  if (g.mode) {
+    int32_t *h_pairs = (int32_t *)(t->h_pin + al256((size_t)std::max(nmap, 1) * 9));
+    for (int i = 0; i < nm; ++i) { h_pairs[2 * i] = pairs[i].map; h_pairs[2 * i + 1] = pairs[i].train; }
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pairs, h_pairs, (size_t)nm * 8, cudaMemcpyHostToDevice, ctx->stream));
+    float *d_p3, *d_p2;
+    double *d_pose_io;
+    int32_t *d_out_i, *d_inl;
+    rc = mvo_pnp_dev_buffers(ctx, nm, &d_p3, &d_p2, &d_pose_io, &d_out_i, &d_inl);
+    if (rc == MVO_OK) rc = mvo_track_gather_pairs(ctx, t->d_pairs, nm, t->d_map_pts, job.d_k, d_p3, d_p2);
+    if (rc == MVO_OK) rc = mvo_pnp_dev_run(ctx, nm, t->K);
+    g.pose_io = d_pose_io; g.out_i = d_out_i; g.inl = d_inl;
+  }
+  if (rc == MVO_OK) rc = mvo_track_glue(ctx, g);
+  // the BA window: newest min(ba_window, total-1) frames (vo.cpp:417-419); frames with < 3 links drop out on the
+  // device (:423-426), where the newest frame's link count is known
+  MvoPoseStore st;
+  memset(&st, 0, sizeof st);
+  int e_upper = 0;
+  const int total = (int)t->frames.size();
+  const bool try_ba = rc == MVO_OK && g.mode && t->prm.ba_enable;
+  if (try_ba) {
+    const int nba = std::min(t->prm.ba_window, total - 1);
+    for (int b = total - 1; b >= total - nba; --b) {
+      const TrackedFrame &f = t->frames[b];
+      st.slot[st.nslots++] = f.slot;
+      e_upper += (b == total - 1) ? nm : f.n_links;
+    }
+    if (st.nslots > 0) {
+      st.map_pts = t->d_map_pts; st.edge_map = t->d_edge_map; st.edge_obs = (const float2 *)t->d_edge_obs; st.cnt = t->d_cnt;
+      st.pose = t->d_pose; st.cap = cap; st.min_links = 3; st.skip_flag = t->d_flags; st.out_info = d_out_info;
+      rc = mvo_ba_pose_store_launch(ctx, st, e_upper, t->K[0], t->K[0], t->K[2], t->K[5], t->prm.information, ctx->prm.ba_iterations,
+                                    ctx->prm.ba_huber_delta > 0, ctx->prm.ba_huber_delta, t->prm.ba_step_tol, t->d_stats);
+    }
+  }
+  if (rc != MVO_OK) { cudaStreamSynchronize(ctx->stream); t->frames.pop_back(); return rc; }
+  // one D2H: [flags / counters / graph info (256 B)][pose before BA (256 B)][BA stats (256 B)] + the pose ring
+  uint8_t *h_out = t->h_pin + al256((size_t)std::max(nmap, 1) * 9) + al256((size_t)std::max(nmap, 1) * 8);
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_out, t->d_flags, 768, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_out + 768, t->d_pose, (size_t)t->dev_ring * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  TMARK(2);
+  const int32_t *h_flags = (const int32_t *)h_out;
+  const int32_t *h_res_i = h_flags + 8, *h_info = h_flags + 16;
+  const double *h_res_d = (const double *)(h_out + 256), *h_stats = (const double *)(h_out + 512);
+  const double *h_ring = (const double *)(h_out + 768);
+  const bool pnp_ok = h_res_i[1] != 0;
+  r.n_inliers = h_res_i[2];
+  r.pnp_ok = pnp_ok;
+  cur.n_links = h_res_i[2];
+  if (pnp_ok) Rt12_to_Twc(h_res_d, cur.T_w_c);
+  else if (t->has_prev) memcpy(cur.T_w_c, t->T_prev, sizeof cur.T_w_c);
+  memcpy(r.T_w_c_pnp, cur.T_w_c, sizeof r.T_w_c_pnp);
+  if (try_ba && st.nslots > 0 && pnp_ok) {
+    const int F = h_info[0];
+    if (F < 0) { t->frames.pop_back(); return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "tracker: BA graph exceeds the device-resident kernel"); }
+    for (int f = 0; f < F; ++f) {
+      const int s = h_info[2 + f];
+      for (int b = total - 1; b >= 0; --b)
+        if (t->frames[b].slot == s) { Rt12_to_Twc(h_ring + (size_t)s * 12, t->frames[b].T_w_c); break; }
+    }
+    r.ba_frames = F;
+    r.ba_edges = h_info[1];
+    static const bool ba_dbg = getenv("MVO_BA_DEBUG") != nullptr;
+    if (ba_dbg)
+      fprintf(stderr, "k_ba_pose(store): F=%d E=%d it=%.0f trials=%.0f cycles solve=%.0f pass=%.0f gather=%.0f decide=%.0f\n", F, h_info[1],
+              h_stats[2], h_stats[15], h_stats[8], h_stats[9], h_stats[10], h_stats[11]);
+  }
+  TMARK(3);
+  if (dbg && ++nacc % 50 == 0) {
+    fprintf(stderr, "tracker(device) us/frame: project+match+sync %.1f filter+dedup %.1f pnp+ba+sync %.1f finish %.1f\n", acc[0] / 50, acc[1] / 50,
+            acc[2] / 50, acc[3] / 50);
+    for (double &a : acc) a = 0;
+  }
+#undef TMARK
+  finish_frame(t, pnp_ok, T_w_c_out);
+  if (res) *res = r;
+  return MVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host-array path: every stage through its public C-ABI entry point
+// ------------------------------------------------------------------------------------------------------------
+static int track_host_arrays(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res) {
+  mvo_ctx *ctx = t->ctx;
+  mvo_track_result r;
+  memset(&r, 0, sizeof r);
+  static const bool dbg = getenv("MVO_TRACK_DEBUG") != nullptr;
+  static double acc[8] = {0};
+  static int nacc = 0;
+  double t0 = dbg ? now_us() : 0;
+#define TMARK(i) do { if (dbg) { const double t_ = now_us(); acc[i] += t_ - t0; t0 = t_; } } while (0)
+
+  // pushFrameToBuff_ (vo.h:81-86) + Frame::calcKeyPoints / calcDescriptors (done by the extraction worker)
+  t->frames.emplace_back();
+  if ((int)t->frames.size() > t->prm.buffer_size) t->frames.pop_front();
+  TrackedFrame &cur = t->frames.back();
+  const int nk = job.nk;
+  const mvo_keypoint *kpts = job.kpts.data();
+  const uint8_t *d_desc = job.d_d;
+  int rc = MVO_OK;
   r.n_keypoints = nk;
   TMARK(0);
 
@@ -280,7 +716,7 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
 
   // ---- matchFeatures(map descriptors, frame descriptors) (vo.cpp:283-289) ----
   t->kp_xy.resize((size_t)nk * 2);
-  for (int i = 0; i < nk; ++i) { t->kp_xy[2 * i] = t->kpts[i].x; t->kp_xy[2 * i + 1] = t->kpts[i].y; }
+  for (int i = 0; i < nk; ++i) { t->kp_xy[2 * i] = kpts[i].x; t->kp_xy[2 * i + 1] = kpts[i].y; }
   t->matches.resize(nc > 0 ? nc : 1);
   int nm = 0;
   if (nc > 0 && nk > 0 && !(t->prm.match_method == 2 && nk < 2)) {
@@ -295,8 +731,8 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   for (int i = 0; i < nm; ++i) {            // vo.cpp:293-301
     const int mi = t->cand_idx[t->matches[i].query_idx], ki = t->matches[i].train_idx;
     memcpy(&t->p3[3 * i], &t->map_pts[3 * mi], 12);
-    t->p2[2 * i] = t->kpts[ki].x;
-    t->p2[2 * i + 1] = t->kpts[ki].y;
+    t->p2[2 * i] = kpts[ki].x;
+    t->p2[2 * i + 1] = kpts[ki].y;
   }
 
   // ---- poseEstimationPnP_ (vo.cpp:304-381) ----
@@ -312,8 +748,8 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
       r.n_inliers = ni;
       for (int i = 0; i < ni; ++i) {        // vo.cpp:333-354
         const mvo_dmatch &m = t->matches[t->inliers[i]];
-        cur.obs_xy.push_back(t->kpts[m.train_idx].x);
-        cur.obs_xy.push_back(t->kpts[m.train_idx].y);
+        cur.obs_xy.push_back(kpts[m.train_idx].x);
+        cur.obs_xy.push_back(kpts[m.train_idx].y);
         cur.map_idx.push_back(t->cand_idx[m.query_idx]);
       }
       double Tc[16], R[9];
@@ -360,29 +796,28 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
       pts.resize((size_t)used.size() * 3);
       for (size_t k = 0; k < used.size(); ++k) memcpy(&pts[3 * k], &t->map_pts[3 * (size_t)used[k]], 12);
       const int fix = t->prm.ba_fix_points ? 1 : 0;
+      const double saved_tol = ctx->prm.ba_step_tol;
+      ctx->prm.ba_step_tol = t->prm.ba_step_tol;
       rc = mvo_bundle_adjustment(ctx, poses.data(), (int)which.size(), pts.data(), (int)used.size(), ef.data(),
                                  ep.data(), ob.data(), (int)ef.size(), t->K, t->prm.information, fix, !fix, nullptr);
+      ctx->prm.ba_step_tol = saved_tol;
       if (rc != MVO_OK) return rc;
       for (size_t k = 0; k < which.size(); ++k) memcpy(t->frames[which[k]].T_w_c, &poses[16 * k], 16 * sizeof(double));
-      if (!fix)
+      if (!fix) {
         for (size_t k = 0; k < used.size(); ++k) memcpy(&t->map_pts[3 * (size_t)used[k]], &pts[3 * k], 12);
+        t->dev_nmap = -1;
+      }
       r.ba_frames = (int)which.size();
       r.ba_edges = (int)ef.size();
     }
   }
   TMARK(4);
   if (dbg && ++nacc % 50 == 0) {
-    fprintf(stderr, "tracker us/frame: extract %.1f candidates %.1f match %.1f pnp %.1f ba %.1f\n", acc[0] / 50, acc[1] / 50, acc[2] / 50, acc[3] / 50, acc[4] / 50);
+    fprintf(stderr, "tracker(host arrays) us/frame: extract %.1f candidates %.1f match %.1f pnp %.1f ba %.1f\n", acc[0] / 50, acc[1] / 50, acc[2] / 50, acc[3] / 50, acc[4] / 50);
     for (double &a : acc) a = 0;
   }
-  // checkLargeMoveForAddKeyFrame_ (vo.cpp:247-265), translation part: the guess pose follows the camera
-  if (pnp_ok && trans_dist(t->frames.back().T_w_c, t->T_ref) > t->prm.min_dist_keyframe)
-    memcpy(t->T_ref, t->frames.back().T_w_c, sizeof t->T_ref);
-  memcpy(t->T_prev, t->frames.back().T_w_c, sizeof t->T_prev);
-  t->has_prev = true;
-  memcpy(T_w_c_out, t->frames.back().T_w_c, 16 * sizeof(double));
+#undef TMARK
+  finish_frame(t, pnp_ok, T_w_c_out);
   if (res) *res = r;
   return MVO_OK;
 }
-
-}  // extern "C"

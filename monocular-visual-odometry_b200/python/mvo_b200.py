@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("max_pts_per_grid", C.c_int32), ("xiang_gao_ratio", C.c_double), ("lowe_ratio", C.c_double),
         ("pnp_hypotheses", C.c_int32), ("pnp_reproj_error", C.c_float), ("pnp_seed", C.c_uint64),
         ("pnp_refine_iters", C.c_int32), ("ba_iterations", C.c_int32), ("ba_huber_delta", C.c_double),
-        ("ba_fix_first_pose", C.c_int32),
+        ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double),
     ]
 
 
@@ -43,7 +43,8 @@ class TrackParams(C.Structure):
     _fields_ = [("match_method", C.c_int32), ("match_radius", C.c_float), ("min_pnp_points", C.c_int32),
                 ("max_dist_to_prev", C.c_double), ("min_dist_keyframe", C.c_double), ("ba_enable", C.c_int32),
                 ("ba_window", C.c_int32), ("ba_fix_points", C.c_int32), ("information", C.c_double * 4),
-                ("buffer_size", C.c_int32)]
+                ("buffer_size", C.c_int32), ("ba_step_tol", C.c_double), ("device_resident", C.c_int32),
+                ("pad", C.c_int32)]
 
 
 class TrackResult(C.Structure):

@@ -60,3 +60,27 @@ def test_remove_duplicated_matches_host(built):
         assert got.tobytes() == ref.tobytes()
         assert len(np.unique(got["train_idx"])) == len(got)
         assert np.all(np.diff(got["train_idx"]) > 0)
+
+
+def test_dedup_proxy_matches_dmatch_sort(built):
+    """The device-resident tracker removes duplicated matches on 8-byte (train, map) records; libstdc++'s
+    std::sort must apply the same permutation to them as to the reference's 16-byte cv::DMatch array
+    (feature_match.cpp:241-260: unstable sort on trainIdx, first of each run survives)."""
+    import ctypes as C
+    import mvo_b200
+    lib = mvo_b200.load_library()
+    lib.mvo_test_dedup_pairs.restype = C.c_int
+    lib.mvo_test_dedup_pairs.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 2, 15, 16, 17, 33, 300, 1300, 2001, 5000):
+        for spread in (2, 3, 10):
+            m = np.zeros(n, mvo_b200.DMATCH_DTYPE)
+            m["query_idx"] = np.arange(n)                      # = position in the match list before the sort
+            m["train_idx"] = rng.integers(0, max(1, n // spread), n)
+            ref = mvo_b200.remove_duplicated_matches(m)
+            train = np.ascontiguousarray(m["train_idx"], np.int32).copy()
+            tag = np.ascontiguousarray(m["query_idx"], np.int32).copy()
+            cnt = C.c_int(n)
+            assert lib.mvo_test_dedup_pairs(train.ctypes.data, tag.ctypes.data, C.byref(cnt)) == 0
+            assert cnt.value == len(ref)
+            assert np.array_equal(train[: cnt.value], ref["train_idx"]) and np.array_equal(tag[: cnt.value], ref["query_idx"])

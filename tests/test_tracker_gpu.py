@@ -133,3 +133,72 @@ def test_lost_frame_keeps_previous_pose(ctx):
     assert r2.pnp_ok == 0 and r2.n_keypoints == 0 and np.array_equal(T2, T1)     # vo.cpp:376-379
     trk.close()
     ctx.set_params(max_keypoints=1500)
+
+
+def test_device_resident_path_equals_host_array_path(ctx):
+    """The two implementations of the tracking step (map / frame buffer / BA graph resident in HBM vs every stage
+    through its host-array C-ABI entry point) must take the same integer decisions and produce the same poses
+    (PnP pose 1e-12: the only arithmetic difference is the Rodrigues round trip on the host-array path; poses after BA
+    1e-8, the BA parity tolerance: which of g2o's final sub-1e-9 trial steps gets accepted depends on rounding)."""
+    import mvo_b200
+    ctx.set_params(max_keypoints=2000, ba_iterations=10)
+    for method in (1, 2, 3):
+        imgs, _ = _make_sequence(4, 9)
+        pts, desc = _map_from_frame0(ctx, imgs[0])
+        runs = []
+        for dev in (1, 0):
+            trk = mvo_b200.Tracker(ctx, K, 480, 640, device_resident=dev, match_method=method)
+            trk.set_map(pts, desc)
+            trk.reset(np.eye(4))
+            out = []
+            for i in range(1, 9):
+                T, r = trk.track(imgs[i])
+                out.append((T.copy(), (r.n_keypoints, r.n_candidates, r.n_matches, r.n_inliers, r.pnp_ok, r.ba_frames, r.ba_edges),
+                            np.array(r.T_w_c_pnp).reshape(4, 4)))
+            hist = np.array([trk.frame_pose(k) for k in range(6)])
+            runs.append((out, hist))
+            trk.close()
+        (a, ha), (b, hb) = runs
+        for (Ta, ia, Pa), (Tb, ib, Pb) in zip(a, b):
+            assert ia == ib, (method, ia, ib)
+            assert ia[4] == 1 and ia[3] > 100
+            assert np.abs(Pa - Pb).max() < 1e-12 and np.abs(Ta - Tb).max() < 1e-8, (method, np.abs(Ta - Tb).max())
+        assert np.abs(ha - hb).max() < 1e-8
+    ctx.set_params(max_keypoints=1500, ba_iterations=50)
+
+
+def test_ba_step_tolerance_only_skips_negligible_trials(ctx):
+    """ba_step_tol ends the LM once a trial step is below the bound; the trajectory must agree with g2o's full
+    control flow (ba_step_tol = 0) far below the parity tolerance of the poses."""
+    import mvo_b200
+    ctx.set_params(max_keypoints=2000, ba_iterations=10)
+    imgs, _ = _make_sequence(5, 8)
+    pts, desc = _map_from_frame0(ctx, imgs[0])
+    poses = []
+    for tol in (0.0, 1e-9):
+        for dev in (1, 0):
+            trk = mvo_b200.Tracker(ctx, K, 480, 640, ba_step_tol=tol, device_resident=dev)
+            trk.set_map(pts, desc)
+            trk.reset(np.eye(4))
+            poses.append(np.array([trk.track(imgs[i])[0] for i in range(1, 8)]))
+            trk.close()
+    for p in poses[1:]:
+        assert np.abs(p - poses[0]).max() < 2e-8, np.abs(p - poses[0]).max()
+    ctx.set_params(max_keypoints=1500, ba_iterations=50)
+
+
+def test_lost_frame_host_array_path(ctx):
+    import mvo_b200
+    ctx.set_params(max_keypoints=2000)
+    imgs, _ = _make_sequence(2, 3)
+    pts, desc = _map_from_frame0(ctx, imgs[0])
+    trk = mvo_b200.Tracker(ctx, K, 480, 640, device_resident=0)
+    trk.set_map(pts, desc)
+    trk.reset(np.eye(4))
+    T1, r1 = trk.track(imgs[1])
+    T2, r2 = trk.track(np.full((480, 640, 3), 90, np.uint8))
+    assert r1.pnp_ok == 1 and r2.pnp_ok == 0 and r2.n_keypoints == 0 and np.array_equal(T2, T1)
+    T3, r3 = trk.track(imgs[2])                                      # and it recovers
+    assert r3.pnp_ok == 1
+    trk.close()
+    ctx.set_params(max_keypoints=1500)
