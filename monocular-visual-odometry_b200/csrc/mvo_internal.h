@@ -138,7 +138,10 @@ struct MvoPoseStore {
 
 // track.cu: glue kernels of the device-resident tracking step
 struct MvoTrackGlue {
-  int mode, slot, cap, ba_enable, has_prev;
+  int mode;                      // 1 PnP ran on n pairs known to the host, 0 no PnP, 2 PnP ran on *n_pairs_dev pairs
+  int min_pnp;                   // mode 2: kMinPtsForPnP, tested on the device
+  const int32_t *n_pairs_dev;
+  int slot, cap, ba_enable, has_prev;
   double max_dist, prev_twc[3], fallback[12];
   const double *pose_io;
   const int32_t *out_i, *inl, *pairs;
@@ -153,9 +156,12 @@ struct MvoTrackGlue {
 int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,
                           int rows, int cols, uint8_t *d_vis, float *d_cxy);
 int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_xy);
-int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const float *d_map_pts, const mvo_keypoint *d_kpts,
-                           float *d_p3, float *d_p2);
+int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const int32_t *d_n, const float *d_map_pts,
+                           const mvo_keypoint *d_kpts, float *d_p3, float *d_p2);
 int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g);
+// thresholds of matchFeatures + removeDuplicatedMatches on the device; d_info: [0] pairs, [1] candidates, [2] status
+int mvo_track_match_filter(mvo_ctx *ctx, const uint32_t *d_keys, const uint8_t *d_vis, int nmap, int nk, int method,
+                           int32_t *d_pairs, int32_t *d_info);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 // mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)
@@ -183,7 +189,7 @@ int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const f
                             uint32_t *d_keys, const uint8_t *d_qmask);
 // pnp.cu: device-resident solvePnPRansac replacement (see there)
 int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **pose_io, int32_t **out_i, int32_t **inl);
-int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K);
+int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K, const int32_t *d_n);
 // ba.cu: pose-only LM over the tracker's device-resident frame buffer
 int mvo_ba_pose_store_launch(mvo_ctx *ctx, const MvoPoseStore &st, int e_upper, double fx, double fy, double cx, double cy,
                              const double *info, int iters, int use_huber, double huber, double step_tol, double *d_stats);

@@ -210,10 +210,12 @@ __device__ int p3p(const V3 *X, const V3 *f, Pose *out) {
 }
 
 __global__ void __launch_bounds__(128)
-k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, uint64_t seed,
-                 int H, double *__restrict__ poses, int32_t *__restrict__ valid) {
+k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev,
+                 PnpCam cam, uint64_t seed, int H, double *__restrict__ poses, int32_t *__restrict__ valid) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
+  if (n_dev) n = min(n, *n_dev);          // device-resident tracker: the pair count never visited the host
+  if (n < 4) { valid[h] = 0; return; }
   int idx[4];
   uint64_t ctr = 0;
   for (int k = 0; k < 4; ++k) {
@@ -255,9 +257,10 @@ k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int
 }
 
 __global__ void __launch_bounds__(256)
-k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, double thr2, int H,
-            const double *__restrict__ poses, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
+k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev, PnpCam cam,
+            double thr2, int H, const double *__restrict__ poses, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
   extern __shared__ float s_pts[];      // [n][5]: X Y Z u v
+  if (n_dev) n = min(n, *n_dev);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     s_pts[5 * i] = p3[3 * i]; s_pts[5 * i + 1] = p3[3 * i + 1]; s_pts[5 * i + 2] = p3[3 * i + 2];
     s_pts[5 * i + 3] = p2[2 * i]; s_pts[5 * i + 4] = p2[2 * i + 1];
@@ -287,14 +290,16 @@ constexpr int FIN_T = 1024;
 // inlier indices in inl[] and the one-frame edge list (ex, eo, ef) for the pose-only LM refit.
 // mode 0: arg-max + consensus set; mode 1: every point is an inlier, pose_io holds the start pose.
 __global__ void __launch_bounds__(FIN_T)
-k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, PnpCam cam, double thr2, int H,
-             const double *__restrict__ poses, const int32_t *__restrict__ counts, int mode, int max_iters,
+k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev, PnpCam cam,
+             double thr2, int H, const double *__restrict__ poses, const int32_t *__restrict__ counts, int mode, int max_iters,
              double *__restrict__ pose_io, int32_t *__restrict__ out_i, int32_t *__restrict__ inl,
              double *__restrict__ ex, double *__restrict__ eo, int32_t *__restrict__ ef) {
   __shared__ double s_red[32 * 28];
   __shared__ double s_pose[12];
   __shared__ int s_best, s_cnt[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_upper = n;                 // the refit is launched for this many edge slots
+  if (n_dev) n = min(n, *n_dev);
   int n_in = 0;
   if (mode == 0) {
     // arg-max of the inlier count, ties -> lowest hypothesis index
@@ -317,7 +322,7 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     __syncthreads();
     if (s_best < 0) {
       if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
-      for (int j = tid; j < n; j += FIN_T) ef[j] = -1;
+      for (int j = tid; j < n_upper; j += FIN_T) ef[j] = -1;
       if (tid < 12) pose_io[tid] = (tid == 0 || tid == 4 || tid == 8) ? 1.0 : 0.0;
       return;
     }
@@ -354,7 +359,7 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     eo[2 * j] = p2[2 * i]; eo[2 * j + 1] = p2[2 * i + 1];
     ef[j] = 0;
   }
-  for (int j = n_in + tid; j < n; j += FIN_T) ef[j] = -1;       // masked out of the refit
+  for (int j = n_in + tid; j < n_upper; j += FIN_T) ef[j] = -1;       // masked out of the refit
   const int it = 0;
   if (tid < 12) pose_io[tid] = s_pose[tid];
   if (tid == 0) { out_i[0] = n_in; out_i[1] = mode == 0 ? s_best : -1; out_i[2] = it; }
@@ -434,22 +439,22 @@ static int pnp_refit(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
 
 // hypotheses -> scores -> consensus set of the best hypothesis -> least-squares refit, all on ctx->stream;
 // w.p3 / w.p2 hold the n correspondences on the device
-static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
+static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, const int32_t *n_dev = nullptr) {
   const int H = ctx->prm.pnp_hypotheses;
   const size_t smem = (size_t)n * 5 * sizeof(float);
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
   const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
   { KTimer kt(ctx, KC_PNP_HYP);
-  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
+  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
   MVO_CHECK_LAUNCH(ctx);
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pnp_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (H + 7) / 8;
   if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
   { KTimer kt(ctx, KC_PNP_SCORE);
-  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.valid, w.counts); }
+  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.valid, w.counts); }
   MVO_CHECK_LAUNCH(ctx);
   { KTimer kt(ctx, KC_PNP_FINISH);
-  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
+  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
                                              w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
   MVO_CHECK_LAUNCH(ctx);
   ctx->pnp_last_h = H;
@@ -469,13 +474,14 @@ int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **po
   return MVO_OK;
 }
 
-int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K) {
+// n = number of correspondences, or their upper bound when d_n (device counter) is given
+int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K, const int32_t *d_n) {
   if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "solvePnPRansac: %d correspondences (< 4)", n);
   PnpCam cam;
   MVO_TRY(pnp_cam(ctx, K, &cam));
   PnpWs w;
   MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
-  return pnp_enqueue(ctx, w, n, cam);
+  return pnp_enqueue(ctx, w, n, cam, d_n);
 }
 
 extern "C" {
@@ -554,7 +560,7 @@ int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, 
   MVO_CUDA(ctx, cudaMemcpyAsync(w.p2, h2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(w.pose_io, h_pose, 96, cudaMemcpyHostToDevice, ctx->stream));
   { KTimer kt(ctx, KC_PNP_FINISH);
-  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, cam, 0.0, 0, nullptr, nullptr, 1, ctx->prm.pnp_refine_iters,
+  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, nullptr, cam, 0.0, 0, nullptr, nullptr, 1, ctx->prm.pnp_refine_iters,
                                              w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
   MVO_CHECK_LAUNCH(ctx);
   MVO_TRY(pnp_refit(ctx, w, n, cam));

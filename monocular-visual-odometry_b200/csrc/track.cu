@@ -9,6 +9,7 @@
 //   k_track_glue    vo.cpp:333-379: inlier connections of the new frame (-> its slot of the frame buffer),
 //                   T_w_c = [R|t]^-1 jump test against the previous frame, pose fallback, BA gate
 // All tiny (<= 2001 elements): one or a few CTAs each; they exist to remove host round trips, not for FLOPs.
+#include <algorithm>
 #include "mvo_internal.h"
 
 namespace {
@@ -50,9 +51,10 @@ k_kpt_xy(const mvo_keypoint *__restrict__ kpts, int n, float2 *__restrict__ xy) 
 }
 
 __global__ void __launch_bounds__(256)
-k_gather_pairs(const int2 *__restrict__ pairs, int n, const float *__restrict__ map_pts,
+k_gather_pairs(const int2 *__restrict__ pairs, int n, const int32_t *__restrict__ n_dev, const float *__restrict__ map_pts,
                const mvo_keypoint *__restrict__ kpts, float *__restrict__ p3, float *__restrict__ p2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, *n_dev);
   if (i >= n) return;
   const int2 pr = pairs[i];
   p3[3 * i] = map_pts[3 * pr.x]; p3[3 * i + 1] = map_pts[3 * pr.x + 1]; p3[3 * i + 2] = map_pts[3 * pr.x + 2];
@@ -60,7 +62,10 @@ k_gather_pairs(const int2 *__restrict__ pairs, int n, const float *__restrict__ 
 }
 
 struct GlueArgs {
-  int mode;                 // 1: a PnP ran (pose_io / out_i / inl valid); 0: too few pairs, only the fallback applies
+  int mode;                 // 1: a PnP ran (pose_io / out_i / inl valid); 0: too few pairs, only the fallback applies;
+                            // 2: a PnP was enqueued for *n_pairs_dev pairs — it counts only if that is >= min_pnp
+  int min_pnp;
+  const int32_t *n_pairs_dev;
   int slot, cap, ba_enable, has_prev;
   double max_dist;          // max_possible_dist_to_prev_keyframe
   double prev_twc[3];       // translation of the previous frame's T_w_c
@@ -85,7 +90,9 @@ __global__ void __launch_bounds__(256) k_track_glue(GlueArgs a) {
     int n_in = 0, model = 0, ok = 0;
     double P[12];
     for (int q = 0; q < 12; ++q) P[q] = a.fallback.v[q];
-    if (a.mode == 1) {
+    int mode = a.mode;
+    if (mode == 2) mode = (*a.n_pairs_dev >= a.min_pnp && *a.n_pairs_dev >= 4) ? 1 : 0;     // vo.cpp:304,311
+    if (mode == 1) {
       n_in = a.out_i[0];
       model = n_in >= 4;
       if (model) {
@@ -140,18 +147,18 @@ int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_x
   return MVO_OK;
 }
 
-int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const float *d_map_pts, const mvo_keypoint *d_kpts,
-                           float *d_p3, float *d_p2) {
+int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const int32_t *d_n, const float *d_map_pts,
+                           const mvo_keypoint *d_kpts, float *d_p3, float *d_p2) {
   if (n <= 0) return MVO_OK;
   KTimer kt(ctx, KC_TRACK);
-  k_gather_pairs<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int2 *)d_pairs, n, d_map_pts, d_kpts, d_p3, d_p2);
+  k_gather_pairs<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int2 *)d_pairs, n, d_n, d_map_pts, d_kpts, d_p3, d_p2);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
 
 int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
   GlueArgs a;
-  a.mode = g.mode; a.slot = g.slot; a.cap = g.cap; a.ba_enable = g.ba_enable; a.has_prev = g.has_prev;
+  a.mode = g.mode; a.min_pnp = g.min_pnp; a.n_pairs_dev = g.n_pairs_dev; a.slot = g.slot; a.cap = g.cap; a.ba_enable = g.ba_enable; a.has_prev = g.has_prev;
   a.max_dist = g.max_dist;
   for (int q = 0; q < 3; ++q) a.prev_twc[q] = g.prev_twc[q];
   for (int q = 0; q < 12; ++q) a.fallback.v[q] = g.fallback[q];
@@ -160,6 +167,231 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
   a.skip_flag = g.skip_flag; a.res_i = g.res_i; a.res_d = g.res_d;
   KTimer kt(ctx, KC_TRACK);
   k_track_glue<<<1, 256, 0, ctx->stream>>>(a);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+// =========================================================================================================
+// k_match_filter: the tail of geometry::matchFeatures on the device — the distance thresholds
+// (feature_match.cpp:179-217) and removeDuplicatedMatches (:241-260) — so that the match list never visits the
+// host between the matcher and PnP.
+//
+// removeDuplicatedMatches is `std::sort(matches, by trainIdx)` (unstable) + "keep the first of every run", so which
+// of several map points matched to one keypoint survives is decided by libstdc++'s introsort.  That algorithm is
+// restated here step by step rather than replaced:
+//   std::sort = __introsort_loop (median-of-3 quicksort until every segment has <= 16 elements, depth limit
+//               2*floor(log2 n), heapsort beyond it) + __final_insertion_sort.
+//   * The final insertion sort is stable, so the first element of a run of equal keys is the one that stands
+//     leftmost after the quicksort phase: the survivors need that phase only (one atomicMin per element afterwards).
+//   * __unguarded_partition(first+1, last, pivot=*first) swaps the k-th element >= pivot from the left (Lo[k])
+//     with the k-th element <= pivot from the right (Ro[k]) while Lo[k] < Ro[k]; both scans only ever look at
+//     untouched elements, so Lo / Ro are properties of the segment BEFORE the partition: a warp lists them with
+//     ballots, counts K = #{k : Lo[k] < Ro[k]}, performs the K swaps in parallel and returns the cut
+//     min(Lo[K], Ro[K-1]) (Lo[0] when K = 0) — exactly where the sequential scan stops.
+//   * Recursion order is irrelevant (segments are disjoint): segments are processed level by level, one warp
+//     per segment.
+//   * If a segment is still > 16 at the depth limit (libstdc++ would switch to heapsort: adversarial inputs
+//     only) the kernel reports status 1 and the host finishes the frame through the host path.
+// Parity: tests/test_tracker_gpu.py (same match lists as the host std::sort on every frame, all three methods).
+namespace {
+
+constexpr int MF_T = 1024;
+constexpr int MF_MAXN = 8192;        // match-list / keypoint capacity of the device path (host path beyond)
+
+struct FilterArgs {
+  const uint32_t *keys;     // [nmap * W]
+  const uint8_t *vis;       // [nmap]
+  int nmap, nk, method, n_cap;
+  double xg_ratio, lowe_ratio;
+  int2 *pairs;              // out: (map index, keypoint index), sorted by keypoint index
+  int32_t *info;            // out: [0] pairs, [1] candidates (map points in view), [2] status (0 ok, 1 host path needed)
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  __syncthreads();                       // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < MF_T / 32; ++w) { const int c = s_warp[w]; if (w < warp) off += c; tot += c; }
+  total = tot;
+  return off + incl - v;
+}
+
+__global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int cap = a.n_cap;
+  uint32_t *arr = (uint32_t *)smraw;                    // [cap]  (train << 16) | position in the match list
+  uint32_t *best = arr + cap;                           // [cap]  per keypoint: leftmost (position << 16 | list index)
+  uint16_t *amap = (uint16_t *)(best + cap);            // [cap]  map index of list entry i
+  uint16_t *Ls = amap + cap;                            // [cap]  Lo lists, segment [first,last) uses Ls[first..last)
+  uint16_t *Rs = Ls + cap;                              // [cap]
+  uint32_t *segA = (uint32_t *)(Rs + cap);              // [cap/16 + 2] segments of the current level (first | last << 16)
+  uint32_t *segB = segA + cap / 16 + 2;
+  __shared__ int s_warp[MF_T / 32];
+  __shared__ unsigned s_min;
+  __shared__ int s_nseg[2], s_status;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmap = a.nmap;
+  const bool sad = a.method == 3;
+  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; }
+  __syncthreads();
+  // ---- thresholds (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2), ordered compaction ----
+  const int per = (nmap + MF_T - 1) / MF_T, q0 = min(tid * per, nmap), q1 = min(q0 + per, nmap);
+  int nvis = 0;
+  if (a.method != 2) {
+    unsigned m = 0xFFFFFFFFu;
+    for (int q = q0; q < q1; ++q) {
+      if (!a.vis[q]) continue;
+      ++nvis;
+      const uint32_t k = a.keys[q];
+      if (k != 0xFFFFFFFFu) m = min(m, k >> 16);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&s_min, m);
+  } else {
+    for (int q = q0; q < q1; ++q) nvis += a.vis[q] != 0;
+  }
+  __syncthreads();
+  double thr = 0;
+  if (a.method != 2) {
+    // min_dis = 9999999 when nothing matched; distance is a float (Hamming count, or SAD/32 through double)
+    const double min_dis = s_min == 0xFFFFFFFFu ? 9999999.0 : (sad ? (double)(float)((double)s_min / 32.0) : (double)(float)s_min);
+    thr = (double)fmaxf((float)(min_dis * a.xg_ratio), 30.0f);        // std::max<float>(min_dis * ratio, 30.0)
+  }
+  auto passes = [&](int q, uint32_t &train) -> bool {
+    if (!a.vis[q]) return false;
+    if (a.method != 2) {
+      const uint32_t k = a.keys[q];
+      if (k == 0xFFFFFFFFu) return false;
+      const uint32_t d = k >> 16;
+      const float dist = sad ? (float)((double)d / 32.0) : (float)d;
+      train = k & 0xFFFFu;
+      return (double)dist < thr;
+    }
+    const uint32_t k0 = a.keys[2 * q], k1 = a.keys[2 * q + 1];
+    if (k0 == 0xFFFFFFFFu) return false;
+    train = k0 & 0xFFFFu;
+    return (double)(float)(k0 >> 16) < a.lowe_ratio * (double)(float)(k1 >> 16);
+  };
+  int cnt = 0;
+  for (int q = q0; q < q1; ++q) { uint32_t tr; cnt += passes(q, tr); }
+  int n = 0, ncand = 0;
+  int pos = block_excl_scan(cnt, s_warp, n);
+  (void)block_excl_scan(nvis, s_warp, ncand);
+  if (n > cap || a.nk > cap) {                          // beyond the device path's capacity
+    if (tid == 0) { a.info[0] = 0; a.info[1] = ncand; a.info[2] = 1; }
+    return;
+  }
+  for (int q = q0; q < q1; ++q) {
+    uint32_t tr;
+    if (passes(q, tr)) { arr[pos] = (tr << 16) | (uint32_t)pos; amap[pos] = (uint16_t)q; ++pos; }
+  }
+  for (int i = tid; i < a.nk; i += MF_T) best[i] = 0xFFFFFFFFu;
+  if (tid == 0 && n > 16) { segA[0] = 0u | ((uint32_t)n << 16); s_nseg[0] = 1; }
+  __syncthreads();
+  // ---- quicksort phase of std::sort, level by level ----
+  int depth_limit = 0;
+  for (int m = n; m > 1; m >>= 1) ++depth_limit;        // std::__lg(n)
+  depth_limit *= 2;
+  uint32_t *cur = segA, *nxt = segB;
+  int level = 0, which = 0;
+  while (true) {
+    const int nseg = s_nseg[which];
+    if (nseg == 0) break;
+    if (level >= depth_limit) { if (tid == 0) s_status = 1; break; }      // libstdc++ would heapsort from here
+    for (int s = warp; s < nseg; s += MF_T / 32) {
+      const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
+      // __move_median_to_first(first, first+1, mid, last-1)
+      if (lane == 0) {
+        const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+        const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
+        int pick;
+        if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+        else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+        const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
+      }
+      __syncwarp();
+      const uint32_t pivot = arr[first] >> 16;
+      const int lo = first + 1, len = last - lo;
+      int nL = 0, nR = 0;
+      for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        const bool inr = i < len;
+        const bool ge = inr && (arr[lo + i] >> 16) >= pivot;              // !(x < pivot): the left scan stops here
+        const bool le = inr && (arr[last - 1 - i] >> 16) <= pivot;        // !(pivot < x): the right scan stops here
+        const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
+        const unsigned below = (1u << lane) - 1u;
+        if (ge) Ls[lo + nL + __popc(bg & below)] = (uint16_t)(lo + i);
+        if (le) Rs[lo + nR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
+        nL += __popc(bg);
+        nR += __popc(bl);
+      }
+      __syncwarp();
+      const int nmin = min(nL, nR);
+      int K = 0;
+      for (int base = 0; base < nmin; base += 32) {
+        const int j = base + lane;
+        const bool sw = j < nmin && Ls[lo + j] < Rs[lo + j];
+        const unsigned b = __ballot_sync(0xffffffffu, sw);
+        if (sw) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
+        const int c = __popc(b);
+        K += c;
+        if (c < 32) break;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        int cut;
+        if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;                    // Lo[0] exists after the median step
+        else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
+        // __introsort_loop: recurse on [cut, last), continue with [first, cut)
+        if (last - cut > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)cut | ((uint32_t)last << 16);
+        if (cut - first > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)first | ((uint32_t)cut << 16);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_nseg[which] = 0;
+    which ^= 1;
+    uint32_t *t = cur; cur = nxt; nxt = t;
+    ++level;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_status != 0) {
+    if (tid == 0) { a.info[0] = 0; a.info[1] = ncand; a.info[2] = 1; }
+    return;
+  }
+  // ---- final insertion sort is stable: of every run of equal keypoint indices the leftmost element survives ----
+  for (int p = tid; p < n; p += MF_T) atomicMin(&best[arr[p] >> 16], ((uint32_t)p << 16) | (arr[p] & 0xFFFFu));
+  __syncthreads();
+  const int pk = (a.nk + MF_T - 1) / MF_T, t0 = min(tid * pk, a.nk), t1 = min(t0 + pk, a.nk);
+  int c2 = 0;
+  for (int t = t0; t < t1; ++t) c2 += best[t] != 0xFFFFFFFFu;
+  int np = 0;
+  int o = block_excl_scan(c2, s_warp, np);
+  for (int t = t0; t < t1; ++t)
+    if (best[t] != 0xFFFFFFFFu) a.pairs[o++] = make_int2((int)amap[best[t] & 0xFFFFu], t);
+  if (tid == 0) { a.info[0] = np; a.info[1] = ncand; a.info[2] = 0; }
+}
+
+}  // namespace
+
+int mvo_track_match_filter(mvo_ctx *ctx, const uint32_t *d_keys, const uint8_t *d_vis, int nmap, int nk, int method,
+                           int32_t *d_pairs, int32_t *d_info) {
+  int cap = 2048;
+  while (cap < std::max(std::min(nmap, 65535), nk) && cap < MF_MAXN) cap *= 2;
+  FilterArgs a;
+  a.keys = d_keys; a.vis = d_vis; a.nmap = nmap; a.nk = nk; a.method = method; a.n_cap = cap;
+  a.xg_ratio = ctx->prm.xiang_gao_ratio; a.lowe_ratio = ctx->prm.lowe_ratio;
+  a.pairs = (int2 *)d_pairs; a.info = d_info;
+  const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 2 * ((size_t)cap / 16 + 2) * 4 + 64;
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KTimer kt(ctx, KC_TRACK);
+  k_match_filter<<<1, MF_T, smem, ctx->stream>>>(a);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

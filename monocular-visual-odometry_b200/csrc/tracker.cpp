@@ -113,6 +113,7 @@ struct mvo_tracker {
   bool has_prev = false;
   double T_prev[16];
   unsigned frame_counter = 0;
+  int fused_holdoff = 0;             // frames left before the device-side match filter is tried again
   // scratch (host-array path)
   std::vector<uint8_t> cand_desc;
   std::vector<float> cand_xy, kp_xy, p3, p2;
@@ -245,7 +246,7 @@ int dev_alloc(mvo_tracker *t) {
   t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs); t->d_cnt = (int32_t *)(nd + o_cnt);
   t->d_pose = (double *)(nd + o_pose); t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res);
   t->d_stats = (double *)(nd + o_stats);
-  const size_t hb = al256((size_t)nm1 * 9) + al256((size_t)nm1 * 8) + al256((size_t)ring * 96) + 1024;
+  const size_t hb = al256((size_t)nm1 * 9) + al256((size_t)nm1 * 8 + 64) + al256((size_t)ring * 96) + 1024;
   if (hb > t->h_pin_bytes) {
     if (t->h_pin) cudaFreeHost(t->h_pin);
     t->h_pin = nullptr;
@@ -272,6 +273,43 @@ void dedup_pairs(std::vector<MatchPair> &v) {
   v.resize(w);
 }
 
+// Thresholds of matchFeatures (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2) and
+// removeDuplicatedMatches (:241-260) over the packed matcher keys of ALL map points (vis = in-view flags).
+void host_match_filter(const mvo_params &prm, int method, bool can_match, const uint32_t *h_keys, const uint8_t *h_vis, int nmap,
+                       std::vector<MatchPair> &pairs, int *ncand_out) {
+  pairs.clear();
+  int ncand = 0;
+  for (int q = 0; q < nmap; ++q) ncand += h_vis[q] != 0;
+  *ncand_out = ncand;
+  if (!can_match || ncand == 0) return;
+  if (method == 1 || method == 3) {
+    const bool sad = method == 3;
+    double min_dis = 9999999, max_dis = 0;
+    for (int q = 0; q < nmap; ++q) {
+      if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
+      const uint32_t d = h_keys[q] >> 16;
+      const double dist = sad ? (double)(float)((double)d / 32.0) : (double)(float)d;
+      if (dist < min_dis) min_dis = dist;
+      if (dist > max_dis) max_dis = dist;
+    }
+    const double thr = std::max<float>(min_dis * prm.xiang_gao_ratio, 30.0);
+    for (int q = 0; q < nmap; ++q) {
+      if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
+      const uint32_t d = h_keys[q] >> 16;
+      const float dist = sad ? (float)((double)d / 32.0) : (float)d;
+      if (dist < thr) pairs.push_back(MatchPair{(int32_t)(h_keys[q] & 0xFFFFu), q});
+    }
+  } else {
+    for (int q = 0; q < nmap; ++q) {
+      if (!h_vis[q] || h_keys[2 * q] == 0xFFFFFFFFu) continue;
+      const uint32_t k0 = h_keys[2 * q], k1 = h_keys[2 * q + 1];
+      const double dist = (float)(k0 >> 16);
+      if (dist < prm.lowe_ratio * (float)(k1 >> 16)) pairs.push_back(MatchPair{(int32_t)(k0 & 0xFFFFu), q});
+    }
+  }
+  dedup_pairs(pairs);
+}
+
 }  // namespace
 
 // exported for the CPU-side test of the proxy sort (not part of mvo.h: test hook)
@@ -283,6 +321,40 @@ extern "C" int mvo_test_dedup_pairs(int32_t *train, int32_t *map, int *n) {
   for (size_t i = 0; i < v.size(); ++i) { train[i] = v[i].train; map[i] = v[i].map; }
   *n = (int)v.size();
   return MVO_OK;
+}
+
+
+// Test hooks (not part of mvo.h): the match-list tail on the host and on the device, from the same packed keys.
+// pairs: n x 2 int32 (map index, keypoint index); info: [0] pairs, [1] candidates, [2] status.
+extern "C" int mvo_test_match_filter_host(mvo_ctx *ctx, const uint32_t *keys, const uint8_t *vis, int nmap, int nk, int method,
+                                          int32_t *pairs, int32_t *info) {
+  if (!ctx || !keys || !vis || !pairs || !info) return MVO_ERR_INVALID_ARG;
+  std::vector<MatchPair> v;
+  int ncand = 0;
+  host_match_filter(ctx->prm, method, nk > 0, keys, vis, nmap, v, &ncand);
+  for (size_t i = 0; i < v.size(); ++i) { pairs[2 * i] = v[i].map; pairs[2 * i + 1] = v[i].train; }
+  info[0] = (int32_t)v.size(); info[1] = ncand; info[2] = 0;
+  return MVO_OK;
+}
+
+extern "C" int mvo_test_match_filter_dev(mvo_ctx *ctx, const uint32_t *keys, const uint8_t *vis, int nmap, int nk, int method,
+                                         int32_t *pairs, int32_t *info) {
+  if (!ctx || !keys || !vis || !pairs || !info || nmap < 1) return MVO_ERR_INVALID_ARG;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int W = method == 2 ? 2 : 1;
+  uint8_t *d = nullptr;
+  const size_t o_vis = (size_t)nmap * 8, o_pairs = al256(o_vis + nmap), o_info = o_pairs + (size_t)nmap * 8, tot = o_info + 64;
+  MVO_CUDA(ctx, cudaMalloc(&d, tot));
+  cudaMemcpyAsync(d, keys, (size_t)nmap * W * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d + o_vis, vis, nmap, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = mvo_track_match_filter(ctx, (const uint32_t *)d, d + o_vis, nmap, nk, method, (int32_t *)(d + o_pairs), (int32_t *)(d + o_info));
+  if (rc == MVO_OK) {
+    cudaMemcpyAsync(info, d + o_info, 12, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = mvo_fail(ctx, MVO_ERR_CUDA, "match filter kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    else if (info[2] == 0 && info[0] > 0) cudaMemcpy(pairs, d + o_pairs, (size_t)info[0] * 8, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  return rc;
 }
 
 static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device) {
@@ -406,6 +478,7 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref) {
   t->frames.clear();
   t->has_prev = false;
   t->frame_counter = 0;
+  t->fused_holdoff = 0;
   drain_jobs(t);                    // drop frames that were prefetched but never tracked
   t->n_submit = t->n_consume = 0;
   {
@@ -473,11 +546,16 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
 // ------------------------------------------------------------------------------------------------------------
 // device-resident path
 // ------------------------------------------------------------------------------------------------------------
+// Layout of the 768-byte result block (d_flags, d_res, d_stats are contiguous):
+//   int32 [0] BA skip flag   [4..6] match filter: pairs, candidates, status   [8..10] model found, pnp_ok, inliers
+//         [16..] BA graph: frames, edges, slot of frame f
+//   +256: world->camera pose of the frame before BA (12 doubles)      +512: BA statistics (16 doubles)
 static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res) {
   mvo_ctx *ctx = t->ctx;
   mvo_track_result r;
   memset(&r, 0, sizeof r);
   static const bool dbg = getenv("MVO_TRACK_DEBUG") != nullptr;
+  static const bool force_host_filter = getenv("MVO_TRACK_HOST_FILTER") != nullptr;     // test hook: the two-sync variant
   static double acc[8] = {0};
   static int nacc = 0;
   double t0 = dbg ? now_us() : 0;
@@ -494,128 +572,131 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   cur.slot = (int)(t->frame_counter++ % (unsigned)t->dev_ring);
   // curr_->T_w_c_ = ref_->T_w_c_.clone()  (vo_addFrame.cpp:74): initial guess = reference keyframe
   memcpy(cur.T_w_c, t->T_ref, sizeof cur.T_w_c);
+  const int total = (int)t->frames.size();
 
-  // ---- getMappointsInCurrentView_ + matchFeatures(map descriptors, frame descriptors) (vo.cpp:16-49, 283-289) ----
   uint32_t *d_keys = (uint32_t *)t->d_keysvis;
   uint8_t *d_vis = t->d_keysvis + (size_t)std::max(nmap, 1) * 8;
+  int32_t *d_finfo = t->d_flags + 4, *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
+  uint8_t *h_out = t->h_pin + al256((size_t)std::max(nmap, 1) * 9) + al256((size_t)std::max(nmap, 1) * 8 + 64);
+  const int32_t *h_flags = (const int32_t *)h_out;
   const bool can_match = nmap > 0 && nk > 0 && !(method == 2 && nk < 2);
-  const uint32_t *h_keys = (const uint32_t *)t->h_pin;
-  const uint8_t *h_vis = t->h_pin + (size_t)std::max(nmap, 1) * 8;
+
+  // ---- getMappointsInCurrentView_ + matchFeatures(map descriptors, frame descriptors) (vo.cpp:16-49, 283-289) ----
+  auto fail = [&](int rc) { cudaStreamSynchronize(ctx->stream); t->frames.pop_back(); return rc; };
+  int rc = MVO_OK;
   if (nmap > 0) {
     double Tcw[12];
     Twc_to_Rt12(cur.T_w_c, Tcw);
-    int rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
+    rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
     if (rc == MVO_OK && can_match) {
       if (method == 3) rc = mvo_track_kpt_xy(ctx, job.d_k, nk, t->d_kxy);
       if (rc == MVO_OK)
         rc = mvo_match_launch_masked(ctx, method == 1 ? 0 : (method == 2 ? 1 : 2), t->d_map_desc, t->d_cxy, nmap, job.d_d, t->d_kxy, nk,
                                      t->prm.match_radius, d_keys, d_vis);
+    } else if (rc == MVO_OK) {
+      if (cudaMemsetAsync(d_keys, 0xFF, (size_t)nmap * 8, ctx->stream) != cudaSuccess) rc = mvo_fail(ctx, MVO_ERR_CUDA, "tracker: memset");
     }
-    if (rc != MVO_OK) { t->frames.pop_back(); return rc; }
-    // one D2H: [keys | visibility flags]
-    const size_t off = can_match ? 0 : (size_t)nmap * 8, len = (size_t)nmap * 9 - off;
-    MVO_CUDA(ctx, cudaMemcpyAsync(t->h_pin + off, t->d_keysvis + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc != MVO_OK) return fail(rc);
+  }
+
+  // ---- everything after the matcher: thresholds + duplicate removal, PnP, frame-buffer update, BA ----
+  // d_n != nullptr: the pair count lives on the device (n = its upper bound); otherwise n pairs are in d_pairs
+  MvoPoseStore st;
+  auto enqueue_tail = [&](int n, const int32_t *d_n) -> int {
+    MvoTrackGlue g;
+    memset(&g, 0, sizeof g);
+    const bool run_pnp = n >= 4 && (d_n != nullptr || n >= t->prm.min_pnp_points);
+    g.mode = run_pnp ? (d_n ? 2 : 1) : 0;
+    g.min_pnp = t->prm.min_pnp_points; g.n_pairs_dev = d_n;
+    g.slot = cur.slot; g.cap = cap; g.ba_enable = t->prm.ba_enable; g.has_prev = t->has_prev;
+    g.max_dist = t->prm.max_dist_to_prev;
+    if (t->has_prev) { g.prev_twc[0] = t->T_prev[3]; g.prev_twc[1] = t->T_prev[7]; g.prev_twc[2] = t->T_prev[11]; }
+    Twc_to_Rt12(t->has_prev ? t->T_prev : cur.T_w_c, g.fallback);      // vo.cpp:376-379
+    g.pairs = t->d_pairs; g.kpts = job.d_k;
+    g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.cnt = t->d_cnt; g.pose = t->d_pose;
+    g.skip_flag = t->d_flags; g.res_i = d_res_i; g.res_d = t->d_res;
+    int rc2 = MVO_OK;
+    if (run_pnp) {
+      float *d_p3, *d_p2;
+      double *d_pose_io;
+      int32_t *d_out_i, *d_inl;
+      rc2 = mvo_pnp_dev_buffers(ctx, n, &d_p3, &d_p2, &d_pose_io, &d_out_i, &d_inl);
+      if (rc2 == MVO_OK) rc2 = mvo_track_gather_pairs(ctx, t->d_pairs, n, d_n, t->d_map_pts, job.d_k, d_p3, d_p2);
+      if (rc2 == MVO_OK) rc2 = mvo_pnp_dev_run(ctx, n, t->K, d_n);
+      g.pose_io = d_pose_io; g.out_i = d_out_i; g.inl = d_inl;
+    }
+    if (rc2 == MVO_OK) rc2 = mvo_track_glue(ctx, g);
+    // the BA window: newest min(ba_window, total-1) frames (vo.cpp:417-419); frames with < 3 links drop out on the
+    // device (:423-426), where the newest frame's link count is known
+    memset(&st, 0, sizeof st);
+    if (rc2 == MVO_OK && run_pnp && t->prm.ba_enable) {
+      int e_upper = 0;
+      const int nba = std::min(t->prm.ba_window, total - 1);
+      for (int b = total - 1; b >= total - nba; --b) {
+        st.slot[st.nslots++] = t->frames[b].slot;
+        e_upper += (b == total - 1) ? n : t->frames[b].n_links;
+      }
+      if (st.nslots > 0) {
+        st.map_pts = t->d_map_pts; st.edge_map = t->d_edge_map; st.edge_obs = (const float2 *)t->d_edge_obs; st.cnt = t->d_cnt;
+        st.pose = t->d_pose; st.cap = cap; st.min_links = 3; st.skip_flag = t->d_flags; st.out_info = d_out_info;
+        rc2 = mvo_ba_pose_store_launch(ctx, st, e_upper, t->K[0], t->K[0], t->K[2], t->K[5], t->prm.information, ctx->prm.ba_iterations,
+                                       ctx->prm.ba_huber_delta > 0, ctx->prm.ba_huber_delta, t->prm.ba_step_tol, t->d_stats);
+      }
+    }
+    if (rc2 != MVO_OK) return rc2;
+    // one D2H: the result block + the pose ring
+    MVO_CUDA(ctx, cudaMemcpyAsync(h_out, t->d_flags, 768, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h_out + 768, t->d_pose, (size_t)t->dev_ring * 96, cudaMemcpyDeviceToHost, ctx->stream));
     MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  TMARK(0);
+    return MVO_OK;
+  };
 
-  // thresholds of matchFeatures (feature_match.cpp:179-217) and removeDuplicatedMatches (:241-260), on the host
-  std::vector<MatchPair> &pairs = t->pairs;
-  pairs.clear();
-  int ncand = 0;
-  for (int q = 0; q < nmap; ++q) ncand += h_vis[q];
-  r.n_candidates = ncand;
-  if (can_match && ncand > 0) {
-    if (method == 1 || method == 3) {
-      const bool sad = method == 3;
-      double min_dis = 9999999, max_dis = 0;
-      for (int q = 0; q < nmap; ++q) {
-        if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
-        const uint32_t d = h_keys[q] >> 16;
-        const double dist = sad ? (double)(float)((double)d / 32.0) : (double)(float)d;
-        if (dist < min_dis) min_dis = dist;
-        if (dist > max_dis) max_dis = dist;
-      }
-      const double thr = std::max<float>(min_dis * ctx->prm.xiang_gao_ratio, 30.0);
-      for (int q = 0; q < nmap; ++q) {
-        if (!h_vis[q] || h_keys[q] == 0xFFFFFFFFu) continue;
-        const uint32_t d = h_keys[q] >> 16;
-        const float dist = sad ? (float)((double)d / 32.0) : (float)d;
-        if (dist < thr) pairs.push_back(MatchPair{(int32_t)(h_keys[q] & 0xFFFFu), q});
-      }
-    } else {
-      for (int q = 0; q < nmap; ++q) {
-        if (!h_vis[q]) continue;
-        const uint32_t k0 = h_keys[2 * q], k1 = h_keys[2 * q + 1];
-        const double dist = (float)(k0 >> 16);
-        if (dist < ctx->prm.lowe_ratio * (float)(k1 >> 16)) pairs.push_back(MatchPair{(int32_t)(k0 & 0xFFFFu), q});
-      }
+  // thresholds of matchFeatures (feature_match.cpp:179-217) and removeDuplicatedMatches (:241-260) on the host,
+  // from the keys the matcher left on the device: the variant with a second synchronisation, used when the
+  // device-side duplicate removal declines (list beyond its capacity, or libstdc++ would have left quicksort)
+  auto host_filter_tail = [&]() -> int {
+    const uint32_t *h_keys = (const uint32_t *)t->h_pin;
+    const uint8_t *h_vis = t->h_pin + (size_t)std::max(nmap, 1) * 8;
+    if (nmap > 0) {
+      MVO_CUDA(ctx, cudaMemcpyAsync(t->h_pin, t->d_keysvis, (size_t)nmap * 9, cudaMemcpyDeviceToHost, ctx->stream));
+      MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    dedup_pairs(pairs);
-  }
-  const int nm = (int)pairs.size();
-  r.n_matches = nm;
-  TMARK(1);
-
-  // ---- poseEstimationPnP_ (vo.cpp:293-381) + callBundleAdjustment_ (:384-478), enqueued back to back ----
-  int32_t *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
-  MvoTrackGlue g;
-  memset(&g, 0, sizeof g);
-  g.mode = nm >= t->prm.min_pnp_points && nm >= 4;
-  g.slot = cur.slot; g.cap = cap; g.ba_enable = t->prm.ba_enable; g.has_prev = t->has_prev;
-  g.max_dist = t->prm.max_dist_to_prev;
-  if (t->has_prev) { g.prev_twc[0] = t->T_prev[3]; g.prev_twc[1] = t->T_prev[7]; g.prev_twc[2] = t->T_prev[11]; }
-  const double *T_fallback = t->has_prev ? t->T_prev : cur.T_w_c;     // vo.cpp:376-379
-  Twc_to_Rt12(T_fallback, g.fallback);
-  g.pairs = t->d_pairs; g.kpts = job.d_k;
-  g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.cnt = t->d_cnt; g.pose = t->d_pose;
-  g.skip_flag = t->d_flags; g.res_i = d_res_i; g.res_d = t->d_res;
-  int rc = MVO_OK;
-  if (g.mode) {
+    std::vector<MatchPair> &pairs = t->pairs;
+    int ncand = 0;
+    host_match_filter(ctx->prm, method, can_match, h_keys, h_vis, nmap, pairs, &ncand);
+    const int nm = (int)pairs.size();
     int32_t *h_pairs = (int32_t *)(t->h_pin + al256((size_t)std::max(nmap, 1) * 9));
     for (int i = 0; i < nm; ++i) { h_pairs[2 * i] = pairs[i].map; h_pairs[2 * i + 1] = pairs[i].train; }
+    int32_t *h_fi = h_pairs + 2 * (size_t)nm;          // filter record, same layout as the kernel writes
+    h_fi[0] = nm; h_fi[1] = ncand; h_fi[2] = 0;
     MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pairs, h_pairs, (size_t)nm * 8, cudaMemcpyHostToDevice, ctx->stream));
-    float *d_p3, *d_p2;
-    double *d_pose_io;
-    int32_t *d_out_i, *d_inl;
-    rc = mvo_pnp_dev_buffers(ctx, nm, &d_p3, &d_p2, &d_pose_io, &d_out_i, &d_inl);
-    if (rc == MVO_OK) rc = mvo_track_gather_pairs(ctx, t->d_pairs, nm, t->d_map_pts, job.d_k, d_p3, d_p2);
-    if (rc == MVO_OK) rc = mvo_pnp_dev_run(ctx, nm, t->K);
-    g.pose_io = d_pose_io; g.out_i = d_out_i; g.inl = d_inl;
+    MVO_CUDA(ctx, cudaMemcpyAsync(d_finfo, h_fi, 12, cudaMemcpyHostToDevice, ctx->stream));
+    return enqueue_tail(nm, nullptr);
+  };
+
+  // The device filter restates the quicksort phase of libstdc++'s std::sort and declines when that phase would hit
+  // its depth limit (libstdc++ then heapsorts: inherently sequential).  Match lists in a presorted-by-level map order
+  // do that on every frame, so after a decline the next frames go straight to the host filter.
+  bool fused = nmap > 0 && !force_host_filter && t->fused_holdoff == 0;
+  if (t->fused_holdoff > 0) --t->fused_holdoff;
+  if (fused) {
+    rc = mvo_track_match_filter(ctx, d_keys, d_vis, nmap, nk, method, t->d_pairs, d_finfo);
+    if (rc == MVO_OK) rc = enqueue_tail(std::min(nmap, std::max(nk, 0)), d_finfo);
+    if (rc != MVO_OK) return fail(rc);
+    TMARK(0);
+    if (h_flags[6] != 0) { fused = false; t->fused_holdoff = 64; }      // the device filter declined: redo the tail through the host
   }
-  if (rc == MVO_OK) rc = mvo_track_glue(ctx, g);
-  // the BA window: newest min(ba_window, total-1) frames (vo.cpp:417-419); frames with < 3 links drop out on the
-  // device (:423-426), where the newest frame's link count is known
-  MvoPoseStore st;
-  memset(&st, 0, sizeof st);
-  int e_upper = 0;
-  const int total = (int)t->frames.size();
-  const bool try_ba = rc == MVO_OK && g.mode && t->prm.ba_enable;
-  if (try_ba) {
-    const int nba = std::min(t->prm.ba_window, total - 1);
-    for (int b = total - 1; b >= total - nba; --b) {
-      const TrackedFrame &f = t->frames[b];
-      st.slot[st.nslots++] = f.slot;
-      e_upper += (b == total - 1) ? nm : f.n_links;
-    }
-    if (st.nslots > 0) {
-      st.map_pts = t->d_map_pts; st.edge_map = t->d_edge_map; st.edge_obs = (const float2 *)t->d_edge_obs; st.cnt = t->d_cnt;
-      st.pose = t->d_pose; st.cap = cap; st.min_links = 3; st.skip_flag = t->d_flags; st.out_info = d_out_info;
-      rc = mvo_ba_pose_store_launch(ctx, st, e_upper, t->K[0], t->K[0], t->K[2], t->K[5], t->prm.information, ctx->prm.ba_iterations,
-                                    ctx->prm.ba_huber_delta > 0, ctx->prm.ba_huber_delta, t->prm.ba_step_tol, t->d_stats);
-    }
+  if (!fused) {
+    rc = host_filter_tail();
+    if (rc != MVO_OK) return fail(rc);
+    TMARK(1);
   }
-  if (rc != MVO_OK) { cudaStreamSynchronize(ctx->stream); t->frames.pop_back(); return rc; }
-  // one D2H: [flags / counters / graph info (256 B)][pose before BA (256 B)][BA stats (256 B)] + the pose ring
-  uint8_t *h_out = t->h_pin + al256((size_t)std::max(nmap, 1) * 9) + al256((size_t)std::max(nmap, 1) * 8);
-  MVO_CUDA(ctx, cudaMemcpyAsync(h_out, t->d_flags, 768, cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaMemcpyAsync(h_out + 768, t->d_pose, (size_t)t->dev_ring * 96, cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  TMARK(2);
-  const int32_t *h_flags = (const int32_t *)h_out;
+
   const int32_t *h_res_i = h_flags + 8, *h_info = h_flags + 16;
   const double *h_res_d = (const double *)(h_out + 256), *h_stats = (const double *)(h_out + 512);
   const double *h_ring = (const double *)(h_out + 768);
+  r.n_matches = h_flags[4];
+  r.n_candidates = h_flags[5];
   const bool pnp_ok = h_res_i[1] != 0;
   r.n_inliers = h_res_i[2];
   r.pnp_ok = pnp_ok;
@@ -623,7 +704,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   if (pnp_ok) Rt12_to_Twc(h_res_d, cur.T_w_c);
   else if (t->has_prev) memcpy(cur.T_w_c, t->T_prev, sizeof cur.T_w_c);
   memcpy(r.T_w_c_pnp, cur.T_w_c, sizeof r.T_w_c_pnp);
-  if (try_ba && st.nslots > 0 && pnp_ok) {
+  if (st.nslots > 0 && pnp_ok) {
     const int F = h_info[0];
     if (F < 0) { t->frames.pop_back(); return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "tracker: BA graph exceeds the device-resident kernel"); }
     for (int f = 0; f < F; ++f) {
@@ -638,10 +719,9 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
       fprintf(stderr, "k_ba_pose(store): F=%d E=%d it=%.0f trials=%.0f cycles solve=%.0f pass=%.0f gather=%.0f decide=%.0f\n", F, h_info[1],
               h_stats[2], h_stats[15], h_stats[8], h_stats[9], h_stats[10], h_stats[11]);
   }
-  TMARK(3);
+  TMARK(2);
   if (dbg && ++nacc % 50 == 0) {
-    fprintf(stderr, "tracker(device) us/frame: project+match+sync %.1f filter+dedup %.1f pnp+ba+sync %.1f finish %.1f\n", acc[0] / 50, acc[1] / 50,
-            acc[2] / 50, acc[3] / 50);
+    fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f\n", acc[0] / 50, acc[1] / 50, acc[2] / 50);
     for (double &a : acc) a = 0;
   }
 #undef TMARK

@@ -138,13 +138,18 @@ def test_lost_frame_keeps_previous_pose(ctx):
 def test_device_resident_path_equals_host_array_path(ctx):
     """The two implementations of the tracking step (map / frame buffer / BA graph resident in HBM vs every stage
     through its host-array C-ABI entry point) must take the same integer decisions and produce the same poses
-    (PnP pose 1e-12: the only arithmetic difference is the Rodrigues round trip on the host-array path; poses after BA
+    (PnP pose 1e-9: the only arithmetic difference is the Rodrigues round trip on the host-array path; poses after BA
     1e-8, the BA parity tolerance: which of g2o's final sub-1e-9 trial steps gets accepted depends on rounding)."""
     import mvo_b200
     ctx.set_params(max_keypoints=2000, ba_iterations=10)
-    for method in (1, 2, 3):
+    for method, shuffle in ((1, False), (1, True), (2, True), (3, False), (3, True)):
         imgs, _ = _make_sequence(4, 9)
         pts, desc = _map_from_frame0(ctx, imgs[0])
+        if shuffle:
+            # level-major map order (as ORB emits keypoints) drives libstdc++'s std::sort in removeDuplicatedMatches to its
+            # heapsort fallback, which the device-side filter declines (-> host filter); a shuffled map stays on the device
+            perm = np.random.default_rng(7).permutation(len(pts))
+            pts, desc = pts[perm], np.ascontiguousarray(desc[perm])
         runs = []
         for dev in (1, 0):
             trk = mvo_b200.Tracker(ctx, K, 480, 640, device_resident=dev, match_method=method)
@@ -162,7 +167,7 @@ def test_device_resident_path_equals_host_array_path(ctx):
         for (Ta, ia, Pa), (Tb, ib, Pb) in zip(a, b):
             assert ia == ib, (method, ia, ib)
             assert ia[4] == 1 and ia[3] > 100
-            assert np.abs(Pa - Pb).max() < 1e-12 and np.abs(Ta - Tb).max() < 1e-8, (method, np.abs(Ta - Tb).max())
+            assert np.abs(Pa - Pb).max() < 1e-9 and np.abs(Ta - Tb).max() < 1e-8, (method, np.abs(Ta - Tb).max())
         assert np.abs(ha - hb).max() < 1e-8
     ctx.set_params(max_keypoints=1500, ba_iterations=50)
 

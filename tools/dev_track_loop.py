@@ -9,7 +9,8 @@ ctx = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
 imgs, T_true, order = bench.build_sequence(0)
 kp0, d0 = ctx.orb_extract(imgs[0])
 trk = mvo_b200.Tracker(ctx, mvo_synth.K_DEFAULT, 480, 640)
-trk.set_map(bench.map_from_first_frame(kp0), d0); trk.reset(np.eye(4))
+perm = bench.map_order(len(kp0))
+trk.set_map(bench.map_from_first_frame(kp0)[perm], np.ascontiguousarray(d0[perm])); trk.reset(np.eye(4))
 d = [torch.from_numpy(im).cuda() for im in imgs]
 torch.cuda.synchronize()
 for i in range(n):
