@@ -296,6 +296,40 @@ def run_gpu(args, rank, world, local_rank):
     run_steps(host_args, warm, 0)
     ms_e2e, _ = timed(host_args, args.steps, warm)
 
+    # ---- batched, device-resident ORB extraction (BASELINE config 2; SURVEY.md §8d: the only form of the path whose
+    # algorithmic bytes are comparable with the HBM roofline) ----
+    orb_batch = None
+    if rank == 0:
+        B = 64
+        cap = MAX_KPTS + 1
+        d_k = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
+        d_d = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
+        d_c = torch.empty(B, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+
+        def orb_batch_call(first_slot):
+            ctx.orb_extract_batch_dev(d_frames[first_slot].data_ptr(), B, H, W, 3, W * 3, frame_bytes, d_k.data_ptr(), d_d.data_ptr(),
+                                      d_c.data_ptr(), cap)
+        for w in range(3):
+            orb_batch_call(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = 10
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for it in range(nrep):
+            orb_batch_call((it % 2) * B)          # 2 x 64 different slots: 118 MB of input between revisits
+        e1.record(stream)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / nrep
+        nk = int(d_c.sum().item())
+        algo = B * (frame_bytes + 28 * (nk / B) + 32 * (nk / B))     # BGR in + KeyPoint + descriptor out
+        peak_b, _ = _peaks()
+        orb_batch = {"batch": B, "us_per_batch": us, "frames_per_s": B / (us * 1e-6), "keypoints_per_frame": nk / B,
+                     "algorithmic_bytes_per_frame": algo / B, "achieved_GBps": algo / (us * 1e-6) / 1e9,
+                     "hbm_frac": algo / (us * 1e-6) / 1e9 / peak_b,
+                     "note": "mvo_orb_extract_batch_dev, 64 frames per call, includes its one host sync per batch; "
+                             "integer-issue bound (FAST + BRIEF), not HBM bound — DESIGN.md §5"}
+
     # sanity: the pipeline is really tracking (not timing failures)
     ok = bool(res_last.pnp_ok) and res_last.n_inliers > 100
 
@@ -329,6 +363,7 @@ def run_gpu(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": roof,
             "stages": stages,
+            "orb_batch": orb_batch,
         }
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()

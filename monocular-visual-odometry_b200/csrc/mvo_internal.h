@@ -160,8 +160,18 @@ int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const in
                            const mvo_keypoint *d_kpts, float *d_p3, float *d_p2);
 int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g);
 // thresholds of matchFeatures + removeDuplicatedMatches on the device; d_info: [0] pairs, [1] candidates, [2] status
-int mvo_track_match_filter(mvo_ctx *ctx, const uint32_t *d_keys, const uint8_t *d_vis, int nmap, int nk, int method,
-                           int32_t *d_pairs, int32_t *d_info);
+struct MvoTrackFilter {
+  const uint32_t *d_keys;        // matcher keys of ALL map points
+  uint8_t *d_vis;                // in-view flags: read, or written when Tcw12 != nullptr (projection done by the filter)
+  int nmap, nk, method;
+  int32_t *d_pairs, *d_info;
+  const double *Tcw12, *K;       // optional projection (methods 1/2)
+  int rows, cols;
+  const float *d_map_pts;
+  const mvo_keypoint *d_kpts;    // optional: write the PnP input arrays (d_p3, d_p2) as well
+  float *d_p3, *d_p2;
+};
+int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 // mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)

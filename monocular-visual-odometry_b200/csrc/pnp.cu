@@ -256,27 +256,76 @@ k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int
   }
 }
 
+// Scoring: count(err^2 <= thr^2) per hypothesis, the count an fp64 evaluation gives, at fp32 cost.  Every point is
+// first reprojected in fp32 together with a bound M on the fp32 error of err^2 (inputs are exact floats; R, t, K are
+// rounded once; 3 FMAs, one approximate reciprocal, 2 FMAs — see the derivation at delta below).  Only points whose
+// err^2 lies within M of the threshold (or whose depth is within the bound of zero) are re-evaluated in fp64 — a
+// fraction of a percent — so the counts are identical to the all-fp64 kernel this replaces, while the fp64 pipe
+// (64 lanes/clk/SM, division included) no longer bounds the stage.  One hypothesis per warp, points staged once
+// per CTA in shared memory.
 __global__ void __launch_bounds__(256)
 k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev, PnpCam cam,
             double thr2, int H, const double *__restrict__ poses, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
   extern __shared__ float s_pts[];      // [n][5]: X Y Z u v
+  __shared__ float s_wmax[8];
   if (n_dev) n = min(n, *n_dev);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_pts[5 * i] = p3[3 * i]; s_pts[5 * i + 1] = p3[3 * i + 1]; s_pts[5 * i + 2] = p3[3 * i + 2];
-    s_pts[5 * i + 3] = p2[2 * i]; s_pts[5 * i + 4] = p2[2 * i + 1];
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float mloc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
+    s_pts[5 * i] = X; s_pts[5 * i + 1] = Y; s_pts[5 * i + 2] = Z;
+    s_pts[5 * i + 3] = p2[2 * i]; s_pts[5 * i + 4] = p2[2 * i + 1];
+    mloc = fmaxf(mloc, fabsf(X) + fabsf(Y) + fabsf(Z));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, d));
+  if (lane == 0) s_wmax[warp] = mloc;
+  __syncthreads();
+  float mmax = 0.f;
+  for (int w = 0; w < wpb; ++w) mmax = fmaxf(mmax, s_wmax[w]);
+  const float EPS = 1.1920929e-7f;      // 2^-23
+  const float fxf = (float)cam.fx, fyf = (float)cam.fy, cxf = (float)cam.cx, cyf = (float)cam.cy, thr2f = (float)thr2;
   for (int h = blockIdx.x * wpb + warp; h < H; h += gridDim.x * wpb) {
     if (!valid[h]) { if (lane == 0) counts[h] = -1; continue; }
     Pose P;
     const double *o = poses + (size_t)h * 12;
     for (int q = 0; q < 9; ++q) P.R[q] = o[q];
     for (int q = 0; q < 3; ++q) P.t[q] = o[9 + q];
+    float Rf[9], tf[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Rf[q] = (float)P.R[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) tf[q] = (float)P.t[q];
+    // |fl(x) - x| <= 4 EPS (max|R_ij| (|X|+|Y|+|Z|) + |t|) for each camera coordinate (coefficient rounding + 3 FMAs,
+    // twice the worst case); ca = that bound times the focal length
+    float rmax = 1.f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) rmax = fmaxf(rmax, fabsf(Rf[q]));
+    const float a = 4.f * EPS * (rmax * mmax + fmaxf(fabsf(tf[0]), fmaxf(fabsf(tf[1]), fabsf(tf[2]))));
+    const float ca = fmaxf(fxf, fyf) * a;
+    const float c0 = 2.f * EPS * (fabsf(cxf) + fabsf(cyf));
     int c = 0;
     for (int i = lane; i < n; i += 32) {
       const float *s = s_pts + 5 * i;
-      c += reproj_err2(P, cam, v3(s[0], s[1], s[2]), s[3], s[4]) <= thr2;
+      const float X = s[0], Y = s[1], Z = s[2], u = s[3], v = s[4];
+      const float x = fmaf(Rf[0], X, fmaf(Rf[1], Y, fmaf(Rf[2], Z, tf[0])));
+      const float y = fmaf(Rf[3], X, fmaf(Rf[4], Y, fmaf(Rf[5], Z, tf[1])));
+      const float z = fmaf(Rf[6], X, fmaf(Rf[7], Y, fmaf(Rf[8], Z, tf[2])));
+      const float iz = __fdividef(1.f, z);
+      const float xz = x * iz, yz = y * iz;
+      const float up = fxf * xz, vp = fyf * yz;
+      const float du = (up + cxf) - u, dv = (vp + cyf) - v;
+      const float e2 = fmaf(du, du, dv * dv);
+      // delta bounds the fp32 error of either projected coordinate:
+      //   f * (a + |x/z| a) / |z|   (errors of x, y, z)  +  5 EPS |f x/z|  (reciprocal, products, focal rounding)  +  2 EPS |c|
+      const float delta = fmaf(ca * fabsf(iz), 2.f + fabsf(xz) + fabsf(yz), fmaf(5.f * EPS, fabsf(up) + fabsf(vp), c0));
+      const float M = 2.f * (fmaf(2.f * (fabsf(du) + fabsf(dv)), delta, 2.f * delta * delta) + 4.f * EPS * (e2 + thr2f));
+      const bool front = z > 2.f * a + 1e-6f;                    // fp64 rule: z > 1e-9
+      const bool behind = z < -(2.f * a + 1e-6f);
+      const bool in = front && (e2 + M <= thr2f), out = behind || (front && (e2 - M > thr2f));
+      bool inl = in;
+      if (!in && !out) inl = reproj_err2(P, cam, v3(X, Y, Z), u, v) <= thr2;      // too close to call in fp32
+      c += inl;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
@@ -448,8 +497,8 @@ static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, c
   k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
   MVO_CHECK_LAUNCH(ctx);
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pnp_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (H + 7) / 8;
-  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+  int grid = (H + 7) / 8;                                   // one hypothesis per warp while the CTAs of one wave allow it
+  if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
   { KTimer kt(ctx, KC_PNP_SCORE);
   k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.valid, w.counts); }
   MVO_CHECK_LAUNCH(ctx);

@@ -10,17 +10,16 @@
 //                   T_w_c = [R|t]^-1 jump test against the previous frame, pose fallback, BA gate
 // All tiny (<= 2001 elements): one or a few CTAs each; they exist to remove host round trips, not for FLOPs.
 #include <algorithm>
+#include <string.h>
 #include "mvo_internal.h"
 
 namespace {
 
 struct Rt12 { double v[12]; };   // R row-major (9) + t (3), world->camera
 
-__global__ void __launch_bounds__(256)
-k_project_map(const float *__restrict__ map_pts, int nmap, Rt12 Tcw, double fx, double fy, double cx, double cy,
-              float fcols, float frows, uint8_t *__restrict__ vis, float2 *__restrict__ cxy) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nmap) return;
+// getMappointsInCurrentView_ (vo.cpp:16-49) for one map point: true when it is in front of the camera and inside the image
+__device__ __forceinline__ bool project_point(const float *__restrict__ map_pts, int i, const Rt12 &Tcw, double fx, double fy, double cx,
+                                              double cy, float fcols, float frows, float2 &uv) {
   // basics::preTranslatePoint3f (opencv_funcs.cpp:67-78): double accumulation of T(row, j) * p[j], j = 0..3,
   // narrowed to float.  Explicit _rn intrinsics: no FMA contraction, so the visibility decision is the one the
   // host arithmetic of the reference takes.
@@ -35,13 +34,22 @@ k_project_map(const float *__restrict__ map_pts, int nmap, Rt12 Tcw, double fx, 
     q[r] = acc;
   }
   const float xc = (float)q[0], yc = (float)q[1], zc = (float)q[2];
-  bool ok = !(zc < 0);
   // geometry::cam2pixel: K(0,0) * p.x / p.z + K(0,2) in double, narrowed to Point2f
   const float u = (float)__dadd_rn(__ddiv_rn(__dmul_rn(fx, (double)xc), (double)zc), cx);
   const float v = (float)__dadd_rn(__ddiv_rn(__dmul_rn(fy, (double)yc), (double)zc), cy);
-  ok = ok && (u > 0 && v > 0 && u < fcols && v < frows);
+  uv = make_float2(u, v);
+  return !(zc < 0) && (u > 0 && v > 0 && u < fcols && v < frows);
+}
+
+__global__ void __launch_bounds__(256)
+k_project_map(const float *__restrict__ map_pts, int nmap, Rt12 Tcw, double fx, double fy, double cx, double cy,
+              float fcols, float frows, uint8_t *__restrict__ vis, float2 *__restrict__ cxy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmap) return;
+  float2 uv;
+  const bool ok = project_point(map_pts, i, Tcw, fx, fy, cx, cy, fcols, frows, uv);
   vis[i] = ok ? 1 : 0;
-  cxy[i] = make_float2(u, v);
+  cxy[i] = uv;
 }
 
 __global__ void __launch_bounds__(256)
@@ -83,40 +91,35 @@ struct GlueArgs {
   double *res_d;            // [0..11] world->camera pose of the frame before BA
 };
 
-__global__ void __launch_bounds__(256) k_track_glue(GlueArgs a) {
-  __shared__ int s_n;
+__global__ void __launch_bounds__(1024) k_track_glue(GlueArgs a) {
   const int tid = threadIdx.x;
+  // every thread derives the (uniform) control values itself, so the edge copy below does not wait for thread 0
+  int mode = a.mode;
+  if (mode == 2) mode = (*a.n_pairs_dev >= a.min_pnp && *a.n_pairs_dev >= 4) ? 1 : 0;     // vo.cpp:304,311
+  int n_in = 0;
+  bool model = false;
+  if (mode == 1) { n_in = a.out_i[0]; model = n_in >= 4; if (!model) n_in = 0; }
   if (tid == 0) {
-    int n_in = 0, model = 0, ok = 0;
+    int ok = 0;
     double P[12];
     for (int q = 0; q < 12; ++q) P[q] = a.fallback.v[q];
-    int mode = a.mode;
-    if (mode == 2) mode = (*a.n_pairs_dev >= a.min_pnp && *a.n_pairs_dev >= 4) ? 1 : 0;     // vo.cpp:304,311
-    if (mode == 1) {
-      n_in = a.out_i[0];
-      model = n_in >= 4;
-      if (model) {
-        ok = 1;
-        for (int q = 0; q < 12; ++q) P[q] = a.pose_io[q];
-        // T_w_c = [R|t]^-1 (vo.cpp:357): translation -R^T t; reject jumps relative to the previous frame (:360-369)
-        const double tx = -(P[0] * P[9] + P[3] * P[10] + P[6] * P[11]);
-        const double ty = -(P[1] * P[9] + P[4] * P[10] + P[7] * P[11]);
-        const double tz = -(P[2] * P[9] + P[5] * P[10] + P[8] * P[11]);
-        const double dx = tx - a.prev_twc[0], dy = ty - a.prev_twc[1], dz = tz - a.prev_twc[2];
-        if (a.has_prev && sqrt(dx * dx + dy * dy + dz * dz) >= a.max_dist) ok = 0;
-        if (!ok) for (int q = 0; q < 12; ++q) P[q] = a.fallback.v[q];
-      } else {
-        n_in = 0;
-      }
+    if (model) {
+      ok = 1;
+      for (int q = 0; q < 12; ++q) P[q] = a.pose_io[q];
+      // T_w_c = [R|t]^-1 (vo.cpp:357): translation -R^T t; reject jumps relative to the previous frame (:360-369)
+      const double tx = -(P[0] * P[9] + P[3] * P[10] + P[6] * P[11]);
+      const double ty = -(P[1] * P[9] + P[4] * P[10] + P[7] * P[11]);
+      const double tz = -(P[2] * P[9] + P[5] * P[10] + P[8] * P[11]);
+      const double dx = tx - a.prev_twc[0], dy = ty - a.prev_twc[1], dz = tz - a.prev_twc[2];
+      if (a.has_prev && sqrt(dx * dx + dy * dy + dz * dz) >= a.max_dist) ok = 0;
+      if (!ok) for (int q = 0; q < 12; ++q) P[q] = a.fallback.v[q];
     }
     for (int q = 0; q < 12; ++q) { a.pose[(size_t)a.slot * 12 + q] = P[q]; a.res_d[q] = P[q]; }
     a.cnt[a.slot] = n_in;                       // the connections are recorded before the jump test (vo.cpp:333-354)
     a.skip_flag[0] = (ok && a.ba_enable) ? 0 : 1;
     a.res_i[0] = model; a.res_i[1] = ok; a.res_i[2] = n_in;
-    s_n = n_in;
   }
-  __syncthreads();
-  const int n_in = min(s_n, a.cap);
+  n_in = min(n_in, a.cap);
   for (int j = tid; j < n_in; j += blockDim.x) {
     const int2 pr = a.pairs[a.inl[j]];
     a.edge_map[(size_t)a.slot * a.cap + j] = pr.x;
@@ -166,7 +169,7 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
   a.edge_map = g.edge_map; a.edge_obs = (float2 *)g.edge_obs; a.cnt = g.cnt; a.pose = g.pose;
   a.skip_flag = g.skip_flag; a.res_i = g.res_i; a.res_d = g.res_d;
   KTimer kt(ctx, KC_TRACK);
-  k_track_glue<<<1, 256, 0, ctx->stream>>>(a);
+  k_track_glue<<<1, 1024, 0, ctx->stream>>>(a);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -196,15 +199,25 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
 namespace {
 
 constexpr int MF_T = 1024;
+constexpr int MF_BIG = 160;          // segments above this are partitioned by the whole CTA, the rest by one warp each
 constexpr int MF_MAXN = 8192;        // match-list / keypoint capacity of the device path (host path beyond)
 
 struct FilterArgs {
   const uint32_t *keys;     // [nmap * W]
-  const uint8_t *vis;       // [nmap]
+  uint8_t *vis;             // [nmap] in (project == 0) or out (project == 1)
   int nmap, nk, method, n_cap;
   double xg_ratio, lowe_ratio;
   int2 *pairs;              // out: (map index, keypoint index), sorted by keypoint index
   int32_t *info;            // out: [0] pairs, [1] candidates (map points in view), [2] status (0 ok, 1 host path needed)
+  // project == 1: getMappointsInCurrentView_ is evaluated here (methods 1/2: the matcher does not need the projections)
+  int project;
+  const float *map_pts;
+  Rt12 Tcw;
+  double fx, fy, cx, cy;
+  float fcols, frows;
+  // optional (p3 != nullptr): the 3d-2d pairs of poseEstimationPnP_ (vo.cpp:293-301) go straight into the PnP input arrays
+  const mvo_keypoint *kpts;
+  float *p3, *p2;
 };
 
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
@@ -215,10 +228,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
   __syncthreads();                       // s_warp may still be read from a previous call
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  int off = 0, tot = 0;
-  for (int w = 0; w < MF_T / 32; ++w) { const int c = s_warp[w]; if (w < warp) off += c; tot += c; }
-  total = tot;
-  return off + incl - v;
+  // every warp scans the 32 warp totals itself (one load + a shuffle scan instead of a serial loop)
+  int w = s_warp[lane];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+  total = __shfl_sync(0xffffffffu, w, 31);
+  const int before = __shfl_sync(0xffffffffu, w, warp) - __shfl_sync(0xffffffffu, s_warp[lane], warp);
+  return before + incl - v;
 }
 
 __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
@@ -241,6 +257,9 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   __syncthreads();
   // ---- thresholds (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2), ordered compaction ----
   const int per = (nmap + MF_T - 1) / MF_T, q0 = min(tid * per, nmap), q1 = min(q0 + per, nmap);
+  if (a.project) {          // every thread reads back only the flags it wrote itself
+    for (int q = q0; q < q1; ++q) { float2 uv; a.vis[q] = project_point(a.map_pts, q, a.Tcw, a.fx, a.fy, a.cx, a.cy, a.fcols, a.frows, uv) ? 1 : 0; }
+  }
   int nvis = 0;
   if (a.method != 2) {
     unsigned m = 0xFFFFFFFFu;
@@ -304,8 +323,52 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
     const int nseg = s_nseg[which];
     if (nseg == 0) break;
     if (level >= depth_limit) { if (tid == 0) s_status = 1; break; }      // libstdc++ would heapsort from here
+    // large segments (the first two or three levels): the whole CTA partitions them, one after the other
+    for (int s = 0; s < nseg; ++s) {
+      const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
+      if (last - first <= MF_BIG) continue;                                  // uniform: every thread reads the same list
+      if (tid == 0) {                                                        // __move_median_to_first(first, first+1, mid, last-1)
+        const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+        const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
+        int pick;
+        if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+        else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+        const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
+      }
+      __syncthreads();
+      const uint32_t pivot = arr[first] >> 16;
+      const int lo = first + 1, len = last - lo;
+      const int pc = (len + MF_T - 1) / MF_T, i0 = min(tid * pc, len), i1 = min(i0 + pc, len);
+      int cL = 0, cR = 0;
+      for (int i = i0; i < i1; ++i) { const uint32_t k = arr[lo + i] >> 16; cL += k >= pivot; cR += k <= pivot; }
+      int nL = 0, nR = 0;
+      int oL = block_excl_scan(cL, s_warp, nL);
+      int oR = block_excl_scan(cR, s_warp, nR);
+      for (int i = i0; i < i1; ++i) {
+        const uint32_t k = arr[lo + i] >> 16;
+        if (k >= pivot) Ls[lo + oL++] = (uint16_t)(lo + i);                  // Lo: ascending positions
+        if (k <= pivot) { Rs[lo + (nR - 1 - oR)] = (uint16_t)(lo + i); ++oR; }   // Ro: descending positions
+      }
+      __syncthreads();
+      const int nmin = min(nL, nR);
+      int kc = 0;
+      for (int j = tid; j < nmin; j += MF_T) kc += Ls[lo + j] < Rs[lo + j];  // monotone in j: the count is K
+      int K = 0;
+      (void)block_excl_scan(kc, s_warp, K);
+      for (int j = tid; j < K; j += MF_T) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
+      if (tid == 0) {
+        int cut;
+        if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;
+        else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
+        if (last - cut > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)cut | ((uint32_t)last << 16);
+        if (cut - first > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)first | ((uint32_t)cut << 16);
+      }
+      __syncthreads();
+    }
+    // the rest: one warp per segment
     for (int s = warp; s < nseg; s += MF_T / 32) {
       const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
+      if (last - first > MF_BIG) continue;
       // __move_median_to_first(first, first+1, mid, last-1)
       if (lane == 0) {
         const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
@@ -374,20 +437,36 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   int np = 0;
   int o = block_excl_scan(c2, s_warp, np);
   for (int t = t0; t < t1; ++t)
-    if (best[t] != 0xFFFFFFFFu) a.pairs[o++] = make_int2((int)amap[best[t] & 0xFFFFu], t);
+    if (best[t] != 0xFFFFFFFFu) {
+      const int mi = (int)amap[best[t] & 0xFFFFu];
+      a.pairs[o] = make_int2(mi, t);
+      if (a.p3) {
+        a.p3[3 * o] = a.map_pts[3 * mi]; a.p3[3 * o + 1] = a.map_pts[3 * mi + 1]; a.p3[3 * o + 2] = a.map_pts[3 * mi + 2];
+        a.p2[2 * o] = a.kpts[t].x; a.p2[2 * o + 1] = a.kpts[t].y;
+      }
+      ++o;
+    }
   if (tid == 0) { a.info[0] = np; a.info[1] = ncand; a.info[2] = 0; }
 }
 
 }  // namespace
 
-int mvo_track_match_filter(mvo_ctx *ctx, const uint32_t *d_keys, const uint8_t *d_vis, int nmap, int nk, int method,
-                           int32_t *d_pairs, int32_t *d_info) {
+int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f) {
   int cap = 2048;
-  while (cap < std::max(std::min(nmap, 65535), nk) && cap < MF_MAXN) cap *= 2;
+  while (cap < std::max(std::min(f.nmap, 65535), f.nk) && cap < MF_MAXN) cap *= 2;
   FilterArgs a;
-  a.keys = d_keys; a.vis = d_vis; a.nmap = nmap; a.nk = nk; a.method = method; a.n_cap = cap;
+  memset(&a, 0, sizeof a);
+  a.keys = f.d_keys; a.vis = f.d_vis; a.nmap = f.nmap; a.nk = f.nk; a.method = f.method; a.n_cap = cap;
   a.xg_ratio = ctx->prm.xiang_gao_ratio; a.lowe_ratio = ctx->prm.lowe_ratio;
-  a.pairs = (int2 *)d_pairs; a.info = d_info;
+  a.pairs = (int2 *)f.d_pairs; a.info = f.d_info;
+  a.project = f.Tcw12 != nullptr;
+  a.map_pts = f.d_map_pts;
+  if (a.project) {
+    for (int q = 0; q < 12; ++q) a.Tcw.v[q] = f.Tcw12[q];
+    a.fx = f.K[0]; a.fy = f.K[4]; a.cx = f.K[2]; a.cy = f.K[5];
+    a.fcols = (float)f.cols; a.frows = (float)f.rows;
+  }
+  a.kpts = f.d_kpts; a.p3 = f.d_p3; a.p2 = f.d_p2;
   const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 2 * ((size_t)cap / 16 + 2) * 4 + 64;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KTimer kt(ctx, KC_TRACK);

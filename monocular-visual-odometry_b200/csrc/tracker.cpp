@@ -347,7 +347,11 @@ extern "C" int mvo_test_match_filter_dev(mvo_ctx *ctx, const uint32_t *keys, con
   MVO_CUDA(ctx, cudaMalloc(&d, tot));
   cudaMemcpyAsync(d, keys, (size_t)nmap * W * 4, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(d + o_vis, vis, nmap, cudaMemcpyHostToDevice, ctx->stream);
-  int rc = mvo_track_match_filter(ctx, (const uint32_t *)d, d + o_vis, nmap, nk, method, (int32_t *)(d + o_pairs), (int32_t *)(d + o_info));
+  MvoTrackFilter f;
+  memset(&f, 0, sizeof f);
+  f.d_keys = (const uint32_t *)d; f.d_vis = d + o_vis; f.nmap = nmap; f.nk = nk; f.method = method;
+  f.d_pairs = (int32_t *)(d + o_pairs); f.d_info = (int32_t *)(d + o_info);
+  int rc = mvo_track_match_filter(ctx, f);
   if (rc == MVO_OK) {
     cudaMemcpyAsync(info, d + o_info, 12, cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = mvo_fail(ctx, MVO_ERR_CUDA, "match filter kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -584,15 +588,18 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   // ---- getMappointsInCurrentView_ + matchFeatures(map descriptors, frame descriptors) (vo.cpp:16-49, 283-289) ----
   auto fail = [&](int rc) { cudaStreamSynchronize(ctx->stream); t->frames.pop_back(); return rc; };
   int rc = MVO_OK;
+  double Tcw[12];
+  Twc_to_Rt12(cur.T_w_c, Tcw);
+  // methods 1/2: the matcher does not need the projections, so the in-view test is folded into the filter kernel
+  // (the keys of points outside the view are simply ignored there); method 3 gates on the projected pixel
+  const bool project_in_filter = method != 3 && !force_host_filter && t->fused_holdoff == 0;
   if (nmap > 0) {
-    double Tcw[12];
-    Twc_to_Rt12(cur.T_w_c, Tcw);
-    rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
+    if (!project_in_filter) rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
     if (rc == MVO_OK && can_match) {
       if (method == 3) rc = mvo_track_kpt_xy(ctx, job.d_k, nk, t->d_kxy);
       if (rc == MVO_OK)
         rc = mvo_match_launch_masked(ctx, method == 1 ? 0 : (method == 2 ? 1 : 2), t->d_map_desc, t->d_cxy, nmap, job.d_d, t->d_kxy, nk,
-                                     t->prm.match_radius, d_keys, d_vis);
+                                     t->prm.match_radius, d_keys, project_in_filter ? nullptr : d_vis);
     } else if (rc == MVO_OK) {
       if (cudaMemsetAsync(d_keys, 0xFF, (size_t)nmap * 8, ctx->stream) != cudaSuccess) rc = mvo_fail(ctx, MVO_ERR_CUDA, "tracker: memset");
     }
@@ -602,7 +609,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   // ---- everything after the matcher: thresholds + duplicate removal, PnP, frame-buffer update, BA ----
   // d_n != nullptr: the pair count lives on the device (n = its upper bound); otherwise n pairs are in d_pairs
   MvoPoseStore st;
-  auto enqueue_tail = [&](int n, const int32_t *d_n) -> int {
+  auto enqueue_tail = [&](int n, const int32_t *d_n, bool gathered) -> int {
     MvoTrackGlue g;
     memset(&g, 0, sizeof g);
     const bool run_pnp = n >= 4 && (d_n != nullptr || n >= t->prm.min_pnp_points);
@@ -621,7 +628,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
       double *d_pose_io;
       int32_t *d_out_i, *d_inl;
       rc2 = mvo_pnp_dev_buffers(ctx, n, &d_p3, &d_p2, &d_pose_io, &d_out_i, &d_inl);
-      if (rc2 == MVO_OK) rc2 = mvo_track_gather_pairs(ctx, t->d_pairs, n, d_n, t->d_map_pts, job.d_k, d_p3, d_p2);
+      if (rc2 == MVO_OK && !gathered) rc2 = mvo_track_gather_pairs(ctx, t->d_pairs, n, d_n, t->d_map_pts, job.d_k, d_p3, d_p2);
       if (rc2 == MVO_OK) rc2 = mvo_pnp_dev_run(ctx, n, t->K, d_n);
       g.pose_io = d_pose_io; g.out_i = d_out_i; g.inl = d_inl;
     }
@@ -671,7 +678,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
     h_fi[0] = nm; h_fi[1] = ncand; h_fi[2] = 0;
     MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pairs, h_pairs, (size_t)nm * 8, cudaMemcpyHostToDevice, ctx->stream));
     MVO_CUDA(ctx, cudaMemcpyAsync(d_finfo, h_fi, 12, cudaMemcpyHostToDevice, ctx->stream));
-    return enqueue_tail(nm, nullptr);
+    return enqueue_tail(nm, nullptr, false);
   };
 
   // The device filter restates the quicksort phase of libstdc++'s std::sort and declines when that phase would hit
@@ -680,8 +687,21 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   bool fused = nmap > 0 && !force_host_filter && t->fused_holdoff == 0;
   if (t->fused_holdoff > 0) --t->fused_holdoff;
   if (fused) {
-    rc = mvo_track_match_filter(ctx, d_keys, d_vis, nmap, nk, method, t->d_pairs, d_finfo);
-    if (rc == MVO_OK) rc = enqueue_tail(std::min(nmap, std::max(nk, 0)), d_finfo);
+    const int n_upper = std::min(nmap, std::max(nk, 0));
+    MvoTrackFilter f;
+    memset(&f, 0, sizeof f);
+    f.d_keys = d_keys; f.d_vis = d_vis; f.nmap = nmap; f.nk = nk; f.method = method;
+    f.d_pairs = t->d_pairs; f.d_info = d_finfo;
+    if (project_in_filter) { f.Tcw12 = Tcw; f.K = t->K; f.rows = t->rows; f.cols = t->cols; }
+    f.d_map_pts = t->d_map_pts;
+    if (n_upper >= 4) {          // the filter writes the PnP input arrays itself
+      double *d_pose_io;
+      int32_t *d_out_i, *d_inl;
+      rc = mvo_pnp_dev_buffers(ctx, n_upper, &f.d_p3, &f.d_p2, &d_pose_io, &d_out_i, &d_inl);
+      f.d_kpts = job.d_k;
+    }
+    if (rc == MVO_OK) rc = mvo_track_match_filter(ctx, f);
+    if (rc == MVO_OK) rc = enqueue_tail(n_upper, d_finfo, true);
     if (rc != MVO_OK) return fail(rc);
     TMARK(0);
     if (h_flags[6] != 0) { fused = false; t->fused_holdoff = 64; }      // the device filter declined: redo the tail through the host
