@@ -322,11 +322,19 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / nrep
         nk = int(d_c.sum().item())
+        # where the batch time goes: CUDA events around every kernel class, separate pass
+        mvo_b200.timing_enable(ctx, (1 << len(names)) - 1)
+        mvo_b200.timing_read(ctx)
+        for it in range(2):
+            orb_batch_call((it % 2) * B)
+        ms_b, cnt_b = mvo_b200.timing_read(ctx)
+        mvo_b200.timing_enable(ctx, 0)
+        batch_stages = {names[k]: round(1e3 * ms_b[k] / (2 * B), 3) for k in range(len(names)) if cnt_b[k]}
         algo = B * (frame_bytes + 28 * (nk / B) + 32 * (nk / B))     # BGR in + KeyPoint + descriptor out
         peak_b, _ = _peaks()
         orb_batch = {"batch": B, "us_per_batch": us, "frames_per_s": B / (us * 1e-6), "keypoints_per_frame": nk / B,
                      "algorithmic_bytes_per_frame": algo / B, "achieved_GBps": algo / (us * 1e-6) / 1e9,
-                     "hbm_frac": algo / (us * 1e-6) / 1e9 / peak_b,
+                     "hbm_frac": algo / (us * 1e-6) / 1e9 / peak_b, "kernel_us_per_frame": batch_stages,
                      "note": "mvo_orb_extract_batch_dev, 64 frames per call, includes its one host sync per batch; "
                              "integer-issue bound (FAST + BRIEF), not HBM bound — DESIGN.md §5"}
 

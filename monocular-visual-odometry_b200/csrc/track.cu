@@ -192,14 +192,15 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
 //     ballots, counts K = #{k : Lo[k] < Ro[k]}, performs the K swaps in parallel and returns the cut
 //     min(Lo[K], Ro[K-1]) (Lo[0] when K = 0) — exactly where the sequential scan stops.
 //   * Recursion order is irrelevant (segments are disjoint): segments are processed level by level, one warp
-//     per segment.
+//     per segment.  (Measured alternatives that were slower on real match lists: whole-CTA partitions of the large
+//     segments — ~4.5K cycles each, and unbalanced median-of-3 splits keep a few large segments alive for many
+//     levels — and warp-local depth-first subtrees.)
 //   * If a segment is still > 16 at the depth limit (libstdc++ would switch to heapsort: adversarial inputs
 //     only) the kernel reports status 1 and the host finishes the frame through the host path.
 // Parity: tests/test_tracker_gpu.py (same match lists as the host std::sort on every frame, all three methods).
 namespace {
 
 constexpr int MF_T = 1024;
-constexpr int MF_BIG = 160;          // segments above this are partitioned by the whole CTA, the rest by one warp each
 constexpr int MF_MAXN = 8192;        // match-list / keypoint capacity of the device path (host path beyond)
 
 struct FilterArgs {
@@ -254,6 +255,8 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   const int nmap = a.nmap;
   const bool sad = a.method == 3;
   if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; }
+  long long tph = clock64();        // phase cycle counters (thread 0) -> info[4..8]: prologue, compaction, sort levels, epilogue
+#define MF_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); a.info[4 + (i)] = (int32_t)(t_ - tph); tph = t_; } } while (0)
   __syncthreads();
   // ---- thresholds (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2), ordered compaction ----
   const int per = (nmap + MF_T - 1) / MF_T, q0 = min(tid * per, nmap), q1 = min(q0 + per, nmap);
@@ -313,62 +316,27 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   for (int i = tid; i < a.nk; i += MF_T) best[i] = 0xFFFFFFFFu;
   if (tid == 0 && n > 16) { segA[0] = 0u | ((uint32_t)n << 16); s_nseg[0] = 1; }
   __syncthreads();
+  MF_MARK(0);
   // ---- quicksort phase of std::sort, level by level ----
   int depth_limit = 0;
   for (int m = n; m > 1; m >>= 1) ++depth_limit;        // std::__lg(n)
   depth_limit *= 2;
   uint32_t *cur = segA, *nxt = segB;
   int level = 0, which = 0;
+  long long tlev = clock64();
   while (true) {
     const int nseg = s_nseg[which];
     if (nseg == 0) break;
     if (level >= depth_limit) { if (tid == 0) s_status = 1; break; }      // libstdc++ would heapsort from here
-    // large segments (the first two or three levels): the whole CTA partitions them, one after the other
-    for (int s = 0; s < nseg; ++s) {
-      const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
-      if (last - first <= MF_BIG) continue;                                  // uniform: every thread reads the same list
-      if (tid == 0) {                                                        // __move_median_to_first(first, first+1, mid, last-1)
-        const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
-        const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
-        int pick;
-        if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
-        else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
-        const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
-      }
-      __syncthreads();
-      const uint32_t pivot = arr[first] >> 16;
-      const int lo = first + 1, len = last - lo;
-      const int pc = (len + MF_T - 1) / MF_T, i0 = min(tid * pc, len), i1 = min(i0 + pc, len);
-      int cL = 0, cR = 0;
-      for (int i = i0; i < i1; ++i) { const uint32_t k = arr[lo + i] >> 16; cL += k >= pivot; cR += k <= pivot; }
-      int nL = 0, nR = 0;
-      int oL = block_excl_scan(cL, s_warp, nL);
-      int oR = block_excl_scan(cR, s_warp, nR);
-      for (int i = i0; i < i1; ++i) {
-        const uint32_t k = arr[lo + i] >> 16;
-        if (k >= pivot) Ls[lo + oL++] = (uint16_t)(lo + i);                  // Lo: ascending positions
-        if (k <= pivot) { Rs[lo + (nR - 1 - oR)] = (uint16_t)(lo + i); ++oR; }   // Ro: descending positions
-      }
-      __syncthreads();
-      const int nmin = min(nL, nR);
-      int kc = 0;
-      for (int j = tid; j < nmin; j += MF_T) kc += Ls[lo + j] < Rs[lo + j];  // monotone in j: the count is K
-      int K = 0;
-      (void)block_excl_scan(kc, s_warp, K);
-      for (int j = tid; j < K; j += MF_T) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
-      if (tid == 0) {
-        int cut;
-        if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;
-        else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
-        if (last - cut > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)cut | ((uint32_t)last << 16);
-        if (cut - first > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)first | ((uint32_t)cut << 16);
-      }
-      __syncthreads();
-    }
-    // the rest: one warp per segment
+    // __introsort_loop recurses on [cut, last) and continues with [first, cut): both go to the next level's lists
+    auto push = [&](int f, int l) {
+      if (l - f <= 16) return;                                              // left to the final insertion sort
+      const uint32_t seg = (uint32_t)f | ((uint32_t)l << 16);
+      nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = seg;
+    };
+    // one warp per segment
     for (int s = warp; s < nseg; s += MF_T / 32) {
       const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
-      if (last - first > MF_BIG) continue;
       // __move_median_to_first(first, first+1, mid, last-1)
       if (lane == 0) {
         const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
@@ -411,13 +379,15 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
         int cut;
         if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;                    // Lo[0] exists after the median step
         else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
-        // __introsort_loop: recurse on [cut, last), continue with [first, cut)
-        if (last - cut > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)cut | ((uint32_t)last << 16);
-        if (cut - first > 16) nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = (uint32_t)first | ((uint32_t)cut << 16);
+        push(cut, last);
+        push(first, cut);
       }
     }
     __syncthreads();
-    if (tid == 0) s_nseg[which] = 0;
+    if (tid == 0) {
+      if (level < 7) { const long long t_ = clock64(); a.info[9 + 2 * level] = (int32_t)(t_ - tlev); a.info[10 + 2 * level] = nseg; tlev = t_; }
+      s_nseg[which] = 0;
+    }
     which ^= 1;
     uint32_t *t = cur; cur = nxt; nxt = t;
     ++level;
@@ -428,6 +398,8 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
     if (tid == 0) { a.info[0] = 0; a.info[1] = ncand; a.info[2] = 1; }
     return;
   }
+  MF_MARK(1);
+  if (tid == 0) a.info[8] = level;
   // ---- final insertion sort is stable: of every run of equal keypoint indices the leftmost element survives ----
   for (int p = tid; p < n; p += MF_T) atomicMin(&best[arr[p] >> 16], ((uint32_t)p << 16) | (arr[p] & 0xFFFFu));
   __syncthreads();
@@ -447,6 +419,8 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
       ++o;
     }
   if (tid == 0) { a.info[0] = np; a.info[1] = ncand; a.info[2] = 0; }
+  MF_MARK(2);
+#undef MF_MARK
 }
 
 }  // namespace

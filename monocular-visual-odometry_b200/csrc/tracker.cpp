@@ -353,7 +353,7 @@ extern "C" int mvo_test_match_filter_dev(mvo_ctx *ctx, const uint32_t *keys, con
   f.d_pairs = (int32_t *)(d + o_pairs); f.d_info = (int32_t *)(d + o_info);
   int rc = mvo_track_match_filter(ctx, f);
   if (rc == MVO_OK) {
-    cudaMemcpyAsync(info, d + o_info, 12, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(info, d + o_info, 48, cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = mvo_fail(ctx, MVO_ERR_CUDA, "match filter kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     else if (info[2] == 0 && info[0] > 0) cudaMemcpy(pairs, d + o_pairs, (size_t)info[0] * 8, cudaMemcpyDeviceToHost);
   }
@@ -551,8 +551,8 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
 // device-resident path
 // ------------------------------------------------------------------------------------------------------------
 // Layout of the 768-byte result block (d_flags, d_res, d_stats are contiguous):
-//   int32 [0] BA skip flag   [4..6] match filter: pairs, candidates, status   [8..10] model found, pnp_ok, inliers
-//         [16..] BA graph: frames, edges, slot of frame f
+//   int32 [0] BA skip flag   [8..10] model found, pnp_ok, inliers   [16..33] BA graph: frames, edges, slot of frame f
+//         [40..48] match filter: pairs, candidates, status, -, phase cycle counters
 //   +256: world->camera pose of the frame before BA (12 doubles)      +512: BA statistics (16 doubles)
 static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res) {
   mvo_ctx *ctx = t->ctx;
@@ -580,7 +580,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
 
   uint32_t *d_keys = (uint32_t *)t->d_keysvis;
   uint8_t *d_vis = t->d_keysvis + (size_t)std::max(nmap, 1) * 8;
-  int32_t *d_finfo = t->d_flags + 4, *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
+  int32_t *d_finfo = t->d_flags + 40, *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
   uint8_t *h_out = t->h_pin + al256((size_t)std::max(nmap, 1) * 9) + al256((size_t)std::max(nmap, 1) * 8 + 64);
   const int32_t *h_flags = (const int32_t *)h_out;
   const bool can_match = nmap > 0 && nk > 0 && !(method == 2 && nk < 2);
@@ -704,7 +704,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
     if (rc == MVO_OK) rc = enqueue_tail(n_upper, d_finfo, true);
     if (rc != MVO_OK) return fail(rc);
     TMARK(0);
-    if (h_flags[6] != 0) { fused = false; t->fused_holdoff = 64; }      // the device filter declined: redo the tail through the host
+    if (h_flags[42] != 0) { fused = false; t->fused_holdoff = 64; }      // the device filter declined: redo the tail through the host
   }
   if (!fused) {
     rc = host_filter_tail();
@@ -715,8 +715,8 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   const int32_t *h_res_i = h_flags + 8, *h_info = h_flags + 16;
   const double *h_res_d = (const double *)(h_out + 256), *h_stats = (const double *)(h_out + 512);
   const double *h_ring = (const double *)(h_out + 768);
-  r.n_matches = h_flags[4];
-  r.n_candidates = h_flags[5];
+  r.n_matches = h_flags[40];
+  r.n_candidates = h_flags[41];
   const bool pnp_ok = h_res_i[1] != 0;
   r.n_inliers = h_res_i[2];
   r.pnp_ok = pnp_ok;
@@ -741,7 +741,11 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   }
   TMARK(2);
   if (dbg && ++nacc % 50 == 0) {
-    fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f\n", acc[0] / 50, acc[1] / 50, acc[2] / 50);
+    fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f | filter kernel cycles: prologue %d sort %d (%d levels) epilogue %d\n",
+            acc[0] / 50, acc[1] / 50, acc[2] / 50, h_flags[44], h_flags[45], h_flags[48], h_flags[46]);
+    fprintf(stderr, "  per level (cycles, nbig*1000+nsmall):");
+    for (int l = 0; l < 7; ++l) fprintf(stderr, " %d/%d", h_flags[49 + 2 * l], h_flags[50 + 2 * l]);
+    fprintf(stderr, "\n");
     for (double &a : acc) a = 0;
   }
 #undef TMARK

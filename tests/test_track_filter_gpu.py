@@ -20,7 +20,7 @@ def _run(ctx, which, keys, vis, nk, method):
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     nmap = len(vis)
     pairs = np.full((max(nmap, 1), 2), -1, np.int32)
-    info = np.zeros(4, np.int32)
+    info = np.zeros(16, np.int32)
     keys = np.ascontiguousarray(keys, np.uint32)
     vis = np.ascontiguousarray(vis, np.uint8)
     rc = fn(ctx.h, keys.ctypes.data, vis.ctypes.data, nmap, nk, method, pairs.ctypes.data, info.ctypes.data)
