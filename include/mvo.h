@@ -7,7 +7,7 @@
  * call in the VO layer.  Each entry point below names the
  * reference interface it replaces (paths relative to the reference repo root).
  * The C++ adapters with the reference's exact signatures live in
- * include/my_slam/ and forward to these functions.
+ * monocular-visual-odometry_b200/my_slam_adapter/ and forward to these functions.
  *
  * Conventions
  *  - All pointers in the mvo_* (non-_dev) functions are HOST pointers owned by

@@ -84,6 +84,15 @@ __device__ void se3_update(const double *d, const double *in, double *out) {
   const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
   double a, b, c;
   if (th < 0.00001) { a = 1; b = 1; c = 1; }        // g2o's small-angle branch: R = V = I + O + O^2
+  else if (th2 < 0.0625) {
+    // sin(th)/th, (1-cos th)/th^2, (th-sin th)/th^3 as Taylor polynomials in th^2 (next term < 1e-24 relative for
+    // th < 0.25): LM steps are small rotations, and this keeps sincos, a square root and three divisions off the
+    // dependent chain of every trial.  Larger angles take the closed form below.
+    const double x = th2;
+    a = 1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 + x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0 + x * (-1.0 / 1307674368000.0 + x * (1.0 / 355687428096000.0))))))));
+    b = 0.5 + x * (-1.0 / 24 + x * (1.0 / 720 + x * (-1.0 / 40320 + x * (1.0 / 3628800 + x * (-1.0 / 479001600 + x * (1.0 / 87178291200.0 + x * (-1.0 / 20922789888000.0 + x * (1.0 / 6402373705728000.0))))))));
+    c = 1.0 / 6 + x * (-1.0 / 120 + x * (1.0 / 5040 + x * (-1.0 / 362880 + x * (1.0 / 39916800 + x * (-1.0 / 6227020800.0 + x * (1.0 / 1307674368000.0 + x * (-1.0 / 355687428096000.0 + x * (1.0 / 121645100408832000.0))))))));
+  }
   else { double sn, cs; sincos(th, &sn, &cs); const double ith = 1.0 / th; a = sn * ith; b = (1 - cs) * ith * ith; c = (th - sn) * ith * ith * ith; }
   const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
   double O2[9];

@@ -351,6 +351,17 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
   if (n_dev) n = min(n, *n_dev);
   int n_in = 0;
   if (mode == 0) {
+    // this thread's chunk of points: loaded first so that the L2 round trip overlaps the arg-max
+    constexpr int MAXPER = 4;             // n <= 4096 on the register path; beyond that the points are re-read
+    const int per = (n + FIN_T - 1) / FIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+    float px[MAXPER][5];
+    if (per <= MAXPER) {
+#pragma unroll
+      for (int k = 0; k < MAXPER; ++k) {
+        const int i = b0 + k;
+        if (i < e0) { px[k][0] = p3[3 * i]; px[k][1] = p3[3 * i + 1]; px[k][2] = p3[3 * i + 2]; px[k][3] = p2[2 * i]; px[k][4] = p2[2 * i + 1]; }
+      }
+    }
     // arg-max of the inlier count, ties -> lowest hypothesis index
     long long best = -1;
     for (int h = tid; h < H; h += FIN_T) {
@@ -381,10 +392,19 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     Pose P;
     for (int q = 0; q < 9; ++q) P.R[q] = s_pose[q];
     for (int q = 0; q < 3; ++q) P.t[q] = s_pose[9 + q];
-    const int per = (n + FIN_T - 1) / FIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+    // one evaluation per point: the chunk's points and verdicts stay in registers between the count and the write
+    unsigned flags = 0;
     int mine = 0;
-    for (int i = b0; i < e0; ++i)
-      mine += reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2;
+    if (per <= MAXPER) {
+#pragma unroll
+      for (int k = 0; k < MAXPER; ++k) {
+        const int i = b0 + k;
+        if (i < e0 && reproj_err2(P, cam, v3(px[k][0], px[k][1], px[k][2]), px[k][3], px[k][4]) <= thr2) { flags |= 1u << k; ++mine; }
+      }
+    } else {
+      for (int i = b0; i < e0; ++i)
+        mine += reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2;
+    }
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -392,22 +412,39 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     __syncthreads();
     int off = incl - mine;
     for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
-    for (int i = b0; i < e0; ++i)
-      if (reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2) inl[off++] = i;
-    __syncthreads();     // inl[] visible to the whole block (global memory, same CTA)
+    // consensus set in ascending order + the one-frame edge list for the pose-only LM refit (ba.cu: k_ba_pose)
+    if (per <= MAXPER) {
+#pragma unroll
+      for (int k = 0; k < MAXPER; ++k)
+        if (flags & (1u << k)) {
+          inl[off] = b0 + k;
+          ex[3 * off] = px[k][0]; ex[3 * off + 1] = px[k][1]; ex[3 * off + 2] = px[k][2];
+          eo[2 * off] = px[k][3]; eo[2 * off + 1] = px[k][4];
+          ef[off] = 0;
+          ++off;
+        }
+    } else {
+      for (int i = b0; i < e0; ++i)
+        if (reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2) {
+          inl[off] = i;
+          ex[3 * off] = p3[3 * i]; ex[3 * off + 1] = p3[3 * i + 1]; ex[3 * off + 2] = p3[3 * i + 2];
+          eo[2 * off] = p2[2 * i]; eo[2 * off + 1] = p2[2 * i + 1];
+          ef[off] = 0;
+          ++off;
+        }
+    }
   } else {
     n_in = n;
     if (tid < 12) s_pose[tid] = pose_io[tid];
     __syncthreads();
+    // refine-only entry: every point is an edge
+    for (int j = tid; j < n_in; j += FIN_T) {
+      ex[3 * j] = p3[3 * j]; ex[3 * j + 1] = p3[3 * j + 1]; ex[3 * j + 2] = p3[3 * j + 2];
+      eo[2 * j] = p2[2 * j]; eo[2 * j + 1] = p2[2 * j + 1];
+      ef[j] = 0;
+    }
   }
 
-  // hand the consensus set to the pose-only LM (ba.cu: k_ba_pose) as a one-frame edge list
-  for (int j = tid; j < n_in; j += FIN_T) {
-    const int i = mode == 0 ? inl[j] : j;
-    ex[3 * j] = p3[3 * i]; ex[3 * j + 1] = p3[3 * i + 1]; ex[3 * j + 2] = p3[3 * i + 2];
-    eo[2 * j] = p2[2 * i]; eo[2 * j + 1] = p2[2 * i + 1];
-    ef[j] = 0;
-  }
   for (int j = n_in + tid; j < n_upper; j += FIN_T) ef[j] = -1;       // masked out of the refit
   const int it = 0;
   if (tid < 12) pose_io[tid] = s_pose[tid];
