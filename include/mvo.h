@@ -305,6 +305,34 @@ int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask);
 int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts);
 uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t);
 
+/* ---- on-disk formats either side of the path (host only) -------------------
+ * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose
+ * per line, "tx ty tz R00 R10 R20 R01 R11 R21 R02 R12 R22", C++ stream defaults (6 significant digits).
+ * T_list: n x 16 doubles, row-major 4x4 camera->world.  mvo_read_pose_file returns MVO_ERR_CAPACITY (with
+ * *n = poses in the file) when cap is too small. */
+int mvo_write_pose_file(const char *filename, const double *T_list, int n);
+int mvo_read_pose_file(const char *filename, double *T_list, int cap, int *n);
+/* readImagePaths (vo_io.cpp:12-37): dataset_dir + image_formatting with one %0Nd directive ("/rgb_%05d.png",
+ * run_vo.cpp:90) applied to `index`. */
+int mvo_image_path(const char *dataset_dir, const char *image_formatting, int index, char *out, size_t cap);
+/* config/config.yaml (OpenCV "%YAML:1.0" dialect as the shipped file uses it: flat scalars, one nesting level
+ * for the dataset sections — addressed as "section/key" —, optional double quotes, # comments), the file
+ * my_slam::basics::Config reads (src/basics/config.cpp:12-47).  get_int rounds like cv::FileNode -> int,
+ * get_bool follows Config::getBool ("true"/"True").  A missing key returns MVO_ERR_INVALID_ARG (the
+ * reference throws std::runtime_error, config.cpp:35). */
+typedef struct mvo_config mvo_config;
+int mvo_config_load(const char *filename, mvo_config **out);
+void mvo_config_free(mvo_config *c);
+int mvo_config_get_string(const mvo_config *c, const char *key, char *out, size_t cap);
+int mvo_config_get_double(const mvo_config *c, const char *key, double *out);
+int mvo_config_get_int(const mvo_config *c, const char *key, int *out);
+int mvo_config_get_bool(const mvo_config *c, const char *key, int *out);
+/* Fill the parameters the hot path latches from the config (any of p / tp / K9 may be NULL): ORB, grid
+ * selection and match ratios (feature_match.cpp:16-23,56-58,137-139), the tracking keys of vo.cpp, and the
+ * 3x3 intrinsics of the dataset selected by dataset_name (readCameraIntrinsics, vo_io.cpp:40-49).  Fields
+ * without a config key (PnP hypotheses, BA iterations, ...) are left as they are. */
+int mvo_config_apply(const mvo_config *c, mvo_params *p, mvo_track_params *tp, double *K9);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,16 @@ SIGNATURES = {
     "mvo_kernel_name": (C.c_char_p, [_i]),
     "mvo_timing_enable": (_i, [_vp, C.c_uint32]),
     "mvo_timing_read": (_i, [_vp, _vp, _vp]),
+    "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
+    "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
+    "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
+    "mvo_config_load": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "mvo_config_free": (None, [_vp]),
+    "mvo_config_get_string": (_i, [_vp, C.c_char_p, C.c_char_p, _sz]),
+    "mvo_config_get_double": (_i, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
+    "mvo_config_get_int": (_i, [_vp, C.c_char_p, _pi]),
+    "mvo_config_get_bool": (_i, [_vp, C.c_char_p, _pi]),
+    "mvo_config_apply": (_i, [_vp, C.POINTER(Params), C.POINTER(TrackParams), _vp]),
 }
 
 _lib = None
