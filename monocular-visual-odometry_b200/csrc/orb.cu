@@ -420,12 +420,18 @@ __constant__ float c_gauss7[7];
 
 constexpr int BLUR_TW = 128, BLUR_TH = 16;
 
+// all pyramid levels of a frame in ONE launch: blockIdx.x walks the tiles of level 0, then level 1, ...
+struct BlurTiles { int first[MVO_MAX_LEVELS + 1]; int nx[MVO_MAX_LEVELS]; };
+
 __global__ void __launch_bounds__(256)
-k_blur(OrbPlanDev plan, int level, uint8_t *__restrict__ planes) {
+k_blur(OrbPlanDev plan, BlurTiles tiles, uint8_t *__restrict__ planes) {
   __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
   __shared__ float s_row[BLUR_TH + 6][BLUR_TW + 1];
+  int level = 0;
+  while (level + 1 < plan.nlevels && (int)blockIdx.x >= tiles.first[level + 1]) ++level;
+  const int tile = (int)blockIdx.x - tiles.first[level];
   const OrbLevelDev &L = plan.lv[level];
-  const int f = blockIdx.z, tx0 = blockIdx.x * BLUR_TW, ty0 = blockIdx.y * BLUR_TH;
+  const int f = blockIdx.z, tx0 = (tile % tiles.nx[level]) * BLUR_TW, ty0 = (tile / tiles.nx[level]) * BLUR_TH;
   const int w = L.w, h = L.h;
   const uint8_t *img = planes + (size_t)f * plan.slot_bytes + L.img_off;
   uint8_t *out = planes + (size_t)f * plan.slot_bytes + L.blur_off;
@@ -731,12 +737,18 @@ int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *stag
 
 int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int batch) {
   MVO_TRY(upload_gauss(ctx));
+  BlurTiles tiles;
+  int total = 0;
   for (int l = 0; l < plan.nlevels; ++l) {
-    dim3 grid((plan.lv[l].w + BLUR_TW - 1) / BLUR_TW, (plan.lv[l].h + BLUR_TH - 1) / BLUR_TH, batch);
-    KTimer kt(ctx, KC_BLUR);
-    k_blur<<<grid, 256, 0, ctx->stream>>>(plan, l, planes);
-    MVO_CHECK_LAUNCH(ctx);
+    tiles.first[l] = total;
+    tiles.nx[l] = (plan.lv[l].w + BLUR_TW - 1) / BLUR_TW;
+    total += tiles.nx[l] * ((plan.lv[l].h + BLUR_TH - 1) / BLUR_TH);
   }
+  tiles.first[plan.nlevels] = total;
+  dim3 grid(total, 1, batch);
+  KTimer kt(ctx, KC_BLUR);
+  k_blur<<<grid, 256, 0, ctx->stream>>>(plan, tiles, planes);
+  MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
 

@@ -207,3 +207,37 @@ def test_lost_frame_host_array_path(ctx):
     assert r3.pnp_ok == 1
     trk.close()
     ctx.set_params(max_keypoints=1500)
+
+
+def test_large_map_and_map_swap_device_vs_host_arrays(ctx):
+    """A map larger than the keypoint capacity (extra points all over the place: most fail the in-view test, the rest
+    compete as wrong matches) and a map replacement in the middle of a sequence (the device copy is re-uploaded, the
+    resident frame buffer survives): the device-resident path must still equal the host-array path."""
+    import mvo_b200
+    ctx.set_params(max_keypoints=2000, ba_iterations=10)
+    imgs, _ = _make_sequence(8, 8)
+    pts, desc = _map_from_frame0(ctx, imgs[0])
+    rng = np.random.default_rng(21)
+    extra = 7000
+    pts_big = np.concatenate([pts, rng.uniform(-6, 6, (extra, 3)).astype(np.float32)])
+    desc_big = np.concatenate([desc, rng.integers(0, 256, (extra, 32), dtype=np.uint8)])
+    perm = rng.permutation(len(pts_big))
+    pts_big, desc_big = pts_big[perm], np.ascontiguousarray(desc_big[perm])
+    runs = []
+    for dev in (1, 0):
+        trk = mvo_b200.Tracker(ctx, K, 480, 640, device_resident=dev)
+        trk.set_map(pts_big, desc_big)
+        trk.reset(np.eye(4))
+        out = []
+        for i in range(1, 8):
+            if i == 4:
+                trk.set_map(pts_big, desc_big)            # same content: exercises the re-upload with live frame buffer
+            T, r = trk.track(imgs[i])
+            out.append((T.copy(), (r.n_keypoints, r.n_candidates, r.n_matches, r.n_inliers, r.pnp_ok, r.ba_frames, r.ba_edges)))
+        runs.append(out)
+        trk.close()
+    for k, ((Ta, ia), (Tb, ib)) in enumerate(zip(*runs)):
+        assert ia == ib, (ia, ib)
+        assert ia[4] == 1 and ia[1] > 2001 and ia[5] == min(k, 5)      # the oldest buffered frame stays out of the window (vo.cpp:417-419)
+        assert np.abs(Ta - Tb).max() < 1e-8
+    ctx.set_params(max_keypoints=1500, ba_iterations=50)
