@@ -121,6 +121,24 @@ def nvml_index(local_rank):
     return local_rank
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this rank's threads (tracker main thread, its extraction worker) on the cores NVML reports as local to the
+    GPU: the step is a chain of small dependent launches, so launch latency across the socket boundary shows."""
+    if os.environ.get("MVO_BENCH_NO_PIN"):
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def build_sequence(seed):
     """16 distinct frames of a textured plane + ground-truth poses; visiting order is a ping-pong."""
     import mvo_synth
@@ -193,8 +211,10 @@ def run_gpu(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    pin_to_gpu_numa_node(nvml_index(local_rank))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -275,9 +275,17 @@ int check_image(mvo_ctx *ctx, const void *image, int rows, int cols, int channel
 int upload_image(mvo_ctx *ctx, const uint8_t *image, int rows, size_t stride, uint8_t **d_out) {
   const size_t bytes = (size_t)rows * stride;
   MVO_TRY(mvo_reserve(ctx, ctx->orb_in, bytes + 256));
-  MVO_TRY(mvo_reserve_pinned(ctx, ctx->orb_h, bytes + 256));
-  memcpy(ctx->orb_h.p, image, bytes);
-  MVO_CUDA(ctx, cudaMemcpyAsync(ctx->orb_in.p, ctx->orb_h.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // page-locked caller memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor) is copied from directly;
+  // pageable memory is staged through the context's pinned buffer first.  Either way the image has to stay valid
+  // until the extraction has been consumed (synchronous entry points: until they return).
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) {
+    cudaGetLastError();
+    MVO_TRY(mvo_reserve_pinned(ctx, ctx->orb_h, bytes + 256));
+    memcpy(ctx->orb_h.p, image, bytes);
+  }
+  MVO_CUDA(ctx, cudaMemcpyAsync(ctx->orb_in.p, pinned ? (const void *)image : ctx->orb_h.p, bytes, cudaMemcpyHostToDevice, ctx->stream));
   *d_out = (uint8_t *)ctx->orb_in.p;
   return MVO_OK;
 }

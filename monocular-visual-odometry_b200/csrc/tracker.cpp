@@ -47,6 +47,9 @@ struct ExtractJob {
   int channels = 0, on_device = 0;
   size_t stride = 0;
   bool want_host = false;
+  // methods 1/2: the matcher does not depend on the pose, so the worker runs it right after the extraction
+  bool prematch = false, matched = false;
+  int match_mode = 0, map_version = 0;
   int rc = MVO_OK, nk = 0;
   const mvo_keypoint *d_k = nullptr;
   const uint8_t *d_d = nullptr;
@@ -139,7 +142,8 @@ struct mvo_tracker {
   size_t dev_bytes = 0;
   int dev_nmap = -1, dev_cap = 0, dev_ring = 0;
   float *d_map_pts = nullptr;  uint8_t *d_map_desc = nullptr;
-  uint8_t *d_keysvis = nullptr;        // [keys nmap*2 u32][vis nmap u8] — one D2H after the match
+  uint8_t *d_keysvis[2] = {nullptr, nullptr};   // per extraction slot: [keys nmap*2 u32][vis nmap u8] — one D2H after the match
+  int map_version = 0;                 // bumped by set_map: keys matched ahead of time against an older map are redone
   float *d_cxy = nullptr, *d_kxy = nullptr;
   int32_t *d_pairs = nullptr, *d_edge_map = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
   float *d_edge_obs = nullptr;
@@ -173,6 +177,14 @@ void worker_main(mvo_tracker *t) {
     } else {
       rc = mvo_orb_extract_begin_dev(x, j->image, t->rows, t->cols, j->channels, j->stride, j->on_device);
       if (rc == MVO_OK) rc = mvo_orb_extract_end_dev(x, &nk, &j->d_k, &j->d_d);
+      j->matched = false;
+      if (rc == MVO_OK && j->prematch && nk > 0 && t->dev_nmap > 0 && !(j->match_mode == 1 && nk < 2)) {
+        // all map descriptors x this frame's descriptors on the extraction stream: off the tracking chain
+        rc = mvo_match_launch_masked(x, j->match_mode, t->d_map_desc, nullptr, t->dev_nmap, j->d_d, nullptr, nk, 0.f,
+                                     (uint32_t *)t->d_keysvis[slot], nullptr);
+        if (rc == MVO_OK && cudaStreamSynchronize(x->stream) != cudaSuccess) rc = MVO_ERR_CUDA;
+        j->matched = rc == MVO_OK;
+      }
     }
     j->rc = rc;
     j->nk = nk;
@@ -213,6 +225,8 @@ int dev_alloc(mvo_tracker *t) {
   const int nmap = (int)(t->map_pts.size() / 3), cap = ctx->prm.max_keypoints + 1, ring = t->prm.buffer_size;
   if (t->dev && nmap == t->dev_nmap && cap == t->dev_cap && ring == t->dev_ring) return MVO_OK;
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  // frames extracted (and matched) ahead of time hold pointers into the old allocation: let them finish first
+  for (unsigned k = t->n_consume; k != t->n_submit; ++k) wait_job(t, (int)(k & 1));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const bool keep_frames = t->dev && cap == t->dev_cap && ring == t->dev_ring;   // a map swap keeps the frame buffer
   const int nm1 = std::max(nmap, 1);
@@ -220,6 +234,7 @@ int dev_alloc(mvo_tracker *t) {
   const size_t o_pts = o;   o = al256(o + (size_t)nm1 * 12);
   const size_t o_desc = o;  o = al256(o + (size_t)nm1 * 32);
   const size_t o_kv = o;    o = al256(o + (size_t)nm1 * 9);
+  const size_t o_kv2 = o;   o = al256(o + (size_t)nm1 * 9);
   const size_t o_cxy = o;   o = al256(o + (size_t)nm1 * 8);
   const size_t o_kxy = o;   o = al256(o + (size_t)cap * 8);
   const size_t o_pairs = o; o = al256(o + (size_t)nm1 * 8);
@@ -241,7 +256,8 @@ int dev_alloc(mvo_tracker *t) {
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (t->dev) cudaFree(t->dev);
   t->dev = nd; t->dev_bytes = o; t->dev_nmap = nmap; t->dev_cap = cap; t->dev_ring = ring;
-  t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis = nd + o_kv;
+  ++t->map_version;                 // keys matched ahead of time lived in the old allocation
+  t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis[0] = nd + o_kv; t->d_keysvis[1] = nd + o_kv2;
   t->d_cxy = (float *)(nd + o_cxy); t->d_kxy = (float *)(nd + o_kxy); t->d_pairs = (int32_t *)(nd + o_pairs);
   t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs); t->d_cnt = (int32_t *)(nd + o_cnt);
   t->d_pose = (double *)(nd + o_pose); t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res);
@@ -372,6 +388,14 @@ static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels,
   j.image = image; j.channels = channels; j.stride = stride; j.on_device = image_on_device;
   j.want_host = !use_device_path(t);
   j.rc = MVO_OK; j.nk = 0; j.d_k = nullptr; j.d_d = nullptr;
+  j.prematch = false; j.matched = false;
+  static const bool no_prematch = getenv("MVO_TRACK_NO_PREMATCH") != nullptr;      // A/B hook
+  if (!j.want_host && t->prm.match_method != 3 && !no_prematch) {
+    MVO_TRY(dev_alloc(t));                          // the worker needs the device copy of the map
+    j.prematch = true;
+    j.match_mode = t->prm.match_method == 1 ? 0 : 1;
+    j.map_version = t->map_version;
+  }
   {
     std::lock_guard<std::mutex> lk(t->mu);
     j.state.store(1, std::memory_order_release);
@@ -390,7 +414,7 @@ static void finish_frame(mvo_tracker *t, bool pnp_ok, double *T_w_c_out) {
   memcpy(T_w_c_out, t->frames.back().T_w_c, 16 * sizeof(double));
 }
 
-static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res);
+static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res);
 static int track_host_arrays(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res);
 
 extern "C" {
@@ -473,6 +497,7 @@ int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc,
   t->map_pts.assign(pts3d, pts3d + (size_t)n * 3);
   t->map_desc.assign(desc, desc + (size_t)n * 32);
   t->dev_nmap = -1;                 // the device copy is refreshed by the next tracked frame
+  ++t->map_version;
   return MVO_OK;
 }
 
@@ -540,7 +565,7 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
   ++t->n_consume;
   int rc = job.rc;
   if (rc != MVO_OK) rc = mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(t->xctx[slot]));
-  else rc = dev_path ? track_device(t, job, T_w_c_out, res) : track_host_arrays(t, job, T_w_c_out, res);
+  else rc = dev_path ? track_device(t, job, slot, T_w_c_out, res) : track_host_arrays(t, job, T_w_c_out, res);
   job.state.store(0, std::memory_order_release);
   return rc;
 }
@@ -554,7 +579,7 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
 //   int32 [0] BA skip flag   [8..10] model found, pnp_ok, inliers   [16..33] BA graph: frames, edges, slot of frame f
 //         [40..48] match filter: pairs, candidates, status, -, phase cycle counters
 //   +256: world->camera pose of the frame before BA (12 doubles)      +512: BA statistics (16 doubles)
-static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res) {
+static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res) {
   mvo_ctx *ctx = t->ctx;
   mvo_track_result r;
   memset(&r, 0, sizeof r);
@@ -578,8 +603,10 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   memcpy(cur.T_w_c, t->T_ref, sizeof cur.T_w_c);
   const int total = (int)t->frames.size();
 
-  uint32_t *d_keys = (uint32_t *)t->d_keysvis;
-  uint8_t *d_vis = t->d_keysvis + (size_t)std::max(nmap, 1) * 8;
+  uint8_t *d_keysvis = t->d_keysvis[slot];
+  uint32_t *d_keys = (uint32_t *)d_keysvis;
+  uint8_t *d_vis = d_keysvis + (size_t)std::max(nmap, 1) * 8;
+  const bool prematched = job.matched && job.map_version == t->map_version && job.match_mode == (method == 1 ? 0 : 1) && method != 3;
   int32_t *d_finfo = t->d_flags + 40, *d_res_i = t->d_flags + 8, *d_out_info = t->d_flags + 16;
   uint8_t *h_out = t->h_pin + al256((size_t)std::max(nmap, 1) * 9) + al256((size_t)std::max(nmap, 1) * 8 + 64);
   const int32_t *h_flags = (const int32_t *)h_out;
@@ -595,7 +622,9 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
   const bool project_in_filter = method != 3 && !force_host_filter && t->fused_holdoff == 0;
   if (nmap > 0) {
     if (!project_in_filter) rc = mvo_track_project_map(ctx, t->d_map_pts, nmap, Tcw, t->K, t->rows, t->cols, d_vis, t->d_cxy);
-    if (rc == MVO_OK && can_match) {
+    if (rc == MVO_OK && can_match && prematched) {
+      // keys of every map point are already there (unmasked: the filter / host filter ignores points outside the view)
+    } else if (rc == MVO_OK && can_match) {
       if (method == 3) rc = mvo_track_kpt_xy(ctx, job.d_k, nk, t->d_kxy);
       if (rc == MVO_OK)
         rc = mvo_match_launch_masked(ctx, method == 1 ? 0 : (method == 2 ? 1 : 2), t->d_map_desc, t->d_cxy, nmap, job.d_d, t->d_kxy, nk,
@@ -665,7 +694,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_
     const uint32_t *h_keys = (const uint32_t *)t->h_pin;
     const uint8_t *h_vis = t->h_pin + (size_t)std::max(nmap, 1) * 8;
     if (nmap > 0) {
-      MVO_CUDA(ctx, cudaMemcpyAsync(t->h_pin, t->d_keysvis, (size_t)nmap * 9, cudaMemcpyDeviceToHost, ctx->stream));
+      MVO_CUDA(ctx, cudaMemcpyAsync(t->h_pin, d_keysvis, (size_t)nmap * 9, cudaMemcpyDeviceToHost, ctx->stream));
       MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     std::vector<MatchPair> &pairs = t->pairs;
