@@ -214,7 +214,7 @@ def run_gpu(args, rank, world, local_rank):
     pin_to_gpu_numa_node(nvml_index(local_rank))
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner off stdout: one JSON line there
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
