@@ -215,7 +215,12 @@ void drain_jobs(mvo_tracker *t) {
   }
 }
 
-bool use_device_path(const mvo_tracker *t) { return t->prm.device_resident && t->prm.ba_fix_points; }
+// The device-resident path covers the shipped configuration (fixed map points) as long as the BA graph fits the
+// shared-memory-cached pose kernel: window x (max_keypoints + 1) observations <= 4 per thread of the 8 x 512 cluster.
+bool use_device_path(const mvo_tracker *t) {
+  const long worst_edges = (long)std::min(t->prm.ba_window, t->prm.buffer_size) * (t->ctx->prm.max_keypoints + 1);
+  return t->prm.device_resident && t->prm.ba_fix_points && worst_edges + 64 <= 4L * 8 * 512;
+}
 
 size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -669,6 +674,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
       int e_upper = 0;
       const int nba = std::min(t->prm.ba_window, total - 1);
       for (int b = total - 1; b >= total - nba; --b) {
+        if (t->frames[b].slot < 0) continue;         // tracked through the host-array path (parameters changed mid-sequence)
         st.slot[st.nslots++] = t->frames[b].slot;
         e_upper += (b == total - 1) ? n : t->frames[b].n_links;
       }
