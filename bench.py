@@ -164,6 +164,27 @@ def map_order(n, seed=20240923):
     return np.random.default_rng(seed).permutation(n)
 
 
+# ------------------------------------------------------------------------- multi-rank plumbing
+def sequence_seed(rank):
+    """Replicas only: rank r tracks its own independent synthetic sequence, seed = r."""
+    return int(rank)
+
+
+def reduce_max_ms(ms, dist, device):
+    """Per-rank elapsed milliseconds -> the slowest rank's (the time the whole job took)."""
+    if dist is None:
+        return float(ms)
+    import torch
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_fps(world, steps, ms):
+    """Aggregate throughput: every rank tracked `steps` frames of its own sequence in `ms` (max over ranks)."""
+    return world * steps / (ms / 1e3)
+
+
 # ------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's CPU path (cv2 + restated g2o) on the host cores; rank 0 only."""
@@ -223,7 +244,7 @@ def run_gpu(args, rank, world, local_rank):
     ctx.set_stream(stream.cuda_stream)
     K = mvo_synth.K_DEFAULT
 
-    imgs, T_true, order = build_sequence(rank)          # one independent sequence per rank / GPU
+    imgs, T_true, order = build_sequence(sequence_seed(rank))          # one independent sequence per rank / GPU
     kp0, desc0 = ctx.orb_extract(imgs[0])
     perm = map_order(len(kp0))
     map_pts = map_from_first_frame(kp0)[perm]
@@ -273,12 +294,7 @@ def run_gpu(args, rank, world, local_rank):
         last = run_steps(args_of, n, first)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, last
+        return reduce_max_ms(e0.elapsed_time(e1), dist, "cuda"), last
 
     # warm-up (>= 3), then a calibration pass with every kernel class timed to find the dominant one
     warm = max(args.warmup, 3)
@@ -363,8 +379,8 @@ def run_gpu(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = _peaks()
-        fps = world * args.steps / (ms / 1e3)
-        fps_e2e = world * args.steps / (ms_e2e / 1e3)
+        fps = whole_job_fps(world, args.steps, ms)
+        fps_e2e = whole_job_fps(world, args.steps, ms_e2e)
         ab = ALGO_BYTES.get(dominant)
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
