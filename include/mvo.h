@@ -283,10 +283,12 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref);
  * image_on_device != 0.  T_w_c_out receives the frame's pose after PnP (+ BA). */
 int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t stride,
                       int image_on_device, double *T_w_c_out, mvo_track_result *res);
-/* Optional look-ahead for recorded sequences: enqueue the ORB extraction of a FUTURE frame on a second stream so
- * that it overlaps the tracking of the current one (at most two frames in flight).  Frames must then be
- * passed to mvo_tracker_track in the same order, with the same image pointer.  The result is identical to
- * tracking without prefetch. */
+/* Optional look-ahead: hand a FUTURE frame to the tracker's extraction worker (own host thread, own stream) so that
+ * its upload, ORB extraction and — for match methods 1/2, which do not depend on the pose — its descriptor matching
+ * against the map overlap the tracking of the current frame.  At most two frames in flight.  Frames must then be
+ * passed to mvo_tracker_track in the same order, with the same image pointer, and the image memory must stay valid
+ * and unchanged until that mvo_tracker_track call returns (page-locked host images are copied from directly).  The
+ * result is identical to tracking without prefetch. */
 int mvo_tracker_prefetch(mvo_tracker *t, const uint8_t *image, int channels, size_t stride,
                          int image_on_device);
 /* Pose of the k-th newest buffered frame (k = 0 is the last tracked one) after BA updates. */
