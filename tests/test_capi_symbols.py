@@ -84,3 +84,16 @@ def test_dedup_proxy_matches_dmatch_sort(built):
             assert lib.mvo_test_dedup_pairs(train.ctypes.data, tag.ctypes.data, C.byref(cnt)) == 0
             assert cnt.value == len(ref)
             assert np.array_equal(train[: cnt.value], ref["train_idx"]) and np.array_equal(tag[: cnt.value], ref["query_idx"])
+
+
+def test_partition_restatement_equals_libstdcxx(tmp_path):
+    """The formula k_match_filter uses for one introsort step against libstdc++'s own __unguarded_partition_pivot
+    (tests/cpp/introsort_partition_check.cpp): identical arrays and cuts on 4000 random / adversarial sequences."""
+    import subprocess
+    exe = tmp_path / "introsort_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", str(ROOT / "tests" / "cpp" / "introsort_partition_check.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert "mismatches 0" in r.stdout
+    # organ-pipe inputs do leave the quicksort phase (heapsort in libstdc++): the case the kernel hands back to the host
+    assert int(r.stdout.split("beyond_depth_limit")[1]) > 0
