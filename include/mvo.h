@@ -93,6 +93,9 @@ typedef struct mvo_params {
                                  points) stops as soon as a trial step is below this bound — at convergence g2o
                                  spends up to 10 rejected trials on steps of ~1e-10 that it then restores; the
                                  poses agree with the full run to within the bound (tests/test_ba_gpu.py) */
+  /* two-view geometry — src/geometry/epipolar_geometry.cpp:17-57 */
+  int32_t epi_hypotheses;     /* batched essential-matrix hypotheses (reference: adaptive RANSAC, prob 0.999); default 4096 */
+  int32_t pad_;
 } mvo_params;
 
 typedef struct mvo_ctx mvo_ctx;
@@ -306,6 +309,23 @@ int mvo_timing_read(mvo_ctx *ctx, double *ms, uint64_t *counts);
 int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask);
 int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts);
 uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t);
+
+/* ---- two-view geometry (first part) -------------------------------------------
+ * geometry::estiMotionByEssential (src/geometry/epipolar_geometry.cpp:17-57): cv::findEssentialMat(pts1, pts2,
+ * focal = (K00+K11)/2, pp = (K02, K12), RANSAC, prob, threshold) + E /= E(2,2) + cv::recoverPose + t /= |t|.
+ * pts1/pts2: n x 2 float pixels.  Outputs: E (3x3 row-major, E[8] = 1), R (3x3), t (unit 3-vector) with
+ * x2 ~ R x1 + t as recoverPose returns them, inliers = indices with mask == 1 after findEssentialMat (ascending;
+ * *n_inliers in = capacity, out = count).  `threshold` is config findEssentialMat_threshold (pixels); the
+ * reference's `prob` has no counterpart: mvo_params::epi_hypotheses minimal samples are always scored.
+ * MVO_ERR_DEGENERATE if n < 8 or no model reaches 8 inliers. */
+int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K,
+                                 double threshold, double *E, double *R, double *t, int32_t *inliers,
+                                 int *n_inliers);
+/* geometry::doTriangulation (epipolar_geometry.cpp:130-175): cv::triangulatePoints([I|0], [R|t], inlier points on
+ * the normalised plane) followed by the division by the fourth coordinate.  pts_np1/pts_np2: n x 2 float,
+ * inliers: n_inliers indices into them, pts3d: n_inliers x 3 float (in camera 1). */
+int mvo_do_triangulation(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, const double *R,
+                         const double *t, const int32_t *inliers, int n_inliers, float *pts3d);
 
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose

@@ -59,7 +59,7 @@ KTimer::~KTimer() {
 
 static const char *kKernelNames[KC_COUNT] = {"k_gray", "k_resize", "k_fast", "k_select", "k_blur", "k_describe",
                                               "k_harris_all", "match_kernel", "k_pnp_hypotheses", "k_pnp_score",
-                                              "k_pnp_finish", "k_ba", "k_track_glue"};
+                                              "k_pnp_finish", "k_ba", "k_track_glue", "k_epi"};
 
 extern "C" {
 
@@ -106,6 +106,7 @@ void mvo_default_params(mvo_params *p) {
   p->ba_huber_delta = 1.0;
   p->ba_fix_first_pose = 0;
   p->ba_step_tol = 0.0;
+  p->epi_hypotheses = 4096;
 }
 
 static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
@@ -118,6 +119,8 @@ static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "orb_fast_threshold outside [1,254]");
   if (p->pnp_hypotheses < 1 || p->pnp_hypotheses > 65535)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_hypotheses outside [1,65535]");
+  if (p->epi_hypotheses < 1 || p->epi_hypotheses > 65535)
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "epi_hypotheses outside [1,65535]");
   if (p->ba_iterations < 0 || p->pnp_refine_iters < 0)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "negative iteration count");
   return MVO_OK;

@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("max_pts_per_grid", C.c_int32), ("xiang_gao_ratio", C.c_double), ("lowe_ratio", C.c_double),
         ("pnp_hypotheses", C.c_int32), ("pnp_reproj_error", C.c_float), ("pnp_seed", C.c_uint64),
         ("pnp_refine_iters", C.c_int32), ("ba_iterations", C.c_int32), ("ba_huber_delta", C.c_double),
-        ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double),
+        ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double), ("epi_hypotheses", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -104,6 +104,8 @@ SIGNATURES = {
     "mvo_kernel_name": (C.c_char_p, [_i]),
     "mvo_timing_enable": (_i, [_vp, C.c_uint32]),
     "mvo_timing_read": (_i, [_vp, _vp, _vp]),
+    "mvo_esti_motion_by_essential": (_i, [_vp, _vp, _vp, _i, _vp, C.c_double, _vp, _vp, _vp, _vp, _pi]),
+    "mvo_do_triangulation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
     "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
     "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
@@ -301,6 +303,23 @@ class Context:
         rvec, tvec = _c(rvec, np.float64).copy().reshape(3), _c(tvec, np.float64).copy().reshape(3)
         self._chk(self.lib.mvo_pnp_refine(self.h, _ptr(p3), _ptr(p2), len(p3), _ptr(K), _ptr(rvec), _ptr(tvec)))
         return rvec, tvec
+
+    # ---- two-view geometry ---------------------------------------------------------------
+    def esti_motion_by_essential(self, pts1, pts2, K, threshold=1.0):
+        p1, p2, K = _c(pts1, np.float32), _c(pts2, np.float32), _c(K, np.float64)
+        E, R, t = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3)
+        inl = np.zeros(max(len(p1), 1), np.int32)
+        n = C.c_int(len(p1))
+        self._chk(self.lib.mvo_esti_motion_by_essential(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(K), float(threshold), _ptr(E), _ptr(R),
+                                                        _ptr(t), _ptr(inl), C.byref(n)))
+        return E, R, t, inl[: n.value].copy()
+
+    def do_triangulation(self, pts_np1, pts_np2, R, t, inliers):
+        p1, p2 = _c(pts_np1, np.float32), _c(pts_np2, np.float32)
+        R, t, inl = _c(R, np.float64), _c(t, np.float64).reshape(3), _c(inliers, np.int32)
+        out = np.zeros((len(inl), 3), np.float32)
+        self._chk(self.lib.mvo_do_triangulation(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(R), _ptr(t), _ptr(inl), len(inl), _ptr(out)))
+        return out
 
     # ---- BA ----------------------------------------------------------------------------
     def bundle_adjustment(self, poses_T_w_c, points, edge_frame, edge_point, obs, K, information=None,

@@ -1,0 +1,14 @@
+// Host build of csrc/epipolar_math.cuh (the same functions the CUDA kernels call) behind a C interface for ctypes,
+// so that the numerics of the two-view stage are checked against numpy / cv2 on the CPU-only test tier.
+#include "epipolar_math.cuh"
+
+extern "C" {
+int epi_essential_from_8(const double *xy1, const double *xy2, double *E) { return epi::essential_from_8(xy1, xy2, E) ? 1 : 0; }
+double epi_sampson(const double *E, double x1, double y1, double x2, double y2) { return epi::sampson_err(E, x1, y1, x2, y2); }
+void epi_decompose(const double *E, double *R1, double *R2, double *t) { epi::decompose_essential(E, R1, R2, t); }
+void epi_triangulate(const double *P1, const double *P2, double x1, double y1, double x2, double y2, double *X) {
+  epi::triangulate_dlt(P1, P2, x1, y1, x2, y2, X);
+}
+void epi_svd3(const double *M, double *U, double *s, double *V) { epi::svd3(M, U, s, V); }
+int epi_null_8x9(const double *M, double *x) { double T[72]; for (int i = 0; i < 72; ++i) T[i] = M[i]; return epi::null_vector_8x9(T, x) ? 1 : 0; }
+}

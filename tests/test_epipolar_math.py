@@ -1,0 +1,125 @@
+"""csrc/epipolar_math.cuh compiled for the host (tests/cpp/epipolar_math_host.cpp): the numerics behind the two-view
+kernels against numpy and, where the reference's arithmetic is an OpenCV routine, against cv2:
+cv::decomposeEssentialMat (recoverPose, reference src/geometry/epipolar_geometry.cpp:53) and cv::triangulatePoints (:154)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def epi(tmp_path_factory):
+    so = tmp_path_factory.mktemp("epi") / "libepi_host.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I",
+                    str(ROOT / "monocular-visual-odometry_b200" / "csrc"), str(ROOT / "tests" / "cpp" / "epipolar_math_host.cpp"),
+                    "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    lib.epi_sampson.restype = C.c_double
+    lib.epi_sampson.argtypes = [C.c_void_p] + [C.c_double] * 4
+    lib.epi_triangulate.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [C.c_void_p]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _rodrigues(r):
+    th = np.linalg.norm(r)
+    if th < 1e-12:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def _two_view(rng, n):
+    """Points in front of both cameras; x2 = R x1 + t (OpenCV's recoverPose convention)."""
+    R = _rodrigues(rng.normal(0, 0.15, 3))
+    t = rng.normal(0, 1, 3)
+    t /= np.linalg.norm(t)
+    X1 = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(3, 9, n)], 1)
+    X2 = X1 @ R.T + 0.4 * t
+    return R, t, X1, X2, X1[:, :2] / X1[:, 2:3], X2[:, :2] / X2[:, 2:3]
+
+
+def test_svd3_and_null_vector(epi):
+    rng = np.random.default_rng(0)
+    for k in range(200):
+        M = rng.normal(0, 1, (3, 3))
+        if k % 5 == 0:
+            M[:, 2] = M[:, 0] * 0.3 - M[:, 1]                 # rank 2, like an essential matrix estimate
+        U, s, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+        epi.epi_svd3(_p(M), _p(U), _p(s), _p(V))
+        assert np.allclose(U @ np.diag(s) @ V.T, M, atol=1e-10)
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-10) and np.allclose(V.T @ V, np.eye(3), atol=1e-10)
+        assert np.allclose(s, np.linalg.svd(M, compute_uv=False), atol=1e-7) and s[0] >= s[1] >= s[2] >= 0
+    for k in range(100):
+        A = rng.normal(0, 1, (8, 9))
+        x = np.zeros(9)
+        assert epi.epi_null_8x9(_p(A), _p(x)) == 1
+        assert abs(np.linalg.norm(x) - 1) < 1e-12 and np.abs(A @ x).max() < 1e-10
+    A = rng.normal(0, 1, (8, 9))
+    A[7] = A[0] + A[1]                                        # rank 7: two-dimensional null space -> rejected
+    assert epi.epi_null_8x9(_p(A), _p(np.zeros(9))) == 0
+
+
+def test_essential_from_8_and_sampson(epi):
+    rng = np.random.default_rng(1)
+    for k in range(100):
+        R, t, X1, X2, x1, x2 = _two_view(rng, 8)
+        E = np.zeros((3, 3))
+        assert epi.epi_essential_from_8(_p(np.ascontiguousarray(x1)), _p(np.ascontiguousarray(x2)), _p(E)) == 1
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        Et = tx @ R
+        Et /= np.linalg.norm(Et)
+        En = E / np.linalg.norm(E)
+        assert min(np.abs(En - Et).max(), np.abs(En + Et).max()) < 1e-7, k
+        assert np.allclose(np.linalg.svd(E, compute_uv=False), [1, 1, 0], atol=1e-9)
+        for i in range(8):
+            assert epi.epi_sampson(_p(E), x1[i, 0], x1[i, 1], x2[i, 0], x2[i, 1]) < 1e-20
+        # a point moved off its epipolar line: Sampson distance ~ squared distance to the line (first order)
+        d = 1e-3
+        l = E @ np.array([x1[0, 0], x1[0, 1], 1.0])
+        nrm = l[:2] / np.linalg.norm(l[:2])
+        s = epi.epi_sampson(_p(E), x1[0, 0], x1[0, 1], x2[0, 0] + d * nrm[0], x2[0, 1] + d * nrm[1])
+        lt = E.T @ np.array([x2[0, 0], x2[0, 1], 1.0])
+        expect = (d * np.linalg.norm(l[:2])) ** 2 / (l[0] ** 2 + l[1] ** 2 + lt[0] ** 2 + lt[1] ** 2)
+        assert abs(s - expect) < 0.05 * expect
+    # degenerate sample: the same point eight times
+    x = np.tile([[0.1, 0.2]], (8, 1))
+    assert epi.epi_essential_from_8(_p(x), _p(x.copy()), _p(np.zeros((3, 3)))) == 0
+
+
+def test_decompose_and_triangulate_vs_cv2(epi):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    for k in range(50):
+        R, t, X1, X2, x1, x2 = _two_view(rng, 40)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        E = tx @ R
+        R1, R2, tt = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3)
+        epi.epi_decompose(_p(np.ascontiguousarray(E)), _p(R1), _p(R2), _p(tt))
+        c1, c2, ct = cv2.decomposeEssentialMat(E)
+        for Rm in (R1, R2):
+            assert abs(np.linalg.det(Rm) - 1) < 1e-9 and np.allclose(Rm @ Rm.T, np.eye(3), atol=1e-9)
+        # the same two rotations as OpenCV (in either order) and the same translation up to sign; the truth among them
+        assert min(max(np.abs(R1 - c1).max(), np.abs(R2 - c2).max()), max(np.abs(R1 - c2).max(), np.abs(R2 - c1).max())) < 1e-8
+        assert min(np.abs(tt - ct.ravel()).max(), np.abs(tt + ct.ravel()).max()) < 1e-8
+        assert min(np.abs(R1 - R).max(), np.abs(R2 - R).max()) < 1e-8 and min(np.abs(tt - t).max(), np.abs(tt + t).max()) < 1e-8
+        # cv::triangulatePoints with the reference's projection matrices [I|0], [R|t] (epipolar_geometry.cpp:146-154)
+        P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+        P2 = np.hstack([R, 0.4 * t[:, None]])
+        noise = rng.normal(0, 1e-3, x2.shape)
+        ref = cv2.triangulatePoints(P1.astype(np.float32), P2.astype(np.float32), x1.T.astype(np.float32), (x2 + noise).T.astype(np.float32))
+        ref = (ref[:3] / ref[3]).T
+        for i in range(len(x1)):
+            X = np.zeros(4)
+            a, b = x1[i].astype(np.float32), (x2[i] + noise[i]).astype(np.float32)
+            epi.epi_triangulate(_p(P1.astype(np.float32).astype(np.float64)), _p(P2.astype(np.float32).astype(np.float64)),
+                                float(a[0]), float(a[1]), float(b[0]), float(b[1]), _p(X))
+            assert np.abs(X[:3] / X[3] - ref[i]).max() < 2e-4 * max(1.0, np.abs(ref[i]).max()), (k, i)
