@@ -14,7 +14,7 @@ class Config {
         {"number_of_keypoints_to_extract", 8000}, {"max_number_of_keypoints", 1500}, {"scale_factor", 1.2},
         {"level_pyramid", 4}, {"score_threshold", 20}, {"kpts_uniform_selection_grid_size", 16},
         {"kpts_uniform_selection_max_pts_per_grid", 8}, {"xiang_gao_method_match_ratio", 2},
-        {"lowe_method_dist_ratio", 0.8}};
+        {"lowe_method_dist_ratio", 0.8}, {"findEssentialMat_prob", 0.999}, {"findEssentialMat_threshold", 1.0}};
     return t;
   }
   template <typename T> static T get(const std::string &key) {
