@@ -159,7 +159,8 @@ int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_x
 int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const int32_t *d_n, const float *d_map_pts,
                            const mvo_keypoint *d_kpts, float *d_p3, float *d_p2);
 int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g);
-// thresholds of matchFeatures + removeDuplicatedMatches on the device; d_info: [0] pairs, [1] candidates, [2] status
+// thresholds of matchFeatures + removeDuplicatedMatches on the device; d_info (>= 24 ints): [0] pairs, [1] candidates,
+// [2] status, [4..22] phase / per-level cycle counters (MVO_TRACK_DEBUG)
 struct MvoTrackFilter {
   const uint32_t *d_keys;        // matcher keys of ALL map points
   uint8_t *d_vis;                // in-view flags: read, or written when Tcw12 != nullptr (projection done by the filter)

@@ -364,7 +364,7 @@ extern "C" int mvo_test_match_filter_dev(mvo_ctx *ctx, const uint32_t *keys, con
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   const int W = method == 2 ? 2 : 1;
   uint8_t *d = nullptr;
-  const size_t o_vis = (size_t)nmap * 8, o_pairs = al256(o_vis + nmap), o_info = o_pairs + (size_t)nmap * 8, tot = o_info + 64;
+  const size_t o_vis = (size_t)nmap * 8, o_pairs = al256(o_vis + nmap), o_info = al256(o_pairs + (size_t)nmap * 8), tot = o_info + 256;   // info: 3 results + phase counters
   MVO_CUDA(ctx, cudaMalloc(&d, tot));
   cudaMemcpyAsync(d, keys, (size_t)nmap * W * 4, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(d + o_vis, vis, nmap, cudaMemcpyHostToDevice, ctx->stream);
