@@ -222,4 +222,109 @@ EPI_HD_CALL void triangulate_dlt(const double *P1, const double *P2, double x1, 
   for (int i = 0; i < 4; ++i) X[i] = V[i * 4 + m];
 }
 
+// ---- homography (estiMotionByHomography, reference src/geometry/epipolar_geometry.cpp:90-128) ----------------------
+
+// H (x2 ~ H x1, row-major 3x3, unit Frobenius norm) from 4 correspondences; any coordinate units.  False for
+// degenerate samples (three collinear points make the 8x9 system rank deficient).
+EPI_HD_CALL bool homography_from_4(const double *xy1, const double *xy2, double *H) {
+  double M[72];
+  for (int k = 0; k < 4; ++k) {
+    const double x1 = xy1[2 * k], y1 = xy1[2 * k + 1], x2 = xy2[2 * k], y2 = xy2[2 * k + 1];
+    double *r = M + 18 * k;
+    r[0] = -x1; r[1] = -y1; r[2] = -1; r[3] = 0; r[4] = 0; r[5] = 0; r[6] = x2 * x1; r[7] = x2 * y1; r[8] = x2;
+    r[9] = 0; r[10] = 0; r[11] = 0; r[12] = -x1; r[13] = -y1; r[14] = -1; r[15] = y2 * x1; r[16] = y2 * y1; r[17] = y2;
+  }
+  if (!null_vector_8x9(M, H)) return false;
+  for (int i = 0; i < 9; ++i)
+    if (!finite_d(H[i])) return false;
+  return true;
+}
+
+// squared forward transfer error |x2 - H x1|^2 (the error cv::findHomography's RANSAC thresholds), +inf at w = 0
+EPI_HD double homography_transfer_err(const double *H, double x1, double y1, double x2, double y2) {
+  const double w = H[6] * x1 + H[7] * y1 + H[8];
+  if (!(fabs(w) > 1e-300)) return 1e300;
+  const double du = (H[0] * x1 + H[1] * y1 + H[2]) / w - x2, dv = (H[3] * x1 + H[4] * y1 + H[5]) / w - y2;
+  return du * du + dv * dv;
+}
+
+EPI_HD void mat3_mul(const double *A, const double *B, double *C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+
+// cv::decomposeHomographyMat on a calibrated homography Hn = K^-1 H K (any scale, any sign): Hn ~ R + t n^T with t in
+// units of the plane distance.  Up to 4 solutions, in pairs (R, t, n), (R, -t, -n); one solution (R = Hn, t = n = 0)
+// for a pure rotation.  Method: Ma, Soatto, Kosecka, Sastry, "An Invitation to 3-D Vision", section 5.3.3 (the
+// eigenvectors of Hn^T Hn); OpenCV's analytical method (Malis & Vargas) yields the same solution set.
+// Rs: 4 x 9, ts: 4 x 3, ns: 4 x 3.  Returns the number of solutions (0 for a singular input).
+EPI_HD_CALL int decompose_homography(const double *Hin, double *Rs, double *ts, double *ns) {
+  double H[9], U[9], sv[3], V[9];
+  svd3(Hin, U, sv, V);
+  if (!(sv[1] > 0) || !finite_d(sv[1])) return 0;
+  const double sgn = det3(Hin) < 0 ? -1.0 : 1.0;                // the camera stays on one side of the plane: det(R + t n^T) > 0
+  for (int i = 0; i < 9; ++i) H[i] = sgn * Hin[i] / sv[1];     // middle singular value -> 1
+  const double s1 = sv[0] / sv[1], s3 = sv[2] / sv[1];
+  const double a2 = 1 - s3 * s3, b2 = s1 * s1 - 1;             // both >= 0
+  if (a2 + b2 < 1e-12) {                                         // H^T H = I: pure rotation
+    for (int i = 0; i < 9; ++i) Rs[i] = H[i];
+    for (int i = 0; i < 3; ++i) { ts[i] = 0; ns[i] = 0; }
+    return 1;
+  }
+  double v1[3], v2[3], v3[3];
+  for (int i = 0; i < 3; ++i) { v1[i] = V[i * 3]; v2[i] = V[i * 3 + 1]; v3[i] = V[i * 3 + 2]; }
+  if (det3(V) < 0) for (int i = 0; i < 3; ++i) v3[i] = -v3[i];
+  const double a = sqrt(a2 > 0 ? a2 : 0.0), b = sqrt(b2 > 0 ? b2 : 0.0), c = 1.0 / sqrt(a2 + b2);
+  for (int k = 0; k < 2; ++k) {
+    const double sg = k == 0 ? 1.0 : -1.0;
+    double u[3], Nn[3], Hv2[3], Hu[3], HN[3], Um[9], Wm[9], R[9];
+    for (int i = 0; i < 3; ++i) u[i] = (a * v1[i] + sg * b * v3[i]) * c;
+    cross3(v2, u, Nn);
+    for (int i = 0; i < 3; ++i) {
+      Hv2[i] = H[i * 3] * v2[0] + H[i * 3 + 1] * v2[1] + H[i * 3 + 2] * v2[2];
+      Hu[i] = H[i * 3] * u[0] + H[i * 3 + 1] * u[1] + H[i * 3 + 2] * u[2];
+    }
+    cross3(Hv2, Hu, HN);
+    for (int i = 0; i < 3; ++i) {                               // U = [v2, u, v2 x u], W = [H v2, H u, H v2 x H u] (columns)
+      Um[i * 3] = v2[i]; Um[i * 3 + 1] = u[i]; Um[i * 3 + 2] = Nn[i];
+      Wm[i * 3] = Hv2[i]; Wm[i * 3 + 1] = Hu[i]; Wm[i * 3 + 2] = HN[i];
+    }
+    for (int i = 0; i < 3; ++i)                                  // R = W U^T
+      for (int j = 0; j < 3; ++j) R[i * 3 + j] = Wm[i * 3] * Um[j * 3] + Wm[i * 3 + 1] * Um[j * 3 + 1] + Wm[i * 3 + 2] * Um[j * 3 + 2];
+    double T[3];
+    for (int i = 0; i < 3; ++i)
+      T[i] = (H[i * 3] - R[i * 3]) * Nn[0] + (H[i * 3 + 1] - R[i * 3 + 1]) * Nn[1] + (H[i * 3 + 2] - R[i * 3 + 2]) * Nn[2];
+    for (int pm = 0; pm < 2; ++pm) {
+      const int o = 2 * k + pm;
+      const double f = pm == 0 ? 1.0 : -1.0;
+      for (int i = 0; i < 9; ++i) Rs[o * 9 + i] = R[i];
+      for (int i = 0; i < 3; ++i) { ts[o * 3 + i] = f * T[i]; ns[o * 3 + i] = f * Nn[i]; }
+    }
+  }
+  return 4;
+}
+
+// cv::filterHomographyDecompByVisibleRefpoints (removeWrongRtOfHomography, epipolar_geometry.cpp:59-88): a solution
+// survives when every reference point lies in front of the plane normal in both views.
+// np1 / np2: n x 2 points on the normalised image planes; keep[s] = 1 for the surviving solutions.  Host and device.
+EPI_HD int filter_homography_solutions(const double *Rs, const double *ns, int n_sol, const float *np1, const float *np2,
+                                       const int *inliers, int n_in, int *keep) {
+  int kept = 0;
+  for (int s = 0; s < n_sol; ++s) {
+    const double *R = Rs + 9 * s, *nv = ns + 3 * s;
+    const double m0 = R[0] * nv[0] + R[1] * nv[1] + R[2] * nv[2], m1 = R[3] * nv[0] + R[4] * nv[1] + R[5] * nv[2],
+                 m2 = R[6] * nv[0] + R[7] * nv[1] + R[8] * nv[2];
+    bool ok = true;
+    for (int j = 0; j < n_in && ok; ++j) {
+      const int i = inliers ? inliers[j] : j;
+      const double d1 = nv[0] * np1[2 * i] + nv[1] * np1[2 * i + 1] + nv[2];
+      const double d2 = m0 * np2[2 * i] + m1 * np2[2 * i + 1] + m2;
+      ok = d1 > 0 && d2 > 0;
+    }
+    keep[s] = ok ? 1 : 0;
+    kept += ok;
+  }
+  return kept;
+}
+
 }  // namespace epi

@@ -10,5 +10,11 @@ void epi_triangulate(const double *P1, const double *P2, double x1, double y1, d
   epi::triangulate_dlt(P1, P2, x1, y1, x2, y2, X);
 }
 void epi_svd3(const double *M, double *U, double *s, double *V) { epi::svd3(M, U, s, V); }
+int epi_homography_from_4(const double *xy1, const double *xy2, double *H) { return epi::homography_from_4(xy1, xy2, H) ? 1 : 0; }
+double epi_transfer_err(const double *H, double x1, double y1, double x2, double y2) { return epi::homography_transfer_err(H, x1, y1, x2, y2); }
+int epi_decompose_homography(const double *H, double *Rs, double *ts, double *ns) { return epi::decompose_homography(H, Rs, ts, ns); }
+int epi_filter_homography(const double *Rs, const double *ns, int n_sol, const float *np1, const float *np2, const int *inl, int n_in, int *keep) {
+  return epi::filter_homography_solutions(Rs, ns, n_sol, np1, np2, inl, n_in, keep);
+}
 int epi_null_8x9(const double *M, double *x) { double T[72]; for (int i = 0; i < 72; ++i) T[i] = M[i]; return epi::null_vector_8x9(T, x) ? 1 : 0; }
 }

@@ -123,3 +123,68 @@ def test_decompose_and_triangulate_vs_cv2(epi):
             epi.epi_triangulate(_p(P1.astype(np.float32).astype(np.float64)), _p(P2.astype(np.float32).astype(np.float64)),
                                 float(a[0]), float(a[1]), float(b[0]), float(b[1]), _p(X))
             assert np.abs(X[:3] / X[3] - ref[i]).max() < 2e-4 * max(1.0, np.abs(ref[i]).max()), (k, i)
+
+
+def _plane_scene(rng, n=60):
+    """Points on a plane n.X = d seen from two cameras: x2 ~ (R + t n^T / d) x1."""
+    R = _rodrigues(rng.normal(0, 0.08, 3))
+    t = rng.normal(0, 0.15, 3)
+    nrm = np.array([rng.normal(0, 0.2), rng.normal(0, 0.2), 1.0])
+    nrm /= np.linalg.norm(nrm)
+    d = rng.uniform(3, 6)
+    P = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), np.zeros(n)], 1)
+    P[:, 2] = (d - P[:, :2] @ nrm[:2]) / nrm[2]
+    P2 = P @ R.T + t
+    return R, t / d, nrm, P[:, :2] / P[:, 2:3], P2[:, :2] / P2[:, 2:3]
+
+
+def test_homography_from_4_and_transfer_error(epi):
+    epi.epi_transfer_err.restype = C.c_double
+    epi.epi_transfer_err.argtypes = [C.c_void_p] + [C.c_double] * 4
+    rng = np.random.default_rng(4)
+    for k in range(100):
+        R, td, nrm, x1, x2 = _plane_scene(rng, 12)
+        H = np.zeros((3, 3))
+        assert epi.epi_homography_from_4(_p(np.ascontiguousarray(x1[:4])), _p(np.ascontiguousarray(x2[:4])), _p(H)) == 1
+        Ht = R + np.outer(td, nrm)
+        Hn, Htn = H / np.linalg.norm(H), Ht / np.linalg.norm(Ht)
+        assert min(np.abs(Hn - Htn).max(), np.abs(Hn + Htn).max()) < 1e-8
+        for i in range(12):                                   # the other points of the plane obey the same homography
+            assert epi.epi_transfer_err(_p(H), x1[i, 0], x1[i, 1], x2[i, 0], x2[i, 1]) < 1e-18
+        assert abs(epi.epi_transfer_err(_p(H), x1[5, 0], x1[5, 1], x2[5, 0] + 3e-3, x2[5, 1] - 4e-3) - 25e-6) < 1e-9
+    x = np.array([[0, 0], [1, 1], [2, 2], [0.5, 0.1]], float)  # three collinear points
+    assert epi.epi_homography_from_4(_p(x), _p(x.copy()), _p(np.zeros((3, 3)))) == 0
+
+
+def test_decompose_homography_and_filter_vs_cv2(epi):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    K = np.array([[615.0, 0, 320], [0, 615, 240], [0, 0, 1]])
+    for k in range(60):
+        R, td, nrm, x1, x2 = _plane_scene(rng, 40)
+        Hn = (R + np.outer(td, nrm)) * rng.choice([1.0, -3.7, 0.2])         # scale and sign are irrelevant
+        Rs, ts, ns = np.zeros((4, 9)), np.zeros((4, 3)), np.zeros((4, 3))
+        m = epi.epi_decompose_homography(_p(np.ascontiguousarray(Hn)), _p(Rs), _p(ts), _p(ns))
+        num, cR, ct, cn = cv2.decomposeHomographyMat(K @ Hn @ np.linalg.inv(K), K)
+        assert m == num == 4
+        used = set()
+        for i in range(4):                                                    # same solution SET as OpenCV
+            assert abs(np.linalg.det(Rs[i].reshape(3, 3)) - 1) < 1e-8
+            best = min(range(4), key=lambda j: np.abs(Rs[i].reshape(3, 3) - cR[j]).max() + np.abs(ts[i] - ct[j].ravel()).max() + np.abs(ns[i] - cn[j].ravel()).max())
+            err = max(np.abs(Rs[i].reshape(3, 3) - cR[best]).max(), np.abs(ts[i] - ct[best].ravel()).max(), np.abs(ns[i] - cn[best].ravel()).max())
+            assert err < 1e-6, (k, i, err)
+            used.add(best)
+        assert used == {0, 1, 2, 3}
+        assert min(max(np.abs(Rs[i].reshape(3, 3) - R).max(), np.abs(ts[i] - td).max(), np.abs(ns[i] - nrm).max()) for i in range(4)) < 1e-8
+        # removeWrongRtOfHomography: the same surviving solutions as cv2.filterHomographyDecompByVisibleRefpoints
+        keep = np.zeros(4, np.int32)
+        a, b = np.ascontiguousarray(x1, np.float32), np.ascontiguousarray(x2, np.float32)
+        kept = epi.epi_filter_homography(_p(Rs), _p(ns), 4, _p(a), _p(b), None, len(a), _p(keep))
+        ref = cv2.filterHomographyDecompByVisibleRefpoints([r.reshape(3, 3) for r in Rs], [v.reshape(3, 1) for v in ns], a.reshape(-1, 1, 2), b.reshape(-1, 1, 2))
+        ref = set() if ref is None else set(ref.ravel().tolist())
+        assert set(np.nonzero(keep)[0].tolist()) == ref and kept == len(ref) and kept >= 1
+    # pure rotation: one solution, no translation
+    Rr = _rodrigues(np.array([0.02, -0.05, 0.01]))
+    Rs, ts, ns = np.zeros((4, 9)), np.zeros((4, 3)), np.zeros((4, 3))
+    assert epi.epi_decompose_homography(_p(np.ascontiguousarray(2.0 * Rr)), _p(Rs), _p(ts), _p(ns)) == 1
+    assert np.abs(Rs[0].reshape(3, 3) - Rr).max() < 1e-9 and np.abs(ts[0]).max() == 0
