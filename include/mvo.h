@@ -321,6 +321,21 @@ uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t);
 int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K,
                                  double threshold, double *E, double *R, double *t, int32_t *inliers,
                                  int *n_inliers);
+/* geometry::estiMotionByHomography (epipolar_geometry.cpp:90-128): cv::findHomography(pts1, pts2, RANSAC, threshold = 3)
+ * + H /= H(2,2) + inliers from its mask + cv::decomposeHomographyMat(H, K) + t /= |t|.  Outputs: H (3x3 pixel
+ * homography, H[8] = 1), up to 4 solutions Rs (4 x 9), ts (4 x 3, unit; zero for a pure rotation), normals (4 x 3) with
+ * K^-1 H K ~ R + t n^T — the solution SET of cv::decomposeHomographyMat, ordered (a, -a, b, -b) —, *n_solutions,
+ * inliers ascending (*n_inliers in = capacity, out = count).  MVO_ERR_DEGENERATE if n < 4 or no model reaches 4 inliers.
+ * NOT yet exercised on hardware by the round-1 GPU budget: tests/test_homography_gpu.py runs it in a child process. */
+int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K,
+                                  double threshold, double *H, double *Rs, double *ts, double *normals,
+                                  int *n_solutions, int32_t *inliers, int *n_inliers);
+/* geometry::removeWrongRtOfHomography (epipolar_geometry.cpp:59-88) = cv::filterHomographyDecompByVisibleRefpoints on
+ * the inlier points (normalised image planes): solutions that put a reference point behind the plane in either view
+ * are removed in place; *n_solutions in = count (<= 4), out = survivors.  Host only. */
+int mvo_remove_wrong_rt_of_homography(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n,
+                                      const int32_t *inliers, int n_inliers, double *Rs, double *ts,
+                                      double *normals, int *n_solutions);
 /* geometry::doTriangulation (epipolar_geometry.cpp:130-175): cv::triangulatePoints([I|0], [R|t], inlier points on
  * the normalised plane) followed by the division by the fourth coordinate.  pts_np1/pts_np2: n x 2 float,
  * inliers: n_inliers indices into them, pts3d: n_inliers x 3 float (in camera 1). */

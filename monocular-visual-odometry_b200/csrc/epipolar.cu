@@ -357,6 +357,230 @@ k_triangulate(const float *__restrict__ np1, const float *__restrict__ np2, cons
   out[3 * j] = x / w; out[3 * j + 1] = y / w; out[3 * j + 2] = z / w;
 }
 
+// ---------------------------------------------------------------------------------------------------- homography
+// estiMotionByHomography (reference src/geometry/epipolar_geometry.cpp:90-128): cv::findHomography(pts1, pts2, RANSAC,
+// 3.0, mask) + H /= H(2,2) + inliers from the mask + cv::decomposeHomographyMat(H, K) + t /= |t|.  Same batched design
+// as the essential-matrix path: H four-point hypotheses, forward transfer error consensus (the error OpenCV
+// thresholds), local optimisation of the best one by Gauss-Newton on the transfer error over its consensus set
+// (OpenCV refines its RANSAC result with LM on the same cost).  All three kernels work in isotropically scaled pixel
+// coordinates ((u - cx) / f, (v - cy) / f, f = mean focal length): errors scale by 1 / f, the conditioning of the
+// 4-point systems and of the normal equations does not depend on the image size.  The decomposition itself is a few
+// hundred flops and runs on the host (the same epipolar_math.cuh routine).
+struct HomoCam { double f, cx, cy; };
+
+__global__ void __launch_bounds__(128)
+k_homo_hypotheses(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, uint64_t seed, int H,
+                  double *__restrict__ Hs, int32_t *__restrict__ valid) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  int idx[4];
+  uint64_t ctr = 0;
+  for (int k = 0; k < 4; ++k)
+    for (int attempt = 0; attempt < 64; ++attempt) {
+      const uint64_t r = splitmix64e(seed ^ splitmix64e(((uint64_t)h << 20) ^ (0x5bd1e995ull + ctr++)));
+      const int cand = (int)(r % (uint64_t)n);
+      bool dup = false;
+      for (int q = 0; q < k; ++q) dup |= idx[q] == cand;
+      idx[k] = cand;
+      if (!dup) break;
+    }
+  double a[8], b[8];
+  const double inv = 1.0 / cam.f;
+  for (int k = 0; k < 4; ++k) {
+    a[2 * k] = ((double)p1[2 * idx[k]] - cam.cx) * inv; a[2 * k + 1] = ((double)p1[2 * idx[k] + 1] - cam.cy) * inv;
+    b[2 * k] = ((double)p2[2 * idx[k]] - cam.cx) * inv; b[2 * k + 1] = ((double)p2[2 * idx[k] + 1] - cam.cy) * inv;
+  }
+  double Hm[9];
+  const bool ok = epi::homography_from_4(a, b, Hm);
+  for (int q = 0; q < 9; ++q) Hs[(size_t)h * 9 + q] = ok ? Hm[q] : 0.0;
+  valid[h] = ok ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_homo_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
+             const double *__restrict__ Hs, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
+  extern __shared__ double s_pt[];         // [n][4] scaled coordinates x1 y1 x2 y2
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s_pt[4 * i] = ((double)p1[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 1] = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+    s_pt[4 * i + 2] = ((double)p2[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 3] = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int h = blockIdx.x * wpb + warp; h < H; h += gridDim.x * wpb) {
+    if (valid[h] <= 0) { if (lane == 0) counts[h] = -1; continue; }
+    double Hm[9];
+    for (int q = 0; q < 9; ++q) Hm[q] = Hs[(size_t)h * 9 + q];
+    int c = 0;
+    for (int i = lane; i < n; i += 32) c += epi::homography_transfer_err(Hm, s_pt[4 * i], s_pt[4 * i + 1], s_pt[4 * i + 2], s_pt[4 * i + 3]) <= thr2;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) counts[h] = c;
+  }
+}
+
+constexpr int HOMO_NV = 54;               // 45 entries of J^T J (upper triangle) + 9 of J^T r
+
+// out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
+// [3] consensus of the best minimal model, [4] consensus after the local optimisation
+__global__ void __launch_bounds__(EFIN_T)
+k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
+              const double *__restrict__ Hs, const int32_t *__restrict__ counts, double *__restrict__ out_d,
+              int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
+  __shared__ long long s_k[32];
+  __shared__ int s_best, s_cnt[32], s_stop;
+  __shared__ double s_H[9], s_H0[9], s_red[32][HOMO_NV], s_sum[HOMO_NV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long best = -1;
+  for (int h = tid; h < H; h += EFIN_T) {
+    const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
+  if (lane == 0) s_k[warp] = best;
+  __syncthreads();
+  if (tid == 0) {
+    long long b = -1;
+    for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
+    s_best = (int)(b >> 20) >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
+    out_i[3] = (int)(b >> 20);
+  }
+  __syncthreads();
+  if (s_best < 0) {
+    if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[4] = 0; }
+    return;
+  }
+  if (tid < 9) { const double v = Hs[(size_t)s_best * 9 + tid]; s_H[tid] = v; s_H0[tid] = v; }
+  __syncthreads();
+  const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+  // ---- local optimisation: Gauss-Newton on the transfer error, additive update of the 9 entries (the scale of H is a
+  // null direction of the normal equations: a small damping fixes the gauge, H is renormalised after every step) ----
+  for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
+    double Hsel[9];
+    for (int q = 0; q < 9; ++q) Hsel[q] = s_H[q];
+    for (int it = 0; it < EPI_GN_ITERS; ++it) {
+      double Hc[9];
+      for (int q = 0; q < 9; ++q) Hc[q] = s_H[q];
+      if (tid == 0) s_stop = 0;
+      double acc[HOMO_NV];
+#pragma unroll
+      for (int q = 0; q < HOMO_NV; ++q) acc[q] = 0;
+      for (int i = b0; i < e0; ++i) {
+        const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+        const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+        if (!(epi::homography_transfer_err(Hsel, x1, y1, x2, y2) <= thr2)) continue;
+        const double w = Hc[6] * x1 + Hc[7] * y1 + Hc[8];
+        if (!(fabs(w) > 1e-12)) continue;
+        const double iw = 1.0 / w, u = (Hc[0] * x1 + Hc[1] * y1 + Hc[2]) * iw, v = (Hc[3] * x1 + Hc[4] * y1 + Hc[5]) * iw;
+        const double ru = u - x2, rv = v - y2;
+        const double Ju[9] = {x1 * iw, y1 * iw, iw, 0, 0, 0, -u * x1 * iw, -u * y1 * iw, -u * iw};
+        const double Jv[9] = {0, 0, 0, x1 * iw, y1 * iw, iw, -v * x1 * iw, -v * y1 * iw, -v * iw};
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+#pragma unroll
+          for (int c = r; c < 9; ++c) acc[q++] += Ju[r] * Ju[c] + Jv[r] * Jv[c];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc[45 + r] += Ju[r] * ru + Jv[r] * rv;
+      }
+#pragma unroll
+      for (int q = 0; q < HOMO_NV; ++q) {
+        double vq = acc[q];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vq += __shfl_xor_sync(0xffffffffu, vq, d);
+        if (lane == 0) s_red[warp][q] = vq;
+      }
+      __syncthreads();
+      if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
+      __syncthreads();
+      if (tid == 0) {
+        double A[9][10];
+        int q = 0;
+        for (int r = 0; r < 9; ++r) for (int c = r; c < 9; ++c) { A[r][c] = s_sum[q]; A[c][r] = s_sum[q]; ++q; }
+        double mxd = 0;
+        for (int r = 0; r < 9; ++r) mxd = fmax(mxd, A[r][r]);
+        for (int r = 0; r < 9; ++r) { A[r][r] += 1e-9 * mxd + 1e-300; A[r][9] = -s_sum[45 + r]; }
+        bool ok = true;
+        for (int k = 0; k < 9 && ok; ++k) {
+          int pr = k;
+          for (int r = k + 1; r < 9; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
+          if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
+          if (pr != k) for (int c = 0; c < 10; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
+          for (int r = k + 1; r < 9; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 10; ++c) A[r][c] -= f * A[k][c]; }
+        }
+        double dx[9], mx = 0;
+        for (int r = 0; r < 9; ++r) dx[r] = 0;
+        if (ok) {
+          for (int r = 8; r >= 0; --r) { double vq = A[r][9]; for (int c = r + 1; c < 9; ++c) vq -= A[r][c] * dx[c]; dx[r] = vq / A[r][r]; }
+          for (int r = 0; r < 9; ++r) { if (!epi::finite_d(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
+        }
+        if (ok && mx < 0.5) {                         // H has unit Frobenius norm: half of that is not a refinement
+          double nrm = 0;
+          for (int r = 0; r < 9; ++r) { s_H[r] += dx[r]; nrm += s_H[r] * s_H[r]; }
+          nrm = sqrt(nrm);
+          for (int r = 0; r < 9; ++r) s_H[r] /= nrm;
+        }
+        if (!ok || mx < 1e-11 || mx >= 0.5) s_stop = 1;
+      }
+      __syncthreads();
+      if (s_stop) break;
+    }
+    __syncthreads();
+  }
+  // the local optimisation must not lose support: otherwise the minimal model stands
+  {
+    int c = 0;
+    for (int i = b0; i < e0; ++i) {
+      const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+      const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+      c += epi::homography_transfer_err(s_H, x1, y1, x2, y2) <= thr2;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += s_cnt[w];
+      out_i[4] = tot;
+      if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_H[q] = s_H0[q];
+    }
+    __syncthreads();
+  }
+  // ---- consensus set of the final model, ascending (the mask of findHomography, epipolar_geometry.cpp:108-116) ----
+  double Hf[9];
+  for (int q = 0; q < 9; ++q) Hf[q] = s_H[q];
+  int mine = 0;
+  for (int i = b0; i < e0; ++i) {
+    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+    mine += epi::homography_transfer_err(Hf, x1, y1, x2, y2) <= thr2;
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  __syncthreads();
+  if (lane == 31) s_cnt[warp] = incl;
+  __syncthreads();
+  int off = incl - mine, n_in = 0;
+  for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+  for (int i = b0; i < e0; ++i) {
+    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+    if (epi::homography_transfer_err(Hf, x1, y1, x2, y2) <= thr2) inl[off++] = i;
+  }
+  if (tid == 0) {
+    // back to pixel coordinates: x_scaled = S x_pix with S = [1/f 0 -cx/f; 0 1/f -cy/f; 0 0 1]  =>  H_pix = S^-1 H S
+    const double f = cam.f, cx = cam.cx, cy = cam.cy;
+    const double S[9] = {1 / f, 0, -cx / f, 0, 1 / f, -cy / f, 0, 0, 1}, Si[9] = {f, 0, cx, 0, f, cy, 0, 0, 1};
+    double T[9], Hp[9];
+    epi::mat3_mul(Hf, S, T);
+    epi::mat3_mul(Si, T, Hp);
+    for (int q = 0; q < 9; ++q) out_d[q] = Hp[q] / Hp[8];                       // H /= H(2,2) (:107)
+    out_i[0] = n_in; out_i[1] = s_best;
+  }
+}
+
 // device-side unit test of epipolar_math.cuh (test hook: tests compare with the host build of the same header)
 __global__ void k_epi_math_test(const double *__restrict__ in, double *__restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -481,6 +705,99 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   memcpy(E, h_out, 72); memcpy(R, h_out + 9, 72); memcpy(t, h_out + 18, 24);
   memcpy(inliers, h_inl, (size_t)ni * 4);
   *n_inliers = ni;
+  return MVO_OK;
+}
+
+int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
+                                  double *Hout, double *Rs, double *ts, double *normals, int *n_solutions, int32_t *inliers,
+                                  int *n_inliers) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!pts1 || !pts2 || !K || !Hout || !Rs || !ts || !normals || !n_solutions || !n_inliers || (*n_inliers > 0 && !inliers))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByHomography: null pointer");
+  *n_solutions = 0;
+  if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "estiMotionByHomography: %d correspondences (< 4)", n);
+  if (!(threshold > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByHomography: threshold must be positive");
+  HomoCam cam;
+  cam.f = (K[0] + K[4]) / 2; cam.cx = K[2]; cam.cy = K[5];
+  if (!(K[0] > 0 && K[4] > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "K: focal lengths must be positive");
+  const size_t smem = (size_t)n * 4 * sizeof(double);
+  if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "estiMotionByHomography: more than %d correspondences", 200 * 1024 / 32);
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int H = ctx->prm.epi_hypotheses;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_p1 = 0, o_p2 = al(o_p1 + (size_t)n * 8), o_inl = al(o_p2 + (size_t)n * 8), o_H = al(o_inl + (size_t)n * 4);
+  const size_t o_valid = al(o_H + (size_t)H * 72), o_cnt = al(o_valid + (size_t)H * 4), o_out = al(o_cnt + (size_t)H * 4), o_end = o_out + 512;
+  MVO_TRY(mvo_reserve(ctx, ctx->d_a, o_end));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, al((size_t)n * 16) + (size_t)n * 4 + 1024));
+  uint8_t *d = (uint8_t *)ctx->d_a.p, *h = (uint8_t *)ctx->h_a.p;
+  memcpy(h, pts1, (size_t)n * 8);
+  memcpy(h + (size_t)n * 8, pts2, (size_t)n * 8);
+  MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p1, h, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p2, h + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const float *d1 = (const float *)(d + o_p1), *d2 = (const float *)(d + o_p2);
+  double *dH = (double *)(d + o_H), *dout = (double *)(d + o_out);
+  int32_t *dvalid = (int32_t *)(d + o_valid), *dcnt = (int32_t *)(d + o_cnt), *dinl = (int32_t *)(d + o_inl), *dout_i = (int32_t *)(d + o_out + 256);
+  const double thr2 = (threshold / cam.f) * (threshold / cam.f);          // pixels -> scaled coordinates
+  MVO_CUDA(ctx, cudaMemsetAsync(dout, 0, 512, ctx->stream));
+  { KTimer kt(ctx, KC_EPI);
+  k_homo_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(d1, d2, n, cam, ctx->prm.pnp_seed, H, dH, dvalid); }
+  MVO_CHECK_LAUNCH(ctx);
+  if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_homo_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (H + 7) / 8;
+  if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
+  { KTimer kt(ctx, KC_EPI);
+  k_homo_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dvalid, dcnt); }
+  MVO_CHECK_LAUNCH(ctx);
+  { KTimer kt(ctx, KC_EPI);
+  k_homo_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dcnt, dout, dout_i, dinl); }
+  MVO_CHECK_LAUNCH(ctx);
+  double *h_out = (double *)(h + al((size_t)n * 16));
+  int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, dinl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int ni = h_i[0];
+  if (ni < 4) {
+    *n_inliers = 0;
+    return mvo_fail(ctx, MVO_ERR_DEGENERATE, "estiMotionByHomography: no model reached 4 inliers (best minimal model %d, after local optimisation %d)",
+                    h_i[3], h_i[4]);
+  }
+  if (ni > *n_inliers) return mvo_fail(ctx, MVO_ERR_CAPACITY, "inlier capacity %d < %d", *n_inliers, ni);
+  memcpy(Hout, h_out, 72);
+  memcpy(inliers, h_inl, (size_t)ni * 4);
+  *n_inliers = ni;
+  // cv::decomposeHomographyMat(H, K) (:119-120) on the host: Hn = K^-1 H K, then t /= |t| (:122-126)
+  const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+  const double Km[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1}, Ki[9] = {1 / fx, 0, -cx / fx, 0, 1 / fy, -cy / fy, 0, 0, 1};
+  double T[9], Hn[9];
+  epi::mat3_mul(Hout, Km, T);
+  epi::mat3_mul(Ki, T, Hn);
+  const int ns = epi::decompose_homography(Hn, Rs, ts, normals);
+  for (int s = 0; s < ns; ++s) {
+    const double nt = sqrt(ts[3 * s] * ts[3 * s] + ts[3 * s + 1] * ts[3 * s + 1] + ts[3 * s + 2] * ts[3 * s + 2]);
+    if (nt > 0) for (int q = 0; q < 3; ++q) ts[3 * s + q] /= nt;      // a pure rotation keeps t = 0 (the reference divides by zero here)
+  }
+  *n_solutions = ns;
+  return MVO_OK;
+}
+
+int mvo_remove_wrong_rt_of_homography(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, const int32_t *inliers, int n_inliers,
+                                      double *Rs, double *ts, double *normals, int *n_solutions) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!n_solutions || *n_solutions < 0 || *n_solutions > 4 || !Rs || !ts || !normals || (n_inliers > 0 && (!inliers || !pts_np1 || !pts_np2)) || n_inliers < 0)
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "removeWrongRtOfHomography: bad arguments");
+  for (int j = 0; j < n_inliers; ++j)
+    if (inliers[j] < 0 || inliers[j] >= n) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "removeWrongRtOfHomography: inlier index %d outside [0,%d)", inliers[j], n);
+  int keep[4] = {0, 0, 0, 0};
+  static_assert(sizeof(int) == sizeof(int32_t), "int32 indices");
+  epi::filter_homography_solutions(Rs, normals, *n_solutions, pts_np1, pts_np2, (const int *)inliers, n_inliers, keep);
+  int w = 0;
+  for (int s = 0; s < *n_solutions; ++s)
+    if (keep[s]) {
+      if (w != s) { memmove(Rs + 9 * w, Rs + 9 * s, 72); memmove(ts + 3 * w, ts + 3 * s, 24); memmove(normals + 3 * w, normals + 3 * s, 24); }
+      ++w;
+    }
+  *n_solutions = w;
   return MVO_OK;
 }
 

@@ -106,6 +106,8 @@ SIGNATURES = {
     "mvo_timing_read": (_i, [_vp, _vp, _vp]),
     "mvo_esti_motion_by_essential": (_i, [_vp, _vp, _vp, _i, _vp, C.c_double, _vp, _vp, _vp, _vp, _pi]),
     "mvo_do_triangulation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "mvo_esti_motion_by_homography": (_i, [_vp, _vp, _vp, _i, _vp, C.c_double, _vp, _vp, _vp, _vp, _pi, _vp, _pi]),
+    "mvo_remove_wrong_rt_of_homography": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _pi]),
     "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
     "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
     "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
@@ -313,6 +315,27 @@ class Context:
         self._chk(self.lib.mvo_esti_motion_by_essential(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(K), float(threshold), _ptr(E), _ptr(R),
                                                         _ptr(t), _ptr(inl), C.byref(n)))
         return E, R, t, inl[: n.value].copy()
+
+    def esti_motion_by_homography(self, pts1, pts2, K, threshold=3.0):
+        p1, p2, K = _c(pts1, np.float32), _c(pts2, np.float32), _c(K, np.float64)
+        H, Rs, ts, ns = np.zeros((3, 3)), np.zeros((4, 3, 3)), np.zeros((4, 3)), np.zeros((4, 3))
+        inl = np.zeros(max(len(p1), 1), np.int32)
+        n, nsol = C.c_int(len(p1)), C.c_int(0)
+        self._chk(self.lib.mvo_esti_motion_by_homography(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(K), float(threshold), _ptr(H), _ptr(Rs),
+                                                         _ptr(ts), _ptr(ns), C.byref(nsol), _ptr(inl), C.byref(n)))
+        k = nsol.value
+        return H, Rs[:k].copy(), ts[:k].copy(), ns[:k].copy(), inl[: n.value].copy()
+
+    def remove_wrong_rt_of_homography(self, pts_np1, pts_np2, inliers, Rs, ts, normals):
+        p1, p2, inl = _c(pts_np1, np.float32), _c(pts_np2, np.float32), _c(inliers, np.int32)
+        k = len(Rs)
+        R4, t4, n4 = np.zeros((4, 3, 3)), np.zeros((4, 3)), np.zeros((4, 3))
+        R4[:k], t4[:k], n4[:k] = Rs, ts, normals
+        nsol = C.c_int(k)
+        self._chk(self.lib.mvo_remove_wrong_rt_of_homography(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(inl), len(inl), _ptr(R4), _ptr(t4),
+                                                             _ptr(n4), C.byref(nsol)))
+        k = nsol.value
+        return R4[:k].copy(), t4[:k].copy(), n4[:k].copy()
 
     def do_triangulation(self, pts_np1, pts_np2, R, t, inliers):
         p1, p2 = _c(pts_np1, np.float32), _c(pts_np2, np.float32)

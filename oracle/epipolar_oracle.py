@@ -32,3 +32,27 @@ def do_triangulation(pts_np1, pts_np2, R, t, inliers):
     X = cv2.triangulatePoints(T1.astype(np.float64), T2, a.T.copy(), b.T.copy())             # :153-156
     X = X.astype(np.float32)
     return (X[:3] / X[3]).T.copy()                              # :160-168
+
+
+def esti_motion_by_homography(pts1, pts2, K, threshold=3.0):
+    """reference src/geometry/epipolar_geometry.cpp:90-128.  Returns (H with H[2,2] = 1, Rs, ts unit, normals, inliers)."""
+    import cv2
+    p1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 1, 2)
+    p2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 1, 2)
+    H, mask = cv2.findHomography(p1, p2, cv2.RANSAC, threshold)                 # :106
+    H = H / H[2, 2]                                                              # :107
+    inliers = np.nonzero(mask.ravel() == 1)[0].astype(np.int32)                  # :110-117
+    _, Rs, ts, ns = cv2.decomposeHomographyMat(H, np.asarray(K, np.float64))     # :120-121
+    ts = [t.ravel() / np.linalg.norm(t) for t in ts]                             # :123-127
+    return H, [np.asarray(R) for R in Rs], ts, [n.ravel() for n in ns], inliers
+
+
+def remove_wrong_rt_of_homography(pts_np1, pts_np2, inliers, Rs, ts, normals):
+    """reference src/geometry/epipolar_geometry.cpp:59-88: indices of the solutions that survive
+    cv::filterHomographyDecompByVisibleRefpoints on the inlier points."""
+    import cv2
+    a = np.ascontiguousarray(pts_np1, np.float32)[inliers].reshape(-1, 1, 2)
+    b = np.ascontiguousarray(pts_np2, np.float32)[inliers].reshape(-1, 1, 2)
+    sol = cv2.filterHomographyDecompByVisibleRefpoints([np.asarray(R, np.float64) for R in Rs],
+                                                       [np.asarray(n, np.float64).reshape(3, 1) for n in normals], a, b)
+    return [] if sol is None else sol.ravel().tolist()
