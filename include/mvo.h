@@ -342,6 +342,20 @@ int mvo_remove_wrong_rt_of_homography(mvo_ctx *ctx, const float *pts_np1, const 
 int mvo_do_triangulation(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, const double *R,
                          const double *t, const int32_t *inliers, int n_inliers, float *pts3d);
 
+/* checkEssentialScore / checkHomographyScore (src/geometry/motion_estimation.cpp:501-581, :583-664): ORB-SLAM's
+ * symmetric chi-square scores (thresholds 3.841 / 5.991, sigma as in the reference's default 1.0) summed over the
+ * inlier list, which is pruned IN PLACE to the points that pass both directions (*n_inliers in/out).  pts: n x 2
+ * float pixels.  Host only, no context. */
+int mvo_check_essential_score(const double *E21, const double *K, const float *pts_img1, const float *pts_img2,
+                              int n, int32_t *inliers, int *n_inliers, double sigma, double *score);
+int mvo_check_homography_score(const double *H21, const float *pts_img1, const float *pts_img2, int n,
+                               int32_t *inliers, int *n_inliers, double sigma, double *score);
+/* The E / H choice of helperEstimatePossibleRelativePosesByEpipolarGeometry (motion_estimation.cpp:134-154):
+ * ratio = score_h / (score_e + score_h); > 0.5 picks, among the num_h homography solutions (indices 1..num_h,
+ * h_normals = num_h x 3), the one with the largest |normal.z|; otherwise solution 0 (essential).  Host only. */
+int mvo_choose_e_or_h(double score_e, double score_h, const double *h_normals, int num_h, int *best_sol,
+                      double *ratio);
+
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose
  * per line, "tx ty tz R00 R10 R20 R01 R11 R21 R02 R12 R22", C++ stream defaults (6 significant digits).

@@ -1,0 +1,88 @@
+"""Host-side E / H scoring and choice (csrc/motion_host.cpp) against the numpy restatement of reference
+src/geometry/motion_estimation.cpp:134-154, 501-664 (oracle/motion_oracle.py), on a general scene (E wins) and a
+planar scene (H wins)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mvo_synth
+
+K = mvo_synth.K_DEFAULT
+
+
+def _rod(r):
+    th = np.linalg.norm(r)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def _views(rng, planar, n=400):
+    R = _rod(rng.normal(0, 0.05, 3) + 1e-9)
+    t = np.array([0.3, 0.02, 0.05])
+    nrm = np.array([0.05, -0.1, 1.0])
+    nrm /= np.linalg.norm(nrm)
+    P = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2.5, 8, n)], 1)
+    if planar:
+        P[:, 2] = (4.0 - P[:, :2] @ nrm[:2]) / nrm[2]
+    P2 = P @ R.T + t
+    p1 = P[:, :2] / P[:, 2:3] * K[0, 0] + K[:2, 2] + rng.normal(0, 0.5, (n, 2))
+    p2 = P2[:, :2] / P2[:, 2:3] * K[0, 0] + K[:2, 2] + rng.normal(0, 0.5, (n, 2))
+    bad = rng.random(n) < 0.1
+    p2[bad] += rng.uniform(-40, 40, (bad.sum(), 2))
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    # on the plane the essential matrix handed to the scorer is a poor one (two-view E estimation is degenerate there):
+    # rotation off by 20 mrad, which is what makes the homography branch win
+    E = tx @ (R @ _rod(np.array([0.0, 0.02, 0.0])) if planar else R)
+    Hn = R + np.outer(t / 4.0, nrm)
+    H = K @ Hn @ np.linalg.inv(K)
+    return p1.astype(np.float32), p2.astype(np.float32), E / E[2, 2], H / H[2, 2], nrm
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_scores_and_choice_equal_reference_restatement(built, planar):
+    import mvo_b200
+    from oracle import motion_oracle
+    lib = mvo_b200.load_library()
+    rng = np.random.default_rng(7 + planar)
+    p1, p2, E, H, nrm = _views(rng, planar)
+    n = len(p1)
+    Kc = np.ascontiguousarray(K, np.float64)
+    out = {}
+    for name, M in (("E", E), ("H", H)):
+        inl = np.arange(n, dtype=np.int32)
+        cnt, score = C.c_int(n), C.c_double(0)
+        Mc = np.ascontiguousarray(M, np.float64)
+        if name == "E":
+            rc = lib.mvo_check_essential_score(Mc.ctypes.data, Kc.ctypes.data, p1.ctypes.data, p2.ctypes.data, n, inl.ctypes.data, C.byref(cnt), 1.0, C.byref(score))
+            ref_score, ref_inl = motion_oracle.check_essential_score(M, K, p1, p2, np.arange(n))
+        else:
+            rc = lib.mvo_check_homography_score(Mc.ctypes.data, p1.ctypes.data, p2.ctypes.data, n, inl.ctypes.data, C.byref(cnt), 1.0, C.byref(score))
+            ref_score, ref_inl = motion_oracle.check_homography_score(M, p1, p2, np.arange(n))
+        assert rc == 0
+        assert np.array_equal(inl[: cnt.value], ref_inl) and abs(score.value - ref_score) < 1e-6 * max(1.0, abs(ref_score))
+        out[name] = score.value
+    normals = np.array([[0.9, 0.1, 0.3], [-0.9, -0.1, -0.3], nrm, -nrm])
+    best, ratio = C.c_int(-1), C.c_double(0)
+    assert lib.mvo_choose_e_or_h(out["E"], out["H"], normals.ctypes.data, 4, C.byref(best), C.byref(ratio)) == 0
+    rb, rr = motion_oracle.choose_e_or_h(out["E"], out["H"], normals)
+    assert best.value == rb and abs(ratio.value - rr) < 1e-12
+    # a general scene scores higher under E; on the plane (with its poor E) the homography branch is taken
+    assert (best.value == 0) == (not planar), (planar, out, ratio.value)
+    if planar:
+        assert best.value == 3                                       # first of the two most frontal normals (+-nrm tie -> lowest index)
+
+
+def test_score_argument_checks(built):
+    import mvo_b200
+    lib = mvo_b200.load_library()
+    cnt, score = C.c_int(1), C.c_double(0)
+    inl = np.array([5], np.int32)
+    p = np.zeros((3, 2), np.float32)
+    E = np.eye(3)
+    assert lib.mvo_check_essential_score(E.ctypes.data, np.ascontiguousarray(K).ctypes.data, p.ctypes.data, p.ctypes.data, 3, inl.ctypes.data,
+                                         C.byref(cnt), 1.0, C.byref(score)) == -1          # inlier index outside the point set
+    sing = np.zeros((3, 3))
+    cnt = C.c_int(0)
+    assert lib.mvo_check_homography_score(sing.ctypes.data, p.ctypes.data, p.ctypes.data, 3, inl.ctypes.data, C.byref(cnt), 1.0, C.byref(score)) == -1
