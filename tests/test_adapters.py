@@ -26,7 +26,8 @@ def test_adapter_layer_builds_with_reference_signatures(built):
                  "my_slam::geometry::selectUniformKptsByGrid(", "my_slam::geometry::computeMeanDistBetweenKeypoints(",
                  "my_slam::geometry::inliers2DMatches(", "my_slam::geometry::pts2Keypts(",
                  "my_slam::optimization::bundleAdjustment(", "my_slam::optimization::optimizeSingleFrame(",
-                 "my_slam::geometry::estiMotionByEssential(std::vector<cv::Point2f", "my_slam::geometry::doTriangulation(std::vector<cv::Point2f"):
+                 "my_slam::geometry::estiMotionByEssential(std::vector<cv::Point2f", "my_slam::geometry::doTriangulation(std::vector<cv::Point2f",
+                 "my_slam::geometry::estiMotionByHomography(std::vector<cv::Point2f", "my_slam::geometry::removeWrongRtOfHomography(std::vector<cv::Point2f"):
         assert want in syms, want
 
 
