@@ -356,6 +356,23 @@ int mvo_check_homography_score(const double *H21, const float *pts_img1, const f
 int mvo_choose_e_or_h(double score_e, double score_h, const double *h_normals, int num_h, int *best_sol,
                       double *ratio);
 
+/* helperEstimatePossibleRelativePosesByEpipolarGeometry (motion_estimation.cpp:10-158) over flat arrays of MATCHED
+ * points (pts_img1[i] <-> pts_img2[i], n x 2 float pixels): solution 0 is the essential-matrix motion, solutions
+ * 1..num_solutions-1 the homography motions that survive removeWrongRtOfHomography (calc_homo != 0); every solution's
+ * inliers are triangulated (camera 1 frame); motion_cam2_to_cam1 == 0 inverts every (R, t) afterwards (basics::invRt);
+ * `best` is the E/H choice.  inliers: 5 x n int32 (row s holds n_inliers[s] indices), pts3d: 5 x n x 3 float. */
+typedef struct mvo_two_view_solutions {
+  int32_t num_solutions, best;
+  int32_t n_inliers[5];
+  int32_t pad_;
+  double R[5][9], t[5][3], normal[5][3];   /* normal of solution 0 is zero (the reference pushes an empty cv::Mat) */
+  double E[9], H[9];
+  double score_e, score_h, ratio;
+} mvo_two_view_solutions;
+int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, const float *pts_img2, int n, const double *K,
+                                int calc_homo, int motion_cam2_to_cam1, mvo_two_view_solutions *sol,
+                                int32_t *inliers, float *pts3d);
+
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose
  * per line, "tx ty tz R00 R10 R20 R01 R11 R21 R02 R12 R22", C++ stream defaults (6 significant digits).

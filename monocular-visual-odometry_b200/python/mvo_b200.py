@@ -53,6 +53,12 @@ class TrackResult(C.Structure):
                 ("pad", C.c_int32), ("T_w_c_pnp", C.c_double * 16)]
 
 
+class TwoViewSolutions(C.Structure):
+    _fields_ = [("num_solutions", C.c_int32), ("best", C.c_int32), ("n_inliers", C.c_int32 * 5), ("pad_", C.c_int32),
+                ("R", (C.c_double * 9) * 5), ("t", (C.c_double * 3) * 5), ("normal", (C.c_double * 3) * 5),
+                ("E", C.c_double * 9), ("H", C.c_double * 9), ("score_e", C.c_double), ("score_h", C.c_double), ("ratio", C.c_double)]
+
+
 class MvoError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
@@ -108,6 +114,7 @@ SIGNATURES = {
     "mvo_do_triangulation": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "mvo_esti_motion_by_homography": (_i, [_vp, _vp, _vp, _i, _vp, C.c_double, _vp, _vp, _vp, _vp, _pi, _vp, _pi]),
     "mvo_remove_wrong_rt_of_homography": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _pi]),
+    "mvo_estimate_relative_poses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, C.POINTER(TwoViewSolutions), _vp, _vp]),
     "mvo_check_essential_score": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
     "mvo_check_homography_score": (_i, [_vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
     "mvo_choose_e_or_h": (_i, [C.c_double, C.c_double, _vp, _i, _pi, C.POINTER(C.c_double)]),
@@ -339,6 +346,22 @@ class Context:
                                                              _ptr(n4), C.byref(nsol)))
         k = nsol.value
         return R4[:k].copy(), t4[:k].copy(), n4[:k].copy()
+
+    def estimate_relative_poses(self, pts1, pts2, K, calc_homo=True, motion_cam2_to_cam1=True):
+        p1, p2, K = _c(pts1, np.float32), _c(pts2, np.float32), _c(K, np.float64)
+        n = len(p1)
+        sol = TwoViewSolutions()
+        inl = np.zeros((5, max(n, 1)), np.int32)
+        pts3d = np.zeros((5, max(n, 1), 3), np.float32)
+        self._chk(self.lib.mvo_estimate_relative_poses(self.h, _ptr(p1), _ptr(p2), n, _ptr(K), int(calc_homo), int(motion_cam2_to_cam1),
+                                                       C.byref(sol), _ptr(inl), _ptr(pts3d)))
+        out = []
+        for s in range(sol.num_solutions):
+            k = sol.n_inliers[s]
+            out.append(dict(R=np.array(sol.R[s]).reshape(3, 3), t=np.array(sol.t[s]), normal=np.array(sol.normal[s]),
+                            inliers=inl[s, :k].copy(), pts3d=pts3d[s, :k].copy()))
+        return out, sol.best, dict(score_e=sol.score_e, score_h=sol.score_h, ratio=sol.ratio, E=np.array(sol.E).reshape(3, 3),
+                                   H=np.array(sol.H).reshape(3, 3))
 
     def do_triangulation(self, pts_np1, pts_np2, R, t, inliers):
         p1, p2 = _c(pts_np1, np.float32), _c(pts_np2, np.float32)

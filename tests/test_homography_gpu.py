@@ -73,6 +73,34 @@ for seed in range(3):
     R2, t2, n2 = ctx.remove_wrong_rt_of_homography(np1, np2, inl, Rs, ts, ns)
     assert len(R2) == len(keep) and all(np.array_equal(R2[j], Rs[k]) and np.array_equal(n2[j], ns[k]) for j, k in enumerate(keep))
     assert len(keep) >= 1 and int(np.argmin(err)) in keep
+# ---- the assembled initialisation helper (motion_estimation.cpp:10-158) on a general scene and on a plane ----
+for planar in (False, True):
+    rng = np.random.default_rng(40 + planar)
+    n = 900
+    R = rod(rng.normal(0, 0.05, 3) + 1e-9)
+    t = np.array([0.3, 0.02, 0.06])
+    nrm = np.array([0.05, -0.08, 1.0]); nrm /= np.linalg.norm(nrm)
+    P = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(2.5, 8, n)], 1)
+    if planar:
+        P[:, 2] = (4.0 - P[:, :2] @ nrm[:2]) / nrm[2]
+    P2 = P @ R.T + t
+    p1 = (P[:, :2] / P[:, 2:3] * K[0, 0] + K[:2, 2] + rng.normal(0, 0.4, (n, 2))).astype(np.float32)
+    p2 = (P2[:, :2] / P2[:, 2:3] * K[0, 0] + K[:2, 2] + rng.normal(0, 0.4, (n, 2))).astype(np.float32)
+    sols, best, info = ctx.estimate_relative_poses(p1, p2, K)
+    assert 1 <= len(sols) <= 5 and 0 <= best < len(sols)
+    td = t / np.linalg.norm(t)
+    if not planar:
+        assert best == 0, (best, info)
+        s0 = sols[0]
+        assert np.abs(s0["R"] - R).max() < 5e-3 and np.arccos(np.clip(s0["t"] @ td, -1, 1)) < 0.05
+        X = s0["pts3d"] * np.linalg.norm(t)                        # unit baseline -> true scale
+        assert np.median(np.linalg.norm(X - P[s0["inliers"]], axis=1) / np.linalg.norm(P[s0["inliers"]], axis=1)) < 0.05
+    else:
+        assert len(sols) >= 2 and np.allclose(sols[0]["normal"], 0)
+        errs = [max(np.abs(s["R"] - R).max(), np.abs(s["t"] - td).max()) for s in sols[1:]]
+        assert min(errs) < 0.03, errs                              # the true motion is among the surviving homography solutions
+    sols_inv, _, _ = ctx.estimate_relative_poses(p1, p2, K, motion_cam2_to_cam1=False)
+    assert np.allclose(sols_inv[0]["R"], sols[0]["R"].T, atol=1e-12) and np.allclose(sols_inv[0]["t"], -sols[0]["R"].T @ sols[0]["t"], atol=1e-12)
 try:
     ctx.esti_motion_by_homography(np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32), K)
     raise SystemExit("n < 4 was accepted")
