@@ -59,6 +59,8 @@ ALGO_BYTES = {
     "k_pnp_score": 20 * 2000 + 100 * 4096,
     "k_pnp_finish": 20 * 2000 + 4 * 4096,
     "k_ba": 10000 * 16 + 2000 * 24 + 5 * 96,
+    # match-list filter (the largest member of the class): keys + in-view flags + map points in, pairs + PnP arrays out
+    "k_track_glue": 2001 * (4 + 1 + 12) + 1300 * (8 + 20),
 }
 
 
