@@ -373,6 +373,26 @@ int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, const float
                                 int calc_homo, int motion_cam2_to_cam1, mvo_two_view_solutions *sol,
                                 int32_t *inliers, float *pts3d);
 
+/* ---- host-side decisions of the initialisation / keyframe logic (no context, no GPU) ----------
+ * retainGoodTriangulationResult_ (src/vo/vo.cpp:181-244): triangulation angle (degrees, with the reference's
+ * pi = 3.1415926) of every point between the two camera centres; points below min_triang_angle or above
+ * max_ratio x the median angle are dropped.  keep: surviving indices, angles: their angles (n capacity each). */
+int mvo_retain_good_triangulation(const float *pts3d_in_curr, int n, const double *T_w_c_curr, const double *T_w_c_ref,
+                                  double min_triang_angle, double max_ratio_to_median, int32_t *keep, double *angles,
+                                  int *n_keep);
+/* The depth normalisation of estimateMotionAnd3DPoints_ (vo.cpp:96-110): scale = assumed_mean_depth / mean z;
+ * points (n x 3 float) and t_curr_to_prev (3) are scaled in place. */
+int mvo_normalize_init_depth(float *pts3d, int n, double *t_curr_to_prev, double assumed_mean_depth, double *scale);
+/* isVoGoodToInit_ (vo.cpp:113-172) over the matched keypoint positions (n_matches x 2 each, row i = one match) and
+ * the triangulation angles that survived: enough matches, mean pixel displacement and median angle above their
+ * thresholds (config min_inlier_matches, min_pixel_dist, min_median_triangulation_angle). */
+int mvo_is_vo_good_to_init(const float *kpts_ref_xy, const float *kpts_curr_xy, int n_matches,
+                           const double *triangulation_angles, int n_angles, int min_inlier_matches, double min_pixel_dist,
+                           double min_median_triangulation_angle, int *good, double *mean_pixel_dist, double *median_angle);
+/* checkLargeMoveForAddKeyFrame_ (vo.cpp:247-265): translation of ref^-1 * curr above min_dist_between_two_keyframes. */
+int mvo_check_large_move(const double *T_w_c_curr, const double *T_w_c_ref, double min_dist_between_two_keyframes, int *large,
+                         double *moved_dist, double *rotated_angle);
+
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose
  * per line, "tx ty tz R00 R10 R20 R01 R11 R21 R02 R12 R22", C++ stream defaults (6 significant digits).

@@ -118,6 +118,10 @@ SIGNATURES = {
     "mvo_check_essential_score": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
     "mvo_check_homography_score": (_i, [_vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
     "mvo_choose_e_or_h": (_i, [C.c_double, C.c_double, _vp, _i, _pi, C.POINTER(C.c_double)]),
+    "mvo_retain_good_triangulation": (_i, [_vp, _i, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _pi]),
+    "mvo_normalize_init_depth": (_i, [_vp, _i, _vp, C.c_double, C.POINTER(C.c_double)]),
+    "mvo_is_vo_good_to_init": (_i, [_vp, _vp, _i, _vp, _i, _i, C.c_double, C.c_double, _pi, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mvo_check_large_move": (_i, [_vp, _vp, C.c_double, _pi, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
     "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
     "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
