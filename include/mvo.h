@@ -393,6 +393,65 @@ int mvo_is_vo_good_to_init(const float *kpts_ref_xy, const float *kpts_curr_xy, 
 int mvo_check_large_move(const double *T_w_c_curr, const double *T_w_c_ref, double min_dist_between_two_keyframes, int *large,
                          double *moved_dist, double *rotated_angle);
 
+/* ---- the whole VisualOdometry state machine ---------------------------------------------------
+ * vo::VisualOdometry::addFrame (src/vo/vo_addFrame.cpp:10-142) with the reference's containers (Frame, MapPoint, Map as
+ * std::unordered_map, the 20-frame buffer) on the host and every numeric stage on the GPU through the entry points
+ * above: BLANK -> first keyframe; DOING_INITIALIZATION -> match against the first keyframe, two-view motion (E / H),
+ * triangulation, depth normalisation, isVoGoodToInit_ -> map + second keyframe; DOING_TRACKING -> map points in view,
+ * match, RANSAC PnP, windowed BA, and on a large move a new keyframe (match, essential inliers, triangulation with the
+ * known motion, pushCurrPointsToMap_, optimizeMap_).  This is the slower, complete counterpart of the mvo_tracker_* calls, which
+ * keep a caller-supplied map resident on the GPU and do no map maintenance.
+ * Where the reference would abort — fewer than 5 matched points handed to findEssentialMat, an empty rvec after a
+ * failed solvePnPRansac — the frame is skipped / the PnP reported as failed. */
+typedef struct mvo_vo mvo_vo;
+
+typedef struct mvo_vo_params {
+  mvo_track_params track;              /* tracking keys (match method / radius for PnP, BA window, keyframe distance ...);
+                                          device_resident is ignored */
+  int32_t match_method_init;           /* feature_match_method_index_initialization = 1 */
+  float max_match_dist_init;           /* max_matching_pixel_dist_in_initialization = 100 */
+  float max_match_dist_triangulation;  /* max_matching_pixel_dist_in_triangulation = 100 */
+  int32_t init_calc_homography;        /* is_calc_homo = true (vo.cpp:68) */
+  int32_t min_inlier_matches;          /* 15 */
+  int32_t pad;
+  double essential_threshold;          /* findEssentialMat_threshold = 1.0 (keyframe branch; the initialisation goes
+                                          through mvo_estimate_relative_poses, which uses 1.0) */
+  double min_triang_angle;             /* 1.0 */
+  double max_ratio_angle_to_median;    /* max_ratio_between_max_angle_and_median_angle = 20 */
+  double min_pixel_dist;               /* 50 */
+  double min_median_triangulation_angle; /* 2.0 */
+  double assumed_mean_depth_init;      /* assumed_mean_pts_depth_during_vo_init = 0.8 */
+} mvo_vo_params;
+
+typedef struct mvo_vo_frame_info {
+  int32_t frame_id, state_in, state_out;   /* states: 0 BLANK, 1 DOING_INITIALIZATION, 2 DOING_TRACKING (vo.h:52-58) */
+  int32_t keyframe;                        /* this frame became a keyframe */
+  int32_t n_keypoints, n_matches, n_candidates, n_inliers;
+  int32_t pnp_ok, ba_frames, ba_edges;
+  int32_t best_sol;                        /* initialisation: chosen two-view solution (0 = essential), -1 = none */
+  int32_t map_points;                      /* map size after the frame */
+  int32_t kf_matches, kf_new_points, pad;  /* keyframe branch: matches with the previous keyframe, points kept by
+                                              retainGoodTriangulationResult_ */
+  double score_e, score_h, eh_ratio, init_mean_pixel_dist, init_median_angle;
+  double T_w_c_pnp[16];                    /* tracking: pose right after PnP (before BA) */
+} mvo_vo_frame_info;
+
+void mvo_vo_default_params(mvo_vo_params *p);
+int mvo_vo_create(mvo_ctx *ctx, const double *K /* 3x3 */, int rows, int cols, const mvo_vo_params *params /* NULL = defaults */,
+                  mvo_vo **out);
+void mvo_vo_destroy(mvo_vo *v);
+/* addFrame: image rows x cols x channels (3 = BGR, 1 = gray) in host memory.  T_w_c_out = the frame's pose when the
+ * call returns (run_vo.cpp:137 records exactly this), info optional. */
+int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t stride, double *T_w_c_out, mvo_vo_frame_info *info);
+int mvo_vo_is_initialized(const mvo_vo *v);                  /* VisualOdometry::isInitialized */
+int mvo_vo_map_size(const mvo_vo *v);
+int mvo_vo_num_keyframes(const mvo_vo *v);
+/* The map in container order (VisualOdometry::getMap): ids, positions (x 3 float), descriptors (x 32), colours (x 3,
+ * r g b); any output may be NULL.  MVO_ERR_CAPACITY (with *n = map size) when cap is too small. */
+int mvo_vo_get_map(const mvo_vo *v, int32_t *ids, float *pts3d, uint8_t *desc, uint8_t *rgb, int cap, int *n);
+/* Pose of the k-th newest buffered frame (k = 0: the last one) including later BA updates. */
+int mvo_vo_frame_pose(const mvo_vo *v, int k, double *T_w_c);
+
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose
  * per line, "tx ty tz R00 R10 R20 R01 R11 R21 R02 R12 R22", C++ stream defaults (6 significant digits).
@@ -420,6 +479,9 @@ int mvo_config_get_bool(const mvo_config *c, const char *key, int *out);
  * 3x3 intrinsics of the dataset selected by dataset_name (readCameraIntrinsics, vo_io.cpp:40-49).  Fields
  * without a config key (PnP hypotheses, BA iterations, ...) are left as they are. */
 int mvo_config_apply(const mvo_config *c, mvo_params *p, mvo_track_params *tp, double *K9);
+/* The same for the state machine: vp->track as above plus the initialisation / triangulation keys of vo.cpp and
+ * vo_addFrame.cpp. */
+int mvo_config_apply_vo(const mvo_config *c, mvo_vo_params *vp);
 
 #ifdef __cplusplus
 }

@@ -227,4 +227,26 @@ int mvo_config_apply(const mvo_config *c, mvo_params *p, mvo_track_params *tp, d
   return MVO_OK;
 }
 
+int mvo_config_apply_vo(const mvo_config *c, mvo_vo_params *vp) {
+  if (!c || !vp) return MVO_ERR_INVALID_ARG;
+  int rc = mvo_config_apply(c, nullptr, &vp->track, nullptr), iv;
+  if (rc != MVO_OK) return rc;
+  double dv;
+#define GET_I(key, dst) do { if ((rc = mvo_config_get_int(c, key, &iv)) != MVO_OK) return rc; dst = iv; } while (0)
+#define GET_D(key, dst) do { if ((rc = mvo_config_get_double(c, key, &dv)) != MVO_OK) return rc; dst = dv; } while (0)
+  GET_I("feature_match_method_index_initialization", vp->match_method_init);          // vo_addFrame.cpp:41
+  GET_D("max_matching_pixel_dist_in_initialization", vp->max_match_dist_init);        // :39-40
+  GET_D("max_matching_pixel_dist_in_triangulation", vp->max_match_dist_triangulation);   // :97-98
+  GET_D("findEssentialMat_threshold", vp->essential_threshold);                       // epipolar_geometry.cpp:32
+  GET_D("min_triang_angle", vp->min_triang_angle);                                    // vo.cpp:183-185
+  GET_D("max_ratio_between_max_angle_and_median_angle", vp->max_ratio_angle_to_median);
+  GET_I("min_inlier_matches", vp->min_inlier_matches);                                // vo.cpp:123-125
+  GET_D("min_pixel_dist", vp->min_pixel_dist);
+  GET_D("min_median_triangulation_angle", vp->min_median_triangulation_angle);
+  GET_D("assumed_mean_pts_depth_during_vo_init", vp->assumed_mean_depth_init);        // vo.cpp:103-104
+#undef GET_I
+#undef GET_D
+  return MVO_OK;
+}
+
 }  // extern "C"

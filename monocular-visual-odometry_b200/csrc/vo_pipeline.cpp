@@ -1,0 +1,599 @@
+// The VisualOdometry state machine of the reference as host C++ over the C-ABI stages of this library:
+//   addFrame                        reference src/vo/vo_addFrame.cpp:10-142
+//   estimateMotionAnd3DPoints_      src/vo/vo.cpp:53-111   -> mvo_estimate_relative_poses, mvo_retain_good_triangulation,
+//                                                             mvo_normalize_init_depth
+//   isVoGoodToInit_                 src/vo/vo.cpp:113-172  -> mvo_is_vo_good_to_init
+//   poseEstimationPnP_              src/vo/vo.cpp:267-381  -> mvo_match_features, mvo_solve_pnp_ransac
+//   callBundleAdjustment_           src/vo/vo.cpp:384-478  -> mvo_bundle_adjustment
+//   addKeyFrame_ / optimizeMap_ / pushCurrPointsToMap_ / getViewAngle_   src/vo/vo.cpp:482-584
+//   keyframe branch                 vo_addFrame.cpp:93-124 -> mvo_esti_motion_by_essential (helperFindInlierMatchesByEpipolarCons,
+//                                                             motion_estimation.cpp:180-196), mvo_do_triangulation
+//                                                             (helperTriangulatePoints, :200-240)
+// Frames, map points and their graph live in the same containers as in the reference (Frame / MapPoint / Map,
+// include/my_slam/vo/*.h): the map and the per-frame keypoint -> map point links are std::unordered_map<int, ...> and are
+// walked in container order, so the candidate order handed to the matcher is the reference's.  Every numeric stage runs on
+// the GPU through the entry points named above; this file holds no arithmetic beyond 4x4 products and the bookkeeping.
+//
+// Where the reference would abort (an OpenCV assertion below 5 matched points in findEssentialMat; an empty rvec after a
+// failed solvePnPRansac) the frame is skipped / the PnP is reported as failed instead.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <deque>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+#include "mvo_internal.h"
+
+namespace {
+
+enum { VO_BLANK = 0, VO_DOING_INITIALIZATION = 1, VO_DOING_TRACKING = 2, VO_LOST = 3 };   // vo.h:52-58
+
+struct PtConn { int pt_ref_idx, pt_map_idx; };                   // frame.h:14-18
+
+struct VoFrame {                                                 // vo::Frame (frame.h:20-98)
+  int id = 0;
+  std::vector<mvo_keypoint> kpts;
+  std::vector<uint8_t> desc;                                     // n x 32
+  std::vector<uint8_t> colors;                                   // n x 3, r g b (kpts_colors_)
+  std::vector<float> xy;                                         // n x 2, keypoints_[i].pt
+  double T_w_c[16];
+  std::vector<mvo_dmatch> matches_with_ref, inliers_matches_with_ref, inliers_matches_for_3d, matches_with_map;
+  std::vector<float> inliers_pts3d;                              // 3 per point, in this camera's frame
+  std::vector<double> triangulation_angles;
+  std::unordered_map<int, PtConn> conn;                          // inliers_to_mappt_connections_
+  int n() const { return (int)kpts.size(); }
+};
+typedef std::shared_ptr<VoFrame> FramePtr;
+
+struct VoMapPoint {                                              // vo::MapPoint (mappoint.h, mappoint.cpp:12-20)
+  int id = 0;
+  float pos[3];
+  double norm[3];
+  uint8_t desc[32];
+  uint8_t rgb[3];
+  int visible_times = 1, matched_times = 1;
+};
+
+void set_identity(double *T) { memset(T, 0, 16 * sizeof(double)); T[0] = T[5] = T[10] = T[15] = 1; }
+void mul44(const double *A, const double *B, double *C) {
+  double r[16];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+    double a = 0;
+    for (int k = 0; k < 4; ++k) a += A[i * 4 + k] * B[k * 4 + j];
+    r[i * 4 + j] = a;
+  }
+  memcpy(C, r, sizeof r);
+}
+void inv_rigid44(const double *T, double *Ti) {                  // [R t; 0 1]^-1
+  double r[16];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i * 4 + j] = T[j * 4 + i];
+  for (int i = 0; i < 3; ++i) r[i * 4 + 3] = -(r[i * 4] * T[3] + r[i * 4 + 1] * T[7] + r[i * 4 + 2] * T[11]);
+  r[12] = r[13] = r[14] = 0; r[15] = 1;
+  memcpy(Ti, r, sizeof r);
+}
+void rt_to_T(const double *R, const double *t, double *T) {      // basics::convertRt2T
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T[i * 4 + j] = R[i * 3 + j]; T[i * 4 + 3] = t[i]; }
+  T[12] = T[13] = T[14] = 0; T[15] = 1;
+}
+// basics::preTranslatePoint3f: T(row, j) * p[j] accumulated in double over j = 0..3, narrowed to Point3f
+void pre_translate(const float *p, const double *T, float *out) {
+  const double p0 = p[0], p1 = p[1], p2 = p[2];
+  for (int r = 0; r < 3; ++r) {
+    double a = 0;
+    a += T[r * 4] * p0; a += T[r * 4 + 1] * p1; a += T[r * 4 + 2] * p2; a += T[r * 4 + 3] * 1.0;
+    out[r] = (float)a;
+  }
+}
+// basics::transCoord (opencv_funcs.cpp:121-125): R * p + t in double, narrowed to Point3f
+void trans_coord(const float *p, const double *R, const double *t, float *out) {
+  for (int r = 0; r < 3; ++r) out[r] = (float)(R[r * 3] * (double)p[0] + R[r * 3 + 1] * (double)p[1] + R[r * 3 + 2] * (double)p[2] + t[r]);
+}
+void rodrigues_to_R(const double *w, double *R) {                // cv::Rodrigues(rvec -> R)
+  const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  if (th < 1e-300) { R[0] = R[4] = R[8] = 1; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0; return; }
+  const double c = cos(th), s = sin(th), c1 = 1 - c, x = w[0] / th, y = w[1] / th, z = w[2] / th;
+  R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
+  R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
+  R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+}
+
+}  // namespace
+
+struct mvo_vo {
+  mvo_ctx *ctx = nullptr;
+  mvo_vo_params prm;
+  double K[9];
+  int rows = 0, cols = 0;
+  int state = VO_BLANK;
+  std::unordered_map<int, VoMapPoint> map_points;                // vo::Map::map_points_ (map.h:21)
+  std::unordered_map<int, FramePtr> keyframes;                   // vo::Map::keyframes_
+  std::deque<FramePtr> buff;                                     // frames_buff_ (vo.h:70)
+  FramePtr curr, prev, ref, prev_ref;
+  int frame_factory_id = 0, point_factory_id = 0;                // Frame::factory_id_, MapPoint::factory_id_ (per instance here)
+  double map_point_erase_ratio = 0.1;                            // function-local static of optimizeMap_ (vo.cpp:490-491)
+  // scratch
+  std::vector<float> p1, p2, np1, np2, pts3d, cand_xy, p3d, p2d, ba_ob, ba_pts;
+  std::vector<uint8_t> cand_desc;
+  std::vector<int32_t> inl, keep, cand_id, ba_ef, ba_ep, ba_used;
+  std::vector<double> angles, ba_poses;
+  std::vector<mvo_dmatch> matches;
+};
+
+namespace {
+
+int match_into(mvo_vo *v, const uint8_t *d1, const float *xy1, int n1, const VoFrame &f2, int method, float radius,
+               std::vector<mvo_dmatch> *out) {
+  out->clear();
+  if (n1 <= 0 || f2.n() <= 0 || (method == 2 && f2.n() < 2)) return MVO_OK;
+  out->resize((size_t)n1);
+  int nm = 0;
+  const int rc = mvo_match_features(v->ctx, d1, n1, f2.desc.data(), f2.n(), method, xy1, f2.xy.data(), radius, out->data(), &nm);
+  if (rc != MVO_OK) { out->clear(); return rc; }
+  out->resize((size_t)nm);
+  return MVO_OK;
+}
+
+// Frame::calcKeyPoints + calcDescriptors (frame.h:73-86)
+int extract(mvo_vo *v, VoFrame *f, const uint8_t *image, int channels, size_t stride) {
+  const int cap = v->ctx->prm.max_keypoints + 8;
+  f->kpts.resize((size_t)cap);
+  f->desc.resize((size_t)cap * 32);
+  int n = cap;
+  MVO_TRY(mvo_orb_extract(v->ctx, image, v->rows, v->cols, channels, stride, f->kpts.data(), &n, f->desc.data()));
+  f->kpts.resize((size_t)n);
+  f->desc.resize((size_t)n * 32);
+  f->xy.resize((size_t)n * 2);
+  f->colors.resize((size_t)n * 3);
+  for (int i = 0; i < n; ++i) {
+    f->xy[2 * i] = f->kpts[i].x;
+    f->xy[2 * i + 1] = f->kpts[i].y;
+    const int x = (int)floorf(f->kpts[i].x), y = (int)floorf(f->kpts[i].y);       // frame.h:80-84
+    const uint8_t *px = image + (size_t)y * stride + (size_t)x * channels;
+    if (channels == 3) { f->colors[3 * i] = px[2]; f->colors[3 * i + 1] = px[1]; f->colors[3 * i + 2] = px[0]; }   // getPixelAt: {r, g, b}
+    else { f->colors[3 * i] = f->colors[3 * i + 1] = f->colors[3 * i + 2] = px[0]; }
+  }
+  return MVO_OK;
+}
+
+void add_keyframe(mvo_vo *v, const FramePtr &f) {                // addKeyFrame_ (vo.cpp:482-486), Map::insertKeyFrame
+  v->keyframes[f->id] = f;
+  v->ref = f;
+}
+
+// retainGoodTriangulationResult_ (vo.cpp:181-244)
+int retain_good_triangulation(mvo_vo *v) {
+  VoFrame &c = *v->curr;
+  const int n = (int)(c.inliers_pts3d.size() / 3);
+  if (n == 0) return MVO_OK;
+  v->keep.resize((size_t)n);
+  v->angles.resize((size_t)n);
+  int nk = 0;
+  MVO_TRY(mvo_retain_good_triangulation(c.inliers_pts3d.data(), n, c.T_w_c, v->ref->T_w_c, v->prm.min_triang_angle,
+                                        v->prm.max_ratio_angle_to_median, v->keep.data(), v->angles.data(), &nk));
+  std::vector<float> kept((size_t)nk * 3);
+  for (int i = 0; i < nk; ++i) {
+    c.inliers_matches_for_3d.push_back(c.inliers_matches_with_ref[(size_t)v->keep[i]]);
+    memcpy(&kept[3 * (size_t)i], &c.inliers_pts3d[3 * (size_t)v->keep[i]], 12);
+    c.triangulation_angles.push_back(v->angles[i]);
+  }
+  c.inliers_pts3d.swap(kept);
+  return MVO_OK;
+}
+
+// estimateMotionAnd3DPoints_ (vo.cpp:53-111).  *usable = 0 when the two-view problem is degenerate (see the file header).
+int estimate_motion_and_3d_points(mvo_vo *v, mvo_vo_frame_info *info, int *usable) {
+  VoFrame &c = *v->curr;
+  const VoFrame &r = *v->ref;
+  *usable = 0;
+  const int n = (int)c.matches_with_ref.size();
+  if (n < 8) return MVO_OK;
+  v->p1.resize((size_t)n * 2); v->p2.resize((size_t)n * 2);
+  for (int i = 0; i < n; ++i) {
+    const mvo_dmatch &m = c.matches_with_ref[i];
+    v->p1[2 * i] = r.xy[2 * m.query_idx]; v->p1[2 * i + 1] = r.xy[2 * m.query_idx + 1];
+    v->p2[2 * i] = c.xy[2 * m.train_idx]; v->p2[2 * i + 1] = c.xy[2 * m.train_idx + 1];
+  }
+  mvo_two_view_solutions sol;
+  v->inl.resize((size_t)5 * n);
+  v->pts3d.resize((size_t)5 * n * 3);
+  const int rc = mvo_estimate_relative_poses(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.init_calc_homography, 1, &sol,
+                                             v->inl.data(), v->pts3d.data());
+  if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
+  if (rc != MVO_OK) return rc;
+  const int best = sol.best, ni = sol.n_inliers[best];
+  info->best_sol = best;
+  info->score_e = sol.score_e; info->score_h = sol.score_h; info->eh_ratio = sol.ratio;
+  const double *R = sol.R[best];
+  double t[3] = {sol.t[best][0], sol.t[best][1], sol.t[best][2]};
+  const int32_t *inl = v->inl.data() + (size_t)best * n;
+  const float *p3 = v->pts3d.data() + (size_t)best * n * 3;
+  c.inliers_matches_with_ref.resize((size_t)ni);
+  c.inliers_pts3d.resize((size_t)ni * 3);
+  for (int i = 0; i < ni; ++i) {
+    mvo_dmatch m = c.matches_with_ref[(size_t)inl[i]];
+    m.img_idx = -1;                                              // cv::DMatch(queryIdx, trainIdx, distance) (motion_estimation.cpp:104-106)
+    c.inliers_matches_with_ref[(size_t)i] = m;
+    trans_coord(p3 + 3 * (size_t)i, R, t, &c.inliers_pts3d[3 * (size_t)i]);          // points in the current camera (vo.cpp:84-86)
+  }
+  double Trt[16], Tinv[16];
+  rt_to_T(R, t, Trt);
+  inv_rigid44(Trt, Tinv);
+  mul44(r.T_w_c, Tinv, c.T_w_c);                                 // vo.cpp:91
+  MVO_TRY(retain_good_triangulation(v));
+  *usable = 1;
+  const int N = (int)(c.inliers_pts3d.size() / 3);
+  if (N < 20) return MVO_OK;                                     // vo.cpp:97-101
+  MVO_TRY(mvo_normalize_init_depth(c.inliers_pts3d.data(), N, t, v->prm.assumed_mean_depth_init, nullptr));     // :104-108
+  rt_to_T(R, t, Trt);
+  inv_rigid44(Trt, Tinv);
+  mul44(r.T_w_c, Tinv, c.T_w_c);                                 // :110
+  return MVO_OK;
+}
+
+// isVoGoodToInit_ (vo.cpp:113-172)
+int is_vo_good_to_init(mvo_vo *v, mvo_vo_frame_info *info, int *good) {
+  VoFrame &c = *v->curr;
+  const VoFrame &r = *v->ref;
+  const int n = (int)c.inliers_matches_for_3d.size();
+  v->p1.resize((size_t)std::max(n, 1) * 2); v->p2.resize((size_t)std::max(n, 1) * 2);
+  for (int i = 0; i < n; ++i) {
+    const mvo_dmatch &m = c.inliers_matches_for_3d[i];
+    v->p1[2 * i] = r.xy[2 * m.query_idx]; v->p1[2 * i + 1] = r.xy[2 * m.query_idx + 1];
+    v->p2[2 * i] = c.xy[2 * m.train_idx]; v->p2[2 * i + 1] = c.xy[2 * m.train_idx + 1];
+  }
+  info->n_inliers = n;
+  const int na = (int)c.triangulation_angles.size();
+  return mvo_is_vo_good_to_init(v->p1.data(), v->p2.data(), n, na ? c.triangulation_angles.data() : nullptr, na, v->prm.min_inlier_matches,
+                                v->prm.min_pixel_dist, v->prm.min_median_triangulation_angle, good, &info->init_mean_pixel_dist,
+                                &info->init_median_angle);
+}
+
+// pushCurrPointsToMap_ (vo.cpp:528-576)
+void push_curr_points_to_map(mvo_vo *v) {
+  VoFrame &c = *v->curr;
+  VoFrame &r = *v->ref;
+  const double cam[3] = {c.T_w_c[3], c.T_w_c[7], c.T_w_c[11]};   // Frame::getCamCenter
+  const int n = (int)c.inliers_matches_for_3d.size();
+  for (int i = 0; i < n; ++i) {
+    const mvo_dmatch &dm = c.inliers_matches_for_3d[i];
+    const int pt_idx = dm.train_idx;
+    int map_point_id;
+    auto it = r.conn.find(dm.query_idx);
+    if (it != r.conn.end()) {
+      map_point_id = it->second.pt_map_idx;                      // triangulated before: reuse (vo.cpp:548-551)
+    } else {
+      VoMapPoint mp;
+      pre_translate(&c.inliers_pts3d[3 * (size_t)i], c.T_w_c, mp.pos);
+      double d[3] = {(double)mp.pos[0] - cam[0], (double)mp.pos[1] - cam[1], (double)mp.pos[2] - cam[2]};
+      const double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);        // basics::getNormalizedMat
+      for (int q = 0; q < 3; ++q) mp.norm[q] = d[q] / len;
+      memcpy(mp.desc, &c.desc[(size_t)pt_idx * 32], 32);
+      memcpy(mp.rgb, &c.colors[(size_t)pt_idx * 3], 3);
+      mp.id = v->point_factory_id++;
+      map_point_id = mp.id;
+      v->map_points[mp.id] = mp;                                 // Map::insertMapPoint
+    }
+    c.conn.insert({pt_idx, PtConn{dm.query_idx, map_point_id}});
+  }
+}
+
+// the test of Frame::isInFrame (frame.cpp:31-38) and getMappointsInCurrentView_ (vo.cpp:28-36)
+bool project_in_frame(const mvo_vo *v, const double *T_c_w, const float *pos, float *u, float *w) {
+  float pc[3];
+  pre_translate(pos, T_c_w, pc);
+  if (pc[2] < 0) return false;
+  *u = (float)(v->K[0] * pc[0] / pc[2] + v->K[2]);               // geometry::cam2pixel (camera.cpp:23-28)
+  *w = (float)(v->K[4] * pc[1] / pc[2] + v->K[5]);
+  return *u > 0 && *w > 0 && *u < (float)v->cols && *w < (float)v->rows;
+}
+
+// optimizeMap_ (vo.cpp:488-526)
+void optimize_map(mvo_vo *v) {
+  const VoFrame &c = *v->curr;
+  double Tcw[16];
+  inv_rigid44(c.T_w_c, Tcw);
+  const double cam[3] = {c.T_w_c[3], c.T_w_c[7], c.T_w_c[11]};
+  for (auto it = v->map_points.begin(); it != v->map_points.end();) {
+    const VoMapPoint &mp = it->second;
+    float u, w;
+    if (!project_in_frame(v, Tcw, mp.pos, &u, &w)) { it = v->map_points.erase(it); continue; }
+    const float match_ratio = float(mp.matched_times) / mp.visible_times;
+    if (match_ratio < v->map_point_erase_ratio) { it = v->map_points.erase(it); continue; }
+    double d[3] = {(double)mp.pos[0] - cam[0], (double)mp.pos[1] - cam[1], (double)mp.pos[2] - cam[2]};        // getViewAngle_ (vo.cpp:578-584)
+    const double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double angle = acos(d[0] / len * mp.norm[0] + d[1] / len * mp.norm[1] + d[2] / len * mp.norm[2]);
+    if (angle > M_PI / 4.) { it = v->map_points.erase(it); continue; }
+    ++it;
+  }
+  if (v->map_points.size() > 1000) v->map_point_erase_ratio += 0.05;
+  else v->map_point_erase_ratio = 0.1;
+}
+
+// poseEstimationPnP_ (vo.cpp:267-381)
+int pose_estimation_pnp(mvo_vo *v, mvo_vo_frame_info *info, bool *good) {
+  VoFrame &c = *v->curr;
+  // getMappointsInCurrentView_ (vo.cpp:16-49): container order
+  double Tcw[16];
+  inv_rigid44(c.T_w_c, Tcw);
+  const size_t nmap = v->map_points.size();
+  v->cand_id.clear(); v->cand_xy.clear(); v->cand_desc.clear();
+  v->cand_id.reserve(nmap); v->cand_xy.reserve(nmap * 2); v->cand_desc.reserve(nmap * 32);
+  for (auto &kv : v->map_points) {
+    VoMapPoint &mp = kv.second;
+    float u, w;
+    if (!project_in_frame(v, Tcw, mp.pos, &u, &w)) continue;
+    v->cand_id.push_back(mp.id);
+    v->cand_xy.push_back(u); v->cand_xy.push_back(w);
+    v->cand_desc.insert(v->cand_desc.end(), mp.desc, mp.desc + 32);
+    mp.visible_times++;
+  }
+  const int nc = (int)v->cand_id.size();
+  info->n_candidates = nc;
+  MVO_TRY(match_into(v, v->cand_desc.data(), v->cand_xy.data(), nc, c, v->prm.track.match_method, v->prm.track.match_radius, &c.matches_with_map));
+  const int nm = (int)c.matches_with_map.size();
+  info->n_matches = nm;
+  v->p3d.resize((size_t)std::max(nm, 1) * 3); v->p2d.resize((size_t)std::max(nm, 1) * 2);
+  for (int i = 0; i < nm; ++i) {                                 // vo.cpp:293-301
+    const mvo_dmatch &m = c.matches_with_map[i];
+    memcpy(&v->p3d[3 * (size_t)i], v->map_points[v->cand_id[(size_t)m.query_idx]].pos, 12);
+    v->p2d[2 * i] = c.xy[2 * m.train_idx]; v->p2d[2 * i + 1] = c.xy[2 * m.train_idx + 1];
+  }
+  bool ok = nm >= v->prm.track.min_pnp_points;
+  if (ok) {
+    double rvec[3], tvec[3];
+    v->inl.resize((size_t)nm);
+    int ni = nm;
+    const int rc = mvo_solve_pnp_ransac(v->ctx, v->p3d.data(), v->p2d.data(), nm, v->K, rvec, tvec, v->inl.data(), &ni);
+    if (rc == MVO_ERR_DEGENERATE) ok = false;
+    else if (rc != MVO_OK) return rc;
+    if (ok) {
+      std::vector<mvo_dmatch> kept((size_t)ni);
+      for (int i = 0; i < ni; ++i) {                             // vo.cpp:333-354
+        const mvo_dmatch &m = c.matches_with_map[(size_t)v->inl[i]];
+        kept[(size_t)i] = m;
+        VoMapPoint &mp = v->map_points[v->cand_id[(size_t)m.query_idx]];
+        mp.matched_times++;
+        c.conn[m.train_idx] = PtConn{-1, mp.id};
+      }
+      c.matches_with_map.swap(kept);
+      info->n_inliers = ni;
+      double R[9], Tc[16];
+      rodrigues_to_R(rvec, R);
+      rt_to_T(R, tvec, Tc);
+      inv_rigid44(Tc, c.T_w_c);                                  // vo.cpp:357
+      const double *a = c.T_w_c, *b = v->prev->T_w_c;            // vo.cpp:360-369
+      const double dx = a[3] - b[3], dy = a[7] - b[7], dz = a[11] - b[11];
+      if (sqrt(dx * dx + dy * dy + dz * dz) >= v->prm.track.max_dist_to_prev) ok = false;
+    }
+  }
+  if (!ok) memcpy(c.T_w_c, v->prev->T_w_c, sizeof c.T_w_c);      // vo.cpp:376-379
+  info->pnp_ok = ok;
+  memcpy(info->T_w_c_pnp, c.T_w_c, sizeof c.T_w_c);
+  *good = ok;
+  return MVO_OK;
+}
+
+// callBundleAdjustment_ (vo.cpp:384-478)
+int call_bundle_adjustment(mvo_vo *v, mvo_vo_frame_info *info) {
+  const mvo_track_params &tp = v->prm.track;
+  if (!tp.ba_enable) return MVO_OK;
+  const int total = (int)v->buff.size();
+  const int nba = std::min(tp.ba_window, total - 1);
+  std::vector<VoFrame *> sel;
+  v->ba_ef.clear(); v->ba_ep.clear(); v->ba_ob.clear(); v->ba_poses.clear(); v->ba_used.clear();
+  std::unordered_map<int, int> slot;                             // map point id -> vertex (um_pts_3d_in_prev_frames)
+  for (int b = total - 1; b >= total - nba; --b) {               // newest first (vo.cpp:417-419)
+    VoFrame &f = *v->buff[(size_t)b];
+    if ((int)f.conn.size() < 3) continue;                        // vo.cpp:423-426
+    const int fi = (int)sel.size();
+    sel.push_back(&f);
+    v->ba_poses.insert(v->ba_poses.end(), f.T_w_c, f.T_w_c + 16);
+    for (auto &kc : f.conn) {                                    // container order (vo.cpp:435-452)
+      const int mappt_idx = kc.second.pt_map_idx;
+      auto mit = v->map_points.find(mappt_idx);
+      if (mit == v->map_points.end()) continue;                  // point has been deleted
+      auto s = slot.find(mappt_idx);
+      int vid;
+      if (s == slot.end()) { vid = (int)v->ba_used.size(); slot[mappt_idx] = vid; v->ba_used.push_back(mappt_idx); }
+      else vid = s->second;
+      v->ba_ef.push_back(fi);
+      v->ba_ep.push_back(vid);
+      v->ba_ob.push_back(f.xy[2 * (size_t)kc.first]);
+      v->ba_ob.push_back(f.xy[2 * (size_t)kc.first + 1]);
+    }
+  }
+  if (sel.empty() || v->ba_ef.empty()) return MVO_OK;
+  v->ba_pts.resize(v->ba_used.size() * 3);
+  for (size_t k = 0; k < v->ba_used.size(); ++k) memcpy(&v->ba_pts[3 * k], v->map_points[v->ba_used[k]].pos, 12);
+  const int fix = tp.ba_fix_points ? 1 : 0;
+  const double saved_tol = v->ctx->prm.ba_step_tol;
+  v->ctx->prm.ba_step_tol = tp.ba_step_tol;
+  const int rc = mvo_bundle_adjustment(v->ctx, v->ba_poses.data(), (int)sel.size(), v->ba_pts.data(), (int)v->ba_used.size(), v->ba_ef.data(),
+                                       v->ba_ep.data(), v->ba_ob.data(), (int)v->ba_ef.size(), v->K, tp.information, fix, !fix, nullptr);
+  v->ctx->prm.ba_step_tol = saved_tol;
+  if (rc != MVO_OK) return rc;
+  for (size_t k = 0; k < sel.size(); ++k) memcpy(sel[k]->T_w_c, &v->ba_poses[16 * k], 16 * sizeof(double));
+  if (!fix)
+    for (size_t k = 0; k < v->ba_used.size(); ++k) memcpy(v->map_points[v->ba_used[k]].pos, &v->ba_pts[3 * k], 12);
+  info->ba_frames = (int)sel.size();
+  info->ba_edges = (int)v->ba_ef.size();
+  return MVO_OK;
+}
+
+// the keyframe branch of addFrame (vo_addFrame.cpp:93-124)
+int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
+  VoFrame &c = *v->curr;
+  const VoFrame &r = *v->ref;
+  MVO_TRY(match_into(v, r.desc.data(), r.xy.data(), r.n(), c, v->prm.track.match_method, v->prm.max_match_dist_triangulation, &c.matches_with_ref));
+  const int n = (int)c.matches_with_ref.size();
+  info->kf_matches = n;
+  if (n < 8) return MVO_OK;                                      // see the file header
+  v->p1.resize((size_t)n * 2); v->p2.resize((size_t)n * 2);
+  for (int i = 0; i < n; ++i) {
+    const mvo_dmatch &m = c.matches_with_ref[i];
+    v->p1[2 * i] = r.xy[2 * m.query_idx]; v->p1[2 * i + 1] = r.xy[2 * m.query_idx + 1];
+    v->p2[2 * i] = c.xy[2 * m.train_idx]; v->p2[2 * i + 1] = c.xy[2 * m.train_idx + 1];
+  }
+  // helperFindInlierMatchesByEpipolarCons (motion_estimation.cpp:180-196): the inliers of the essential-matrix RANSAC
+  double E[9], Re[9], te[3];
+  v->inl.resize((size_t)n);
+  int ni = n;
+  const int rc = mvo_esti_motion_by_essential(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.essential_threshold, E, Re, te, v->inl.data(), &ni);
+  if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
+  if (rc != MVO_OK) return rc;
+  c.inliers_matches_with_ref.resize((size_t)ni);
+  v->np1.resize((size_t)ni * 2); v->np2.resize((size_t)ni * 2);
+  for (int i = 0; i < ni; ++i) {
+    mvo_dmatch m = c.matches_with_ref[(size_t)v->inl[i]];
+    m.img_idx = -1;
+    c.inliers_matches_with_ref[(size_t)i] = m;
+    // pixel2CamNormPlane (camera.cpp:10-15)
+    v->np1[2 * i] = (float)(((double)r.xy[2 * m.query_idx] - v->K[2]) / v->K[0]); v->np1[2 * i + 1] = (float)(((double)r.xy[2 * m.query_idx + 1] - v->K[5]) / v->K[4]);
+    v->np2[2 * i] = (float)(((double)c.xy[2 * m.train_idx] - v->K[2]) / v->K[0]); v->np2[2 * i + 1] = (float)(((double)c.xy[2 * m.train_idx + 1] - v->K[5]) / v->K[4]);
+  }
+  // helperTriangulatePoints with the known motion getMotionFromFrame1to2(curr_, ref_) = curr^-1 * ref (vo_commons.cpp:9-15)
+  double Tci[16], T[16], R[9], t[3];
+  inv_rigid44(c.T_w_c, Tci);
+  mul44(Tci, r.T_w_c, T);
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[i * 4 + j]; t[i] = T[i * 4 + 3]; }
+  std::vector<int32_t> all((size_t)ni);
+  for (int i = 0; i < ni; ++i) all[(size_t)i] = i;
+  v->pts3d.resize((size_t)std::max(ni, 1) * 3);
+  if (ni > 0) MVO_TRY(mvo_do_triangulation(v->ctx, v->np1.data(), v->np2.data(), ni, R, t, all.data(), ni, v->pts3d.data()));
+  c.inliers_pts3d.resize((size_t)ni * 3);
+  for (int i = 0; i < ni; ++i) trans_coord(&v->pts3d[3 * (size_t)i], R, t, &c.inliers_pts3d[3 * (size_t)i]);
+  MVO_TRY(retain_good_triangulation(v));
+  info->kf_new_points = (int)c.inliers_matches_for_3d.size();
+  push_curr_points_to_map(v);
+  optimize_map(v);
+  add_keyframe(v, v->curr);
+  info->keyframe = 1;
+  return MVO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void mvo_vo_default_params(mvo_vo_params *p) {
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  mvo_default_track_params(&p->track);
+  p->match_method_init = 1;                  // feature_match_method_index_initialization (config.yaml)
+  p->max_match_dist_init = 100.f;            // max_matching_pixel_dist_in_initialization
+  p->max_match_dist_triangulation = 100.f;   // max_matching_pixel_dist_in_triangulation
+  p->essential_threshold = 1.0;              // findEssentialMat_threshold
+  p->init_calc_homography = 1;               // is_calc_homo = true (vo.cpp:68)
+  p->min_inlier_matches = 15;
+  p->min_triang_angle = 1.0;
+  p->max_ratio_angle_to_median = 20.0;       // max_ratio_between_max_angle_and_median_angle
+  p->min_pixel_dist = 50.0;
+  p->min_median_triangulation_angle = 2.0;
+  p->assumed_mean_depth_init = 0.8;          // assumed_mean_pts_depth_during_vo_init
+}
+
+int mvo_vo_create(mvo_ctx *ctx, const double *K, int rows, int cols, const mvo_vo_params *params, mvo_vo **out) {
+  if (!ctx || !out) return MVO_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!K || rows <= 0 || cols <= 0) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "vo: bad K / image size");
+  mvo_vo_params p;
+  if (params) p = *params; else mvo_vo_default_params(&p);
+  if (p.match_method_init < 1 || p.match_method_init > 3 || p.track.match_method < 1 || p.track.match_method > 3 || p.track.ba_window < 1 ||
+      p.track.ba_window > 16 || p.track.buffer_size < 2 || !(p.track.ba_step_tol >= 0))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "vo: bad parameters");
+  mvo_vo *v = new mvo_vo();
+  v->ctx = ctx;
+  v->prm = p;
+  memcpy(v->K, K, sizeof v->K);
+  v->rows = rows; v->cols = cols;
+  *out = v;
+  return MVO_OK;
+}
+
+void mvo_vo_destroy(mvo_vo *v) { delete v; }
+
+int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t stride, double *T_w_c_out, mvo_vo_frame_info *info_out) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  if (!image || (channels != 1 && channels != 3) || stride < (size_t)v->cols * channels)
+    return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: bad image arguments");
+  mvo_vo_frame_info info;
+  memset(&info, 0, sizeof info);
+  info.best_sol = -1;
+  FramePtr frame = std::make_shared<VoFrame>();
+  frame->id = v->frame_factory_id;
+  set_identity(frame->T_w_c);
+  MVO_TRY(extract(v, frame.get(), image, channels, stride));     // before any state changes: an extraction error leaves the VO untouched
+  v->frame_factory_id++;
+  v->buff.push_back(frame);                                      // pushFrameToBuff_ (vo.h:81-86)
+  if ((int)v->buff.size() > v->prm.track.buffer_size) v->buff.pop_front();
+  v->curr = frame;
+  info.frame_id = frame->id;
+  info.state_in = v->state;
+  info.n_keypoints = frame->n();
+  v->prev_ref = v->ref;
+  int rc = MVO_OK;
+  if (v->state == VO_BLANK) {                                    // vo_addFrame.cpp:29-34
+    v->state = VO_DOING_INITIALIZATION;
+    add_keyframe(v, frame);
+    info.keyframe = 1;
+  } else if (v->state == VO_DOING_INITIALIZATION) {              // :35-69
+    const VoFrame &r = *v->ref;
+    rc = match_into(v, r.desc.data(), r.xy.data(), r.n(), *frame, v->prm.match_method_init, v->prm.max_match_dist_init, &frame->matches_with_ref);
+    int usable = 0, good = 0;
+    if (rc == MVO_OK) { info.n_matches = (int)frame->matches_with_ref.size(); rc = estimate_motion_and_3d_points(v, &info, &usable); }
+    if (rc == MVO_OK && usable) rc = is_vo_good_to_init(v, &info, &good);
+    if (rc == MVO_OK && good) {
+      push_curr_points_to_map(v);
+      add_keyframe(v, frame);
+      v->state = VO_DOING_TRACKING;
+      info.keyframe = 1;
+    } else {
+      memcpy(frame->T_w_c, v->ref->T_w_c, sizeof frame->T_w_c);  // :64-68
+    }
+  } else if (v->state == VO_DOING_TRACKING) {                    // :70-125
+    memcpy(frame->T_w_c, v->ref->T_w_c, sizeof frame->T_w_c);
+    bool pnp_good = false;
+    rc = pose_estimation_pnp(v, &info, &pnp_good);
+    if (rc == MVO_OK && pnp_good) {
+      rc = call_bundle_adjustment(v, &info);
+      int large = 0;
+      if (rc == MVO_OK) rc = mvo_check_large_move(frame->T_w_c, v->ref->T_w_c, v->prm.track.min_dist_keyframe, &large, nullptr, nullptr);
+      if (rc == MVO_OK && large) rc = insert_keyframe(v, &info);
+    }
+  }
+  v->prev = frame;                                               // :141
+  info.state_out = v->state;
+  info.map_points = (int)v->map_points.size();
+  if (T_w_c_out) memcpy(T_w_c_out, frame->T_w_c, 16 * sizeof(double));
+  if (info_out) *info_out = info;
+  return rc;
+}
+
+int mvo_vo_is_initialized(const mvo_vo *v) { return v && v->state == VO_DOING_TRACKING; }      // vo.cpp:174-177
+int mvo_vo_map_size(const mvo_vo *v) { return v ? (int)v->map_points.size() : 0; }
+int mvo_vo_num_keyframes(const mvo_vo *v) { return v ? (int)v->keyframes.size() : 0; }
+
+int mvo_vo_get_map(const mvo_vo *v, int32_t *ids, float *pts3d, uint8_t *desc, uint8_t *rgb, int cap, int *n) {
+  if (!v || !n) return MVO_ERR_INVALID_ARG;
+  *n = (int)v->map_points.size();
+  if (cap < *n) return MVO_ERR_CAPACITY;
+  int k = 0;
+  for (auto &kv : v->map_points) {                               // container order, as getMappointsInCurrentView_ walks it
+    const VoMapPoint &mp = kv.second;
+    if (ids) ids[k] = mp.id;
+    if (pts3d) memcpy(pts3d + 3 * (size_t)k, mp.pos, 12);
+    if (desc) memcpy(desc + 32 * (size_t)k, mp.desc, 32);
+    if (rgb) memcpy(rgb + 3 * (size_t)k, mp.rgb, 3);
+    ++k;
+  }
+  return MVO_OK;
+}
+
+int mvo_vo_frame_pose(const mvo_vo *v, int k, double *T_w_c) {
+  if (!v || !T_w_c || k < 0 || k >= (int)v->buff.size()) return MVO_ERR_INVALID_ARG;
+  memcpy(T_w_c, v->buff[v->buff.size() - 1 - (size_t)k]->T_w_c, 16 * sizeof(double));
+  return MVO_OK;
+}
+
+}  // extern "C"

@@ -59,6 +59,23 @@ class TwoViewSolutions(C.Structure):
                 ("E", C.c_double * 9), ("H", C.c_double * 9), ("score_e", C.c_double), ("score_h", C.c_double), ("ratio", C.c_double)]
 
 
+class VoParams(C.Structure):
+    _fields_ = [("track", TrackParams), ("match_method_init", C.c_int32), ("max_match_dist_init", C.c_float),
+                ("max_match_dist_triangulation", C.c_float), ("init_calc_homography", C.c_int32),
+                ("min_inlier_matches", C.c_int32), ("pad", C.c_int32), ("essential_threshold", C.c_double),
+                ("min_triang_angle", C.c_double), ("max_ratio_angle_to_median", C.c_double), ("min_pixel_dist", C.c_double),
+                ("min_median_triangulation_angle", C.c_double), ("assumed_mean_depth_init", C.c_double)]
+
+
+class VoFrameInfo(C.Structure):
+    _fields_ = [("frame_id", C.c_int32), ("state_in", C.c_int32), ("state_out", C.c_int32), ("keyframe", C.c_int32),
+                ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_candidates", C.c_int32), ("n_inliers", C.c_int32),
+                ("pnp_ok", C.c_int32), ("ba_frames", C.c_int32), ("ba_edges", C.c_int32), ("best_sol", C.c_int32),
+                ("map_points", C.c_int32), ("kf_matches", C.c_int32), ("kf_new_points", C.c_int32), ("pad", C.c_int32),
+                ("score_e", C.c_double), ("score_h", C.c_double), ("eh_ratio", C.c_double),
+                ("init_mean_pixel_dist", C.c_double), ("init_median_angle", C.c_double), ("T_w_c_pnp", C.c_double * 16)]
+
+
 class MvoError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
@@ -122,6 +139,15 @@ SIGNATURES = {
     "mvo_normalize_init_depth": (_i, [_vp, _i, _vp, C.c_double, C.POINTER(C.c_double)]),
     "mvo_is_vo_good_to_init": (_i, [_vp, _vp, _i, _vp, _i, _i, C.c_double, C.c_double, _pi, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mvo_check_large_move": (_i, [_vp, _vp, C.c_double, _pi, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mvo_vo_default_params": (None, [C.POINTER(VoParams)]),
+    "mvo_vo_create": (_i, [_vp, _vp, _i, _i, C.POINTER(VoParams), C.POINTER(_vp)]),
+    "mvo_vo_destroy": (None, [_vp]),
+    "mvo_vo_add_frame": (_i, [_vp, _vp, _i, _sz, _vp, C.POINTER(VoFrameInfo)]),
+    "mvo_vo_is_initialized": (_i, [_vp]),
+    "mvo_vo_map_size": (_i, [_vp]),
+    "mvo_vo_num_keyframes": (_i, [_vp]),
+    "mvo_vo_get_map": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _pi]),
+    "mvo_vo_frame_pose": (_i, [_vp, _i, _vp]),
     "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
     "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
     "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
@@ -132,6 +158,7 @@ SIGNATURES = {
     "mvo_config_get_int": (_i, [_vp, C.c_char_p, _pi]),
     "mvo_config_get_bool": (_i, [_vp, C.c_char_p, _pi]),
     "mvo_config_apply": (_i, [_vp, C.POINTER(Params), C.POINTER(TrackParams), _vp]),
+    "mvo_config_apply_vo": (_i, [_vp, C.POINTER(VoParams)]),
 }
 
 _lib = None
@@ -397,6 +424,68 @@ class Context:
         self._chk(self.lib.mvo_optimize_single_frame(self.h, _ptr(pose), _ptr(pts), _ptr(ob), len(pts), _ptr(K),
                                                       int(fix_points), int(update_points)))
         return pose.reshape(4, 4), pts
+
+
+class VisualOdometry:
+    """mvo_vo: the whole addFrame state machine (initialisation, tracking, keyframes, map maintenance)."""
+
+    def __init__(self, ctx: "Context", K, rows, cols, track=None, **overrides):
+        self.ctx, self.lib = ctx, ctx.lib
+        p = VoParams()
+        self.lib.mvo_vo_default_params(C.byref(p))
+        for k, v in (track or {}).items():
+            if k == "information":
+                for i, x in enumerate(np.asarray(v, np.float64).ravel()):
+                    p.track.information[i] = float(x)
+            else:
+                if not hasattr(p.track, k):
+                    raise AttributeError(k)
+                setattr(p.track, k, v)
+        for k, v in overrides.items():
+            if not hasattr(p, k) or k == "track":
+                raise AttributeError(k)
+            setattr(p, k, v)
+        self.params = p
+        K = _c(K, np.float64)
+        h = C.c_void_p()
+        ctx._chk(self.lib.mvo_vo_create(ctx.h, _ptr(K), rows, cols, C.byref(p), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mvo_vo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_frame(self, image):
+        img = np.ascontiguousarray(image, np.uint8)
+        channels = 1 if img.ndim == 2 else img.shape[2]
+        T, info = np.zeros(16), VoFrameInfo()
+        self.ctx._chk(self.lib.mvo_vo_add_frame(self.h, _ptr(img), channels, img.shape[1] * channels, _ptr(T), C.byref(info)))
+        return T.reshape(4, 4), info
+
+    def is_initialized(self):
+        return bool(self.lib.mvo_vo_is_initialized(self.h))
+
+    def num_keyframes(self):
+        return self.lib.mvo_vo_num_keyframes(self.h)
+
+    def get_map(self):
+        n = C.c_int(self.lib.mvo_vo_map_size(self.h))
+        cap = max(n.value, 1)
+        ids, pts, desc, rgb = np.zeros(cap, np.int32), np.zeros((cap, 3), np.float32), np.zeros((cap, 32), np.uint8), np.zeros((cap, 3), np.uint8)
+        self.ctx._chk(self.lib.mvo_vo_get_map(self.h, _ptr(ids), _ptr(pts), _ptr(desc), _ptr(rgb), cap, C.byref(n)))
+        return ids[: n.value], pts[: n.value], desc[: n.value], rgb[: n.value]
+
+    def frame_pose(self, k=0):
+        T = np.zeros(16)
+        self.ctx._chk(self.lib.mvo_vo_frame_pose(self.h, k, _ptr(T)))
+        return T.reshape(4, 4)
 
 
 class Tracker:

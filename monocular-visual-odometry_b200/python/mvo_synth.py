@@ -169,3 +169,72 @@ def random_descriptors(seed, n, dup_every=0):
         for i in range(dup_every, n, dup_every):
             d[i] = d[i - dup_every]      # exact duplicates -> distance ties
     return d
+
+
+# ---- a 3-D scene: textured box room seen from a moving camera (two-view initialisation needs depth variation) ----
+_ROOM = dict(half_w=1.7, top=-1.1, bottom=1.0, back=6.0, z0=-1.5, ppm=120.0)
+
+
+def _room_planes(seed):
+    """(normal, offset, (axis_u, u0, axis_v, v0), texture) of the five faces; a point X is on a face when n.X = h."""
+    r = _ROOM
+    depth = r["back"] - r["z0"]
+    size = lambda a, b: (int(np.ceil(a * r["ppm"])) + 2, int(np.ceil(b * r["ppm"])) + 2)       # (width, height) in texels
+    faces = [
+        ((0, 0, 1.0), r["back"], (0, -r["half_w"], 1, r["top"]), size(2 * r["half_w"], r["bottom"] - r["top"])),     # back wall: (x, y)
+        ((0, 1.0, 0), r["bottom"], (0, -r["half_w"], 2, r["z0"]), size(2 * r["half_w"], depth)),                     # floor: (x, z)
+        ((0, 1.0, 0), r["top"], (0, -r["half_w"], 2, r["z0"]), size(2 * r["half_w"], depth)),                        # ceiling
+        ((1.0, 0, 0), -r["half_w"], (2, r["z0"], 1, r["top"]), size(depth, r["bottom"] - r["top"])),                 # left wall: (z, y)
+        ((1.0, 0, 0), r["half_w"], (2, r["z0"], 1, r["top"]), size(depth, r["bottom"] - r["top"])),                  # right wall
+    ]
+    out = []
+    for i, (n, h, uv, (tw, th)) in enumerate(faces):
+        tex = rect_scene(seed * 16 + i + 1, tw, th, n_rect=int(tw * th / 200))
+        out.append((np.array(n, np.float64), float(h), uv, tex))
+    return out
+
+
+def render_room(T_w_c, planes, K=K_DEFAULT, width=W, height=H):
+    """Ray-cast the box room: nearest face along every pixel ray, bilinear texture lookup.  T_w_c: camera->world."""
+    T_w_c = np.asarray(T_w_c, np.float64)
+    ys, xs = np.mgrid[0:height, 0:width]
+    d = np.linalg.inv(K) @ np.stack([xs.ravel(), ys.ravel(), np.ones(width * height)]).astype(np.float64)
+    d = T_w_c[:3, :3] @ d
+    o = T_w_c[:3, 3]
+    best_s = np.full(width * height, np.inf)
+    val = np.full(width * height, 128.0)
+    ppm = _ROOM["ppm"]
+    for n, h, (au, u0, av, v0), tex in planes:
+        nd = n @ d
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = (h - n @ o) / nd
+            X = o[:, None] + s * d
+        tu, tv = (X[au] - u0) * ppm, (X[av] - v0) * ppm
+        th, tw = tex.shape
+        ok = np.isfinite(s) & (s > 1e-6) & (s < best_s) & (tu >= 0) & (tv >= 0) & (tu < tw - 1) & (tv < th - 1)
+        tu, tv = np.where(ok, tu, 0), np.where(ok, tv, 0)
+        x0, y0 = np.floor(tu).astype(np.int64), np.floor(tv).astype(np.int64)
+        fx, fy = tu - x0, tv - y0
+        t = tex.astype(np.float64)
+        v = t[y0, x0] * (1 - fx) * (1 - fy) + t[y0, x0 + 1] * fx * (1 - fy) + t[y0 + 1, x0] * (1 - fx) * fy + t[y0 + 1, x0 + 1] * fx * fy
+        val = np.where(ok, v, val)
+        best_s = np.where(ok, s, best_s)
+    return np.clip(np.rint(val), 0, 255).astype(np.uint8).reshape(height, width)
+
+
+def room_sequence(seed=0, n_frames=30, step=0.05, K=K_DEFAULT):
+    """Frames of the box room from a camera that moves mostly sideways with a slow rotation.
+
+    Returns (frames[n] uint8 HxW, T_w_c[n] 4x4 camera->world ground truth).  Frame 0 is taken from the origin."""
+    planes = _room_planes(seed)
+    rng = np.random.default_rng(2000 + seed)
+    drift_r = rng.normal(0, 1, 3) * 0.003
+    drift_t = np.array([step, -0.15 * step, 0.3 * step])
+    frames, poses = [], []
+    for i in range(n_frames):
+        T = np.eye(4)
+        T[:3, :3] = rodrigues(drift_r * i)
+        T[:3, 3] = drift_t * i
+        frames.append(render_room(T, planes, K))
+        poses.append(T)
+    return frames, poses

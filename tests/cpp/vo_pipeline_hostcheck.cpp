@@ -1,0 +1,77 @@
+// TEST INFRASTRUCTURE (CPU tier): the VO state machine (csrc/vo_pipeline.cpp) compiled a second time into its own
+// shared object in which the GPU stages it calls are replaced by forwarders to function pointers the test installs
+// (tests/test_vo_pipeline_host.py points them at the oracle stages).  This checks the HOST logic of the state machine —
+// containers, bookkeeping, index plumbing — frame by frame against oracle/vo_pipeline_oracle.py without a GPU.
+// Nothing here is part of libmvo.so; the product has no such indirection.
+#include <stdarg.h>
+#include "mvo_internal.h"
+
+int mvo_fail(mvo_ctx *ctx, int code, const char *fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+extern "C" {
+
+struct HostcheckStages {
+  int (*orb_extract)(const uint8_t *image, int rows, int cols, int channels, size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);
+  int (*match_features)(const uint8_t *d1, int n1, const uint8_t *d2, int n2, int method, const float *xy1, const float *xy2, float radius,
+                        mvo_dmatch *out, int *n_out);
+  int (*estimate_relative_poses)(const float *p1, const float *p2, int n, const double *K, int calc_homo, int cam2_to_cam1,
+                                 mvo_two_view_solutions *sol, int32_t *inliers, float *pts3d);
+  int (*esti_motion_by_essential)(const float *p1, const float *p2, int n, const double *K, double threshold, double *E, double *R, double *t,
+                                  int32_t *inliers, int *n_inliers);
+  int (*do_triangulation)(const float *np1, const float *np2, int n, const double *R, const double *t, const int32_t *inliers, int n_inliers,
+                          float *pts3d);
+  int (*solve_pnp_ransac)(const float *pts3d, const float *pts2d, int n, const double *K, double *rvec, double *tvec, int32_t *inliers,
+                          int *n_inliers);
+  int (*bundle_adjustment)(double *poses, int n_frames, float *points, int n_points, const int32_t *ef, const int32_t *ep, const float *obs,
+                           int n_edges, const double *K, const double *information, int fix_points, int update_points);
+};
+static HostcheckStages g_stages;
+
+void hostcheck_set_stages(const HostcheckStages *s) { g_stages = *s; }
+mvo_ctx *hostcheck_ctx_new(int max_keypoints) {
+  mvo_ctx *c = new mvo_ctx();
+  mvo_default_params(&c->prm);
+  c->prm.max_keypoints = max_keypoints;
+  return c;
+}
+void hostcheck_ctx_free(mvo_ctx *c) { delete c; }
+
+int mvo_orb_extract(mvo_ctx *, const uint8_t *image, int rows, int cols, int channels, size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
+  return g_stages.orb_extract(image, rows, cols, channels, stride, kpts, n_kpts, desc);
+}
+int mvo_match_features(mvo_ctx *, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int method_index, const float *xy1, const float *xy2,
+                       float radius, mvo_dmatch *out, int *n_out) {
+  return g_stages.match_features(d1, n1, d2, n2, method_index, xy1, xy2, radius, out, n_out);
+}
+int mvo_estimate_relative_poses(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, int calc_homo, int cam2_to_cam1,
+                                mvo_two_view_solutions *sol, int32_t *inliers, float *pts3d) {
+  return g_stages.estimate_relative_poses(p1, p2, n, K, calc_homo, cam2_to_cam1, sol, inliers, pts3d);
+}
+int mvo_esti_motion_by_essential(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, double threshold, double *E, double *R,
+                                 double *t, int32_t *inliers, int *n_inliers) {
+  return g_stages.esti_motion_by_essential(p1, p2, n, K, threshold, E, R, t, inliers, n_inliers);
+}
+int mvo_do_triangulation(mvo_ctx *, const float *np1, const float *np2, int n, const double *R, const double *t, const int32_t *inliers,
+                         int n_inliers, float *pts3d) {
+  return g_stages.do_triangulation(np1, np2, n, R, t, inliers, n_inliers, pts3d);
+}
+int mvo_solve_pnp_ransac(mvo_ctx *, const float *pts3d, const float *pts2d, int n, const double *K, double *rvec, double *tvec, int32_t *inliers,
+                         int *n_inliers) {
+  return g_stages.solve_pnp_ransac(pts3d, pts2d, n, K, rvec, tvec, inliers, n_inliers);
+}
+int mvo_bundle_adjustment(mvo_ctx *, double *poses, int n_frames, float *points, int n_points, const int32_t *ef, const int32_t *ep,
+                          const float *obs, int n_edges, const double *K, const double *information, int fix_points, int update_points, double *) {
+  return g_stages.bundle_adjustment(poses, n_frames, points, n_points, ef, ep, obs, n_edges, K, information, fix_points, update_points);
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+"""GPU run of the whole VO state machine (mvo_vo_*, csrc/vo_pipeline.cpp; reference src/vo/vo_addFrame.cpp:10-142) on a
+synthetic 3-D sequence, next to the oracle pipeline (oracle/vo_pipeline_oracle.py: the same control flow over cv2 and the
+CPU restatements).
+
+The host logic of the state machine is checked frame by frame on the CPU tier (tests/test_vo_pipeline_host.py).  What is
+left for the hardware is the assembly with the real stages.  The two RANSACs draw different samples than OpenCV's, so the
+two pipelines are compared through what the reference's own acceptance would look at: both initialise, both keep tracking
+and inserting keyframes, and the trajectory error against the ground truth (after the similarity alignment a monocular
+trajectory needs) of the GPU pipeline is within 1e-4 + 25 % of the oracle's, or better.
+
+Written after the round-1 GPU budget was spent, so — like tests/test_homography_gpu.py — each check runs in a CHILD process
+and is xfail(strict=False): XPASS = works as written."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+from conftest import have_cv2
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")]
+
+CHILD = r'''
+import sys
+import numpy as np
+sys.path.insert(0, r"{root}"); sys.path.insert(0, r"{root}/monocular-visual-odometry_b200/python")
+import mvo_b200, mvo_synth
+from oracle import vo_pipeline_oracle as vp
+K = mvo_synth.K_DEFAULT
+HOMO = {homo}
+frames, truth = mvo_synth.room_sequence(0, 26)
+ctx = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
+vo = mvo_b200.VisualOdometry(ctx, K, 480, 640, init_calc_homography=HOMO)
+cpu = vp.CpuVo(K, 480, 640, max_number_of_keypoints=2000, ba_iterations=10, init_calc_homography=bool(HOMO))
+Tg, Tc, ig, ic = [], [], [], []
+for f in frames:
+    img = mvo_synth.gray_to_bgr(f)
+    T, info = vo.add_frame(img)
+    Tg.append(T); ig.append(info)
+    T2, info2 = cpu.add_frame(img)
+    Tc.append(T2); ic.append(info2)
+    assert info.n_keypoints == info2["n_keypoints"]                       # extraction is bit-exact
+sg = [i.state_out for i in ig]; sc = [i["state_out"] for i in ic]
+assert sg[0] == 1 and sg[-1] == 2 and sc[-1] == 2, (sg, sc)
+g0, c0 = sg.index(2), sc.index(2)
+print("initialised at frame", g0, "(oracle:", c0, ") map", ig[g0].map_points, "(oracle:", ic[c0]["map_points"], ")")
+assert abs(g0 - c0) <= 2                                                   # same acceptance tests, different RANSAC draws
+assert ig[g0].best_sol == 0 and ig[g0].map_points >= 100
+later = ig[g0 + 1:]
+assert all(i.pnp_ok == 1 for i in later), [i.pnp_ok for i in later]
+assert all(i.ba_frames >= 1 for i in later)
+assert sum(i.keyframe for i in later) >= 2 and vo.num_keyframes() == 2 + sum(i.keyframe for i in later)
+assert all(i.n_inliers >= 100 for i in later), [i.n_inliers for i in later]
+ids, pts, desc, rgb = vo.get_map()
+assert len(ids) == ig[-1].map_points == len(set(ids.tolist())) and np.isfinite(pts).all()
+s = max(g0, c0)
+eg, scale_g = vp.trajectory_error(Tg[s:], truth[s:])
+ec, scale_c = vp.trajectory_error(Tc[s:], truth[s:])
+path = float(np.linalg.norm(truth[-1][:3, 3] - truth[s][:3, 3]))
+print("trajectory RMS error: gpu %.5f  oracle %.5f  (path %.3f, scales %.3f / %.3f)" % (eg, ec, path, scale_g, scale_c))
+assert eg < 0.02 * path
+assert eg <= 1.25 * ec + 1e-4, (eg, ec)
+# the buffered poses carry the BA updates: the newest one is the pose just returned
+assert np.array_equal(vo.frame_pose(0), Tg[-1])
+print("vo pipeline child ok")
+'''
+
+
+def _run(homo):
+    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT), homo=homo)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "vo pipeline child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+    print(r.stdout[-600:])
+
+
+@pytest.mark.xfail(strict=False, reason="state machine assembled after the round-1 GPU budget was spent: first hardware run")
+def test_vo_pipeline_essential_only_initialisation(built):
+    _run(0)
+
+
+@pytest.mark.xfail(strict=False, reason="depends on the homography kernels, which have not run on hardware yet")
+def test_vo_pipeline_reference_configuration(built):
+    _run(1)

@@ -1,0 +1,262 @@
+"""Host logic of the VO state machine (csrc/vo_pipeline.cpp) on the CPU tier: the file is compiled a second time with
+the GPU stages replaced by forwarders (tests/cpp/vo_pipeline_hostcheck.cpp) that this test points at the oracle stages
+(cv2 + oracle/), and the result is compared frame by frame with oracle/vo_pipeline_oracle.py — the restatement of
+reference src/vo/vo_addFrame.cpp:10-142 and src/vo/vo.cpp — on a synthetic 3-D sequence.  Same stages on both sides, so
+every difference is a difference in the state machine: container order, bookkeeping, index plumbing."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import mvo_synth
+from conftest import have_cv2
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.skipif(not have_cv2(), reason="cv2 (the reference's third-party code) is needed for the oracle stages")
+K = mvo_synth.K_DEFAULT
+ROWS, COLS = 480, 640
+# identical stages on both sides; what differs is double rounding in the 4x4 algebra (rigid inverse vs numpy's LU inverse),
+# which the 10-iteration LM of the BA stage carries along: observed <= 2e-9 over 22 frames
+POSE_TOL = 1e-7
+
+
+def _arr(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype).reshape(shape)
+
+
+class Stages:
+    """The numeric stages of the oracle pipeline behind the C signatures of the product's entry points."""
+
+    def __init__(self, helper, ba_iterations):
+        import mvo_b200
+        from oracle import epipolar_oracle, motion_oracle, oracle_lib
+        self.h, self.epi, self.mot, self.ol, self.mvo = helper, epipolar_oracle, motion_oracle, oracle_lib, mvo_b200
+        self.ba_iterations = ba_iterations
+        vp, i, sz, f, d = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_double
+        self.protos = [
+            (C.CFUNCTYPE(i, vp, i, i, i, sz, vp, vp, vp), self.orb_extract),
+            (C.CFUNCTYPE(i, vp, i, vp, i, i, vp, vp, f, vp, vp), self.match_features),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, i, i, vp, vp, vp), self.estimate_relative_poses),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, d, vp, vp, vp, vp, vp), self.esti_motion_by_essential),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, vp, vp, i, vp), self.do_triangulation),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, vp, vp, vp, vp), self.solve_pnp_ransac),
+            (C.CFUNCTYPE(i, vp, i, vp, i, vp, vp, vp, i, vp, vp, i, i), self.bundle_adjustment),
+        ]
+        self.cbs = [proto(fn) for proto, fn in self.protos]          # keep the callbacks alive
+        self.table = (C.c_void_p * len(self.cbs))(*[C.cast(cb, C.c_void_p) for cb in self.cbs])
+
+    def orb_extract(self, image, rows, cols, channels, stride, kpts, n_kpts, desc):
+        from oracle.vo_pipeline_oracle import Frame
+        img = _arr(image, (rows, stride), np.uint8)[:, : cols * channels].reshape(rows, cols, channels)
+        fr = Frame(0, np.ascontiguousarray(img if channels == 3 else img[:, :, 0]))
+        self.h._extract(fr)
+        cap = C.c_int.from_address(n_kpts)
+        n = len(fr.kp)
+        assert n <= cap.value
+        _arr(kpts, (n,), self.mvo.KEYPOINT_DTYPE)[:] = fr.kp
+        _arr(desc, (n, 32), np.uint8)[:] = fr.desc
+        cap.value = n
+        return 0
+
+    def match_features(self, d1, n1, d2, n2, method, xy1, xy2, radius, out, n_out):
+        m = self.h._match(_arr(d1, (n1, 32), np.uint8).copy(), _arr(d2, (n2, 32), np.uint8).copy(), method,
+                          _arr(xy1, (n1, 2), np.float32).copy(), _arr(xy2, (n2, 2), np.float32).copy(), radius)
+        _arr(out, (len(m),), self.mvo.DMATCH_DTYPE)[:] = m
+        C.c_int.from_address(n_out).value = len(m)
+        return 0
+
+    def estimate_relative_poses(self, p1, p2, n, Kp, calc_homo, cam2_to_cam1, sol, inliers, pts3d):
+        from oracle.vo_pipeline_oracle import _norm_plane
+        assert cam2_to_cam1 == 1
+        a, b = _arr(p1, (n, 2), np.float32).copy(), _arr(p2, (n, 2), np.float32).copy()
+        Kc = _arr(Kp, (3, 3), np.float64).copy()
+        na, nb = _norm_plane(a, Kc), _norm_plane(b, Kc)
+        E, R_e, t_e, inl_e = self.epi.esti_motion_by_essential(a, b, Kc, 0.999, 1.0)
+        Rs, ts, ns, inls = [R_e], [t_e], [np.zeros(3)], [inl_e]
+        H, inl_h = np.zeros((3, 3)), np.zeros(0, np.int32)
+        if calc_homo:
+            H, Rh, th, nh, inl_h = self.epi.esti_motion_by_homography(a, b, Kc, 3.0)
+            for s in self.epi.remove_wrong_rt_of_homography(na, nb, inl_h, Rh, th, nh):
+                Rs.append(Rh[s]); ts.append(th[s]); ns.append(nh[s]); inls.append(inl_h)
+        S = self.mvo.TwoViewSolutions.from_address(sol)
+        C.memset(sol, 0, C.sizeof(S))
+        S.num_solutions = len(Rs)
+        inl_out, pts_out = _arr(inliers, (5, n), np.int32), _arr(pts3d, (5, n, 3), np.float32)
+        for s in range(len(Rs)):
+            S.n_inliers[s] = len(inls[s])
+            for q, x in enumerate(np.asarray(Rs[s], np.float64).ravel()):
+                S.R[s][q] = x
+            for q in range(3):
+                S.t[s][q] = float(np.asarray(ts[s]).ravel()[q])
+                S.normal[s][q] = float(np.asarray(ns[s]).ravel()[q])
+            inl_out[s, : len(inls[s])] = inls[s]
+            pts_out[s, : len(inls[s])] = self.epi.do_triangulation(na, nb, Rs[s], ts[s], inls[s])
+        for q, x in enumerate(E.ravel()):
+            S.E[q] = x
+        for q, x in enumerate(np.asarray(H, np.float64).ravel()):
+            S.H[q] = x
+        best, ratio = 0, 0.0
+        if calc_homo:
+            S.score_e, _ = self.mot.check_essential_score(E, Kc, a, b, inl_e)
+            S.score_h, _ = self.mot.check_homography_score(H, a, b, inl_h)
+            best, ratio = self.mot.choose_e_or_h(S.score_e, S.score_h, np.array(ns[1:]).reshape(-1, 3))
+        S.best, S.ratio = best, ratio
+        return 0
+
+    def esti_motion_by_essential(self, p1, p2, n, Kp, threshold, E, R, t, inliers, n_inliers):
+        a, b = _arr(p1, (n, 2), np.float32).copy(), _arr(p2, (n, 2), np.float32).copy()
+        Em, Rm, tm, inl = self.epi.esti_motion_by_essential(a, b, _arr(Kp, (3, 3), np.float64).copy(), 0.999, threshold)
+        _arr(E, (3, 3), np.float64)[:] = Em
+        _arr(R, (3, 3), np.float64)[:] = Rm
+        _arr(t, (3,), np.float64)[:] = tm
+        _arr(inliers, (len(inl),), np.int32)[:] = inl
+        C.c_int.from_address(n_inliers).value = len(inl)
+        return 0
+
+    def do_triangulation(self, np1, np2, n, R, t, inliers, n_inliers, pts3d):
+        X = self.epi.do_triangulation(_arr(np1, (n, 2), np.float32).copy(), _arr(np2, (n, 2), np.float32).copy(), _arr(R, (3, 3), np.float64).copy(),
+                                      _arr(t, (3,), np.float64).copy(), _arr(inliers, (n_inliers,), np.int32).copy())
+        _arr(pts3d, (n_inliers, 3), np.float32)[:] = X
+        return 0
+
+    def solve_pnp_ransac(self, pts3d, pts2d, n, Kp, rvec, tvec, inliers, n_inliers):
+        import cv2
+        ok, rv, tv, inl = cv2.solvePnPRansac(_arr(pts3d, (n, 3), np.float32).copy(), _arr(pts2d, (n, 2), np.float32).copy(),
+                                             _arr(Kp, (3, 3), np.float64).copy(), None, None, None, False, 100, 2.0, 0.999)
+        if not ok or inl is None:
+            return -6                                                 # MVO_ERR_DEGENERATE
+        inl = inl.ravel()
+        _arr(rvec, (3,), np.float64)[:] = rv.ravel()
+        _arr(tvec, (3,), np.float64)[:] = tv.ravel()
+        _arr(inliers, (len(inl),), np.int32)[:] = inl
+        C.c_int.from_address(n_inliers).value = len(inl)
+        return 0
+
+    def bundle_adjustment(self, poses, nf, points, npts, ef, ep, obs, ne, Kp, info, fix_points, update_points):
+        P = _arr(poses, (nf, 16), np.float64)
+        new_poses, _, _ = self.ol.bundle_adjustment(P.copy(), _arr(points, (npts, 3), np.float32).copy(), _arr(ef, (ne,), np.int32).copy(),
+                                                    _arr(ep, (ne,), np.int32).copy(), _arr(obs, (ne, 2), np.float32).copy(),
+                                                    _arr(Kp, (3, 3), np.float64).copy(), _arr(info, (2, 2), np.float64).copy(),
+                                                    fix_points=bool(fix_points), update_points=bool(update_points), iterations=self.ba_iterations)
+        P[:] = new_poses.reshape(nf, 16)
+        return 0
+
+
+@pytest.fixture(scope="module")
+def hostcheck(built, tmp_path_factory):
+    so = tmp_path_factory.mktemp("vohost") / "libvo_hostcheck.so"
+    pkg = ROOT / "monocular-visual-odometry_b200"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "include"), "-I", str(pkg / "csrc"),
+                    "-I", "/usr/local/cuda/include", str(ROOT / "tests" / "cpp" / "vo_pipeline_hostcheck.cpp"), str(pkg / "csrc" / "vo_pipeline.cpp"),
+                    "-L", str(pkg), "-lmvo", "-Wl,-Bsymbolic", f"-Wl,-rpath,{pkg}", "-o", str(so)], check=True)
+    import mvo_b200
+    lib = C.CDLL(str(so))
+    lib.hostcheck_ctx_new.restype = C.c_void_p
+    lib.hostcheck_ctx_new.argtypes = [C.c_int]
+    lib.hostcheck_ctx_free.argtypes = [C.c_void_p]
+    lib.hostcheck_set_stages.argtypes = [C.c_void_p]
+    for name in ("mvo_vo_default_params", "mvo_vo_create", "mvo_vo_destroy", "mvo_vo_add_frame", "mvo_vo_is_initialized", "mvo_vo_map_size",
+                 "mvo_vo_num_keyframes", "mvo_vo_get_map", "mvo_vo_frame_pose"):
+        res, args = mvo_b200.SIGNATURES[name]
+        getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
+    return lib
+
+
+def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
+    import mvo_b200
+    from oracle import vo_pipeline_oracle as vp
+    oracle = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=max_kpts, ba_iterations=ba_iterations, **vo_cfg)
+    helper = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=max_kpts)
+    stages = Stages(helper, ba_iterations)
+    hostcheck.hostcheck_set_stages(C.cast(stages.table, C.c_void_p))
+    ctx = C.c_void_p(hostcheck.hostcheck_ctx_new(max_kpts))
+    p = mvo_b200.VoParams()
+    hostcheck.mvo_vo_default_params(C.byref(p))
+    p.track.ba_step_tol = 0.0
+    if "min_dist_between_two_keyframes" in vo_cfg:
+        p.track.min_dist_keyframe = vo_cfg["min_dist_between_two_keyframes"]
+    if "init_calc_homography" in vo_cfg:
+        p.init_calc_homography = int(vo_cfg["init_calc_homography"])
+    h = C.c_void_p()
+    Kc = np.ascontiguousarray(K, np.float64)
+    assert hostcheck.mvo_vo_create(ctx, Kc.ctypes.data, ROWS, COLS, C.byref(p), C.byref(h)) == 0
+    rows = []
+    try:
+        for f in frames:
+            img = mvo_synth.gray_to_bgr(f)
+            T_o, info_o = oracle.add_frame(img)
+            T_p, info_p = np.zeros(16), mvo_b200.VoFrameInfo()
+            assert hostcheck.mvo_vo_add_frame(h, img.ctypes.data, 3, img.shape[1] * 3, T_p.ctypes.data, C.byref(info_p)) == 0
+            rows.append((T_o, info_o, T_p.reshape(4, 4).copy(), info_p))
+        n = C.c_int(hostcheck.mvo_vo_map_size(h))
+        ids, pts = np.zeros(max(n.value, 1), np.int32), np.zeros((max(n.value, 1), 3), np.float32)
+        assert hostcheck.mvo_vo_get_map(h, ids.ctypes.data, pts.ctypes.data, None, None, len(ids), C.byref(n)) == 0
+        final = (ids[: n.value].copy(), pts[: n.value].copy(), hostcheck.mvo_vo_num_keyframes(h),
+                 np.stack([_pose(hostcheck, h, k) for k in range(min(len(frames), 20))]))
+    finally:
+        hostcheck.mvo_vo_destroy(h)
+        hostcheck.hostcheck_ctx_free(ctx)
+    return oracle, rows, final
+
+
+def _pose(lib, h, k):
+    T = np.zeros(16)
+    assert lib.mvo_vo_frame_pose(h, k, T.ctypes.data) == 0
+    return T.reshape(4, 4)
+
+
+def test_state_machine_equals_oracle_on_room_sequence(hostcheck):
+    from oracle import vo_pipeline_oracle as vp
+    frames, truth = mvo_synth.room_sequence(0, 28)
+    oracle, rows, (ids, pts, n_kf, buff_poses) = _run_both(hostcheck, frames, 2000, 10)
+    keys = [("state_in", "state_in"), ("state_out", "state_out"), ("keyframe", "keyframe"), ("n_keypoints", "n_keypoints"), ("n_matches", "n_matches"),
+            ("n_inliers", "n_inliers"), ("pnp_ok", "pnp_ok"), ("ba_frames", "ba_frames"), ("best_sol", "best_sol"), ("map_points", "map_points")]
+    for i, (T_o, io, T_p, ip) in enumerate(rows):
+        for ko, kp in keys:
+            assert io[ko] == getattr(ip, kp), (i, ko, io[ko], getattr(ip, kp))
+        for opt, kp in (("n_candidates", "n_candidates"), ("ba_edges", "ba_edges"), ("kf_matches", "kf_matches"), ("kf_new_points_in", "kf_new_points")):
+            if opt in io:
+                assert io[opt] == getattr(ip, kp), (i, opt, io[opt], getattr(ip, kp))
+        assert np.abs(T_o - T_p).max() < POSE_TOL, (i, np.abs(T_o - T_p).max())
+        if "T_pnp" in io:
+            assert np.abs(io["T_pnp"] - np.array(ip.T_w_c_pnp).reshape(4, 4)).max() < POSE_TOL
+        if "init_median_angle" in io:
+            assert abs(io["init_median_angle"] - ip.init_median_angle) < 1e-9 and abs(io["init_mean_pixel_dist"] - ip.init_mean_pixel_dist) < 1e-9
+            assert abs(io["score_e"] - ip.score_e) < 1e-6 * max(1, io["score_e"]) and abs(io["eh_ratio"] - ip.eh_ratio) < 1e-9
+    # the sequence exercises every branch: initialisation after several skipped frames, tracking, >= 2 later keyframes with culling
+    states = [r[1]["state_out"] for r in rows]
+    assert states[0] == vp.DOING_INITIALIZATION and states[-1] == vp.DOING_TRACKING
+    init_at = states.index(vp.DOING_TRACKING)
+    assert init_at >= 2 and sum(r[1]["keyframe"] for r in rows[init_at + 1:]) >= 2
+    assert n_kf == len(oracle.keyframes)
+    # the map outgrew 1000 points, so the later keyframes culled with the raised erase ratio of optimizeMap_ (vo.cpp:519-524)
+    assert max(r[1]["map_points"] for r in rows) > 1000 and oracle.map_point_erase_ratio > 0.1
+    # the map: same ids in the same container order, same positions
+    assert ids.tolist() == oracle.map.keys()
+    assert np.abs(pts - np.stack([oracle.map[i].pos for i in ids])).max() < 1e-6          # float32 positions from poses that agree to POSE_TOL
+    # buffered poses (later BA updates included)
+    ob = list(oracle.buff)
+    for k in range(len(buff_poses)):
+        assert np.abs(buff_poses[k] - ob[len(ob) - 1 - k].T_w_c).max() < POSE_TOL
+    # and the trajectory is a sane one: RMS error after similarity alignment below 2 % of the path length
+    est = [r[2] for r in rows[init_at:]]
+    err, _ = vp.trajectory_error(est, truth[init_at:])
+    path = np.linalg.norm(truth[-1][:3, 3] - truth[init_at][:3, 3])
+    assert err < 0.02 * path, (err, path)
+
+
+def test_state_machine_without_homography_and_dense_keyframes(hostcheck):
+    """Essential-only initialisation and a keyframe on every tracked frame."""
+    frames, _ = mvo_synth.room_sequence(0, 14)
+    oracle, rows, (ids, pts, n_kf, _) = _run_both(hostcheck, frames, 2000, 10, init_calc_homography=False, min_dist_between_two_keyframes=0.005)
+    for i, (T_o, io, T_p, ip) in enumerate(rows):
+        assert (io["state_out"], io["keyframe"], io["map_points"], io["n_inliers"]) == (ip.state_out, ip.keyframe, ip.map_points, ip.n_inliers), i
+        assert np.abs(T_o - T_p).max() < POSE_TOL
+    assert sum(r[1]["keyframe"] for r in rows) >= 5 and n_kf == len(oracle.keyframes)
+    assert ids.tolist() == oracle.map.keys()
