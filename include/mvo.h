@@ -451,6 +451,19 @@ int mvo_vo_num_keyframes(const mvo_vo *v);
 int mvo_vo_get_map(const mvo_vo *v, int32_t *ids, float *pts3d, uint8_t *desc, uint8_t *rgb, int cap, int *n);
 /* Pose of the k-th newest buffered frame (k = 0: the last one) including later BA updates. */
 int mvo_vo_frame_pose(const mvo_vo *v, int k, double *T_w_c);
+/* What run_vo.cpp's display code reads from a Frame (run_vo.cpp:184-232, 286-300): `which` = k-th newest buffered frame
+ * (0 = the one just added) or -1 = VisualOdometry::getPrevRef(); `what` selects the member.  *n = element count;
+ * MVO_ERR_CAPACITY when cap is too small. */
+enum {
+  MVO_VO_KEYPOINTS = 0,          /* keypoints_                 mvo_keypoint[] */
+  MVO_VO_DESCRIPTORS = 1,        /* descriptors_               32 bytes each */
+  MVO_VO_MATCHES_WITH_REF = 2,   /* matches_with_ref_          mvo_dmatch[] */
+  MVO_VO_MATCHES_WITH_MAP = 3,   /* matches_with_map_ (PnP inliers after tracking)  mvo_dmatch[] */
+  MVO_VO_INLIERS_PTS3D = 4,      /* inliers_pts3d_ (in the frame's camera coordinates)  3 floats each */
+  MVO_VO_FRAME_ID = 5            /* id_                        one int32 */
+};
+int mvo_vo_frame_data(const mvo_vo *v, int which, int what, void *out, int cap, int *n);
+int mvo_vo_has_keyframe(const mvo_vo *v, int frame_id);       /* Map::hasKeyFrame */
 
 /* ---- on-disk formats either side of the path (host only) -------------------
  * Trajectory file of my_slam::vo::writePoseToFile / readPoseFromFile (src/vo/vo_io.cpp:51-120): one pose

@@ -590,6 +590,36 @@ int mvo_vo_get_map(const mvo_vo *v, int32_t *ids, float *pts3d, uint8_t *desc, u
   return MVO_OK;
 }
 
+int mvo_vo_has_keyframe(const mvo_vo *v, int frame_id) { return v && v->keyframes.count(frame_id) ? 1 : 0; }      // Map::hasKeyFrame
+
+int mvo_vo_frame_data(const mvo_vo *v, int which, int what, void *out, int cap, int *n) {
+  if (!v || !n) return MVO_ERR_INVALID_ARG;
+  const VoFrame *f = nullptr;
+  if (which == -1) f = v->prev_ref.get();                        // VisualOdometry::getPrevRef
+  else if (which >= 0 && which < (int)v->buff.size()) f = v->buff[v->buff.size() - 1 - (size_t)which].get();
+  if (!f) return MVO_ERR_INVALID_ARG;
+  const void *src = nullptr;
+  size_t count = 0, elem = 0;
+  switch (what) {
+    case MVO_VO_KEYPOINTS: src = f->kpts.data(); count = f->kpts.size(); elem = sizeof(mvo_keypoint); break;
+    case MVO_VO_DESCRIPTORS: src = f->desc.data(); count = f->desc.size() / 32; elem = 32; break;
+    case MVO_VO_MATCHES_WITH_REF: src = f->matches_with_ref.data(); count = f->matches_with_ref.size(); elem = sizeof(mvo_dmatch); break;
+    case MVO_VO_MATCHES_WITH_MAP: src = f->matches_with_map.data(); count = f->matches_with_map.size(); elem = sizeof(mvo_dmatch); break;
+    case MVO_VO_INLIERS_PTS3D: src = f->inliers_pts3d.data(); count = f->inliers_pts3d.size() / 3; elem = 12; break;
+    case MVO_VO_FRAME_ID: {
+      *n = 1;
+      if (cap < 1 || !out) return MVO_ERR_CAPACITY;
+      *(int32_t *)out = f->id;
+      return MVO_OK;
+    }
+    default: return MVO_ERR_INVALID_ARG;
+  }
+  *n = (int)count;
+  if ((int)count > cap || (count > 0 && !out)) return MVO_ERR_CAPACITY;
+  if (count > 0) memcpy(out, src, count * elem);
+  return MVO_OK;
+}
+
 int mvo_vo_frame_pose(const mvo_vo *v, int k, double *T_w_c) {
   if (!v || !T_w_c || k < 0 || k >= (int)v->buff.size()) return MVO_ERR_INVALID_ARG;
   memcpy(T_w_c, v->buff[v->buff.size() - 1 - (size_t)k]->T_w_c, 16 * sizeof(double));

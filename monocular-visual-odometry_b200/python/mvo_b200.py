@@ -148,6 +148,8 @@ SIGNATURES = {
     "mvo_vo_num_keyframes": (_i, [_vp]),
     "mvo_vo_get_map": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _pi]),
     "mvo_vo_frame_pose": (_i, [_vp, _i, _vp]),
+    "mvo_vo_frame_data": (_i, [_vp, _i, _i, _vp, _i, _pi]),
+    "mvo_vo_has_keyframe": (_i, [_vp, _i]),
     "mvo_write_pose_file": (_i, [C.c_char_p, _vp, _i]),
     "mvo_read_pose_file": (_i, [C.c_char_p, _vp, _i, _pi]),
     "mvo_image_path": (_i, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _sz]),
@@ -486,6 +488,23 @@ class VisualOdometry:
         T = np.zeros(16)
         self.ctx._chk(self.lib.mvo_vo_frame_pose(self.h, k, _ptr(T)))
         return T.reshape(4, 4)
+
+    _FRAME_DATA = {"keypoints": (0, KEYPOINT_DTYPE, ()), "descriptors": (1, np.uint8, (32,)), "matches_with_ref": (2, DMATCH_DTYPE, ()),
+                   "matches_with_map": (3, DMATCH_DTYPE, ()), "inliers_pts3d": (4, np.float32, (3,)), "id": (5, np.int32, ())}
+
+    def frame_data(self, what, which=0):
+        """Members of the `which`-th newest frame (or -1 = getPrevRef()) that run_vo.cpp's display code reads."""
+        code, dtype, tail = self._FRAME_DATA[what]
+        n = C.c_int(0)
+        rc = self.lib.mvo_vo_frame_data(self.h, which, code, None, 0, C.byref(n))
+        if rc not in (0, -4):
+            self.ctx._chk(rc)
+        out = np.zeros((max(n.value, 1),) + tail, dtype)
+        self.ctx._chk(self.lib.mvo_vo_frame_data(self.h, which, code, _ptr(out), max(n.value, 1), C.byref(n)))
+        return out[: n.value]
+
+    def has_keyframe(self, frame_id):
+        return bool(self.lib.mvo_vo_has_keyframe(self.h, int(frame_id)))
 
 
 class Tracker:

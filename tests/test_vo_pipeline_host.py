@@ -162,7 +162,7 @@ def hostcheck(built, tmp_path_factory):
     lib.hostcheck_ctx_free.argtypes = [C.c_void_p]
     lib.hostcheck_set_stages.argtypes = [C.c_void_p]
     for name in ("mvo_vo_default_params", "mvo_vo_create", "mvo_vo_destroy", "mvo_vo_add_frame", "mvo_vo_is_initialized", "mvo_vo_map_size",
-                 "mvo_vo_num_keyframes", "mvo_vo_get_map", "mvo_vo_frame_pose"):
+                 "mvo_vo_num_keyframes", "mvo_vo_get_map", "mvo_vo_frame_pose", "mvo_vo_frame_data", "mvo_vo_has_keyframe"):
         res, args = mvo_b200.SIGNATURES[name]
         getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
     return lib
@@ -194,6 +194,7 @@ def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
             T_p, info_p = np.zeros(16), mvo_b200.VoFrameInfo()
             assert hostcheck.mvo_vo_add_frame(h, img.ctypes.data, 3, img.shape[1] * 3, T_p.ctypes.data, C.byref(info_p)) == 0
             rows.append((T_o, info_o, T_p.reshape(4, 4).copy(), info_p))
+            _check_frame_members(hostcheck, h, oracle)
         n = C.c_int(hostcheck.mvo_vo_map_size(h))
         ids, pts = np.zeros(max(n.value, 1), np.int32), np.zeros((max(n.value, 1), 3), np.float32)
         assert hostcheck.mvo_vo_get_map(h, ids.ctypes.data, pts.ctypes.data, None, None, len(ids), C.byref(n)) == 0
@@ -203,6 +204,37 @@ def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
         hostcheck.mvo_vo_destroy(h)
         hostcheck.hostcheck_ctx_free(ctx)
     return oracle, rows, final
+
+
+def _frame_data(lib, h, which, what, dtype, tail=()):
+    n = C.c_int(0)
+    rc = lib.mvo_vo_frame_data(h, which, what, None, 0, C.byref(n))
+    assert rc in (0, -4), rc                                          # MVO_ERR_CAPACITY reports the size
+    out = np.zeros((max(n.value, 1),) + tail, dtype)
+    assert lib.mvo_vo_frame_data(h, which, what, out.ctypes.data, len(out), C.byref(n)) == 0
+    return out[: n.value]
+
+
+def _check_frame_members(lib, h, oracle):
+    """What run_vo.cpp's display code reads after addFrame (run_vo.cpp:184-232, 286-300)."""
+    import mvo_b200
+    cur = oracle.curr
+    assert _frame_data(lib, h, 0, 5, np.int32)[0] == cur.id
+    assert _frame_data(lib, h, 0, 0, mvo_b200.KEYPOINT_DTYPE).tobytes() == np.ascontiguousarray(cur.kp).tobytes()
+    assert np.array_equal(_frame_data(lib, h, 0, 1, np.uint8, (32,)), cur.desc)
+    for what, ref in ((2, cur.matches_with_ref), (3, cur.matches_with_map)):
+        got = _frame_data(lib, h, 0, what, mvo_b200.DMATCH_DTYPE)
+        assert np.array_equal(got["query_idx"], ref["query_idx"]) and np.array_equal(got["train_idx"], ref["train_idx"])
+    p3 = _frame_data(lib, h, 0, 4, np.float32, (3,))
+    assert p3.shape == cur.inliers_pts3d.shape and (len(p3) == 0 or np.abs(p3 - cur.inliers_pts3d).max() < 1e-5)
+    assert bool(lib.mvo_vo_has_keyframe(h, cur.id)) == (cur.id in oracle.keyframes)
+    if oracle.prev_ref is None:
+        n = C.c_int(0)
+        assert lib.mvo_vo_frame_data(h, -1, 5, None, 0, C.byref(n)) == -1          # no previous reference keyframe yet
+    else:
+        assert _frame_data(lib, h, -1, 5, np.int32)[0] == oracle.prev_ref.id
+    n = C.c_int(0)
+    assert lib.mvo_vo_frame_data(h, 0, 99, None, 0, C.byref(n)) == -1 and lib.mvo_vo_frame_data(h, 64, 0, None, 0, C.byref(n)) == -1
 
 
 def _pose(lib, h, k):
