@@ -45,6 +45,15 @@ mvo_ctx *hostcheck_ctx_new(int max_keypoints) {
   return c;
 }
 void hostcheck_ctx_free(mvo_ctx *c) { delete c; }
+// for the my_slam adapter layer, which creates its own context (my_slam_adapter/mvo_context.cpp)
+int mvo_create(mvo_ctx **out, int, const mvo_params *params) {
+  mvo_ctx *c = new mvo_ctx();
+  if (params) c->prm = *params; else mvo_default_params(&c->prm);
+  *out = c;
+  return MVO_OK;
+}
+void mvo_destroy(mvo_ctx *c) { delete c; }
+const char *mvo_last_error(const mvo_ctx *c) { return c ? c->err.c_str() : ""; }
 
 int mvo_orb_extract(mvo_ctx *, const uint8_t *image, int rows, int cols, int channels, size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
   return g_stages.orb_extract(image, rows, cols, channels, stride, kpts, n_kpts, desc);

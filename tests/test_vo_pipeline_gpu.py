@@ -80,3 +80,39 @@ def test_vo_pipeline_essential_only_initialisation(built):
 @pytest.mark.xfail(strict=False, reason="depends on the homography kernels, which have not run on hardware yet")
 def test_vo_pipeline_reference_configuration(built):
     _run(1)
+
+
+ADAPTER_CHILD = r'''
+import subprocess, sys
+import numpy as np
+sys.path.insert(0, r"{root}"); sys.path.insert(0, r"{root}/monocular-visual-odometry_b200/python")
+import mvo_b200, mvo_synth
+n = 14
+frames, _ = mvo_synth.room_sequence(0, n)
+imgs = [mvo_synth.gray_to_bgr(f) for f in frames]
+np.stack(imgs).tofile(r"{tmp}/frames.bin")
+r = subprocess.run([r"{root}/monocular-visual-odometry_b200/build/adapter_vo_demo", r"{tmp}", str(n)], capture_output=True, text=True, timeout=120)
+assert r.returncode == 0, r.stderr[-2000:]
+rows = [[int(x) for x in ln.split()] for ln in open(r"{tmp}/summary.txt").read().splitlines()]
+ctx = mvo_b200.Context(0, max_keypoints=2000)          # the adapter's context: config defaults + max_number_of_keypoints = 2000
+vo = mvo_b200.VisualOdometry(ctx, mvo_synth.K_DEFAULT, 480, 640)
+poses = []
+for i, img in enumerate(imgs):
+    T, info = vo.add_frame(img)
+    poses.append(T)
+    fid, init, is_kf, nk, n_ref, n_map, n_p3, n_pts, prev_ref = rows[i]
+    assert (fid, init, is_kf, nk, n_pts) == (i, int(vo.is_initialized()), info.keyframe, info.n_keypoints, info.map_points), (i, rows[i])
+    assert n_ref == len(vo.frame_data("matches_with_ref")) and n_map == len(vo.frame_data("matches_with_map")) and n_p3 == len(vo.frame_data("inliers_pts3d"))
+lib = mvo_b200.load_library()
+import ctypes as C
+got, cnt = np.zeros((n, 16)), C.c_int(0)
+assert lib.mvo_read_pose_file(r"{tmp}/traj.txt".encode(), got.ctypes.data, n, C.byref(cnt)) == 0 and cnt.value == n
+assert np.abs(got.reshape(n, 4, 4) - np.stack(poses)).max() < 2e-5        # 6 significant digits in the file
+print("vo adapter child ok")
+'''
+
+
+@pytest.mark.xfail(strict=False, reason="state machine assembled after the round-1 GPU budget was spent: first hardware run")
+def test_my_slam_visual_odometry_adapter_demo(built, tmp_path):
+    r = subprocess.run([sys.executable, "-c", ADAPTER_CHILD.format(root=str(ROOT), tmp=str(tmp_path))], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "vo adapter child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])

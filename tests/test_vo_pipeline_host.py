@@ -168,6 +168,48 @@ def hostcheck(built, tmp_path_factory):
     return lib
 
 
+def test_my_slam_visual_odometry_adapter(hostcheck, tmp_path):
+    """my_slam::vo::VisualOdometry / Frame / Map (my_slam_adapter/vo_mvo.h) driven by the run_vo.cpp-style loop of
+    tests/cpp/adapter_vo_demo.cpp, linked against the host-check build: the members run_vo.cpp reads and the trajectory file."""
+    import mvo_b200
+    from oracle import vo_pipeline_oracle as vp
+    pkg = ROOT / "monocular-visual-odometry_b200"
+    so = tmp_path / "libadapter_vo_demo.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Dmain=adapter_vo_demo_main", "-I", str(pkg / "my_slam_adapter" / "include"),
+                    "-I", str(ROOT / "tests" / "cvshim"), "-I", str(ROOT / "include"), "-I", str(pkg / "my_slam_adapter"),
+                    str(ROOT / "tests" / "cpp" / "adapter_vo_demo.cpp"), str(pkg / "my_slam_adapter" / "mvo_context.cpp"), str(pkg / "my_slam_adapter" / "vo_mvo.cpp"),
+                    "-L", str(Path(hostcheck._name).parent), "-lvo_hostcheck", "-L", str(pkg), "-lmvo", f"-Wl,-rpath,{Path(hostcheck._name).parent}",
+                    f"-Wl,-rpath,{pkg}", "-o", str(so)], check=True)
+    n = 16
+    frames, _ = mvo_synth.room_sequence(0, n)
+    imgs = [mvo_synth.gray_to_bgr(f) for f in frames]
+    np.stack(imgs).tofile(tmp_path / "frames.bin")
+    oracle = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=2000, ba_iterations=10)
+    helper = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=2000)
+    stages = Stages(helper, 10)
+    hostcheck.hostcheck_set_stages(C.cast(stages.table, C.c_void_p))
+    demo = C.CDLL(str(so))
+    argv = (C.c_char_p * 3)(b"adapter_vo_demo", str(tmp_path).encode(), str(n).encode())
+    assert getattr(demo, "_Z20adapter_vo_demo_mainiPPc")(3, argv) == 0          # the renamed main has C++ linkage
+    rows = [[int(x) for x in ln.split()] for ln in (tmp_path / "summary.txt").read_text().splitlines()]
+    assert len(rows) == n
+    poses = []
+    for i, img in enumerate(imgs):
+        T, info = oracle.add_frame(img)
+        poses.append(T)
+        cur = oracle.curr
+        fid, init, is_kf, nk, n_ref, n_map, n_p3, n_pts, prev_ref = rows[i]
+        assert (fid, init, is_kf, nk) == (cur.id, int(oracle.state == vp.DOING_TRACKING), int(cur.id in oracle.keyframes), len(cur.kp)), i
+        assert (n_ref, n_map, n_p3, n_pts) == (len(cur.matches_with_ref), len(cur.matches_with_map), len(cur.inliers_pts3d), len(oracle.map)), i
+        assert prev_ref == (oracle.prev_ref.id if oracle.prev_ref is not None else -1), i
+    assert rows[-1][1] == 1 and sum(r[2] for r in rows) >= 3
+    # the trajectory file (writePoseToFile format, 6 significant digits) holds the poses returned by addFrame
+    lib = mvo_b200.load_library()
+    got, cnt = np.zeros((n, 16)), C.c_int(0)
+    assert lib.mvo_read_pose_file(str(tmp_path / "traj.txt").encode(), got.ctypes.data, n, C.byref(cnt)) == 0 and cnt.value == n
+    assert np.abs(got.reshape(n, 4, 4) - np.stack(poses)).max() < 2e-5
+
+
 def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
     import mvo_b200
     from oracle import vo_pipeline_oracle as vp
