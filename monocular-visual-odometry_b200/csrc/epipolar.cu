@@ -418,7 +418,7 @@ k_homo_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   }
 }
 
-constexpr int HOMO_NV = 54;               // 45 entries of J^T J (upper triangle) + 9 of J^T r
+constexpr int HOMO_NV = epi::HOMO_GN_NV;    // 45 entries of J^T J (upper triangle) + 9 of J^T r
 
 // out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
 // [3] consensus of the best minimal model, [4] consensus after the local optimisation
@@ -469,19 +469,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
         const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
         const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
         if (!(epi::homography_transfer_err(Hsel, x1, y1, x2, y2) <= thr2)) continue;
-        const double w = Hc[6] * x1 + Hc[7] * y1 + Hc[8];
-        if (!(fabs(w) > 1e-12)) continue;
-        const double iw = 1.0 / w, u = (Hc[0] * x1 + Hc[1] * y1 + Hc[2]) * iw, v = (Hc[3] * x1 + Hc[4] * y1 + Hc[5]) * iw;
-        const double ru = u - x2, rv = v - y2;
-        const double Ju[9] = {x1 * iw, y1 * iw, iw, 0, 0, 0, -u * x1 * iw, -u * y1 * iw, -u * iw};
-        const double Jv[9] = {0, 0, 0, x1 * iw, y1 * iw, iw, -v * x1 * iw, -v * y1 * iw, -v * iw};
-        int q = 0;
-#pragma unroll
-        for (int r = 0; r < 9; ++r)
-#pragma unroll
-          for (int c = r; c < 9; ++c) acc[q++] += Ju[r] * Ju[c] + Jv[r] * Jv[c];
-#pragma unroll
-        for (int r = 0; r < 9; ++r) acc[45 + r] += Ju[r] * ru + Jv[r] * rv;
+        epi::homography_gn_accumulate(Hc, x1, y1, x2, y2, acc);
       }
 #pragma unroll
       for (int q = 0; q < HOMO_NV; ++q) {
@@ -494,33 +482,10 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
       if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
       __syncthreads();
       if (tid == 0) {
-        double A[9][10];
-        int q = 0;
-        for (int r = 0; r < 9; ++r) for (int c = r; c < 9; ++c) { A[r][c] = s_sum[q]; A[c][r] = s_sum[q]; ++q; }
-        double mxd = 0;
-        for (int r = 0; r < 9; ++r) mxd = fmax(mxd, A[r][r]);
-        for (int r = 0; r < 9; ++r) { A[r][r] += 1e-9 * mxd + 1e-300; A[r][9] = -s_sum[45 + r]; }
-        bool ok = true;
-        for (int k = 0; k < 9 && ok; ++k) {
-          int pr = k;
-          for (int r = k + 1; r < 9; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
-          if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
-          if (pr != k) for (int c = 0; c < 10; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
-          for (int r = k + 1; r < 9; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 10; ++c) A[r][c] -= f * A[k][c]; }
-        }
-        double dx[9], mx = 0;
-        for (int r = 0; r < 9; ++r) dx[r] = 0;
-        if (ok) {
-          for (int r = 8; r >= 0; --r) { double vq = A[r][9]; for (int c = r + 1; c < 9; ++c) vq -= A[r][c] * dx[c]; dx[r] = vq / A[r][r]; }
-          for (int r = 0; r < 9; ++r) { if (!epi::finite_d(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
-        }
-        if (ok && mx < 0.5) {                         // H has unit Frobenius norm: half of that is not a refinement
-          double nrm = 0;
-          for (int r = 0; r < 9; ++r) { s_H[r] += dx[r]; nrm += s_H[r] * s_H[r]; }
-          nrm = sqrt(nrm);
-          for (int r = 0; r < 9; ++r) s_H[r] /= nrm;
-        }
-        if (!ok || mx < 1e-11 || mx >= 0.5) s_stop = 1;
+        double Hn[9];
+        for (int q = 0; q < 9; ++q) Hn[q] = s_H[q];
+        if (epi::homography_gn_step(s_sum, Hn)) s_stop = 1;
+        for (int q = 0; q < 9; ++q) s_H[q] = Hn[q];
       }
       __syncthreads();
       if (s_stop) break;

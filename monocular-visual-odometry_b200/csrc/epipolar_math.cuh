@@ -248,6 +248,54 @@ EPI_HD double homography_transfer_err(const double *H, double x1, double y1, dou
   return du * du + dv * dv;
 }
 
+// ---- Gauss-Newton on the forward transfer error, additive update of the 9 entries of H (unit Frobenius norm) ----
+// One correspondence's contribution to the normal equations: acc[0..44] += upper triangle of J^T J (row-major),
+// acc[45..53] += J^T r, with r = (u - x2, v - y2), (u, v) = H x1 dehomogenised.  Points at w ~ 0 contribute nothing.
+constexpr int HOMO_GN_NV = 54;
+EPI_HD void homography_gn_accumulate(const double *Hc, double x1, double y1, double x2, double y2, double *acc) {
+  const double w = Hc[6] * x1 + Hc[7] * y1 + Hc[8];
+  if (!(fabs(w) > 1e-12)) return;
+  const double iw = 1.0 / w, u = (Hc[0] * x1 + Hc[1] * y1 + Hc[2]) * iw, v = (Hc[3] * x1 + Hc[4] * y1 + Hc[5]) * iw;
+  const double ru = u - x2, rv = v - y2;
+  const double Ju[9] = {x1 * iw, y1 * iw, iw, 0, 0, 0, -u * x1 * iw, -u * y1 * iw, -u * iw};
+  const double Jv[9] = {0, 0, 0, x1 * iw, y1 * iw, iw, -v * x1 * iw, -v * y1 * iw, -v * iw};
+  int q = 0;
+  for (int r = 0; r < 9; ++r)
+    for (int c = r; c < 9; ++c) acc[q++] += Ju[r] * Ju[c] + Jv[r] * Jv[c];
+  for (int r = 0; r < 9; ++r) acc[45 + r] += Ju[r] * ru + Jv[r] * rv;
+}
+
+// Solve the accumulated normal equations and apply the step to H (renormalised to unit Frobenius norm).  The scale of H
+// is a null direction of J^T J: a small damping of the diagonal fixes the gauge.  Returns true when the iteration
+// should STOP: singular / non-finite system, a step below 1e-11 (converged) or above 0.5 (half the norm of H is not a
+// refinement; H is left untouched in that case).
+EPI_HD_CALL bool homography_gn_step(const double *sum, double *H) {
+  double A[9][10];
+  int q = 0;
+  for (int r = 0; r < 9; ++r)
+    for (int c = r; c < 9; ++c) { A[r][c] = sum[q]; A[c][r] = sum[q]; ++q; }
+  double mxd = 0;
+  for (int r = 0; r < 9; ++r) mxd = fmax(mxd, A[r][r]);
+  for (int r = 0; r < 9; ++r) { A[r][r] += 1e-9 * mxd + 1e-300; A[r][9] = -sum[45 + r]; }
+  for (int k = 0; k < 9; ++k) {                                  // Gaussian elimination with partial pivoting
+    int pr = k;
+    for (int r = k + 1; r < 9; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
+    if (!(fabs(A[pr][k]) > 0)) return true;
+    if (pr != k) for (int c = 0; c < 10; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
+    for (int r = k + 1; r < 9; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 10; ++c) A[r][c] -= f * A[k][c]; }
+  }
+  double dx[9], mx = 0;
+  for (int r = 0; r < 9; ++r) dx[r] = 0;
+  for (int r = 8; r >= 0; --r) { double vq = A[r][9]; for (int c = r + 1; c < 9; ++c) vq -= A[r][c] * dx[c]; dx[r] = vq / A[r][r]; }
+  for (int r = 0; r < 9; ++r) { if (!finite_d(dx[r])) return true; mx = fmax(mx, fabs(dx[r])); }
+  if (mx >= 0.5) return true;
+  double nrm = 0;
+  for (int r = 0; r < 9; ++r) { H[r] += dx[r]; nrm += H[r] * H[r]; }
+  nrm = sqrt(nrm);
+  for (int r = 0; r < 9; ++r) H[r] /= nrm;
+  return mx < 1e-11;
+}
+
 EPI_HD void mat3_mul(const double *A, const double *B, double *C) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];

@@ -16,5 +16,25 @@ int epi_decompose_homography(const double *H, double *Rs, double *ts, double *ns
 int epi_filter_homography(const double *Rs, const double *ns, int n_sol, const float *np1, const float *np2, const int *inl, int n_in, int *keep) {
   return epi::filter_homography_solutions(Rs, ns, n_sol, np1, np2, inl, n_in, keep);
 }
+// the local optimisation of k_homo_finish, serially: `rounds` times re-select the consensus set of the current H (scaled
+// coordinates, squared threshold thr2), then up to `iters` Gauss-Newton steps on it (csrc/epipolar.cu, k_homo_finish)
+int epi_homography_lo(const double *xy1, const double *xy2, int n, double thr2, int rounds, int iters, double *H) {
+  int steps = 0;
+  for (int round = 0; round < rounds; ++round) {
+    double Hsel[9];
+    for (int q = 0; q < 9; ++q) Hsel[q] = H[q];
+    for (int it = 0; it < iters; ++it) {
+      double acc[epi::HOMO_GN_NV];
+      for (int q = 0; q < epi::HOMO_GN_NV; ++q) acc[q] = 0;
+      for (int i = 0; i < n; ++i) {
+        if (!(epi::homography_transfer_err(Hsel, xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1]) <= thr2)) continue;
+        epi::homography_gn_accumulate(H, xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1], acc);
+      }
+      ++steps;
+      if (epi::homography_gn_step(acc, H)) break;
+    }
+  }
+  return steps;
+}
 int epi_null_8x9(const double *M, double *x) { double T[72]; for (int i = 0; i < 72; ++i) T[i] = M[i]; return epi::null_vector_8x9(T, x) ? 1 : 0; }
 }

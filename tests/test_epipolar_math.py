@@ -156,6 +156,52 @@ def test_homography_from_4_and_transfer_error(epi):
     assert epi.epi_homography_from_4(_p(x), _p(x.copy()), _p(np.zeros((3, 3)))) == 0
 
 
+def test_homography_local_optimisation(epi):
+    """The Gauss-Newton refinement k_homo_finish applies to the best four-point model (same header functions, run serially):
+    from a minimal model fitted to NOISY points it reaches the least-squares homography of the consensus set — as good as
+    cv2.findHomography's own refinement on the noise-free plane — and stops by itself."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    f = 615.0
+    thr2 = (3.0 / f) ** 2
+    for k in range(20):
+        R, td, nrm, x1, x2 = _plane_scene(rng, 400)
+        a = x1 + rng.normal(0, 0.4 / f, x1.shape)               # 0.4 px of noise in scaled coordinates
+        b = x2 + rng.normal(0, 0.4 / f, x2.shape)
+        bad = rng.random(len(a)) < 0.2
+        b[bad] += rng.uniform(-0.1, 0.1, (bad.sum(), 2))
+        # the RANSAC front end in miniature: 64 four-point samples, the one with the largest consensus is refined
+        H, best = np.zeros((3, 3)), -1
+        for s_ in range(64):
+            idx = rng.choice(len(a), 4, replace=False)
+            Hs = np.zeros((3, 3))
+            if epi.epi_homography_from_4(_p(np.ascontiguousarray(a[idx])), _p(np.ascontiguousarray(b[idx])), _p(Hs)) != 1:
+                continue
+            m = np.c_[a, np.ones(len(a))] @ Hs.T
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cnt = int((np.sum((m[:, :2] / m[:, 2:3] - b) ** 2, 1) <= thr2).sum())
+            if cnt > best:
+                best, H = cnt, Hs
+        assert best > 200
+
+        def plane_err(Hm):                                      # RMS transfer error on the noise-free points, pixels
+            m = np.c_[x1, np.ones(len(x1))] @ Hm.T
+            return f * np.sqrt(np.mean(np.sum((m[:, :2] / m[:, 2:3] - x2) ** 2, 1)))
+        e_min = plane_err(H)
+        a_c, b_c = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        steps = epi.epi_homography_lo(_p(a_c), _p(b_c), len(a), C.c_double(thr2), 3, 8, _p(H))
+        e_lo = plane_err(H)
+        assert abs(np.linalg.norm(H) - 1) < 1e-12 and 3 <= steps <= 24
+        Hcv, _ = cv2.findHomography((a * f).astype(np.float32), (b * f).astype(np.float32), cv2.RANSAC, 3.0)
+        S = np.diag([1 / f, 1 / f, 1.0])
+        e_cv = plane_err(S @ Hcv @ np.linalg.inv(S))
+        assert e_lo < 0.15 and e_lo < e_cv + 0.02, (k, e_min, e_lo, e_cv)
+        assert e_lo <= e_min + 1e-9
+        # a second run from the optimum is a fixed point: the first step already reports convergence
+        H2 = H.copy()
+        assert epi.epi_homography_lo(_p(a_c), _p(b_c), len(a), C.c_double(thr2), 1, 8, _p(H2)) <= 2 and np.abs(H2 - H).max() < 1e-9
+
+
 def test_decompose_homography_and_filter_vs_cv2(epi):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(5)
