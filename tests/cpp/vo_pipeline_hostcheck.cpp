@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE (CPU tier): the VO state machine (csrc/vo_pipeline.cpp) compiled a second time into its own
+// TEST INFRASTRUCTURE (CPU tier): the VO state machine (csrc/vo_pipeline.cpp, csrc/two_view.cpp) compiled a second time into its own
 // shared object in which the GPU stages it calls are replaced by forwarders to function pointers the test installs
 // (tests/test_vo_pipeline_host.py points them at the oracle stages).  This checks the HOST logic of the state machine —
 // containers, bookkeeping, index plumbing — frame by frame against oracle/vo_pipeline_oracle.py without a GPU.
@@ -24,8 +24,10 @@ struct HostcheckStages {
   int (*orb_extract)(const uint8_t *image, int rows, int cols, int channels, size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);
   int (*match_features)(const uint8_t *d1, int n1, const uint8_t *d2, int n2, int method, const float *xy1, const float *xy2, float radius,
                         mvo_dmatch *out, int *n_out);
-  int (*estimate_relative_poses)(const float *p1, const float *p2, int n, const double *K, int calc_homo, int cam2_to_cam1,
-                                 mvo_two_view_solutions *sol, int32_t *inliers, float *pts3d);
+  int (*esti_motion_by_homography)(const float *p1, const float *p2, int n, const double *K, double threshold, double *H, double *Rs, double *ts,
+                                   double *normals, int *n_solutions, int32_t *inliers, int *n_inliers);
+  int (*remove_wrong_rt_of_homography)(const float *np1, const float *np2, int n, const int32_t *inliers, int n_inliers, double *Rs, double *ts,
+                                       double *normals, int *n_solutions);
   int (*esti_motion_by_essential)(const float *p1, const float *p2, int n, const double *K, double threshold, double *E, double *R, double *t,
                                   int32_t *inliers, int *n_inliers);
   int (*do_triangulation)(const float *np1, const float *np2, int n, const double *R, const double *t, const int32_t *inliers, int n_inliers,
@@ -62,9 +64,14 @@ int mvo_match_features(mvo_ctx *, const uint8_t *d1, int n1, const uint8_t *d2, 
                        float radius, mvo_dmatch *out, int *n_out) {
   return g_stages.match_features(d1, n1, d2, n2, method_index, xy1, xy2, radius, out, n_out);
 }
-int mvo_estimate_relative_poses(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, int calc_homo, int cam2_to_cam1,
-                                mvo_two_view_solutions *sol, int32_t *inliers, float *pts3d) {
-  return g_stages.estimate_relative_poses(p1, p2, n, K, calc_homo, cam2_to_cam1, sol, inliers, pts3d);
+// mvo_estimate_relative_poses itself is the product's csrc/two_view.cpp, compiled into this object next to vo_pipeline.cpp
+int mvo_esti_motion_by_homography(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, double threshold, double *H, double *Rs,
+                                  double *ts, double *normals, int *n_solutions, int32_t *inliers, int *n_inliers) {
+  return g_stages.esti_motion_by_homography(p1, p2, n, K, threshold, H, Rs, ts, normals, n_solutions, inliers, n_inliers);
+}
+int mvo_remove_wrong_rt_of_homography(mvo_ctx *, const float *np1, const float *np2, int n, const int32_t *inliers, int n_inliers, double *Rs,
+                                      double *ts, double *normals, int *n_solutions) {
+  return g_stages.remove_wrong_rt_of_homography(np1, np2, n, inliers, n_inliers, Rs, ts, normals, n_solutions);
 }
 int mvo_esti_motion_by_essential(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, double threshold, double *E, double *R,
                                  double *t, int32_t *inliers, int *n_inliers) {

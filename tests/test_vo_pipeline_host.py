@@ -2,7 +2,9 @@
 the GPU stages replaced by forwarders (tests/cpp/vo_pipeline_hostcheck.cpp) that this test points at the oracle stages
 (cv2 + oracle/), and the result is compared frame by frame with oracle/vo_pipeline_oracle.py — the restatement of
 reference src/vo/vo_addFrame.cpp:10-142 and src/vo/vo.cpp — on a synthetic 3-D sequence.  Same stages on both sides, so
-every difference is a difference in the state machine: container order, bookkeeping, index plumbing."""
+every difference is a difference in the state machine: container order, bookkeeping, index plumbing.  The two-view
+assembly (csrc/two_view.cpp = helperEstimatePossibleRelativePosesByEpipolarGeometry, reference
+src/geometry/motion_estimation.cpp:10-158) is part of that second build too, over forwarders for ITS stages."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -42,7 +44,8 @@ class Stages:
         self.protos = [
             (C.CFUNCTYPE(i, vp, i, i, i, sz, vp, vp, vp), self.orb_extract),
             (C.CFUNCTYPE(i, vp, i, vp, i, i, vp, vp, f, vp, vp), self.match_features),
-            (C.CFUNCTYPE(i, vp, vp, i, vp, i, i, vp, vp, vp), self.estimate_relative_poses),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, d, vp, vp, vp, vp, vp, vp, vp), self.esti_motion_by_homography),
+            (C.CFUNCTYPE(i, vp, vp, i, vp, i, vp, vp, vp, vp), self.remove_wrong_rt_of_homography),
             (C.CFUNCTYPE(i, vp, vp, i, vp, d, vp, vp, vp, vp, vp), self.esti_motion_by_essential),
             (C.CFUNCTYPE(i, vp, vp, i, vp, vp, vp, i, vp), self.do_triangulation),
             (C.CFUNCTYPE(i, vp, vp, i, vp, vp, vp, vp, vp), self.solve_pnp_ransac),
@@ -71,42 +74,29 @@ class Stages:
         C.c_int.from_address(n_out).value = len(m)
         return 0
 
-    def estimate_relative_poses(self, p1, p2, n, Kp, calc_homo, cam2_to_cam1, sol, inliers, pts3d):
-        from oracle.vo_pipeline_oracle import _norm_plane
-        assert cam2_to_cam1 == 1
+    def esti_motion_by_homography(self, p1, p2, n, Kp, threshold, H, Rs, ts, normals, n_solutions, inliers, n_inliers):
         a, b = _arr(p1, (n, 2), np.float32).copy(), _arr(p2, (n, 2), np.float32).copy()
-        Kc = _arr(Kp, (3, 3), np.float64).copy()
-        na, nb = _norm_plane(a, Kc), _norm_plane(b, Kc)
-        E, R_e, t_e, inl_e = self.epi.esti_motion_by_essential(a, b, Kc, 0.999, 1.0)
-        Rs, ts, ns, inls = [R_e], [t_e], [np.zeros(3)], [inl_e]
-        H, inl_h = np.zeros((3, 3)), np.zeros(0, np.int32)
-        if calc_homo:
-            H, Rh, th, nh, inl_h = self.epi.esti_motion_by_homography(a, b, Kc, 3.0)
-            for s in self.epi.remove_wrong_rt_of_homography(na, nb, inl_h, Rh, th, nh):
-                Rs.append(Rh[s]); ts.append(th[s]); ns.append(nh[s]); inls.append(inl_h)
-        S = self.mvo.TwoViewSolutions.from_address(sol)
-        C.memset(sol, 0, C.sizeof(S))
-        S.num_solutions = len(Rs)
-        inl_out, pts_out = _arr(inliers, (5, n), np.int32), _arr(pts3d, (5, n, 3), np.float32)
-        for s in range(len(Rs)):
-            S.n_inliers[s] = len(inls[s])
-            for q, x in enumerate(np.asarray(Rs[s], np.float64).ravel()):
-                S.R[s][q] = x
-            for q in range(3):
-                S.t[s][q] = float(np.asarray(ts[s]).ravel()[q])
-                S.normal[s][q] = float(np.asarray(ns[s]).ravel()[q])
-            inl_out[s, : len(inls[s])] = inls[s]
-            pts_out[s, : len(inls[s])] = self.epi.do_triangulation(na, nb, Rs[s], ts[s], inls[s])
-        for q, x in enumerate(E.ravel()):
-            S.E[q] = x
-        for q, x in enumerate(np.asarray(H, np.float64).ravel()):
-            S.H[q] = x
-        best, ratio = 0, 0.0
-        if calc_homo:
-            S.score_e, _ = self.mot.check_essential_score(E, Kc, a, b, inl_e)
-            S.score_h, _ = self.mot.check_homography_score(H, a, b, inl_h)
-            best, ratio = self.mot.choose_e_or_h(S.score_e, S.score_h, np.array(ns[1:]).reshape(-1, 3))
-        S.best, S.ratio = best, ratio
+        Hm, Rh, th, nh, inl = self.epi.esti_motion_by_homography(a, b, _arr(Kp, (3, 3), np.float64).copy(), threshold)
+        _arr(H, (3, 3), np.float64)[:] = Hm
+        k = len(Rh)
+        assert k <= 4
+        _arr(Rs, (k, 9), np.float64)[:] = np.array(Rh).reshape(k, 9)
+        _arr(ts, (k, 3), np.float64)[:] = np.array(th).reshape(k, 3)
+        _arr(normals, (k, 3), np.float64)[:] = np.array(nh).reshape(k, 3)
+        C.c_int.from_address(n_solutions).value = k
+        _arr(inliers, (len(inl),), np.int32)[:] = inl
+        C.c_int.from_address(n_inliers).value = len(inl)
+        return 0
+
+    def remove_wrong_rt_of_homography(self, np1, np2, n, inliers, n_inliers, Rs, ts, normals, n_solutions):
+        k = C.c_int.from_address(n_solutions)
+        R, t, nr = _arr(Rs, (k.value, 9), np.float64), _arr(ts, (k.value, 3), np.float64), _arr(normals, (k.value, 3), np.float64)
+        keep = self.epi.remove_wrong_rt_of_homography(_arr(np1, (n, 2), np.float32).copy(), _arr(np2, (n, 2), np.float32).copy(),
+                                                      _arr(inliers, (n_inliers,), np.int32).copy(), [r.reshape(3, 3).copy() for r in R],
+                                                      [x.copy() for x in t], [x.copy() for x in nr])
+        Rk, tk, nk = R[keep].copy(), t[keep].copy(), nr[keep].copy()
+        R[: len(keep)], t[: len(keep)], nr[: len(keep)] = Rk, tk, nk
+        k.value = len(keep)
         return 0
 
     def esti_motion_by_essential(self, p1, p2, n, Kp, threshold, E, R, t, inliers, n_inliers):
@@ -154,6 +144,7 @@ def hostcheck(built, tmp_path_factory):
     pkg = ROOT / "monocular-visual-odometry_b200"
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "include"), "-I", str(pkg / "csrc"),
                     "-I", "/usr/local/cuda/include", str(ROOT / "tests" / "cpp" / "vo_pipeline_hostcheck.cpp"), str(pkg / "csrc" / "vo_pipeline.cpp"),
+                    str(pkg / "csrc" / "two_view.cpp"),
                     "-L", str(pkg), "-lmvo", "-Wl,-Bsymbolic", f"-Wl,-rpath,{pkg}", "-o", str(so)], check=True)
     import mvo_b200
     lib = C.CDLL(str(so))
