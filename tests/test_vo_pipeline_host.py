@@ -325,3 +325,28 @@ def test_state_machine_without_homography_and_dense_keyframes(hostcheck):
         assert np.abs(T_o - T_p).max() < POSE_TOL
     assert sum(r[1]["keyframe"] for r in rows) >= 5 and n_kf == len(oracle.keyframes)
     assert ids.tolist() == oracle.map.keys()
+
+
+def test_state_machine_through_blank_and_far_away_frames(hostcheck):
+    """Frames the reference's happy path never sees: a featureless image while initialising (no keypoints, no matches), one
+    while tracking (PnP cannot run: the pose falls back to the previous frame's, vo.cpp:376-379), and a view from far away
+    (vo.cpp:360-369 rejects the jump or the PnP fails) — the state machine goes on, and agrees with the oracle throughout."""
+    from oracle import vo_pipeline_oracle as vp
+    frames, truth = mvo_synth.room_sequence(0, 16)
+    planes = mvo_synth._room_planes(0)
+    blank = np.full_like(frames[0], 117)
+    far = truth[12].copy()
+    far[:3, 3] += np.array([1.2, 0.0, 2.6])       # 2.9 m = 0.48 in the units of the normalised map (threshold 0.3)
+    seq = frames[:3] + [blank] + frames[3:10] + [blank] + frames[10:12] + [mvo_synth.render_room(far, planes)] + frames[12:]
+    oracle, rows, (ids, pts, n_kf, _) = _run_both(hostcheck, seq, 2000, 10)
+    for i, (T_o, io, T_p, ip) in enumerate(rows):
+        assert (io["state_out"], io["keyframe"], io["map_points"], io["n_keypoints"], io["n_matches"], io["n_inliers"], io["pnp_ok"]) == \
+               (ip.state_out, ip.keyframe, ip.map_points, ip.n_keypoints, ip.n_matches, ip.n_inliers, ip.pnp_ok), i
+        assert np.abs(T_o - T_p).max() < POSE_TOL, i
+    info = [r[1] for r in rows]
+    assert info[3]["n_keypoints"] == 0 and info[3]["state_out"] == vp.DOING_INITIALIZATION
+    assert info[8]["state_out"] == vp.DOING_TRACKING                                # initialised in spite of the blank frame
+    assert info[11]["n_keypoints"] == 0 and info[11]["pnp_ok"] == 0 and np.array_equal(rows[11][0], rows[10][0])
+    assert info[14]["pnp_ok"] == 0 and np.array_equal(rows[14][0], rows[13][0])      # the far-away view is not accepted
+    assert all(i["pnp_ok"] == 1 for i in info[15:])                                 # and tracking resumes
+    assert ids.tolist() == oracle.map.keys() and n_kf == len(oracle.keyframes)
