@@ -86,6 +86,13 @@ def test_config_yaml(lib):
         lib.mvo_default_track_params(C.byref(tp))
         K = np.zeros(9)
         assert lib.mvo_config_apply(h, C.byref(p), C.byref(tp), K.ctypes.data) == 0
+        vp = mvo_b200.VoParams()
+        lib.mvo_vo_default_params(C.byref(vp))
+        vp.min_inlier_matches, vp.assumed_mean_depth_init, vp.track.ba_window = -1, -1.0, -1
+        assert lib.mvo_config_apply_vo(h, C.byref(vp)) == 0                                                 # vo.cpp / vo_addFrame.cpp keys
+        assert (vp.match_method_init, vp.max_match_dist_init, vp.max_match_dist_triangulation, vp.min_inlier_matches) == (1, 100.0, 100.0, 15)
+        assert (vp.essential_threshold, vp.min_triang_angle, vp.max_ratio_angle_to_median, vp.min_pixel_dist) == (1.0, 1.0, 20.0, 50.0)
+        assert (vp.min_median_triangulation_angle, vp.assumed_mean_depth_init, vp.track.ba_window, vp.track.match_radius) == (2.0, 0.8, 5, 50.0)
         assert (p.orb_nfeatures, p.orb_nlevels, p.orb_fast_threshold, p.max_keypoints, p.grid_size, p.max_pts_per_grid) == (8000, 4, 20, 2000, 16, 8)
         assert abs(p.orb_scale_factor - 1.2) < 1e-6 and (p.xiang_gao_ratio, p.lowe_ratio) == (2.0, 1.0)
         assert (tp.match_method, tp.match_radius, tp.ba_enable, tp.ba_window, tp.ba_fix_points) == (1, 50.0, 1, 5, 1)
