@@ -422,7 +422,7 @@ constexpr int HOMO_NV = epi::HOMO_GN_NV;    // 45 entries of J^T J (upper triang
 
 // out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
 // [3] consensus of the best minimal model, [4] consensus after the local optimisation
-__global__ void __launch_bounds__(EFIN_T)
+__global__ void __launch_bounds__(EFIN_T, 1)
 k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
               const double *__restrict__ Hs, const int32_t *__restrict__ counts, double *__restrict__ out_d,
               int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
