@@ -1,6 +1,6 @@
 import sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python")); sys.path.insert(0, str(ROOT))
 import numpy as np, mvo_b200, mvo_synth
 from oracle import oracle_lib

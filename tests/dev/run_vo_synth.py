@@ -1,6 +1,6 @@
 """The whole VO state machine (mvo_vo_*) on the ray-cast room sequence next to the oracle pipeline on the same frames:
 frames/s of both and the trajectory error of both against the ground truth.  GPU needed.
-Usage: python tools/run_vo_synth.py [n_frames] [calc_homography 0|1] > gpurun_out/run_vo_synth.json"""
+Usage: python tests/dev/run_vo_synth.py [n_frames] [calc_homography 0|1] > gpurun_out/run_vo_synth.json"""
 import json
 import sys
 import time
@@ -8,7 +8,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python"))
 import mvo_b200  # noqa: E402
