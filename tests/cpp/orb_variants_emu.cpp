@@ -1,0 +1,158 @@
+// TEST INFRASTRUCTURE (CPU tier): csrc/orb_variants.cuh — the very text nvcc compiles for the experimental k_blur2 /
+// k_describe_sel2 kernels — compiled for the host and executed one OS thread per CUDA thread, one block at a time:
+// threadIdx / blockIdx are thread-local, __shared__ arrays are function-local statics (one block runs at a time),
+// __syncthreads() is a barrier over the block's threads, __shfl_xor_sync an exchange through a per-warp buffer with two
+// warp barriers, and the round-to-nearest intrinsics are plain float operations (built with -ffp-contract=off).
+// This checks the index arithmetic and the data flow of the kernels against the oracle without a GPU; what it cannot
+// show is timing and anything specific to the hardware's scheduling.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
+static thread_local EmuIdx threadIdx, blockIdx;
+static EmuIdx blockDim, gridDim;
+static pthread_barrier_t g_block_barrier;
+static pthread_barrier_t g_warp_barrier[32];
+static int g_xchg[32][32];
+
+#undef __shared__
+#define __shared__ static
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __align__
+#define __align__(n) __attribute__((aligned(n)))
+
+static inline void __syncthreads() { pthread_barrier_wait(&g_block_barrier); }
+static inline int __shfl_xor_sync(unsigned, int v, int d) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  g_xchg[w][l] = v;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  const int r = g_xchg[w][l ^ d];
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  return r;
+}
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline int __float2int_rn(float x) { return (int)nearbyintf(x); }      // round half to even (default rounding mode)
+using std::max;
+using std::min;
+
+#include "orb.cuh"
+namespace {
+#include "orb_pattern.inc"
+float c_gauss7[7];
+constexpr int BLUR_TW = 128, BLUR_TH = 16;                        // as in orb.cu
+struct BlurTiles { int first[MVO_MAX_LEVELS + 1]; int nx[MVO_MAX_LEVELS]; };
+constexpr int DESC_WARPS = 8;
+#include "orb_variants.cuh"
+
+template <class F> void run_grid(unsigned gx, unsigned gy, unsigned gz, unsigned threads, F &&kernel) {
+  gridDim = EmuIdx{gx, gy, gz};
+  blockDim = EmuIdx{threads, 1, 1};
+  const unsigned warps = threads / 32;
+  for (unsigned bz = 0; bz < gz; ++bz)
+    for (unsigned by = 0; by < gy; ++by)
+      for (unsigned bx = 0; bx < gx; ++bx) {
+        pthread_barrier_init(&g_block_barrier, nullptr, threads);
+        for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (unsigned t = 0; t < threads; ++t)
+          pool.emplace_back([&, t] {
+            threadIdx = EmuIdx{t, 0, 0};
+            blockIdx = EmuIdx{bx, by, bz};
+            kernel();
+          });
+        for (auto &th : pool) th.join();
+        pthread_barrier_destroy(&g_block_barrier);
+        for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
+      }
+}
+
+// one pyramid level per "plan level", planes laid out like orb_host.cpp does (pitch multiple of 128, 256-byte aligned offsets)
+OrbPlanDev make_plan(int nlevels, const int *w, const int *h, const float *scale, std::vector<uint8_t> *planes) {
+  OrbPlanDev pl;
+  memset(&pl, 0, sizeof pl);
+  pl.nlevels = nlevels;
+  size_t off = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    OrbLevelDev &L = pl.lv[l];
+    L.w = w[l]; L.h = h[l]; L.scale = scale[l];
+    L.pitch = (L.w + 127) & ~127;
+    L.img_off = (uint32_t)off; off = (off + (size_t)L.pitch * L.h + 255) & ~(size_t)255;
+    L.blur_off = (uint32_t)off; off = (off + (size_t)L.pitch * L.h + 255) & ~(size_t)255;
+  }
+  pl.slot_bytes = (uint32_t)off;
+  planes->assign(off + 64, 0xA5);                                  // padding bytes hold junk, like recycled device memory
+  return pl;
+}
+}  // namespace
+
+extern "C" {
+
+// imgs: the level images back to back (w[l] x h[l] bytes each); out: the blurred levels in the same packing
+int emu_blur2(int nlevels, const int *w, const int *h, const uint8_t *imgs, uint8_t *out) {
+  double k[7], s = 0;                                              // cv::getGaussianKernel(7, 2, CV_32F), as upload_gauss (orb.cu)
+  for (int i = 0; i < 7; ++i) { const double x = i - 3; k[i] = exp(-x * x / 8.0); s += k[i]; }
+  for (int i = 0; i < 7; ++i) c_gauss7[i] = (float)(k[i] / s);
+  std::vector<uint8_t> planes;
+  std::vector<float> scale((size_t)nlevels, 1.f);
+  const OrbPlanDev pl = make_plan(nlevels, w, h, scale.data(), &planes);
+  const uint8_t *src = imgs;
+  for (int l = 0; l < nlevels; ++l) {
+    for (int y = 0; y < h[l]; ++y) memcpy(&planes[pl.lv[l].img_off + (size_t)y * pl.lv[l].pitch], src + (size_t)y * w[l], (size_t)w[l]);
+    src += (size_t)w[l] * h[l];
+  }
+  BlurTiles tiles;
+  int total = 0;
+  for (int l = 0; l < nlevels; ++l) {                              // as orb_launch_blur
+    tiles.first[l] = total;
+    tiles.nx[l] = (w[l] + BLUR_TW - 1) / BLUR_TW;
+    total += tiles.nx[l] * ((h[l] + BLUR_TH - 1) / BLUR_TH);
+  }
+  tiles.first[nlevels] = total;
+  uint8_t *p = planes.data();
+  run_grid((unsigned)total, 1, 1, 256, [&] { k_blur2(pl, tiles, p); });
+  uint8_t *dst = out;
+  for (int l = 0; l < nlevels; ++l) {
+    for (int y = 0; y < h[l]; ++y) memcpy(dst + (size_t)y * w[l], &planes[pl.lv[l].blur_off + (size_t)y * pl.lv[l].pitch], (size_t)w[l]);
+    dst += (size_t)w[l] * h[l];
+  }
+  return 0;
+}
+
+// imgs / blurred: level images back to back; sel: n x (packed x | y << 12, level); outputs: n keypoints, n x 32 descriptor bytes
+int emu_describe_sel2(int nlevels, const int *w, const int *h, const float *scale, const uint8_t *imgs, const uint8_t *blurred,
+                      const uint32_t *sel_xy, const uint32_t *sel_level, int n, mvo_keypoint *kout, uint8_t *desc) {
+  std::vector<uint8_t> planes;
+  OrbPlanDev pl = make_plan(nlevels, w, h, scale, &planes);
+  pl.max_kpts = n;                                                 // selection rows are max_kpts + 1 apart
+  const uint8_t *a = imgs, *b = blurred;
+  for (int l = 0; l < nlevels; ++l) {
+    for (int y = 0; y < h[l]; ++y) {
+      memcpy(&planes[pl.lv[l].img_off + (size_t)y * pl.lv[l].pitch], a + (size_t)y * w[l], (size_t)w[l]);
+      memcpy(&planes[pl.lv[l].blur_off + (size_t)y * pl.lv[l].pitch], b + (size_t)y * w[l], (size_t)w[l]);
+    }
+    a += (size_t)w[l] * h[l]; b += (size_t)w[l] * h[l];
+  }
+  std::vector<uint2> sel((size_t)n + 1);
+  for (int i = 0; i < n; ++i) sel[(size_t)i] = make_uint2(sel_xy[i], sel_level[i]);
+  OrbFrameMeta meta;
+  memset(&meta, 0, sizeof meta);
+  meta.n_sel = n;
+  int32_t count = -1;
+  const int blocks = std::max(1, std::min(8, (n + DESC_WARPS - 1) / DESC_WARPS));      // grid-stride loop: any grid size covers all keypoints
+  const uint8_t *p = planes.data();
+  run_grid((unsigned)blocks, 1, 1, DESC_WARPS * 32, [&] { k_describe_sel2(pl, p, sel.data(), &meta, nullptr, kout, desc, &count, n, 1); });
+  return count;
+}
+
+}  // extern "C"
