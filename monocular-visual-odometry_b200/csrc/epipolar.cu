@@ -23,528 +23,8 @@
 
 namespace {
 
-__device__ __forceinline__ uint64_t splitmix64e(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-
-struct EpiCam { double f, cx, cy; };      // findEssentialMat(focal, pp): one focal length (epipolar_geometry.cpp:26-27)
-
-__global__ void __launch_bounds__(128)
-k_epi_hypotheses(const float *__restrict__ p1, const float *__restrict__ p2, int n, EpiCam cam, uint64_t seed, int H,
-                 double *__restrict__ Es, int32_t *__restrict__ valid) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  int idx[8];
-  uint64_t ctr = 0;
-  for (int k = 0; k < 8; ++k)
-    for (int attempt = 0; attempt < 64; ++attempt) {
-      const uint64_t r = splitmix64e(seed ^ splitmix64e(((uint64_t)h << 20) ^ ctr++));
-      const int cand = (int)(r % (uint64_t)n);
-      bool dup = false;
-      for (int q = 0; q < k; ++q) dup |= idx[q] == cand;
-      idx[k] = cand;
-      if (!dup) break;
-    }
-  double a[16], b[16];
-  const double inv = 1.0 / cam.f;
-  for (int k = 0; k < 8; ++k) {
-    a[2 * k] = ((double)p1[2 * idx[k]] - cam.cx) * inv; a[2 * k + 1] = ((double)p1[2 * idx[k] + 1] - cam.cy) * inv;
-    b[2 * k] = ((double)p2[2 * idx[k]] - cam.cx) * inv; b[2 * k + 1] = ((double)p2[2 * idx[k] + 1] - cam.cy) * inv;
-  }
-  double E[9];
-  int reason = 0;
-  const bool ok = epi::essential_from_8(a, b, E, &reason);
-  for (int q = 0; q < 9; ++q) Es[(size_t)h * 9 + q] = ok ? E[q] : 0.0;
-  valid[h] = ok ? 1 : -reason;             // <= 0: rejected sample (the reason is kept for MVO_EPI_DEBUG)
-}
-
-__global__ void __launch_bounds__(256)
-k_epi_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, EpiCam cam, double thr2, int H,
-            const double *__restrict__ Es, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
-  extern __shared__ double s_pt[];         // [n][4] calibrated coordinates x1 y1 x2 y2
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_pt[4 * i] = ((double)p1[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 1] = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    s_pt[4 * i + 2] = ((double)p2[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 3] = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  for (int h = blockIdx.x * wpb + warp; h < H; h += gridDim.x * wpb) {
-    if (valid[h] <= 0) { if (lane == 0) counts[h] = -1; continue; }
-    double E[9];
-    for (int q = 0; q < 9; ++q) E[q] = Es[(size_t)h * 9 + q];
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += epi::sampson_err(E, s_pt[4 * i], s_pt[4 * i + 1], s_pt[4 * i + 2], s_pt[4 * i + 3]) <= thr2;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) counts[h] = c;
-  }
-}
-
-constexpr int EFIN_T = 1024;
-constexpr int EPI_LO_ROUNDS = 3, EPI_GN_ITERS = 8;
-
-__device__ __forceinline__ void skew_times(const double *t, const double *R, double *E) {      // E = [t]x R
-  for (int j = 0; j < 3; ++j) {
-    E[0 * 3 + j] = -t[2] * R[1 * 3 + j] + t[1] * R[2 * 3 + j];
-    E[1 * 3 + j] = t[2] * R[0 * 3 + j] - t[0] * R[2 * 3 + j];
-    E[2 * 3 + j] = -t[1] * R[0 * 3 + j] + t[0] * R[1 * 3 + j];
-  }
-}
-
-__device__ void so3_exp(const double *w, double *R) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
-  double A, B;
-  if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
-  else { A = sin(th) / th; B = (1 - cos(th)) / th2; }
-  const double x = w[0], y = w[1], z = w[2];
-  R[0] = 1 - B * (y * y + z * z); R[1] = -A * z + B * x * y;      R[2] = A * y + B * x * z;
-  R[3] = A * z + B * x * y;       R[4] = 1 - B * (x * x + z * z); R[5] = -A * x + B * y * z;
-  R[6] = -A * y + B * x * z;      R[7] = A * x + B * y * z;       R[8] = 1 - B * (x * x + y * y);
-}
-
-// (R, t) moved by d = (rotation increment on the right, two tangent-plane components of the unit translation)
-__device__ void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
-  double dR[9];
-  so3_exp(d, dR);
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) Ro[i * 3 + j] = R[i * 3] * dR[j] + R[i * 3 + 1] * dR[3 + j] + R[i * 3 + 2] * dR[6 + j];
-  double a[3] = {1, 0, 0};
-  if (fabs(t[0]) >= 0.9) { a[0] = 0; a[1] = 1; }
-  double b1[3], b2[3];
-  epi::cross3(t, a, b1);
-  const double n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
-  for (int i = 0; i < 3; ++i) b1[i] /= n1;
-  epi::cross3(t, b1, b2);
-  double n = 0;
-  for (int i = 0; i < 3; ++i) { to[i] = t[i] + d[3] * b1[i] + d[4] * b2[i]; n += to[i] * to[i]; }
-  n = sqrt(n);
-  for (int i = 0; i < 3; ++i) to[i] /= n;
-}
-
-__device__ __forceinline__ double sampson_signed(const double *E, double x1, double y1, double x2, double y2) {
-  const double Ex0 = E[0] * x1 + E[1] * y1 + E[2], Ex1 = E[3] * x1 + E[4] * y1 + E[5], Ex2 = E[6] * x1 + E[7] * y1 + E[8];
-  const double Et0 = E[0] * x2 + E[3] * y2 + E[6], Et1 = E[1] * x2 + E[4] * y2 + E[7];
-  return (x2 * Ex0 + y2 * Ex1 + Ex2) * rsqrt(Ex0 * Ex0 + Ex1 * Ex1 + Et0 * Et0 + Et1 * Et1);
-}
-
-// out_d: [0..8] E (scaled so that E[8] = 1, epipolar_geometry.cpp:37), [9..17] R, [18..20] t (unit); out_i: [0] inliers,
-// [1] best hypothesis, [2] cheirality votes of the chosen (R, t), [3] consensus of the best minimal model
-//
-// After the arg-max the best minimal model is locally optimised (LO-RANSAC style): EPI_LO_ROUNDS times its consensus
-// set is re-selected and (R, t/|t|) is re-estimated on it by Gauss-Newton on the signed Sampson residual (5 degrees of
-// freedom, forward-difference Jacobian).  OpenCV returns the minimal five-point model as it is; the eight-point
-// minimal models used here are noisier, and the local optimisation more than makes up for it (pose errors against
-// synthetic truth ~10x below cv2's on the test scenes).  The reported inliers are the consensus set of the final model.
-__global__ void __launch_bounds__(EFIN_T)
-k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, EpiCam cam, double thr2, int H,
-             const double *__restrict__ Es, const int32_t *__restrict__ counts, double *__restrict__ out_d,
-             int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
-  __shared__ long long s_k[32];
-  __shared__ int s_best, s_cnt[32], s_good[4][32], s_stop;
-  __shared__ double s_E[9], s_R1[9], s_R2[9], s_t[3], s_R[9], s_E0[9];
-  __shared__ double s_Ek[6][9], s_red[32][20], s_sum[20];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  long long best = -1;
-  for (int h = tid; h < H; h += EFIN_T) {
-    const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
-    best = key > best ? key : best;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-  if (lane == 0) s_k[warp] = best;
-  __syncthreads();
-  if (tid == 0) {
-    long long b = -1;
-    for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
-    s_best = (int)(b >> 20) >= 8 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
-    out_i[3] = (int)(b >> 20);
-  }
-  __syncthreads();
-  if (s_best < 0) {
-    if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
-    return;
-  }
-  if (tid == 0) {
-    for (int q = 0; q < 9; ++q) s_E[q] = Es[(size_t)s_best * 9 + q];
-    epi::decompose_essential(s_E, s_R1, s_R2, s_t);
-    for (int q = 0; q < 9; ++q) { s_R[q] = s_R1[q]; s_E0[q] = s_E[q]; }      // either rotation of the twisted pair spans the same E = [t]x R (up to sign)
-    skew_times(s_t, s_R, s_E);
-  }
-  __syncthreads();
-  // this thread's points (contiguous chunk), calibrated coordinates
-  const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
-  // ---- local optimisation ----
-  for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
-    double Esel[9];
-    for (int q = 0; q < 9; ++q) Esel[q] = s_E[q];          // consensus set of this round: fixed during its GN iterations
-    for (int it = 0; it < EPI_GN_ITERS; ++it) {
-      if (tid < 6) {                                         // E at the current estimate and at its 5 forward perturbations
-        double d[5] = {0, 0, 0, 0, 0}, Rk[9], tk[3];
-        if (tid > 0) d[tid - 1] = 1e-6;
-        epi_retract(s_R, s_t, d, Rk, tk);
-        skew_times(tk, Rk, s_Ek[tid]);
-      }
-      if (tid == 0) s_stop = 0;
-      __syncthreads();
-      double acc[20];
-#pragma unroll
-      for (int q = 0; q < 20; ++q) acc[q] = 0;
-      for (int i = b0; i < e0; ++i) {
-        const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-        const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-        if (!(epi::sampson_err(Esel, x1, y1, x2, y2) <= thr2)) continue;
-        const double r0 = sampson_signed(s_Ek[0], x1, y1, x2, y2);
-        double J[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) J[k] = (sampson_signed(s_Ek[k + 1], x1, y1, x2, y2) - r0) * 1e6;
-        int q = 0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r)
-#pragma unroll
-          for (int c = r; c < 5; ++c) acc[q++] += J[r] * J[c];
-#pragma unroll
-        for (int r = 0; r < 5; ++r) acc[15 + r] += J[r] * r0;
-      }
-#pragma unroll
-      for (int q = 0; q < 20; ++q) {
-        double v = acc[q];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) s_red[warp][q] = v;
-      }
-      __syncthreads();
-      if (tid < 20) { double v = 0; for (int w = 0; w < 32; ++w) v += s_red[w][tid]; s_sum[tid] = v; }
-      __syncthreads();
-      if (tid == 0) {
-        // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
-        double A[5][6];
-        int q = 0;
-        for (int r = 0; r < 5; ++r) for (int c = r; c < 5; ++c) { A[r][c] = s_sum[q]; A[c][r] = s_sum[q]; ++q; }
-        double tr = 0;
-        for (int r = 0; r < 5; ++r) tr += A[r][r];
-        for (int r = 0; r < 5; ++r) { A[r][r] += 1e-12 * tr + 1e-300; A[r][5] = -s_sum[15 + r]; }
-        bool ok = true;
-        for (int k = 0; k < 5 && ok; ++k) {
-          int pr = k;
-          for (int r = k + 1; r < 5; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
-          if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
-          if (pr != k) for (int c = 0; c < 6; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
-          for (int r = k + 1; r < 5; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 6; ++c) A[r][c] -= f * A[k][c]; }
-        }
-        double dx[5] = {0, 0, 0, 0, 0}, mx = 0;
-        if (ok) {
-          for (int r = 4; r >= 0; --r) { double v = A[r][5]; for (int c = r + 1; c < 5; ++c) v -= A[r][c] * dx[c]; dx[r] = v / A[r][r]; }
-          for (int r = 0; r < 5; ++r) { if (!isfinite(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
-        }
-        if (ok && mx < 0.5) {                                 // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
-          double Rn[9], tn[3];
-          epi_retract(s_R, s_t, dx, Rn, tn);
-          for (int r = 0; r < 9; ++r) s_R[r] = Rn[r];
-          for (int r = 0; r < 3; ++r) s_t[r] = tn[r];
-        }
-        if (!ok || mx < 1e-10 || mx >= 0.5) s_stop = 1;
-      }
-      __syncthreads();
-      if (s_stop) break;
-    }
-    if (tid == 0) skew_times(s_t, s_R, s_E);
-    __syncthreads();
-  }
-  // the local optimisation must not lose support: otherwise the minimal model stands
-  {
-    int c = 0;
-    for (int i = b0; i < e0; ++i) {
-      const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-      const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-      c += epi::sampson_err(s_E, x1, y1, x2, y2) <= thr2;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_cnt[warp] = c;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < 32; ++w) tot += s_cnt[w];
-      out_i[4] = tot;
-      if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_E[q] = s_E0[q];
-    }
-    __syncthreads();
-  }
-  // ---- consensus set of the final model, ascending (the mask of findEssentialMat, epipolar_geometry.cpp:40-47) ----
-  if (tid == 0) epi::decompose_essential(s_E, s_R1, s_R2, s_t);
-  double E[9];
-  for (int q = 0; q < 9; ++q) E[q] = s_E[q];
-  int mine = 0;
-  for (int i = b0; i < e0; ++i) {
-    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-    mine += epi::sampson_err(E, x1, y1, x2, y2) <= thr2;
-  }
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-  if (lane == 31) s_cnt[warp] = incl;
-  __syncthreads();                                   // also publishes R1, R2, t
-  int off = incl - mine, n_in = 0;
-  for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
-  // recoverPose (calib3d five-point.cpp): triangulate every inlier with [I|0] and each of (R1,t) (R2,t) (R1,-t) (R2,-t);
-  // a point votes for a candidate when its depth is in (0, 50) in both cameras
-  int good[4] = {0, 0, 0, 0};
-  const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  for (int i = b0; i < e0; ++i) {
-    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-    if (!(epi::sampson_err(E, x1, y1, x2, y2) <= thr2)) continue;
-    inl[off++] = i;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const double *R = (c & 1) ? s_R2 : s_R1;
-      const double sg = c < 2 ? 1.0 : -1.0;
-      double P[12];
-      for (int r = 0; r < 3; ++r) { P[4 * r] = R[3 * r]; P[4 * r + 1] = R[3 * r + 1]; P[4 * r + 2] = R[3 * r + 2]; P[4 * r + 3] = sg * s_t[r]; }
-      double X[4];
-      epi::triangulate_dlt(P0, P, x1, y1, x2, y2, X);
-      bool ok = X[2] * X[3] > 0;                     // mask = Q.z * Q.w > 0
-      const double z1 = X[2] / X[3];
-      ok = ok && z1 < 50.0;                          // distanceThresh
-      const double z2 = (P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * X[3]) / X[3];
-      ok = ok && z2 > 0 && z2 < 50.0;
-      good[c] += ok;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    int g = good[c];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffffffu, g, d);
-    if (lane == 0) s_good[c][warp] = g;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int g[4] = {0, 0, 0, 0};
-    for (int c = 0; c < 4; ++c) for (int w = 0; w < 32; ++w) g[c] += s_good[c][w];
-    // OpenCV's order: (R1,t) if good1 is a maximum, else (R2,t), else (R1,-t), else (R2,-t)
-    int pick = 3;
-    if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
-    else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
-    else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
-    const double *R = (pick & 1) ? s_R2 : s_R1;
-    const double sg = pick < 2 ? 1.0 : -1.0;
-    const double e22 = s_E[8];
-    for (int q = 0; q < 9; ++q) { out_d[q] = s_E[q] / e22; out_d[9 + q] = R[q]; }       // E /= E(2,2) (:37)
-    const double nt = sqrt(s_t[0] * s_t[0] + s_t[1] * s_t[1] + s_t[2] * s_t[2]);          // t /= |t| (:54-55)
-    for (int q = 0; q < 3; ++q) out_d[18 + q] = sg * s_t[q] / nt;
-    out_i[0] = n_in; out_i[1] = s_best; out_i[2] = g[pick];
-  }
-}
-
-__global__ void __launch_bounds__(128)
-k_triangulate(const float *__restrict__ np1, const float *__restrict__ np2, const int32_t *__restrict__ inl, int n_in,
-              const double *__restrict__ Rt /* 9 + 3 */, float *__restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_in) return;
-  const int i = inl[j];
-  const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  double P[12];
-  for (int r = 0; r < 3; ++r) { P[4 * r] = Rt[3 * r]; P[4 * r + 1] = Rt[3 * r + 1]; P[4 * r + 2] = Rt[3 * r + 2]; P[4 * r + 3] = Rt[9 + r]; }
-  double X[4];
-  epi::triangulate_dlt(P0, P, np1[2 * i], np1[2 * i + 1], np2[2 * i], np2[2 * i + 1], X);
-  // pts4d is CV_32F for float input points; the reference divides by the fourth coordinate in float (:161-168)
-  const float x = (float)X[0], y = (float)X[1], z = (float)X[2], w = (float)X[3];
-  out[3 * j] = x / w; out[3 * j + 1] = y / w; out[3 * j + 2] = z / w;
-}
-
-// ---------------------------------------------------------------------------------------------------- homography
-// estiMotionByHomography (reference src/geometry/epipolar_geometry.cpp:90-128): cv::findHomography(pts1, pts2, RANSAC,
-// 3.0, mask) + H /= H(2,2) + inliers from the mask + cv::decomposeHomographyMat(H, K) + t /= |t|.  Same batched design
-// as the essential-matrix path: H four-point hypotheses, forward transfer error consensus (the error OpenCV
-// thresholds), local optimisation of the best one by Gauss-Newton on the transfer error over its consensus set
-// (OpenCV refines its RANSAC result with LM on the same cost).  All three kernels work in isotropically scaled pixel
-// coordinates ((u - cx) / f, (v - cy) / f, f = mean focal length): errors scale by 1 / f, the conditioning of the
-// 4-point systems and of the normal equations does not depend on the image size.  The decomposition itself is a few
-// hundred flops and runs on the host (the same epipolar_math.cuh routine).
-struct HomoCam { double f, cx, cy; };
-
-__global__ void __launch_bounds__(128)
-k_homo_hypotheses(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, uint64_t seed, int H,
-                  double *__restrict__ Hs, int32_t *__restrict__ valid) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  int idx[4];
-  uint64_t ctr = 0;
-  for (int k = 0; k < 4; ++k)
-    for (int attempt = 0; attempt < 64; ++attempt) {
-      const uint64_t r = splitmix64e(seed ^ splitmix64e(((uint64_t)h << 20) ^ (0x5bd1e995ull + ctr++)));
-      const int cand = (int)(r % (uint64_t)n);
-      bool dup = false;
-      for (int q = 0; q < k; ++q) dup |= idx[q] == cand;
-      idx[k] = cand;
-      if (!dup) break;
-    }
-  double a[8], b[8];
-  const double inv = 1.0 / cam.f;
-  for (int k = 0; k < 4; ++k) {
-    a[2 * k] = ((double)p1[2 * idx[k]] - cam.cx) * inv; a[2 * k + 1] = ((double)p1[2 * idx[k] + 1] - cam.cy) * inv;
-    b[2 * k] = ((double)p2[2 * idx[k]] - cam.cx) * inv; b[2 * k + 1] = ((double)p2[2 * idx[k] + 1] - cam.cy) * inv;
-  }
-  double Hm[9];
-  const bool ok = epi::homography_from_4(a, b, Hm);
-  for (int q = 0; q < 9; ++q) Hs[(size_t)h * 9 + q] = ok ? Hm[q] : 0.0;
-  valid[h] = ok ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256)
-k_homo_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
-             const double *__restrict__ Hs, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
-  extern __shared__ double s_pt[];         // [n][4] scaled coordinates x1 y1 x2 y2
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_pt[4 * i] = ((double)p1[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 1] = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    s_pt[4 * i + 2] = ((double)p2[2 * i] - cam.cx) / cam.f; s_pt[4 * i + 3] = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  for (int h = blockIdx.x * wpb + warp; h < H; h += gridDim.x * wpb) {
-    if (valid[h] <= 0) { if (lane == 0) counts[h] = -1; continue; }
-    double Hm[9];
-    for (int q = 0; q < 9; ++q) Hm[q] = Hs[(size_t)h * 9 + q];
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += epi::homography_transfer_err(Hm, s_pt[4 * i], s_pt[4 * i + 1], s_pt[4 * i + 2], s_pt[4 * i + 3]) <= thr2;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) counts[h] = c;
-  }
-}
-
-constexpr int HOMO_NV = epi::HOMO_GN_NV;    // 45 entries of J^T J (upper triangle) + 9 of J^T r
-
-// out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
-// [3] consensus of the best minimal model, [4] consensus after the local optimisation
-__global__ void __launch_bounds__(EFIN_T, 1)
-k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
-              const double *__restrict__ Hs, const int32_t *__restrict__ counts, double *__restrict__ out_d,
-              int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
-  __shared__ long long s_k[32];
-  __shared__ int s_best, s_cnt[32], s_stop;
-  __shared__ double s_H[9], s_H0[9], s_red[32][HOMO_NV], s_sum[HOMO_NV];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  long long best = -1;
-  for (int h = tid; h < H; h += EFIN_T) {
-    const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
-    best = key > best ? key : best;
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-  if (lane == 0) s_k[warp] = best;
-  __syncthreads();
-  if (tid == 0) {
-    long long b = -1;
-    for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
-    s_best = (int)(b >> 20) >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
-    out_i[3] = (int)(b >> 20);
-  }
-  __syncthreads();
-  if (s_best < 0) {
-    if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[4] = 0; }
-    return;
-  }
-  if (tid < 9) { const double v = Hs[(size_t)s_best * 9 + tid]; s_H[tid] = v; s_H0[tid] = v; }
-  __syncthreads();
-  const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
-  // ---- local optimisation: Gauss-Newton on the transfer error, additive update of the 9 entries (the scale of H is a
-  // null direction of the normal equations: a small damping fixes the gauge, H is renormalised after every step) ----
-  for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
-    double Hsel[9];
-    for (int q = 0; q < 9; ++q) Hsel[q] = s_H[q];
-    for (int it = 0; it < EPI_GN_ITERS; ++it) {
-      double Hc[9];
-      for (int q = 0; q < 9; ++q) Hc[q] = s_H[q];
-      if (tid == 0) s_stop = 0;
-      double acc[HOMO_NV];
-#pragma unroll
-      for (int q = 0; q < HOMO_NV; ++q) acc[q] = 0;
-      for (int i = b0; i < e0; ++i) {
-        const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-        const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-        if (!(epi::homography_transfer_err(Hsel, x1, y1, x2, y2) <= thr2)) continue;
-        epi::homography_gn_accumulate(Hc, x1, y1, x2, y2, acc);
-      }
-#pragma unroll
-      for (int q = 0; q < HOMO_NV; ++q) {
-        double vq = acc[q];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) vq += __shfl_xor_sync(0xffffffffu, vq, d);
-        if (lane == 0) s_red[warp][q] = vq;
-      }
-      __syncthreads();
-      if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
-      __syncthreads();
-      if (tid == 0) {
-        double Hn[9];
-        for (int q = 0; q < 9; ++q) Hn[q] = s_H[q];
-        if (epi::homography_gn_step(s_sum, Hn)) s_stop = 1;
-        for (int q = 0; q < 9; ++q) s_H[q] = Hn[q];
-      }
-      __syncthreads();
-      if (s_stop) break;
-    }
-    __syncthreads();
-  }
-  // the local optimisation must not lose support: otherwise the minimal model stands
-  {
-    int c = 0;
-    for (int i = b0; i < e0; ++i) {
-      const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-      const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-      c += epi::homography_transfer_err(s_H, x1, y1, x2, y2) <= thr2;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_cnt[warp] = c;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < 32; ++w) tot += s_cnt[w];
-      out_i[4] = tot;
-      if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_H[q] = s_H0[q];
-    }
-    __syncthreads();
-  }
-  // ---- consensus set of the final model, ascending (the mask of findHomography, epipolar_geometry.cpp:108-116) ----
-  double Hf[9];
-  for (int q = 0; q < 9; ++q) Hf[q] = s_H[q];
-  int mine = 0;
-  for (int i = b0; i < e0; ++i) {
-    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-    mine += epi::homography_transfer_err(Hf, x1, y1, x2, y2) <= thr2;
-  }
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-  __syncthreads();
-  if (lane == 31) s_cnt[warp] = incl;
-  __syncthreads();
-  int off = incl - mine, n_in = 0;
-  for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
-  for (int i = b0; i < e0; ++i) {
-    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
-    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-    if (epi::homography_transfer_err(Hf, x1, y1, x2, y2) <= thr2) inl[off++] = i;
-  }
-  if (tid == 0) {
-    // back to pixel coordinates: x_scaled = S x_pix with S = [1/f 0 -cx/f; 0 1/f -cy/f; 0 0 1]  =>  H_pix = S^-1 H S
-    const double f = cam.f, cx = cam.cx, cy = cam.cy;
-    const double S[9] = {1 / f, 0, -cx / f, 0, 1 / f, -cy / f, 0, 0, 1}, Si[9] = {f, 0, cx, 0, f, cy, 0, 0, 1};
-    double T[9], Hp[9];
-    epi::mat3_mul(Hf, S, T);
-    epi::mat3_mul(Si, T, Hp);
-    for (int q = 0; q < 9; ++q) out_d[q] = Hp[q] / Hp[8];                       // H /= H(2,2) (:107)
-    out_i[0] = n_in; out_i[1] = s_best;
-  }
-}
+#define EPI_DYN_SMEM(type, name) extern __shared__ type name[]
+#include "epipolar_kernels.cuh"
 
 // device-side unit test of epipolar_math.cuh (test hook: tests compare with the host build of the same header)
 __global__ void k_epi_math_test(const double *__restrict__ in, double *__restrict__ out) {

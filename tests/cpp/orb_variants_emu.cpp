@@ -5,45 +5,7 @@
 // warp barriers, and the round-to-nearest intrinsics are plain float operations (built with -ffp-contract=off).
 // This checks the index arithmetic and the data flow of the kernels against the oracle without a GPU; what it cannot
 // show is timing and anything specific to the hardware's scheduling.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <pthread.h>
-#include <stdint.h>
-#include <string.h>
-#include <algorithm>
-#include <thread>
-#include <vector>
-
-struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
-static thread_local EmuIdx threadIdx, blockIdx;
-static EmuIdx blockDim, gridDim;
-static pthread_barrier_t g_block_barrier;
-static pthread_barrier_t g_warp_barrier[32];
-static int g_xchg[32][32];
-
-#undef __shared__
-#define __shared__ static
-#undef __launch_bounds__
-#define __launch_bounds__(...)
-#undef __align__
-#define __align__(n) __attribute__((aligned(n)))
-
-static inline void __syncthreads() { pthread_barrier_wait(&g_block_barrier); }
-static inline int __shfl_xor_sync(unsigned, int v, int d) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  g_xchg[w][l] = v;
-  pthread_barrier_wait(&g_warp_barrier[w]);
-  const int r = g_xchg[w][l ^ d];
-  pthread_barrier_wait(&g_warp_barrier[w]);
-  return r;
-}
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fsub_rn(float a, float b) { return a - b; }
-static inline float __fdiv_rn(float a, float b) { return a / b; }
-static inline int __float2int_rn(float x) { return (int)nearbyintf(x); }      // round half to even (default rounding mode)
-using std::max;
-using std::min;
+#include "cuda_emu.h"
 
 #include "orb.cuh"
 namespace {
@@ -53,29 +15,6 @@ constexpr int BLUR_TW = 128, BLUR_TH = 16;                        // as in orb.c
 struct BlurTiles { int first[MVO_MAX_LEVELS + 1]; int nx[MVO_MAX_LEVELS]; };
 constexpr int DESC_WARPS = 8;
 #include "orb_variants.cuh"
-
-template <class F> void run_grid(unsigned gx, unsigned gy, unsigned gz, unsigned threads, F &&kernel) {
-  gridDim = EmuIdx{gx, gy, gz};
-  blockDim = EmuIdx{threads, 1, 1};
-  const unsigned warps = threads / 32;
-  for (unsigned bz = 0; bz < gz; ++bz)
-    for (unsigned by = 0; by < gy; ++by)
-      for (unsigned bx = 0; bx < gx; ++bx) {
-        pthread_barrier_init(&g_block_barrier, nullptr, threads);
-        for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
-        std::vector<std::thread> pool;
-        pool.reserve(threads);
-        for (unsigned t = 0; t < threads; ++t)
-          pool.emplace_back([&, t] {
-            threadIdx = EmuIdx{t, 0, 0};
-            blockIdx = EmuIdx{bx, by, bz};
-            kernel();
-          });
-        for (auto &th : pool) th.join();
-        pthread_barrier_destroy(&g_block_barrier);
-        for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
-      }
-}
 
 // one pyramid level per "plan level", planes laid out like orb_host.cpp does (pitch multiple of 128, 256-byte aligned offsets)
 OrbPlanDev make_plan(int nlevels, const int *w, const int *h, const float *scale, std::vector<uint8_t> *planes) {
@@ -120,7 +59,7 @@ int emu_blur2(int nlevels, const int *w, const int *h, const uint8_t *imgs, uint
   }
   tiles.first[nlevels] = total;
   uint8_t *p = planes.data();
-  run_grid((unsigned)total, 1, 1, 256, [&] { k_blur2(pl, tiles, p); });
+  run_grid((unsigned)total, 1, 1, 256, 0, [&] { k_blur2(pl, tiles, p); });
   uint8_t *dst = out;
   for (int l = 0; l < nlevels; ++l) {
     for (int y = 0; y < h[l]; ++y) memcpy(dst + (size_t)y * w[l], &planes[pl.lv[l].blur_off + (size_t)y * pl.lv[l].pitch], (size_t)w[l]);
@@ -151,7 +90,7 @@ int emu_describe_sel2(int nlevels, const int *w, const int *h, const float *scal
   int32_t count = -1;
   const int blocks = std::max(1, std::min(8, (n + DESC_WARPS - 1) / DESC_WARPS));      // grid-stride loop: any grid size covers all keypoints
   const uint8_t *p = planes.data();
-  run_grid((unsigned)blocks, 1, 1, DESC_WARPS * 32, [&] { k_describe_sel2(pl, p, sel.data(), &meta, nullptr, kout, desc, &count, n, 1); });
+  run_grid((unsigned)blocks, 1, 1, DESC_WARPS * 32, 0, [&] { k_describe_sel2(pl, p, sel.data(), &meta, nullptr, kout, desc, &count, n, 1); });
   return count;
 }
 

@@ -20,7 +20,7 @@ def emu(tmp_path_factory):
     so = tmp_path_factory.mktemp("orbemu") / "liborb_emu.so"
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", str(ROOT / "include"),
                     "-I", str(ROOT / "monocular-visual-odometry_b200" / "csrc"), "-I", "/usr/local/cuda/include",
-                    str(ROOT / "tests" / "cpp" / "orb_variants_emu.cpp"), "-o", str(so)], check=True)
+                    "-I", str(ROOT / "tests" / "cpp"), str(ROOT / "tests" / "cpp" / "orb_variants_emu.cpp"), "-o", str(so)], check=True)
     return C.CDLL(str(so))
 
 
