@@ -4,7 +4,9 @@
 //   __shared__             function-local static (only one block is alive at a time)
 //   __syncthreads()        pthread barrier over the block's threads
 //   __shfl_xor_sync / __shfl_up_sync   exchange through a per-warp buffer between two warp barriers (full masks only)
+//   __shfl_sync / __shfl_down_sync / __ballot_sync / __syncwarp   the same way;  atomic*  GCC atomics on the same address
 //   __fmul_rn ...          plain float operations (build with -ffp-contract=off), __float2int_rn = nearbyintf (half to even)
+//   __popc, __ffs, __vsadu4, __ldcg, __threadfence, clock64 (0)
 // It reproduces data flow and arithmetic, not timing or scheduling.  Include BEFORE the kernel header.
 #pragma once
 #include <cuda_runtime.h>
@@ -56,6 +58,62 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __float2int_rn(float x) { return (int)nearbyintf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float __fdividef(float a, float b) { return a / b; }        // approximate on the GPU: do not expect bit parity through it
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline unsigned __vsadu4(unsigned a, unsigned b) {                   // sum of absolute differences of the four unsigned bytes
+  unsigned s = 0;
+  for (int i = 0; i < 4; ++i) { const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF; s += (unsigned)(x > y ? x - y : y - x); }
+  return s;
+}
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+  const int w = threadIdx.x >> 5;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src & 31); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int o) {
+  const int l = threadIdx.x & 31;
+  return emu_exchange(v, l + o < 32 ? l + o : l);
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  g_xchg[w][l] = pred ? 1ull : 0ull;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  unsigned m = 0;
+  const unsigned lanes = std::min(32u, blockDim.x - 32u * (unsigned)w);
+  for (unsigned i = 0; i < lanes; ++i) m |= (unsigned)g_xchg[w][i] << i;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  return m;
+}
+static inline unsigned emu_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }     // %lanemask_lt (kernels read it through inline PTX)
+// atomics on shared or global memory: the GCC builtins on the same address
+template <class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double *p, double v) {
+  double old = *p, next;
+  do { next = old + v; } while (!__atomic_compare_exchange(p, &old, &next, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return old;
+}
+static inline float atomicAdd(float *p, float v) {
+  float old = *p, next;
+  do { next = old + v; } while (!__atomic_compare_exchange(p, &old, &next, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return old;
+}
+template <class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+template <class T> static inline T atomicMin(T *p, T v) { T old = *p; while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return old; }
+template <class T> static inline T atomicMax(T *p, T v) { T old = *p; while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return old; }
+static inline long long clock64() { return 0; }
 using std::max;
 using std::min;
 
