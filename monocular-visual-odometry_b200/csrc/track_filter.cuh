@@ -1,0 +1,257 @@
+// The match-list filter kernel (k_match_filter: thresholds of matchFeatures + removeDuplicatedMatches restated on the device,
+// see the comment in track.cu) and the projection helper it shares with the other tracking kernels — the text nvcc
+// compiles, in a header so that the CPU test tier can build it for the host (tests/cpp/track_filter_emu.cpp, through
+// tests/cpp/cuda_emu.h).  Included by track.cu inside an anonymous namespace.
+// MVO_DYN_SMEM(type, name) declares the kernel's dynamic shared memory (`extern __shared__ __align__(16) type name[]` for nvcc).
+#pragma once
+
+struct Rt12 { double v[12]; };   // R row-major (9) + t (3), world->camera
+
+// getMappointsInCurrentView_ (vo.cpp:16-49) for one map point: true when it is in front of the camera and inside the image
+__device__ __forceinline__ bool project_point(const float *__restrict__ map_pts, int i, const Rt12 &Tcw, double fx, double fy, double cx,
+                                              double cy, float fcols, float frows, float2 &uv) {
+  // basics::preTranslatePoint3f (opencv_funcs.cpp:67-78): double accumulation of T(row, j) * p[j], j = 0..3,
+  // narrowed to float.  Explicit _rn intrinsics: no FMA contraction, so the visibility decision is the one the
+  // host arithmetic of the reference takes.
+  const double p0 = map_pts[3 * i], p1 = map_pts[3 * i + 1], p2 = map_pts[3 * i + 2];
+  double q[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double acc = __dmul_rn(Tcw.v[3 * r], p0);
+    acc = __dadd_rn(acc, __dmul_rn(Tcw.v[3 * r + 1], p1));
+    acc = __dadd_rn(acc, __dmul_rn(Tcw.v[3 * r + 2], p2));
+    acc = __dadd_rn(acc, Tcw.v[9 + r]);
+    q[r] = acc;
+  }
+  const float xc = (float)q[0], yc = (float)q[1], zc = (float)q[2];
+  // geometry::cam2pixel: K(0,0) * p.x / p.z + K(0,2) in double, narrowed to Point2f
+  const float u = (float)__dadd_rn(__ddiv_rn(__dmul_rn(fx, (double)xc), (double)zc), cx);
+  const float v = (float)__dadd_rn(__ddiv_rn(__dmul_rn(fy, (double)yc), (double)zc), cy);
+  uv = make_float2(u, v);
+  return !(zc < 0) && (u > 0 && v > 0 && u < fcols && v < frows);
+}
+
+
+constexpr int MF_T = 1024;
+constexpr int MF_MAXN = 8192;        // match-list / keypoint capacity of the device path (host path beyond)
+
+struct FilterArgs {
+  const uint32_t *keys;     // [nmap * W]
+  uint8_t *vis;             // [nmap] in (project == 0) or out (project == 1)
+  int nmap, nk, method, n_cap;
+  double xg_ratio, lowe_ratio;
+  int2 *pairs;              // out: (map index, keypoint index), sorted by keypoint index
+  int32_t *info;            // out: [0] pairs, [1] candidates (map points in view), [2] status (0 ok, 1 host path needed)
+  // project == 1: getMappointsInCurrentView_ is evaluated here (methods 1/2: the matcher does not need the projections)
+  int project;
+  const float *map_pts;
+  Rt12 Tcw;
+  double fx, fy, cx, cy;
+  float fcols, frows;
+  // optional (p3 != nullptr): the 3d-2d pairs of poseEstimationPnP_ (vo.cpp:293-301) go straight into the PnP input arrays
+  const mvo_keypoint *kpts;
+  float *p3, *p2;
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  __syncthreads();                       // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  // every warp scans the 32 warp totals itself (one load + a shuffle scan instead of a serial loop)
+  int w = s_warp[lane];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+  total = __shfl_sync(0xffffffffu, w, 31);
+  const int before = __shfl_sync(0xffffffffu, w, warp) - __shfl_sync(0xffffffffu, s_warp[lane], warp);
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
+  MVO_DYN_SMEM(uint8_t, smraw);
+  const int cap = a.n_cap;
+  uint32_t *arr = (uint32_t *)smraw;                    // [cap]  (train << 16) | position in the match list
+  uint32_t *best = arr + cap;                           // [cap]  per keypoint: leftmost (position << 16 | list index)
+  uint16_t *amap = (uint16_t *)(best + cap);            // [cap]  map index of list entry i
+  uint16_t *Ls = amap + cap;                            // [cap]  Lo lists, segment [first,last) uses Ls[first..last)
+  uint16_t *Rs = Ls + cap;                              // [cap]
+  uint32_t *segA = (uint32_t *)(Rs + cap);              // [cap/16 + 2] segments of the current level (first | last << 16)
+  uint32_t *segB = segA + cap / 16 + 2;
+  __shared__ int s_warp[MF_T / 32];
+  __shared__ unsigned s_min;
+  __shared__ int s_nseg[2], s_status;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmap = a.nmap;
+  const bool sad = a.method == 3;
+  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; }
+  long long tph = clock64();        // phase cycle counters (thread 0) -> info[4..8]: prologue, compaction, sort levels, epilogue
+#define MF_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); a.info[4 + (i)] = (int32_t)(t_ - tph); tph = t_; } } while (0)
+  __syncthreads();
+  // ---- thresholds (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2), ordered compaction ----
+  const int per = (nmap + MF_T - 1) / MF_T, q0 = min(tid * per, nmap), q1 = min(q0 + per, nmap);
+  if (a.project) {          // every thread reads back only the flags it wrote itself
+    for (int q = q0; q < q1; ++q) { float2 uv; a.vis[q] = project_point(a.map_pts, q, a.Tcw, a.fx, a.fy, a.cx, a.cy, a.fcols, a.frows, uv) ? 1 : 0; }
+  }
+  int nvis = 0;
+  if (a.method != 2) {
+    unsigned m = 0xFFFFFFFFu;
+    for (int q = q0; q < q1; ++q) {
+      if (!a.vis[q]) continue;
+      ++nvis;
+      const uint32_t k = a.keys[q];
+      if (k != 0xFFFFFFFFu) m = min(m, k >> 16);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&s_min, m);
+  } else {
+    for (int q = q0; q < q1; ++q) nvis += a.vis[q] != 0;
+  }
+  __syncthreads();
+  double thr = 0;
+  if (a.method != 2) {
+    // min_dis = 9999999 when nothing matched; distance is a float (Hamming count, or SAD/32 through double)
+    const double min_dis = s_min == 0xFFFFFFFFu ? 9999999.0 : (sad ? (double)(float)((double)s_min / 32.0) : (double)(float)s_min);
+    thr = (double)fmaxf((float)(min_dis * a.xg_ratio), 30.0f);        // std::max<float>(min_dis * ratio, 30.0)
+  }
+  auto passes = [&](int q, uint32_t &train) -> bool {
+    if (!a.vis[q]) return false;
+    if (a.method != 2) {
+      const uint32_t k = a.keys[q];
+      if (k == 0xFFFFFFFFu) return false;
+      const uint32_t d = k >> 16;
+      const float dist = sad ? (float)((double)d / 32.0) : (float)d;
+      train = k & 0xFFFFu;
+      return (double)dist < thr;
+    }
+    const uint32_t k0 = a.keys[2 * q], k1 = a.keys[2 * q + 1];
+    if (k0 == 0xFFFFFFFFu) return false;
+    train = k0 & 0xFFFFu;
+    return (double)(float)(k0 >> 16) < a.lowe_ratio * (double)(float)(k1 >> 16);
+  };
+  int cnt = 0;
+  for (int q = q0; q < q1; ++q) { uint32_t tr; cnt += passes(q, tr); }
+  int n = 0, ncand = 0;
+  int pos = block_excl_scan(cnt, s_warp, n);
+  (void)block_excl_scan(nvis, s_warp, ncand);
+  if (n > cap || a.nk > cap) {                          // beyond the device path's capacity
+    if (tid == 0) { a.info[0] = 0; a.info[1] = ncand; a.info[2] = 1; }
+    return;
+  }
+  for (int q = q0; q < q1; ++q) {
+    uint32_t tr;
+    if (passes(q, tr)) { arr[pos] = (tr << 16) | (uint32_t)pos; amap[pos] = (uint16_t)q; ++pos; }
+  }
+  for (int i = tid; i < a.nk; i += MF_T) best[i] = 0xFFFFFFFFu;
+  if (tid == 0 && n > 16) { segA[0] = 0u | ((uint32_t)n << 16); s_nseg[0] = 1; }
+  __syncthreads();
+  MF_MARK(0);
+  // ---- quicksort phase of std::sort, level by level ----
+  int depth_limit = 0;
+  for (int m = n; m > 1; m >>= 1) ++depth_limit;        // std::__lg(n)
+  depth_limit *= 2;
+  uint32_t *cur = segA, *nxt = segB;
+  int level = 0, which = 0;
+  long long tlev = clock64();
+  while (true) {
+    const int nseg = s_nseg[which];
+    if (nseg == 0) break;
+    if (level >= depth_limit) { if (tid == 0) s_status = 1; break; }      // libstdc++ would heapsort from here
+    // __introsort_loop recurses on [cut, last) and continues with [first, cut): both go to the next level's lists
+    auto push = [&](int f, int l) {
+      if (l - f <= 16) return;                                              // left to the final insertion sort
+      const uint32_t seg = (uint32_t)f | ((uint32_t)l << 16);
+      nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = seg;
+    };
+    // one warp per segment
+    for (int s = warp; s < nseg; s += MF_T / 32) {
+      const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
+      // __move_median_to_first(first, first+1, mid, last-1)
+      if (lane == 0) {
+        const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+        const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
+        int pick;
+        if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+        else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+        const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
+      }
+      __syncwarp();
+      const uint32_t pivot = arr[first] >> 16;
+      const int lo = first + 1, len = last - lo;
+      int nL = 0, nR = 0;
+      for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        const bool inr = i < len;
+        const bool ge = inr && (arr[lo + i] >> 16) >= pivot;              // !(x < pivot): the left scan stops here
+        const bool le = inr && (arr[last - 1 - i] >> 16) <= pivot;        // !(pivot < x): the right scan stops here
+        const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
+        const unsigned below = (1u << lane) - 1u;
+        if (ge) Ls[lo + nL + __popc(bg & below)] = (uint16_t)(lo + i);
+        if (le) Rs[lo + nR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
+        nL += __popc(bg);
+        nR += __popc(bl);
+      }
+      __syncwarp();
+      const int nmin = min(nL, nR);
+      int K = 0;
+      for (int base = 0; base < nmin; base += 32) {
+        const int j = base + lane;
+        const bool sw = j < nmin && Ls[lo + j] < Rs[lo + j];
+        const unsigned b = __ballot_sync(0xffffffffu, sw);
+        if (sw) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
+        const int c = __popc(b);
+        K += c;
+        if (c < 32) break;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        int cut;
+        if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;                    // Lo[0] exists after the median step
+        else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
+        push(cut, last);
+        push(first, cut);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (level < 7) { const long long t_ = clock64(); a.info[9 + 2 * level] = (int32_t)(t_ - tlev); a.info[10 + 2 * level] = nseg; tlev = t_; }
+      s_nseg[which] = 0;
+    }
+    which ^= 1;
+    uint32_t *t = cur; cur = nxt; nxt = t;
+    ++level;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_status != 0) {
+    if (tid == 0) { a.info[0] = 0; a.info[1] = ncand; a.info[2] = 1; }
+    return;
+  }
+  MF_MARK(1);
+  if (tid == 0) a.info[8] = level;
+  // ---- final insertion sort is stable: of every run of equal keypoint indices the leftmost element survives ----
+  for (int p = tid; p < n; p += MF_T) atomicMin(&best[arr[p] >> 16], ((uint32_t)p << 16) | (arr[p] & 0xFFFFu));
+  __syncthreads();
+  const int pk = (a.nk + MF_T - 1) / MF_T, t0 = min(tid * pk, a.nk), t1 = min(t0 + pk, a.nk);
+  int c2 = 0;
+  for (int t = t0; t < t1; ++t) c2 += best[t] != 0xFFFFFFFFu;
+  int np = 0;
+  int o = block_excl_scan(c2, s_warp, np);
+  for (int t = t0; t < t1; ++t)
+    if (best[t] != 0xFFFFFFFFu) {
+      const int mi = (int)amap[best[t] & 0xFFFFu];
+      a.pairs[o] = make_int2(mi, t);
+      if (a.p3) {
+        a.p3[3 * o] = a.map_pts[3 * mi]; a.p3[3 * o + 1] = a.map_pts[3 * mi + 1]; a.p3[3 * o + 2] = a.map_pts[3 * mi + 2];
+        a.p2[2 * o] = a.kpts[t].x; a.p2[2 * o + 1] = a.kpts[t].y;
+      }
+      ++o;
+    }
+  if (tid == 0) { a.info[0] = np; a.info[1] = ncand; a.info[2] = 0; }
+  MF_MARK(2);
+#undef MF_MARK
+}
+
