@@ -142,3 +142,20 @@ template <class F> static void run_grid(unsigned gx, unsigned gy, unsigned gz, u
       }
   g_dyn_smem = nullptr;
 }
+
+// kernel launch as written in the product (`k<<<grid, block, smem, stream>>>(args)`, rewritten by tests/emu_build.py):
+// grid and block may be ints or dim3; blocks are one-dimensional in this code base.
+static inline EmuIdx emu_dim(const dim3 &d) { return EmuIdx{d.x, d.y, d.z}; }
+static inline EmuIdx emu_dim(int v) { return EmuIdx{(unsigned)v, 1, 1}; }
+static inline EmuIdx emu_dim(unsigned v) { return EmuIdx{v, 1, 1}; }
+template <class G, class B, class F> static void emu_launch(G grid, B block, size_t dyn_smem_bytes, F &&kernel) {
+  const EmuIdx g = emu_dim(grid), b = emu_dim(block);
+  run_grid(g.x, g.y, g.z, b.x, dyn_smem_bytes, kernel);
+}
+
+// the C++ convenience overloads of the runtime that cuda_runtime.h only declares for nvcc
+template <class R, class... A> static inline cudaError_t cudaFuncSetAttribute(R (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMemcpyToSymbolAsync(const T &symbol, const void *src, size_t n, size_t off, cudaMemcpyKind, cudaStream_t) {
+  memcpy((char *)&symbol + off, src, n);
+  return cudaSuccess;
+}

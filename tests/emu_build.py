@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE (CPU tier): host builds of the product's CUDA translation units.
+
+`build(tmp_dir, units)` turns each .cu file into a C++ file the host compiler accepts — kernel launches
+`k<<<grid, block, smem, stream>>>(args);` become `emu_launch(grid, block, smem, [&] { k(args); });`, dynamic shared-memory
+declarations become pointers into the emulated block's buffer, the one inline-PTX read of %lanemask_lt becomes its
+emulation — prepends tests/cpp/cuda_emu.h (one OS thread per CUDA thread) and links the result with
+tests/emu/cuda_runtime_emu.cpp (the CUDA runtime calls of the host code over host memory).  Kernel and host code are
+otherwise compiled as written.  Used by tests/test_orb_emu.py; never by the product."""
+import re
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "monocular-visual-odometry_b200" / "csrc"
+
+LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
+DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];")
+LANEMASK = re.compile(r'asm\("mov\.u32 %0, %%lanemask_lt;"\s*:\s*"=r"\((\w+)\)\);')
+
+
+def _split_args(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur.strip())
+    return out
+
+
+def transform(text):
+    def launch(m):
+        kernel, cfg, args = m.group(1), _split_args(m.group(2)), m.group(3)
+        grid, block = cfg[0], cfg[1]
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return f"emu_launch({grid}, {block}, {smem}, [&] {{ {kernel}({args}); }});"
+    text, n = LAUNCH.subn(launch, text)
+    text = DYN_SMEM.sub(r"\1 *\2 = (\1 *)g_dyn_smem;", text)
+    text = LANEMASK.sub(r"\1 = emu_lanemask_lt();", text)
+    text = re.sub(r"#include <cooperative_groups.h>\n", "", text)
+    text = re.sub(r"namespace cg = cooperative_groups;\n", "", text)
+    return '#include "cuda_emu.h"\n' + text, n
+
+
+def build(tmp_dir, units, name="libmvo_emu.so"):
+    """units: file names under csrc/ (.cu are transformed, .cpp compiled as they are).  Returns the path of the shared object."""
+    tmp_dir = Path(tmp_dir)
+    srcs = []
+    for u in units:
+        src = CSRC / u
+        if u.endswith(".cu"):
+            text, _ = transform(src.read_text())
+            out = tmp_dir / (u + ".emu.cpp")
+            out.write_text(text)
+            srcs.append(str(out))
+        else:
+            srcs.append(str(src))
+    so = tmp_dir / name
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", str(ROOT / "include"), "-I", str(CSRC),
+                    "-I", str(ROOT / "tests" / "cpp"), "-I", "/usr/local/cuda/include", *srcs, str(ROOT / "tests" / "emu" / "cuda_runtime_emu.cpp"),
+                    "-o", str(so)], check=True)
+    return so
