@@ -15,6 +15,7 @@ CSRC = ROOT / "monocular-visual-odometry_b200" / "csrc"
 
 LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
 DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];")
+DYN_SMEM_MACRO = re.compile(r"(#define\s+\w+\(type, name\))\s+extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?type name\[\]")
 LANEMASK = re.compile(r'asm\("mov\.u32 %0, %%lanemask_lt;"\s*:\s*"=r"\((\w+)\)\);')
 
 
@@ -42,6 +43,7 @@ def transform(text):
         return f"emu_launch({grid}, {block}, {smem}, [&] {{ {kernel}({args}); }});"
     text, n = LAUNCH.subn(launch, text)
     text = DYN_SMEM.sub(r"\1 *\2 = (\1 *)g_dyn_smem;", text)
+    text = DYN_SMEM_MACRO.sub(r"\1 type *name = (type *)g_dyn_smem", text)
     text = LANEMASK.sub(r"\1 = emu_lanemask_lt();", text)
     text = re.sub(r"#include <cooperative_groups.h>\n", "", text)
     text = re.sub(r"namespace cg = cooperative_groups;\n", "", text)
