@@ -64,7 +64,9 @@ def build(tmp_dir, units, name="libmvo_emu.so"):
         else:
             srcs.append(str(src))
     so = tmp_dir / name
-    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", str(ROOT / "include"), "-I", str(CSRC),
+    # -Bsymbolic: the library's own definitions of the CUDA runtime entry points win over a real libcudart that another test may
+    # have brought into the process (torch loads it with RTLD_GLOBAL)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-I", str(ROOT / "include"), "-I", str(CSRC),
                     "-I", str(ROOT / "tests" / "cpp"), "-I", "/usr/local/cuda/include", *srcs, str(ROOT / "tests" / "emu" / "cuda_runtime_emu.cpp"),
                     "-o", str(so)], check=True)
     return so
