@@ -96,6 +96,11 @@ typedef struct mvo_params {
   /* two-view geometry — src/geometry/epipolar_geometry.cpp:17-57 */
   int32_t epi_hypotheses;     /* batched essential-matrix hypotheses (reference: adaptive RANSAC, prob 0.999); default 4096 */
   int32_t pad_;
+  double eh_ratio_threshold;  /* mvo_estimate_relative_poses takes the homography branch when H/(E+H) exceeds this: 0.5
+                                 (motion_estimation.cpp:140; the reference's README.md:57 documents 0.45).  The locally
+                                 optimised essential matrix keeps more inliers than OpenCV's un-refined five-point model, so
+                                 the ratio sits ~0.03 lower here: exactly planar scenes come out at 0.485-0.492 (OpenCV
+                                 0.50-0.52) and fall on the E side of 0.5 */
 } mvo_params;
 
 typedef struct mvo_ctx mvo_ctx;
@@ -355,6 +360,9 @@ int mvo_check_homography_score(const double *H21, const float *pts_img1, const f
  * h_normals = num_h x 3), the one with the largest |normal.z|; otherwise solution 0 (essential).  Host only. */
 int mvo_choose_e_or_h(double score_e, double score_h, const double *h_normals, int num_h, int *best_sol,
                       double *ratio);
+/* The same with the threshold as an argument (mvo_params::eh_ratio_threshold is what mvo_estimate_relative_poses passes). */
+int mvo_choose_e_or_h_thr(double score_e, double score_h, const double *h_normals, int num_h, double threshold,
+                          int *best_sol, double *ratio);
 
 /* helperEstimatePossibleRelativePosesByEpipolarGeometry (motion_estimation.cpp:10-158) over flat arrays of MATCHED
  * points (pts_img1[i] <-> pts_img2[i], n x 2 float pixels): solution 0 is the essential-matrix motion, solutions

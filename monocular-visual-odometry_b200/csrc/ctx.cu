@@ -107,6 +107,7 @@ void mvo_default_params(mvo_params *p) {
   p->ba_fix_first_pose = 0;
   p->ba_step_tol = 0.0;
   p->epi_hypotheses = 4096;
+  p->eh_ratio_threshold = 0.5;  // reference src/geometry/motion_estimation.cpp:140
 }
 
 static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
@@ -121,6 +122,8 @@ static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_hypotheses outside [1,65535]");
   if (p->epi_hypotheses < 1 || p->epi_hypotheses > 65535)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "epi_hypotheses outside [1,65535]");
+  if (!(p->eh_ratio_threshold > 0 && p->eh_ratio_threshold < 1))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "eh_ratio_threshold outside (0,1)");
   if (p->ba_iterations < 0 || p->pnp_refine_iters < 0)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "negative iteration count");
   return MVO_OK;

@@ -101,11 +101,16 @@ int mvo_check_homography_score(const double *H21, const float *pts_img1, const f
 }
 
 int mvo_choose_e_or_h(double score_e, double score_h, const double *h_normals, int num_h, int *best_sol, double *ratio_out) {
-  if (!best_sol || num_h < 0 || (num_h > 0 && !h_normals)) return MVO_ERR_INVALID_ARG;
+  return mvo_choose_e_or_h_thr(score_e, score_h, h_normals, num_h, 0.5, best_sol, ratio_out);      // :140
+}
+
+int mvo_choose_e_or_h_thr(double score_e, double score_h, const double *h_normals, int num_h, double threshold, int *best_sol,
+                          double *ratio_out) {
+  if (!best_sol || num_h < 0 || (num_h > 0 && !h_normals) || !(threshold > 0 && threshold < 1)) return MVO_ERR_INVALID_ARG;
   // solution 0 is the essential one, 1..num_h the homography ones (motion_estimation.cpp:60-103)
   const double ratio = score_h / (score_e + score_h);            // :137
   int best = 0;
-  if (ratio > 0.5 && num_h > 0) {                                // :140-152: the homography solution whose plane normal is most frontal
+  if (ratio > threshold && num_h > 0) {                                // :140-152: the homography solution whose plane normal is most frontal
     best = 1;
     double largest = fabs(h_normals[2]);
     for (int i = 2; i <= num_h; ++i) {

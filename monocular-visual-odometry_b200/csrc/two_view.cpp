@@ -67,7 +67,7 @@ extern "C" int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, 
     if (rc != MVO_OK) sol->score_h = 0;          // a singular H cannot be inverted for the symmetric transfer error
   }
   int best = 0;
-  MVO_TRY(mvo_choose_e_or_h(sol->score_e, sol->score_h, &sol->normal[1][0], num_h, &best, &sol->ratio));
+  MVO_TRY(mvo_choose_e_or_h_thr(sol->score_e, sol->score_h, &sol->normal[1][0], num_h, ctx->prm.eh_ratio_threshold, &best, &sol->ratio));
   sol->best = best;
   return MVO_OK;
 }

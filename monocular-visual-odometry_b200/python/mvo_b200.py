@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("max_pts_per_grid", C.c_int32), ("xiang_gao_ratio", C.c_double), ("lowe_ratio", C.c_double),
         ("pnp_hypotheses", C.c_int32), ("pnp_reproj_error", C.c_float), ("pnp_seed", C.c_uint64),
         ("pnp_refine_iters", C.c_int32), ("ba_iterations", C.c_int32), ("ba_huber_delta", C.c_double),
-        ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double), ("epi_hypotheses", C.c_int32), ("pad_", C.c_int32),
+        ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double), ("epi_hypotheses", C.c_int32), ("pad_", C.c_int32), ("eh_ratio_threshold", C.c_double),
     ]
 
 
@@ -134,6 +134,7 @@ SIGNATURES = {
     "mvo_estimate_relative_poses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, C.POINTER(TwoViewSolutions), _vp, _vp]),
     "mvo_check_essential_score": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
     "mvo_check_homography_score": (_i, [_vp, _vp, _vp, _i, _vp, _pi, C.c_double, C.POINTER(C.c_double)]),
+    "mvo_choose_e_or_h_thr": (_i, [C.c_double, C.c_double, _vp, _i, C.c_double, _pi, C.POINTER(C.c_double)]),
     "mvo_choose_e_or_h": (_i, [C.c_double, C.c_double, _vp, _i, _pi, C.POINTER(C.c_double)]),
     "mvo_retain_good_triangulation": (_i, [_vp, _i, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _pi]),
     "mvo_normalize_init_depth": (_i, [_vp, _i, _vp, C.c_double, C.POINTER(C.c_double)]),

@@ -68,6 +68,12 @@ def test_scores_and_choice_equal_reference_restatement(built, planar):
     assert lib.mvo_choose_e_or_h(out["E"], out["H"], normals.ctypes.data, 4, C.byref(best), C.byref(ratio)) == 0
     rb, rr = motion_oracle.choose_e_or_h(out["E"], out["H"], normals)
     assert best.value == rb and abs(ratio.value - rr) < 1e-12
+    # the threshold as an argument: 0.5 is the reference's constant; just above / below the ratio flips the choice
+    b2, r2 = C.c_int(-1), C.c_double(0)
+    assert lib.mvo_choose_e_or_h_thr(out["E"], out["H"], normals.ctypes.data, 4, 0.5, C.byref(b2), C.byref(r2)) == 0 and (b2.value, r2.value) == (best.value, ratio.value)
+    assert lib.mvo_choose_e_or_h_thr(out["E"], out["H"], normals.ctypes.data, 4, min(ratio.value + 1e-6, 0.999999), C.byref(b2), None) == 0 and b2.value == 0
+    assert lib.mvo_choose_e_or_h_thr(out["E"], out["H"], normals.ctypes.data, 4, max(ratio.value - 1e-6, 1e-6), C.byref(b2), None) == 0 and b2.value >= 1
+    assert lib.mvo_choose_e_or_h_thr(out["E"], out["H"], normals.ctypes.data, 4, 1.5, C.byref(b2), None) == -1
     # a general scene scores higher under E; on the plane (with its poor E) the homography branch is taken
     assert (best.value == 0) == (not planar), (planar, out, ratio.value)
     if planar:

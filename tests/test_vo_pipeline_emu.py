@@ -126,3 +126,95 @@ def test_state_machine_with_the_products_two_view_kernels(hostcheck, tmp_path): 
     path = float(np.linalg.norm(truth[-1][:3, 3] - truth[s0][:3, 3]))
     print("trajectory RMS error: product two-view kernels %.5f, oracle %.5f, path %.3f" % (ep, eo, path))
     assert ep < 0.02 * path and ep <= 1.25 * eo + 1e-4
+
+
+class RealEntryPointStages(Stages):
+    """Extraction, matching and the two-view stage go to the library's REAL entry points — host code and kernels built for the host
+    by tests/emu_build.py — and only PnP and BA (whose LM runs on thread-block clusters, not emulated) stay on the oracle."""
+
+    def __init__(self, helper, ba_iterations, lib, ctx):
+        self.lib, self.ctx = lib, ctx
+        super().__init__(helper, ba_iterations)
+
+    def orb_extract(self, image, rows, cols, channels, stride, kpts, n_kpts, desc):
+        return self.lib.mvo_orb_extract(self.ctx, image, rows, cols, channels, stride, kpts, n_kpts, desc)
+
+    def match_features(self, d1, n1, d2, n2, method, xy1, xy2, radius, out, n_out):
+        return self.lib.mvo_match_features(self.ctx, d1, n1, d2, n2, method, xy1, xy2, radius, out, n_out)
+
+    def esti_motion_by_essential(self, p1, p2, n, Kp, threshold, E, R, t, inliers, n_inliers):
+        return self.lib.mvo_esti_motion_by_essential(self.ctx, p1, p2, n, Kp, threshold, E, R, t, inliers, n_inliers)
+
+    def esti_motion_by_homography(self, p1, p2, n, Kp, threshold, H, Rs, ts, normals, n_solutions, inliers, n_inliers):
+        return self.lib.mvo_esti_motion_by_homography(self.ctx, p1, p2, n, Kp, threshold, H, Rs, ts, normals, n_solutions, inliers, n_inliers)
+
+    def remove_wrong_rt_of_homography(self, np1, np2, n, inliers, n_inliers, Rs, ts, normals, n_solutions):
+        return self.lib.mvo_remove_wrong_rt_of_homography(self.ctx, np1, np2, n, inliers, n_inliers, Rs, ts, normals, n_solutions)
+
+    def do_triangulation(self, np1, np2, n, R, t, inliers, n_inliers, pts3d):
+        return self.lib.mvo_do_triangulation(self.ctx, np1, np2, n, R, t, inliers, n_inliers, pts3d)
+
+
+def test_state_machine_over_the_real_entry_points(hostcheck, tmp_path):  # noqa: F811
+    """Plumbing check at half resolution (the emulated extraction costs ~13 s per 320x240 frame): every call the state machine
+    makes into the real entry points succeeds, extraction and matching agree with the oracle pipeline running beside it on the same
+    frames (they are bit-exact), and the two-view results that come back are well-formed.  Whether and when the map gets initialised
+    is NOT asserted here: at this resolution the first frame pairs are close to the planar / low-parallax degeneracy of the essential
+    matrix and the two RANSACs legitimately settle on different motions (the full-resolution behaviour is the test above)."""
+    import emu_build
+    import mvo_b200
+    from oracle import vo_pipeline_oracle as vp
+    lib = C.CDLL(str(emu_build.build(tmp_path, ["ctx.cu", "orb.cu", "orb_host.cpp", "match.cu", "match_host.cpp", "epipolar.cu", "two_view.cpp", "motion_host.cpp"])))
+    for name in ("mvo_default_params", "mvo_create", "mvo_destroy", "mvo_last_error", "mvo_orb_extract", "mvo_match_features", "mvo_esti_motion_by_essential",
+                 "mvo_esti_motion_by_homography", "mvo_remove_wrong_rt_of_homography", "mvo_do_triangulation"):
+        res, args = mvo_b200.SIGNATURES[name]
+        # the forwarders hand raw addresses through: every pointer parameter as void*
+        getattr(lib, name).restype, getattr(lib, name).argtypes = res, [C.c_void_p if hasattr(a, "contents") or a is C.c_char_p else a for a in args]
+    prm = mvo_b200.Params()
+    lib.mvo_default_params(C.byref(prm))
+    prm.max_keypoints, prm.epi_hypotheses = 1000, 384
+    ctx = C.c_void_p()
+    assert lib.mvo_create(C.byref(ctx), 0, C.byref(prm)) == 0
+    rows, cols = 240, 320
+    Kh = K.copy()
+    Kh[:2] *= 0.5
+    planes = mvo_synth._room_planes(0)
+    _, truth = None, []
+    frames = []
+    rng = np.random.default_rng(2000)
+    drift_r = rng.normal(0, 1, 3) * 0.003
+    for i in range(5):
+        T = np.eye(4)
+        T[:3, :3] = mvo_synth.rodrigues(drift_r * i)
+        T[:3, 3] = np.array([0.08, -0.012, 0.024]) * i
+        truth.append(T)
+        frames.append(mvo_synth.render_room(T, planes, Kh, cols, rows))
+    cfg = dict(max_number_of_keypoints=1000, ba_iterations=10, min_pixel_dist=25.0)
+    oracle = vp.CpuVo(Kh, rows, cols, **cfg)
+    helper = vp.CpuVo(Kh, rows, cols, max_number_of_keypoints=1000)
+    stages = RealEntryPointStages(helper, 10, lib, ctx)
+    hostcheck.hostcheck_set_stages(C.cast(stages.table, C.c_void_p))
+    hctx = C.c_void_p(hostcheck.hostcheck_ctx_new(1000))
+    p = mvo_b200.VoParams()
+    hostcheck.mvo_vo_default_params(C.byref(p))
+    p.min_pixel_dist = 25.0
+    h = C.c_void_p()
+    Kc = np.ascontiguousarray(Kh, np.float64)
+    assert hostcheck.mvo_vo_create(hctx, Kc.ctypes.data, rows, cols, C.byref(p), C.byref(h)) == 0
+    Tp, To, infos = [], [], []
+    for f in frames:
+        img = mvo_synth.gray_to_bgr(f)
+        T, info = np.zeros(16), mvo_b200.VoFrameInfo()
+        assert hostcheck.mvo_vo_add_frame(h, img.ctypes.data, 3, cols * 3, T.ctypes.data, C.byref(info)) == 0, lib.mvo_last_error(ctx)
+        To.append(oracle.add_frame(img)[0])
+        io = oracle.log[-1]
+        Tp.append(T.reshape(4, 4).copy())
+        infos.append((info.state_out, info.keyframe, info.best_sol, info.n_keypoints, info.n_matches, info.n_inliers, info.map_points))
+        assert info.n_keypoints == io["n_keypoints"]                                  # extraction: bit-exact with the oracle
+        if info.state_in == 1 and io["state_in"] == 1:
+            assert info.n_matches == io["n_matches"]                                  # and so is the matching against the first keyframe
+    hostcheck.mvo_vo_destroy(h)
+    hostcheck.hostcheck_ctx_free(hctx)
+    lib.mvo_destroy(ctx)
+    print(infos)
+    assert infos[0][:2] == (1, 1) and all(0 <= i[2] <= 4 for i in infos[1:])         # a two-view solution was chosen on every later frame
