@@ -123,23 +123,29 @@ template <class F> static void run_grid(unsigned gx, unsigned gy, unsigned gz, u
   const unsigned warps = (threads + 31) / 32;
   std::vector<unsigned char> dyn(dyn_smem_bytes + 64);
   g_dyn_smem = dyn.data();
-  for (unsigned bz = 0; bz < gz; ++bz)
-    for (unsigned by = 0; by < gy; ++by)
-      for (unsigned bx = 0; bx < gx; ++bx) {
-        pthread_barrier_init(&g_block_barrier, nullptr, threads);
-        for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, std::min(32u, threads - 32 * w));
-        std::vector<std::thread> pool;
-        pool.reserve(threads);
-        for (unsigned t = 0; t < threads; ++t)
-          pool.emplace_back([&, t] {
-            threadIdx = EmuIdx{t, 0, 0};
+  // one set of OS threads for the whole grid: every thread plays the same threadIdx in block after block; a barrier at the end of
+  // each block keeps the blocks strictly one after the other (the __shared__ statics and the block barrier are reused)
+  pthread_barrier_t end_of_block;
+  pthread_barrier_init(&end_of_block, nullptr, threads);
+  pthread_barrier_init(&g_block_barrier, nullptr, threads);
+  for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, std::min(32u, threads - 32 * w));
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      threadIdx = EmuIdx{t, 0, 0};
+      for (unsigned bz = 0; bz < gz; ++bz)
+        for (unsigned by = 0; by < gy; ++by)
+          for (unsigned bx = 0; bx < gx; ++bx) {
             blockIdx = EmuIdx{bx, by, bz};
             kernel();
-          });
-        for (auto &th : pool) th.join();
-        pthread_barrier_destroy(&g_block_barrier);
-        for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
-      }
+            pthread_barrier_wait(&end_of_block);
+          }
+    });
+  for (auto &th : pool) th.join();
+  pthread_barrier_destroy(&end_of_block);
+  pthread_barrier_destroy(&g_block_barrier);
+  for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
   g_dyn_smem = nullptr;
 }
 
