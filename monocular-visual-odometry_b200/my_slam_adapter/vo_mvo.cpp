@@ -89,7 +89,11 @@ void VisualOdometry::addFrame(Frame::Ptr frame) {
   by_id_[info.frame_id] = frame;
   lib_id_[frame->id_] = info.frame_id;
   frames_buff_.push_back(frame);                                  // pushFrameToBuff_ (vo.h:81-86)
-  if (frames_buff_.size() > 20) { by_id_.erase(lib_id_[frames_buff_.front()->id_]); frames_buff_.pop_front(); }
+  if (frames_buff_.size() > 20) {
+    auto it = lib_id_.find(frames_buff_.front()->id_);
+    if (it != lib_id_.end()) { by_id_.erase(it->second); lib_id_.erase(it); }
+    frames_buff_.pop_front();
+  }
 
   // ---- the members run_vo.cpp reads from the frame ----
   frame->keypoints_ = fetch<cv::KeyPoint>(vo_, 0, MVO_VO_KEYPOINTS);
