@@ -120,14 +120,17 @@ void VisualOdometry::addFrame(Frame::Ptr frame) {
     int n = 0;
     if (mvo_vo_frame_data(vo_, -1, MVO_VO_FRAME_ID, &rid, 1, &n) == MVO_OK) {
       auto it = by_id_.find(rid);
-      auto kf = map_->keyframes_.find(rid);
-      prev_ref_ = it != by_id_.end() ? it->second : (kf != map_->keyframes_.end() ? kf->second : prev_ref_);
+      auto kf = kf_by_lib_id_.find(rid);                          // a reference keyframe may be older than the 20-frame buffer
+      prev_ref_ = it != by_id_.end() ? it->second : (kf != kf_by_lib_id_.end() ? kf->second : prev_ref_);
     } else {
       prev_ref_ = nullptr;
     }
   }
   // ---- the map ----
-  if (info.keyframe) map_->keyframes_[frame->id_] = frame;         // Map::insertKeyFrame, keyed by the caller's frame id like the reference
+  if (info.keyframe) {
+    map_->keyframes_[frame->id_] = frame;                         // Map::insertKeyFrame, keyed by the caller's frame id like the reference
+    kf_by_lib_id_[info.frame_id] = frame;
+  }
   const int nmap = mvo_vo_map_size(vo_);
   std::vector<int32_t> ids((size_t)(nmap > 0 ? nmap : 1));
   std::vector<float> pos((size_t)(nmap > 0 ? nmap : 1) * 3);

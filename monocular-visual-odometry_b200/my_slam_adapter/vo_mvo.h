@@ -82,6 +82,7 @@ class VisualOdometry {                                            // include/my_
   std::deque<Frame::Ptr> frames_buff_;                            // the same 20 newest frames libmvo keeps
   std::unordered_map<int, Frame::Ptr> by_id_;                     // libmvo frame id -> the caller's Frame
   std::unordered_map<int, int> lib_id_;                           // caller's Frame::id_ -> libmvo frame id
+  std::unordered_map<int, Frame::Ptr> kf_by_lib_id_;              // keyframes by libmvo frame id (getPrevRef)
 };
 
 }  // namespace vo
