@@ -15,16 +15,55 @@
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 #include <thread>
 #include <vector>
 
+#include <mutex>
+
 struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
+struct EmuCluster;
+struct EmuBlock {                                                 // what the threads of one block share
+  pthread_barrier_t bar;
+  pthread_barrier_t wbar[32];
+  unsigned long long xchg[32][32];
+  unsigned char *dyn = nullptr;                                   // dynamic shared memory
+  size_t dyn_bytes = 0;
+  unsigned char *stat = nullptr;                                  // per-block storage of rewritten __shared__ declarations (EMU_SHARED)
+  unsigned rank = 0;                                              // rank inside its cluster
+  EmuCluster *cluster = nullptr;
+};
+struct EmuCluster {
+  pthread_barrier_t bar;
+  std::vector<EmuBlock *> blocks;
+};
+constexpr size_t EMU_STATIC_ARENA = 256 * 1024;
 static thread_local EmuIdx threadIdx, blockIdx;
-static EmuIdx blockDim, gridDim;
-static pthread_barrier_t g_block_barrier;
-static pthread_barrier_t g_warp_barrier[32];
-static unsigned long long g_xchg[32][32];
-static unsigned char *g_dyn_smem = nullptr;                      // dynamic shared memory of the running block
+static thread_local EmuBlock *tl_blk = nullptr;
+static thread_local EmuIdx blockDim, gridDim;                  // thread-local: launches may come from several host threads at once
+#define g_dyn_smem (tl_blk->dyn)
+#define g_block_barrier (tl_blk->bar)
+#define g_warp_barrier (tl_blk->wbar)
+#define g_xchg (tl_blk->xchg)
+
+// Per-block storage for `__shared__` declarations that tests/emu_build.py rewrote (needed where the blocks of a cluster run
+// at the same time; a function-local static would be one array for all of them).  Every declaration has an id; its offset in
+// the block's arena is fixed the first time any thread asks for it.
+static inline void *emu_block_static(int id, size_t bytes) {
+  static std::mutex mu;
+  static std::vector<size_t> offset;
+  static size_t used = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)offset.size() <= id) offset.resize((size_t)id + 1, (size_t)-1);
+  if (offset[(size_t)id] == (size_t)-1) {
+    used = (used + 15) & ~(size_t)15;
+    offset[(size_t)id] = used;
+    used += bytes;
+    if (used > EMU_STATIC_ARENA) { fprintf(stderr, "cuda_emu: static shared arena exhausted\n"); abort(); }
+  }
+  return tl_blk->stat + offset[(size_t)id];
+}
 
 #undef __shared__
 #define __shared__ static
@@ -58,6 +97,7 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int __float2int_rn(float x) { return (int)nearbyintf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }       // approximate on the GPU (2 ulp): no bit parity through it
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
@@ -117,23 +157,36 @@ static inline long long clock64() { return 0; }
 using std::max;
 using std::min;
 
-template <class F> static void run_grid(unsigned gx, unsigned gy, unsigned gz, unsigned threads, size_t dyn_smem_bytes, F &&kernel) {
-  gridDim = EmuIdx{gx, gy, gz};
-  blockDim = EmuIdx{threads, 1, 1};
+static inline void emu_block_init(EmuBlock *b, unsigned threads, size_t dyn_bytes) {
   const unsigned warps = (threads + 31) / 32;
-  std::vector<unsigned char> dyn(dyn_smem_bytes + 64);
-  g_dyn_smem = dyn.data();
-  // one set of OS threads for the whole grid: every thread plays the same threadIdx in block after block; a barrier at the end of
-  // each block keeps the blocks strictly one after the other (the __shared__ statics and the block barrier are reused)
+  pthread_barrier_init(&b->bar, nullptr, threads);
+  for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&b->wbar[w], nullptr, std::min(32u, threads - 32 * w));
+  b->dyn_bytes = dyn_bytes;
+  b->dyn = (unsigned char *)calloc(dyn_bytes + 64, 1);
+  b->stat = (unsigned char *)calloc(EMU_STATIC_ARENA, 1);
+}
+static inline void emu_block_destroy(EmuBlock *b, unsigned threads) {
+  const unsigned warps = (threads + 31) / 32;
+  pthread_barrier_destroy(&b->bar);
+  for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&b->wbar[w]);
+  free(b->dyn);
+  free(b->stat);
+}
+
+// blocks strictly one after the other (function-local `static` __shared__ arrays are reused block after block)
+template <class F> static void run_grid(unsigned gx, unsigned gy, unsigned gz, unsigned threads, size_t dyn_smem_bytes, F &&kernel) {
+  EmuBlock blk;
+  emu_block_init(&blk, threads, dyn_smem_bytes);
   pthread_barrier_t end_of_block;
   pthread_barrier_init(&end_of_block, nullptr, threads);
-  pthread_barrier_init(&g_block_barrier, nullptr, threads);
-  for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, std::min(32u, threads - 32 * w));
   std::vector<std::thread> pool;
   pool.reserve(threads);
   for (unsigned t = 0; t < threads; ++t)
     pool.emplace_back([&, t] {
       threadIdx = EmuIdx{t, 0, 0};
+      gridDim = EmuIdx{gx, gy, gz};
+      blockDim = EmuIdx{threads, 1, 1};
+      tl_blk = &blk;
       for (unsigned bz = 0; bz < gz; ++bz)
         for (unsigned by = 0; by < gy; ++by)
           for (unsigned bx = 0; bx < gx; ++bx) {
@@ -144,9 +197,67 @@ template <class F> static void run_grid(unsigned gx, unsigned gy, unsigned gz, u
     });
   for (auto &th : pool) th.join();
   pthread_barrier_destroy(&end_of_block);
-  pthread_barrier_destroy(&g_block_barrier);
-  for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
-  g_dyn_smem = nullptr;
+  emu_block_destroy(&blk, threads);
+}
+
+// one thread-block cluster after the other; the blocks of a cluster run at the same time (distributed shared memory, cluster
+// barriers).  Kernels launched this way must not keep block state in function-local statics: tests/emu_build.py rewrites their
+// `__shared__` declarations into per-block storage (EMU_SHARED).
+template <class F> static void run_clusters(unsigned grid_x, unsigned cluster_size, unsigned threads, size_t dyn_smem_bytes, F &&kernel) {
+  for (unsigned c0 = 0; c0 < grid_x; c0 += cluster_size) {
+    EmuCluster cl;
+    std::vector<EmuBlock> blocks(cluster_size);
+    pthread_barrier_init(&cl.bar, nullptr, cluster_size * threads);
+    for (unsigned r = 0; r < cluster_size; ++r) {
+      emu_block_init(&blocks[r], threads, dyn_smem_bytes);
+      blocks[r].rank = r;
+      blocks[r].cluster = &cl;
+      cl.blocks.push_back(&blocks[r]);
+    }
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)cluster_size * threads);
+    for (unsigned r = 0; r < cluster_size; ++r)
+      for (unsigned t = 0; t < threads; ++t)
+        pool.emplace_back([&, r, t] {
+          threadIdx = EmuIdx{t, 0, 0};
+          blockIdx = EmuIdx{c0 + r, 0, 0};
+          gridDim = EmuIdx{grid_x, 1, 1};
+          blockDim = EmuIdx{threads, 1, 1};
+          tl_blk = &blocks[r];
+          kernel();
+        });
+    for (auto &th : pool) th.join();
+    for (unsigned r = 0; r < cluster_size; ++r) emu_block_destroy(&blocks[r], threads);
+    pthread_barrier_destroy(&cl.bar);
+  }
+}
+
+// cooperative_groups, as far as csrc/ba.cu uses it
+namespace cooperative_groups {
+struct cluster_group {
+  unsigned block_rank() const { return tl_blk->rank; }
+  unsigned num_blocks() const { return (unsigned)tl_blk->cluster->blocks.size(); }
+  void sync() const { pthread_barrier_wait(&tl_blk->cluster->bar); }
+  template <class T> T *map_shared_rank(T *p, unsigned r) const {
+    const unsigned char *q = (const unsigned char *)p;
+    EmuBlock *me = tl_blk, *other = me->cluster->blocks[r];
+    if (q >= me->dyn && q < me->dyn + me->dyn_bytes + 64) return (T *)(other->dyn + (q - me->dyn));
+    if (q >= me->stat && q < me->stat + EMU_STATIC_ARENA) return (T *)(other->stat + (q - me->stat));
+    fprintf(stderr, "cuda_emu: map_shared_rank of an address outside the block's shared memory\n");
+    abort();
+  }
+};
+static inline cluster_group this_cluster() { return cluster_group(); }
+}  // namespace cooperative_groups
+
+// cudaLaunchKernelEx with a cluster-dimension attribute (the only extended launch in this code base; tests/emu_build.py
+// renames the call: cuda_runtime.h has its own host template of that name)
+template <class... P, class... A> static inline cudaError_t emu_cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*kernel)(P...), A &&...args) {
+  unsigned csize = 1;
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) csize = cfg->attrs[i].val.clusterDim.x;
+  run_clusters(cfg->gridDim.x, csize, cfg->blockDim.x, cfg->dynamicSmemBytes, [&] { kernel(args...); });
+  return cudaSuccess;
 }
 
 // kernel launch as written in the product (`k<<<grid, block, smem, stream>>>(args)`, rewritten by tests/emu_build.py):

@@ -13,6 +13,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "monocular-visual-odometry_b200" / "csrc"
 
+CLUSTER_UNITS = {"ba.cu"}            # kernels launched as thread-block clusters: their blocks run concurrently in the emulation
+
 LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
 DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];")
 DYN_SMEM_MACRO = re.compile(r"(#define\s+\w+\(type, name\))\s+extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?type name\[\]")
@@ -35,7 +37,41 @@ def _split_args(s):
     return out
 
 
-def transform(text):
+SHARED_DECL = re.compile(r"^(?P<indent>[ \t]*)__shared__\s+(?P<body>[^;=]+);(?P<tail>.*)$", re.M)
+DECLARATOR = re.compile(r"^(?P<name>\w+)\s*(?P<dims>(?:\[[^\]]*\])*)$")
+_shared_id = [0]
+
+
+def per_block_shared(text):
+    """`__shared__ T a[N], b;` -> references into the emulated block's own storage (clusters run their blocks concurrently)."""
+    def repl(m):
+        body = m.group("body").strip()
+        if body.startswith("extern"):
+            return m.group(0)
+        body = re.sub(r"__align__\(\d+\)\s*", "", body)
+        first = re.search(r"\b\w+\s*(?:\[[^\]]*\])*\s*(?:,|$)", body)
+        # the type is everything before the first declarator
+        decls = _split_args(body)
+        head = decls[0]
+        mm = re.match(r"^(?P<type>.+?)\s+(?P<decl>\w+\s*(?:\[[^\]]*\])*)$", head)
+        assert mm, body
+        ctype = mm.group("type")
+        out = []
+        for d in [mm.group("decl")] + decls[1:]:
+            dm = DECLARATOR.match(d.strip())
+            assert dm, (body, d)
+            name, dims = dm.group("name"), dm.group("dims")
+            i = _shared_id[0]
+            _shared_id[0] += 1
+            if dims:
+                out.append(f"auto &{name} = *reinterpret_cast<{ctype} (*){dims}>(emu_block_static({i}, sizeof({ctype}{dims})));")
+            else:
+                out.append(f"auto &{name} = *reinterpret_cast<{ctype} *>(emu_block_static({i}, sizeof({ctype})));")
+        return m.group("indent") + " ".join(out) + m.group("tail")
+    return SHARED_DECL.sub(repl, text)
+
+
+def transform(text, cluster_kernels=False):
     def launch(m):
         kernel, cfg, args = m.group(1), _split_args(m.group(2)), m.group(3)
         grid, block = cfg[0], cfg[1]
@@ -46,7 +82,11 @@ def transform(text):
     text = DYN_SMEM_MACRO.sub(r"\1 type *name = (type *)g_dyn_smem", text)
     text = LANEMASK.sub(r"\1 = emu_lanemask_lt();", text)
     text = re.sub(r"#include <cooperative_groups.h>\n", "", text)
-    text = re.sub(r"namespace cg = cooperative_groups;\n", "", text)
+    text = text.replace("cudaLaunchKernelEx(", "emu_cudaLaunchKernelEx(")
+    if cluster_kernels:
+        text = per_block_shared(text)                      # `namespace cg = cooperative_groups;` stays: cuda_emu.h provides the namespace
+    else:
+        text = re.sub(r"namespace cg = cooperative_groups;\n", "", text)
     return '#include "cuda_emu.h"\n' + text, n
 
 
@@ -57,7 +97,7 @@ def build(tmp_dir, units, name="libmvo_emu.so"):
     for u in units:
         src = CSRC / u
         if u.endswith(".cu"):
-            text, _ = transform(src.read_text())
+            text, _ = transform(src.read_text(), cluster_kernels=(u in CLUSTER_UNITS))
             out = tmp_dir / (u + ".emu.cpp")
             out.write_text(text)
             srcs.append(str(out))
