@@ -13,6 +13,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "monocular-visual-odometry_b200" / "csrc"
 
+ALL_UNITS = ["ctx.cu", "orb.cu", "orb_host.cpp", "match.cu", "match_host.cpp", "pnp.cu", "ba.cu", "track.cu", "tracker.cpp", "epipolar.cu",
+             "two_view.cpp", "motion_host.cpp", "vo_host.cpp", "vo_io.cpp", "vo_pipeline.cpp"]
 CLUSTER_UNITS = {"ba.cu"}            # kernels launched as thread-block clusters: their blocks run concurrently in the emulation
 
 LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
@@ -93,6 +95,7 @@ def transform(text, cluster_kernels=False):
 def build(tmp_dir, units, name="libmvo_emu.so"):
     """units: file names under csrc/ (.cu are transformed, .cpp compiled as they are).  Returns the path of the shared object."""
     tmp_dir = Path(tmp_dir)
+    tmp_dir.mkdir(parents=True, exist_ok=True)
     srcs = []
     for u in units:
         src = CSRC / u
