@@ -15,15 +15,12 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-UNITS = ["ctx.cu", "orb.cu", "orb_host.cpp", "match.cu", "match_host.cpp", "pnp.cu", "ba.cu", "track.cu", "tracker.cpp", "epipolar.cu", "two_view.cpp",
-         "motion_host.cpp", "vo_host.cpp", "vo_io.cpp", "vo_pipeline.cpp"]
-
 
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
     import emu_build
     import mvo_b200
-    so = emu_build.build(tmp_path_factory.mktemp("fullemu"), UNITS)
+    so = emu_build.build(tmp_path_factory.mktemp("fullemu"), emu_build.ALL_UNITS)
     import ctypes as C
     lib = C.CDLL(str(so))
     missing = [n for n in mvo_b200.SIGNATURES if not hasattr(lib, n)]
