@@ -12,6 +12,9 @@ import sys
 from pathlib import Path
 
 import pytest
+
+import os as _os
+_TIMEOUT_SCALE = float(_os.environ.get("MVO_TEST_TIMEOUT_SCALE", "1"))      # > 1 when the library under test is the CPU emulation (MVO_LIB)
 from conftest import have_cv2
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -112,5 +115,5 @@ print("homography child ok")
 
 @pytest.mark.xfail(strict=False, reason="kernels written after the round-1 GPU budget was spent: first hardware run")
 def test_homography_path_in_child_process(built):
-    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT))], capture_output=True, text=True, timeout=180)
+    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT))], capture_output=True, text=True, timeout=180 * _TIMEOUT_SCALE)
     assert r.returncode == 0 and "homography child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])

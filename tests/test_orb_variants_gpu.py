@@ -11,6 +11,9 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+import os as _os
+_TIMEOUT_SCALE = float(_os.environ.get("MVO_TEST_TIMEOUT_SCALE", "1"))      # > 1 when the library under test is the CPU emulation (MVO_LIB)
+
 ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +41,7 @@ def _extract(tmp_path, name, env):
     out = tmp_path / f"{name}.npz"
     e = dict(os.environ)
     e.update(env)
-    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT), out=str(out))], capture_output=True, text=True, timeout=240, env=e)
+    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT), out=str(out))], capture_output=True, text=True, timeout=240 * _TIMEOUT_SCALE, env=e)
     assert r.returncode == 0 and "orb variant child ok" in r.stdout, (r.stdout[-800:], r.stderr[-2500:])
     return np.load(out)
 

@@ -15,6 +15,9 @@ import sys
 from pathlib import Path
 
 import pytest
+
+import os as _os
+_TIMEOUT_SCALE = float(_os.environ.get("MVO_TEST_TIMEOUT_SCALE", "1"))      # > 1 when the library under test is the CPU emulation (MVO_LIB)
 from conftest import have_cv2
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -67,7 +70,7 @@ print("vo pipeline child ok")
 
 
 def _run(homo):
-    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT), homo=homo)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT), homo=homo)], capture_output=True, text=True, timeout=300 * _TIMEOUT_SCALE)
     assert r.returncode == 0 and "vo pipeline child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
     print(r.stdout[-600:])
 
@@ -114,5 +117,5 @@ print("vo adapter child ok")
 
 @pytest.mark.xfail(strict=False, reason="state machine assembled after the round-1 GPU budget was spent: first hardware run")
 def test_my_slam_visual_odometry_adapter_demo(built, tmp_path):
-    r = subprocess.run([sys.executable, "-c", ADAPTER_CHILD.format(root=str(ROOT), tmp=str(tmp_path))], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", ADAPTER_CHILD.format(root=str(ROOT), tmp=str(tmp_path))], capture_output=True, text=True, timeout=300 * _TIMEOUT_SCALE)
     assert r.returncode == 0 and "vo adapter child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
