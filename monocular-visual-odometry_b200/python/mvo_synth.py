@@ -238,3 +238,26 @@ def room_sequence(seed=0, n_frames=30, step=0.05, K=K_DEFAULT):
         frames.append(render_room(T, planes, K))
         poses.append(T)
     return frames, poses
+
+
+def room_loop_poses(seed=0, n_frames=150, period=120, radius=(0.9, 0.12, 0.7)):
+    """Camera poses (camera->world) on a closed loop inside the box room: an ellipse in x/z with a small vertical wobble and a slow
+    yaw/pitch oscillation, ~0.05 m between frames at the default period — long sequences that never leave the room (BASELINE
+    config 5: >= 150 frames per sequence)."""
+    rng = np.random.default_rng(3000 + seed)
+    ph = rng.uniform(0, 2 * np.pi, 3)
+    poses = []
+    for i in range(n_frames):
+        a = 2 * np.pi * i / period
+        T = np.eye(4)
+        T[:3, 3] = [radius[0] * np.sin(a), radius[1] * np.sin(2 * a + ph[0]), radius[2] * (1 - np.cos(a))]
+        T[:3, :3] = rodrigues(np.array([0.03 * np.sin(a + ph[1]), 0.10 * np.sin(a + ph[2]), 0.01 * np.sin(2 * a)]))
+        poses.append(T)
+    return poses
+
+
+def room_loop_sequence(seed=0, n_frames=150, K=K_DEFAULT, **kw):
+    """Frames of the box room along room_loop_poses.  Returns (frames[n] uint8 HxW, T_w_c[n])."""
+    planes = _room_planes(seed)
+    poses = room_loop_poses(seed, n_frames, **kw)
+    return [render_room(T, planes, K) for T in poses], poses
