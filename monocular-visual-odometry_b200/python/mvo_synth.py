@@ -251,7 +251,7 @@ def room_loop_poses(seed=0, n_frames=150, period=120, radius=(0.9, 0.12, 0.7)):
         a = 2 * np.pi * i / period
         T = np.eye(4)
         T[:3, 3] = [radius[0] * np.sin(a), radius[1] * np.sin(2 * a + ph[0]), radius[2] * (1 - np.cos(a))]
-        T[:3, :3] = rodrigues(np.array([0.03 * np.sin(a + ph[1]), 0.10 * np.sin(a + ph[2]), 0.01 * np.sin(2 * a)]))
+        T[:3, :3] = rodrigues(np.array([0.02 * np.sin(a + ph[1]), 0.04 * np.sin(a), 0.01 * np.sin(2 * a)]))
         poses.append(T)
     return poses
 

@@ -88,3 +88,18 @@ def test_check_large_move(built):
         seen.add(rl)
     assert seen == {True, False}
     assert lib.mvo_check_large_move(None, None, 0.1, C.byref(large), None, None) != 0
+
+
+def test_room_loop_trajectory_stays_inside_the_room():
+    """The long-sequence generator for BASELINE config 5 (>= 150 frames per sequence): closed loop, ~0.04 m per frame, inside the walls."""
+    import mvo_synth
+    poses = mvo_synth.room_loop_poses(3, 240)
+    c = np.array([T[:3, 3] for T in poses])
+    steps = np.linalg.norm(np.diff(c, axis=0), axis=1)
+    r = mvo_synth._ROOM
+    assert 0.03 < steps.min() and steps.max() < 0.06
+    assert np.abs(c[:, 0]).max() < r["half_w"] - 0.5 and r["top"] + 0.5 < c[:, 1].min() and c[:, 1].max() < r["bottom"] - 0.5
+    assert r["z0"] + 1.0 < c[:, 2].min() and c[:, 2].max() < r["back"] - 3.0
+    assert np.abs(c[120] - c[0]).max() < 1e-9                       # period 120: the loop closes
+    for T in poses[::17]:
+        assert np.abs(T[:3, :3] @ T[:3, :3].T - np.eye(3)).max() < 1e-12
