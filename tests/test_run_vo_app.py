@@ -76,7 +76,8 @@ cfg = open(r"{fixture}").read()
 cfg = cfg.replace('dataset_name: "fr1_desk"', 'dataset_name: "matlab"').replace("dataset_dir: data/dataset_images_matlab", 'dataset_dir: "{tmp}"')
 cfg = re.sub(r"num_images: 150", "num_images: %d" % n, cfg, count=1).replace("save_predicted_traj_to: data/test_data/cam_traj.txt", 'save_predicted_traj_to: "{tmp}/traj.txt"')
 open(r"{tmp}/config.yaml", "w").write(cfg)
-r = subprocess.run([r"{app}", r"{tmp}/config.yaml"], capture_output=True, text=True, timeout=200)
+import os
+r = subprocess.run([r"{app}", r"{tmp}/config.yaml"], capture_output=True, text=True, timeout=200 * float(os.environ.get("MVO_TEST_TIMEOUT_SCALE", "1")))
 assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
 assert "Wrote %d poses" % n in r.stdout
 # the same frames through the ctypes path with the same configuration
