@@ -2,11 +2,8 @@
 mvo_remove_wrong_rt_of_homography; reference src/geometry/epipolar_geometry.cpp:59-128) against the reference's
 arithmetic (oracle/epipolar_oracle.py = cv2.findHomography + decomposeHomographyMat + filterHomographyDecompByVisibleRefpoints).
 
-The three RANSAC kernels of this path were written after the round's GPU budget was spent: their numerics are covered
-on the CPU tier (tests/test_epipolar_math.py, same header compiled for the host) and they mirror the essential-matrix
-kernels that did run on hardware, but they have not executed on a B200 yet.  The check therefore runs in a CHILD
-process (a faulting kernel cannot take the rest of the suite with it) and is marked xfail(strict=False): XPASS = it
-works as written, xfail = round 2 starts there."""
+Passes on the B200 (round-1 driver run, GPUTEST_r01.json).  The check runs in a CHILD process so that a faulting kernel
+cannot take the rest of the suite with it."""
 import subprocess
 import sys
 from pathlib import Path
@@ -113,7 +110,6 @@ print("homography child ok")
 '''
 
 
-@pytest.mark.xfail(strict=False, reason="kernels written after the round-1 GPU budget was spent: first hardware run")
 def test_homography_path_in_child_process(built):
     r = subprocess.run([sys.executable, "-c", CHILD.format(root=str(ROOT))], capture_output=True, text=True, timeout=180 * _TIMEOUT_SCALE)
     assert r.returncode == 0 and "homography child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])

@@ -1,8 +1,7 @@
 """Experimental ORB kernel variants (csrc/orb.cu: k_blur2 under MVO_BLUR2=1, k_describe_sel2 under MVO_DESCRIBE2=1): same
-arithmetic as the shipped kernels with fewer instructions, written after the round-1 GPU budget was spent.  The switch is
-read once per process, so each configuration runs in its own child process; keypoints and descriptors must be
-byte-identical with the shipped kernels' (which are themselves bit-exact with cv2, tests/test_orb_gpu.py).
-xfail(strict=False): XPASS = the variant can be made the default after a timing run (tools/dev_orb_variants.py)."""
+arithmetic as the shipped kernels with fewer instructions.  The switch is read once per process, so each configuration
+runs in its own child process; keypoints and descriptors must be byte-identical with the shipped kernels' (which are
+themselves bit-exact with cv2, tests/test_orb_gpu.py).  Passes on the B200 (GPUTEST_r01.json)."""
 import os
 import subprocess
 import sys
@@ -47,7 +46,6 @@ def _extract(tmp_path, name, env):
 
 
 @pytest.mark.parametrize("env", [{"MVO_BLUR2": "1"}, {"MVO_DESCRIBE2": "1"}, {"MVO_BLUR2": "1", "MVO_DESCRIBE2": "1"}], ids=["blur2", "describe2", "both"])
-@pytest.mark.xfail(strict=False, reason="experimental kernel variants: first hardware run")
 def test_variant_is_byte_identical_with_the_shipped_kernels(built, tmp_path, env):
     ref = _extract(tmp_path, "shipped", {"MVO_BLUR2": "0", "MVO_DESCRIBE2": "0"})
     got = _extract(tmp_path, "variant", env)

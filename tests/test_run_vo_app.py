@@ -106,7 +106,6 @@ print("run_vo child ok")
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_cv2(), reason="cv2 writes the PNG dataset")
-@pytest.mark.xfail(strict=False, reason="application assembled after the round-1 GPU budget was spent: first hardware run")
 def test_run_vo_on_a_png_dataset(built, tmp_path):
     r = subprocess.run([sys.executable, "-c", GPU_CHILD.format(root=str(ROOT), tmp=str(tmp_path), app=str(APP), fixture=str(GOLDEN / "config_fixture.yaml"))],
                        capture_output=True, text=True, timeout=300 * _TIMEOUT_SCALE)
