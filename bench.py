@@ -1,23 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — frames/sec of the per-frame VO hot path on B200.
+"""bench.py — frames/sec of the whole run_vo pipeline on B200 (BASELINE.json config 5).
 
-A STEP is one tracked frame: ORB extract + grid-NMS (640x480, max 2000+1 keypoints) -> Hamming
-match of the visible map points against the frame -> batched RANSAC PnP (4096 hypotheses) ->
-bundle adjustment over the newest 5 frames (10 LM iterations), i.e. mvo_tracker_track().
+A STEP is one pass of the VisualOdometry state machine (mvo_vo_add_frame, reference src/vo/vo_addFrame.cpp:10-142) over
+one synthetic 150-frame 640x480 sequence, from a BLANK state: ORB extract + grid-NMS (<= 2001 keypoints) on every frame,
+two-view initialisation (essential + homography RANSAC, triangulation, E/H choice), then per frame the match of the map
+points in view against the frame, RANSAC PnP, the 5-frame bundle adjustment (10 LM iterations, fixed map points as
+shipped), and on every large move a keyframe: match with the previous keyframe, epipolar inliers, triangulation,
+pushCurrPointsToMap_, optimizeMap_.  Initialisation and keyframes are inside the timed region.
 
-  value   frames/s with the frame images already resident in HBM (160 device copies = 147 MB,
-          larger than the 126 MB L2, cycled so no frame is re-read from cache)
-  e2e     the same metric through the C ABI with HOST images: the H2D copy of every frame and
-          the D2H read of its pose are inside the timed region
-  --impl reference   the reference's own CPU path on the host cores: cv2 (the OpenCV the
-          reference calls) for ORB / matching / solvePnPRansac + oracle/ba_oracle.c (g2o
-          restated); the reference binary itself cannot be built here (no OpenCV C++/g2o/...)
+  value   frames/s with the frame images already resident in HBM (150 slots = 138 MB > the 126 MB L2)
+  e2e     the same metric through the C ABI with HOST images (page-locked): the H2D copy of every frame and the D2H read
+          of its pose are inside the timed region; e2e_pageable: the same from ordinary (pageable) memory, as a cv::Mat is
+  --impl reference   the reference's own CPU path on the host cores over the same sequence: oracle/vo_pipeline_oracle.py =
+          the same state machine over cv2 (the OpenCV the reference calls) + oracle/ba_oracle.c (g2o restated); the
+          reference binary itself cannot be built here (no OpenCV C++/g2o/...)
 
 One JSON line on stdout (rank 0).  Launch for N > 1:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port P bench.py --gpus N --steps K --warmup W
-Multi-GPU = independent sequences per GPU (replicas only): NCCL only carries the
-per-rank timings (all_reduce MAX).
+Multi-GPU = independent sequences per GPU (replicas only): NCCL only carries the per-rank timings
+(all_reduce MAX).
 """
 from __future__ import annotations
 
@@ -36,13 +38,24 @@ sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python"))
 sys.path.insert(0, str(ROOT))
 
 W, H = 640, 480
-N_DISTINCT = 16          # distinct rendered frames per sequence (ping-pong trajectory)
-N_DEVICE_COPIES = 160    # device-resident frame slots: 160 x 921,600 B = 147 MB > L2 (126 MB)
+# frames per sequence (BASELINE config 5: >= 150); MVO_BENCH_FRAMES is a test hook (tests/test_multirank_cpu.py runs the
+# reference arm on a short sequence) and shows up in config.frames_per_step
+N_FRAMES = int(os.environ.get("MVO_BENCH_FRAMES", "150"))
 MAX_KPTS = 2000
 BA_ITERS = 10
 METRIC = "VO frames/sec @ 640x480, 2000 kpts, 5-frame BA"
-WORKLOAD = ("tracked frame: ORB extract+grid-NMS 640x480 (<=2001 kpts) + Hamming match vs map + RANSAC PnP "
-            "(4096 hyp, 2 px) + 5-frame BA (10 LM it, Huber, fixed map points as shipped)")
+WORKLOAD = ("full run_vo pipeline (VisualOdometry::addFrame state machine) over one synthetic 640x480 sequence per GPU: "
+            "ORB extract+grid-NMS (<=2001 kpts), two-view initialisation (E+H RANSAC, triangulation), then per frame Hamming match "
+            "vs map + RANSAC PnP (2 px) + 5-frame BA (10 LM it, Huber, fixed map points as shipped), keyframe insertion + "
+            "triangulation + map culling on every large move")
+
+
+def bench_config():
+    """The configuration both arms run, verbatim in both JSON lines."""
+    return {"workload": WORKLOAD, "frames_per_step": N_FRAMES, "image": "640x480 BGR u8",
+            "sequence": f"mvo_synth.room_loop_sequence(seed=rank, {N_FRAMES} frames): ray-cast textured box room, closed-loop 6-dof trajectory",
+            "l2": f"inputs larger than L2: {N_FRAMES} frames x 921,600 B = {N_FRAMES * H * W * 3 / 1e6:.0f} MB > 126 MB, each read once per step"}
+
 
 # Algorithmic bytes per launch of each kernel class for ONE 640x480 frame (DESIGN.md §Kernels;
 # SURVEY.md §8d gives the per-frame ORB figure 1,041,660 B = BGR in + keypoints + descriptors out).
@@ -61,6 +74,7 @@ ALGO_BYTES = {
     "k_ba": 10000 * 16 + 2000 * 24 + 5 * 96,
     # match-list filter (the largest member of the class): keys + in-view flags + map points in, pairs + PnP arrays out
     "k_track_glue": 2001 * (4 + 1 + 12) + 1300 * (8 + 20),
+    "k_epi": 2000 * 16 + 4096 * 72,
 }
 
 
@@ -124,8 +138,8 @@ def nvml_index(local_rank):
 
 
 def pin_to_gpu_numa_node(index):
-    """Run this rank's threads (tracker main thread, its extraction worker) on the cores NVML reports as local to the
-    GPU: the step is a chain of small dependent launches, so launch latency across the socket boundary shows."""
+    """Run this rank's threads (main thread, extraction worker) on the cores NVML reports as local to the GPU: a tracked
+    frame is a chain of small dependent launches, so launch latency across the socket boundary shows."""
     if os.environ.get("MVO_BENCH_NO_PIN"):
         return
     try:
@@ -142,33 +156,25 @@ def pin_to_gpu_numa_node(index):
 
 
 def build_sequence(seed):
-    """16 distinct frames of a textured plane + ground-truth poses; visiting order is a ping-pong."""
+    """The rank's sequence: N_FRAMES BGR frames of the ray-cast room + ground-truth camera->world poses."""
     import mvo_synth
-    frames, T_c_w, _ = mvo_synth.planar_sequence(seed, n_frames=N_DISTINCT, plane_z=4.0)
-    imgs = [mvo_synth.gray_to_bgr(f) for f in frames]
-    order = list(range(1, N_DISTINCT)) + list(range(N_DISTINCT - 2, 0, -1))      # 1..15,14..1 then repeat
-    return imgs, [np.linalg.inv(T) for T in T_c_w], order
+    frames, truth = mvo_synth.cached_room_loop_sequence(seed, N_FRAMES)
+    return [mvo_synth.gray_to_bgr(f) for f in frames], [np.asarray(T) for T in truth]
 
 
-def map_from_first_frame(kp, plane_z=4.0):
+def trajectory_stats(poses, truth, states):
+    """ATE of the estimated trajectory from the frame the VO initialised at (similarity-aligned: monocular scale)."""
     import mvo_synth
-    Ki = np.linalg.inv(mvo_synth.K_DEFAULT)
-    rays = (Ki @ np.stack([kp["x"], kp["y"], np.ones(len(kp))]).astype(np.float64)).T
-    return (rays * (plane_z / rays[:, 2:3])).astype(np.float32)
-
-
-def map_order(n, seed=20240923):
-    """Order in which the map points are handed to the tracker (both arms): a seeded permutation, standing for the
-    iteration order of the reference's std::unordered_map<int, MapPoint::Ptr> (include/my_slam/vo/map.h:25,
-    src/vo/vo.cpp:25).  The order keypoints come out of ORB (level-major, raster within a level) is a degenerate
-    input for removeDuplicatedMatches: libstdc++'s median-of-3 std::sort over the match list then exhausts its depth
-    limit on every frame and falls back to heapsort (feature_match.cpp:244-247)."""
-    return np.random.default_rng(seed).permutation(n)
+    init = states.index(2) if 2 in states else -1
+    if init < 0 or len(poses) - init < 3:
+        return {"initialised_at": init, "ate_rms": None}
+    err, scale = mvo_synth.trajectory_error(poses[init:], truth[init:])
+    return {"initialised_at": init, "ate_rms": err, "scale": scale}
 
 
 # ------------------------------------------------------------------------- multi-rank plumbing
 def sequence_seed(rank):
-    """Replicas only: rank r tracks its own independent synthetic sequence, seed = r."""
+    """Replicas only: rank r runs its own independent synthetic sequence, seed = r."""
     return int(rank)
 
 
@@ -183,46 +189,69 @@ def reduce_max_ms(ms, dist, device):
 
 
 def whole_job_fps(world, steps, ms):
-    """Aggregate throughput: every rank tracked `steps` frames of its own sequence in `ms` (max over ranks)."""
-    return world * steps / (ms / 1e3)
+    """Aggregate throughput: every rank ran `steps` passes over its own N_FRAMES-frame sequence in `ms` (max over ranks)."""
+    return world * steps * N_FRAMES / (ms / 1e3)
 
 
 # ------------------------------------------------------------------------------- reference arm
+def cpu_pass(imgs):
+    """One pass of the reference's CPU path (the oracle pipeline) over the sequence; returns poses, states, keyframes."""
+    import mvo_synth
+    from oracle import vo_pipeline_oracle as vp
+    cpu = vp.CpuVo(mvo_synth.K_DEFAULT, H, W, max_number_of_keypoints=MAX_KPTS, ba_iterations=BA_ITERS, init_calc_homography=True)
+    poses, states, kf = [], [], 0
+    for im in imgs:
+        T, info = cpu.add_frame(im)
+        poses.append(T); states.append(info["state_out"]); kf += int(info["keyframe"])
+    return poses, states, kf
+
+
+def cpu_sample_text(cv2, n_pass, dt):
+    return (f"{n_pass} pass(es) over the {N_FRAMES}-frame sequence of seed 0 ({dt:.1f} s): the run_vo state machine restated in Python "
+            f"(oracle/vo_pipeline_oracle.py, libstdc++ container order) over cv2 {cv2.__version__} — ORB detect/compute, BFMatcher, "
+            f"findEssentialMat/recoverPose, findHomography/decomposeHomographyMat, triangulatePoints, solvePnPRansac(100 it, 2 px, 0.999): "
+            f"the OpenCV routines the reference calls — + oracle/ba_oracle.c (g2o restated, {BA_ITERS} LM it); reference binary not buildable here")
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU path (cv2 + restated g2o) on the host cores; rank 0 only."""
+    """The reference's CPU path on the host cores; rank 0 only."""
     if rank != 0:
         return
     import cv2
-    import mvo_synth
-    from oracle import vo_oracle
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
-    imgs, T_true, order = build_sequence(0)
-    trk = vo_oracle.CpuTracker(mvo_synth.K_DEFAULT, H, W, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
-    kp0, desc0 = trk.extract(imgs[0])
-    perm = map_order(len(kp0))
-    trk.set_map(map_from_first_frame(kp0)[perm], desc0[perm])
-    trk.reset(np.eye(4))
-    for i in range(args.warmup):
-        trk.track(imgs[order[i % len(order)]])
+    imgs, truth = build_sequence(0)
+    for _ in range(args.warmup):
+        cpu_pass(imgs[:30])                 # warm-up: page in cv2 / the oracle library (a bounded prefix per warm-up step)
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        trk.track(imgs[order[(args.warmup + i) % len(order)]])
+    for _ in range(args.steps):
+        poses, states, kf = cpu_pass(imgs)
     dt = time.perf_counter() - t0
-    fps = args.steps / dt
-    sample = (f"{args.steps} tracked frames of sequence seed 0 (cv2 {cv2.__version__} ORB detect/compute, exact Hamming "
-              f"matcher restated in C++, cv2.solvePnPRansac(100 it, 2 px, 0.999), oracle/ba_oracle.c g2o restatement, "
-              f"5-frame window, {BA_ITERS} LM it); reference binary not buildable here")
+    fps = args.steps * N_FRAMES / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": 1, "image": "640x480 BGR u8"},
+        "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic", "config": bench_config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cv2.getNumThreads(), "host_cores": cores,
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "sample": cpu_sample_text(cv2, args.steps, dt)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "trajectory": dict(trajectory_stats(poses, truth, states), keyframes=kf),
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline():
+    """The same workload on the host cores (bounded sample: one pass = 150 frames), rank 0 / N=1 only."""
+    import cv2
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    imgs, truth = build_sequence(0)
+    cpu_pass(imgs[:20])
+    t0 = time.perf_counter()
+    poses, states, kf = cpu_pass(imgs)
+    dt = time.perf_counter() - t0
+    return {"value": N_FRAMES / dt, "unit": "frames/s", "cores": cv2.getNumThreads(), "host_cores": cores, "kind": "port",
+            "sample": cpu_sample_text(cv2, 1, dt), "trajectory": dict(trajectory_stats(poses, truth, states), keyframes=kf)}
 
 
 # --------------------------------------------------------------------------------------- own arm
@@ -245,210 +274,257 @@ def run_gpu(args, rank, world, local_rank):
     ctx = mvo_b200.Context(local_rank, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
     ctx.set_stream(stream.cuda_stream)
     K = mvo_synth.K_DEFAULT
+    imgs, truth = build_sequence(sequence_seed(rank))          # one independent sequence per rank / GPU
+    vo = mvo_b200.VisualOdometry(ctx, K, H, W)
+    if not vo.device_resident:
+        raise SystemExit("bench.py: the state machine did not select the device-resident tracking path")
 
-    imgs, T_true, order = build_sequence(sequence_seed(rank))          # one independent sequence per rank / GPU
-    kp0, desc0 = ctx.orb_extract(imgs[0])
-    perm = map_order(len(kp0))
-    map_pts = map_from_first_frame(kp0)[perm]
-    desc0 = np.ascontiguousarray(desc0[perm])
-    trk = mvo_b200.Tracker(ctx, K, H, W)
-    trk.set_map(map_pts, desc0)
-    trk.reset(np.eye(4))
-
-    # device-resident frame slots (> L2) and pinned host frames
-    d_frames = torch.empty((N_DEVICE_COPIES, H, W, 3), dtype=torch.uint8, device="cuda")
-    h_frames = [torch.from_numpy(im).pin_memory() for im in imgs]
-    for s in range(N_DEVICE_COPIES):
-        d_frames[s].copy_(h_frames[order[s % len(order)]], non_blocking=True)
-    torch.cuda.synchronize()
+    # device-resident frames (> L2) and page-locked / pageable host frames
     frame_bytes = H * W * 3
+    d_frames = torch.empty((N_FRAMES, H, W, 3), dtype=torch.uint8, device="cuda")
+    h_frames = [torch.from_numpy(im).pin_memory() for im in imgs]
+    for s in range(N_FRAMES):
+        d_frames[s].copy_(h_frames[s], non_blocking=True)
+    torch.cuda.synchronize()
+    h_np = [t.numpy() for t in h_frames]          # views of the pinned buffers (stable pointers)
+    p_np = [np.array(im, copy=True) for im in imgs]   # ordinary (pageable) memory, as a cv::Mat from cv::imread is
 
     def dev_args(i):
-        return (d_frames[i % N_DEVICE_COPIES].data_ptr(),), dict(channels=3, stride=W * 3, on_device=True)
+        return (d_frames[i].data_ptr(),), dict(channels=3, stride=W * 3, on_device=True)
 
     def host_args(i):
-        return (h_np[order[i % len(order)]],), {}
+        return (h_np[i],), {}
 
-    h_np = [t.numpy() for t in h_frames]          # views of the pinned buffers (stable pointers)
+    def pageable_args(i):
+        return (p_np[i],), {}
 
-    def run_steps(args_of, n, first):
-        """n tracked frames; the extraction of frame i+1 is enqueued (second stream) before frame i is tracked."""
-        last = None
-        a, k = args_of(first)
-        trk.prefetch(*a, **k)
-        for i in range(n):
-            if i + 1 < n:
-                a2, k2 = args_of(first + i + 1)
-                trk.prefetch(*a2, **k2)
-            a, k = args_of(first + i)
-            last = trk.track(*a, **k)
-        return last
+    def run_pass(args_of):
+        """One step: the whole sequence from a BLANK state; frame i+1 is handed over (look-ahead) before frame i is added."""
+        vo.reset()
+        poses, states, kf = [], [], 0
+        a, k = args_of(0)
+        vo.prefetch(*a, **k)
+        info = None
+        for i in range(N_FRAMES):
+            if i + 1 < N_FRAMES:
+                a2, k2 = args_of(i + 1)
+                vo.prefetch(*a2, **k2)
+            a, k = args_of(i)
+            T, info = vo.add_frame(*a, **k)
+            poses.append(T); states.append(info.state_out); kf += info.keyframe
+        return poses, states, kf, info
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(args_of, n, first):
+    def timed(args_of, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        last = run_steps(args_of, n, first)
+        last = None
+        for _ in range(n):
+            last = run_pass(args_of)
         e1.record(stream)
         barrier()
         return reduce_max_ms(e0.elapsed_time(e1), dist, "cuda"), last
 
-    # warm-up (>= 3), then a calibration pass with every kernel class timed to find the dominant one
+    # warm-up (>= 3 passes), then a calibration pass with every kernel class timed to find the dominant one
     warm = max(args.warmup, 3)
-    run_steps(dev_args, warm, 0)
+    for _ in range(warm):
+        run_pass(dev_args)
     names = mvo_b200.kernel_names()
-    trk.timing_enable((1 << len(names)) - 1)
-    trk.timing_read()
-    ncal = min(32, max(8, args.steps))
-    run_steps(dev_args, ncal, warm)
-    ms_k, cnt_k = trk.timing_read()
-    stages = {names[k]: {"us_per_frame": 1e3 * ms_k[k] / ncal, "launches_per_frame": float(cnt_k[k]) / ncal}
+    vo.timing_enable((1 << len(names)) - 1)
+    vo.timing_read()
+    run_pass(dev_args)
+    ms_k, cnt_k = vo.timing_read()
+    stages = {names[k]: {"us_per_frame": 1e3 * ms_k[k] / N_FRAMES, "launches_per_frame": float(cnt_k[k]) / N_FRAMES}
               for k in range(len(names)) if cnt_k[k]}
     dominant = max(stages, key=lambda k: stages[k]["us_per_frame"])
-    trk.timing_enable(0)
+    vo.timing_enable(0)
 
     # ---- timed region: K steps, images resident in HBM, no per-kernel events ----
     sampler = ClockSampler(nvml_index(local_rank))
     sampler.start()
-    launches0 = trk.kernel_launches
-    first = warm + ncal
-    ms, (T_last, res_last) = timed(dev_args, args.steps, first)
-    launches = trk.kernel_launches - launches0
+    launches0 = vo.kernel_launches
+    ms, (poses, states, kf, info_last) = timed(dev_args, args.steps)
+    launches = vo.kernel_launches - launches0
     clocks = sampler.stop()
     # the dominant kernel's average launch duration: CUDA events around ITS launches only, same loop, separate pass
-    trk.timing_enable(1 << names.index(dominant))
-    trk.timing_read()
-    run_steps(dev_args, ncal, first + args.steps)
-    ms_d, cnt_d = trk.timing_read()
     kd = names.index(dominant)
+    vo.timing_enable(1 << kd)
+    vo.timing_read()
+    run_pass(dev_args)
+    ms_d, cnt_d = vo.timing_read()
     dom_us = 1e3 * ms_d[kd] / max(int(cnt_d[kd]), 1)
-    trk.timing_enable(0)
+    vo.timing_enable(0)
 
     # ---- e2e: host images through the C ABI, H2D + D2H inside the timed region ----
-    trk.reset(np.eye(4))
-    run_steps(host_args, warm, 0)
-    ms_e2e, _ = timed(host_args, args.steps, warm)
+    run_pass(host_args)
+    ms_e2e, _ = timed(host_args, args.steps)
+    n_pg = max(1, min(args.steps, 5))
+    run_pass(pageable_args)
+    ms_pg, _ = timed(pageable_args, n_pg)
 
-    # ---- batched, device-resident ORB extraction (BASELINE config 2; SURVEY.md §8d: the only form of the path whose
-    # algorithmic bytes are comparable with the HBM roofline) ----
-    orb_batch = None
+    by_kind = None
+    extra = None
     if rank == 0:
-        B = 64
-        cap = MAX_KPTS + 1
-        d_k = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
-        d_d = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
-        d_c = torch.empty(B, dtype=torch.int32, device="cuda")
-        torch.cuda.synchronize()
+        # where the wall time of a pass goes, by kind of frame (host clock, one extra pass)
+        vo.reset()
+        kinds = {}
+        vo.prefetch(*dev_args(0)[0], **dev_args(0)[1])
+        for i in range(N_FRAMES):
+            if i + 1 < N_FRAMES:
+                vo.prefetch(*dev_args(i + 1)[0], **dev_args(i + 1)[1])
+            t1 = time.perf_counter()
+            _, inf = vo.add_frame(*dev_args(i)[0], **dev_args(i)[1])
+            dt = time.perf_counter() - t1
+            kind = "first" if inf.state_in == 0 else "initialisation" if inf.state_in == 1 else "keyframe" if inf.keyframe else "tracked"
+            kinds.setdefault(kind, []).append(dt)
+        by_kind = {k: {"n": len(v), "ms_mean": 1e3 * float(np.mean(v)), "ms_median": 1e3 * float(np.median(v))} for k, v in kinds.items()}
+        extra = bench_extras(ctx, stream, d_frames, names, torch, mvo_b200, mvo_synth)
 
-        def orb_batch_call(first_slot):
-            ctx.orb_extract_batch_dev(d_frames[first_slot].data_ptr(), B, H, W, 3, W * 3, frame_bytes, d_k.data_ptr(), d_d.data_ptr(),
-                                      d_c.data_ptr(), cap)
-        for w in range(3):
-            orb_batch_call(0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nrep = 10
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for it in range(nrep):
-            orb_batch_call((it % 2) * B)          # 2 x 64 different slots: 118 MB of input between revisits
-        e1.record(stream)
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / nrep
-        nk = int(d_c.sum().item())
-        # where the batch time goes: CUDA events around every kernel class, separate pass
-        mvo_b200.timing_enable(ctx, (1 << len(names)) - 1)
-        mvo_b200.timing_read(ctx)
-        for it in range(2):
-            orb_batch_call((it % 2) * B)
-        ms_b, cnt_b = mvo_b200.timing_read(ctx)
-        mvo_b200.timing_enable(ctx, 0)
-        batch_stages = {names[k]: round(1e3 * ms_b[k] / (2 * B), 3) for k in range(len(names)) if cnt_b[k]}
-        algo = B * (frame_bytes + 28 * (nk / B) + 32 * (nk / B))     # SURVEY §8d: BGR in + KeyPoint + descriptor out
-        peak_b, _ = _peaks()
-        orb_batch = {"batch": B, "us_per_batch": us, "frames_per_s": B / (us * 1e-6), "keypoints_per_frame": nk / B,
-                     "algorithmic_bytes_per_frame": algo / B, "achieved_GBps": algo / (us * 1e-6) / 1e9,
-                     "hbm_frac": algo / (us * 1e-6) / 1e9 / peak_b, "kernel_us_per_frame": batch_stages,
-                     "note": "mvo_orb_extract_batch_dev, 64 frames per call, includes its one host sync per batch; "
-                             "integer-issue bound (FAST + BRIEF), not HBM bound — DESIGN.md §5"}
-
-    # sanity: the pipeline is really tracking (not timing failures)
-    ok = bool(res_last.pnp_ok) and res_last.n_inliers > 100
+    ok = bool(info_last.state_out == 2) and kf >= 5 and info_last.n_inliers > 30
 
     if rank == 0:
         peak, peak_src = _peaks()
         fps = whole_job_fps(world, args.steps, ms)
         fps_e2e = whole_job_fps(world, args.steps, ms_e2e)
+        fps_pg = whole_job_fps(world, n_pg, ms_pg)
         ab = ALGO_BYTES.get(dominant)
-        traffic = None
+        traffic, issue = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             traffic = json.loads(tp.read_text()).get(dominant)
+        ip = ROOT / "profiles" / "issue.json"
+        if ip.exists():
+            issue = json.loads(ip.read_text()).get(dominant)
         roof = {"kernel": dominant, "bound": "hbm", "achieved": (ab / (dom_us * 1e-6) / 1e9) if ab else None,
                 "peak": peak, "unit": "GB/s", "frac": (ab / (dom_us * 1e-6) / 1e9 / peak) if ab else None,
                 "traffic": traffic, "us_per_launch": dom_us, "algorithmic_bytes_per_launch": ab, "peak_source": peak_src,
-                "note": "single-frame launches are latency/issue-bound, not HBM-bound (DESIGN.md §Roofline)"}
+                "issue_frac": issue,
+                "note": "single-frame launches are latency/issue-bound, not HBM-bound (DESIGN.md §Roofline); issue_frac = issue-active "
+                        "share of the kernel's SM cycles x share of SMs it occupies, from the committed ncu capture (profiles/issue.json)"}
+        d2h = 768 + 20 * 96
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/f32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": 1, "image": "640x480 BGR u8",
-                       "sequences": "one independent synthetic sequence per GPU (seed = rank)",
-                       "map": f"{len(map_pts)} points triangulated from frame 0, handed over in a seeded random order (bench.map_order)",
-                       "pipelining": "ORB extraction of frame i+1 overlaps the tracking of frame i (2 streams); results identical",
-                       "l2": f"{N_DEVICE_COPIES} device-resident frame slots = {N_DEVICE_COPIES * frame_bytes / 1e6:.0f} MB > 126 MB L2, cycled",
-                       "tracking_ok": ok, "last_frame": {"keypoints": res_last.n_keypoints, "matches": res_last.n_matches,
-                                                         "inliers": res_last.n_inliers, "ba_frames": res_last.ba_frames}},
+            "dtype": "u8/f32/f64", "data": "synthetic", "config": bench_config(),
+            "detail": {"sequences": "one independent synthetic sequence per GPU (seed = rank)",
+                       "ms_per_frame": ms / args.steps / N_FRAMES,
+                       "pipelining": "the next frame is handed over with mvo_vo_prefetch: its upload, ORB extraction and descriptor matching "
+                                     "overlap the current frame (2 streams); results identical",
+                       "device_resident": True, "tracking_ok": ok, "keyframes": int(kf),
+                       "last_frame": {"keypoints": info_last.n_keypoints, "matches": info_last.n_matches,
+                                      "inliers": info_last.n_inliers, "ba_frames": info_last.ba_frames, "map_points": info_last.map_points},
+                       "ms_per_frame_by_kind": by_kind},
+            "trajectory": dict(trajectory_stats(poses, truth, states), keyframes=int(kf)),
             "clocks": clocks,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 768 + 20 * 96,
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * N_FRAMES, "d2h_bytes_per_step": d2h * N_FRAMES,
+                    "ms_per_step": ms_e2e / args.steps, "host_memory": "page-locked (cudaHostAlloc) caller buffers"},
+            "e2e_pageable": {"value": fps_pg, "unit": "frames/s", "steps": n_pg, "ms_per_step": ms_pg / n_pg,
+                             "host_memory": "pageable caller buffers (as cv::imread's cv::Mat)"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "stages": stages,
-            "orb_batch": orb_batch,
+            "extra": extra,
         }
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
-    trk.close()
+    vo.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(n_frames=100):
-    """The same workload on the host cores (bounded sample), rank 0 / N=1 only."""
-    import cv2
-    import mvo_synth
-    from oracle import vo_oracle
-    cores = os.cpu_count() or 1
-    cv2.setNumThreads(cores)
-    imgs, _, order = build_sequence(0)
-    trk = vo_oracle.CpuTracker(mvo_synth.K_DEFAULT, H, W, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
-    kp0, desc0 = trk.extract(imgs[0])
-    perm = map_order(len(kp0))
-    trk.set_map(map_from_first_frame(kp0)[perm], desc0[perm])
-    trk.reset(np.eye(4))
-    for i in range(3):
-        trk.track(imgs[order[i]])
+def bench_extras(ctx, stream, d_frames, names, torch, mvo_b200, mvo_synth):
+    """BASELINE configs 2-4 as stand-alone stage timings (rank 0): batched device-resident ORB extraction, RANSAC PnP on
+    2000 correspondences x 4096 hypotheses, bundle adjustment of 5 frames x 2000 FREE points (Schur), 10 LM iterations."""
+    out = {}
+    peak_b, _ = _peaks()
+    frame_bytes = H * W * 3
+
+    def ev_time(fn, nrep):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for it in range(nrep):
+            fn(it)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / nrep        # us per call
+
+    # ---- config 2: batched ORB (the only form of the path whose algorithmic bytes are comparable with the HBM roofline) ----
+    B = 64
+    cap = MAX_KPTS + 1
+    d_k = torch.empty(B * cap * 28, dtype=torch.uint8, device="cuda")
+    d_d = torch.empty(B * cap * 32, dtype=torch.uint8, device="cuda")
+    d_c = torch.empty(B, dtype=torch.int32, device="cuda")
+
+    def orb_batch_call(it):
+        ctx.orb_extract_batch_dev(d_frames[(it % 2) * B].data_ptr(), B, H, W, 3, W * 3, frame_bytes, d_k.data_ptr(), d_d.data_ptr(),
+                                  d_c.data_ptr(), cap)
+    for w in range(3):
+        orb_batch_call(w)
+    us = ev_time(orb_batch_call, 10)                       # 2 x 64 different slots: 118 MB of input between revisits
+    nk = int(d_c.sum().item())
+    mvo_b200.timing_enable(ctx, (1 << len(names)) - 1)
+    mvo_b200.timing_read(ctx)
+    for it in range(2):
+        orb_batch_call(it)
+    ms_b, cnt_b = mvo_b200.timing_read(ctx)
+    mvo_b200.timing_enable(ctx, 0)
+    batch_stages = {names[k]: round(1e3 * ms_b[k] / (2 * B), 3) for k in range(len(names)) if cnt_b[k]}
+    algo = B * (frame_bytes + 28 * (nk / B) + 32 * (nk / B))     # SURVEY §8d: BGR in + KeyPoint + descriptor out
+    out["orb_batch"] = {"batch": B, "us_per_batch": us, "frames_per_s": B / (us * 1e-6), "keypoints_per_frame": nk / B,
+                        "algorithmic_bytes_per_frame": algo / B, "achieved_GBps": algo / (us * 1e-6) / 1e9,
+                        "hbm_frac": algo / (us * 1e-6) / 1e9 / peak_b, "kernel_us_per_frame": batch_stages,
+                        "kernel_only_hbm_frac": (algo / B) / (sum(batch_stages.values()) * 1e-6) / 1e9 / peak_b if batch_stages else None,
+                        "note": "mvo_orb_extract_batch_dev, 64 frames per call; integer-issue bound (FAST + BRIEF), not HBM bound — DESIGN.md §6"}
+
+    # ---- config 3: RANSAC PnP, 2000 correspondences, 4096 hypotheses (host-array entry point, includes its copies) ----
+    P, uv, _, _, _ = mvo_synth.pnp_problem(0, n=2000)
+    hyp = int(ctx.params.pnp_hypotheses)
+    for _ in range(3):
+        ctx.solve_pnp_ransac(P, uv, mvo_synth.K_DEFAULT)
     t0 = time.perf_counter()
-    for i in range(n_frames):
-        trk.track(imgs[order[(3 + i) % len(order)]])
-    dt = time.perf_counter() - t0
-    return {"value": n_frames / dt, "unit": "frames/s", "cores": cv2.getNumThreads(), "host_cores": cores, "kind": "port",
-            "sample": f"{n_frames} tracked frames of sequence seed 0: cv2 {cv2.__version__} ORB/solvePnPRansac (the OpenCV routines "
-                      f"the reference calls), exact Hamming matcher + g2o BA restated in C (oracle/), {dt:.1f} s"}
+    nrep = 50
+    for _ in range(nrep):
+        rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, mvo_synth.K_DEFAULT)
+    us_pnp = (time.perf_counter() - t0) / nrep * 1e6
+    out["pnp_config3"] = {"correspondences": 2000, "hypotheses": int(hyp), "us_per_call": us_pnp, "reprojections_per_s": 2000 * hyp / (us_pnp * 1e-6),
+                          "inliers": int(len(inl)), "timing": "host clock around mvo_solve_pnp_ransac (H2D of the points, 4 kernels, D2H of the result)"}
+
+    # ---- config 4: BA, 5 frames x 2000 free points (Schur complement), 10 LM iterations ----
+    pb = mvo_synth.ba_problem(0, n_frames=5, n_points=2000)
+    ctx.set_params(ba_iterations=BA_ITERS)
+    for _ in range(3):
+        ctx.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"], fix_points=False, update_points=True)
+    mvo_b200.timing_enable(ctx, 1 << names.index("k_ba"))
+    mvo_b200.timing_read(ctx)
+    t0 = time.perf_counter()
+    nrep = 20
+    for _ in range(nrep):
+        _, _, st = ctx.bundle_adjustment(pb["T_w_c"], pb["points"], pb["edge_frame"], pb["edge_point"], pb["obs"], pb["K"], fix_points=False, update_points=True)
+    us_ba = (time.perf_counter() - t0) / nrep * 1e6
+    ms_ba, cnt_ba = mvo_b200.timing_read(ctx)
+    mvo_b200.timing_enable(ctx, 0)
+    kb = names.index("k_ba")
+    E = len(pb["edge_frame"])
+    k_us = 1e3 * ms_ba[kb] / max(int(cnt_ba[kb]), 1)
+    out["ba_config4"] = {"frames": 5, "points": 2000, "edges": int(E), "lm_iterations": int(st[2]), "us_per_call": us_ba, "kernel_us": k_us,
+                         "edge_iterations_per_s": E * float(st[2]) / (k_us * 1e-6), "algorithmic_GBps": ALGO_BYTES["k_ba"] * float(st[2]) / (k_us * 1e-6) / 1e9,
+                         "timing": "kernel_us: CUDA events around k_ba (free points, Schur); us_per_call: host clock around mvo_bundle_adjustment"}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -283,7 +283,10 @@ int mvo_tracker_create(mvo_ctx *ctx, const double *K /* 3x3 */, int rows, int co
                        const mvo_track_params *params /* NULL = defaults */, mvo_tracker **out);
 void mvo_tracker_destroy(mvo_tracker *t);
 /* Replace the map: n points (x,y,z float) with their 32-byte descriptors (MapPoint::pos_,
- * MapPoint::descriptor_).  Copied.  Point index = map point id for the BA graph. */
+ * MapPoint::descriptor_).  Copied.  Point index = map point ID, and ids are stable: frames already in the
+ * buffer keep their connections by id, so a new map must keep every surviving point at its index (append new points, never
+ * reorder); connections to ids >= n leave the BA graph, as connections to erased map points do in the reference
+ * (vo.cpp:438-440).  Call mvo_tracker_reset as well when the new map is unrelated to the old one. */
 int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc, int n);
 /* Clear the frame buffer and set the reference keyframe pose (camera->world 4x4 row-major). */
 int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref);
@@ -415,7 +418,8 @@ typedef struct mvo_vo mvo_vo;
 
 typedef struct mvo_vo_params {
   mvo_track_params track;              /* tracking keys (match method / radius for PnP, BA window, keyframe distance ...);
-                                          device_resident is ignored */
+                                          device_resident = 1 (default): tracked frames run through the device-resident
+                                          tracker with the map kept in HBM (re-uploaded when a keyframe changes it) */
   int32_t match_method_init;           /* feature_match_method_index_initialization = 1 */
   float max_match_dist_init;           /* max_matching_pixel_dist_in_initialization = 100 */
   float max_match_dist_triangulation;  /* max_matching_pixel_dist_in_triangulation = 100 */
@@ -451,6 +455,23 @@ void mvo_vo_destroy(mvo_vo *v);
 /* addFrame: image rows x cols x channels (3 = BGR, 1 = gray) in host memory.  T_w_c_out = the frame's pose when the
  * call returns (run_vo.cpp:137 records exactly this), info optional. */
 int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t stride, double *T_w_c_out, mvo_vo_frame_info *info);
+/* The same with the image optionally already in device memory (image_on_device != 0). */
+int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device, double *T_w_c_out,
+                        mvo_vo_frame_info *info);
+/* Optional look-ahead (device-resident mode; a no-op otherwise): hand the NEXT frame over so that its upload, ORB extraction
+ * and descriptor matching against the map overlap the current frame (mvo_tracker_prefetch).  Frames must then be added in
+ * the same order with the same image pointer; at most two frames in flight; results are identical. */
+int mvo_vo_prefetch(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device);
+/* 1 when the tracking branch runs through the device-resident tracker (mvo_vo_params::track.device_resident, fixed map
+ * points), 0 when every stage goes through its host-array entry point. */
+int mvo_vo_device_resident(const mvo_vo *v);
+/* Back to the BLANK state (empty map, no frames, ids restart at 0) keeping the allocations: the next frame is the first
+ * frame of a new sequence.  Frames handed to mvo_vo_prefetch but not added yet are dropped. */
+int mvo_vo_reset(mvo_vo *v);
+/* Kernel launch count / per-kernel-class timing over every context the state machine owns (see mvo_timing_*). */
+uint64_t mvo_vo_kernel_launches(const mvo_vo *v);
+int mvo_vo_timing_enable(mvo_vo *v, uint32_t mask);
+int mvo_vo_timing_read(mvo_vo *v, double *ms, uint64_t *counts);
 int mvo_vo_is_initialized(const mvo_vo *v);                  /* VisualOdometry::isInitialized */
 int mvo_vo_map_size(const mvo_vo *v);
 int mvo_vo_num_keyframes(const mvo_vo *v);

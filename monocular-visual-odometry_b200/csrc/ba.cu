@@ -822,9 +822,12 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
       double X0 = 0, X1 = 0, X2 = 1, ou = -1e300, ov = 0;
       if (real) {
         const size_t o = (size_t)s_fslot[f] * a.st.cap + e0 + k;
-        const float *mp = a.st.map_pts + 3 * (size_t)a.st.edge_map[o];
-        const float2 ob = a.st.edge_obs[o];
-        X0 = mp[0]; X1 = mp[1]; X2 = mp[2]; ou = ob.x; ov = ob.y;
+        const int id = a.st.edge_map[o];
+        if (id >= 0 && id < a.st.n_ids && a.st.alive[id]) {       // deleted map points leave the graph (vo.cpp:438-440)
+          const float *mp = a.st.map_pts + 3 * (size_t)id;
+          const float2 ob = a.st.edge_obs[o];
+          X0 = mp[0]; X1 = mp[1]; X2 = mp[2]; ou = ob.x; ov = ob.y;
+        }
       }
       ed[0] = X0; ed[PF_T] = X1; ed[2 * PF_T] = X2; ed[3 * PF_T] = ou; ed[4 * PF_T] = ov;
     }

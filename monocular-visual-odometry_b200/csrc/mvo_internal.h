@@ -125,8 +125,10 @@ int mvo_reserve_pinned(mvo_ctx *ctx, PinBuf &b, size_t bytes);
 // A buffered frame lives in one ring slot: its world->camera pose, its observation list (map point index +
 // pixel, in PnP-inlier order = Frame::inliers_to_mappt_connections_) and the length of that list.
 struct MvoPoseStore {
-  const float *map_pts;        // [nmap][3] MapPoint::pos_
-  const int32_t *edge_map;     // [ring][cap]
+  const float *map_pts;        // [n_ids][3] MapPoint::pos_, indexed by map point ID
+  const uint8_t *alive;        // [n_ids] 0 = the point has left the map: its observations are dropped (vo.cpp:438-440)
+  int n_ids;                   // ids >= n_ids are dropped as well
+  const int32_t *edge_map;     // [ring][cap] map point id
   const float2 *edge_obs;      // [ring][cap]
   const int32_t *cnt;          // [ring]
   double *pose;                // [ring][12] R row-major, t (world->camera)
@@ -148,10 +150,16 @@ struct MvoTrackGlue {
   const mvo_keypoint *kpts;
   int32_t *edge_map;
   float *edge_obs;
+  int32_t *edge_kp;              // [ring][cap] keypoint index of every connection (the key of inliers_to_mappt_connections_)
   int32_t *cnt;
   double *pose;
   int32_t *skip_flag, *res_i;
   double *res_d;
+  const int32_t *map_ids;        // position in the map arrays -> map point id (what the frame buffer stores)
+  // MapPoint::visible_times_ / matched_times_ increments (vo.cpp:44, :347), per position in the map arrays; nullptr = not counted
+  const uint8_t *vis;
+  int nmap;
+  int32_t *vis_cnt, *match_cnt;
 };
 int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,
                           int rows, int cols, uint8_t *d_vis, float *d_cxy);
@@ -173,6 +181,21 @@ struct MvoTrackFilter {
   float *d_p3, *d_p2;
 };
 int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f);
+
+// tracker.cpp: what the state machine (vo_pipeline.cpp) needs from the device-resident tracker beyond mvo.h
+int mvo_trk_device_mode(const mvo_tracker *t);
+void mvo_trk_configure(mvo_tracker *t, int external_ref, int count_stats);
+int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device, int *slot, int *nk);
+void mvo_trk_release(mvo_tracker *t, int slot);
+int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc);
+const uint8_t *mvo_trk_desc_dev(mvo_tracker *t, int slot);
+unsigned mvo_trk_slot_serial(const mvo_tracker *t, int slot);
+int mvo_trk_set_map_ids(mvo_tracker *t, const float *pts3d, const uint8_t *desc, const int32_t *ids, int n, int reset_ids);
+int mvo_trk_push_frame(mvo_tracker *t, const double *T_w_c, const int32_t *ids, const int32_t *kp_idx, const float *obs_xy, int n);
+int mvo_trk_append_links(mvo_tracker *t, int k, const int32_t *ids, const int32_t *kp_idx, const float *obs_xy, int n);
+int mvo_trk_links(mvo_tracker *t, int k, int32_t *ids, int32_t *kp_idx, int cap, int *n);
+int mvo_trk_counters(mvo_tracker *t, int32_t *visible, int32_t *matched, int n);
+int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 // mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)

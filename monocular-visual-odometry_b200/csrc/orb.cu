@@ -748,7 +748,9 @@ int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int b
   }
   tiles.first[plan.nlevels] = total;
   dim3 grid(total, 1, batch);
-  static const bool use_blur2 = getenv("MVO_BLUR2") != nullptr && atoi(getenv("MVO_BLUR2")) != 0;     // experimental variant, see k_blur2
+  // k_blur2 (tile moved as words, 4 outputs per thread) measured 2.86 us/frame against 5.19 for k_blur in the batched
+  // extraction on the B200 (gpurun_out/r2s1_orb_variants.jsonl), byte-identical output: default since round 2; MVO_BLUR2=0 = old kernel
+  static const bool use_blur2 = getenv("MVO_BLUR2") == nullptr || atoi(getenv("MVO_BLUR2")) != 0;
   KTimer kt(ctx, KC_BLUR);
   if (use_blur2) k_blur2<<<grid, 256, 0, ctx->stream>>>(plan, tiles, planes);
   else k_blur<<<grid, 256, 0, ctx->stream>>>(plan, tiles, planes);

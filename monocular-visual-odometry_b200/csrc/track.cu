@@ -59,8 +59,13 @@ struct GlueArgs {
   const int32_t *out_i, *inl;
   const int2 *pairs;
   const mvo_keypoint *kpts;
-  int32_t *edge_map;        // [ring][cap]
+  int32_t *edge_map;        // [ring][cap] map point ids
   float2 *edge_obs;
+  int32_t *edge_kp;         // [ring][cap] keypoint indices
+  const int32_t *map_ids;   // position in the map arrays -> id
+  const uint8_t *vis;       // in-view flags of this frame (visible_times_++ of getMappointsInCurrentView_, vo.cpp:44)
+  int nmap;
+  int32_t *vis_cnt, *match_cnt;
   int32_t *cnt;             // [ring]
   double *pose;             // [ring][12]
   int32_t *skip_flag;
@@ -99,9 +104,13 @@ __global__ void __launch_bounds__(1024) k_track_glue(GlueArgs a) {
   n_in = min(n_in, a.cap);
   for (int j = tid; j < n_in; j += blockDim.x) {
     const int2 pr = a.pairs[a.inl[j]];
-    a.edge_map[(size_t)a.slot * a.cap + j] = pr.x;
+    a.edge_map[(size_t)a.slot * a.cap + j] = a.map_ids[pr.x];
+    a.edge_kp[(size_t)a.slot * a.cap + j] = pr.y;
     a.edge_obs[(size_t)a.slot * a.cap + j] = make_float2(a.kpts[pr.y].x, a.kpts[pr.y].y);
+    if (a.match_cnt) a.match_cnt[pr.x] += 1;        // matched_times_++ (vo.cpp:347); the pairs have distinct map points
   }
+  if (a.vis_cnt)
+    for (int q = tid; q < a.nmap; q += blockDim.x) a.vis_cnt[q] += a.vis[q] != 0;
 }
 
 }  // namespace
@@ -143,7 +152,8 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
   for (int q = 0; q < 3; ++q) a.prev_twc[q] = g.prev_twc[q];
   for (int q = 0; q < 12; ++q) a.fallback.v[q] = g.fallback[q];
   a.pose_io = g.pose_io; a.out_i = g.out_i; a.inl = g.inl; a.pairs = (const int2 *)g.pairs; a.kpts = g.kpts;
-  a.edge_map = g.edge_map; a.edge_obs = (float2 *)g.edge_obs; a.cnt = g.cnt; a.pose = g.pose;
+  a.edge_map = g.edge_map; a.edge_obs = (float2 *)g.edge_obs; a.edge_kp = g.edge_kp; a.cnt = g.cnt; a.pose = g.pose;
+  a.map_ids = g.map_ids; a.vis = g.vis; a.nmap = g.nmap; a.vis_cnt = g.vis_cnt; a.match_cnt = g.match_cnt;
   a.skip_flag = g.skip_flag; a.res_i = g.res_i; a.res_d = g.res_d;
   KTimer kt(ctx, KC_TRACK);
   k_track_glue<<<1, 1024, 0, ctx->stream>>>(a);

@@ -50,6 +50,11 @@ struct ExtractJob {
   // methods 1/2: the matcher does not depend on the pose, so the worker runs it right after the extraction
   bool prematch = false, matched = false;
   int match_mode = 0, map_version = 0;
+  unsigned serial = 0;                 // submission number: tells whether the slot still holds a given frame
+  // snapshot taken at submission (the API thread may replace the map while the job runs; a stale match is redone)
+  const uint8_t *d_map_desc = nullptr;
+  uint32_t *d_keys = nullptr;
+  int nmap = 0;
   int rc = MVO_OK, nk = 0;
   const mvo_keypoint *d_k = nullptr;
   const uint8_t *d_d = nullptr;
@@ -109,8 +114,14 @@ struct mvo_tracker {
   double K[9];
   int rows = 0, cols = 0;
   mvo_track_params prm;
+  // The map as the caller handed it over: n points in HIS order (the reference walks std::unordered_map<int, MapPoint::Ptr>
+  // in container order, vo.cpp:25) with their stable ids.  Buffered frames refer to map points by ID.
   std::vector<float> map_pts;        // n x 3
   std::vector<uint8_t> map_desc;     // n x 32
+  std::vector<int32_t> map_ids;      // n
+  std::vector<float> pos_by_id;      // n_ids x 3
+  std::vector<uint8_t> alive;        // n_ids: 1 = the id is in the current map
+  bool external_ref = false;         // the caller (mvo_vo) supplies the guess / previous pose of every frame
   std::deque<TrackedFrame> frames;   // frames_buff_ (oldest first)
   double T_ref[16];                  // reference keyframe pose (initial guess for the next frame)
   bool has_prev = false;
@@ -131,17 +142,20 @@ struct mvo_tracker {
   // extraction worker
   mvo_ctx *xctx[2] = {nullptr, nullptr};
   ExtractJob job[2];
-  unsigned n_submit = 0, n_consume = 0;
+  unsigned n_submit = 0, n_consume = 0, n_submit_total = 0;
   std::thread worker;
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
   bool stop = false;
   unsigned n_run = 0;                // worker-side cursor
-  // device-resident state (one allocation, carved in dev_alloc)
-  uint8_t *dev = nullptr;
-  size_t dev_bytes = 0;
-  int dev_nmap = -1, dev_cap = 0, dev_ring = 0;
+  // device-resident state: three allocations (map arrays by position, by-id arrays, frame ring), each grown by doubling
+  uint8_t *dev = nullptr, *dev_map = nullptr, *dev_ids = nullptr;
+  int dev_nmap = -1;                   // points in the device copy of the map; -1 = stale (refreshed by the next frame)
+  int dev_mcap = 0, dev_idcap = 0, dev_cap = 0, dev_ring = 0;
   float *d_map_pts = nullptr;  uint8_t *d_map_desc = nullptr;
+  int32_t *d_map_ids = nullptr, *d_vis_cnt = nullptr, *d_match_cnt = nullptr, *d_edge_kp = nullptr;
+  float *d_pos_by_id = nullptr;  uint8_t *d_alive = nullptr;
+  bool count_stats = false;            // accumulate visible / matched counts per map point on the device
   uint8_t *d_keysvis[2] = {nullptr, nullptr};   // per extraction slot: [keys nmap*2 u32][vis nmap u8] — one D2H after the match
   int map_version = 0;                 // bumped by set_map: keys matched ahead of time against an older map are redone
   float *d_cxy = nullptr, *d_kxy = nullptr;
@@ -178,10 +192,9 @@ void worker_main(mvo_tracker *t) {
       rc = mvo_orb_extract_begin_dev(x, j->image, t->rows, t->cols, j->channels, j->stride, j->on_device);
       if (rc == MVO_OK) rc = mvo_orb_extract_end_dev(x, &nk, &j->d_k, &j->d_d);
       j->matched = false;
-      if (rc == MVO_OK && j->prematch && nk > 0 && t->dev_nmap > 0 && !(j->match_mode == 1 && nk < 2)) {
+      if (rc == MVO_OK && j->prematch && nk > 0 && j->nmap > 0 && !(j->match_mode == 1 && nk < 2)) {
         // all map descriptors x this frame's descriptors on the extraction stream: off the tracking chain
-        rc = mvo_match_launch_masked(x, j->match_mode, t->d_map_desc, nullptr, t->dev_nmap, j->d_d, nullptr, nk, 0.f,
-                                     (uint32_t *)t->d_keysvis[slot], nullptr);
+        rc = mvo_match_launch_masked(x, j->match_mode, j->d_map_desc, nullptr, j->nmap, j->d_d, nullptr, nk, 0.f, j->d_keys, nullptr);
         if (rc == MVO_OK && cudaStreamSynchronize(x->stream) != cudaSuccess) rc = MVO_ERR_CUDA;
         j->matched = rc == MVO_OK;
       }
@@ -224,61 +237,98 @@ bool use_device_path(const mvo_tracker *t) {
 
 size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// (Re)allocate the device-resident state for the current map size / keypoint capacity / ring size.
+// (Re)allocate / refresh the device-resident state.  Three blocks, each reallocated only when it has to grow (the map
+// changes at every keyframe once mvo_vo drives the tracker): the frame ring (keypoint capacity x ring size; holds the
+// buffered frames, so it is only rebuilt when those parameters change), the map arrays by position (capacity doubled on
+// demand) and the by-id arrays (positions + alive flags the BA graph builder reads).  A stale device copy of the map
+// (dev_nmap == -1) is re-uploaded here.
 int dev_alloc(mvo_tracker *t) {
   mvo_ctx *ctx = t->ctx;
-  const int nmap = (int)(t->map_pts.size() / 3), cap = ctx->prm.max_keypoints + 1, ring = t->prm.buffer_size;
-  if (t->dev && nmap == t->dev_nmap && cap == t->dev_cap && ring == t->dev_ring) return MVO_OK;
+  const int nmap = (int)t->map_ids.size(), n_ids = (int)t->alive.size();
+  const int cap = ctx->prm.max_keypoints + 1, ring = t->prm.buffer_size;
+  const bool ring_ok = t->dev && cap == t->dev_cap && ring == t->dev_ring;
+  const bool map_ok = t->dev_map && nmap <= t->dev_mcap, ids_ok = t->dev_ids && n_ids <= t->dev_idcap;
+  if (ring_ok && map_ok && ids_ok && t->dev_nmap == nmap) return MVO_OK;
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
-  // frames extracted (and matched) ahead of time hold pointers into the old allocation: let them finish first
+  // frames extracted (and matched) ahead of time hold pointers into the map arrays: let them finish first
   for (unsigned k = t->n_consume; k != t->n_submit; ++k) wait_job(t, (int)(k & 1));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const bool keep_frames = t->dev && cap == t->dev_cap && ring == t->dev_ring;   // a map swap keeps the frame buffer
-  const int nm1 = std::max(nmap, 1);
-  size_t o = 0;
-  const size_t o_pts = o;   o = al256(o + (size_t)nm1 * 12);
-  const size_t o_desc = o;  o = al256(o + (size_t)nm1 * 32);
-  const size_t o_kv = o;    o = al256(o + (size_t)nm1 * 9);
-  const size_t o_kv2 = o;   o = al256(o + (size_t)nm1 * 9);
-  const size_t o_cxy = o;   o = al256(o + (size_t)nm1 * 8);
-  const size_t o_kxy = o;   o = al256(o + (size_t)cap * 8);
-  const size_t o_pairs = o; o = al256(o + (size_t)nm1 * 8);
-  const size_t o_frames = o;
-  const size_t o_emap = o;  o = al256(o + (size_t)ring * cap * 4);
-  const size_t o_eobs = o;  o = al256(o + (size_t)ring * cap * 8);
-  const size_t o_cnt = o;   o = al256(o + (size_t)ring * 4);
-  const size_t o_pose = o;  o = al256(o + (size_t)ring * 96);
-  const size_t o_flags = o; o = al256(o + 256);       // [0] BA skip flag, [8..] res_i (3), [16..] out_info (2 + 16)
-  const size_t o_res = o;   o = al256(o + 256);       // res_d (12 doubles)
-  const size_t o_stats = o; o = al256(o + 256);       // BA stats (16 doubles)
-  uint8_t *nd = nullptr;
-  MVO_CUDA(ctx, cudaMalloc(&nd, o));
-  MVO_CUDA(ctx, cudaMemsetAsync(nd, 0, o, ctx->stream));
-  if (keep_frames) {
-    const size_t old_frames = (uint8_t *)t->d_edge_map - t->dev;
-    MVO_CUDA(ctx, cudaMemcpyAsync(nd + o_frames, t->dev + old_frames, o_flags - o_frames, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (!ring_ok) {
+    size_t o = 0;
+    const size_t o_kxy = o;   o = al256(o + (size_t)cap * 8);
+    const size_t o_emap = o;  o = al256(o + (size_t)ring * cap * 4);
+    const size_t o_eobs = o;  o = al256(o + (size_t)ring * cap * 8);
+    const size_t o_ekp = o;   o = al256(o + (size_t)ring * cap * 4);
+    const size_t o_cnt = o;   o = al256(o + (size_t)ring * 4);
+    const size_t o_pose = o;  o = al256(o + (size_t)ring * 96);
+    const size_t o_flags = o; o = al256(o + 256);       // [0] BA skip flag, [8..] res_i (3), [16..] out_info (2 + 16)
+    const size_t o_res = o;   o = al256(o + 256);       // res_d (12 doubles)
+    const size_t o_stats = o; o = al256(o + 256);       // BA stats (16 doubles)
+    uint8_t *nd = nullptr;
+    MVO_CUDA(ctx, cudaMalloc(&nd, o));
+    MVO_CUDA(ctx, cudaMemsetAsync(nd, 0, o, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t->dev) cudaFree(t->dev);
+    for (TrackedFrame &f : t->frames) f.slot = -1;      // frames buffered under the old layout leave the device-side BA window
+    t->dev = nd; t->dev_cap = cap; t->dev_ring = ring;
+    t->d_kxy = (float *)(nd + o_kxy); t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs);
+    t->d_edge_kp = (int32_t *)(nd + o_ekp); t->d_cnt = (int32_t *)(nd + o_cnt); t->d_pose = (double *)(nd + o_pose);
+    t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res); t->d_stats = (double *)(nd + o_stats);
   }
-  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (t->dev) cudaFree(t->dev);
-  t->dev = nd; t->dev_bytes = o; t->dev_nmap = nmap; t->dev_cap = cap; t->dev_ring = ring;
-  ++t->map_version;                 // keys matched ahead of time lived in the old allocation
-  t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis[0] = nd + o_kv; t->d_keysvis[1] = nd + o_kv2;
-  t->d_cxy = (float *)(nd + o_cxy); t->d_kxy = (float *)(nd + o_kxy); t->d_pairs = (int32_t *)(nd + o_pairs);
-  t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs); t->d_cnt = (int32_t *)(nd + o_cnt);
-  t->d_pose = (double *)(nd + o_pose); t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res);
-  t->d_stats = (double *)(nd + o_stats);
-  const size_t hb = al256((size_t)nm1 * 9) + al256((size_t)nm1 * 8 + 64) + al256((size_t)ring * 96) + 1024;
-  if (hb > t->h_pin_bytes) {
-    if (t->h_pin) cudaFreeHost(t->h_pin);
-    t->h_pin = nullptr;
-    MVO_CUDA(ctx, cudaMallocHost(&t->h_pin, hb));
-    t->h_pin_bytes = hb;
+  if (!map_ok) {
+    int mcap = std::max(t->dev_mcap, 1024);
+    while (mcap < nmap) mcap *= 2;
+    size_t o = 0;
+    const size_t o_pts = o;   o = al256(o + (size_t)mcap * 12);
+    const size_t o_desc = o;  o = al256(o + (size_t)mcap * 32);
+    const size_t o_kv = o;    o = al256(o + (size_t)mcap * 9);
+    const size_t o_kv2 = o;   o = al256(o + (size_t)mcap * 9);
+    const size_t o_cxy = o;   o = al256(o + (size_t)mcap * 8);
+    const size_t o_pairs = o; o = al256(o + (size_t)mcap * 8);
+    const size_t o_ids = o;   o = al256(o + (size_t)mcap * 4);
+    const size_t o_vc = o;    o = al256(o + (size_t)mcap * 4);
+    const size_t o_mc = o;    o = al256(o + (size_t)mcap * 4);
+    uint8_t *nd = nullptr;
+    MVO_CUDA(ctx, cudaMalloc(&nd, o));
+    MVO_CUDA(ctx, cudaMemsetAsync(nd, 0, o, ctx->stream));
+    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t->dev_map) cudaFree(t->dev_map);
+    t->dev_map = nd; t->dev_mcap = mcap;
+    t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis[0] = nd + o_kv; t->d_keysvis[1] = nd + o_kv2;
+    t->d_cxy = (float *)(nd + o_cxy); t->d_pairs = (int32_t *)(nd + o_pairs); t->d_map_ids = (int32_t *)(nd + o_ids);
+    t->d_vis_cnt = (int32_t *)(nd + o_vc); t->d_match_cnt = (int32_t *)(nd + o_mc);
+    const size_t hb = al256((size_t)mcap * 9) + al256((size_t)mcap * 8 + 64) + al256((size_t)4096 * 96) + 1024;
+    if (hb > t->h_pin_bytes) {
+      if (t->h_pin) cudaFreeHost(t->h_pin);
+      t->h_pin = nullptr;
+      MVO_CUDA(ctx, cudaMallocHost(&t->h_pin, hb));
+      t->h_pin_bytes = hb;
+    }
   }
+  if (!ids_ok) {
+    int idcap = std::max(t->dev_idcap, 4096);
+    while (idcap < n_ids) idcap *= 2;
+    const size_t o_alive = al256((size_t)idcap * 12), tot = o_alive + al256((size_t)idcap);
+    uint8_t *nd = nullptr;
+    MVO_CUDA(ctx, cudaMalloc(&nd, tot));
+    if (t->dev_ids) cudaFree(t->dev_ids);
+    t->dev_ids = nd; t->dev_idcap = idcap;
+    t->d_pos_by_id = (float *)nd; t->d_alive = nd + o_alive;
+  }
+  ++t->map_version;                 // keys matched ahead of time were computed against the previous device copy
+  t->dev_nmap = nmap;
   if (nmap > 0) {
     MVO_CUDA(ctx, cudaMemcpyAsync(t->d_map_pts, t->map_pts.data(), (size_t)nmap * 12, cudaMemcpyHostToDevice, ctx->stream));
     MVO_CUDA(ctx, cudaMemcpyAsync(t->d_map_desc, t->map_desc.data(), (size_t)nmap * 32, cudaMemcpyHostToDevice, ctx->stream));
-    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_map_ids, t->map_ids.data(), (size_t)nmap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemsetAsync(t->d_vis_cnt, 0, (size_t)nmap * 4, ctx->stream));
+    MVO_CUDA(ctx, cudaMemsetAsync(t->d_match_cnt, 0, (size_t)nmap * 4, ctx->stream));
   }
+  if (n_ids > 0) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pos_by_id, t->pos_by_id.data(), (size_t)n_ids * 12, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_alive, t->alive.data(), (size_t)n_ids, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the extraction stream reads the map right away
   return MVO_OK;
 }
 
@@ -391,6 +441,7 @@ static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels,
   mvo_ctx *x = t->xctx[slot];
   MVO_TRY(mvo_set_params(x, &ctx->prm));          // follow parameter changes made on the main context
   j.image = image; j.channels = channels; j.stride = stride; j.on_device = image_on_device;
+  j.serial = t->n_submit_total + 1;
   j.want_host = !use_device_path(t);
   j.rc = MVO_OK; j.nk = 0; j.d_k = nullptr; j.d_d = nullptr;
   j.prematch = false; j.matched = false;
@@ -400,6 +451,7 @@ static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels,
     j.prematch = true;
     j.match_mode = t->prm.match_method == 1 ? 0 : 1;
     j.map_version = t->map_version;
+    j.d_map_desc = t->d_map_desc; j.nmap = t->dev_nmap; j.d_keys = (uint32_t *)t->d_keysvis[slot];
   }
   {
     std::lock_guard<std::mutex> lk(t->mu);
@@ -407,12 +459,13 @@ static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels,
   }
   t->cv_job.notify_one();
   ++t->n_submit;
+  ++t->n_submit_total;
   return MVO_OK;
 }
 
 // checkLargeMoveForAddKeyFrame_ (vo.cpp:247-265), translation part + bookkeeping shared by both paths
 static void finish_frame(mvo_tracker *t, bool pnp_ok, double *T_w_c_out) {
-  if (pnp_ok && trans_dist(t->frames.back().T_w_c, t->T_ref) > t->prm.min_dist_keyframe)
+  if (!t->external_ref && pnp_ok && trans_dist(t->frames.back().T_w_c, t->T_ref) > t->prm.min_dist_keyframe)
     memcpy(t->T_ref, t->frames.back().T_w_c, sizeof t->T_ref);
   memcpy(t->T_prev, t->frames.back().T_w_c, sizeof t->T_prev);
   t->has_prev = true;
@@ -485,7 +538,13 @@ void mvo_tracker_destroy(mvo_tracker *t) {
   }
   for (int k = 0; k < 2; ++k)
     if (t->xctx[k]) mvo_destroy(t->xctx[k]);
-  if (t->dev) { cudaSetDevice(t->ctx->device); cudaStreamSynchronize(t->ctx->stream); cudaFree(t->dev); }
+  if (t->dev || t->dev_map || t->dev_ids) {
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    if (t->dev) cudaFree(t->dev);
+    if (t->dev_map) cudaFree(t->dev_map);
+    if (t->dev_ids) cudaFree(t->dev_ids);
+  }
   if (t->h_pin) cudaFreeHost(t->h_pin);
   delete t;
 }
@@ -499,11 +558,10 @@ int mvo_tracker_set_map(mvo_tracker *t, const float *pts3d, const uint8_t *desc,
   if (!t) return MVO_ERR_INVALID_ARG;
   if (n < 0 || (n > 0 && (!pts3d || !desc))) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: null map");
   if (n > 65535) return mvo_fail(t->ctx, MVO_ERR_UNSUPPORTED, "tracker: more than 65535 map points");
-  t->map_pts.assign(pts3d, pts3d + (size_t)n * 3);
-  t->map_desc.assign(desc, desc + (size_t)n * 32);
-  t->dev_nmap = -1;                 // the device copy is refreshed by the next tracked frame
-  ++t->map_version;
-  return MVO_OK;
+  // point index = map point id: frames already buffered keep their links by id, links to ids >= n leave the BA graph
+  std::vector<int32_t> ids((size_t)n);
+  for (int i = 0; i < n; ++i) ids[(size_t)i] = i;
+  return mvo_trk_set_map_ids(t, pts3d, desc, ids.data(), n, 1);
 }
 
 int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref) {
@@ -552,30 +610,194 @@ int mvo_tracker_frame_pose(const mvo_tracker *t, int k, double *T_w_c) {
 int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device,
                       double *T_w_c_out, mvo_track_result *res) {
   if (!t) return MVO_ERR_INVALID_ARG;
+  if (!T_w_c_out) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
+  int slot = 0, nk = 0;
+  MVO_TRY(mvo_trk_acquire(t, image, channels, stride, image_on_device, &slot, &nk));
+  ExtractJob &job = t->job[slot];
+  const int rc = job.want_host ? track_host_arrays(t, job, T_w_c_out, res) : track_device(t, job, slot, T_w_c_out, res);
+  mvo_trk_release(t, slot);
+  return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Internal interface for the state machine (vo_pipeline.cpp, device-resident mode): mvo_vo keeps the reference's
+// containers on the host and drives this tracker as the owner of everything that lives on the GPU — the map arrays, the
+// frame ring mirroring frames_buff_, the per-point visibility / match counters.
+// ------------------------------------------------------------------------------------------------------------
+int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device, int *slot_out, int *nk_out) {
   mvo_ctx *ctx = t->ctx;
-  if (!image || !T_w_c_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
+  if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
   // take the frame from the prefetch queue, or extract it now
   if (t->n_submit != t->n_consume && t->job[t->n_consume & 1].image != image)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: frames must be tracked in the order they were prefetched");
   if (t->n_submit == t->n_consume) MVO_TRY(submit_extraction(t, image, channels, stride, image_on_device));
   const int slot = t->n_consume & 1;
   ExtractJob &job = t->job[slot];
-  const bool dev_path = !job.want_host;
-  if (dev_path) {
+  if (!job.want_host) {
     // the device copy of the map is refreshed while the extraction runs
     const int rc = dev_alloc(t);
     if (rc != MVO_OK) { wait_job(t, slot); job.state.store(0, std::memory_order_release); ++t->n_consume; return rc; }
   }
   wait_job(t, slot);
   ++t->n_consume;
-  int rc = job.rc;
-  if (rc != MVO_OK) rc = mvo_fail(ctx, rc, "tracker: %s", mvo_last_error(t->xctx[slot]));
-  else rc = dev_path ? track_device(t, job, slot, T_w_c_out, res) : track_host_arrays(t, job, T_w_c_out, res);
-  job.state.store(0, std::memory_order_release);
-  return rc;
+  if (job.rc != MVO_OK) {
+    const int rc = mvo_fail(ctx, job.rc, "tracker: %s", mvo_last_error(t->xctx[slot]));
+    job.state.store(0, std::memory_order_release);
+    return rc;
+  }
+  *slot_out = slot;
+  if (nk_out) *nk_out = job.nk;
+  return MVO_OK;
 }
 
-}  // extern "C"
+void mvo_trk_release(mvo_tracker *t, int slot) { t->job[slot].state.store(0, std::memory_order_release); }
+
+int mvo_trk_device_mode(const mvo_tracker *t) { return use_device_path(t) ? 1 : 0; }
+
+void mvo_trk_configure(mvo_tracker *t, int external_ref, int count_stats) {
+  t->external_ref = external_ref != 0;
+  t->count_stats = count_stats != 0;
+}
+
+// keypoints / descriptors of an acquired frame -> host (the device buffers stay valid until the slot is released)
+int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc) {
+  mvo_ctx *ctx = t->ctx;
+  ExtractJob &job = t->job[slot];
+  if (job.want_host) {
+    if (kpts && job.nk) memcpy(kpts, job.kpts.data(), (size_t)job.nk * sizeof(mvo_keypoint));
+    if (desc && job.nk) memcpy(desc, job.desc.data(), (size_t)job.nk * 32);
+    return MVO_OK;
+  }
+  if (job.nk <= 0) return MVO_OK;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (kpts) MVO_CUDA(ctx, cudaMemcpyAsync(kpts, job.d_k, (size_t)job.nk * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (desc) MVO_CUDA(ctx, cudaMemcpyAsync(desc, job.d_d, (size_t)job.nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MVO_OK;
+}
+
+const uint8_t *mvo_trk_desc_dev(mvo_tracker *t, int slot) { return t->job[slot].d_d; }
+unsigned mvo_trk_slot_serial(const mvo_tracker *t, int slot) { return t->job[slot].serial; }
+
+int mvo_trk_set_map_ids(mvo_tracker *t, const float *pts3d, const uint8_t *desc, const int32_t *ids, int n, int reset_ids) {
+  if (n < 0 || (n > 0 && (!pts3d || !desc || !ids))) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: null map");
+  if (n > 65535) return mvo_fail(t->ctx, MVO_ERR_UNSUPPORTED, "tracker: more than 65535 map points");
+  int max_id = -1;
+  for (int i = 0; i < n; ++i) {
+    if (ids[i] < 0) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: negative map point id");
+    max_id = std::max(max_id, ids[i]);
+  }
+  t->map_pts.assign(pts3d, pts3d + (size_t)n * 3);
+  t->map_desc.assign(desc, desc + (size_t)n * 32);
+  t->map_ids.assign(ids, ids + (size_t)n);
+  // ids are never reused (MapPoint::factory_id_): the by-id arrays only grow, except for the index-is-id maps of
+  // mvo_tracker_set_map, which restart at every call
+  const size_t n_ids = reset_ids ? (size_t)(max_id + 1) : std::max(t->alive.size(), (size_t)(max_id + 1));
+  t->alive.assign(n_ids, 0);
+  t->pos_by_id.resize(n_ids * 3, 0.f);
+  for (int i = 0; i < n; ++i) {
+    t->alive[(size_t)ids[i]] = 1;
+    memcpy(&t->pos_by_id[3 * (size_t)ids[i]], pts3d + 3 * (size_t)i, 12);
+  }
+  t->dev_nmap = -1;                 // the device copy is refreshed by the next frame
+  ++t->map_version;
+  return MVO_OK;
+}
+
+// pushFrameToBuff_ for a frame that does not go through the tracking step (BLANK / DOING_INITIALIZATION): pose + its
+// connections (map point id, keypoint index, pixel), so that the BA window sees the same frames_buff_ as the reference
+int mvo_trk_push_frame(mvo_tracker *t, const double *T_w_c, const int32_t *ids, const int32_t *kp_idx, const float *obs_xy, int n) {
+  mvo_ctx *ctx = t->ctx;
+  MVO_TRY(dev_alloc(t));
+  if (n > t->dev_cap) return mvo_fail(ctx, MVO_ERR_CAPACITY, "tracker: %d connections exceed the keypoint capacity %d", n, t->dev_cap);
+  t->frames.emplace_back();
+  if ((int)t->frames.size() > t->prm.buffer_size) t->frames.pop_front();
+  TrackedFrame &cur = t->frames.back();
+  cur.slot = (int)(t->frame_counter++ % (unsigned)t->dev_ring);
+  cur.n_links = n;
+  memcpy(cur.T_w_c, T_w_c, sizeof cur.T_w_c);
+  double P[12];
+  Twc_to_Rt12(T_w_c, P);
+  const size_t o = (size_t)cur.slot * t->dev_cap;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pose + (size_t)cur.slot * 12, P, sizeof P, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_cnt + cur.slot, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (n > 0) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_map + o, ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_kp + o, kp_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_obs + 2 * o, obs_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(t->T_prev, T_w_c, sizeof t->T_prev);
+  t->has_prev = true;
+  return MVO_OK;
+}
+
+// connections a keyframe gains from triangulation (pushCurrPointsToMap_, vo.cpp:528-576) appended to the k-th newest frame
+int mvo_trk_append_links(mvo_tracker *t, int k, const int32_t *ids, const int32_t *kp_idx, const float *obs_xy, int n) {
+  mvo_ctx *ctx = t->ctx;
+  if (k < 0 || k >= (int)t->frames.size()) return MVO_ERR_INVALID_ARG;
+  TrackedFrame &f = t->frames[t->frames.size() - 1 - (size_t)k];
+  if (n <= 0 || f.slot < 0) return MVO_OK;
+  if (f.n_links + n > t->dev_cap) return mvo_fail(ctx, MVO_ERR_CAPACITY, "tracker: %d connections exceed the keypoint capacity %d", f.n_links + n, t->dev_cap);
+  const size_t o = (size_t)f.slot * t->dev_cap + f.n_links;
+  const int total = f.n_links + n;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_map + o, ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_kp + o, kp_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_obs + 2 * o, obs_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_cnt + f.slot, &total, 4, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  f.n_links = total;
+  return MVO_OK;
+}
+
+// inliers_to_mappt_connections_ of the k-th newest frame: (map point id, keypoint index) in insertion order
+int mvo_trk_links(mvo_tracker *t, int k, int32_t *ids, int32_t *kp_idx, int cap, int *n) {
+  mvo_ctx *ctx = t->ctx;
+  if (k < 0 || k >= (int)t->frames.size() || !n) return MVO_ERR_INVALID_ARG;
+  const TrackedFrame &f = t->frames[t->frames.size() - 1 - (size_t)k];
+  *n = f.slot < 0 ? 0 : f.n_links;
+  if (*n > cap) return MVO_ERR_CAPACITY;
+  if (*n == 0) return MVO_OK;
+  const size_t o = (size_t)f.slot * t->dev_cap;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaMemcpyAsync(ids, t->d_edge_map + o, (size_t)*n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(kp_idx, t->d_edge_kp + o, (size_t)*n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MVO_OK;
+}
+
+// MapPoint::visible_times_ / matched_times_ increments since the last call (or map upload), per position in the map arrays
+int mvo_trk_counters(mvo_tracker *t, int32_t *visible, int32_t *matched, int n) {
+  mvo_ctx *ctx = t->ctx;
+  if (n <= 0) return MVO_OK;
+  if (t->dev_nmap < 0) {              // no frame has been tracked against this map yet
+    memset(visible, 0, (size_t)n * 4);
+    memset(matched, 0, (size_t)n * 4);
+    return MVO_OK;
+  }
+  if (n != t->dev_nmap) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: counters asked for %d points, the device map holds %d", n, t->dev_nmap);
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaMemcpyAsync(visible, t->d_vis_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemcpyAsync(matched, t->d_match_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaMemsetAsync(t->d_vis_cnt, 0, (size_t)n * 4, ctx->stream));
+  MVO_CUDA(ctx, cudaMemsetAsync(t->d_match_cnt, 0, (size_t)n * 4, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MVO_OK;
+}
+
+// the tracking step of an acquired frame with the caller's guess (reference keyframe) and previous-frame poses
+int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res) {
+  ExtractJob &job = t->job[slot];
+  if (job.want_host) return mvo_fail(t->ctx, MVO_ERR_UNSUPPORTED, "tracker: the frame was extracted for the host-array path");
+  memcpy(t->T_ref, T_guess, sizeof t->T_ref);
+  t->has_prev = T_prev != nullptr;
+  if (T_prev) memcpy(t->T_prev, T_prev, sizeof t->T_prev);
+  return track_device(t, job, slot, T_w_c_out, res);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // device-resident path
@@ -643,6 +865,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   // ---- everything after the matcher: thresholds + duplicate removal, PnP, frame-buffer update, BA ----
   // d_n != nullptr: the pair count lives on the device (n = its upper bound); otherwise n pairs are in d_pairs
   MvoPoseStore st;
+  bool counted = false;            // visible_times_ / matched_times_ are accumulated by the first tail only
   auto enqueue_tail = [&](int n, const int32_t *d_n, bool gathered) -> int {
     MvoTrackGlue g;
     memset(&g, 0, sizeof g);
@@ -654,8 +877,10 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
     if (t->has_prev) { g.prev_twc[0] = t->T_prev[3]; g.prev_twc[1] = t->T_prev[7]; g.prev_twc[2] = t->T_prev[11]; }
     Twc_to_Rt12(t->has_prev ? t->T_prev : cur.T_w_c, g.fallback);      // vo.cpp:376-379
     g.pairs = t->d_pairs; g.kpts = job.d_k;
-    g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.cnt = t->d_cnt; g.pose = t->d_pose;
+    g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.edge_kp = t->d_edge_kp; g.cnt = t->d_cnt; g.pose = t->d_pose;
     g.skip_flag = t->d_flags; g.res_i = d_res_i; g.res_d = t->d_res;
+    g.map_ids = t->d_map_ids; g.vis = d_vis; g.nmap = nmap;
+    if (t->count_stats && !counted && nmap > 0) { g.vis_cnt = t->d_vis_cnt; g.match_cnt = t->d_match_cnt; }
     int rc2 = MVO_OK;
     if (run_pnp) {
       float *d_p3, *d_p2;
@@ -679,7 +904,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
         e_upper += (b == total - 1) ? n : t->frames[b].n_links;
       }
       if (st.nslots > 0) {
-        st.map_pts = t->d_map_pts; st.edge_map = t->d_edge_map; st.edge_obs = (const float2 *)t->d_edge_obs; st.cnt = t->d_cnt;
+        st.map_pts = t->d_pos_by_id; st.alive = t->d_alive; st.n_ids = (int)t->alive.size(); st.edge_map = t->d_edge_map; st.edge_obs = (const float2 *)t->d_edge_obs; st.cnt = t->d_cnt;
         st.pose = t->d_pose; st.cap = cap; st.min_links = 3; st.skip_flag = t->d_flags; st.out_info = d_out_info;
         rc2 = mvo_ba_pose_store_launch(ctx, st, e_upper, t->K[0], t->K[0], t->K[2], t->K[5], t->prm.information, ctx->prm.ba_iterations,
                                        ctx->prm.ba_huber_delta > 0, ctx->prm.ba_huber_delta, t->prm.ba_step_tol, t->d_stats);
@@ -739,7 +964,8 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
     if (rc == MVO_OK) rc = enqueue_tail(n_upper, d_finfo, true);
     if (rc != MVO_OK) return fail(rc);
     TMARK(0);
-    if (h_flags[42] != 0) { fused = false; t->fused_holdoff = 64; }      // the device filter declined: redo the tail through the host
+    // the device filter declined: redo the tail through the host (its first pass saw zero pairs: only the in-view counts were taken)
+    if (h_flags[42] != 0) { fused = false; counted = true; t->fused_holdoff = 64; }
   }
   if (!fused) {
     rc = host_filter_tail();
@@ -920,11 +1146,14 @@ static int track_host_arrays(mvo_tracker *t, ExtractJob &job, double *T_w_c_out,
       const int fi = (int)which.size();
       which.push_back(b);
       poses.insert(poses.end(), f.T_w_c, f.T_w_c + 16);
-      ef.insert(ef.end(), f.map_idx.size(), fi);
-      ep.insert(ep.end(), f.map_idx.begin(), f.map_idx.end());
-      ob.insert(ob.end(), f.obs_xy.begin(), f.obs_xy.end());
+      for (size_t e = 0; e < f.map_idx.size(); ++e) {
+        if (f.map_idx[e] >= nmap) continue;                   // the point left the map with a later mvo_tracker_set_map (vo.cpp:438-440)
+        ef.push_back(fi);
+        ep.push_back(f.map_idx[e]);
+        ob.push_back(f.obs_xy[2 * e]); ob.push_back(f.obs_xy[2 * e + 1]);
+      }
     }
-    if (!which.empty()) {
+    if (!which.empty() && !ef.empty()) {
       // only the map points that appear in the graph become vertices (um_pts_3d_in_prev_frames)
       if ((int)t->ba_remap.size() != nmap) { t->ba_remap.assign(nmap, 0); t->ba_stamp.assign(nmap, 0); t->ba_gen = 0; }
       const int32_t gen = ++t->ba_gen;

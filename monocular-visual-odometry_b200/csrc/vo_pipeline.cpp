@@ -16,6 +16,18 @@
 //
 // Where the reference would abort (an OpenCV assertion below 5 matched points in findEssentialMat; an empty rvec after a
 // failed solvePnPRansac) the frame is skipped / the PnP is reported as failed instead.
+//
+// Two modes, selected by mvo_vo_params::track.device_resident:
+//   * device-resident (default; shipped configuration = fixed map points): the tracking branch (vo_addFrame.cpp:71-91) runs
+//     through the device-resident tracker (tracker.cpp): the map (in THIS file's container order, re-uploaded whenever a
+//     keyframe changes it), the frame buffer and the BA graph stay in HBM, a tracked frame costs one host synchronisation,
+//     and MapPoint::visible_times_ / matched_times_ are accumulated on the device and read back when optimizeMap_ needs
+//     them.  Keypoints, descriptors and connections of a tracked frame are only copied to the host when the frame becomes
+//     a keyframe (or the caller asks for them).  Initialisation and keyframe insertion run through the host-array entry
+//     points as below: they happen once per sequence / per keyframe.
+//   * host arrays (device_resident = 0, and always with free map points): every stage through its public entry point,
+//     four host round trips per tracked frame, as a maintainer who only swaps the bodies of the reference functions gets it.
+// Both give the same states, counts and keyframes; poses agree to the summation order of the BA (tests/test_vo_pipeline_gpu.py).
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -42,7 +54,11 @@ struct VoFrame {                                                 // vo::Frame (f
   std::vector<float> inliers_pts3d;                              // 3 per point, in this camera's frame
   std::vector<double> triangulation_angles;
   std::unordered_map<int, PtConn> conn;                          // inliers_to_mappt_connections_
-  int n() const { return (int)kpts.size(); }
+  // device-resident mode: keypoints / descriptors / connections of a tracked frame stay on the GPU until somebody needs them
+  bool host_ready = true, conn_ready = true;
+  int nk = 0, slot = -1;
+  unsigned serial = 0;
+  int n() const { return host_ready ? (int)kpts.size() : nk; }
 };
 typedef std::shared_ptr<VoFrame> FramePtr;
 
@@ -118,6 +134,17 @@ struct mvo_vo {
   std::vector<int32_t> inl, keep, cand_id, ba_ef, ba_ep, ba_used;
   std::vector<double> angles, ba_poses;
   std::vector<mvo_dmatch> matches;
+  // device-resident mode
+  mvo_tracker *trk = nullptr;
+  bool dev = false;
+  std::vector<int32_t> dev_order;                                // map point ids in the order of the last upload (container order)
+  const uint8_t *cur_image = nullptr;                            // the frame being added (host pointer, or device pointer + scratch copy)
+  int cur_channels = 0, cur_on_device = 0;
+  size_t cur_stride = 0;
+  std::vector<uint8_t> img_scratch;
+  std::vector<int32_t> new_ids, new_kp, cnt_vis, cnt_match;
+  std::vector<float> new_obs, up_pts;
+  std::vector<uint8_t> up_desc;
 };
 
 namespace {
@@ -134,26 +161,124 @@ int match_into(mvo_vo *v, const uint8_t *d1, const float *xy1, int n1, const VoF
   return MVO_OK;
 }
 
-// Frame::calcKeyPoints + calcDescriptors (frame.h:73-86)
-int extract(mvo_vo *v, VoFrame *f, const uint8_t *image, int channels, size_t stride) {
-  const int cap = v->ctx->prm.max_keypoints + 8;
-  f->kpts.resize((size_t)cap);
-  f->desc.resize((size_t)cap * 32);
-  int n = cap;
-  MVO_TRY(mvo_orb_extract(v->ctx, image, v->rows, v->cols, channels, stride, f->kpts.data(), &n, f->desc.data()));
-  f->kpts.resize((size_t)n);
-  f->desc.resize((size_t)n * 32);
-  f->xy.resize((size_t)n * 2);
+// pixel colours of Frame::calcDescriptors (frame.h:80-84) from a HOST image
+void sample_colors(VoFrame *f, const uint8_t *image, int channels, size_t stride) {
+  const int n = (int)f->kpts.size();
   f->colors.resize((size_t)n * 3);
   for (int i = 0; i < n; ++i) {
-    f->xy[2 * i] = f->kpts[i].x;
-    f->xy[2 * i + 1] = f->kpts[i].y;
-    const int x = (int)floorf(f->kpts[i].x), y = (int)floorf(f->kpts[i].y);       // frame.h:80-84
+    const int x = (int)floorf(f->kpts[i].x), y = (int)floorf(f->kpts[i].y);
     const uint8_t *px = image + (size_t)y * stride + (size_t)x * channels;
     if (channels == 3) { f->colors[3 * i] = px[2]; f->colors[3 * i + 1] = px[1]; f->colors[3 * i + 2] = px[0]; }   // getPixelAt: {r, g, b}
     else { f->colors[3 * i] = f->colors[3 * i + 1] = f->colors[3 * i + 2] = px[0]; }
   }
+}
+
+// the image of the frame being added as a host pointer (an image handed over in device memory is copied once, on demand)
+int host_image(mvo_vo *v, const uint8_t **img, size_t *stride) {
+  if (!v->cur_on_device) { *img = v->cur_image; *stride = v->cur_stride; return MVO_OK; }
+  const size_t row = (size_t)v->cols * v->cur_channels;
+  if (v->img_scratch.size() != row * v->rows) {
+    v->img_scratch.resize(row * v->rows);
+    MVO_CUDA(v->ctx, cudaMemcpy2D(v->img_scratch.data(), row, v->cur_image, v->cur_stride, row, v->rows, cudaMemcpyDeviceToHost));
+  }
+  *img = v->img_scratch.data();
+  *stride = row;
   return MVO_OK;
+}
+
+// Frame::calcKeyPoints + calcDescriptors (frame.h:73-86), host-array mode
+int extract(mvo_vo *v, VoFrame *f, const uint8_t *image, int channels, size_t stride, int on_device) {
+  const int cap = v->ctx->prm.max_keypoints + 8;
+  f->kpts.resize((size_t)cap);
+  f->desc.resize((size_t)cap * 32);
+  int n = cap;
+  MVO_TRY(mvo_orb_extract_ex(v->ctx, image, v->rows, v->cols, channels, stride, on_device, f->kpts.data(), &n, f->desc.data()));
+  f->kpts.resize((size_t)n);
+  f->desc.resize((size_t)n * 32);
+  f->xy.resize((size_t)n * 2);
+  for (int i = 0; i < n; ++i) { f->xy[2 * i] = f->kpts[i].x; f->xy[2 * i + 1] = f->kpts[i].y; }
+  const uint8_t *himg;
+  size_t hstride;
+  MVO_TRY(host_image(v, &himg, &hstride));
+  sample_colors(f, himg, channels, hstride);
+  return MVO_OK;
+}
+
+// device-resident mode: keypoints / descriptors of a frame whose extraction slot still holds it -> host
+int ensure_host(mvo_vo *v, VoFrame *f) {
+  if (f->host_ready) return MVO_OK;
+  if (f->slot < 0 || mvo_trk_slot_serial(v->trk, f->slot) != f->serial)
+    return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: frame %d has left the device (its keypoints are kept for two frames unless it is a keyframe)", f->id);
+  f->kpts.resize((size_t)f->nk);
+  f->desc.resize((size_t)f->nk * 32);
+  MVO_TRY(mvo_trk_fetch(v->trk, f->slot, f->kpts.data(), f->desc.data()));
+  f->xy.resize((size_t)f->nk * 2);
+  for (int i = 0; i < f->nk; ++i) { f->xy[2 * i] = f->kpts[i].x; f->xy[2 * i + 1] = f->kpts[i].y; }
+  if (f == v->curr.get() && v->cur_image) {
+    const uint8_t *himg;
+    size_t hstride;
+    MVO_TRY(host_image(v, &himg, &hstride));
+    sample_colors(f, himg, v->cur_channels, hstride);
+  } else {
+    f->colors.assign((size_t)f->nk * 3, 0);
+  }
+  f->host_ready = true;
+  return MVO_OK;
+}
+
+// device-resident mode: inliers_to_mappt_connections_ of the k-th newest buffered frame -> host (insertion order = PnP inlier
+// order, the order the host-array mode inserts them in, so the container order is the same)
+int ensure_conn(mvo_vo *v, VoFrame *f, int k) {
+  if (f->conn_ready) return MVO_OK;
+  const int cap = v->ctx->prm.max_keypoints + 8;
+  std::vector<int32_t> ids((size_t)cap), kp((size_t)cap);
+  int n = 0;
+  MVO_TRY(mvo_trk_links(v->trk, k, ids.data(), kp.data(), cap, &n));
+  for (int i = 0; i < n; ++i) f->conn[kp[(size_t)i]] = PtConn{-1, ids[(size_t)i]};
+  f->conn_ready = true;
+  return MVO_OK;
+}
+
+// device-resident mode: the map in container order -> tracker (positions, descriptors, ids)
+int upload_map(mvo_vo *v) {
+  const size_t n = v->map_points.size();
+  v->up_pts.resize(n * 3 + 3); v->up_desc.resize(n * 32 + 32); v->dev_order.resize(n);
+  size_t k = 0;
+  for (auto &kv : v->map_points) {
+    const VoMapPoint &mp = kv.second;
+    memcpy(&v->up_pts[3 * k], mp.pos, 12);
+    memcpy(&v->up_desc[32 * k], mp.desc, 32);
+    v->dev_order[k] = mp.id;
+    ++k;
+  }
+  return mvo_trk_set_map_ids(v->trk, v->up_pts.data(), v->up_desc.data(), v->dev_order.data(), (int)n, 0);
+}
+
+// device-resident mode: fold the visible / matched increments the tracker accumulated since the last upload into the map
+int pull_counters(mvo_vo *v) {
+  const int n = (int)v->dev_order.size();
+  if (n == 0) return MVO_OK;
+  v->cnt_vis.resize((size_t)n); v->cnt_match.resize((size_t)n);
+  MVO_TRY(mvo_trk_counters(v->trk, v->cnt_vis.data(), v->cnt_match.data(), n));
+  for (int k = 0; k < n; ++k) {
+    auto it = v->map_points.find(v->dev_order[(size_t)k]);
+    if (it == v->map_points.end()) continue;
+    it->second.visible_times += v->cnt_vis[(size_t)k];
+    it->second.matched_times += v->cnt_match[(size_t)k];
+  }
+  return MVO_OK;
+}
+
+// device-resident mode: a frame that did not go through the tracking step enters the tracker's frame buffer
+int push_frame_to_tracker(mvo_vo *v, const VoFrame &f) {
+  std::vector<int32_t> ids, kp;
+  std::vector<float> obs;
+  for (auto &kc : f.conn) {
+    ids.push_back(kc.second.pt_map_idx);
+    kp.push_back(kc.first);
+    obs.push_back(f.xy[2 * (size_t)kc.first]); obs.push_back(f.xy[2 * (size_t)kc.first + 1]);
+  }
+  return mvo_trk_push_frame(v->trk, f.T_w_c, ids.data(), kp.data(), obs.data(), (int)ids.size());
 }
 
 void add_keyframe(mvo_vo *v, const FramePtr &f) {                // addKeyFrame_ (vo.cpp:482-486), Map::insertKeyFrame
@@ -274,7 +399,11 @@ void push_curr_points_to_map(mvo_vo *v) {
       map_point_id = mp.id;
       v->map_points[mp.id] = mp;                                 // Map::insertMapPoint
     }
-    c.conn.insert({pt_idx, PtConn{dm.query_idx, map_point_id}});
+    if (c.conn.insert({pt_idx, PtConn{dm.query_idx, map_point_id}}).second && v->dev) {
+      v->new_ids.push_back(map_point_id);
+      v->new_kp.push_back(pt_idx);
+      v->new_obs.push_back(c.xy[2 * (size_t)pt_idx]); v->new_obs.push_back(c.xy[2 * (size_t)pt_idx + 1]);
+    }
   }
 }
 
@@ -425,6 +554,10 @@ int call_bundle_adjustment(mvo_vo *v, mvo_vo_frame_info *info) {
 int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   VoFrame &c = *v->curr;
   const VoFrame &r = *v->ref;
+  if (v->dev) {                                                  // the frame's keypoints and connections come to the host now
+    MVO_TRY(ensure_host(v, &c));
+    MVO_TRY(ensure_conn(v, &c, 0));
+  }
   MVO_TRY(match_into(v, r.desc.data(), r.xy.data(), r.n(), c, v->prm.track.match_method, v->prm.max_match_dist_triangulation, &c.matches_with_ref));
   const int n = (int)c.matches_with_ref.size();
   info->kf_matches = n;
@@ -465,8 +598,14 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   for (int i = 0; i < ni; ++i) trans_coord(&v->pts3d[3 * (size_t)i], R, t, &c.inliers_pts3d[3 * (size_t)i]);
   MVO_TRY(retain_good_triangulation(v));
   info->kf_new_points = (int)c.inliers_matches_for_3d.size();
+  v->new_ids.clear(); v->new_kp.clear(); v->new_obs.clear();
   push_curr_points_to_map(v);
+  if (v->dev) MVO_TRY(pull_counters(v));                         // visible_times_ / matched_times_ as of this frame
   optimize_map(v);
+  if (v->dev) {
+    MVO_TRY(upload_map(v));
+    MVO_TRY(mvo_trk_append_links(v->trk, 0, v->new_ids.data(), v->new_kp.data(), v->new_obs.data(), (int)v->new_ids.size()));
+  }
   add_keyframe(v, v->curr);
   info->keyframe = 1;
   return MVO_OK;
@@ -507,13 +646,73 @@ int mvo_vo_create(mvo_ctx *ctx, const double *K, int rows, int cols, const mvo_v
   v->prm = p;
   memcpy(v->K, K, sizeof v->K);
   v->rows = rows; v->cols = cols;
+  if (p.track.device_resident) {
+    const int rc = mvo_tracker_create(ctx, K, rows, cols, &p.track, &v->trk);
+    if (rc != MVO_OK) { delete v; return rc; }
+    v->dev = mvo_trk_device_mode(v->trk) != 0;                   // fixed map points and a BA window the cluster kernel holds
+    if (v->dev) mvo_trk_configure(v->trk, 1, 1);
+    else { mvo_tracker_destroy(v->trk); v->trk = nullptr; }
+  }
   *out = v;
   return MVO_OK;
 }
 
-void mvo_vo_destroy(mvo_vo *v) { delete v; }
+void mvo_vo_destroy(mvo_vo *v) {
+  if (!v) return;
+  if (v->trk) mvo_tracker_destroy(v->trk);
+  delete v;
+}
+
+int mvo_vo_device_resident(const mvo_vo *v) { return v && v->dev ? 1 : 0; }
+
+int mvo_vo_reset(mvo_vo *v) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  v->state = VO_BLANK;
+  std::unordered_map<int, VoMapPoint>().swap(v->map_points);     // fresh containers: the iteration order depends on the bucket history
+  std::unordered_map<int, FramePtr>().swap(v->keyframes);
+  v->buff.clear();
+  v->curr.reset(); v->prev.reset(); v->ref.reset(); v->prev_ref.reset();
+  v->frame_factory_id = v->point_factory_id = 0;
+  v->map_point_erase_ratio = 0.1;
+  v->dev_order.clear();
+  if (v->trk) {
+    double I[16];
+    set_identity(I);
+    MVO_TRY(mvo_tracker_reset(v->trk, I));
+    MVO_TRY(mvo_trk_set_map_ids(v->trk, nullptr, nullptr, nullptr, 0, 1));
+  }
+  return MVO_OK;
+}
+
+int mvo_vo_prefetch(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  if (!image || (channels != 1 && channels != 3) || stride < (size_t)v->cols * channels)
+    return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: bad image arguments");
+  if (!v->dev) return MVO_OK;                                    // host-array mode extracts inside add_frame
+  return mvo_tracker_prefetch(v->trk, image, channels, stride, image_on_device);
+}
+
+uint64_t mvo_vo_kernel_launches(const mvo_vo *v) {
+  if (!v) return 0;
+  return v->trk ? mvo_tracker_kernel_launches(v->trk) : mvo_kernel_launches(v->ctx);
+}
+
+int mvo_vo_timing_enable(mvo_vo *v, uint32_t mask) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  return v->trk ? mvo_tracker_timing_enable(v->trk, mask) : mvo_timing_enable(v->ctx, mask);
+}
+
+int mvo_vo_timing_read(mvo_vo *v, double *ms, uint64_t *counts) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  return v->trk ? mvo_tracker_timing_read(v->trk, ms, counts) : mvo_timing_read(v->ctx, ms, counts);
+}
 
 int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t stride, double *T_w_c_out, mvo_vo_frame_info *info_out) {
+  return mvo_vo_add_frame_ex(v, image, channels, stride, 0, T_w_c_out, info_out);
+}
+
+int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device, double *T_w_c_out,
+                        mvo_vo_frame_info *info_out) {
   if (!v) return MVO_ERR_INVALID_ARG;
   if (!image || (channels != 1 && channels != 3) || stride < (size_t)v->cols * channels)
     return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: bad image arguments");
@@ -523,7 +722,19 @@ int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t strid
   FramePtr frame = std::make_shared<VoFrame>();
   frame->id = v->frame_factory_id;
   set_identity(frame->T_w_c);
-  MVO_TRY(extract(v, frame.get(), image, channels, stride));     // before any state changes: an extraction error leaves the VO untouched
+  v->cur_image = image; v->cur_channels = channels; v->cur_stride = stride; v->cur_on_device = image_on_device;
+  v->img_scratch.clear();
+  // Frame::calcKeyPoints + calcDescriptors, before any state changes: an extraction error leaves the VO untouched
+  int slot = -1;
+  if (v->dev) {
+    MVO_TRY(mvo_trk_acquire(v->trk, image, channels, stride, image_on_device, &slot, &frame->nk));
+    frame->host_ready = false;
+    frame->slot = slot;
+    frame->serial = mvo_trk_slot_serial(v->trk, slot);
+  } else {
+    MVO_TRY(extract(v, frame.get(), image, channels, stride, image_on_device));
+  }
+  struct Release { mvo_vo *v; int slot; ~Release() { if (slot >= 0) mvo_trk_release(v->trk, slot); v->cur_image = nullptr; } } release{v, slot};
   v->frame_factory_id++;
   v->buff.push_back(frame);                                      // pushFrameToBuff_ (vo.h:81-86)
   if ((int)v->buff.size() > v->prm.track.buffer_size) v->buff.pop_front();
@@ -534,24 +745,54 @@ int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t strid
   v->prev_ref = v->ref;
   int rc = MVO_OK;
   if (v->state == VO_BLANK) {                                    // vo_addFrame.cpp:29-34
-    v->state = VO_DOING_INITIALIZATION;
-    add_keyframe(v, frame);
-    info.keyframe = 1;
+    if (v->dev) rc = ensure_host(v, frame.get());
+    if (rc == MVO_OK) {
+      v->state = VO_DOING_INITIALIZATION;
+      add_keyframe(v, frame);
+      info.keyframe = 1;
+      if (v->dev) rc = push_frame_to_tracker(v, *frame);
+    }
   } else if (v->state == VO_DOING_INITIALIZATION) {              // :35-69
     const VoFrame &r = *v->ref;
-    rc = match_into(v, r.desc.data(), r.xy.data(), r.n(), *frame, v->prm.match_method_init, v->prm.max_match_dist_init, &frame->matches_with_ref);
+    if (v->dev) rc = ensure_host(v, frame.get());
+    if (rc == MVO_OK)
+      rc = match_into(v, r.desc.data(), r.xy.data(), r.n(), *frame, v->prm.match_method_init, v->prm.max_match_dist_init, &frame->matches_with_ref);
     int usable = 0, good = 0;
     if (rc == MVO_OK) { info.n_matches = (int)frame->matches_with_ref.size(); rc = estimate_motion_and_3d_points(v, &info, &usable); }
     if (rc == MVO_OK && usable) rc = is_vo_good_to_init(v, &info, &good);
     if (rc == MVO_OK && good) {
+      v->new_ids.clear(); v->new_kp.clear(); v->new_obs.clear();
       push_curr_points_to_map(v);
       add_keyframe(v, frame);
       v->state = VO_DOING_TRACKING;
       info.keyframe = 1;
+      if (v->dev) rc = upload_map(v);
     } else {
       memcpy(frame->T_w_c, v->ref->T_w_c, sizeof frame->T_w_c);  // :64-68
     }
-  } else if (v->state == VO_DOING_TRACKING) {                    // :70-125
+    if (rc == MVO_OK && v->dev) rc = push_frame_to_tracker(v, *frame);
+  } else if (v->state == VO_DOING_TRACKING && v->dev) {          // :70-125 through the device-resident tracker
+    frame->conn_ready = false;
+    mvo_track_result r;
+    rc = mvo_trk_track(v->trk, slot, v->ref->T_w_c, v->prev->T_w_c, frame->T_w_c, &r);
+    if (rc != MVO_OK) {                                          // the tracker has dropped the frame again: so do we
+      v->buff.pop_back();
+      v->curr = v->prev;
+      v->frame_factory_id--;
+      return rc;
+    }
+    info.n_candidates = r.n_candidates; info.n_matches = r.n_matches; info.n_inliers = r.n_inliers; info.pnp_ok = r.pnp_ok;
+    info.ba_frames = r.ba_frames; info.ba_edges = r.ba_edges;
+    memcpy(info.T_w_c_pnp, r.T_w_c_pnp, sizeof info.T_w_c_pnp);
+    // bundle adjustment has moved the newest frames of the buffer (g2o_ba.cpp:298-305 writes the poses back in place)
+    const int total = (int)v->buff.size(), nba = r.ba_frames > 0 ? std::min(v->prm.track.ba_window, total - 1) : 0;
+    for (int k = 1; k < nba && rc == MVO_OK; ++k) rc = mvo_tracker_frame_pose(v->trk, k, v->buff[(size_t)(total - 1 - k)]->T_w_c);
+    if (rc == MVO_OK && r.pnp_ok) {
+      int large = 0;
+      rc = mvo_check_large_move(frame->T_w_c, v->ref->T_w_c, v->prm.track.min_dist_keyframe, &large, nullptr, nullptr);
+      if (rc == MVO_OK && large) rc = insert_keyframe(v, &info);
+    }
+  } else if (v->state == VO_DOING_TRACKING) {                    // :70-125, host arrays
     memcpy(frame->T_w_c, v->ref->T_w_c, sizeof frame->T_w_c);
     bool pnp_good = false;
     rc = pose_estimation_pnp(v, &info, &pnp_good);
@@ -598,6 +839,19 @@ int mvo_vo_frame_data(const mvo_vo *v, int which, int what, void *out, int cap, 
   if (which == -1) f = v->prev_ref.get();                        // VisualOdometry::getPrevRef
   else if (which >= 0 && which < (int)v->buff.size()) f = v->buff[v->buff.size() - 1 - (size_t)which].get();
   if (!f) return MVO_ERR_INVALID_ARG;
+  if (v->dev && (!f->host_ready || !f->conn_ready) && what != MVO_VO_FRAME_ID && which >= 0) {
+    // device-resident mode: a tracked frame's keypoints / descriptors / PnP inliers are brought over on request
+    mvo_vo *mv = const_cast<mvo_vo *>(v);
+    VoFrame *mf = const_cast<VoFrame *>(f);
+    if (what == MVO_VO_KEYPOINTS || what == MVO_VO_DESCRIPTORS) MVO_TRY(ensure_host(mv, mf));
+    if (what == MVO_VO_MATCHES_WITH_MAP && mf->matches_with_map.empty()) {
+      MVO_TRY(ensure_conn(mv, mf, which));
+      // the PnP inliers (vo.cpp:333-354) as (map point id, keypoint index): the candidate-list index and the descriptor
+      // distance of the reference's DMatch are not kept in this mode
+      for (auto &kc : mf->conn)
+        if (kc.second.pt_ref_idx < 0) mf->matches_with_map.push_back(mvo_dmatch{kc.second.pt_map_idx, kc.first, 0, 0.f});
+    }
+  }
   const void *src = nullptr;
   size_t count = 0, elem = 0;
   switch (what) {

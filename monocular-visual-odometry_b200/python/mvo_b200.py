@@ -147,6 +147,13 @@ SIGNATURES = {
     "mvo_vo_is_initialized": (_i, [_vp]),
     "mvo_vo_map_size": (_i, [_vp]),
     "mvo_vo_num_keyframes": (_i, [_vp]),
+    "mvo_vo_add_frame_ex": (_i, [_vp, _vp, _i, _sz, _i, _vp, C.POINTER(VoFrameInfo)]),
+    "mvo_vo_prefetch": (_i, [_vp, _vp, _i, _sz, _i]),
+    "mvo_vo_device_resident": (_i, [_vp]),
+    "mvo_vo_reset": (_i, [_vp]),
+    "mvo_vo_kernel_launches": (C.c_uint64, [_vp]),
+    "mvo_vo_timing_enable": (_i, [_vp, C.c_uint32]),
+    "mvo_vo_timing_read": (_i, [_vp, _vp, _vp]),
     "mvo_vo_get_map": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _pi]),
     "mvo_vo_frame_pose": (_i, [_vp, _i, _vp]),
     "mvo_vo_frame_data": (_i, [_vp, _i, _i, _vp, _i, _pi]),
@@ -465,12 +472,45 @@ class VisualOdometry:
         except Exception:
             pass
 
-    def add_frame(self, image):
-        img = np.ascontiguousarray(image, np.uint8)
+    def _image_args(self, image, channels, stride, on_device):
+        if on_device:
+            return C.c_void_p(int(image)), int(channels), int(stride)
+        img = image if (isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.flags.c_contiguous) else np.ascontiguousarray(image, np.uint8)
         channels = 1 if img.ndim == 2 else img.shape[2]
+        self._keep = (getattr(self, "_keep", []) + [img])[-4:]      # a prefetched image must stay alive until its add_frame returns
+        return _ptr(img), channels, img.shape[1] * channels
+
+    def add_frame(self, image, channels=None, stride=None, on_device=False):
+        """image: HxW(x3) uint8 array, or a device pointer (int) with channels / stride when on_device."""
+        p, ch, st = self._image_args(image, channels, stride, on_device)
         T, info = np.zeros(16), VoFrameInfo()
-        self.ctx._chk(self.lib.mvo_vo_add_frame(self.h, _ptr(img), channels, img.shape[1] * channels, _ptr(T), C.byref(info)))
+        self.ctx._chk(self.lib.mvo_vo_add_frame_ex(self.h, p, ch, st, 1 if on_device else 0, _ptr(T), C.byref(info)))
         return T.reshape(4, 4), info
+
+    def prefetch(self, image, channels=None, stride=None, on_device=False):
+        """Hand the NEXT frame over (same array object / pointer as the later add_frame call)."""
+        p, ch, st = self._image_args(image, channels, stride, on_device)
+        self.ctx._chk(self.lib.mvo_vo_prefetch(self.h, p, ch, st, 1 if on_device else 0))
+
+    @property
+    def device_resident(self):
+        return bool(self.lib.mvo_vo_device_resident(self.h))
+
+    def reset(self):
+        self.ctx._chk(self.lib.mvo_vo_reset(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.mvo_vo_kernel_launches(self.h))
+
+    def timing_enable(self, mask: int):
+        self.ctx._chk(self.lib.mvo_vo_timing_enable(self.h, int(mask)))
+
+    def timing_read(self):
+        n = self.lib.mvo_kernel_classes()
+        ms, cnt = np.zeros(n, np.float64), np.zeros(n, np.uint64)
+        self.ctx._chk(self.lib.mvo_vo_timing_read(self.h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
 
     def is_initialized(self):
         return bool(self.lib.mvo_vo_is_initialized(self.h))

@@ -261,3 +261,38 @@ def room_loop_sequence(seed=0, n_frames=150, K=K_DEFAULT, **kw):
     planes = _room_planes(seed)
     poses = room_loop_poses(seed, n_frames, **kw)
     return [render_room(T, planes, K) for T in poses], poses
+
+
+def trajectory_error(T_est, T_true):
+    """RMS position error (absolute trajectory error) after the best similarity alignment (Umeyama) of the estimated camera
+    centres to the true ones — a monocular trajectory has a free scale.  Returns (rms, scale)."""
+    a = np.stack([np.asarray(T)[:3, 3] for T in T_est])
+    b = np.stack([np.asarray(T)[:3, 3] for T in T_true])
+    ma, mb = a.mean(0), b.mean(0)
+    A, B = a - ma, b - mb
+    U, S, Vt = np.linalg.svd(B.T @ A / len(a))
+    D = np.diag([1, 1, np.sign(np.linalg.det(U @ Vt))])
+    R = U @ D @ Vt
+    s = np.trace(np.diag(S) @ D) / max((A * A).sum(), 1e-300) * len(a)
+    aligned = (s * (R @ A.T)).T + mb
+    return float(np.sqrt(((aligned - b) ** 2).sum(1).mean())), float(s)
+
+
+def cached_room_loop_sequence(seed=0, n_frames=150, cache_dir="/tmp"):
+    """room_loop_sequence with an on-disk cache (rendering 150 frames takes ~30 s of one core)."""
+    import os
+    path = os.path.join(cache_dir, f"mvo_room_loop_s{seed}_n{n_frames}.npz")
+    if os.path.exists(path):
+        try:
+            d = np.load(path)
+            return list(d["frames"]), list(d["truth"])
+        except Exception:
+            pass
+    frames, truth = room_loop_sequence(seed, n_frames)
+    try:
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, frames=np.stack(frames), truth=np.stack(truth))
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return frames, truth

@@ -83,6 +83,68 @@ def test_vo_pipeline_reference_configuration(built):
     _run(1)
 
 
+MODES_CHILD = r'''
+import sys
+import numpy as np
+sys.path.insert(0, r"{root}"); sys.path.insert(0, r"{root}/monocular-visual-odometry_b200/python")
+import mvo_b200, mvo_synth
+K = mvo_synth.K_DEFAULT
+n = 40
+frames, truth = mvo_synth.room_loop_sequence(0, n)
+imgs = [mvo_synth.gray_to_bgr(f) for f in frames]
+ctxA = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
+ctxB = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
+voA = mvo_b200.VisualOdometry(ctxA, K, 480, 640)                                        # device-resident (default)
+voB = mvo_b200.VisualOdometry(ctxB, K, 480, 640, track=dict(device_resident=0))         # host arrays
+assert voA.device_resident and not voB.device_resident
+FIELDS = ["state_out", "keyframe", "n_keypoints", "n_matches", "n_candidates", "n_inliers", "pnp_ok", "ba_frames", "ba_edges", "map_points",
+          "kf_matches", "kf_new_points", "best_sol"]
+def run(vo, prefetch):
+    out = []
+    if prefetch: vo.prefetch(imgs[0])
+    for i, img in enumerate(imgs):
+        if prefetch and i + 1 < n: vo.prefetch(imgs[i + 1])
+        T, info = vo.add_frame(img)
+        out.append((T, [getattr(info, f) for f in FIELDS]))
+    return out
+ra, rb = run(voA, True), run(voB, False)
+for i, ((Ta, fa), (Tb, fb)) in enumerate(zip(ra, rb)):
+    assert fa == fb, (i, fa, fb)                                       # same states, keyframes, candidate / match / inlier / edge counts
+    assert np.abs(Ta - Tb).max() < 1e-6, (i, np.abs(Ta - Tb).max())    # poses: only the BA's summation order differs
+assert sum(f[1] for _, f in ra) >= 4 and ra[-1][1][0] == 2            # it did initialise and insert keyframes
+ia, pa, da, ca = voA.get_map(); ib, pb, db, cb = voB.get_map()
+assert np.array_equal(ia, ib) and np.array_equal(da, db) and np.array_equal(ca, cb)     # same map, same container order
+assert np.abs(pa - pb).max() < 1e-5
+for k in range(6):
+    assert np.abs(voA.frame_pose(k) - voB.frame_pose(k)).max() < 1e-6
+# frame data on request: keypoints / descriptors of the newest frame come over from the device
+assert np.array_equal(voA.frame_data("keypoints"), voB.frame_data("keypoints")) and np.array_equal(voA.frame_data("descriptors"), voB.frame_data("descriptors"))
+ma, mb = voA.frame_data("matches_with_map"), voB.frame_data("matches_with_map")
+assert len(ma) == len(mb) and sorted(ma["train_idx"].tolist()) == sorted(mb["train_idx"].tolist())
+# a second pass after reset reproduces the first one exactly (fresh containers, ids restart), also with images in device memory
+import torch
+voA.reset()
+d = [torch.from_numpy(im).cuda() for im in imgs]
+torch.cuda.synchronize()
+voA.prefetch(d[0].data_ptr(), channels=3, stride=1920, on_device=True)
+for i in range(n):
+    if i + 1 < n: voA.prefetch(d[i + 1].data_ptr(), channels=3, stride=1920, on_device=True)
+    T, info = voA.add_frame(d[i].data_ptr(), channels=3, stride=1920, on_device=True)
+    assert [getattr(info, f) for f in FIELDS] == ra[i][1], i
+    assert np.array_equal(T, ra[i][0]), (i, np.abs(T - ra[i][0]).max())
+i2, p2, d2, c2 = voA.get_map()
+assert np.array_equal(i2, ia) and np.array_equal(p2, pa) and np.array_equal(c2, ca)
+print("vo modes child ok")
+'''
+
+
+def test_device_resident_state_machine_equals_the_host_array_one(built):
+    """mvo_vo over the device-resident tracker (map, frame buffer, BA graph and the visible / matched counters in HBM; one host
+    synchronisation per tracked frame) against the same state machine through the host-array entry points."""
+    r = subprocess.run([sys.executable, "-c", MODES_CHILD.format(root=str(ROOT))], capture_output=True, text=True, timeout=400 * _TIMEOUT_SCALE)
+    assert r.returncode == 0 and "vo modes child ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
 ADAPTER_CHILD = r'''
 import subprocess, sys
 import numpy as np

@@ -13,7 +13,7 @@ CONFIGS = [{}, {"MVO_BLUR2": "1"}, {"MVO_DESCRIBE2": "1"}, {"MVO_BLUR2": "1", "M
 
 def child():
     sys.path.insert(0, str(ROOT))
-    import bench  # noqa: F401  (sys.path for the package)
+    sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python"))
     import mvo_b200
     import mvo_synth
     import torch

@@ -2,8 +2,9 @@
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python")); sys.path.insert(0, str(ROOT))
-import numpy as np, torch, mvo_b200, mvo_synth, bench
+sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python")); sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
+import numpy as np, torch, mvo_b200, mvo_synth
+import tracker_workload as bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 ctx = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
 imgs, T_true, order = bench.build_sequence(0)

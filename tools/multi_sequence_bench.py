@@ -14,7 +14,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-import bench  # noqa: E402  (puts the package on sys.path)
+sys.path.insert(0, str(ROOT / "tools"))
+import tracker_workload as bench  # noqa: E402  (puts the package on sys.path)
 import mvo_b200  # noqa: E402
 import mvo_synth  # noqa: E402
 import torch  # noqa: E402
