@@ -37,3 +37,70 @@ def test_projection_and_rodrigues_vs_cv2():
     R, _ = cv2.Rodrigues(g["rvec"])
     assert np.abs(R - po.rodrigues(g["rvec"])).max() < 1e-12
     assert np.abs(po.rvec_from_R(R) - g["rvec"]).max() < 1e-12
+
+
+# ---- cv::solvePnPRansac's control flow restated (oracle/pnp_cv_oracle.py), pinned to cv2 live and to the golden vector ----
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_cv_ransac_restatement_is_inlier_index_exact(seed):
+    """Same sampler (cv::RNG((uint64)-1), 5 distinct indices per iteration), same minimal solver (EPnP on 5 points), same float
+    scoring and adaptive iteration count, same final refit: identical inlier index list and pose as cv2.solvePnPRansac with
+    the reference's arguments (vo.cpp:314-320) — with cv2.SVDecomp standing for cv::SVD inside EPnP."""
+    import cv2
+    import mvo_synth
+    from oracle import pnp_cv_oracle as pc
+    P, uv, _, _, _ = mvo_synth.pnp_problem(seed, n=2000)
+    K = mvo_synth.K_DEFAULT
+    ok, r, t, inl = cv2.solvePnPRansac(P, uv, K, None, iterationsCount=100, reprojectionError=2.0, confidence=0.999)
+    ok2, r2, t2, inl2, trace = pc.solve_pnp_ransac_cv(P, uv, K)
+    assert ok and ok2 and np.array_equal(inl.ravel(), inl2)
+    assert np.abs(r.ravel() - r2).max() < 1e-9 and np.abs(t.ravel() - t2).max() < 1e-9
+    assert len(trace) < 100                                   # the 0.999 confidence rule ended the loop early
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+def test_cv_ransac_restatement_reproduces_the_golden_vector():
+    from oracle import pnp_cv_oracle as pc
+    g = np.load(GOLDEN / "pnp_config3.npz")
+    ok, r, t, inl, _ = pc.solve_pnp_ransac_cv(g["P"], g["uv"], g["K"])
+    assert ok and np.array_equal(inl, g["inliers"].ravel())
+    assert np.abs(r - g["rvec"]).max() < 1e-9 and np.abs(t - g["tvec"]).max() < 1e-9
+
+
+def test_cv_rng_and_subsets_are_the_published_generator():
+    from oracle import pnp_cv_oracle as pc
+    rng = pc.CvRng()
+    # multiply-with-carry, coefficient 4164903690, seed (uint64)-1: first outputs computed by hand from the recurrence
+    s = 0xFFFFFFFFFFFFFFFF
+    outs = []
+    for _ in range(4):
+        s = ((s & 0xFFFFFFFF) * 4164903690 + (s >> 32)) & 0xFFFFFFFFFFFFFFFF
+        outs.append(s & 0xFFFFFFFF)
+    assert [rng.next() for _ in range(4)] == outs
+    sub = pc.get_subset(pc.CvRng(), 2000, 5)
+    assert len(set(sub)) == 5 and all(0 <= i < 2000 for i in sub)
+    assert pc.ransac_update_num_iters(0.999, 0.3, 5, 100) == 38 and pc.ransac_update_num_iters(0.999, 0.0, 5, 100) == 0
+    assert pc.ransac_update_num_iters(0.999, 0.9, 5, 100) == 100
+
+
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+def test_cv_ransac_minimal_solver_is_decided_by_rounding_noise():
+    """The documented limit of any independent re-implementation: EPnP on 5 points takes two null vectors of a rank-10 12 x 12
+    matrix from cv::SVD; on samples that contain an outlier (most samples at 30 % outliers) the pose depends on WHICH basis of
+    that plane the Jacobi sweeps leave, which rounding noise decides — the same algorithm restated (pc.jacobi_svd) gives
+    different poses there, while all-inlier samples (the ones that win the RANSAC) agree to ~1e-6."""
+    import mvo_synth
+    from oracle import pnp_cv_oracle as pc
+    P, uv, _, _, _ = mvo_synth.pnp_problem(0, n=2000)
+    K = mvo_synth.K_DEFAULT
+    rng = pc.CvRng()
+    good, bad = [], []
+    for _ in range(40):
+        sub = pc.get_subset(rng, 2000, 5)
+        Pd, us = P[sub].astype(np.float64), pc.epnp_pixels(P[sub], uv[sub], K)
+        R1, t1, e1, _ = pc.epnp(Pd, us, K[0, 0], K[1, 1], K[0, 2], K[1, 2], svd=pc.cv_svd)
+        R2, t2, _, _ = pc.epnp(Pd, us, K[0, 0], K[1, 1], K[0, 2], K[1, 2], svd=pc.jacobi_svd)
+        d = max(np.abs(R1 - R2).max(), np.abs(t1 - t2).max())
+        (good if min(e1) < 2.0 else bad).append(d)
+    assert len(good) >= 2 and max(good) < 1e-4               # all-inlier samples: the minimal model is well defined
+    assert len(bad) >= 20 and np.median(bad) > 1e-3          # contaminated samples: the model is an artefact of the SVD's rounding
