@@ -95,7 +95,11 @@ typedef struct mvo_params {
                                  poses agree with the full run to within the bound (tests/test_ba_gpu.py) */
   /* two-view geometry — src/geometry/epipolar_geometry.cpp:17-57 */
   int32_t epi_hypotheses;     /* batched essential-matrix hypotheses (reference: adaptive RANSAC, prob 0.999); default 4096 */
-  int32_t pad_;
+  int32_t pnp_mode;           /* 0 (default): pnp_hypotheses batched P3P hypotheses, all scored; 1: cv::solvePnPRansac's own flow as
+                                 the reference calls it (vo.cpp:314-320) — cv::RNG sampler, 5-point EPnP minimal models, <= 100
+                                 adaptive iterations at confidence 0.999, float scoring (csrc/pnp_cv_kernels.cuh; CPU restatement
+                                 pinned inlier-index-exact to cv2: oracle/pnp_cv_oracle.py).  Its result agrees with OpenCV's up to
+                                 correspondences within ~1e-3 px of the threshold (the minimal solver's SVD noise, see the oracle) */
   double eh_ratio_threshold;  /* mvo_estimate_relative_poses takes the homography branch when H/(E+H) exceeds this: 0.5
                                  (motion_estimation.cpp:140; the reference's README.md:57 documents 0.45).  The locally
                                  optimised essential matrix keeps more inliers than OpenCV's un-refined five-point model, so

@@ -99,6 +99,7 @@ void mvo_default_params(mvo_params *p) {
   p->xiang_gao_ratio = 2.0;      // :84
   p->lowe_ratio = 1.0;           // :85 (0.8 read through Config::get<int>, feature_match.cpp:138)
   p->pnp_hypotheses = 4096;
+  p->pnp_mode = 0;
   p->pnp_reproj_error = 2.0f;    // src/vo/vo.cpp:316
   p->pnp_seed = 0x9E3779B97F4A7C15ull;
   p->pnp_refine_iters = 20;
@@ -118,6 +119,7 @@ static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "bad keypoint selection parameters");
   if (p->orb_fast_threshold < 1 || p->orb_fast_threshold > 254)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "orb_fast_threshold outside [1,254]");
+  if (p->pnp_mode != 0 && p->pnp_mode != 1) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_mode must be 0 or 1");
   if (p->pnp_hypotheses < 1 || p->pnp_hypotheses > 65535)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_hypotheses outside [1,65535]");
   if (p->epi_hypotheses < 1 || p->epi_hypotheses > 65535)

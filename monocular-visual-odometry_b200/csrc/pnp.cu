@@ -51,6 +51,7 @@ static void rvec_to_rotation(const double *w, double *R) {
   R[6] = -A * wy + B * wx * wz;       R[7] = A * wx + B * wy * wz;        R[8] = 1 - B * (wx * wx + wy * wy);
 }
 
+static int pnp_hyp_count(const mvo_ctx *ctx);
 struct PnpWs { float *p3, *p2; double *poses, *pose_io, *ex, *eo, *stats; int32_t *valid, *counts, *out_i, *inl, *ef; };
 
 // ba.cu
@@ -96,7 +97,28 @@ static int pnp_refit(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam) {
 
 // hypotheses -> scores -> consensus set of the best hypothesis -> least-squares refit, all on ctx->stream;
 // w.p3 / w.p2 hold the n correspondences on the device
+static int pnp_hyp_count(const mvo_ctx *ctx) { return ctx->prm.pnp_mode == 1 ? 100 : ctx->prm.pnp_hypotheses; }   // vo.cpp:315: iterationsCount = 100
+
+// pnp_mode = 1: cv::solvePnPRansac's own flow (pnp_cv_kernels.cuh) — 100 EPnP iterations evaluated in parallel, the adaptive loop replayed
+static int pnp_enqueue_cv(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, const int32_t *n_dev) {
+  const int H = pnp_hyp_count(ctx);
+  const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
+  { KTimer kt(ctx, KC_PNP_HYP);
+  k_pnp_epnp<<<(H + CVP_WARPS - 1) / CVP_WARPS, CVP_WARPS * 32, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, H, w.poses, w.valid); }
+  MVO_CHECK_LAUNCH(ctx);
+  { KTimer kt(ctx, KC_PNP_SCORE);
+  k_pnp_score_cv<<<(H + 7) / 8, 256, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, (float)thr2, H, w.poses, w.valid, w.counts); }
+  MVO_CHECK_LAUNCH(ctx);
+  { KTimer kt(ctx, KC_PNP_FINISH);
+  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.counts, 2, ctx->prm.pnp_refine_iters,
+                                             w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
+  MVO_CHECK_LAUNCH(ctx);
+  ctx->pnp_last_h = H;
+  return pnp_refit(ctx, w, n, cam);
+}
+
 static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, const int32_t *n_dev = nullptr) {
+  if (ctx->prm.pnp_mode == 1) return pnp_enqueue_cv(ctx, w, n, cam, n_dev);
   const int H = ctx->prm.pnp_hypotheses;
   const size_t smem = (size_t)n * 5 * sizeof(float);
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
@@ -126,7 +148,7 @@ static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, c
 // (< 4: no model), inl = its ascending indices.
 int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **pose_io, int32_t **out_i, int32_t **inl) {
   PnpWs w;
-  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  MVO_TRY(pnp_ws(ctx, n, pnp_hyp_count(ctx), &w));
   *p3 = w.p3; *p2 = w.p2; *pose_io = w.pose_io; *out_i = w.out_i; *inl = w.inl;
   return MVO_OK;
 }
@@ -137,7 +159,7 @@ int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K, const int32_t *d_n) {
   PnpCam cam;
   MVO_TRY(pnp_cam(ctx, K, &cam));
   PnpWs w;
-  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  MVO_TRY(pnp_ws(ctx, n, pnp_hyp_count(ctx), &w));
   return pnp_enqueue(ctx, w, n, cam, d_n);
 }
 
@@ -152,7 +174,7 @@ int mvo_solve_pnp_ransac(mvo_ctx *ctx, const float *pts3d, const float *pts2d, i
   PnpCam cam;
   MVO_TRY(pnp_cam(ctx, K, &cam));
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int H = ctx->prm.pnp_hypotheses;
+  const int H = pnp_hyp_count(ctx);
   PnpWs w;
   MVO_TRY(pnp_ws(ctx, n, H, &w));
   if ((size_t)n * 20 > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
@@ -205,7 +227,7 @@ int mvo_pnp_refine(mvo_ctx *ctx, const float *pts3d, const float *pts2d, int n, 
   MVO_TRY(pnp_cam(ctx, K, &cam));
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   PnpWs w;
-  MVO_TRY(pnp_ws(ctx, n, ctx->prm.pnp_hypotheses, &w));
+  MVO_TRY(pnp_ws(ctx, n, pnp_hyp_count(ctx), &w));
   MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, (size_t)n * 20 + 1024));
   float *h3 = (float *)ctx->h_b.p, *h2 = h3 + (size_t)n * 3;
   double *h_pose = (double *)((uint8_t *)ctx->h_b.p + (size_t)n * 20);

@@ -320,9 +320,13 @@ k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, c
 
 constexpr int FIN_T = 1024;
 
+#include "pnp_cv_kernels.cuh"   // mvo_params::pnp_mode = 1 (cv::solvePnPRansac's flow)
+
+
 // out: [0..8] R, [9..11] t, then int32 n_inliers at out_i[0], best hypothesis at out_i[1],
 // inlier indices in inl[] and the one-frame edge list (ex, eo, ef) for the pose-only LM refit.
-// mode 0: arg-max + consensus set; mode 1: every point is an inlier, pose_io holds the start pose.
+// mode 0: arg-max + consensus set; mode 1: every point is an inlier, pose_io holds the start pose; mode 2: cv::solvePnPRansac's
+// flow (pnp_cv_kernels.cuh): the model RANSACPointSetRegistrator::run ends with + its consensus set under the float rule.
 __global__ void __launch_bounds__(FIN_T)
 k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev, PnpCam cam,
              double thr2, int H, const double *__restrict__ poses, const int32_t *__restrict__ counts, int mode, int max_iters,
@@ -335,7 +339,9 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
   const int n_upper = n;                 // the refit is launched for this many edge slots
   if (n_dev) n = min(n, *n_dev);
   int n_in = 0;
-  if (mode == 0) {
+  const bool cv_rule = mode == 2;
+  const float thr2f = (float)thr2;
+  if (mode == 0 || mode == 2) {
     // this thread's chunk of points: loaded first so that the L2 round trip overlaps the arg-max
     constexpr int MAXPER = 4;             // n <= 4096 on the register path; beyond that the points are re-read
     const int per = (n + FIN_T - 1) / FIN_T, b0 = tid * per, e0 = min(b0 + per, n);
@@ -349,7 +355,7 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
     }
     // arg-max of the inlier count, ties -> lowest hypothesis index
     long long best = -1;
-    for (int h = tid; h < H; h += FIN_T) {
+    for (int h = tid; h < (cv_rule ? 0 : H); h += FIN_T) {
       const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
       best = key > best ? key : best;
     }
@@ -363,6 +369,7 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
       for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
       const int cnt = (int)(b >> 20);
       s_best = cnt >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
+      if (cv_rule) { int iters_run = 0; s_best = cvp_replay(counts, H, n, 0.999, &iters_run); out_i[3] = iters_run; }
     }
     __syncthreads();
     if (s_best < 0) {
@@ -384,11 +391,13 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
 #pragma unroll
       for (int k = 0; k < MAXPER; ++k) {
         const int i = b0 + k;
-        if (i < e0 && reproj_err2(P, cam, v3(px[k][0], px[k][1], px[k][2]), px[k][3], px[k][4]) <= thr2) { flags |= 1u << k; ++mine; }
+        if (i < e0 && (cv_rule ? cvp_is_inlier(P, cam, v3(px[k][0], px[k][1], px[k][2]), px[k][3], px[k][4], thr2f)
+                               : reproj_err2(P, cam, v3(px[k][0], px[k][1], px[k][2]), px[k][3], px[k][4]) <= thr2)) { flags |= 1u << k; ++mine; }
       }
     } else {
       for (int i = b0; i < e0; ++i)
-        mine += reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2;
+        mine += cv_rule ? cvp_is_inlier(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1], thr2f)
+                        : reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2;
     }
     int incl = mine;
 #pragma unroll
@@ -410,7 +419,8 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
         }
     } else {
       for (int i = b0; i < e0; ++i)
-        if (reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2) {
+        if (cv_rule ? cvp_is_inlier(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1], thr2f)
+                    : reproj_err2(P, cam, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), p2[2 * i], p2[2 * i + 1]) <= thr2) {
           inl[off] = i;
           ex[3 * off] = p3[3 * i]; ex[3 * off + 1] = p3[3 * i + 1]; ex[3 * off + 2] = p3[3 * i + 2];
           eo[2 * off] = p2[2 * i]; eo[2 * off + 1] = p2[2 * i + 1];
@@ -433,6 +443,6 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
   for (int j = n_in + tid; j < n_upper; j += FIN_T) ef[j] = -1;       // masked out of the refit
   const int it = 0;
   if (tid < 12) pose_io[tid] = s_pose[tid];
-  if (tid == 0) { out_i[0] = n_in; out_i[1] = mode == 0 ? s_best : -1; out_i[2] = it; }
+  if (tid == 0) { out_i[0] = n_in; out_i[1] = mode != 1 ? s_best : -1; out_i[2] = it; }
 }
 

@@ -113,3 +113,52 @@ def test_edge_cases(ctx):
     uvp = (pc[:, :2] / pc[:, 2:3] * 615 + np.array([320, 240])).astype(np.float32)
     rvec, tvec, inl = ctx.solve_pnp_ransac(Pp, uvp, K)
     assert len(inl) >= 295 and np.abs(rvec - [0.2, -0.1, 0.05]).max() < 1e-3 and np.abs(tvec - [0.1, 0, 4.0]).max() < 5e-3
+
+
+# ---- mvo_params::pnp_mode = 1: cv::solvePnPRansac's own flow on the device (csrc/pnp_cv_kernels.cuh) ----
+@pytest.mark.skipif(not have_cv2(), reason="cv2 not importable")
+def test_cv_flow_equals_cv2_solve_pnp_ransac(ctx):
+    """Same sampler, same minimal solver, same float scoring, same adaptive stop as cv::solvePnPRansac(P, uv, K, noArray(), rvec, t,
+    false, 100, 2.0, 0.999, inliers) (vo.cpp:314-320): the consensus sets are equal up to correspondences within ~1e-3 px of
+    the threshold (oracle/pnp_cv_oracle.py explains why no independent implementation can promise more), the pose to 1e-5."""
+    import cv2
+    from oracle import pnp_cv_oracle as pc
+    ctx.set_params(pnp_mode=1)
+    try:
+        cases = [mvo_synth.pnp_problem(s, n=2000)[:2] for s in range(5)]
+        g = np.load(GOLDEN / "pnp_config3.npz")
+        cases.append((g["P"], g["uv"]))
+        identical = 0
+        for P, uv in cases:
+            ok, rc, tc, ic = cv2.solvePnPRansac(P, uv, K, None, None, None, False, 100, 2.0, 0.999)
+            rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, K)
+            a, b = set(inl.tolist()), set(ic.ravel().tolist())
+            assert len(a & b) / len(a | b) >= 0.999, (len(a), len(b), len(a & b))
+            assert np.abs(rvec - rc.ravel()).max() < 1e-5 and np.abs(tvec - tc.ravel()).max() < 1e-5
+            identical += int(np.array_equal(inl, ic.ravel()))
+            # the iterations the adaptive rule let through: the same count as the CPU restatement's
+            poses, counts = ctx.pnp_last_hypotheses()
+            assert len(counts) == 100
+            _, _, _, inl_o, trace = pc.solve_pnp_ransac_cv(P, uv, K)
+            assert np.array_equal(inl_o, ic.ravel())                   # the oracle itself is index-exact (cv2.SVDecomp inside)
+            good = [(i, t[1]) for i, t in enumerate(trace) if i == 0 or t[1] != trace[i - 1][1]]      # iterations that improved the best model
+            # their inlier counts come out the same on the device wherever the winning models are all-inlier samples
+            assert counts[good[-1][0]] == good[-1][1] or abs(int(counts[good[-1][0]]) - good[-1][1]) <= 2
+        print("identical inlier lists:", identical, "of", len(cases))
+        assert identical >= len(cases) - 2
+    finally:
+        ctx.set_params(pnp_mode=0)
+
+
+def test_cv_flow_small_and_degenerate_inputs(ctx):
+    import mvo_b200
+    ctx.set_params(pnp_mode=1)
+    try:
+        P, uv, rt, tt, _ = mvo_synth.pnp_problem(8, n=40, outlier_frac=0.1)
+        rvec, tvec, inl = ctx.solve_pnp_ransac(P, uv, K)
+        assert len(inl) >= 30 and np.abs(rvec - rt).max() < 2e-2 and np.abs(tvec - tt).max() < 1e-1
+        with pytest.raises(mvo_b200.MvoError) as e:
+            ctx.solve_pnp_ransac(P[:5], uv[:5], K)                     # fewer than 6 correspondences: no RANSAC model
+        assert e.value.code == -6
+    finally:
+        ctx.set_params(pnp_mode=0)

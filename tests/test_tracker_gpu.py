@@ -241,3 +241,39 @@ def test_large_map_and_map_swap_device_vs_host_arrays(ctx):
         assert ia[4] == 1 and ia[1] > 2001 and ia[5] == min(k, 5)      # the oldest buffered frame stays out of the window (vo.cpp:417-419)
         assert np.abs(Ta - Tb).max() < 1e-8
     ctx.set_params(max_keypoints=1500, ba_iterations=50)
+
+
+def test_cv_flow_tracker_reproduces_the_cpu_trajectory(ctx):
+    """north_star: 'trajectory ATE within 1e-4 of the reference'.  With mvo_params::pnp_mode = 1 (cv::solvePnPRansac's own flow
+    on the device) every stage of the tracking step has the reference's arithmetic: the tracked trajectory equals the CPU
+    path's (cv2 + the BA restatement) frame by frame, and the two ATEs agree within 1e-4."""
+    import mvo_b200
+    from oracle import vo_oracle
+    ctx.set_params(max_keypoints=2000, ba_iterations=10, pnp_mode=1)
+    try:
+        imgs, T_true = _make_sequence(0, 12)
+        pts, desc = _map_from_frame0(ctx, imgs[0])
+        trk = mvo_b200.Tracker(ctx, K, 480, 640, ba_step_tol=0.0)
+        trk.set_map(pts, desc)
+        trk.reset(np.eye(4))
+        cpu = vo_oracle.CpuTracker(K, 480, 640, max_keypoints=2000, ba_iterations=10)
+        cpu.set_map(pts, desc)
+        cpu.reset(np.eye(4))
+        err_g, err_c, worst, same = [], [], 0.0, 0
+        for i in range(1, 12):
+            Tg, r = trk.track(imgs[i])
+            Tc, info = cpu.track(imgs[i])
+            assert (r.n_keypoints, r.n_candidates, r.n_matches) == (info["n_keypoints"], info["n_candidates"], info["n_matches"])
+            assert r.pnp_ok == info["pnp_ok"] == 1 and r.ba_frames == info["ba_frames"]
+            assert abs(r.n_inliers - info["n_inliers"]) <= 3, (i, r.n_inliers, info["n_inliers"])
+            same += int(r.n_inliers == info["n_inliers"])
+            worst = max(worst, np.abs(Tg - Tc).max())
+            err_g.append(np.linalg.norm(Tg[:3, 3] - T_true[i][:3, 3]))
+            err_c.append(np.linalg.norm(Tc[:3, 3] - T_true[i][:3, 3]))
+        ate_g, ate_c = np.sqrt(np.mean(np.square(err_g))), np.sqrt(np.mean(np.square(err_c)))
+        print(f"cv flow: ATE gpu {ate_g:.6f} cpu {ate_c:.6f}, largest pose difference {worst:.2e}, equal consensus-set sizes on {same} of 11 frames")
+        assert abs(ate_g - ate_c) <= 1e-4, (ate_g, ate_c)
+        assert worst < 1e-4
+        trk.close()
+    finally:
+        ctx.set_params(max_keypoints=1500, ba_iterations=50, pnp_mode=0)
