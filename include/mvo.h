@@ -105,6 +105,9 @@ typedef struct mvo_params {
                                  optimised essential matrix keeps more inliers than OpenCV's un-refined five-point model, so
                                  the ratio sits ~0.03 lower here: exactly planar scenes come out at 0.485-0.492 (OpenCV
                                  0.50-0.52) and fall on the E side of 0.5 */
+  double essential_threshold; /* mvo_estimate_relative_poses: cv::findEssentialMat threshold in pixels (config findEssentialMat_threshold = 1.0,
+                                 epipolar_geometry.cpp:29-36) */
+  double homography_threshold;/* mvo_estimate_relative_poses: cv::findHomography ransacReprojThreshold = 3 (epipolar_geometry.cpp:101) */
 } mvo_params;
 
 typedef struct mvo_ctx mvo_ctx;
@@ -430,8 +433,7 @@ typedef struct mvo_vo_params {
   int32_t init_calc_homography;        /* is_calc_homo = true (vo.cpp:68) */
   int32_t min_inlier_matches;          /* 15 */
   int32_t pad;
-  double essential_threshold;          /* findEssentialMat_threshold = 1.0 (keyframe branch; the initialisation goes
-                                          through mvo_estimate_relative_poses, which uses 1.0) */
+  double essential_threshold;          /* findEssentialMat_threshold = 1.0 (initialisation and keyframe branch) */
   double min_triang_angle;             /* 1.0 */
   double max_ratio_angle_to_median;    /* max_ratio_between_max_angle_and_median_angle = 20 */
   double min_pixel_dist;               /* 50 */
@@ -457,7 +459,8 @@ int mvo_vo_create(mvo_ctx *ctx, const double *K /* 3x3 */, int rows, int cols, c
                   mvo_vo **out);
 void mvo_vo_destroy(mvo_vo *v);
 /* addFrame: image rows x cols x channels (3 = BGR, 1 = gray) in host memory.  T_w_c_out = the frame's pose when the
- * call returns (run_vo.cpp:137 records exactly this), info optional. */
+ * call returns (run_vo.cpp:137 records exactly this), info optional.  When the call fails the frame is not kept: the
+ * frame buffer (mvo_vo_frame_pose / mvo_vo_frame_data) only holds frames whose call returned MVO_OK. */
 int mvo_vo_add_frame(mvo_vo *v, const uint8_t *image, int channels, size_t stride, double *T_w_c_out, mvo_vo_frame_info *info);
 /* The same with the image optionally already in device memory (image_on_device != 0). */
 int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device, double *T_w_c_out,

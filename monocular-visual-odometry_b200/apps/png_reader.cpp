@@ -54,7 +54,7 @@ bool read_png_bgr(const std::string &path, std::vector<uint8_t> *bgr, int *rows,
     pos += 12 + (size_t)len;
   }
   if (!seen_iend || ctype < 0) return fail(err, path + ": missing IHDR / IEND");
-  if (w == 0 || h == 0 || w > 32768 || h > 32768) return fail(err, path + ": unsupported image size");
+  if (w == 0 || h == 0 || w > 32768 || h > 32768 || (uint64_t)w * h > (64ull << 20)) return fail(err, path + ": unsupported image size");   // <= 64 Mpixel
   if (interlace) return fail(err, path + ": interlaced PNG is not supported");
   if (!((depth == 8 || depth == 16) && (ctype == 0 || ctype == 2 || ctype == 4 || ctype == 6)) && !(ctype == 3 && depth == 8))
     return fail(err, path + ": unsupported colour type / bit depth");

@@ -60,6 +60,7 @@ int main(int argc, char **argv) {
     std::vector<double> history;
     std::vector<uint8_t> bgr;
     const int n = std::min(max_frames, num_images);
+    int rows0 = 0, cols0 = 0;
     for (int img_id = 0; img_id < n; ++img_id) {
       char path[2048];
       chk(mvo_image_path(dataset_dir.c_str(), "/rgb_%05d.png", img_id, path, sizeof path), ctx, "image path");
@@ -69,7 +70,9 @@ int main(int argc, char **argv) {
         printf("The image file %s is empty. Finished. (%s)\n", path, err.c_str());
         break;
       }
-      if (!vo) chk(mvo_vo_create(ctx, K, rows, cols, &vp, &vo), ctx, "mvo_vo_create");
+      if (!vo) { chk(mvo_vo_create(ctx, K, rows, cols, &vp, &vo), ctx, "mvo_vo_create"); rows0 = rows; cols0 = cols; }
+      if (rows != rows0 || cols != cols0)
+        throw Fail{std::string(path) + ": " + std::to_string(cols) + "x" + std::to_string(rows) + " differs from the first frame's " + std::to_string(cols0) + "x" + std::to_string(rows0)};
       double T[16];
       mvo_vo_frame_info info;
       chk(mvo_vo_add_frame(vo, bgr.data(), 3, (size_t)cols * 3, T, &info), ctx, "addFrame");
@@ -81,6 +84,9 @@ int main(int argc, char **argv) {
     printf("Wrote %d poses to %s\n", (int)(history.size() / 16), traj_file.c_str());
   } catch (const Fail &f) {
     fprintf(stderr, "run_vo: %s\n", f.msg.c_str());
+    status = 1;
+  } catch (const std::exception &e) {                            // e.g. std::bad_alloc from a huge image
+    fprintf(stderr, "run_vo: %s\n", e.what());
     status = 1;
   }
   mvo_vo_destroy(vo);

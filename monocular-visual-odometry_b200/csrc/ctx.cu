@@ -59,7 +59,7 @@ KTimer::~KTimer() {
 
 static const char *kKernelNames[KC_COUNT] = {"k_gray", "k_resize", "k_fast", "k_select", "k_blur", "k_describe",
                                               "k_harris_all", "match_kernel", "k_pnp_hypotheses", "k_pnp_score",
-                                              "k_pnp_finish", "k_ba", "k_track_glue", "k_epi"};
+                                              "k_pnp_finish", "k_ba", "k_track_glue", "k_epi", "k_epi_score", "k_epi_finish"};
 
 extern "C" {
 
@@ -100,6 +100,8 @@ void mvo_default_params(mvo_params *p) {
   p->lowe_ratio = 1.0;           // :85 (0.8 read through Config::get<int>, feature_match.cpp:138)
   p->pnp_hypotheses = 4096;
   p->pnp_mode = 0;
+  p->essential_threshold = 1.0;
+  p->homography_threshold = 3.0;
   p->pnp_reproj_error = 2.0f;    // src/vo/vo.cpp:316
   p->pnp_seed = 0x9E3779B97F4A7C15ull;
   p->pnp_refine_iters = 20;
@@ -119,6 +121,7 @@ static int validate_params(mvo_ctx *ctx, const mvo_params *p) {
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "bad keypoint selection parameters");
   if (p->orb_fast_threshold < 1 || p->orb_fast_threshold > 254)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "orb_fast_threshold outside [1,254]");
+  if (!(p->essential_threshold > 0) || !(p->homography_threshold > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "two-view thresholds must be positive");
   if (p->pnp_mode != 0 && p->pnp_mode != 1) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_mode must be 0 or 1");
   if (p->pnp_hypotheses < 1 || p->pnp_hypotheses > 65535)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "pnp_hypotheses outside [1,65535]");

@@ -117,10 +117,10 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_epi_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (H + 7) / 8;
   if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
-  { KTimer kt(ctx, KC_EPI);
+  { KTimer kt(ctx, KC_EPI_SCORE);
   k_epi_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dvalid, dcnt); }
   MVO_CHECK_LAUNCH(ctx);
-  { KTimer kt(ctx, KC_EPI);
+  { KTimer kt(ctx, KC_EPI_FINISH);
   k_epi_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dcnt, dout, dout_i, dinl); }
   MVO_CHECK_LAUNCH(ctx);
   double *h_out = (double *)(h + al((size_t)n * 16));
@@ -190,10 +190,10 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_homo_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (H + 7) / 8;
   if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
-  { KTimer kt(ctx, KC_EPI);
+  { KTimer kt(ctx, KC_EPI_SCORE);
   k_homo_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dvalid, dcnt); }
   MVO_CHECK_LAUNCH(ctx);
-  { KTimer kt(ctx, KC_EPI);
+  { KTimer kt(ctx, KC_EPI_FINISH);
   k_homo_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dcnt, dout, dout_i, dinl); }
   MVO_CHECK_LAUNCH(ctx);
   double *h_out = (double *)(h + al((size_t)n * 16));

@@ -14,7 +14,7 @@ struct mvo_ctx;
 
 // kernel classes for the optional CUDA-event timing (mvo_timing_*)
 enum MvoKernelClass { KC_GRAY = 0, KC_RESIZE, KC_FAST, KC_SELECT, KC_BLUR, KC_DESCRIBE, KC_HARRIS, KC_MATCH,
-                      KC_PNP_HYP, KC_PNP_SCORE, KC_PNP_FINISH, KC_BA, KC_TRACK, KC_EPI, KC_COUNT };
+                      KC_PNP_HYP, KC_PNP_SCORE, KC_PNP_FINISH, KC_BA, KC_TRACK, KC_EPI, KC_EPI_SCORE, KC_EPI_FINISH, KC_COUNT };
 struct MvoEvPair { int id; cudaEvent_t a, b; };
 
 // ---- error plumbing -------------------------------------------------------------------

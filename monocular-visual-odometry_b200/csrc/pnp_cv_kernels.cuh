@@ -30,35 +30,92 @@ struct CvRngDev {
   __device__ int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
 };
 
-// Householder QR least squares of an m x n system (m <= 6, n <= 5), column-major-free: A[i][j] row-major in a[6][5]
-__device__ void cvp_lstsq(double a[6][5], double *b, int m, int n, double *x) {
-  for (int k = 0; k < n; ++k) {
-    double nrm = 0;
-    for (int i = k; i < m; ++i) nrm += a[i][k] * a[i][k];
-    nrm = sqrt(nrm);
-    if (nrm == 0) continue;
-    const double alpha = a[k][k] > 0 ? -nrm : nrm;
-    a[k][k] -= alpha;                              // v = column below the diagonal (in place)
-    double vv = 0;
-    for (int i = k; i < m; ++i) vv += a[i][k] * a[i][k];
-    if (vv > 0) {
-      for (int j = k + 1; j < n; ++j) {
-        double s = 0;
-        for (int i = k; i < m; ++i) s += a[i][k] * a[i][j];
-        s = 2 * s / vv;
-        for (int i = k; i < m; ++i) a[i][j] -= s * a[i][k];
-      }
-      double s = 0;
-      for (int i = k; i < m; ++i) s += a[i][k] * b[i];
-      s = 2 * s / vv;
-      for (int i = k; i < m; ++i) b[i] -= s * a[i][k];
-    }
-    a[k][k] = alpha;                               // R's diagonal entry
+// cvSolve(A, b, x, CV_SVD) for a 6 x n system (n <= 5): cv::SVD of A by one-sided Jacobi on the rows of A^T (OpenCV's sweep
+// order), then SVD::backSubst — x = sum over the singular values above 2 eps sum(w) of v_k (u_k . b) / w_k, i.e. the
+// minimum-norm least-squares solution (rank-deficient systems occur with coplanar points).
+__device__ void cvp_solve_svd(const double a[6][5], const double *b, int n, double *x) {
+  double At[5][6], Vt[5][5], W[5];
+  for (int i = 0; i < n; ++i) {
+    double s = 0;
+    for (int k = 0; k < 6; ++k) { At[i][k] = a[k][i]; s += a[k][i] * a[k][i]; }
+    W[i] = s;
+    for (int k = 0; k < n; ++k) Vt[i][k] = i == k ? 1.0 : 0.0;
   }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < n; ++j) s -= a[i][j] * x[j];
-    x[i] = a[i][i] != 0 ? s / a[i][i] : 0.0;
+  const double eps = 2.220446049250313e-16 * 10;
+  for (int iter = 0; iter < 30; ++iter) {
+    bool changed = false;
+    for (int i = 0; i < n - 1; ++i)
+      for (int j = i + 1; j < n; ++j) {
+        const double aa = W[i], bb = W[j];
+        double p = 0;
+        for (int k = 0; k < 6; ++k) p += At[i][k] * At[j][k];
+        if (fabs(p) <= eps * sqrt(aa * bb)) continue;
+        p *= 2;
+        const double beta = aa - bb, gamma = hypot(p, beta);
+        double c, s;
+        if (beta < 0) { s = sqrt((gamma - beta) * 0.5 / gamma); c = p / (gamma * s * 2); }
+        else { c = sqrt((gamma + beta) / (gamma * 2)); s = p / (gamma * c * 2); }
+        double na = 0, nb = 0;
+        for (int k = 0; k < 6; ++k) {
+          const double t0 = c * At[i][k] + s * At[j][k], t1 = -s * At[i][k] + c * At[j][k];
+          At[i][k] = t0; At[j][k] = t1;
+          na += t0 * t0; nb += t1 * t1;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double v0 = c * Vt[i][k] + s * Vt[j][k], v1 = -s * Vt[i][k] + c * Vt[j][k];
+          Vt[i][k] = v0; Vt[j][k] = v1;
+        }
+        W[i] = na; W[j] = nb;
+        changed = true;
+      }
+    if (!changed) break;
+  }
+  double thr = 0;
+  for (int i = 0; i < n; ++i) {
+    double s = 0;
+    for (int k = 0; k < 6; ++k) s += At[i][k] * At[i][k];
+    W[i] = sqrt(s);
+    thr += W[i];
+  }
+  thr *= 2.220446049250313e-16 * 2;
+  for (int q = 0; q < n; ++q) x[q] = 0;
+  for (int i = 0; i < n; ++i) {
+    if (fabs(W[i]) <= thr) continue;
+    double ub = 0;
+    for (int k = 0; k < 6; ++k) ub += At[i][k] * b[k];          // (w_i u_i) . b
+    const double f = ub / (W[i] * W[i]);
+    for (int q = 0; q < n; ++q) x[q] += f * Vt[i][q];
+  }
+}
+
+// JacobiSVDImpl_'s treatment of zero singular values (exactly singular input: coplanar points): the row is replaced by a
+// pseudo-random +-1/m vector (cv::RNG 0x12345678, bit 8 of every draw), orthogonalised against the rows before it in two
+// Gram-Schmidt rounds with an L1 renormalisation, then normalised.  W = the sorted singular values; rows = U^T.
+template <int N>
+__device__ void cvp_fill_zero_rows(double (*At)[N], const double *W) {
+  const double tiny = 2.2250738585072014e-308, eps = 2.220446049250313e-16 * 10;
+  CvRngDev rng;
+  rng.state = 0x12345678ull;
+  for (int i = 0; i < N; ++i) {
+    double sd = W[i];
+    for (int ii = 0; ii < 100 && sd <= tiny; ++ii) {
+      const double val0 = 1.0 / N;
+      for (int k = 0; k < N; ++k) At[i][k] = (rng.next() & 256) != 0 ? val0 : -val0;
+      for (int iter = 0; iter < 2; ++iter)
+        for (int j = 0; j < i; ++j) {
+          double d = 0;
+          for (int k = 0; k < N; ++k) d += At[i][k] * At[j][k];
+          double asum = 0;
+          for (int k = 0; k < N; ++k) { const double t = At[i][k] - d * At[j][k]; At[i][k] = t; asum += fabs(t); }
+          asum = asum > eps * 100 ? 1.0 / asum : 0.0;
+          for (int k = 0; k < N; ++k) At[i][k] *= asum;
+        }
+      sd = 0;
+      for (int k = 0; k < N; ++k) sd += At[i][k] * At[i][k];
+      sd = sqrt(sd);
+    }
+    const double s = sd > tiny ? 1.0 / sd : 0.0;
+    for (int k = 0; k < N; ++k) At[i][k] *= s;
   }
 }
 
@@ -105,11 +162,8 @@ __device__ void cvp_jacobi3(double At[3][3], double Vt[3][3], double *w) {
       for (int k = 0; k < 3; ++k) { t = At[i][k]; At[i][k] = At[j][k]; At[j][k] = t; t = Vt[i][k]; Vt[i][k] = Vt[j][k]; Vt[j][k] = t; }
     }
   }
-  for (int i = 0; i < 3; ++i) {
-    w[i] = W[i];
-    const double s = W[i] > 2.2250738585072014e-308 ? 1.0 / W[i] : 0.0;
-    for (int k = 0; k < 3; ++k) At[i][k] *= s;
-  }
+  for (int i = 0; i < 3; ++i) w[i] = W[i];
+  cvp_fill_zero_rows<3>(At, W);
 }
 
 __device__ __forceinline__ double cvp_sum16(double v) {          // sum over lanes 0..15 (12 used), result in every lane of the half warp
@@ -170,10 +224,7 @@ __device__ void cvp_jacobi12(double (*At)[12], double *W, int lane) {
         for (int q = 0; q < 12; ++q) { t = At[i][q]; At[i][q] = At[j][q]; At[j][q] = t; }
       }
     }
-    for (int i = 0; i < 12; ++i) {
-      const double s = W[i] > 2.2250738585072014e-308 ? 1.0 / W[i] : 0.0;
-      for (int q = 0; q < 12; ++q) At[i][q] *= s;
-    }
+    cvp_fill_zero_rows<12>(At, W);
   }
   __syncwarp();
 }
@@ -269,17 +320,16 @@ k_pnp_epnp(const float *__restrict__ p3, const float *__restrict__ p2, int n, co
       const double kk = sqrt(dc[i - 1] / 5);
       for (int q = 0; q < 3; ++q) S.cws[i][q] = c0[q] + kk * A3[i - 1][q];
     }
-    // compute_barycentric_coordinates: inverse of the 3 x 3 matrix of control-point offsets
-    double cc[3][3];
-    for (int i = 0; i < 3; ++i) for (int j = 1; j < 4; ++j) cc[i][j - 1] = S.cws[j][i] - S.cws[0][i];
-    const double d = cc[0][0] * (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) - cc[0][1] * (cc[1][0] * cc[2][2] - cc[1][2] * cc[2][0]) +
-                     cc[0][2] * (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]);
-    if (!(fabs(d) > 1e-300)) bad = 1;
-    const double id = 1.0 / d;
-    double ci[3][3];
-    ci[0][0] = (cc[1][1] * cc[2][2] - cc[1][2] * cc[2][1]) * id; ci[0][1] = (cc[0][2] * cc[2][1] - cc[0][1] * cc[2][2]) * id; ci[0][2] = (cc[0][1] * cc[1][2] - cc[0][2] * cc[1][1]) * id;
-    ci[1][0] = (cc[1][2] * cc[2][0] - cc[1][0] * cc[2][2]) * id; ci[1][1] = (cc[0][0] * cc[2][2] - cc[0][2] * cc[2][0]) * id; ci[1][2] = (cc[0][2] * cc[1][0] - cc[0][0] * cc[1][2]) * id;
-    ci[2][0] = (cc[1][0] * cc[2][1] - cc[1][1] * cc[2][0]) * id; ci[2][1] = (cc[0][1] * cc[2][0] - cc[0][0] * cc[2][1]) * id; ci[2][2] = (cc[0][0] * cc[1][1] - cc[0][1] * cc[1][0]) * id;
+    // compute_barycentric_coordinates: cvInvert(&CC, &CC_inv, CV_SVD) of the 3 x 3 matrix of control-point offsets — the
+    // pseudo-inverse, singular values <= 2 eps sum(w) dropped (coplanar points leave the third control point on the centroid)
+    double cct[3][3], cvt[3][3], cw[3], ci[3][3] = {};
+    for (int i = 0; i < 3; ++i) for (int j = 1; j < 4; ++j) cct[j - 1][i] = S.cws[j][i] - S.cws[0][i];      // rows of cct = columns of CC
+    cvp_jacobi3(cct, cvt, cw);
+    const double cthr = 2.220446049250313e-16 * 2 * (cw[0] + cw[1] + cw[2]);
+    for (int q = 0; q < 3; ++q)
+      if (fabs(cw[q]) > cthr)
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) ci[i][j] += cvt[q][i] * cct[q][j] / cw[q];
+    if (!(cw[0] > 0)) bad = 1;                       // all five points coincide
     for (int p = 0; p < 5; ++p) {
       for (int j = 0; j < 3; ++j)
         S.al[p][1 + j] = ci[j][0] * (S.P[p][0] - c0[0]) + ci[j][1] * (S.P[p][1] - c0[1]) + ci[j][2] * (S.P[p][2] - c0[2]);
@@ -336,7 +386,7 @@ k_pnp_epnp(const float *__restrict__ p3, const float *__restrict__ p2, int n, co
     const int *cols = N == 1 ? cols1 : (N == 2 ? cols2 : cols3);
     double a[6][5], b[6], x[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < 6; ++i) { for (int j = 0; j < nc; ++j) a[i][j] = L[i][cols[j]]; b[i] = rho[i]; }
-    cvp_lstsq(a, b, 6, nc, x);
+    cvp_solve_svd(a, b, nc, x);
     double be[4] = {0, 0, 0, 0};
     if (N == 1) {
       if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
@@ -359,7 +409,7 @@ k_pnp_epnp(const float *__restrict__ p3, const float *__restrict__ p2, int n, co
         b[i] = rho[i] - (r[0] * be[0] * be[0] + r[1] * be[0] * be[1] + r[2] * be[1] * be[1] + r[3] * be[0] * be[2] + r[4] * be[1] * be[2] +
                          r[5] * be[2] * be[2] + r[6] * be[0] * be[3] + r[7] * be[1] * be[3] + r[8] * be[2] * be[3] + r[9] * be[3] * be[3]);
       }
-      cvp_lstsq(a, b, 6, 4, dx);
+      cvp_solve_svd(a, b, 4, dx);
       for (int q = 0; q < 4; ++q) be[q] += dx[q];
     }
     double R[9], t[3];

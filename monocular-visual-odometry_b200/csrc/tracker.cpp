@@ -880,7 +880,9 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
     g.edge_map = t->d_edge_map; g.edge_obs = t->d_edge_obs; g.edge_kp = t->d_edge_kp; g.cnt = t->d_cnt; g.pose = t->d_pose;
     g.skip_flag = t->d_flags; g.res_i = d_res_i; g.res_d = t->d_res;
     g.map_ids = t->d_map_ids; g.vis = d_vis; g.nmap = nmap;
-    if (t->count_stats && !counted && nmap > 0) { g.vis_cnt = t->d_vis_cnt; g.match_cnt = t->d_match_cnt; }
+    // visible_times_ once per frame; matched_times_ by the tail whose PnP saw the pairs (a declined device filter hands
+    // its tail zero pairs, so the redo through the host filter is the one that counts the inliers)
+    if (t->count_stats && nmap > 0) { g.match_cnt = t->d_match_cnt; if (!counted) g.vis_cnt = t->d_vis_cnt; }
     int rc2 = MVO_OK;
     if (run_pnp) {
       float *d_p3, *d_p2;

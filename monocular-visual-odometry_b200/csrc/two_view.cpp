@@ -20,16 +20,16 @@ extern "C" int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, 
     np1[2 * i] = (float)(((double)pts_img1[2 * i] - K[2]) / K[0]); np1[2 * i + 1] = (float)(((double)pts_img1[2 * i + 1] - K[5]) / K[4]);
     np2[2 * i] = (float)(((double)pts_img2[2 * i] - K[2]) / K[0]); np2[2 * i + 1] = (float)(((double)pts_img2[2 * i + 1] - K[5]) / K[4]);
   }
-  // ---- essential (:43-48); config findEssentialMat_threshold = 1.0 ----
+  // ---- essential (:43-48); threshold = config findEssentialMat_threshold (mvo_params::essential_threshold) ----
   std::vector<int32_t> inl_e((size_t)n), inl_h((size_t)n);
   int n_e = n, n_h = 0;
-  MVO_TRY(mvo_esti_motion_by_essential(ctx, pts_img1, pts_img2, n, K, 1.0, sol->E, sol->R[0], sol->t[0], inl_e.data(), &n_e));
+  MVO_TRY(mvo_esti_motion_by_essential(ctx, pts_img1, pts_img2, n, K, ctx->prm.essential_threshold, sol->E, sol->R[0], sol->t[0], inl_e.data(), &n_e));
   // ---- homography + removeWrongRtOfHomography (:56-67) ----
   double Rh[36], th[12], nh[12];
   int num_h = 0;
   if (calc_homo) {
     n_h = n;
-    const int rc = mvo_esti_motion_by_homography(ctx, pts_img1, pts_img2, n, K, 3.0, sol->H, Rh, th, nh, &num_h, inl_h.data(), &n_h);
+    const int rc = mvo_esti_motion_by_homography(ctx, pts_img1, pts_img2, n, K, ctx->prm.homography_threshold, sol->H, Rh, th, nh, &num_h, inl_h.data(), &n_h);
     if (rc == MVO_ERR_DEGENERATE) { num_h = 0; n_h = 0; }
     else if (rc != MVO_OK) return rc;
     if (num_h > 0) MVO_TRY(mvo_remove_wrong_rt_of_homography(ctx, np1.data(), np2.data(), n, inl_h.data(), n_h, Rh, th, nh, &num_h));

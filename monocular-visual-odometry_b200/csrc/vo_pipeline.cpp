@@ -29,8 +29,10 @@
 //     four host round trips per tracked frame, as a maintainer who only swaps the bodies of the reference functions gets it.
 // Both give the same states, counts and keyframes; poses agree to the summation order of the BA (tests/test_vo_pipeline_gpu.py).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <memory>
 #include <unordered_map>
@@ -38,6 +40,23 @@
 #include "mvo_internal.h"
 
 namespace {
+
+// MVO_VO_DEBUG=1: host wall time of the stages of the initialisation / keyframe branches, printed per frame (stderr)
+struct StageClock {
+  bool on;
+  double t0, acc[12];
+  const char *name[12];
+  int n;
+  static double now() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  StageClock() : on(getenv("MVO_VO_DEBUG") != nullptr), t0(0), n(0) { if (on) t0 = now(); }
+  void mark(const char *what) { if (!on || n >= 12) return; const double t = now(); name[n] = what; acc[n++] = t - t0; t0 = t; }
+  void report(const char *head, int frame) {
+    if (!on) return;
+    fprintf(stderr, "%s frame %d:", head, frame);
+    for (int i = 0; i < n; ++i) fprintf(stderr, " %s %.0f", name[i], acc[i]);
+    fprintf(stderr, " us\n");
+  }
+};
 
 enum { VO_BLANK = 0, VO_DOING_INITIALIZATION = 1, VO_DOING_TRACKING = 2, VO_LOST = 3 };   // vo.h:52-58
 
@@ -322,8 +341,12 @@ int estimate_motion_and_3d_points(mvo_vo *v, mvo_vo_frame_info *info, int *usabl
   mvo_two_view_solutions sol;
   v->inl.resize((size_t)5 * n);
   v->pts3d.resize((size_t)5 * n * 3);
+  // the initialisation uses the configured findEssentialMat_threshold like the keyframe branch does (vo.cpp:60-70)
+  const double saved_thr = v->ctx->prm.essential_threshold;
+  v->ctx->prm.essential_threshold = v->prm.essential_threshold;
   const int rc = mvo_estimate_relative_poses(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.init_calc_homography, 1, &sol,
                                              v->inl.data(), v->pts3d.data());
+  v->ctx->prm.essential_threshold = saved_thr;
   if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
   if (rc != MVO_OK) return rc;
   const int best = sol.best, ni = sol.n_inliers[best];
@@ -554,11 +577,14 @@ int call_bundle_adjustment(mvo_vo *v, mvo_vo_frame_info *info) {
 int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   VoFrame &c = *v->curr;
   const VoFrame &r = *v->ref;
+  StageClock clk;
   if (v->dev) {                                                  // the frame's keypoints and connections come to the host now
     MVO_TRY(ensure_host(v, &c));
     MVO_TRY(ensure_conn(v, &c, 0));
   }
+  clk.mark("fetch");
   MVO_TRY(match_into(v, r.desc.data(), r.xy.data(), r.n(), c, v->prm.track.match_method, v->prm.max_match_dist_triangulation, &c.matches_with_ref));
+  clk.mark("match");
   const int n = (int)c.matches_with_ref.size();
   info->kf_matches = n;
   if (n < 8) return MVO_OK;                                      // see the file header
@@ -575,6 +601,7 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   const int rc = mvo_esti_motion_by_essential(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.essential_threshold, E, Re, te, v->inl.data(), &ni);
   if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
   if (rc != MVO_OK) return rc;
+  clk.mark("essential");
   c.inliers_matches_with_ref.resize((size_t)ni);
   v->np1.resize((size_t)ni * 2); v->np2.resize((size_t)ni * 2);
   for (int i = 0; i < ni; ++i) {
@@ -596,18 +623,24 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   if (ni > 0) MVO_TRY(mvo_do_triangulation(v->ctx, v->np1.data(), v->np2.data(), ni, R, t, all.data(), ni, v->pts3d.data()));
   c.inliers_pts3d.resize((size_t)ni * 3);
   for (int i = 0; i < ni; ++i) trans_coord(&v->pts3d[3 * (size_t)i], R, t, &c.inliers_pts3d[3 * (size_t)i]);
+  clk.mark("triangulate");
   MVO_TRY(retain_good_triangulation(v));
   info->kf_new_points = (int)c.inliers_matches_for_3d.size();
   v->new_ids.clear(); v->new_kp.clear(); v->new_obs.clear();
   push_curr_points_to_map(v);
+  clk.mark("retain+push");
   if (v->dev) MVO_TRY(pull_counters(v));                         // visible_times_ / matched_times_ as of this frame
+  clk.mark("counters");
   optimize_map(v);
+  clk.mark("optimize_map");
   if (v->dev) {
     MVO_TRY(upload_map(v));
     MVO_TRY(mvo_trk_append_links(v->trk, 0, v->new_ids.data(), v->new_kp.data(), v->new_obs.data(), (int)v->new_ids.size()));
   }
+  clk.mark("upload");
   add_keyframe(v, v->curr);
   info->keyframe = 1;
+  clk.report("keyframe", c.id);
   return MVO_OK;
 }
 
@@ -802,6 +835,14 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
       if (rc == MVO_OK) rc = mvo_check_large_move(frame->T_w_c, v->ref->T_w_c, v->prm.track.min_dist_keyframe, &large, nullptr, nullptr);
       if (rc == MVO_OK && large) rc = insert_keyframe(v, &info);
     }
+  }
+  if (rc != MVO_OK && !info.keyframe && !v->buff.empty() && v->buff.back() == frame) {
+    // a stage failed (a CUDA error, an unsupported size): the frame leaves the buffer again, in both modes, so that
+    // mvo_vo_frame_pose(k) keeps addressing the frames whose mvo_vo_add_frame call succeeded
+    v->buff.pop_back();
+    v->curr = v->prev;
+    v->frame_factory_id--;
+    return rc;
   }
   v->prev = frame;                                               // :141
   info.state_out = v->state;

@@ -57,6 +57,7 @@ void VisualOdometry::create(const Frame &first) {
   const cv::Mat &K = first.camera_->K_;
   double Kf[9];
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Kf[i * 3 + j] = K.at<double>(i, j);
+  buffer_size_ = p.track.buffer_size;
   mvo_adapter::check(mvo_vo_create(mvo_adapter::context(), Kf, first.rgb_img_.rows, first.rgb_img_.cols, &p, &vo_), "VisualOdometry");
 }
 
@@ -89,7 +90,7 @@ void VisualOdometry::addFrame(Frame::Ptr frame) {
   by_id_[info.frame_id] = frame;
   lib_id_[frame->id_] = info.frame_id;
   frames_buff_.push_back(frame);                                  // pushFrameToBuff_ (vo.h:81-86)
-  if (frames_buff_.size() > 20) {
+  if ((int)frames_buff_.size() > buffer_size_) {                  // kBuffSize_ (vo.h:77) = mvo_track_params::buffer_size
     auto it = lib_id_.find(frames_buff_.front()->id_);
     if (it != lib_id_.end()) { by_id_.erase(it->second); lib_id_.erase(it); }
     frames_buff_.pop_front();

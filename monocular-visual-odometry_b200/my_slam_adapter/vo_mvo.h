@@ -77,6 +77,7 @@ class VisualOdometry {                                            // include/my_
  private:
   void create(const Frame &first);
   mvo_vo *vo_ = nullptr;
+  int buffer_size_ = 20;                                          // kBuffSize_ (include/my_slam/vo/vo.h:77)
   Map::Ptr map_;
   Frame::Ptr prev_ref_;
   std::deque<Frame::Ptr> frames_buff_;                            // the same 20 newest frames libmvo keeps

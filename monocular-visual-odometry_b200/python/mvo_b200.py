@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("pnp_hypotheses", C.c_int32), ("pnp_reproj_error", C.c_float), ("pnp_seed", C.c_uint64),
         ("pnp_refine_iters", C.c_int32), ("ba_iterations", C.c_int32), ("ba_huber_delta", C.c_double),
         ("ba_fix_first_pose", C.c_int32), ("ba_step_tol", C.c_double), ("epi_hypotheses", C.c_int32), ("pnp_mode", C.c_int32), ("eh_ratio_threshold", C.c_double),
+        ("essential_threshold", C.c_double), ("homography_threshold", C.c_double),
     ]
 
 

@@ -117,8 +117,26 @@ def jacobi_svd(A):
             W[[i, j]] = W[[j, i]]
             At[[i, j]] = At[[j, i]]
             Vt[[i, j]] = Vt[[j, i]]
+    # rows with a zero singular value: OpenCV fills them with pseudo-random +-1/m vectors (RNG 0x12345678), orthogonalised
+    # against the rows before them (two Gram-Schmidt rounds with an L1 renormalisation), then normalised
+    tiny = np.finfo(np.float64).tiny
+    rng = CvRng(0x12345678)
+    m = n
     for i in range(n):
-        At[i] *= (1.0 / W[i]) if W[i] > np.finfo(np.float64).tiny else 0.0
+        sd = W[i]
+        for _ in range(100):
+            if sd > tiny:
+                break
+            val0 = 1.0 / m
+            At[i] = [val0 if (rng.next() & 256) != 0 else -val0 for _k in range(m)]
+            for _it in range(2):
+                for j in range(i):
+                    dot = float(At[i] @ At[j])
+                    At[i] = At[i] - dot * At[j]
+                    asum = float(np.abs(At[i]).sum())
+                    At[i] = At[i] * ((1.0 / asum) if asum > eps * 100 else 0.0)
+            sd = math.sqrt(float(At[i] @ At[i]))
+        At[i] *= (1.0 / sd) if sd > tiny else 0.0
     return At.T.copy(), W, Vt
 
 
@@ -141,7 +159,13 @@ def epnp(P, us, fu, fv, uc, vc, svd=None):
     cws[0] = c0
     for i in range(1, 4):
         cws[i] = c0 + np.sqrt(dc[i - 1] / n) * uct[i - 1]
-    CCi = np.linalg.inv((cws[1:] - cws[0]).T)
+    # cvInvert(&CC, &CC_inv, CV_SVD): pseudo-inverse, singular values <= 2 eps * sum(w) dropped (coplanar points)
+    Uc, wc, Vtc = svd((cws[1:] - cws[0]).T)
+    thr = np.finfo(np.float64).eps * 2 * wc.sum()
+    CCi = np.zeros((3, 3))
+    for k in range(3):
+        if abs(wc[k]) > thr:
+            CCi += np.outer(Vtc[k], Uc[:, k]) / wc[k]
     al = np.zeros((n, 4))
     al[:, 1:] = (CCi @ (P - c0).T).T
     al[:, 0] = 1.0 - al[:, 1] - al[:, 2] - al[:, 3]

@@ -60,6 +60,19 @@ const char *mvo_last_error(const mvo_ctx *c) { return c ? c->err.c_str() : ""; }
 int mvo_orb_extract(mvo_ctx *, const uint8_t *image, int rows, int cols, int channels, size_t stride, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
   return g_stages.orb_extract(image, rows, cols, channels, stride, kpts, n_kpts, desc);
 }
+// The host check covers the host-array mode of the state machine: the device-resident tracker reports itself unavailable, so
+// mvo_vo_create selects the host-array path (mvo_trk_device_mode == 0) and none of the other tracker entry points is reached.
+int mvo_tracker_create(mvo_ctx *, const double *, int, int, const mvo_track_params *, mvo_tracker **out) { *out = (mvo_tracker *)nullptr; return MVO_OK; }
+void mvo_tracker_destroy(mvo_tracker *) {}
+int mvo_tracker_prefetch(mvo_tracker *, const uint8_t *, int, size_t, int) { return MVO_ERR_UNSUPPORTED; }
+int mvo_tracker_reset(mvo_tracker *, const double *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_tracker_frame_pose(const mvo_tracker *, int, double *) { return MVO_ERR_UNSUPPORTED; }
+uint64_t mvo_tracker_kernel_launches(const mvo_tracker *) { return 0; }
+int mvo_tracker_timing_enable(mvo_tracker *, uint32_t) { return MVO_ERR_UNSUPPORTED; }
+int mvo_tracker_timing_read(mvo_tracker *, double *, uint64_t *) { return MVO_ERR_UNSUPPORTED; }
+uint64_t mvo_kernel_launches(const mvo_ctx *) { return 0; }
+int mvo_timing_enable(mvo_ctx *, uint32_t) { return MVO_ERR_UNSUPPORTED; }
+int mvo_timing_read(mvo_ctx *, double *, uint64_t *) { return MVO_ERR_UNSUPPORTED; }
 int mvo_match_features(mvo_ctx *, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int method_index, const float *xy1, const float *xy2,
                        float radius, mvo_dmatch *out, int *n_out) {
   return g_stages.match_features(d1, n1, d2, n2, method_index, xy1, xy2, radius, out, n_out);
@@ -91,3 +104,24 @@ int mvo_bundle_adjustment(mvo_ctx *, double *poses, int n_frames, float *points,
 }
 
 }  // extern "C"
+
+// never reached in the host check (only device images are copied back); libmvo.so links the CUDA runtime statically
+extern "C" cudaError_t cudaMemcpy2D(void *, size_t, const void *, size_t, size_t, size_t, cudaMemcpyKind) { return cudaErrorNotSupported; }
+extern "C" const char *cudaGetErrorString(cudaError_t) { return "host check: no CUDA runtime"; }
+
+// C++ linkage, as declared in mvo_internal.h
+int mvo_orb_extract_ex(mvo_ctx *, const uint8_t *image, int rows, int cols, int channels, size_t stride, int, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
+  return g_stages.orb_extract(image, rows, cols, channels, stride, kpts, n_kpts, desc);
+}
+int mvo_trk_device_mode(const mvo_tracker *) { return 0; }
+void mvo_trk_configure(mvo_tracker *, int, int) {}
+int mvo_trk_acquire(mvo_tracker *, const uint8_t *, int, size_t, int, int *, int *) { return MVO_ERR_UNSUPPORTED; }
+void mvo_trk_release(mvo_tracker *, int) {}
+int mvo_trk_fetch(mvo_tracker *, int, mvo_keypoint *, uint8_t *) { return MVO_ERR_UNSUPPORTED; }
+unsigned mvo_trk_slot_serial(const mvo_tracker *, int) { return 0; }
+int mvo_trk_set_map_ids(mvo_tracker *, const float *, const uint8_t *, const int32_t *, int, int) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_push_frame(mvo_tracker *, const double *, const int32_t *, const int32_t *, const float *, int) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_append_links(mvo_tracker *, int, const int32_t *, const int32_t *, const float *, int) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_links(mvo_tracker *, int, int32_t *, int32_t *, int, int *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_counters(mvo_tracker *, int32_t *, int32_t *, int) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_track(mvo_tracker *, int, const double *, const double *, double *, mvo_track_result *) { return MVO_ERR_UNSUPPORTED; }
