@@ -412,6 +412,277 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
   }
 }
 
+
+// ------------------------------------------------------------------------------ retainBest
+// cv::KeyPointsFilter::retainBest as cv::ORB applies it per pyramid level (orb.cpp computeKeyPoints): first by FAST score to
+// 2 x featuresPerLevel, then — with the Harris responses of the survivors — to featuresPerLevel.  retainBest is
+//   std::nth_element(begin, begin + n - 1, end, response greater) ; ambiguous = v[n - 1].response ;
+//   std::partition(begin + n, end, response >= ambiguous) ; resize
+// and both the surviving SET and its ORDER (which the reference's first-come grid selection depends on) are decided by
+// libstdc++'s algorithms, restated here step by step:
+//   nth_element = __introselect: while the range holds more than 3 elements, __unguarded_partition_pivot (median of
+//     first+1 / middle / last-1 moved to the front, then the unguarded Hoare partition) and continue in the part that
+//     holds the nth position; __insertion_sort on the last <= 3 elements.  The partition is evaluated by one warp with the
+//     technique of k_match_filter (track_filter.cuh): the stop positions of the left scan (Lo) and of the right scan (Ro)
+//     are properties of the range before any swap, the k-th swap pairs Lo[k] with Ro[k] while Lo[k] < Ro[k], and the cut
+//     is min(Lo[K], Ro[K-1]).  Beyond the depth limit 2 lg(n) libstdc++ switches to heap-select: the kernel then reports
+//     the frame for the host path (adversarial inputs only).
+//   partition (bidirectional): the k-th swap pairs the k-th element from the left that fails the predicate with the k-th
+//     element from the right that passes it, while the former lies left of the latter; new end = begin + #passing.
+// One warp per (level, frame); the level's records live in shared memory (response 4 B + index 2 B + the two stop lists).
+constexpr int RET_MAX = 12288;       // candidates of one level the device path holds; more -> host path
+
+struct RetBuf { float *key; uint16_t *idx, *Ls, *Rs; };
+
+__device__ __forceinline__ void ret_swap(const RetBuf &b, int x, int y) {
+  const float k = b.key[x]; b.key[x] = b.key[y]; b.key[y] = k;
+  const uint16_t i = b.idx[x]; b.idx[x] = b.idx[y]; b.idx[y] = i;
+}
+
+// std::__unguarded_partition_pivot(first, last, greater) by one warp; returns the cut
+__device__ int ret_partition_pivot(const RetBuf &b, int first, int last, int lane) {
+  if (lane == 0) {                       // __move_median_to_first(first, first + 1, mid, last - 1), comp(a, b) = a > b
+    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+    const float ka = b.key[ia], kb = b.key[ib], kc = b.key[ic];
+    int pick;
+    if (ka > kb) pick = (kb > kc) ? ib : ((ka > kc) ? ic : ia);
+    else pick = (ka > kc) ? ia : ((kb > kc) ? ic : ib);
+    ret_swap(b, first, pick);
+  }
+  __syncwarp();
+  const float pivot = b.key[first];
+  const int lo = first + 1, len = last - lo;
+  int nL = 0, nR = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < len;
+    const bool ls = inr && !(b.key[lo + i] > pivot);              // the left scan `while (*first > pivot) ++first` stops here
+    const bool rs = inr && !(pivot > b.key[last - 1 - i]);        // the right scan `while (pivot > *last) --last` stops here
+    const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
+    const unsigned below = (1u << lane) - 1u;
+    if (ls) b.Ls[lo + nL + __popc(bl & below)] = (uint16_t)(lo + i);
+    if (rs) b.Rs[lo + nR + __popc(br & below)] = (uint16_t)(last - 1 - i);
+    nL += __popc(bl);
+    nR += __popc(br);
+  }
+  __syncwarp();
+  const int nmin = min(nL, nR);
+  int K = 0;
+  for (int base = 0; base < nmin; base += 32) {
+    const int j = base + lane;
+    const bool sw = j < nmin && b.Ls[lo + j] < b.Rs[lo + j];
+    const unsigned m = __ballot_sync(0xffffffffu, sw);
+    if (sw) ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]);
+    const int c = __popc(m);
+    K += c;
+    if (c < 32) break;
+  }
+  __syncwarp();
+  int cut;
+  if (K == 0) cut = nL > 0 ? (int)b.Ls[lo] : last;
+  else { cut = (int)b.Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)b.Ls[lo + K]); }
+  return cut;
+}
+
+// cv::KeyPointsFilter::retainBest on b.key / b.idx [0, n): returns the new size, or -1 where libstdc++ would heap-select
+__device__ int ret_retain_best(const RetBuf &b, int n, int npts, int lane) {
+  if (npts < 0 || n <= npts) return n;
+  if (npts == 0) return 0;
+  // std::nth_element(begin, begin + npts - 1, end)
+  {
+    int first = 0, last = n;
+    const int nth = npts - 1;
+    int depth = 0;
+    for (int m = n; m > 1; m >>= 1) ++depth;
+    depth *= 2;
+    while (last - first > 3) {
+      if (depth == 0) return -1;
+      --depth;
+      const int cut = ret_partition_pivot(b, first, last, lane);
+      if (cut <= nth) first = cut; else last = cut;
+    }
+    if (lane == 0) {                     // __insertion_sort(first, last, greater)
+      for (int i = first + 1; i < last; ++i) {
+        const float v = b.key[i];
+        const uint16_t vi = b.idx[i];
+        int j = i - 1;
+        if (v > b.key[first]) {          // move_backward(first, i, i + 1); *first = val
+          for (; j >= first; --j) { b.key[j + 1] = b.key[j]; b.idx[j + 1] = b.idx[j]; }
+          b.key[first] = v; b.idx[first] = vi;
+        } else {                         // __unguarded_linear_insert
+          for (; v > b.key[j]; --j) { b.key[j + 1] = b.key[j]; b.idx[j + 1] = b.idx[j]; }
+          b.key[j + 1] = v; b.idx[j + 1] = vi;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // std::partition(begin + npts, end, response >= ambiguous)
+  const float amb = b.key[npts - 1];
+  const int lo = npts, len = n - npts;
+  int nF = 0, nT = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < len;
+    const bool fl = inr && !(b.key[lo + i] >= amb);               // from the left: fails the predicate
+    const bool tr = inr && (b.key[n - 1 - i] >= amb);             // from the right: passes it
+    const unsigned bf = __ballot_sync(0xffffffffu, fl), bt = __ballot_sync(0xffffffffu, tr);
+    const unsigned below = (1u << lane) - 1u;
+    if (fl) b.Ls[lo + nF + __popc(bf & below)] = (uint16_t)(lo + i);
+    if (tr) b.Rs[lo + nT + __popc(bt & below)] = (uint16_t)(n - 1 - i);
+    nF += __popc(bf);
+    nT += __popc(bt);
+  }
+  __syncwarp();
+  const int nmin = min(nF, nT);
+  for (int base = 0; base < nmin; base += 32) {
+    const int j = base + lane;
+    const bool sw = j < nmin && b.Ls[lo + j] < b.Rs[lo + j];
+    const unsigned m = __ballot_sync(0xffffffffu, sw);
+    if (sw) ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]);
+    if (__popc(m) < 32) break;
+  }
+  __syncwarp();
+  return npts + nT;
+}
+
+__global__ void __launch_bounds__(32)
+k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__restrict__ harris, OrbFrameMeta *__restrict__ meta,
+         uint16_t *__restrict__ kept, int32_t *__restrict__ kept_cnt) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int l = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  if (meta[f].overflow == 0) return;
+  RetBuf b;
+  b.key = reinterpret_cast<float *>(smem);
+  b.idx = reinterpret_cast<uint16_t *>(b.key + RET_MAX);
+  b.Ls = b.idx + RET_MAX;
+  b.Rs = b.Ls + RET_MAX;
+  const int n = meta[f].lvl_count[l];
+  int base = 0;
+  for (int q = 0; q < l; ++q) base += meta[f].lvl_count[q];
+  uint16_t *out = kept + ((size_t)f * plan.nlevels + l) * RET_MAX;
+  const int cap = plan.lv[l].cap;
+  if (n > RET_MAX || base + n > plan.cand_cap) {           // beyond the device path: the host finishes this frame
+    if (lane == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
+    return;
+  }
+  if (n <= cap) {                                           // both retainBest calls are no-ops
+    for (int i = lane; i < n; i += 32) out[i] = (uint16_t)i;
+    if (lane == 0) kept_cnt[f * plan.nlevels + l] = n;
+    return;
+  }
+  const uint32_t *cf = cand + (size_t)f * plan.cand_cap + base;
+  const float *hf = harris + (size_t)f * plan.cand_cap + base;
+  for (int i = lane; i < n; i += 32) { b.key[i] = (float)orb_ps(cf[i]); b.idx[i] = (uint16_t)i; }
+  __syncwarp();
+  int m = ret_retain_best(b, n, 2 * cap, lane);            // by FAST score
+  if (m >= 0) {
+    for (int i = lane; i < m; i += 32) b.key[i] = hf[b.idx[i]];   // HarrisResponses of the survivors, in their order
+    __syncwarp();
+    m = ret_retain_best(b, m, cap, lane);                   // by Harris response
+  }
+  if (m < 0) {
+    if (lane == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
+    return;
+  }
+  for (int i = lane; i < m; i += 32) out[i] = b.idx[i];
+  if (lane == 0) kept_cnt[f * plan.nlevels + l] = m;
+}
+
+// selectUniformKptsByGrid (feature_match.cpp:51-84) over the retained lists of a frame whose levels overflowed: the closed
+// form of k_select (rank inside the 16 x 16 cell < max_per_cell, cut after max_kpts + 1 kept) in the retained ORDER.
+__global__ void __launch_bounds__(1024)
+k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t *__restrict__ kept, const int32_t *__restrict__ kept_cnt,
+              uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (meta[f].overflow != 1) return;
+  const int ncell = plan.grid_rows * plan.grid_cols, scap = plan.sel_cap;
+  int32_t *s_cellcnt = reinterpret_cast<int32_t *>(smem);          // [ncell + 1]
+  int32_t *s_cursor = s_cellcnt + ncell + 1;                        // [ncell]
+  uint32_t *s_pk = reinterpret_cast<uint32_t *>(s_cursor + ncell);  // [scap] packed candidate of list item i
+  uint16_t *s_cell = reinterpret_cast<uint16_t *>(s_pk + scap);     // [scap]
+  uint16_t *s_bucket = s_cell + scap;                               // [scap]
+  uint8_t *s_keep = reinterpret_cast<uint8_t *>(s_bucket + scap);   // [scap]
+  uint8_t *s_lvl = s_keep + scap;                                   // [scap]
+  __shared__ int s_warp[32];
+  __shared__ int s_off[MVO_MAX_LEVELS + 1], s_base[MVO_MAX_LEVELS + 1];
+  if (tid == 0) {
+    int o = 0, bb = 0;
+    for (int l = 0; l < plan.nlevels; ++l) { s_off[l] = o; s_base[l] = bb; o += kept_cnt[f * plan.nlevels + l]; bb += meta[f].lvl_count[l]; }
+    s_off[plan.nlevels] = o;
+  }
+  for (int i = tid; i <= ncell; i += 1024) s_cellcnt[i] = 0;
+  __syncthreads();
+  const int n = s_off[plan.nlevels];
+  if (n > scap) {                                                   // ties at the Harris cut beyond nfeatures: host path
+    if (tid == 0) meta[f].overflow = 2;
+    return;
+  }
+  const uint32_t *cf = cand + (size_t)f * plan.cand_cap;
+  for (int i = tid; i < n; i += 1024) {
+    int l = 0;
+    while (l + 1 < plan.nlevels && i >= s_off[l + 1]) ++l;
+    const uint32_t p = cf[s_base[l] + kept[((size_t)f * plan.nlevels + l) * RET_MAX + (i - s_off[l])]];
+    const float scale = plan.lv[l].scale;
+    const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
+    const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
+    int row = ((int)fy) / plan.grid_size, col = ((int)fx) / plan.grid_size;
+    row = min(row, plan.grid_rows - 1);
+    col = min(col, plan.grid_cols - 1);
+    const int cell = row * plan.grid_cols + col;
+    s_pk[i] = p; s_lvl[i] = (uint8_t)l; s_cell[i] = (uint16_t)cell;
+    atomicAdd(&s_cellcnt[cell], 1);
+  }
+  __syncthreads();
+  {
+    const int per = (ncell + 1023) >> 10;
+    const int b = tid * per, e = min(b + per, ncell);
+    int mine = 0;
+    for (int i = b; i < e; ++i) mine += s_cellcnt[i];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    for (int i = b; i < e; ++i) { const int c = s_cellcnt[i]; s_cellcnt[i] = off; s_cursor[i] = off; off += c; }
+    if (tid == 1023) s_cellcnt[ncell] = n;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) s_bucket[atomicAdd(&s_cursor[s_cell[i]], 1)] = (uint16_t)i;
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const int c = s_cell[i];
+    int rank = 0;
+    for (int k = s_cellcnt[c]; k < s_cellcnt[c + 1]; ++k) rank += (s_bucket[k] < i);
+    s_keep[i] = rank < plan.max_per_cell;
+  }
+  __syncthreads();
+  {
+    const int per = (n + 1023) >> 10;
+    const int b = tid * per, e = min(b + per, n);
+    int mine = 0;
+    for (int i = b; i < e; ++i) mine += s_keep[i];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int pos = incl - mine, total = 0;
+    for (int k = 0; k < 32; ++k) { if (k < warp) pos += s_warp[k]; total += s_warp[k]; }
+    uint2 *sf = sel + (size_t)f * (plan.max_kpts + 1);
+    for (int i = b; i < e; ++i)
+      if (s_keep[i]) {
+        if (pos <= plan.max_kpts) sf[pos] = make_uint2(s_pk[i], (uint32_t)s_lvl[i]);
+        ++pos;
+      }
+    if (tid == 0) { meta[f].n_sel = min(total, plan.max_kpts + 1); meta[f].overflow = 3; }      // 3 = resolved on the device
+  }
+}
+
 // ------------------------------------------------------------------------------------ blur
 // cv::GaussianBlur(7x7, 2, 2, BORDER_REFLECT_101) as ORB applies it to a pyramid level: float
 // separable filter, row pass taps in ascending order, symmetric column pass, saturate_cast<uchar>
@@ -651,6 +922,7 @@ __global__ void __launch_bounds__(256)
 k_harris_all(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint32_t *__restrict__ cand,
              const OrbFrameMeta *__restrict__ meta, float *__restrict__ harris) {
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (meta[f].overflow == 0) return;              // only retainBest needs the response of every candidate
   const int n = min(meta[f].n_cand, plan.cand_cap);
   const uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
   for (int k = blockIdx.x * 8 + warp; k < n; k += gridDim.x * 8) {
@@ -763,6 +1035,26 @@ int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *p
   dim3 grid(2 * ctx->sm_count, batch);
   KTimer kt(ctx, KC_HARRIS);
   k_harris_all<<<grid, 256, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int orb_retain_max(void) { return RET_MAX; }
+
+// retainBest + grid selection on the device for the frames whose levels overflowed (meta.overflow == 1 -> 3; 2 = host path needed)
+int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand, const float *harris, OrbFrameMeta *meta,
+                      uint16_t *kept, int32_t *kept_cnt, uint2 *sel, int batch) {
+  const size_t smem = (size_t)RET_MAX * 10;
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_retain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { KTimer kt(ctx, KC_SELECT);
+  k_retain<<<dim3(plan.nlevels, batch), 32, smem, ctx->stream>>>(plan, cand, harris, meta, kept, kept_cnt); }
+  MVO_CHECK_LAUNCH(ctx);
+  const int ncell = plan.grid_rows * plan.grid_cols;
+  const size_t smem2 = (size_t)(2 * ncell + 1) * 4 + (size_t)plan.sel_cap * (4 + 2 + 2 + 1 + 1) + 64;
+  if (smem2 > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "selection grid too large");
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_select_kept, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  { KTimer kt(ctx, KC_SELECT);
+  k_select_kept<<<batch, 1024, smem2, ctx->stream>>>(plan, cand, kept, kept_cnt, sel, meta); }
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

@@ -33,7 +33,8 @@ struct OrbPlanDev {
 // Per-frame metadata written by the selection kernel.
 struct OrbFrameMeta {
   int32_t n_sel;                       // keypoints selected on the fast path
-  int32_t overflow;                    // 1: some level exceeds featuresPerLevel -> host retainBest
+  int32_t overflow;                    // 0: no level exceeds featuresPerLevel; 1: some do (k_select) -> 3: retainBest + selection done on
+                                       // the device (k_retain, k_select_kept); 2: beyond the device path -> host retainBest
   int32_t n_cand;                      // total FAST candidates (all levels)
   int32_t lvl_count[MVO_MAX_LEVELS];
   int32_t pad[5];
@@ -57,6 +58,9 @@ int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *stag
 int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int batch);
 int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint32_t *cand,
                           const OrbFrameMeta *meta, float *harris, int batch);
+int orb_retain_max(void);
+int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand, const float *harris, OrbFrameMeta *meta,
+                      uint16_t *kept, int32_t *kept_cnt, uint2 *sel, int batch);
 // mode 0: from selection list (sel) -> keypoints (+ descriptors if with_desc)
 int orb_launch_describe_sel(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint2 *sel,
                             const OrbFrameMeta *meta, const int32_t *n_override, mvo_keypoint *kpts, uint8_t *desc,

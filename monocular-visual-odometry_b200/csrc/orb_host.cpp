@@ -2,6 +2,7 @@
 // host-side steps that are deliberately NOT on the GPU because their result depends on libstdc++
 // (cv::KeyPointsFilter::retainBest = std::nth_element + std::partition).
 #include <algorithm>
+#include <atomic>
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -132,6 +133,8 @@ struct OrbWs {
   int32_t *tables;
   int32_t *n_override;
   int32_t *bad_flag;
+  uint16_t *kept;          // [batch][nlevels][orb_retain_max()] retained candidates of an overflowing level, in retainBest's order
+  int32_t *kept_cnt;       // [batch][nlevels]
 };
 
 int ensure_ws(mvo_ctx *ctx, OrbState *st, int rows, int cols, int batch, OrbWs *ws) {
@@ -150,7 +153,7 @@ int ensure_ws(mvo_ctx *ctx, OrbState *st, int rows, int cols, int batch, OrbWs *
     MVO_TRY(mvo_reserve(ctx, ctx->orb_sel, (size_t)batch * (pl.max_kpts + 1) * 8));
     // misc: cand + harris + meta + n_override + bad flag + tables
     const size_t misc = (size_t)batch * pl.cand_cap * 8 + (size_t)batch * 64 + (size_t)batch * 4 + 256 +
-                        st->tables.size() * 4 + 4096;
+                        st->tables.size() * 4 + 4096 + (size_t)batch * pl.nlevels * orb_retain_max() * 2 + (size_t)batch * pl.nlevels * 4 + 1024;
     MVO_TRY(mvo_reserve(ctx, ctx->orb_misc, misc));
   }
   const bool fresh = grow || ctx->orb_batch == 0;
@@ -164,6 +167,8 @@ int ensure_ws(mvo_ctx *ctx, OrbState *st, int rows, int cols, int batch, OrbWs *
   ws->meta = (OrbFrameMeta *)(m + o); o = al(o + (size_t)batch * 64);
   ws->n_override = (int32_t *)(m + o); o = al(o + (size_t)batch * 4);
   ws->bad_flag = (int32_t *)(m + o); o = al(o + 64);
+  ws->kept = (uint16_t *)(m + o); o = al(o + (size_t)batch * pl.nlevels * orb_retain_max() * 2);
+  ws->kept_cnt = (int32_t *)(m + o); o = al(o + (size_t)batch * pl.nlevels * 4);
   ws->tables = (int32_t *)(m + o);
   ws->planes = (uint8_t *)ctx->orb_planes.p;
   ws->staging = (uint32_t *)ctx->orb_cand.p;
@@ -211,10 +216,13 @@ std::vector<int> grid_select(int n, GetXY xy, int rows, int cols, int grid, int 
   return keep;
 }
 
+std::atomic<uint64_t> g_host_fallbacks{0};
+
 // Host retainBest + grid selection for one overflowing frame; uploads the selection list.
 int slow_path_frame(mvo_ctx *ctx, const OrbPlanDev &pl, const OrbWs &ws, int f, const OrbFrameMeta &meta,
                     std::vector<uint32_t> &cand, std::vector<float> &harris, int *n_sel_out) {
   const int n = std::min(meta.n_cand, pl.cand_cap);
+  g_host_fallbacks.fetch_add(1);
   cand.resize(n);
   harris.resize(n);
   if (n) {
@@ -260,6 +268,10 @@ int run_detect(mvo_ctx *ctx, OrbState *st, const OrbWs &ws, const uint8_t *d_in,
   MVO_TRY(orb_launch_pyramid(ctx, pl, ws.tables, ws.planes, batch));
   MVO_TRY(orb_launch_fast(ctx, pl, ws.planes, ws.staging, ws.bandcnt, batch));
   MVO_TRY(orb_launch_select(ctx, pl, ws.staging, ws.bandcnt, ws.cand, ws.sel, ws.meta, batch));
+  // frames with a level above OpenCV's featuresPerLevel: Harris response of every candidate, retainBest (twice per level) and
+  // the grid selection on the device; both kernels return at once for the other frames
+  MVO_TRY(orb_launch_harris_all(ctx, pl, ws.planes, ws.cand, ws.meta, ws.harris, batch));
+  MVO_TRY(orb_launch_retain(ctx, pl, ws.cand, ws.harris, ws.meta, ws.kept, ws.kept_cnt, ws.sel, batch));
   return MVO_OK;
 }
 
@@ -362,11 +374,10 @@ int extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc, co
   OrbState *st = state_of(ctx);
   const OrbPlanDev &pl = st->plan;
   int n = pd->h_meta->n_sel;
-  if (pd->h_meta->overflow) {
-    // some level exceeds featuresPerLevel: OpenCV's retainBest (libstdc++ nth_element) decides
-    // both the surviving set and its ORDER, which the first-come grid selection depends on.
+  if (pd->h_meta->overflow == 2) {
+    // a level exceeds featuresPerLevel AND the device retainBest declined (more candidates than it holds, or an input on
+    // which libstdc++'s nth_element leaves quickselect for heap-select): the host runs the real std::nth_element
     OrbFrameMeta meta = *pd->h_meta;
-    MVO_TRY(orb_launch_harris_all(ctx, pl, pd->ws.planes, pd->ws.cand, pd->ws.meta, pd->ws.harris, 1));
     std::vector<uint32_t> cand;
     std::vector<float> harris;
     MVO_TRY(slow_path_frame(ctx, pl, pd->ws, 0, meta, cand, harris, &n));
@@ -440,6 +451,9 @@ void orb_state_free(mvo_ctx *ctx) {
 }
 
 extern "C" {
+
+// test hook (not part of mvo.h): frames whose retainBest ran on the host because the device path declined
+uint64_t mvo_test_orb_host_fallbacks(void) { return g_host_fallbacks.load(); }
 
 int mvo_calc_keypoints(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
                        mvo_keypoint *kpts, int *n_kpts) {
@@ -524,16 +538,15 @@ int mvo_orb_extract_batch_dev(mvo_ctx *ctx, const uint8_t *d_images, int batch, 
   MVO_CUDA(ctx, cudaMemcpyAsync(hm, ws.meta, (size_t)batch * sizeof(OrbFrameMeta), cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   bool any = false;
-  for (int f = 0; f < batch; ++f) any |= hm[f].overflow != 0;
+  for (int f = 0; f < batch; ++f) any |= hm[f].overflow == 2;      // the device retainBest declined (see extract_end)
   if (!any) return MVO_OK;
-  MVO_TRY(orb_launch_harris_all(ctx, pl, ws.planes, ws.cand, ws.meta, ws.harris, batch));
   std::vector<int32_t> ns(batch);
   std::vector<uint32_t> cand;
   std::vector<float> harris;
   std::vector<OrbFrameMeta> metas(hm, hm + batch);
   for (int f = 0; f < batch; ++f) {
     ns[f] = metas[f].n_sel;
-    if (metas[f].overflow) MVO_TRY(slow_path_frame(ctx, pl, ws, f, metas[f], cand, harris, &ns[f]));
+    if (metas[f].overflow == 2) MVO_TRY(slow_path_frame(ctx, pl, ws, f, metas[f], cand, harris, &ns[f]));
   }
   MVO_CUDA(ctx, cudaMemcpyAsync(ws.n_override, ns.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,28 @@
+"""One pass of the device-resident state machine over the bench sequence (images resident in HBM) — target command for
+ncu captures and for MVO_VO_DEBUG=1 stage timing.  Usage: python tools/dev_vo_pass.py [n_frames] [passes]"""
+import sys
+import time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "monocular-visual-odometry_b200" / "python")); sys.path.insert(0, str(ROOT))
+import numpy as np, torch, mvo_b200, mvo_synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+frames, truth = mvo_synth.cached_room_loop_sequence(0, 150)
+imgs = [mvo_synth.gray_to_bgr(f) for f in frames[:n]]
+ctx = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
+vo = mvo_b200.VisualOdometry(ctx, mvo_synth.K_DEFAULT, 480, 640)
+d = [torch.from_numpy(im).cuda() for im in imgs]
+torch.cuda.synchronize()
+for p in range(passes):
+    vo.reset()
+    t0 = time.perf_counter()
+    vo.prefetch(d[0].data_ptr(), channels=3, stride=1920, on_device=True)
+    kf = 0
+    for i in range(n):
+        if i + 1 < n:
+            vo.prefetch(d[i + 1].data_ptr(), channels=3, stride=1920, on_device=True)
+        T, info = vo.add_frame(d[i].data_ptr(), channels=3, stride=1920, on_device=True)
+        kf += info.keyframe
+    dt = time.perf_counter() - t0
+    print(f"pass {p}: {n} frames in {1e3 * dt:.1f} ms = {n / dt:.0f} fps, keyframes {kf}, state {info.state_out}, map {info.map_points}", flush=True)
