@@ -791,9 +791,8 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
     }
     if (rank == 0 && tid == 0) {
       a.st.out_info[0] = F;
-      int E = 0;
-      for (int f = 0; f < F; ++f) { E += s_fcnt[f]; a.st.out_info[2 + f] = s_fslot[f]; }
-      a.st.out_info[1] = E;
+      for (int f = 0; f < F; ++f) a.st.out_info[2 + f] = s_fslot[f];
+      a.st.out_info[1] = 0;                   // edges to map points that still exist, counted after the first cluster barrier
     }
   }
   const int NV = F * PF_V;
@@ -809,6 +808,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   if (STORE) { for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.st.pose[(size_t)s_fslot[i / 12] * 12 + i % 12]; }
   else { for (int i = tid; i < F * 12; i += PF_T) s_pose[i] = a.poses[i]; }
   for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
+  int my_edges = 0;
   if (STORE) {                               // this thread's chunk: gather the (fixed) map points of its observations
     const int c = (int)rank * PF_T + tid;
     int f = -1;
@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
           const float *mp = a.st.map_pts + 3 * (size_t)id;
           const float2 ob = a.st.edge_obs[o];
           X0 = mp[0]; X1 = mp[1]; X2 = mp[2]; ou = ob.x; ov = ob.y;
+          ++my_edges;
         }
       }
       ed[0] = X0; ed[PF_T] = X1; ed[2 * PF_T] = X2; ed[3 * PF_T] = ou; ed[4 * PF_T] = ov;
@@ -866,6 +867,11 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   double *p_cur = s_pose, *p_try = s_try;    // poses ping-pong like the linearisations
   pose_pass<CH, CACHED>(a, F, nchunks, p_cur, s_ed, s_ef, s_wacc, parity ? s_part1 : s_part0, rank, csize);
   gather(s_cur);
+  if (STORE) {                               // behind the cluster barrier of the gather: out_info[1] has been zeroed
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_edges += __shfl_xor_sync(0xffffffffu, my_edges, o);
+    if ((tid & 31) == 0 && my_edges) atomicAdd(&a.st.out_info[1], my_edges);
+  }
   if (tid == 0) {
     double chi = 0, md = 0;
     for (int f = 0; f < F; ++f) {

@@ -123,6 +123,9 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   { KTimer kt(ctx, KC_EPI_FINISH);
   k_epi_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dcnt, dout, dout_i, dinl); }
   MVO_CHECK_LAUNCH(ctx);
+  { KTimer kt(ctx, KC_EPI);
+  k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl); }
+  MVO_CHECK_LAUNCH(ctx);
   double *h_out = (double *)(h + al((size_t)n * 16));
   int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
@@ -147,7 +150,18 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
                     h_i[3], h_i[4], ni);
   }
   if (ni > *n_inliers) return mvo_fail(ctx, MVO_ERR_CAPACITY, "inlier capacity %d < %d", *n_inliers, ni);
-  memcpy(E, h_out, 72); memcpy(R, h_out + 9, 72); memcpy(t, h_out + 18, 24);
+  // recoverPose's choice among (R1,t) (R2,t) (R1,-t) (R2,-t), OpenCV's order: the first candidate whose vote count is a maximum
+  const int32_t *g = h_i + 8;
+  int pick = 3;
+  if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
+  else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
+  else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
+  h_i[2] = g[pick];
+  const double *tt = h_out + 27, sg = pick < 2 ? 1.0 : -1.0;
+  const double nt = sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);                 // t /= |t| (epipolar_geometry.cpp:54-55)
+  memcpy(E, h_out, 72);
+  memcpy(R, h_out + ((pick & 1) ? 18 : 9), 72);
+  for (int q = 0; q < 3; ++q) t[q] = sg * tt[q] / nt;
   memcpy(inliers, h_inl, (size_t)ni * 4);
   *n_inliers = ni;
   return MVO_OK;

@@ -124,7 +124,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
              const double *__restrict__ Es, const int32_t *__restrict__ counts, double *__restrict__ out_d,
              int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
   __shared__ long long s_k[32];
-  __shared__ int s_best, s_cnt[32], s_good[4][32], s_stop;
+  __shared__ int s_best, s_cnt[32], s_stop;
   __shared__ double s_E[9], s_R1[9], s_R2[9], s_t[3], s_R[9], s_E0[9];
   __shared__ double s_Ek[6][9], s_red[32][20], s_sum[20];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -273,54 +273,51 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   __syncthreads();                                   // also publishes R1, R2, t
   int off = incl - mine, n_in = 0;
   for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
-  // recoverPose (calib3d five-point.cpp): triangulate every inlier with [I|0] and each of (R1,t) (R2,t) (R1,-t) (R2,-t);
-  // a point votes for a candidate when its depth is in (0, 50) in both cameras
-  int good[4] = {0, 0, 0, 0};
-  const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  // the consensus set, ascending; the cheirality vote of recoverPose runs in k_epi_vote (all SMs) and the host picks
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
     const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-    if (!(epi::sampson_err(E, x1, y1, x2, y2) <= thr2)) continue;
-    inl[off++] = i;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const double *R = (c & 1) ? s_R2 : s_R1;
-      const double sg = c < 2 ? 1.0 : -1.0;
-      double P[12];
-      for (int r = 0; r < 3; ++r) { P[4 * r] = R[3 * r]; P[4 * r + 1] = R[3 * r + 1]; P[4 * r + 2] = R[3 * r + 2]; P[4 * r + 3] = sg * s_t[r]; }
-      double X[4];
-      epi::triangulate_dlt(P0, P, x1, y1, x2, y2, X);
-      bool ok = X[2] * X[3] > 0;                     // mask = Q.z * Q.w > 0
-      const double z1 = X[2] / X[3];
-      ok = ok && z1 < 50.0;                          // distanceThresh
-      const double z2 = (P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * X[3]) / X[3];
-      ok = ok && z2 > 0 && z2 < 50.0;
-      good[c] += ok;
-    }
+    if (epi::sampson_err(E, x1, y1, x2, y2) <= thr2) inl[off++] = i;
   }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    int g = good[c];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffffffu, g, d);
-    if (lane == 0) s_good[c][warp] = g;
-  }
-  __syncthreads();
   if (tid == 0) {
-    int g[4] = {0, 0, 0, 0};
-    for (int c = 0; c < 4; ++c) for (int w = 0; w < 32; ++w) g[c] += s_good[c][w];
-    // OpenCV's order: (R1,t) if good1 is a maximum, else (R2,t), else (R1,-t), else (R2,-t)
-    int pick = 3;
-    if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
-    else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
-    else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
-    const double *R = (pick & 1) ? s_R2 : s_R1;
-    const double sg = pick < 2 ? 1.0 : -1.0;
     const double e22 = s_E[8];
-    for (int q = 0; q < 9; ++q) { out_d[q] = s_E[q] / e22; out_d[9 + q] = R[q]; }       // E /= E(2,2) (:37)
-    const double nt = sqrt(s_t[0] * s_t[0] + s_t[1] * s_t[1] + s_t[2] * s_t[2]);          // t /= |t| (:54-55)
-    for (int q = 0; q < 3; ++q) out_d[18 + q] = sg * s_t[q] / nt;
-    out_i[0] = n_in; out_i[1] = s_best; out_i[2] = g[pick];
+    for (int q = 0; q < 9; ++q) { out_d[q] = s_E[q] / e22; out_d[9 + q] = s_R1[q]; out_d[18 + q] = s_R2[q]; }       // E /= E(2,2) (:37)
+    for (int q = 0; q < 3; ++q) out_d[27 + q] = s_t[q];
+    out_i[0] = n_in; out_i[1] = s_best;
+    out_i[8] = out_i[9] = out_i[10] = out_i[11] = 0;                      // votes, accumulated by k_epi_vote
+  }
+}
+
+// recoverPose (calib3d five-point.cpp): triangulate every inlier with [I|0] and each of (R1,t) (R2,t) (R1,-t) (R2,-t); a point
+// votes for a candidate when its depth is in (0, 50) in both cameras.  One thread per (inlier, candidate); out_i[8 + c] += votes.
+__global__ void __launch_bounds__(256)
+k_epi_vote(const float *__restrict__ p1, const float *__restrict__ p2, EpiCam cam, const double *__restrict__ out_d,
+           int32_t *__restrict__ out_i, const int32_t *__restrict__ inl) {
+  const int n_in = out_i[0];
+  const int j = blockIdx.x * 64 + (threadIdx.x >> 2), c = threadIdx.x & 3;
+  bool ok = false;
+  if (j < n_in) {
+    const int i = inl[j];
+    const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
+    const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
+    const double *R = out_d + ((c & 1) ? 18 : 9);
+    const double sg = c < 2 ? 1.0 : -1.0;
+    const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    double P[12];
+    for (int r = 0; r < 3; ++r) { P[4 * r] = R[3 * r]; P[4 * r + 1] = R[3 * r + 1]; P[4 * r + 2] = R[3 * r + 2]; P[4 * r + 3] = sg * out_d[27 + r]; }
+    double X[4];
+    epi::triangulate_dlt(P0, P, x1, y1, x2, y2, X);
+    ok = X[2] * X[3] > 0;                            // mask = Q.z * Q.w > 0
+    const double z1 = X[2] / X[3];
+    ok = ok && z1 < 50.0;                            // distanceThresh
+    const double z2 = (P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * X[3]) / X[3];
+    ok = ok && z2 > 0 && z2 < 50.0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  const int lane = threadIdx.x & 31;
+  if (lane < 4) {                                    // lanes c, c + 4, ... hold candidate c
+    const int votes = __popc(m & (0x11111111u << lane));
+    if (votes) atomicAdd(&out_i[8 + lane], votes);
   }
 }
 

@@ -164,6 +164,7 @@ struct MvoTrackGlue {
 int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,
                           int rows, int cols, uint8_t *d_vis, float *d_cxy);
 int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_xy);
+int mvo_track_kpt_colors(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, const uint8_t *d_image, int channels, size_t stride, uint8_t *d_rgb);
 int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const int32_t *d_n, const float *d_map_pts,
                            const mvo_keypoint *d_kpts, float *d_p3, float *d_p2);
 int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g);
@@ -187,7 +188,7 @@ int mvo_trk_device_mode(const mvo_tracker *t);
 void mvo_trk_configure(mvo_tracker *t, int external_ref, int count_stats);
 int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device, int *slot, int *nk);
 void mvo_trk_release(mvo_tracker *t, int slot);
-int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc);
+int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc, uint8_t *rgb);
 const uint8_t *mvo_trk_desc_dev(mvo_tracker *t, int slot);
 unsigned mvo_trk_slot_serial(const mvo_tracker *t, int slot);
 int mvo_trk_set_map_ids(mvo_tracker *t, const float *pts3d, const uint8_t *desc, const int32_t *ids, int n, int reset_ids);

@@ -35,6 +35,17 @@ k_kpt_xy(const mvo_keypoint *__restrict__ kpts, int n, float2 *__restrict__ xy) 
   if (i < n) xy[i] = make_float2(kpts[i].x, kpts[i].y);
 }
 
+// Frame::calcDescriptors' colour sampling (frame.h:80-84, basics::getPixelAt): {r, g, b} of pixel (floor x, floor y)
+__global__ void __launch_bounds__(256)
+k_kpt_colors(const mvo_keypoint *__restrict__ kpts, int n, const uint8_t *__restrict__ image, int channels, size_t stride, uint8_t *__restrict__ rgb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)floorf(kpts[i].x), y = (int)floorf(kpts[i].y);
+  const uint8_t *px = image + (size_t)y * stride + (size_t)x * channels;
+  if (channels == 3) { rgb[3 * i] = px[2]; rgb[3 * i + 1] = px[1]; rgb[3 * i + 2] = px[0]; }
+  else { rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = px[0]; }
+}
+
 __global__ void __launch_bounds__(256)
 k_gather_pairs(const int2 *__restrict__ pairs, int n, const int32_t *__restrict__ n_dev, const float *__restrict__ map_pts,
                const mvo_keypoint *__restrict__ kpts, float *__restrict__ p3, float *__restrict__ p2) {
@@ -124,6 +135,14 @@ int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const 
   KTimer kt(ctx, KC_TRACK);
   k_project_map<<<(nmap + 255) / 256, 256, 0, ctx->stream>>>(d_map_pts, nmap, T, K[0], K[4], K[2], K[5], (float)cols, (float)rows,
                                                                d_vis, (float2 *)d_cxy);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
+
+int mvo_track_kpt_colors(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, const uint8_t *d_image, int channels, size_t stride, uint8_t *d_rgb) {
+  if (n <= 0) return MVO_OK;
+  KTimer kt(ctx, KC_TRACK);
+  k_kpt_colors<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_kpts, n, d_image, channels, stride, d_rgb);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

@@ -661,20 +661,35 @@ void mvo_trk_configure(mvo_tracker *t, int external_ref, int count_stats) {
   t->count_stats = count_stats != 0;
 }
 
-// keypoints / descriptors of an acquired frame -> host (the device buffers stay valid until the slot is released)
-int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc) {
+// keypoints / descriptors (/ colours, for an image in device memory: rgb != nullptr) of an acquired frame -> host, through a
+// page-locked staging buffer (the device buffers stay valid until the slot is released)
+int mvo_trk_fetch(mvo_tracker *t, int slot, mvo_keypoint *kpts, uint8_t *desc, uint8_t *rgb) {
   mvo_ctx *ctx = t->ctx;
   ExtractJob &job = t->job[slot];
   if (job.want_host) {
     if (kpts && job.nk) memcpy(kpts, job.kpts.data(), (size_t)job.nk * sizeof(mvo_keypoint));
     if (desc && job.nk) memcpy(desc, job.desc.data(), (size_t)job.nk * 32);
+    if (rgb) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "tracker: colours of a host-path frame are sampled by the caller");
     return MVO_OK;
   }
-  if (job.nk <= 0) return MVO_OK;
+  const int n = job.nk;
+  if (n <= 0) return MVO_OK;
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (kpts) MVO_CUDA(ctx, cudaMemcpyAsync(kpts, job.d_k, (size_t)job.nk * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-  if (desc) MVO_CUDA(ctx, cudaMemcpyAsync(desc, job.d_d, (size_t)job.nk * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t o_d = al256((size_t)n * sizeof(mvo_keypoint)), o_c = o_d + al256((size_t)n * 32), tot = o_c + al256((size_t)n * 3);
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, tot));
+  uint8_t *h = (uint8_t *)ctx->h_b.p;
+  if (kpts) MVO_CUDA(ctx, cudaMemcpyAsync(h, job.d_k, (size_t)n * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (desc) MVO_CUDA(ctx, cudaMemcpyAsync(h + o_d, job.d_d, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rgb) {
+    if (!job.on_device) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: the image of this frame is in host memory");
+    MVO_TRY(mvo_reserve(ctx, ctx->d_f, (size_t)n * 3 + 256));
+    MVO_TRY(mvo_track_kpt_colors(ctx, job.d_k, n, job.image, job.channels, job.stride, (uint8_t *)ctx->d_f.p));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_c, ctx->d_f.p, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (kpts) memcpy(kpts, h, (size_t)n * sizeof(mvo_keypoint));
+  if (desc) memcpy(desc, h + o_d, (size_t)n * 32);
+  if (rgb) memcpy(rgb, h + o_c, (size_t)n * 3);
   return MVO_OK;
 }
 

@@ -216,8 +216,8 @@ int extract(mvo_vo *v, VoFrame *f, const uint8_t *image, int channels, size_t st
   f->desc.resize((size_t)n * 32);
   f->xy.resize((size_t)n * 2);
   for (int i = 0; i < n; ++i) { f->xy[2 * i] = f->kpts[i].x; f->xy[2 * i + 1] = f->kpts[i].y; }
-  const uint8_t *himg;
-  size_t hstride;
+  const uint8_t *himg = nullptr;
+  size_t hstride = 0;
   MVO_TRY(host_image(v, &himg, &hstride));
   sample_colors(f, himg, channels, hstride);
   return MVO_OK;
@@ -230,17 +230,13 @@ int ensure_host(mvo_vo *v, VoFrame *f) {
     return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: frame %d has left the device (its keypoints are kept for two frames unless it is a keyframe)", f->id);
   f->kpts.resize((size_t)f->nk);
   f->desc.resize((size_t)f->nk * 32);
-  MVO_TRY(mvo_trk_fetch(v->trk, f->slot, f->kpts.data(), f->desc.data()));
+  f->colors.assign((size_t)f->nk * 3, 0);
+  const bool cur = f == v->curr.get() && v->cur_image;
+  // an image in device memory: the colours are gathered there (a few KB) instead of copying the image back
+  MVO_TRY(mvo_trk_fetch(v->trk, f->slot, f->kpts.data(), f->desc.data(), cur && v->cur_on_device ? f->colors.data() : nullptr));
   f->xy.resize((size_t)f->nk * 2);
   for (int i = 0; i < f->nk; ++i) { f->xy[2 * i] = f->kpts[i].x; f->xy[2 * i + 1] = f->kpts[i].y; }
-  if (f == v->curr.get() && v->cur_image) {
-    const uint8_t *himg;
-    size_t hstride;
-    MVO_TRY(host_image(v, &himg, &hstride));
-    sample_colors(f, himg, v->cur_channels, hstride);
-  } else {
-    f->colors.assign((size_t)f->nk * 3, 0);
-  }
+  if (cur && !v->cur_on_device) sample_colors(f, v->cur_image, v->cur_channels, v->cur_stride);
   f->host_ready = true;
   return MVO_OK;
 }

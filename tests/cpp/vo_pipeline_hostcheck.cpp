@@ -117,7 +117,7 @@ int mvo_trk_device_mode(const mvo_tracker *) { return 0; }
 void mvo_trk_configure(mvo_tracker *, int, int) {}
 int mvo_trk_acquire(mvo_tracker *, const uint8_t *, int, size_t, int, int *, int *) { return MVO_ERR_UNSUPPORTED; }
 void mvo_trk_release(mvo_tracker *, int) {}
-int mvo_trk_fetch(mvo_tracker *, int, mvo_keypoint *, uint8_t *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_fetch(mvo_tracker *, int, mvo_keypoint *, uint8_t *, uint8_t *) { return MVO_ERR_UNSUPPORTED; }
 unsigned mvo_trk_slot_serial(const mvo_tracker *, int) { return 0; }
 int mvo_trk_set_map_ids(mvo_tracker *, const float *, const uint8_t *, const int32_t *, int, int) { return MVO_ERR_UNSUPPORTED; }
 int mvo_trk_push_frame(mvo_tracker *, const double *, const int32_t *, const int32_t *, const float *, int) { return MVO_ERR_UNSUPPORTED; }
