@@ -3,12 +3,22 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include "mvo.h"
 namespace my_slam {
 namespace basics {
 class Config {
  public:
+  // Config::setParameterFile (config.cpp:12-24): from then on the keys come from that file (the product's reader of the
+  // reference's config dialect, mvo_config_*); without it the built-in table of the shipped values below answers
+  static std::shared_ptr<mvo_config> &file() { static std::shared_ptr<mvo_config> f; return f; }
+  static void setParameterFile(const std::string &filename) {
+    mvo_config *c = nullptr;
+    if (mvo_config_load(filename.c_str(), &c) != MVO_OK) throw std::runtime_error("parameter file " + filename + " does not exist.");
+    file() = std::shared_ptr<mvo_config>(c, mvo_config_free);
+  }
   static std::map<std::string, double> &table() {
     static std::map<std::string, double> t = {
         {"number_of_keypoints_to_extract", 8000}, {"max_number_of_keypoints", 1500}, {"scale_factor", 1.2},
@@ -29,11 +39,21 @@ class Config {
     return t;
   }
   static bool getBool(const std::string &key) {                    // config.h: "true" / "True"
+    if (file()) {
+      int b = 0;
+      if (mvo_config_get_bool(file().get(), key.c_str(), &b) != MVO_OK) throw std::runtime_error("Key " + key + " doesn't exist");
+      return b != 0;
+    }
     auto it = strings().find(key);
     if (it == strings().end()) throw std::runtime_error("Key " + key + " doesn't exist");
     return it->second == "true" || it->second == "True";
   }
   template <typename T> static T get(const std::string &key) {
+    if (file()) {
+      double v = 0;
+      if (mvo_config_get_double(file().get(), key.c_str(), &v) != MVO_OK) throw std::runtime_error("Key " + key + " doesn't exist");
+      return convert<T>(v);
+    }
     auto it = table().find(key);
     if (it == table().end()) throw std::runtime_error("Key " + key + " doesn't exist");     // config.cpp:35
     return convert<T>(it->second);
@@ -45,6 +65,11 @@ class Config {
 };
 template <> inline int Config::convert<int>(double v) { return (int)std::nearbyint(v); }
 template <> inline std::string Config::get<std::string>(const std::string &key) {
+  if (file()) {
+    char buf[4096];
+    if (mvo_config_get_string(file().get(), key.c_str(), buf, sizeof buf) != MVO_OK) throw std::runtime_error("Key " + key + " doesn't exist");
+    return buf;
+  }
   auto it = strings().find(key);
   if (it == strings().end()) throw std::runtime_error("Key " + key + " doesn't exist");
   return it->second;
