@@ -64,7 +64,7 @@ k_epi_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, E
   }
 }
 
-constexpr int EFIN_T = 1024;
+constexpr int EFIN_T = 256;       // 255 registers per thread: the 20 (54) Gauss-Newton accumulators stay in registers (1024 threads = 64 registers spilled them)
 constexpr int EPI_LO_ROUNDS = 3, EPI_GN_ITERS = 8;
 
 __device__ __forceinline__ void skew_times(const double *t, const double *R, double *E) {      // E = [t]x R
@@ -139,7 +139,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   __syncthreads();
   if (tid == 0) {
     long long b = -1;
-    for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
+    for (int w = 0; w < EFIN_T / 32; ++w) b = s_k[w] > b ? s_k[w] : b;
     s_best = (int)(b >> 20) >= 8 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
     out_i[3] = (int)(b >> 20);
   }
@@ -197,7 +197,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
         if (lane == 0) s_red[warp][q] = v;
       }
       __syncthreads();
-      if (tid < 20) { double v = 0; for (int w = 0; w < 32; ++w) v += s_red[w][tid]; s_sum[tid] = v; }
+      if (tid < 20) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += s_red[w][tid]; s_sum[tid] = v; }
       __syncthreads();
       if (tid == 0) {
         // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
@@ -250,7 +250,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
-      for (int w = 0; w < 32; ++w) tot += s_cnt[w];
+      for (int w = 0; w < EFIN_T / 32; ++w) tot += s_cnt[w];
       out_i[4] = tot;
       if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_E[q] = s_E0[q];
     }
@@ -272,7 +272,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   if (lane == 31) s_cnt[warp] = incl;
   __syncthreads();                                   // also publishes R1, R2, t
   int off = incl - mine, n_in = 0;
-  for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
   // the consensus set, ascending; the cheirality vote of recoverPose runs in k_epi_vote (all SMs) and the host picks
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
@@ -421,7 +421,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   __syncthreads();
   if (tid == 0) {
     long long b = -1;
-    for (int w = 0; w < 32; ++w) b = s_k[w] > b ? s_k[w] : b;
+    for (int w = 0; w < EFIN_T / 32; ++w) b = s_k[w] > b ? s_k[w] : b;
     s_best = (int)(b >> 20) >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
     out_i[3] = (int)(b >> 20);
   }
@@ -459,7 +459,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
         if (lane == 0) s_red[warp][q] = vq;
       }
       __syncthreads();
-      if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
+      if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < EFIN_T / 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
       __syncthreads();
       if (tid == 0) {
         double Hn[9];
@@ -486,7 +486,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
-      for (int w = 0; w < 32; ++w) tot += s_cnt[w];
+      for (int w = 0; w < EFIN_T / 32; ++w) tot += s_cnt[w];
       out_i[4] = tot;
       if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_H[q] = s_H0[q];
     }
@@ -508,7 +508,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   if (lane == 31) s_cnt[warp] = incl;
   __syncthreads();
   int off = incl - mine, n_in = 0;
-  for (int w = 0; w < 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
     const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;

@@ -429,19 +429,105 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
 //     the frame for the host path (adversarial inputs only).
 //   partition (bidirectional): the k-th swap pairs the k-th element from the left that fails the predicate with the k-th
 //     element from the right that passes it, while the former lies left of the latter; new end = begin + #passing.
-// One warp per (level, frame); the level's records live in shared memory (response 4 B + index 2 B + the two stop lists).
+// One CTA of RET_T threads per (level, frame); the level's records live in shared memory (response 4 B + index 2 B + the two
+// stop lists).  Ranges of RET_WARP_LEN elements or more are scanned by the whole CTA (every warp lists the stops of its chunk,
+// a prefix over the warps places them), shorter ones by warp 0 alone.
 constexpr int RET_MAX = 12288;       // candidates of one level the device path holds; more -> host path
+constexpr int RET_T = 256, RET_W = RET_T / 32;
+constexpr int RET_WARP_LEN = 768;
 
-struct RetBuf { float *key; uint16_t *idx, *Ls, *Rs; };
+struct RetBuf { float *key; uint16_t *idx, *Ls, *Rs; int *s_i; };   // s_i: 2 * RET_W + 8 ints of block scratch
 
 __device__ __forceinline__ void ret_swap(const RetBuf &b, int x, int y) {
   const float k = b.key[x]; b.key[x] = b.key[y]; b.key[y] = k;
   const uint16_t i = b.idx[x]; b.idx[x] = b.idx[y]; b.idx[y] = i;
 }
 
-// std::__unguarded_partition_pivot(first, last, greater) by one warp; returns the cut
-__device__ int ret_partition_pivot(const RetBuf &b, int first, int last, int lane) {
-  if (lane == 0) {                       // __move_median_to_first(first, first + 1, mid, last - 1), comp(a, b) = a > b
+// The two stop lists of a scan pair over positions lo .. lo + len - 1 (left list, ascending) and top .. top - len + 1 (right
+// list, descending): Ls[lo + k] = k-th position from the left with left(key), Rs[lo + k] = k-th from the right with right(key).
+// WHOLE: all RET_W warps take part (block barriers inside); otherwise the calling warp works alone.
+template <bool WHOLE, class FL, class FR>
+__device__ __forceinline__ void ret_stop_lists(const RetBuf &b, int lo, int len, int top, FL left, FR right, int &nL, int &nR) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned below = (1u << lane) - 1u;
+  if (!WHOLE) {
+    nL = nR = 0;
+    for (int base = 0; base < len; base += 32) {
+      const int i = base + lane;
+      const bool inr = i < len;
+      const bool ls = inr && left(b.key[lo + i]), rs = inr && right(b.key[top - i]);
+      const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
+      if (ls) b.Ls[lo + nL + __popc(bl & below)] = (uint16_t)(lo + i);
+      if (rs) b.Rs[lo + nR + __popc(br & below)] = (uint16_t)(top - i);
+      nL += __popc(bl);
+      nR += __popc(br);
+    }
+    __syncwarp();
+    return;
+  }
+  const int chunk = ((len + RET_T - 1) / RET_T) * 32;               // per warp, a multiple of 32
+  const int c0 = min(warp * chunk, len), c1 = min(c0 + chunk, len);
+  int cl = 0, cr = 0;
+  for (int base = c0; base < c1; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < c1;
+    cl += __popc(__ballot_sync(0xffffffffu, inr && left(b.key[lo + i])));
+    cr += __popc(__ballot_sync(0xffffffffu, inr && right(b.key[top - i])));
+  }
+  if (lane == 0) { b.s_i[warp] = cl; b.s_i[RET_W + warp] = cr; }
+  __syncthreads();
+  int oL = 0, oR = 0;
+  nL = nR = 0;
+  for (int w = 0; w < RET_W; ++w) { if (w < warp) { oL += b.s_i[w]; oR += b.s_i[RET_W + w]; } nL += b.s_i[w]; nR += b.s_i[RET_W + w]; }
+  for (int base = c0; base < c1; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < c1;
+    const bool ls = inr && left(b.key[lo + i]), rs = inr && right(b.key[top - i]);
+    const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
+    if (ls) b.Ls[lo + oL + __popc(bl & below)] = (uint16_t)(lo + i);
+    if (rs) b.Rs[lo + oR + __popc(br & below)] = (uint16_t)(top - i);
+    oL += __popc(bl);
+    oR += __popc(br);
+  }
+  __syncthreads();
+}
+
+// the swaps of a Hoare-style scan pair: pairs (Ls[k], Rs[k]) while Ls[k] < Rs[k]; returns their number K
+template <bool WHOLE>
+__device__ __forceinline__ int ret_swap_pairs(const RetBuf &b, int lo, int nmin) {
+  const int lane = threadIdx.x & 31;
+  int K = 0;
+  if (!WHOLE) {
+    for (int base = 0; base < nmin; base += 32) {
+      const int j = base + lane;
+      const bool sw = j < nmin && b.Ls[lo + j] < b.Rs[lo + j];
+      const unsigned m = __ballot_sync(0xffffffffu, sw);
+      if (sw) ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]);
+      const int c = __popc(m);
+      K += c;
+      if (c < 32) break;
+    }
+    __syncwarp();
+    return K;
+  }
+  if (threadIdx.x == 0) b.s_i[2 * RET_W] = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int j = threadIdx.x; j < nmin; j += RET_T)                   // Ls ascends, Rs descends: the condition holds on a prefix
+    if (b.Ls[lo + j] < b.Rs[lo + j]) { ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]); ++mine; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0 && mine) atomicAdd(&b.s_i[2 * RET_W], mine);
+  __syncthreads();
+  K = b.s_i[2 * RET_W];
+  __syncthreads();
+  return K;
+}
+
+// std::__unguarded_partition_pivot(first, last, greater); returns the cut.  Uniform over the calling group.
+template <bool WHOLE>
+__device__ int ret_partition_pivot(const RetBuf &b, int first, int last) {
+  if (threadIdx.x == 0) {                // __move_median_to_first(first, first + 1, mid, last - 1), comp(a, b) = a > b
     const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
     const float ka = b.key[ia], kb = b.key[ib], kc = b.key[ic];
     int pick;
@@ -449,45 +535,25 @@ __device__ int ret_partition_pivot(const RetBuf &b, int first, int last, int lan
     else pick = (ka > kc) ? ia : ((kb > kc) ? ic : ib);
     ret_swap(b, first, pick);
   }
-  __syncwarp();
+  if (WHOLE) __syncthreads(); else __syncwarp();
   const float pivot = b.key[first];
   const int lo = first + 1, len = last - lo;
-  int nL = 0, nR = 0;
-  for (int base = 0; base < len; base += 32) {
-    const int i = base + lane;
-    const bool inr = i < len;
-    const bool ls = inr && !(b.key[lo + i] > pivot);              // the left scan `while (*first > pivot) ++first` stops here
-    const bool rs = inr && !(pivot > b.key[last - 1 - i]);        // the right scan `while (pivot > *last) --last` stops here
-    const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
-    const unsigned below = (1u << lane) - 1u;
-    if (ls) b.Ls[lo + nL + __popc(bl & below)] = (uint16_t)(lo + i);
-    if (rs) b.Rs[lo + nR + __popc(br & below)] = (uint16_t)(last - 1 - i);
-    nL += __popc(bl);
-    nR += __popc(br);
-  }
-  __syncwarp();
-  const int nmin = min(nL, nR);
-  int K = 0;
-  for (int base = 0; base < nmin; base += 32) {
-    const int j = base + lane;
-    const bool sw = j < nmin && b.Ls[lo + j] < b.Rs[lo + j];
-    const unsigned m = __ballot_sync(0xffffffffu, sw);
-    if (sw) ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]);
-    const int c = __popc(m);
-    K += c;
-    if (c < 32) break;
-  }
-  __syncwarp();
+  int nL, nR;
+  // the left scan `while (*first > pivot) ++first` stops at !(key > pivot); the right scan `while (pivot > *last) --last` at !(pivot > key)
+  ret_stop_lists<WHOLE>(b, lo, len, last - 1, [pivot](float k) { return !(k > pivot); }, [pivot](float k) { return !(pivot > k); }, nL, nR);
+  const int K = ret_swap_pairs<WHOLE>(b, lo, min(nL, nR));
   int cut;
   if (K == 0) cut = nL > 0 ? (int)b.Ls[lo] : last;
   else { cut = (int)b.Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)b.Ls[lo + K]); }
   return cut;
 }
 
-// cv::KeyPointsFilter::retainBest on b.key / b.idx [0, n): returns the new size, or -1 where libstdc++ would heap-select
-__device__ int ret_retain_best(const RetBuf &b, int n, int npts, int lane) {
+// cv::KeyPointsFilter::retainBest on b.key / b.idx [0, n): returns the new size, or -1 where libstdc++ would heap-select.
+// Called by the whole CTA; n, npts uniform.
+__device__ int ret_retain_best(const RetBuf &b, int n, int npts) {
   if (npts < 0 || n <= npts) return n;
   if (npts == 0) return 0;
+  const int warp = threadIdx.x >> 5;
   // std::nth_element(begin, begin + npts - 1, end)
   {
     int first = 0, last = n;
@@ -498,10 +564,17 @@ __device__ int ret_retain_best(const RetBuf &b, int n, int npts, int lane) {
     while (last - first > 3) {
       if (depth == 0) return -1;
       --depth;
-      const int cut = ret_partition_pivot(b, first, last, lane);
+      int cut;
+      if (last - first >= RET_WARP_LEN) cut = ret_partition_pivot<true>(b, first, last);
+      else {
+        if (warp == 0) { cut = ret_partition_pivot<false>(b, first, last); if (threadIdx.x == 0) b.s_i[2 * RET_W + 1] = cut; }
+        __syncthreads();
+        cut = b.s_i[2 * RET_W + 1];
+        __syncthreads();
+      }
       if (cut <= nth) first = cut; else last = cut;
     }
-    if (lane == 0) {                     // __insertion_sort(first, last, greater)
+    if (threadIdx.x == 0) {              // __insertion_sort(first, last, greater)
       for (int i = first + 1; i < last; ++i) {
         const float v = b.key[i];
         const uint16_t vi = b.idx[i];
@@ -515,78 +588,62 @@ __device__ int ret_retain_best(const RetBuf &b, int n, int npts, int lane) {
         }
       }
     }
-    __syncwarp();
+    __syncthreads();
   }
-  // std::partition(begin + npts, end, response >= ambiguous)
+  // std::partition(begin + npts, end, response >= ambiguous): the k-th element from the left that fails is swapped with the
+  // k-th from the right that passes while it lies left of it; new end = begin + npts + #passing
   const float amb = b.key[npts - 1];
-  const int lo = npts, len = n - npts;
-  int nF = 0, nT = 0;
-  for (int base = 0; base < len; base += 32) {
-    const int i = base + lane;
-    const bool inr = i < len;
-    const bool fl = inr && !(b.key[lo + i] >= amb);               // from the left: fails the predicate
-    const bool tr = inr && (b.key[n - 1 - i] >= amb);             // from the right: passes it
-    const unsigned bf = __ballot_sync(0xffffffffu, fl), bt = __ballot_sync(0xffffffffu, tr);
-    const unsigned below = (1u << lane) - 1u;
-    if (fl) b.Ls[lo + nF + __popc(bf & below)] = (uint16_t)(lo + i);
-    if (tr) b.Rs[lo + nT + __popc(bt & below)] = (uint16_t)(n - 1 - i);
-    nF += __popc(bf);
-    nT += __popc(bt);
-  }
-  __syncwarp();
-  const int nmin = min(nF, nT);
-  for (int base = 0; base < nmin; base += 32) {
-    const int j = base + lane;
-    const bool sw = j < nmin && b.Ls[lo + j] < b.Rs[lo + j];
-    const unsigned m = __ballot_sync(0xffffffffu, sw);
-    if (sw) ret_swap(b, b.Ls[lo + j], b.Rs[lo + j]);
-    if (__popc(m) < 32) break;
-  }
-  __syncwarp();
+  int nF, nT;
+  ret_stop_lists<true>(b, npts, n - npts, n - 1, [amb](float k) { return !(k >= amb); }, [amb](float k) { return k >= amb; }, nF, nT);
+  (void)ret_swap_pairs<true>(b, npts, min(nF, nT));
   return npts + nT;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(RET_T)
 k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__restrict__ harris, OrbFrameMeta *__restrict__ meta,
          uint16_t *__restrict__ kept, int32_t *__restrict__ kept_cnt) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int l = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  __shared__ int s_scratch[2 * RET_W + 8];
+  const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
   if (meta[f].overflow == 0) return;
   RetBuf b;
   b.key = reinterpret_cast<float *>(smem);
   b.idx = reinterpret_cast<uint16_t *>(b.key + RET_MAX);
   b.Ls = b.idx + RET_MAX;
   b.Rs = b.Ls + RET_MAX;
+  b.s_i = s_scratch;
   const int n = meta[f].lvl_count[l];
   int base = 0;
   for (int q = 0; q < l; ++q) base += meta[f].lvl_count[q];
   uint16_t *out = kept + ((size_t)f * plan.nlevels + l) * RET_MAX;
   const int cap = plan.lv[l].cap;
   if (n > RET_MAX || base + n > plan.cand_cap) {           // beyond the device path: the host finishes this frame
-    if (lane == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
+    if (tid == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
     return;
   }
   if (n <= cap) {                                           // both retainBest calls are no-ops
-    for (int i = lane; i < n; i += 32) out[i] = (uint16_t)i;
-    if (lane == 0) kept_cnt[f * plan.nlevels + l] = n;
+    for (int i = tid; i < n; i += RET_T) out[i] = (uint16_t)i;
+    if (tid == 0) kept_cnt[f * plan.nlevels + l] = n;
     return;
   }
   const uint32_t *cf = cand + (size_t)f * plan.cand_cap + base;
   const float *hf = harris + (size_t)f * plan.cand_cap + base;
-  for (int i = lane; i < n; i += 32) { b.key[i] = (float)orb_ps(cf[i]); b.idx[i] = (uint16_t)i; }
-  __syncwarp();
-  int m = ret_retain_best(b, n, 2 * cap, lane);            // by FAST score
+  for (int i = tid; i < n; i += RET_T) { b.key[i] = (float)orb_ps(cf[i]); b.idx[i] = (uint16_t)i; }
+  __syncthreads();
+  int m = ret_retain_best(b, n, 2 * cap);                  // by FAST score
   if (m >= 0) {
-    for (int i = lane; i < m; i += 32) b.key[i] = hf[b.idx[i]];   // HarrisResponses of the survivors, in their order
-    __syncwarp();
-    m = ret_retain_best(b, m, cap, lane);                   // by Harris response
+    __syncthreads();
+    for (int i = tid; i < m; i += RET_T) b.key[i] = hf[b.idx[i]];   // HarrisResponses of the survivors, in their order
+    __syncthreads();
+    m = ret_retain_best(b, m, cap);                         // by Harris response
   }
   if (m < 0) {
-    if (lane == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
+    if (tid == 0) { atomicExch(&meta[f].overflow, 2); kept_cnt[f * plan.nlevels + l] = 0; }
     return;
   }
-  for (int i = lane; i < m; i += 32) out[i] = b.idx[i];
-  if (lane == 0) kept_cnt[f * plan.nlevels + l] = m;
+  __syncthreads();
+  for (int i = tid; i < m; i += RET_T) out[i] = b.idx[i];
+  if (tid == 0) kept_cnt[f * plan.nlevels + l] = m;
 }
 
 // selectUniformKptsByGrid (feature_match.cpp:51-84) over the retained lists of a frame whose levels overflowed: the closed
@@ -1047,7 +1104,7 @@ int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand
   const size_t smem = (size_t)RET_MAX * 10;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_retain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { KTimer kt(ctx, KC_SELECT);
-  k_retain<<<dim3(plan.nlevels, batch), 32, smem, ctx->stream>>>(plan, cand, harris, meta, kept, kept_cnt); }
+  k_retain<<<dim3(plan.nlevels, batch), RET_T, smem, ctx->stream>>>(plan, cand, harris, meta, kept, kept_cnt); }
   MVO_CHECK_LAUNCH(ctx);
   const int ncell = plan.grid_rows * plan.grid_cols;
   const size_t smem2 = (size_t)(2 * ncell + 1) * 4 + (size_t)plan.sel_cap * (4 + 2 + 2 + 1 + 1) + 64;
