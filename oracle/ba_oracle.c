@@ -160,6 +160,13 @@ static int inv3(const double *m, double *o) {
   return 1;
 }
 
+/* Optional trace of the Levenberg-Marquardt control flow (tests/test_ba_oracle.py compares it with the independent numpy
+ * implementation oracle/ba_g2o_trace.py): one record of 5 doubles per TRIAL — outer iteration, lambda used by the trial,
+ * robust chi2 of the trial state, gain ratio rho, accepted (1/0). */
+static double *g_trace = 0;
+static int g_trace_cap = 0, *g_trace_n = 0;
+void orc_ba_set_trace(double *buf, int cap_records, int *count) { g_trace = buf; g_trace_cap = cap_records; g_trace_n = count; if (count) *count = 0; }
+
 /* poses_T_w_c: F x 16 row-major camera->world (in/out); points: P x 3 float (in/out if update_points)
  * stats[4]: initial robust chi2, final robust chi2, outer iterations run, final lambda.
  * use_huber = 0 reproduces optimizeSingleFrame (no robust kernel). Returns 0 on success. */
@@ -331,6 +338,10 @@ int orc_bundle_adjustment(double *poses_T_w_c, int F, float *points, int P, cons
       }
       double temp_chi = ok ? robust_chi2(&pb, trial, pts_try) : 1.7976931348623157e308;
       rho = (current_chi - temp_chi) / (scale + 1e-3);
+      if (g_trace && g_trace_n && *g_trace_n < g_trace_cap) {
+        double *rec = g_trace + 5 * (*g_trace_n)++;
+        rec[0] = it; rec[1] = lambda; rec[2] = temp_chi; rec[3] = rho; rec[4] = (rho > 0 && isfinite(temp_chi)) ? 1 : 0;
+      }
       if (rho > 0 && isfinite(temp_chi)) {
         double alpha = 1. - pow(2 * rho - 1, 3);
         alpha = fmin(alpha, 2. / 3.);

@@ -128,3 +128,17 @@ def bundle_adjustment(poses_T_w_c, points, edge_frame, edge_point, obs, K, infor
     if rc != 0:
         raise RuntimeError(f"orc_bundle_adjustment failed ({rc})")
     return poses.reshape(-1, 4, 4), pts, stats
+
+
+def bundle_adjustment_with_trace(*args, max_records=4096, **kw):
+    """bundle_adjustment + the per-trial record of its Levenberg-Marquardt loop: rows (iteration, lambda, chi2 of the trial,
+    gain ratio, accepted)."""
+    L = lib()
+    buf, cnt = np.zeros((max_records, 5)), C.c_int(0)
+    L.orc_ba_set_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.orc_ba_set_trace(_p(buf), max_records, C.byref(cnt))
+    try:
+        out = bundle_adjustment(*args, **kw)
+    finally:
+        L.orc_ba_set_trace(None, 0, None)
+    return out + (buf[: cnt.value].copy(),)
