@@ -179,6 +179,7 @@ void mvo_destroy(mvo_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   orb_state_free(ctx);
+  orb_tma_free(ctx);
   DevBuf *dbs[] = {&ctx->d_a, &ctx->d_b, &ctx->d_c, &ctx->d_d, &ctx->d_e, &ctx->d_f, &ctx->orb_planes,
                    &ctx->orb_cand, &ctx->orb_bandcnt, &ctx->orb_sel, &ctx->orb_misc, &ctx->orb_in,
                    &ctx->orb_kpts, &ctx->orb_desc, &ctx->orb_counts, &ctx->match_part,

@@ -90,6 +90,7 @@ struct mvo_ctx {
   DevBuf orb_kpts, orb_desc, orb_counts;
   PinBuf orb_h;
   void *orb_state = nullptr, *orb_pending = nullptr;   // orb_host.cpp: OrbState / OrbPending of this context
+  void *orb_tma = nullptr;                             // orb.cu: tensor maps of the gray planes (OrbTmaState)
 
   // match
   DevBuf match_part, match_tickets, match_in, match_keys;
@@ -199,6 +200,7 @@ int mvo_trk_counters(mvo_tracker *t, int32_t *visible, int32_t *matched, int n);
 int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
+void orb_tma_free(mvo_ctx *ctx);     // orb.cu
 // mvo_orb_extract with the image optionally already resident on the device (orb_host.cpp)
 int mvo_orb_extract_ex(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride,
                        int on_device, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc);

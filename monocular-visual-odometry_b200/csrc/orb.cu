@@ -19,6 +19,8 @@
 //                 BRIEF tests (lane i produces descriptor byte i)
 // Float formulas that OpenCV evaluates without FMA use __fmul_rn/__fadd_rn explicitly.
 #include <cooperative_groups.h>
+#include <cuda.h>               // CUtensorMap: the FAST band tiles are staged by TMA (cp.async.bulk.tensor)
+#include <stdlib.h>
 #include "orb.cuh"
 
 namespace cg = cooperative_groups;
@@ -121,10 +123,24 @@ __device__ __forceinline__ int fast_score(const uint8_t *__restrict__ p, int str
   return m > t ? m - 1 : 0;
 }
 
+// One tensor map per pyramid level over the gray planes of all frame slots: (x in 4-byte words, y, frame slot), box =
+// one whole band: pitch / 4 words x 16 rows x 1 frame.  TMA = true: one elected thread issues a single
+// cp.async.bulk.tensor.3d for the band's 16 image rows (rows past the image are zero-filled by the unit) and the CTA waits on
+// the mbarrier it completes; no thread moves image bytes through registers.  TMA = false: 16-byte vector loads (images wider
+// than 1024 pixels, whose rows do not fit a 256-element box, and the CPU test tier).
+struct FastMaps { CUtensorMap m[MVO_MAX_LEVELS]; };
+
+#ifndef __CUDA_ARCH__
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+#endif
+
+template <bool TMA>
 __global__ void __launch_bounds__(256)
 k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict__ staging,
-       int32_t *__restrict__ bandcnt) {
-  extern __shared__ __align__(16) uint8_t smem[];
+       int32_t *__restrict__ bandcnt, const __grid_constant__ FastMaps maps) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const int band = blockIdx.x, f = blockIdx.y;
   int l = 0;
 #pragma unroll 1
@@ -134,7 +150,7 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
   const int t = plan.fast_threshold;
   const int y0 = ORB_EDGE + (band - L.band_first) * ORB_BAND_H;     // first NMS row
   const int nms_rows = min(ORB_BAND_H, h - ORB_EDGE - y0);
-  const int sstride = pitch + 16;                                    // de-alias rows across banks
+  const int sstride = TMA ? pitch : pitch + 16;                      // TMA lands dense rows; the vector path de-aliases rows across banks
   const int img_rows = nms_rows + 8;                                 // rows y0-4 .. y0+nms_rows+3
   const int sc_rows = nms_rows + 2;                                  // rows y0-1 .. y0+nms_rows
   const int w32 = (w + 31) >> 5;
@@ -149,13 +165,34 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint8_t *img = planes + (size_t)f * plan.slot_bytes + L.img_off;
 
-  // stage image rows (whole padded rows, 16-byte vectors), clear score rows and the keep bitmap
+  // stage image rows (TMA: one bulk tensor copy of the whole band; otherwise whole padded rows as 16-byte vectors), clear
+  // score rows and the keep bitmap
+  __shared__ __align__(8) unsigned long long s_bar;
   {
-    const int vec_per_row = pitch >> 4;
-    for (int i = tid; i < img_rows * vec_per_row; i += 256) {
-      const int r = i / vec_per_row, v = i - r * vec_per_row;
-      const uint4 val = *reinterpret_cast<const uint4 *>(img + (size_t)(y0 - 4 + r) * pitch + v * 16);
-      *reinterpret_cast<uint4 *>(s_img + r * sstride + v * 16) = val;
+    bool staged = false;
+#if defined(__CUDA_ARCH__)
+    if (TMA) {
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar), dst = (unsigned)__cvta_generic_to_shared(s_img);
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned bytes = (unsigned)((ORB_BAND_H + 8) * pitch);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const unsigned long long mp = reinterpret_cast<unsigned long long>(&maps.m[l]);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(mp), "r"(0), "r"(y0 - 4), "r"(f), "r"(bar) : "memory");
+      }
+      staged = true;
+    }
+#endif
+    if (!staged) {
+      const int vec_per_row = pitch >> 4;
+      for (int i = tid; i < img_rows * vec_per_row; i += 256) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const uint4 val = *reinterpret_cast<const uint4 *>(img + (size_t)(y0 - 4 + r) * pitch + v * 16);
+        *reinterpret_cast<uint4 *>(s_img + r * sstride + v * 16) = val;
+      }
     }
     const int svec = (sc_rows * sstride) >> 4;
     for (int i = tid; i < svec; i += 256) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
@@ -163,6 +200,16 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
     if (tid == 0) s_cnt = 0;
   }
   __syncthreads();
+#if defined(__CUDA_ARCH__)
+  if (TMA) {                                                        // the band has landed when the mbarrier's phase 0 completes
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(0) : "memory");
+      if (spin > (1 << 24)) __trap();                               // a faulty descriptor must not hang the GPU
+    }
+  }
+#endif
 
   // phase 1: quick reject on the 4 compass points; survivors go to a shared list.
   // An arc of 9 contiguous ring pixels always contains one of {0,8} and one of {4,12}.
@@ -258,7 +305,7 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
 __global__ void __launch_bounds__(1024)
 k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *__restrict__ bandcnt,
          uint32_t *__restrict__ cand, uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncell = plan.grid_rows * plan.grid_cols;
   const int cap = plan.cand_cap, scap = plan.sel_cap;
@@ -602,7 +649,7 @@ __device__ int ret_retain_best(const RetBuf &b, int n, int npts) {
 __global__ void __launch_bounds__(RET_T)
 k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__restrict__ harris, OrbFrameMeta *__restrict__ meta,
          uint16_t *__restrict__ kept, int32_t *__restrict__ kept_cnt) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_scratch[2 * RET_W + 8];
   const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
   if (meta[f].overflow == 0) return;
@@ -651,7 +698,7 @@ k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__rest
 __global__ void __launch_bounds__(1024)
 k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t *__restrict__ kept, const int32_t *__restrict__ kept_cnt,
               uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (meta[f].overflow != 1) return;
   const int ncell = plan.grid_rows * plan.grid_cols, scap = plan.sel_cap;
@@ -1039,15 +1086,72 @@ static size_t fast_smem_bytes(const OrbPlanDev &plan) {
   return m;
 }
 
+// Tensor maps of the gray planes (one per level) for the current workspace; rebuilt when the planes move or the geometry changes.
+struct OrbTmaState {
+  const uint8_t *planes = nullptr;
+  int slots = 0, nlevels = 0, w[MVO_MAX_LEVELS] = {0}, h[MVO_MAX_LEVELS] = {0};
+  uint32_t slot_bytes = 0;
+  bool ok = false;
+  FastMaps maps;
+};
+
+static bool orb_tma_maps(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, int slots, const FastMaps **out) {
+  static const bool off = getenv("MVO_FAST_TMA") != nullptr && atoi(getenv("MVO_FAST_TMA")) == 0;      // A/B hook
+  if (off) return false;
+  if (!ctx->orb_tma) ctx->orb_tma = new OrbTmaState();
+  OrbTmaState *t = (OrbTmaState *)ctx->orb_tma;
+  bool same = t->planes == planes && t->slots == slots && t->nlevels == plan.nlevels && t->slot_bytes == plan.slot_bytes;
+  for (int l = 0; same && l < plan.nlevels; ++l) same = t->w[l] == plan.lv[l].w && t->h[l] == plan.lv[l].h;
+  if (!same) {
+    t->planes = planes; t->slots = slots; t->nlevels = plan.nlevels; t->slot_bytes = plan.slot_bytes; t->ok = false;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    bool ok = true;
+    for (int l = 0; l < plan.nlevels && ok; ++l) {
+      const OrbLevelDev &L = plan.lv[l];
+      t->w[l] = L.w; t->h[l] = L.h;
+      if (L.pitch / 4 > 256) { ok = false; break; }                 // a row must fit one box (256 elements): images up to 1024 wide
+      const cuuint64_t dims[3] = {(cuuint64_t)(L.pitch / 4), (cuuint64_t)L.h, (cuuint64_t)slots};
+      const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)plan.slot_bytes};
+      const cuuint32_t box[3] = {(cuuint32_t)(L.pitch / 4), (cuuint32_t)(ORB_BAND_H + 8), 1}, es[3] = {1, 1, 1};
+      const CUresult r = ((EncodeFn)fn)(&t->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)(planes + L.img_off), dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ok = r == CUDA_SUCCESS;
+    }
+    t->ok = ok;
+  }
+  *out = &t->maps;
+  return t->ok;
+}
+
+void orb_tma_free(mvo_ctx *ctx) {
+  delete (OrbTmaState *)ctx->orb_tma;
+  ctx->orb_tma = nullptr;
+}
+
 int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, uint32_t *staging,
                     int32_t *bandcnt, int batch) {
   const size_t smem = fast_smem_bytes(plan);
   if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "image too wide for the FAST band kernel");
-  if (smem > 48 * 1024)
-    MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const FastMaps *maps = nullptr;
+  const bool tma = orb_tma_maps(ctx, plan, planes, ctx->orb_batch > batch ? ctx->orb_batch : batch, &maps);
   dim3 grid(plan.total_bands, batch);
   KTimer kt(ctx, KC_FAST);
-  k_fast<<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt);
+  if (tma) {
+    MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fast<true><<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt, *maps);
+  } else {
+    static const FastMaps none = {};
+    MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fast<false><<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt, none);
+  }
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

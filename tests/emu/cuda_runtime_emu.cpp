@@ -45,6 +45,12 @@ cudaError_t cudaMemcpyToSymbolAsync(const void *sym, const void *s, size_t n, si
   memcpy((char *)sym + off, s, n);
   return cudaSuccess;
 }
+// no driver behind the emulation: the product then stages the FAST bands with plain loads instead of TMA
+cudaError_t cudaGetDriverEntryPoint(const char *, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *q) {
+  if (fn) *fn = nullptr;
+  if (q) *q = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorNotSupported;
+}
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t) { return "emulated runtime"; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t) new EmuEvent(); return cudaSuccess; }
