@@ -1021,20 +1021,50 @@ k_describe(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__r
 
 #include "orb_variants.cuh"   // experimental k_blur2 / k_describe_sel2 (MVO_BLUR2 / MVO_DESCRIBE2), host-emulated in tests
 
-// Harris response for every compact candidate (host retainBest path only).
-__global__ void __launch_bounds__(256)
+// Harris response of every compact candidate of the frames whose levels overflow (retainBest needs them all).  One THREAD
+// per candidate: the 9 x 9 neighbourhood is read once into registers, the 49 Sobel-like gradients and the three integer sums
+// follow from it (a warp per candidate spent ~100 instructions on three shuffle reductions for 49 pixels).  Same integer
+// sums and the same float expression as harris_warp, so the responses are bit-identical with k_describe's.
+__global__ void __launch_bounds__(128)
 k_harris_all(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint32_t *__restrict__ cand,
              const OrbFrameMeta *__restrict__ meta, float *__restrict__ harris) {
-  const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = blockIdx.y;
   if (meta[f].overflow == 0) return;              // only retainBest needs the response of every candidate
   const int n = min(meta[f].n_cand, plan.cand_cap);
   const uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
-  for (int k = blockIdx.x * 8 + warp; k < n; k += gridDim.x * 8) {
+  const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));            // 1.f/((1<<2)*7*255.f)
+  const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     int l = 0, acc = meta[f].lvl_count[0];
     while (l + 1 < plan.nlevels && k >= acc) acc += meta[f].lvl_count[++l];
     const uint32_t p = cand[(size_t)f * plan.cand_cap + k];
-    const float r = harris_warp(slot + plan.lv[l].img_off, plan.lv[l].pitch, orb_px(p), orb_py(p), lane);
-    if (lane == 0) harris[(size_t)f * plan.cand_cap + k] = r;
+    const int pitch = plan.lv[l].pitch, x0 = orb_px(p), y0 = orb_py(p);
+    const uint8_t *c0 = slot + plan.lv[l].img_off + (size_t)(y0 - 4) * pitch + (x0 - 4);
+    int a = 0, b = 0, c = 0;
+    // three rows at a time slide down the 9 rows: gradients of block row i need image rows i-1, i, i+1
+    int r0[9], r1[9], r2[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { r0[j] = c0[j]; r1[j] = c0[pitch + j]; }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const uint8_t *row = c0 + (size_t)(i + 2) * pitch;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) r2[j] = row[j];
+#pragma unroll
+      for (int j = 1; j <= 7; ++j) {
+        const int Ix = (r1[j + 1] - r1[j - 1]) * 2 + (r0[j + 1] - r0[j - 1]) + (r2[j + 1] - r2[j - 1]);
+        const int Iy = (r2[j] - r0[j]) * 2 + (r2[j - 1] - r0[j - 1]) + (r2[j + 1] - r0[j + 1]);
+        a += Ix * Ix;
+        b += Iy * Iy;
+        c += Ix * Iy;
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+    }
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float ab = __fadd_rn(fa, fb);
+    harris[(size_t)f * plan.cand_cap + k] =
+        __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, ab), ab)), s4);
   }
 }
 
@@ -1193,9 +1223,9 @@ int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int b
 
 int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, const uint32_t *cand,
                           const OrbFrameMeta *meta, float *harris, int batch) {
-  dim3 grid(2 * ctx->sm_count, batch);
+  dim3 grid(ctx->sm_count, batch);
   KTimer kt(ctx, KC_HARRIS);
-  k_harris_all<<<grid, 256, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
+  k_harris_all<<<grid, 128, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
