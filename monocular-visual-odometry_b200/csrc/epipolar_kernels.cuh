@@ -126,7 +126,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   __shared__ long long s_k[32];
   __shared__ int s_best, s_cnt[32], s_stop;
   __shared__ double s_E[9], s_R1[9], s_R2[9], s_t[3], s_R[9], s_E0[9];
-  __shared__ double s_Ek[6][9], s_red[32][20], s_sum[20];
+  __shared__ double s_Ek[6][9], s_red[32][20];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long best = -1;
   for (int h = tid; h < H; h += EFIN_T) {
@@ -158,18 +158,22 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   // this thread's points (contiguous chunk), calibrated coordinates
   const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
   // ---- local optimisation ----
+  // Per Gauss-Newton iteration: one pass over the points (every thread its chunk, warp-reduced partial sums), one barrier, then
+  // lanes 0..5 of warp 0 each sum the partials, solve the 5 x 5 system (redundantly: identical inputs, identical result),
+  // apply the step and evaluate E at the new estimate (lane 0) / at its five forward perturbations (lanes 1..5), one barrier.
+  auto perturbed_E = [&](int k, const double *R, const double *t) {       // E at (R, t) retracted by 1e-6 along tangent direction k - 1
+    double d[5] = {0, 0, 0, 0, 0}, Rk[9], tk[3];
+    if (k > 0) d[k - 1] = 1e-6;
+    epi_retract(R, t, d, Rk, tk);
+    skew_times(tk, Rk, s_Ek[k]);
+  };
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Esel[9];
     for (int q = 0; q < 9; ++q) Esel[q] = s_E[q];          // consensus set of this round: fixed during its GN iterations
+    if (tid < 6) perturbed_E(tid, s_R, s_t);
+    if (tid == 0) s_stop = 0;
+    __syncthreads();
     for (int it = 0; it < EPI_GN_ITERS; ++it) {
-      if (tid < 6) {                                         // E at the current estimate and at its 5 forward perturbations
-        double d[5] = {0, 0, 0, 0, 0}, Rk[9], tk[3];
-        if (tid > 0) d[tid - 1] = 1e-6;
-        epi_retract(s_R, s_t, d, Rk, tk);
-        skew_times(tk, Rk, s_Ek[tid]);
-      }
-      if (tid == 0) s_stop = 0;
-      __syncthreads();
       double acc[20];
 #pragma unroll
       for (int q = 0; q < 20; ++q) acc[q] = 0;
@@ -197,38 +201,51 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
         if (lane == 0) s_red[warp][q] = v;
       }
       __syncthreads();
-      if (tid < 20) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += s_red[w][tid]; s_sum[tid] = v; }
-      __syncthreads();
-      if (tid == 0) {
-        // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
-        double A[5][6];
-        int q = 0;
-        for (int r = 0; r < 5; ++r) for (int c = r; c < 5; ++c) { A[r][c] = s_sum[q]; A[c][r] = s_sum[q]; ++q; }
-        double tr = 0;
-        for (int r = 0; r < 5; ++r) tr += A[r][r];
-        for (int r = 0; r < 5; ++r) { A[r][r] += 1e-12 * tr + 1e-300; A[r][5] = -s_sum[15 + r]; }
-        bool ok = true;
-        for (int k = 0; k < 5 && ok; ++k) {
-          int pr = k;
-          for (int r = k + 1; r < 5; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
-          if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
-          if (pr != k) for (int c = 0; c < 6; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
-          for (int r = k + 1; r < 5; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 6; ++c) A[r][c] -= f * A[k][c]; }
+      if (warp == 0) {
+        bool stop = true;
+        double Rn[9], tn[3];
+        for (int r = 0; r < 9; ++r) Rn[r] = s_R[r];
+        for (int r = 0; r < 3; ++r) tn[r] = s_t[r];
+        if (lane < 6) {
+          // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
+          double sum[20];
+          for (int q = 0; q < 20; ++q) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += s_red[w][q]; sum[q] = v; }
+          double A[5][6];
+          int q = 0;
+          for (int r = 0; r < 5; ++r) for (int c = r; c < 5; ++c) { A[r][c] = sum[q]; A[c][r] = sum[q]; ++q; }
+          double tr = 0;
+          for (int r = 0; r < 5; ++r) tr += A[r][r];
+          for (int r = 0; r < 5; ++r) { A[r][r] += 1e-12 * tr + 1e-300; A[r][5] = -sum[15 + r]; }
+          bool ok = true;
+          for (int k = 0; k < 5 && ok; ++k) {
+            int pr = k;
+            for (int r = k + 1; r < 5; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
+            if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
+            if (pr != k) for (int c = 0; c < 6; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
+            for (int r = k + 1; r < 5; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 6; ++c) A[r][c] -= f * A[k][c]; }
+          }
+          double dx[5] = {0, 0, 0, 0, 0}, mx = 0;
+          if (ok) {
+            for (int r = 4; r >= 0; --r) { double v = A[r][5]; for (int c = r + 1; c < 5; ++c) v -= A[r][c] * dx[c]; dx[r] = v / A[r][r]; }
+            for (int r = 0; r < 5; ++r) { if (!isfinite(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
+          }
+          if (ok && mx < 0.5) {                               // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
+            double R2[9], t2[3];
+            epi_retract(Rn, tn, dx, R2, t2);
+            for (int r = 0; r < 9; ++r) Rn[r] = R2[r];
+            for (int r = 0; r < 3; ++r) tn[r] = t2[r];
+          }
+          // forward-difference Jacobian (1e-6 steps): the Gauss-Newton steps bottom out around 1e-9; 1e-8 rad is four orders
+          // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
+          stop = !ok || mx < 1e-8 || mx >= 0.5;
         }
-        double dx[5] = {0, 0, 0, 0, 0}, mx = 0;
-        if (ok) {
-          for (int r = 4; r >= 0; --r) { double v = A[r][5]; for (int c = r + 1; c < 5; ++c) v -= A[r][c] * dx[c]; dx[r] = v / A[r][r]; }
-          for (int r = 0; r < 5; ++r) { if (!isfinite(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
-        }
-        if (ok && mx < 0.5) {                                 // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
-          double Rn[9], tn[3];
-          epi_retract(s_R, s_t, dx, Rn, tn);
+        __syncwarp();                                         // every lane has read s_R / s_t
+        if (lane == 0) {
           for (int r = 0; r < 9; ++r) s_R[r] = Rn[r];
           for (int r = 0; r < 3; ++r) s_t[r] = tn[r];
+          s_stop = stop ? 1 : 0;
         }
-        // forward-difference Jacobian (1e-6 steps): the Gauss-Newton steps bottom out around 1e-9; 1e-8 rad is four orders
-        // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
-        if (!ok || mx < 1e-8 || mx >= 0.5) s_stop = 1;
+        if (lane < 6 && !stop) perturbed_E(lane, Rn, tn);
       }
       __syncthreads();
       if (s_stop) break;

@@ -26,7 +26,18 @@ int emu_essential(const float *p1, const float *p2, int n, const double *K, doub
   const int grid = std::min((H + 7) / 8, 64);                    // any grid covers all hypotheses (grid-stride loop)
   run_grid((unsigned)grid, 1, 1, 256, (size_t)n * 32, [&] { k_epi_score(p1, p2, n, cam, thr2, H, Es.data(), valid.data(), counts.data()); });
   run_grid(1, 1, 1, EFIN_T, 0, [&] { k_epi_finish(p1, p2, n, cam, thr2, H, Es.data(), counts.data(), out.data(), oi.data(), inliers); });
-  memcpy(E, out.data(), 72); memcpy(R, out.data() + 9, 72); memcpy(t, out.data() + 18, 24);
+  run_grid((unsigned)((n + 63) / 64), 1, 1, 256, 0, [&] { k_epi_vote(p1, p2, cam, out.data(), oi.data(), inliers); });
+  // recoverPose's choice on the host, as mvo_esti_motion_by_essential does it: the first candidate whose vote count is a maximum
+  const int32_t *g = oi.data() + 8;
+  int pick = 3;
+  if (g[0] >= g[1] && g[0] >= g[2] && g[0] >= g[3]) pick = 0;
+  else if (g[1] >= g[0] && g[1] >= g[2] && g[1] >= g[3]) pick = 1;
+  else if (g[2] >= g[0] && g[2] >= g[1] && g[2] >= g[3]) pick = 2;
+  oi[2] = g[pick];
+  const double *tt = out.data() + 27, sg = pick < 2 ? 1.0 : -1.0;
+  const double nt = sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+  memcpy(E, out.data(), 72); memcpy(R, out.data() + ((pick & 1) ? 18 : 9), 72);
+  for (int q = 0; q < 3; ++q) t[q] = sg * tt[q] / nt;
   memcpy(out_i, oi.data(), 5 * sizeof(int32_t));
   return oi[0];
 }
