@@ -15,6 +15,7 @@
 //   k_epi_finish      one CTA: arg-max (ties -> lowest hypothesis), ordered inlier list, recoverPose vote
 //   k_triangulate     one thread per point: epi::triangulate_dlt
 // The numerics live in epipolar_math.cuh and are unit-tested on the host (tests/test_epipolar_math.py).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -120,9 +121,24 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   { KTimer kt(ctx, KC_EPI_SCORE);
   k_epi_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dvalid, dcnt); }
   MVO_CHECK_LAUNCH(ctx);
-  { KTimer kt(ctx, KC_EPI_FINISH);
-  k_epi_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dcnt, dout, dout_i, dinl); }
-  MVO_CHECK_LAUNCH(ctx);
+  {
+    // one thread-block cluster of EFIN_C CTAs (distributed shared memory between them)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(EFIN_C);
+    cfg.blockDim = dim3(EFIN_T);
+    cfg.dynamicSmemBytes = sizeof(EpiFinSmem);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = EFIN_C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KTimer kt(ctx, KC_EPI_FINISH);
+    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_epi_finish, d1, d2, n, cam, thr2, H, (const double *)dE, (const int32_t *)dcnt, dout, dout_i, dinl));
+    ctx->launches++;
+  }
   { KTimer kt(ctx, KC_EPI);
   k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl); }
   MVO_CHECK_LAUNCH(ctx);

@@ -111,23 +111,40 @@ __device__ __forceinline__ double sampson_signed(const double *E, double x1, dou
   return (x2 * Ex0 + y2 * Ex1 + Ex2) * rsqrt(Ex0 * Ex0 + Ex1 * Ex1 + Et0 * Et0 + Et1 * Et1);
 }
 
-// out_d: [0..8] E (scaled so that E[8] = 1, epipolar_geometry.cpp:37), [9..17] R, [18..20] t (unit); out_i: [0] inliers,
-// [1] best hypothesis, [2] cheirality votes of the chosen (R, t), [3] consensus of the best minimal model
+// out_d: [0..8] E (scaled so that E[8] = 1, epipolar_geometry.cpp:37), [9..17] R1, [18..26] R2, [27..29] t of
+// decomposeEssentialMat; out_i: [0] inliers, [1] best hypothesis, [3] consensus of the best minimal model, [4] consensus after the
+// local optimisation, [5] Gauss-Newton iterations run, [8..11] cheirality votes (k_epi_vote)
 //
 // After the arg-max the best minimal model is locally optimised (LO-RANSAC style): EPI_LO_ROUNDS times its consensus
 // set is re-selected and (R, t/|t|) is re-estimated on it by Gauss-Newton on the signed Sampson residual (5 degrees of
 // freedom, forward-difference Jacobian).  OpenCV returns the minimal five-point model as it is; the eight-point
 // minimal models used here are noisier, and the local optimisation more than makes up for it (pose errors against
 // synthetic truth ~10x below cv2's on the test scenes).  The reported inliers are the consensus set of the final model.
+//
+// One thread-block CLUSTER of EFIN_C CTAs (round 2; before: one CTA): a Gauss-Newton iteration is ~500 fp64 instructions per
+// correspondence, which kept ONE SM busy for ~14 us per iteration (16 iterations per call).  Every CTA owns a slice of the
+// correspondences; the partial normal equations meet through distributed shared memory — each CTA reads all partials in rank
+// order, so all of them hold bit-identical sums, take the same step and need no broadcast (the scheme of k_ba_pose).  All block
+// state lives in DYNAMIC shared memory (the CPU test tier gives every block of a cluster its own copy of that).
+constexpr int EFIN_C = 8;
+
+struct EpiFinSmem {
+  long long k[EFIN_T / 32];
+  double E[9], R1[9], R2[9], t[3], R[9], E0[9];
+  double Ek[6][9], red[EFIN_T / 32][20], part[2][20];
+  int cnt[EFIN_T / 32], best, stop, ipart[4];
+};
+
 __global__ void __launch_bounds__(EFIN_T)
 k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, EpiCam cam, double thr2, int H,
              const double *__restrict__ Es, const int32_t *__restrict__ counts, double *__restrict__ out_d,
              int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
-  __shared__ long long s_k[32];
-  __shared__ int s_best, s_cnt[32], s_stop;
-  __shared__ double s_E[9], s_R1[9], s_R2[9], s_t[3], s_R[9], s_E0[9];
-  __shared__ double s_Ek[6][9], s_red[32][20];
+  EPI_DYN_SMEM(double, smraw);
+  EpiFinSmem &S = *reinterpret_cast<EpiFinSmem *>(smraw);
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // arg-max over the hypotheses: every CTA for itself (identical result)
   long long best = -1;
   for (int h = tid; h < H; h += EFIN_T) {
     const long long key = ((long long)counts[h] << 20) | (long long)(0xFFFFF - h);
@@ -135,45 +152,60 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-  if (lane == 0) s_k[warp] = best;
+  if (lane == 0) S.k[warp] = best;
   __syncthreads();
   if (tid == 0) {
     long long b = -1;
-    for (int w = 0; w < EFIN_T / 32; ++w) b = s_k[w] > b ? s_k[w] : b;
-    s_best = (int)(b >> 20) >= 8 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
-    out_i[3] = (int)(b >> 20);
+    for (int w = 0; w < EFIN_T / 32; ++w) b = S.k[w] > b ? S.k[w] : b;
+    S.best = (int)(b >> 20) >= 8 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
+    if (rank == 0) out_i[3] = (int)(b >> 20);
   }
   __syncthreads();
-  if (s_best < 0) {
-    if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
+  if (S.best < 0) {                                                  // every CTA takes this branch together
+    if (rank == 0 && tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[2] = 0; }
     return;
   }
   if (tid == 0) {
-    for (int q = 0; q < 9; ++q) s_E[q] = Es[(size_t)s_best * 9 + q];
-    epi::decompose_essential(s_E, s_R1, s_R2, s_t);
-    for (int q = 0; q < 9; ++q) { s_R[q] = s_R1[q]; s_E0[q] = s_E[q]; }      // either rotation of the twisted pair spans the same E = [t]x R (up to sign)
-    skew_times(s_t, s_R, s_E);
+    for (int q = 0; q < 9; ++q) S.E[q] = Es[(size_t)S.best * 9 + q];
+    epi::decompose_essential(S.E, S.R1, S.R2, S.t);
+    for (int q = 0; q < 9; ++q) { S.R[q] = S.R1[q]; S.E0[q] = S.E[q]; }      // either rotation of the twisted pair spans the same E = [t]x R (up to sign)
+    skew_times(S.t, S.R, S.E);
   }
   __syncthreads();
-  // this thread's points (contiguous chunk), calibrated coordinates
-  const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+  // this thread's correspondences: a contiguous chunk, ascending over (rank, tid)
+  const int nthr = (int)csize * EFIN_T, g = (int)rank * EFIN_T + tid;
+  const int per = (n + nthr - 1) / nthr, b0 = min(g * per, n), e0 = min(b0 + per, n);
+  int parity = 0, gn_total = 0;
+  // cluster-wide sum of NV doubles whose per-warp partials sit in S.red: every CTA ends up with the same sums in `sum`
+  auto cluster_sums = [&](double *sum, int NV) {
+    if (tid < NV) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += S.red[w][tid]; S.part[parity][tid] = v; }
+    cluster.sync();                                                  // partials of every CTA are in place (and the previous round's have been read)
+    if (tid < 32)
+      for (int q = 0; q < NV; ++q) {
+        double v = 0;
+        for (unsigned r = 0; r < csize; ++r) v += *cluster.map_shared_rank(&S.part[parity][q], r);      // rank order: identical in every CTA
+        sum[q] = v;
+      }
+    parity ^= 1;
+  };
   // ---- local optimisation ----
-  // Per Gauss-Newton iteration: one pass over the points (every thread its chunk, warp-reduced partial sums), one barrier, then
-  // lanes 0..5 of warp 0 each sum the partials, solve the 5 x 5 system (redundantly: identical inputs, identical result),
-  // apply the step and evaluate E at the new estimate (lane 0) / at its five forward perturbations (lanes 1..5), one barrier.
+  // Per Gauss-Newton iteration: one pass over the points (every thread its chunk, warp-reduced partial sums), the cluster-wide
+  // sums, then lanes 0..5 of warp 0 of every CTA solve the 5 x 5 system (redundantly: identical inputs, identical result), apply
+  // the step and evaluate E at the new estimate (lane 0) / at its five forward perturbations (lanes 1..5).
   auto perturbed_E = [&](int k, const double *R, const double *t) {       // E at (R, t) retracted by 1e-6 along tangent direction k - 1
     double d[5] = {0, 0, 0, 0, 0}, Rk[9], tk[3];
     if (k > 0) d[k - 1] = 1e-6;
     epi_retract(R, t, d, Rk, tk);
-    skew_times(tk, Rk, s_Ek[k]);
+    skew_times(tk, Rk, S.Ek[k]);
   };
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Esel[9];
-    for (int q = 0; q < 9; ++q) Esel[q] = s_E[q];          // consensus set of this round: fixed during its GN iterations
-    if (tid < 6) perturbed_E(tid, s_R, s_t);
-    if (tid == 0) s_stop = 0;
+    for (int q = 0; q < 9; ++q) Esel[q] = S.E[q];          // consensus set of this round: fixed during its GN iterations
+    if (tid < 6) perturbed_E(tid, S.R, S.t);
+    if (tid == 0) S.stop = 0;
     __syncthreads();
     for (int it = 0; it < EPI_GN_ITERS; ++it) {
+      ++gn_total;
       double acc[20];
 #pragma unroll
       for (int q = 0; q < 20; ++q) acc[q] = 0;
@@ -181,10 +213,10 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
         const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
         const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
         if (!(epi::sampson_err(Esel, x1, y1, x2, y2) <= thr2)) continue;
-        const double r0 = sampson_signed(s_Ek[0], x1, y1, x2, y2);
+        const double r0 = sampson_signed(S.Ek[0], x1, y1, x2, y2);
         double J[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) J[k] = (sampson_signed(s_Ek[k + 1], x1, y1, x2, y2) - r0) * 1e6;
+        for (int k = 0; k < 5; ++k) J[k] = (sampson_signed(S.Ek[k + 1], x1, y1, x2, y2) - r0) * 1e6;
         int q = 0;
 #pragma unroll
         for (int r = 0; r < 5; ++r)
@@ -198,18 +230,18 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
         double v = acc[q];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) s_red[warp][q] = v;
+        if (lane == 0) S.red[warp][q] = v;
       }
       __syncthreads();
+      double sum[20];
+      cluster_sums(sum, 20);
       if (warp == 0) {
         bool stop = true;
         double Rn[9], tn[3];
-        for (int r = 0; r < 9; ++r) Rn[r] = s_R[r];
-        for (int r = 0; r < 3; ++r) tn[r] = s_t[r];
+        for (int r = 0; r < 9; ++r) Rn[r] = S.R[r];
+        for (int r = 0; r < 3; ++r) tn[r] = S.t[r];
         if (lane < 6) {
           // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
-          double sum[20];
-          for (int q = 0; q < 20; ++q) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += s_red[w][q]; sum[q] = v; }
           double A[5][6];
           int q = 0;
           for (int r = 0; r < 5; ++r) for (int c = r; c < 5; ++c) { A[r][c] = sum[q]; A[c][r] = sum[q]; ++q; }
@@ -239,18 +271,18 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
           // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
           stop = !ok || mx < 1e-8 || mx >= 0.5;
         }
-        __syncwarp();                                         // every lane has read s_R / s_t
+        __syncwarp();                                         // every lane has read S.R / S.t
         if (lane == 0) {
-          for (int r = 0; r < 9; ++r) s_R[r] = Rn[r];
-          for (int r = 0; r < 3; ++r) s_t[r] = tn[r];
-          s_stop = stop ? 1 : 0;
+          for (int r = 0; r < 9; ++r) S.R[r] = Rn[r];
+          for (int r = 0; r < 3; ++r) S.t[r] = tn[r];
+          S.stop = stop ? 1 : 0;
         }
         if (lane < 6 && !stop) perturbed_E(lane, Rn, tn);
       }
       __syncthreads();
-      if (s_stop) break;
+      if (S.stop) break;
     }
-    if (tid == 0) skew_times(s_t, s_R, s_E);
+    if (tid == 0) skew_times(S.t, S.R, S.E);
     __syncthreads();
   }
   // the local optimisation must not lose support: otherwise the minimal model stands
@@ -259,24 +291,27 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
     for (int i = b0; i < e0; ++i) {
       const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
       const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-      c += epi::sampson_err(s_E, x1, y1, x2, y2) <= thr2;
+      c += epi::sampson_err(S.E, x1, y1, x2, y2) <= thr2;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_cnt[warp] = c;
+    if (lane == 0) S.red[warp][0] = (double)c;
     __syncthreads();
+    double tot[1];
+    cluster_sums(tot, 1);
     if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < EFIN_T / 32; ++w) tot += s_cnt[w];
-      out_i[4] = tot;
-      if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_E[q] = s_E0[q];
+      const int total = (int)tot[0];
+      if (rank == 0) { out_i[4] = total; out_i[5] = gn_total; }
+      long long b = -1;
+      for (int w = 0; w < EFIN_T / 32; ++w) b = S.k[w] > b ? S.k[w] : b;
+      if (!(total >= (int)(b >> 20))) for (int q = 0; q < 9; ++q) S.E[q] = S.E0[q];
     }
     __syncthreads();
   }
   // ---- consensus set of the final model, ascending (the mask of findEssentialMat, epipolar_geometry.cpp:40-47) ----
-  if (tid == 0) epi::decompose_essential(s_E, s_R1, s_R2, s_t);
+  if (tid == 0) epi::decompose_essential(S.E, S.R1, S.R2, S.t);
   double E[9];
-  for (int q = 0; q < 9; ++q) E[q] = s_E[q];
+  for (int q = 0; q < 9; ++q) E[q] = S.E[q];
   int mine = 0;
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
@@ -286,23 +321,32 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-  if (lane == 31) s_cnt[warp] = incl;
+  if (lane == 31) S.cnt[warp] = incl;
   __syncthreads();                                   // also publishes R1, R2, t
-  int off = incl - mine, n_in = 0;
-  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+  int off = incl - mine, cta_total = 0;
+  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += S.cnt[w]; cta_total += S.cnt[w]; }
+  if (tid == 0) S.ipart[0] = cta_total;
+  cluster.sync();
+  int n_in = 0;
+  for (unsigned r = 0; r < csize; ++r) {
+    const int c = *cluster.map_shared_rank(&S.ipart[0], r);
+    if (r < rank) off += c;
+    n_in += c;
+  }
   // the consensus set, ascending; the cheirality vote of recoverPose runs in k_epi_vote (all SMs) and the host picks
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
     const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
     if (epi::sampson_err(E, x1, y1, x2, y2) <= thr2) inl[off++] = i;
   }
-  if (tid == 0) {
-    const double e22 = s_E[8];
-    for (int q = 0; q < 9; ++q) { out_d[q] = s_E[q] / e22; out_d[9 + q] = s_R1[q]; out_d[18 + q] = s_R2[q]; }       // E /= E(2,2) (:37)
-    for (int q = 0; q < 3; ++q) out_d[27 + q] = s_t[q];
-    out_i[0] = n_in; out_i[1] = s_best;
+  if (rank == 0 && tid == 0) {
+    const double e22 = S.E[8];
+    for (int q = 0; q < 9; ++q) { out_d[q] = S.E[q] / e22; out_d[9 + q] = S.R1[q]; out_d[18 + q] = S.R2[q]; }       // E /= E(2,2) (:37)
+    for (int q = 0; q < 3; ++q) out_d[27 + q] = S.t[q];
+    out_i[0] = n_in; out_i[1] = S.best;
     out_i[8] = out_i[9] = out_i[10] = out_i[11] = 0;                      // votes, accumulated by k_epi_vote
   }
+  cluster.sync();                                    // no CTA leaves while another still reads its shared memory
 }
 
 // recoverPose (calib3d five-point.cpp): triangulate every inlier with [I|0] and each of (R1,t) (R2,t) (R1,-t) (R2,-t); a point

@@ -25,7 +25,7 @@ int emu_essential(const float *p1, const float *p2, int n, const double *K, doub
   run_grid((unsigned)((H + 127) / 128), 1, 1, 128, 0, [&] { k_epi_hypotheses(p1, p2, n, cam, seed, H, Es.data(), valid.data()); });
   const int grid = std::min((H + 7) / 8, 64);                    // any grid covers all hypotheses (grid-stride loop)
   run_grid((unsigned)grid, 1, 1, 256, (size_t)n * 32, [&] { k_epi_score(p1, p2, n, cam, thr2, H, Es.data(), valid.data(), counts.data()); });
-  run_grid(1, 1, 1, EFIN_T, 0, [&] { k_epi_finish(p1, p2, n, cam, thr2, H, Es.data(), counts.data(), out.data(), oi.data(), inliers); });
+  run_clusters(EFIN_C, EFIN_C, EFIN_T, sizeof(EpiFinSmem), [&] { k_epi_finish(p1, p2, n, cam, thr2, H, Es.data(), counts.data(), out.data(), oi.data(), inliers); });
   run_grid((unsigned)((n + 63) / 64), 1, 1, 256, 0, [&] { k_epi_vote(p1, p2, cam, out.data(), oi.data(), inliers); });
   // recoverPose's choice on the host, as mvo_esti_motion_by_essential does it: the first candidate whose vote count is a maximum
   const int32_t *g = oi.data() + 8;
@@ -39,6 +39,7 @@ int emu_essential(const float *p1, const float *p2, int n, const double *K, doub
   memcpy(E, out.data(), 72); memcpy(R, out.data() + ((pick & 1) ? 18 : 9), 72);
   for (int q = 0; q < 3; ++q) t[q] = sg * tt[q] / nt;
   memcpy(out_i, oi.data(), 5 * sizeof(int32_t));
+  if (getenv("MVO_EPI_DEBUG")) fprintf(stderr, "emu_essential: n %d inliers %d GN iterations %d\n", n, oi[0], oi[5]);
   return oi[0];
 }
 
