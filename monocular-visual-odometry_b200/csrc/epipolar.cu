@@ -67,6 +67,23 @@ __global__ void k_epi_math_test(const double *__restrict__ in, double *__restric
   for (int q = 0; q < 3; ++q) out[61 + q] = w2[q];
 }
 
+// one thread-block cluster of EFIN_C CTAs (distributed shared memory between them), all block state in dynamic shared memory
+template <class K, class... A>
+cudaError_t launch_finish_cluster(mvo_ctx *ctx, size_t smem, K kernel, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(EFIN_C);
+  cfg.blockDim = dim3(EFIN_T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = EFIN_C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 }  // namespace
 
 extern "C" int mvo_test_epi_math(mvo_ctx *ctx, const double *in /* 113 */, double *out /* 64 */) {
@@ -121,24 +138,9 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   { KTimer kt(ctx, KC_EPI_SCORE);
   k_epi_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dE, dvalid, dcnt); }
   MVO_CHECK_LAUNCH(ctx);
-  {
-    // one thread-block cluster of EFIN_C CTAs (distributed shared memory between them)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(EFIN_C);
-    cfg.blockDim = dim3(EFIN_T);
-    cfg.dynamicSmemBytes = sizeof(EpiFinSmem);
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = EFIN_C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    KTimer kt(ctx, KC_EPI_FINISH);
-    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_epi_finish, d1, d2, n, cam, thr2, H, (const double *)dE, (const int32_t *)dcnt, dout, dout_i, dinl));
-    ctx->launches++;
-  }
+  { KTimer kt(ctx, KC_EPI_FINISH);
+    MVO_CUDA(ctx, launch_finish_cluster(ctx, sizeof(EpiFinSmem), k_epi_finish, d1, d2, n, cam, thr2, H, (const double *)dE, (const int32_t *)dcnt, dout, dout_i, dinl)); }
+  MVO_CHECK_LAUNCH(ctx);
   { KTimer kt(ctx, KC_EPI);
   k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl); }
   MVO_CHECK_LAUNCH(ctx);
@@ -224,7 +226,7 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
   k_homo_score<<<grid, 256, smem, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dvalid, dcnt); }
   MVO_CHECK_LAUNCH(ctx);
   { KTimer kt(ctx, KC_EPI_FINISH);
-  k_homo_finish<<<1, EFIN_T, 0, ctx->stream>>>(d1, d2, n, cam, thr2, H, dH, dcnt, dout, dout_i, dinl); }
+    MVO_CUDA(ctx, launch_finish_cluster(ctx, sizeof(HomoFinSmem), k_homo_finish, d1, d2, n, cam, thr2, H, (const double *)dH, (const int32_t *)dcnt, dout, dout_i, dinl)); }
   MVO_CHECK_LAUNCH(ctx);
   double *h_out = (double *)(h + al((size_t)n * 16));
   int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);

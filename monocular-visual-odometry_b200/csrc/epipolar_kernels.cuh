@@ -463,13 +463,22 @@ constexpr int HOMO_NV = epi::HOMO_GN_NV;    // 45 entries of J^T J (upper triang
 
 // out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
 // [3] consensus of the best minimal model, [4] consensus after the local optimisation
+// One cluster of EFIN_C CTAs like k_epi_finish: every CTA owns a slice of the correspondences, the partial normal equations are
+// summed in rank order through distributed shared memory (bit-identical in every CTA), thread 0 of every CTA takes the step.
+struct HomoFinSmem {
+  long long k[EFIN_T / 32];
+  double H[9], H0[9], red[EFIN_T / 32][HOMO_NV], part[2][HOMO_NV], sum[HOMO_NV];
+  int cnt[EFIN_T / 32], best, stop, ipart[4];
+};
+
 __global__ void __launch_bounds__(EFIN_T, 1)
 k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, HomoCam cam, double thr2, int H,
               const double *__restrict__ Hs, const int32_t *__restrict__ counts, double *__restrict__ out_d,
               int32_t *__restrict__ out_i, int32_t *__restrict__ inl) {
-  __shared__ long long s_k[32];
-  __shared__ int s_best, s_cnt[32], s_stop;
-  __shared__ double s_H[9], s_H0[9], s_red[32][HOMO_NV], s_sum[HOMO_NV];
+  EPI_DYN_SMEM(double, smraw);
+  HomoFinSmem &S = *reinterpret_cast<HomoFinSmem *>(smraw);
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   long long best = -1;
   for (int h = tid; h < H; h += EFIN_T) {
@@ -478,31 +487,45 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { const long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o > best ? o : best; }
-  if (lane == 0) s_k[warp] = best;
+  if (lane == 0) S.k[warp] = best;
   __syncthreads();
   if (tid == 0) {
     long long b = -1;
-    for (int w = 0; w < EFIN_T / 32; ++w) b = s_k[w] > b ? s_k[w] : b;
-    s_best = (int)(b >> 20) >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
-    out_i[3] = (int)(b >> 20);
+    for (int w = 0; w < EFIN_T / 32; ++w) b = S.k[w] > b ? S.k[w] : b;
+    S.best = (int)(b >> 20) >= 4 ? (int)(0xFFFFF - (b & 0xFFFFF)) : -1;
+    S.ipart[1] = (int)(b >> 20);
+    if (rank == 0) out_i[3] = (int)(b >> 20);
   }
   __syncthreads();
-  if (s_best < 0) {
-    if (tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[4] = 0; }
+  if (S.best < 0) {                                                  // every CTA takes this branch together
+    if (rank == 0 && tid == 0) { out_i[0] = 0; out_i[1] = -1; out_i[4] = 0; }
     return;
   }
-  if (tid < 9) { const double v = Hs[(size_t)s_best * 9 + tid]; s_H[tid] = v; s_H0[tid] = v; }
+  if (tid < 9) { const double v = Hs[(size_t)S.best * 9 + tid]; S.H[tid] = v; S.H0[tid] = v; }
   __syncthreads();
-  const int per = (n + EFIN_T - 1) / EFIN_T, b0 = tid * per, e0 = min(b0 + per, n);
+  const int nthr = (int)csize * EFIN_T, g = (int)rank * EFIN_T + tid;
+  const int per = (n + nthr - 1) / nthr, b0 = min(g * per, n), e0 = min(b0 + per, n);
+  int parity = 0;
+  // cluster-wide sums of the NV per-warp partials in S.red -> S.sum (the same bits in every CTA)
+  auto cluster_sums = [&](int NV) {
+    if (tid < NV) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += S.red[w][tid]; S.part[parity][tid] = v; }
+    cluster.sync();
+    if (tid < NV) {
+      double v = 0;
+      for (unsigned r = 0; r < csize; ++r) v += *cluster.map_shared_rank(&S.part[parity][tid], r);
+      S.sum[tid] = v;
+    }
+    parity ^= 1;
+    __syncthreads();
+  };
   // ---- local optimisation: Gauss-Newton on the transfer error, additive update of the 9 entries (the scale of H is a
   // null direction of the normal equations: a small damping fixes the gauge, H is renormalised after every step) ----
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Hsel[9];
-    for (int q = 0; q < 9; ++q) Hsel[q] = s_H[q];
+    for (int q = 0; q < 9; ++q) Hsel[q] = S.H[q];
     for (int it = 0; it < EPI_GN_ITERS; ++it) {
       double Hc[9];
-      for (int q = 0; q < 9; ++q) Hc[q] = s_H[q];
-      if (tid == 0) s_stop = 0;
+      for (int q = 0; q < 9; ++q) Hc[q] = S.H[q];
       double acc[HOMO_NV];
 #pragma unroll
       for (int q = 0; q < HOMO_NV; ++q) acc[q] = 0;
@@ -517,21 +540,19 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
         double vq = acc[q];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) vq += __shfl_xor_sync(0xffffffffu, vq, d);
-        if (lane == 0) s_red[warp][q] = vq;
+        if (lane == 0) S.red[warp][q] = vq;
       }
       __syncthreads();
-      if (tid < HOMO_NV) { double vq = 0; for (int w = 0; w < EFIN_T / 32; ++w) vq += s_red[w][tid]; s_sum[tid] = vq; }
-      __syncthreads();
+      cluster_sums(HOMO_NV);
       if (tid == 0) {
         double Hn[9];
-        for (int q = 0; q < 9; ++q) Hn[q] = s_H[q];
-        if (epi::homography_gn_step(s_sum, Hn)) s_stop = 1;
-        for (int q = 0; q < 9; ++q) s_H[q] = Hn[q];
+        for (int q = 0; q < 9; ++q) Hn[q] = S.H[q];
+        S.stop = epi::homography_gn_step(S.sum, Hn) ? 1 : 0;
+        for (int q = 0; q < 9; ++q) S.H[q] = Hn[q];
       }
       __syncthreads();
-      if (s_stop) break;
+      if (S.stop) break;
     }
-    __syncthreads();
   }
   // the local optimisation must not lose support: otherwise the minimal model stands
   {
@@ -539,23 +560,23 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
     for (int i = b0; i < e0; ++i) {
       const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
       const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
-      c += epi::homography_transfer_err(s_H, x1, y1, x2, y2) <= thr2;
+      c += epi::homography_transfer_err(S.H, x1, y1, x2, y2) <= thr2;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) s_cnt[warp] = c;
+    if (lane == 0) S.red[warp][0] = (double)c;
     __syncthreads();
+    cluster_sums(1);
     if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < EFIN_T / 32; ++w) tot += s_cnt[w];
-      out_i[4] = tot;
-      if (!(tot >= out_i[3])) for (int q = 0; q < 9; ++q) s_H[q] = s_H0[q];
+      const int tot = (int)S.sum[0];
+      if (rank == 0) out_i[4] = tot;
+      if (!(tot >= S.ipart[1])) for (int q = 0; q < 9; ++q) S.H[q] = S.H0[q];
     }
     __syncthreads();
   }
   // ---- consensus set of the final model, ascending (the mask of findHomography, epipolar_geometry.cpp:108-116) ----
   double Hf[9];
-  for (int q = 0; q < 9; ++q) Hf[q] = s_H[q];
+  for (int q = 0; q < 9; ++q) Hf[q] = S.H[q];
   int mine = 0;
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
@@ -565,25 +586,33 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  if (lane == 31) S.cnt[warp] = incl;
   __syncthreads();
-  if (lane == 31) s_cnt[warp] = incl;
-  __syncthreads();
-  int off = incl - mine, n_in = 0;
-  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += s_cnt[w]; n_in += s_cnt[w]; }
+  int off = incl - mine, cta_total = 0;
+  for (int w = 0; w < EFIN_T / 32; ++w) { if (w < warp) off += S.cnt[w]; cta_total += S.cnt[w]; }
+  if (tid == 0) S.ipart[0] = cta_total;
+  cluster.sync();
+  int n_in = 0;
+  for (unsigned r = 0; r < csize; ++r) {
+    const int c = *cluster.map_shared_rank(&S.ipart[0], r);
+    if (r < rank) off += c;
+    n_in += c;
+  }
   for (int i = b0; i < e0; ++i) {
     const double x1 = ((double)p1[2 * i] - cam.cx) / cam.f, y1 = ((double)p1[2 * i + 1] - cam.cy) / cam.f;
     const double x2 = ((double)p2[2 * i] - cam.cx) / cam.f, y2 = ((double)p2[2 * i + 1] - cam.cy) / cam.f;
     if (epi::homography_transfer_err(Hf, x1, y1, x2, y2) <= thr2) inl[off++] = i;
   }
-  if (tid == 0) {
+  if (rank == 0 && tid == 0) {
     // back to pixel coordinates: x_scaled = S x_pix with S = [1/f 0 -cx/f; 0 1/f -cy/f; 0 0 1]  =>  H_pix = S^-1 H S
     const double f = cam.f, cx = cam.cx, cy = cam.cy;
-    const double S[9] = {1 / f, 0, -cx / f, 0, 1 / f, -cy / f, 0, 0, 1}, Si[9] = {f, 0, cx, 0, f, cy, 0, 0, 1};
+    const double Sm[9] = {1 / f, 0, -cx / f, 0, 1 / f, -cy / f, 0, 0, 1}, Si[9] = {f, 0, cx, 0, f, cy, 0, 0, 1};
     double T[9], Hp[9];
-    epi::mat3_mul(Hf, S, T);
+    epi::mat3_mul(Hf, Sm, T);
     epi::mat3_mul(Si, T, Hp);
     for (int q = 0; q < 9; ++q) out_d[q] = Hp[q] / Hp[8];                       // H /= H(2,2) (:107)
-    out_i[0] = n_in; out_i[1] = s_best;
+    out_i[0] = n_in; out_i[1] = S.best;
   }
+  cluster.sync();                                    // no CTA leaves while another still reads its shared memory
 }
 
