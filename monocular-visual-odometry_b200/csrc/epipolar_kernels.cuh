@@ -75,7 +75,7 @@ __device__ __forceinline__ void skew_times(const double *t, const double *R, dou
   }
 }
 
-__device__ void so3_exp(const double *w, double *R) {
+__device__ __noinline__ void so3_exp(const double *w, double *R) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
   double A, B;
   if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
@@ -87,7 +87,7 @@ __device__ void so3_exp(const double *w, double *R) {
 }
 
 // (R, t) moved by d = (rotation increment on the right, two tangent-plane components of the unit translation)
-__device__ void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
+__device__ __noinline__ void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
   double dR[9];
   so3_exp(d, dR);
   for (int i = 0; i < 3; ++i)
@@ -198,12 +198,14 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
     epi_retract(R, t, d, Rk, tk);
     skew_times(tk, Rk, S.Ek[k]);
   };
+#pragma unroll 1      // one copy of the loop body: unrolled, the 8 x 3 copies (29k instructions) missed the instruction cache every iteration
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Esel[9];
     for (int q = 0; q < 9; ++q) Esel[q] = S.E[q];          // consensus set of this round: fixed during its GN iterations
     if (tid < 6) perturbed_E(tid, S.R, S.t);
     if (tid == 0) S.stop = 0;
     __syncthreads();
+#pragma unroll 1
     for (int it = 0; it < EPI_GN_ITERS; ++it) {
       ++gn_total;
       double acc[20];
@@ -520,9 +522,11 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   };
   // ---- local optimisation: Gauss-Newton on the transfer error, additive update of the 9 entries (the scale of H is a
   // null direction of the normal equations: a small damping fixes the gauge, H is renormalised after every step) ----
+#pragma unroll 1      // one copy of the loop body: unrolled, the 8 x 3 copies (29k instructions) missed the instruction cache every iteration
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Hsel[9];
     for (int q = 0; q < 9; ++q) Hsel[q] = S.H[q];
+#pragma unroll 1
     for (int it = 0; it < EPI_GN_ITERS; ++it) {
       double Hc[9];
       for (int q = 0; q < 9; ++q) Hc[q] = S.H[q];
