@@ -25,6 +25,11 @@
 namespace {
 
 #define EPI_DYN_SMEM(type, name) extern __shared__ type name[]
+#ifdef __CUDACC__
+#define EPI_NOINLINE __noinline__
+#else
+#define EPI_NOINLINE
+#endif
 #include "epipolar_kernels.cuh"
 
 // device-side unit test of epipolar_math.cuh (test hook: tests compare with the host build of the same header)

@@ -75,7 +75,7 @@ __device__ __forceinline__ void skew_times(const double *t, const double *R, dou
   }
 }
 
-__device__ __noinline__ void so3_exp(const double *w, double *R) {
+__device__ EPI_NOINLINE void so3_exp(const double *w, double *R) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
   double A, B;
   if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
@@ -87,7 +87,7 @@ __device__ __noinline__ void so3_exp(const double *w, double *R) {
 }
 
 // (R, t) moved by d = (rotation increment on the right, two tangent-plane components of the unit translation)
-__device__ __noinline__ void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
+__device__ EPI_NOINLINE void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
   double dR[9];
   so3_exp(d, dR);
   for (int i = 0; i < 3; ++i)

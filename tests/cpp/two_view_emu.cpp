@@ -9,6 +9,7 @@
 #include "mvo.h"
 namespace {
 #define EPI_DYN_SMEM(type, name) type *name = (type *)g_dyn_smem
+#define EPI_NOINLINE
 #include "epipolar_kernels.cuh"
 }  // namespace
 
