@@ -75,34 +75,113 @@ __device__ __forceinline__ void skew_times(const double *t, const double *R, dou
   }
 }
 
-__device__ EPI_NOINLINE void so3_exp(const double *w, double *R) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+// exp of a rotation vector.  Below 0.1 rad the two coefficients come from their Taylor series (remainder < 1e-19: the Gauss-Newton
+// steps and the 1e-6 probing rotations all live there), above from sin / cos.
+__device__ __forceinline__ void so3_exp(const double *w, double *R) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   double A, B;
-  if (th < 1e-8) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; }
-  else { A = sin(th) / th; B = (1 - cos(th)) / th2; }
+  if (th2 < 1e-2) {
+    A = 1 - th2 * (1.0 / 6) * (1 - th2 * (1.0 / 20) * (1 - th2 * (1.0 / 42) * (1 - th2 * (1.0 / 72) * (1 - th2 * (1.0 / 110)))));
+    B = 0.5 * (1 - th2 * (1.0 / 12) * (1 - th2 * (1.0 / 30) * (1 - th2 * (1.0 / 56) * (1 - th2 * (1.0 / 90) * (1 - th2 * (1.0 / 132))))));
+  } else {
+    const double th = sqrt(th2);
+    A = sin(th) / th; B = (1 - cos(th)) / th2;
+  }
   const double x = w[0], y = w[1], z = w[2];
   R[0] = 1 - B * (y * y + z * z); R[1] = -A * z + B * x * y;      R[2] = A * y + B * x * z;
   R[3] = A * z + B * x * y;       R[4] = 1 - B * (x * x + z * z); R[5] = -A * x + B * y * z;
   R[6] = -A * y + B * x * z;      R[7] = A * x + B * y * z;       R[8] = 1 - B * (x * x + y * y);
 }
 
-// (R, t) moved by d = (rotation increment on the right, two tangent-plane components of the unit translation)
-__device__ EPI_NOINLINE void epi_retract(const double *R, const double *t, const double *d, double *Ro, double *to) {
-  double dR[9];
+// The estimate the Gauss-Newton iteration of k_epi_finish moves: R, the unit translation t and an orthonormal basis (b1, b2) of
+// the tangent plane of the unit sphere at t.  A step d = (rotation increment on the right, two tangent-plane components).
+struct EpiPose { double R[9], t[3], b1[3], b2[3]; };
+
+__device__ __forceinline__ void epi_tangent_basis(EpiPose &P) {
+  double a[3] = {1, 0, 0};
+  if (fabs(P.t[0]) >= 0.9) { a[0] = 0; a[1] = 1; }
+  epi::cross3(P.t, a, P.b1);
+  const double in1 = 1.0 / sqrt(P.b1[0] * P.b1[0] + P.b1[1] * P.b1[1] + P.b1[2] * P.b1[2]);
+  for (int i = 0; i < 3; ++i) P.b1[i] *= in1;
+  epi::cross3(P.t, P.b1, P.b2);
+}
+
+__device__ __forceinline__ void epi_apply_step(EpiPose &P, const double *d) {
+  double dR[9], Ro[9];
   so3_exp(d, dR);
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) Ro[i * 3 + j] = R[i * 3] * dR[j] + R[i * 3 + 1] * dR[3 + j] + R[i * 3 + 2] * dR[6 + j];
-  double a[3] = {1, 0, 0};
-  if (fabs(t[0]) >= 0.9) { a[0] = 0; a[1] = 1; }
-  double b1[3], b2[3];
-  epi::cross3(t, a, b1);
-  const double n1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
-  for (int i = 0; i < 3; ++i) b1[i] /= n1;
-  epi::cross3(t, b1, b2);
+    for (int j = 0; j < 3; ++j) Ro[i * 3 + j] = P.R[i * 3] * dR[j] + P.R[i * 3 + 1] * dR[3 + j] + P.R[i * 3 + 2] * dR[6 + j];
+  for (int i = 0; i < 9; ++i) P.R[i] = Ro[i];
   double n = 0;
-  for (int i = 0; i < 3; ++i) { to[i] = t[i] + d[3] * b1[i] + d[4] * b2[i]; n += to[i] * to[i]; }
-  n = sqrt(n);
-  for (int i = 0; i < 3; ++i) to[i] /= n;
+  for (int i = 0; i < 3; ++i) { P.t[i] = P.t[i] + d[3] * P.b1[i] + d[4] * P.b2[i]; n += P.t[i] * P.t[i]; }
+  const double in = 1.0 / sqrt(n);
+  for (int i = 0; i < 3; ++i) P.t[i] *= in;
+  epi_tangent_basis(P);
+}
+
+// E at the estimate (k = 0) or at the estimate moved by 1e-6 along tangent direction k - 1 (k = 1..5): a rotation about axis
+// k - 1 (k <= 3), a move of t along b1 / b2 (k = 4, 5)
+__device__ __forceinline__ void epi_probe_E(const EpiPose &P, int k, double *E) {
+  double Rk[9], tk[3];
+  for (int i = 0; i < 9; ++i) Rk[i] = P.R[i];
+  for (int i = 0; i < 3; ++i) tk[i] = P.t[i];
+  if (k >= 1 && k <= 3) {
+    double d[3] = {0, 0, 0}, dR[9];
+    d[k - 1] = 1e-6;
+    so3_exp(d, dR);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Rk[i * 3 + j] = P.R[i * 3] * dR[j] + P.R[i * 3 + 1] * dR[3 + j] + P.R[i * 3 + 2] * dR[6 + j];
+  } else if (k >= 4) {
+    const double *b = k == 4 ? P.b1 : P.b2;
+    double n = 0;
+    for (int i = 0; i < 3; ++i) { tk[i] = P.t[i] + 1e-6 * b[i]; n += tk[i] * tk[i]; }
+    const double in = 1.0 / sqrt(n);
+    for (int i = 0; i < 3; ++i) tk[i] *= in;
+  }
+  skew_times(tk, Rk, E);
+}
+
+// (J^T J + eps I) dx = -J^T r for the 5 x 5 system in sum[0..14] (upper triangle, row-major) / sum[15..19] (J^T r).  The damped
+// matrix is symmetric positive definite: elimination without pivoting, every index static (the 30 entries stay in registers; the
+// pivoting version indexed rows dynamically and ran out of local memory).  false: a non-positive pivot or a non-finite step.
+__device__ __forceinline__ bool epi_solve5(const double *sum, double *dx, double *mx_out) {
+  double A[5][6];
+  int q = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = r; c < 5; ++c) { A[r][c] = sum[q]; A[c][r] = sum[q]; ++q; }
+  double tr = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) tr += A[r][r];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { A[r][r] += 1e-12 * tr + 1e-300; A[r][5] = -sum[15 + r]; }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (!(A[k][k] > 0)) ok = false;
+    const double ip = 1.0 / A[k][k];
+#pragma unroll
+    for (int r = k + 1; r < 5; ++r) {
+      const double f = A[r][k] * ip;
+#pragma unroll
+      for (int c = k + 1; c < 6; ++c) A[r][c] -= f * A[k][c];
+    }
+#pragma unroll
+    for (int c = k + 1; c < 6; ++c) A[k][c] *= ip;                 // row k of the unit upper triangle
+  }
+  double mx = 0;
+#pragma unroll
+  for (int r = 4; r >= 0; --r) {
+    double v = A[r][5];
+#pragma unroll
+    for (int c = r + 1; c < 5; ++c) v -= A[r][c] * dx[c];
+    dx[r] = v;
+  }
+#pragma unroll
+  for (int r = 0; r < 5; ++r) { if (!isfinite(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
+  *mx_out = mx;
+  return ok;
 }
 
 __device__ __forceinline__ double sampson_signed(const double *E, double x1, double y1, double x2, double y2) {
@@ -191,18 +270,18 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   // ---- local optimisation ----
   // Per Gauss-Newton iteration: one pass over the points (every thread its chunk, warp-reduced partial sums), the cluster-wide
   // sums, then lanes 0..5 of warp 0 of every CTA solve the 5 x 5 system (redundantly: identical inputs, identical result), apply
-  // the step and evaluate E at the new estimate (lane 0) / at its five forward perturbations (lanes 1..5).
-  auto perturbed_E = [&](int k, const double *R, const double *t) {       // E at (R, t) retracted by 1e-6 along tangent direction k - 1
-    double d[5] = {0, 0, 0, 0, 0}, Rk[9], tk[3];
-    if (k > 0) d[k - 1] = 1e-6;
-    epi_retract(R, t, d, Rk, tk);
-    skew_times(tk, Rk, S.Ek[k]);
-  };
+  // the step to the estimate they hold in registers and evaluate E there (lane 0) / at its five forward probes (lanes 1..5).
+  // That serial stretch is what an iteration costs (one warp, dependent fp64 chains): it is kept short — static-index solve, series
+  // for the small rotations, reciprocals instead of divisions.
+  EpiPose P;
+  for (int q = 0; q < 9; ++q) P.R[q] = S.R[q];
+  for (int q = 0; q < 3; ++q) P.t[q] = S.t[q];
+  epi_tangent_basis(P);
 #pragma unroll 1      // one copy of the loop body: unrolled, the 8 x 3 copies (29k instructions) missed the instruction cache every iteration
   for (int round = 0; round < EPI_LO_ROUNDS; ++round) {
     double Esel[9];
     for (int q = 0; q < 9; ++q) Esel[q] = S.E[q];          // consensus set of this round: fixed during its GN iterations
-    if (tid < 6) perturbed_E(tid, S.R, S.t);
+    if (tid < 6) epi_probe_E(P, tid, S.Ek[tid]);
     if (tid == 0) S.stop = 0;
     __syncthreads();
 #pragma unroll 1
@@ -238,53 +317,19 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
       double sum[20];
       cluster_sums(sum, 20);
       if (warp == 0) {
-        bool stop = true;
-        double Rn[9], tn[3];
-        for (int r = 0; r < 9; ++r) Rn[r] = S.R[r];
-        for (int r = 0; r < 3; ++r) tn[r] = S.t[r];
-        if (lane < 6) {
-          // (J^T J + eps I) dx = -J^T r by Gaussian elimination with partial pivoting
-          double A[5][6];
-          int q = 0;
-          for (int r = 0; r < 5; ++r) for (int c = r; c < 5; ++c) { A[r][c] = sum[q]; A[c][r] = sum[q]; ++q; }
-          double tr = 0;
-          for (int r = 0; r < 5; ++r) tr += A[r][r];
-          for (int r = 0; r < 5; ++r) { A[r][r] += 1e-12 * tr + 1e-300; A[r][5] = -sum[15 + r]; }
-          bool ok = true;
-          for (int k = 0; k < 5 && ok; ++k) {
-            int pr = k;
-            for (int r = k + 1; r < 5; ++r) if (fabs(A[r][k]) > fabs(A[pr][k])) pr = r;
-            if (!(fabs(A[pr][k]) > 0)) { ok = false; break; }
-            if (pr != k) for (int c = 0; c < 6; ++c) { const double t_ = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t_; }
-            for (int r = k + 1; r < 5; ++r) { const double f = A[r][k] / A[k][k]; for (int c = k; c < 6; ++c) A[r][c] -= f * A[k][c]; }
-          }
-          double dx[5] = {0, 0, 0, 0, 0}, mx = 0;
-          if (ok) {
-            for (int r = 4; r >= 0; --r) { double v = A[r][5]; for (int c = r + 1; c < 5; ++c) v -= A[r][c] * dx[c]; dx[r] = v / A[r][r]; }
-            for (int r = 0; r < 5; ++r) { if (!isfinite(dx[r])) ok = false; mx = fmax(mx, fabs(dx[r])); }
-          }
-          if (ok && mx < 0.5) {                               // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
-            double R2[9], t2[3];
-            epi_retract(Rn, tn, dx, R2, t2);
-            for (int r = 0; r < 9; ++r) Rn[r] = R2[r];
-            for (int r = 0; r < 3; ++r) tn[r] = t2[r];
-          }
-          // forward-difference Jacobian (1e-6 steps): the Gauss-Newton steps bottom out around 1e-9; 1e-8 rad is four orders
-          // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
-          stop = !ok || mx < 1e-8 || mx >= 0.5;
-        }
-        __syncwarp();                                         // every lane has read S.R / S.t
-        if (lane == 0) {
-          for (int r = 0; r < 9; ++r) S.R[r] = Rn[r];
-          for (int r = 0; r < 3; ++r) S.t[r] = tn[r];
-          S.stop = stop ? 1 : 0;
-        }
-        if (lane < 6 && !stop) perturbed_E(lane, Rn, tn);
+        double dx[5] = {0, 0, 0, 0, 0}, mx = 0;
+        const bool ok = epi_solve5(sum, dx, &mx);
+        if (ok && mx < 0.5) epi_apply_step(P, dx);            // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
+        // forward-difference Jacobian (1e-6 probes): the Gauss-Newton steps bottom out around 1e-9; 1e-8 rad is four orders
+        // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
+        const bool stop = !ok || mx < 1e-8 || mx >= 0.5;
+        if (lane == 0) S.stop = stop ? 1 : 0;
+        if (lane < 6 && !stop) epi_probe_E(P, lane, S.Ek[lane]);
       }
       __syncthreads();
       if (S.stop) break;
     }
-    if (tid == 0) skew_times(S.t, S.R, S.E);
+    if (tid == 0) skew_times(P.t, P.R, S.E);
     __syncthreads();
   }
   // the local optimisation must not lose support: otherwise the minimal model stands
@@ -463,8 +508,77 @@ k_homo_score(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
 
 constexpr int HOMO_NV = epi::HOMO_GN_NV;    // 45 entries of J^T J (upper triangle) + 9 of J^T r
 
+// epi::homography_gn_step evaluated by one WARP: lane r holds row r of the augmented 9 x 10 system in registers, the pivot search is a
+// warp arg-max (first row among equals, like the serial scan), row swaps and the pivot row travel by shuffles, the back
+// substitution broadcasts one unknown per step.  Every entry goes through the operations of the serial function in the same
+// order: the results are bit-identical.  (The serial function indexes rows dynamically, i.e. runs out of local memory: ~40 us per
+// call for one thread, against ~2 us here.)  All 32 lanes call it; every lane returns the same flag and the same H.
+__device__ __forceinline__ bool homography_gn_step_warp(const double *sum, double *H) {
+  const int lane = threadIdx.x & 31, r = lane < 9 ? lane : 8;
+  double row[10];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const int lo = r < c ? r : c, hi = r < c ? c : r;
+    row[c] = sum[lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
+  }
+  double mxd = 0;
+#pragma unroll
+  for (int q = 0, d = 0; d < 9; q += 9 - d, ++d) mxd = fmax(mxd, sum[q]);          // the diagonal entries
+#pragma unroll
+  for (int c = 0; c < 9; ++c) if (c == r) row[c] += 1e-9 * mxd + 1e-300;
+  row[9] = -sum[45 + r];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double bv = (lane >= k && lane < 9) ? fabs(row[k]) : -1.0;
+    int br = lane;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+      const int orow = __shfl_xor_sync(0xffffffffu, br, d);
+      if (ov > bv || (ov == bv && orow < br)) { bv = ov; br = orow; }
+    }
+    if (!(bv > 0)) return true;
+    if (br != k) {                                                     // uniform
+      const int src = lane == k ? br : (lane == br ? k : lane);
+#pragma unroll
+      for (int c = 0; c < 10; ++c) row[c] = __shfl_sync(0xffffffffu, row[c], src);
+    }
+    double pk[10];
+#pragma unroll
+    for (int c = k; c < 10; ++c) pk[c] = __shfl_sync(0xffffffffu, row[c], k);
+    if (lane > k && lane < 9) {
+      const double f = row[k] / pk[k];
+#pragma unroll
+      for (int c = k; c < 10; ++c) row[c] -= f * pk[c];
+    }
+  }
+  double dx[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) dx[q] = 0;
+#pragma unroll
+  for (int q = 8; q >= 0; --q) {
+    double vq = row[9];
+#pragma unroll
+    for (int c = q + 1; c < 9; ++c) vq -= row[c] * dx[c];
+    vq = vq / row[q];
+    dx[q] = __shfl_sync(0xffffffffu, vq, q);
+  }
+  double mx = 0;
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { if (!epi::finite_d(dx[q])) bad = true; mx = fmax(mx, fabs(dx[q])); }
+  if (bad || mx >= 0.5) return true;
+  double nrm = 0;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { H[q] += dx[q]; nrm += H[q] * H[q]; }
+  nrm = sqrt(nrm);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) H[q] /= nrm;
+  return mx < 1e-11;
+}
+
 // out_d: [0..8] H in pixel coordinates scaled so that H[8] = 1; out_i: [0] inliers, [1] best hypothesis,
-// [3] consensus of the best minimal model, [4] consensus after the local optimisation
+// [3] consensus of the best minimal model, [4] consensus after the local optimisation, [5] Gauss-Newton iterations run
 // One cluster of EFIN_C CTAs like k_epi_finish: every CTA owns a slice of the correspondences, the partial normal equations are
 // summed in rank order through distributed shared memory (bit-identical in every CTA), thread 0 of every CTA takes the step.
 struct HomoFinSmem {
@@ -507,7 +621,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
   __syncthreads();
   const int nthr = (int)csize * EFIN_T, g = (int)rank * EFIN_T + tid;
   const int per = (n + nthr - 1) / nthr, b0 = min(g * per, n), e0 = min(b0 + per, n);
-  int parity = 0;
+  int parity = 0, gn_total = 0;
   // cluster-wide sums of the NV per-warp partials in S.red -> S.sum (the same bits in every CTA)
   auto cluster_sums = [&](int NV) {
     if (tid < NV) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += S.red[w][tid]; S.part[parity][tid] = v; }
@@ -548,11 +662,13 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
       }
       __syncthreads();
       cluster_sums(HOMO_NV);
-      if (tid == 0) {
+      ++gn_total;
+      if (warp == 0) {
         double Hn[9];
         for (int q = 0; q < 9; ++q) Hn[q] = S.H[q];
-        S.stop = epi::homography_gn_step(S.sum, Hn) ? 1 : 0;
-        for (int q = 0; q < 9; ++q) S.H[q] = Hn[q];
+        const bool stop = homography_gn_step_warp(S.sum, Hn);
+        __syncwarp();                                         // every lane has read S.H
+        if (lane == 0) { S.stop = stop ? 1 : 0; for (int q = 0; q < 9; ++q) S.H[q] = Hn[q]; }
       }
       __syncthreads();
       if (S.stop) break;
@@ -573,7 +689,7 @@ k_homo_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n,
     cluster_sums(1);
     if (tid == 0) {
       const int tot = (int)S.sum[0];
-      if (rank == 0) out_i[4] = tot;
+      if (rank == 0) { out_i[4] = tot; out_i[5] = gn_total; }
       if (!(tot >= S.ipart[1])) for (int q = 0; q < 9; ++q) S.H[q] = S.H0[q];
     }
     __syncthreads();

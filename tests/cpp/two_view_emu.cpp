@@ -55,6 +55,7 @@ int emu_homography(const float *p1, const float *p2, int n, const double *K, dou
   const int grid = std::min((H + 7) / 8, 64);
   run_grid((unsigned)grid, 1, 1, 256, (size_t)n * 32, [&] { k_homo_score(p1, p2, n, cam, thr2, H, Hs.data(), valid.data(), counts.data()); });
   run_clusters(EFIN_C, EFIN_C, EFIN_T, sizeof(HomoFinSmem), [&] { k_homo_finish(p1, p2, n, cam, thr2, H, Hs.data(), counts.data(), out.data(), oi.data(), inliers); });
+  if (getenv("MVO_EPI_DEBUG")) fprintf(stderr, "emu_homography: n %d inliers %d GN iterations %d\n", n, oi[0], oi[5]);
   memcpy(Hout, out.data(), 72);
   memcpy(out_i, oi.data(), 5 * sizeof(int32_t));
   return oi[0];
