@@ -75,14 +75,16 @@ __global__ void k_epi_math_test(const double *__restrict__ in, double *__restric
 // one thread-block cluster of EFIN_C CTAs (distributed shared memory between them), all block state in dynamic shared memory
 template <class K, class... A>
 cudaError_t launch_finish_cluster(mvo_ctx *ctx, size_t smem, K kernel, A... args) {
+  static const int env_c = getenv("MVO_EFIN_CLUSTER") ? atoi(getenv("MVO_EFIN_CLUSTER")) : EFIN_C;     // A/B hook: CTAs per cluster
+  const int csz = (env_c >= 1 && env_c <= 8) ? env_c : EFIN_C;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(EFIN_C);
+  cfg.gridDim = dim3(csz);
   cfg.blockDim = dim3(EFIN_T);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = EFIN_C;
+  attr[0].val.clusterDim.x = csz;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;

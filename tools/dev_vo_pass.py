@@ -19,10 +19,14 @@ for p in range(passes):
     t0 = time.perf_counter()
     vo.prefetch(d[0].data_ptr(), channels=3, stride=1920, on_device=True)
     kf = 0
+    cls = {"init": [], "tracked": [], "keyframe": []}
     for i in range(n):
+        tf = time.perf_counter()
         if i + 1 < n:
             vo.prefetch(d[i + 1].data_ptr(), channels=3, stride=1920, on_device=True)
         T, info = vo.add_frame(d[i].data_ptr(), channels=3, stride=1920, on_device=True)
         kf += info.keyframe
+        cls["keyframe" if info.keyframe else ("tracked" if info.state_in == 2 else "init")].append(time.perf_counter() - tf)
     dt = time.perf_counter() - t0
+    print("  " + ", ".join(f"{k} {len(v)} x {1e3 * sum(v) / max(len(v), 1):.3f} ms" for k, v in cls.items()), flush=True)
     print(f"pass {p}: {n} frames in {1e3 * dt:.1f} ms = {n / dt:.0f} fps, keyframes {kf}, state {info.state_out}, map {info.map_points}", flush=True)
