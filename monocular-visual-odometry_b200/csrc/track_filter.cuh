@@ -70,6 +70,45 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total) {
   return before + incl - v;
 }
 
+// std::__adjust_heap (+ the std::__push_heap it ends with) on h[0, len), comp(x, y) = keypoint index of x < keypoint index of y
+__device__ __forceinline__ void mf_adjust_heap(uint32_t *h, int hole, int len, uint32_t value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if ((h[child] >> 16) < (h[child - 1] >> 16)) --child;
+    h[hole] = h[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h[hole] = h[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && (h[parent] >> 16) < (value >> 16)) {
+    h[hole] = h[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  h[hole] = value;
+}
+
+// What __introsort_loop does with a segment at its depth limit: std::__partial_sort(first, last, last) = __heap_select with an
+// empty tail (= std::__make_heap) followed by std::__sort_heap.  Sequential by nature: one thread per segment.
+__device__ __forceinline__ void mf_heapsort(uint32_t *h, int len) {
+  if (len < 2) return;
+  for (int parent = (len - 2) / 2;; --parent) {
+    mf_adjust_heap(h, parent, len, h[parent]);
+    if (parent == 0) break;
+  }
+  for (int last = len - 1; last > 0; --last) {          // __pop_heap(first, last, last)
+    const uint32_t value = h[last];
+    h[last] = h[0];
+    mf_adjust_heap(h, 0, last, value);
+  }
+}
+
 __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   MVO_DYN_SMEM(uint8_t, smraw);
   const int cap = a.n_cap;
@@ -82,11 +121,11 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   uint32_t *segB = segA + cap / 16 + 2;
   __shared__ int s_warp[MF_T / 32];
   __shared__ unsigned s_min;
-  __shared__ int s_nseg[2], s_status;
+  __shared__ int s_nseg[2], s_status, s_heap_segs, s_heap_max;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmap = a.nmap;
   const bool sad = a.method == 3;
-  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; }
+  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; s_heap_segs = 0; s_heap_max = 0; }
   long long tph = clock64();        // phase cycle counters (thread 0) -> info[4..8]: prologue, compaction, sort levels, epilogue
 #define MF_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); a.info[4 + (i)] = (int32_t)(t_ - tph); tph = t_; } } while (0)
   __syncthreads();
@@ -159,7 +198,17 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   while (true) {
     const int nseg = s_nseg[which];
     if (nseg == 0) break;
-    if (level >= depth_limit) { if (tid == 0) s_status = 1; break; }      // libstdc++ would heapsort from here
+    if (level >= depth_limit) {                         // libstdc++ heapsorts what is left: one thread per segment
+      int big = 0;
+      for (int sg = tid; sg < nseg; sg += MF_T) {
+        const int first = (int)(cur[sg] & 0xFFFFu), last = (int)(cur[sg] >> 16);
+        mf_heapsort(arr + first, last - first);
+        big = max(big, last - first);
+      }
+      if (big) atomicMax(&s_heap_max, big);
+      if (tid == 0) s_heap_segs = nseg;
+      break;
+    }
     // __introsort_loop recurses on [cut, last) and continues with [first, cut): both go to the next level's lists
     auto push = [&](int f, int l) {
       if (l - f <= 16) return;                                              // left to the final insertion sort
@@ -231,7 +280,7 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
     return;
   }
   MF_MARK(1);
-  if (tid == 0) a.info[8] = level;
+  if (tid == 0) { a.info[8] = level; a.info[3] = s_heap_segs; a.info[7] = s_heap_max; }     // [3], [7]: segments heapsorted at the depth limit, the longest
   // ---- final insertion sort is stable: of every run of equal keypoint indices the leftmost element survives ----
   for (int p = tid; p < n; p += MF_T) atomicMin(&best[arr[p] >> 16], ((uint32_t)p << 16) | (arr[p] & 0xFFFFu));
   __syncthreads();

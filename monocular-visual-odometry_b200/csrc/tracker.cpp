@@ -1019,8 +1019,8 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   }
   TMARK(2);
   if (dbg && ++nacc % 50 == 0) {
-    fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f | filter kernel cycles: prologue %d sort %d (%d levels) epilogue %d\n",
-            acc[0] / 50, acc[1] / 50, acc[2] / 50, h_flags[44], h_flags[45], h_flags[48], h_flags[46]);
+    fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f | filter kernel cycles: prologue %d sort %d (%d levels, %d segments heapsorted, longest %d) epilogue %d\n",
+            acc[0] / 50, acc[1] / 50, acc[2] / 50, h_flags[44], h_flags[45], h_flags[48], h_flags[43], h_flags[47], h_flags[46]);
     fprintf(stderr, "  per level (cycles, nbig*1000+nsmall):");
     for (int l = 0; l < 7; ++l) fprintf(stderr, " %d/%d", h_flags[49 + 2 * l], h_flags[50 + 2 * l]);
     fprintf(stderr, "\n");

@@ -40,6 +40,7 @@ def _both(emu, keys, vis, nk, method, xg=2.0, lowe=1.0):
         emu.emu_params_ctx_free(ctx)
     pd, idv = np.full((max(nmap, 1), 2), -1, np.int32), np.zeros(64, np.int32)
     assert emu.emu_match_filter(keys.ctypes.data, vis.ctypes.data, nmap, nk, method, xg, lowe, pd.ctypes.data, idv.ctypes.data) == 0
+    _both.last_info = idv.copy()        # the kernel's full record ([3] segments heapsorted at the depth limit, [7] the longest)
     return ph[: ih[0]], ih[:3], pd[: idv[0]], idv[:3]
 
 
@@ -75,9 +76,10 @@ def test_emulated_filter_methods_2_and_3_and_declines(emu):
     k3[rng.random(nmap) < 0.2] = 0xFFFFFFFF
     ph, ih, pd, idv = _both(emu, k3, vis, nk, 3)
     assert np.array_equal(ih, idv) and np.array_equal(ph, pd) and ih[0] > 0
-    # organ pipe: libstdc++ would leave quicksort for heapsort -> the kernel declines (status 1) with the candidate count set
+    # organ pipe: libstdc++ leaves quicksort for heapsort at its depth limit -> the kernel heapsorts those segments too
     n = 2001
     train = np.minimum(np.arange(n), np.arange(n)[::-1]) % 1003
     keys = (np.full(n, 5, np.uint32) << 16) | train.astype(np.uint32)
-    _, ih, _, idv = _both(emu, keys, np.ones(n, np.uint8), 1003, 1)
-    assert idv[2] == 1 and idv[1] == ih[1] == n
+    ph, ih, pd, idv = _both(emu, keys, np.ones(n, np.uint8), 1003, 1)
+    assert idv[2] == 0 and np.array_equal(ih, idv) and np.array_equal(ph, pd) and idv[1] == n
+    assert _both.last_info[3] > 0 and _both.last_info[7] > 16, _both.last_info[:9]
