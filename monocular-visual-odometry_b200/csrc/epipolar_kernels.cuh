@@ -210,7 +210,7 @@ constexpr int EFIN_C = 8;
 struct EpiFinSmem {
   long long k[EFIN_T / 32];
   double E[9], R1[9], R2[9], t[3], R[9], E0[9];
-  double Ek[6][9], red[EFIN_T / 32][20], part[2][20];
+  double Ek[6][9], red[EFIN_T / 32][20], part[2][20], sumv[20];
   int cnt[EFIN_T / 32], best, stop, ipart[4];
 };
 
@@ -259,13 +259,18 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
   auto cluster_sums = [&](double *sum, int NV) {
     if (tid < NV) { double v = 0; for (int w = 0; w < EFIN_T / 32; ++w) v += S.red[w][tid]; S.part[parity][tid] = v; }
     cluster.sync();                                                  // partials of every CTA are in place (and the previous round's have been read)
-    if (tid < 32)
-      for (int q = 0; q < NV; ++q) {
-        double v = 0;
-        for (unsigned r = 0; r < csize; ++r) v += *cluster.map_shared_rank(&S.part[parity][q], r);      // rank order: identical in every CTA
-        sum[q] = v;
-      }
+    if (tid < NV) {                                                  // one entry per thread, the remote loads in flight together
+      double v[EFIN_C];
+#pragma unroll
+      for (unsigned r = 0; r < EFIN_C; ++r) v[r] = r < csize ? *cluster.map_shared_rank(&S.part[parity][tid], r) : 0.0;
+      double t = 0;
+#pragma unroll
+      for (unsigned r = 0; r < EFIN_C; ++r) t += v[r];               // rank order: identical in every CTA
+      S.sumv[tid] = t;
+    }
     parity ^= 1;
+    __syncthreads();
+    for (int q = 0; q < NV; ++q) sum[q] = S.sumv[q];
   };
   // ---- local optimisation ----
   // Per Gauss-Newton iteration: one pass over the points (every thread its chunk, warp-reduced partial sums), the cluster-wide
@@ -322,7 +327,7 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
         if (ok && mx < 0.5) epi_apply_step(P, dx);            // a Gauss-Newton step of half a radian is not a refinement: keep the estimate
         // forward-difference Jacobian (1e-6 probes): the Gauss-Newton steps bottom out around 1e-9; 1e-8 rad is four orders
         // below what 0.5 px of keypoint noise leaves in the pose (was 1e-10: never reached, 8 iterations every round)
-        const bool stop = !ok || mx < 1e-8 || mx >= 0.5;
+        const bool stop = !ok || mx < (round + 1 < EPI_LO_ROUNDS ? 1e-6 : 1e-8) || mx >= 0.5;      // the last round polishes; the earlier ones only have to settle the consensus set
         if (lane == 0) S.stop = stop ? 1 : 0;
         if (lane < 6 && !stop) epi_probe_E(P, lane, S.Ek[lane]);
       }
@@ -351,12 +356,21 @@ k_epi_finish(const float *__restrict__ p1, const float *__restrict__ p2, int n, 
       if (rank == 0) { out_i[4] = total; out_i[5] = gn_total; }
       long long b = -1;
       for (int w = 0; w < EFIN_T / 32; ++w) b = S.k[w] > b ? S.k[w] : b;
-      if (!(total >= (int)(b >> 20))) for (int q = 0; q < 9; ++q) S.E[q] = S.E0[q];
+      if (!(total >= (int)(b >> 20))) {
+        for (int q = 0; q < 9; ++q) S.E[q] = S.E0[q];                  // R1, R2, t of the minimal model are still in place
+      } else {
+        // decomposeEssentialMat of E = [t]x R without another SVD: the twisted pair is {R, (2 t t^T - I) R} (a half turn about t)
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) {
+            S.R1[i * 3 + j] = P.R[i * 3 + j];
+            S.R2[i * 3 + j] = 2 * P.t[i] * (P.t[0] * P.R[j] + P.t[1] * P.R[3 + j] + P.t[2] * P.R[6 + j]) - P.R[i * 3 + j];
+          }
+        for (int q = 0; q < 3; ++q) S.t[q] = P.t[q];
+      }
     }
     __syncthreads();
   }
   // ---- consensus set of the final model, ascending (the mask of findEssentialMat, epipolar_geometry.cpp:40-47) ----
-  if (tid == 0) epi::decompose_essential(S.E, S.R1, S.R2, S.t);
   double E[9];
   for (int q = 0; q < 9; ++q) E[q] = S.E[q];
   int mine = 0;
