@@ -30,6 +30,7 @@
 #include <string.h>
 #include <vector>
 #include "mvo_internal.h"
+#include "launch_pdl.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -760,6 +761,8 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
   const int tid = threadIdx.x;
+  pdl_wait();                                // PnP finish / the glue kernel wrote what this kernel reads (launch_pdl.cuh)
+  pdl_launch_dependents();
   extern __shared__ __align__(16) double sm[];
   __shared__ int s_ef[PF_T];
   __shared__ double s_c[8];                  // 0 lambda, 2 chi (initial)
@@ -988,21 +991,9 @@ static int pose_launch(mvo_ctx *ctx, void (*kern)(PoseArgs), const PoseArgs &a, 
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "pose BA: shared memory %zu B", smem);
   MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (csz > 8) MVO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(csz);
-  cfg.blockDim = dim3(PF_T);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csz;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   {
     KTimer kt(ctx, KC_BA);
-    MVO_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
+    MVO_CUDA(ctx, launch_pdl(ctx->stream, (unsigned)csz, PF_T, smem, (unsigned)csz, kern, a));      // one cluster; may start under its predecessor's tail
   }
   ctx->launches++;
   return MVO_OK;

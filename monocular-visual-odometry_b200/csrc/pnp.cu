@@ -20,6 +20,7 @@
 namespace {
 
 #define PNP_DYN_SMEM(type, name) extern __shared__ type name[]
+#include "launch_pdl.cuh"
 #include "pnp_kernels.cuh"
 
 }  // namespace
@@ -124,18 +125,20 @@ static int pnp_enqueue(mvo_ctx *ctx, const PnpWs &w, int n, const PnpCam &cam, c
   if (smem > 200 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "solvePnPRansac: more than %d correspondences", 200 * 1024 / 20);
   const double thr2 = (double)ctx->prm.pnp_reproj_error * (double)ctx->prm.pnp_reproj_error;
   { KTimer kt(ctx, KC_PNP_HYP);
-  k_pnp_hypotheses<<<(H + 127) / 128, 128, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, ctx->prm.pnp_seed, H, w.poses, w.valid); }
-  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, launch_pdl(ctx->stream, (unsigned)((H + 127) / 128), 128, 0, 1, k_pnp_hypotheses, (const float *)w.p3, (const float *)w.p2, n, n_dev, cam,
+                           (uint64_t)ctx->prm.pnp_seed, H, w.poses, w.valid)); }
+  ctx->launches++;
   if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pnp_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (H + 7) / 8;                                   // one hypothesis per warp while the CTAs of one wave allow it
   if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
   { KTimer kt(ctx, KC_PNP_SCORE);
-  k_pnp_score<<<grid, 256, smem, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.valid, w.counts); }
-  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, launch_pdl(ctx->stream, (unsigned)grid, 256, smem, 1, k_pnp_score, (const float *)w.p3, (const float *)w.p2, n, n_dev, cam, thr2, H,
+                           (const double *)w.poses, (const int32_t *)w.valid, w.counts)); }
+  ctx->launches++;
   { KTimer kt(ctx, KC_PNP_FINISH);
-  k_pnp_finish<<<1, FIN_T, 0, ctx->stream>>>(w.p3, w.p2, n, n_dev, cam, thr2, H, w.poses, w.counts, 0, ctx->prm.pnp_refine_iters,
-                                             w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef); }
-  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, launch_pdl(ctx->stream, 1, FIN_T, 0, 1, k_pnp_finish, (const float *)w.p3, (const float *)w.p2, n, n_dev, cam, thr2, H,
+                           (const double *)w.poses, (const int32_t *)w.counts, 0, (int)ctx->prm.pnp_refine_iters, w.pose_io, w.out_i, w.inl, w.ex, w.eo, w.ef)); }
+  ctx->launches++;
   ctx->pnp_last_h = H;
   // the refit runs on the consensus set whose size only the device knows: launch it for the
   // worst case E = n with the real count read on the device (edges beyond n_in are masked out)

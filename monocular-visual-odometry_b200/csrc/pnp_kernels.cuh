@@ -3,6 +3,7 @@
 // Included by pnp.cu inside its anonymous namespace.  PNP_DYN_SMEM(type, name) declares the scoring kernel's dynamic shared
 // memory (`extern __shared__ type name[]` for nvcc).
 #pragma once
+#include "pdl_device.cuh"
 
 struct PnpCam { double fx, fy, cx, cy; };
 
@@ -198,6 +199,8 @@ __global__ void __launch_bounds__(128)
 k_pnp_hypotheses(const float *__restrict__ p3, const float *__restrict__ p2, int n, const int32_t *__restrict__ n_dev,
                  PnpCam cam, uint64_t seed, int H, double *__restrict__ poses, int32_t *__restrict__ valid) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();                             // the predecessor (match filter) wrote n_dev / p3 / p2
+  pdl_launch_dependents();
   if (h >= H) return;
   if (n_dev) n = min(n, *n_dev);          // device-resident tracker: the pair count never visited the host
   if (n < 4) { valid[h] = 0; return; }
@@ -253,6 +256,8 @@ k_pnp_score(const float *__restrict__ p3, const float *__restrict__ p2, int n, c
             double thr2, int H, const double *__restrict__ poses, const int32_t *__restrict__ valid, int32_t *__restrict__ counts) {
   PNP_DYN_SMEM(float, s_pts);      // [n][5]: X Y Z u v
   __shared__ float s_wmax[8];
+  pdl_wait();
+  pdl_launch_dependents();
   if (n_dev) n = min(n, *n_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float mloc = 0.f;
@@ -337,6 +342,8 @@ k_pnp_finish(const float *__restrict__ p3, const float *__restrict__ p2, int n, 
   __shared__ int s_best, s_cnt[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_upper = n;                 // the refit is launched for this many edge slots
+  pdl_wait();
+  pdl_launch_dependents();
   if (n_dev) n = min(n, *n_dev);
   int n_in = 0;
   const bool cv_rule = mode == 2;

@@ -16,6 +16,7 @@
 namespace {
 
 #define MVO_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#include "launch_pdl.cuh"
 #include "track_filter.cuh"
 
 __global__ void __launch_bounds__(256)
@@ -86,6 +87,8 @@ struct GlueArgs {
 
 __global__ void __launch_bounds__(1024) k_track_glue(GlueArgs a) {
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   // every thread derives the (uniform) control values itself, so the edge copy below does not wait for thread 0
   int mode = a.mode;
   if (mode == 2) mode = (*a.n_pairs_dev >= a.min_pnp && *a.n_pairs_dev >= 4) ? 1 : 0;     // vo.cpp:304,311
@@ -175,8 +178,8 @@ int mvo_track_glue(mvo_ctx *ctx, const MvoTrackGlue &g) {
   a.map_ids = g.map_ids; a.vis = g.vis; a.nmap = g.nmap; a.vis_cnt = g.vis_cnt; a.match_cnt = g.match_cnt;
   a.skip_flag = g.skip_flag; a.res_i = g.res_i; a.res_d = g.res_d;
   KTimer kt(ctx, KC_TRACK);
-  k_track_glue<<<1, 1024, 0, ctx->stream>>>(a);
-  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, launch_pdl(ctx->stream, 1, 1024, 0, 1, k_track_glue, a));
+  ctx->launches++;
   return MVO_OK;
 }
 
@@ -228,7 +231,7 @@ int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f) {
   const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 2 * ((size_t)cap / 16 + 2) * 4 + 64;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KTimer kt(ctx, KC_TRACK);
-  k_match_filter<<<1, MF_T, smem, ctx->stream>>>(a);
-  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, launch_pdl(ctx->stream, 1, MF_T, smem, 1, k_match_filter, a));
+  ctx->launches++;
   return MVO_OK;
 }

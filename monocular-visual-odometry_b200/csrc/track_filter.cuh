@@ -4,6 +4,7 @@
 // tests/cpp/cuda_emu.h).  Included by track.cu inside an anonymous namespace.
 // MVO_DYN_SMEM(type, name) declares the kernel's dynamic shared memory (`extern __shared__ __align__(16) type name[]` for nvcc).
 #pragma once
+#include "pdl_device.cuh"
 
 struct Rt12 { double v[12]; };   // R row-major (9) + t (3), world->camera
 
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   const int nmap = a.nmap;
   const bool sad = a.method == 3;
   if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; s_heap_segs = 0; s_heap_max = 0; }
+  pdl_wait();                       // first kernel of a tracked frame's chain (see launch_pdl.cuh)
+  pdl_launch_dependents();
   long long tph = clock64();        // phase cycle counters (thread 0) -> info[4..8]: prologue, compaction, sort levels, epilogue
 #define MF_MARK(i) do { if (tid == 0) { const long long t_ = clock64(); a.info[4 + (i)] = (int32_t)(t_ - tph); tph = t_; } } while (0)
   __syncthreads();
