@@ -297,6 +297,34 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
   }
 }
 
+// keep[i] = 1 iff fewer than max_per_cell items j < i lie in item i's cell: the per-cell counter of selectUniformKptsByGrid
+// (feature_match.cpp:68-81) in closed form.  max_per_cell rounds: in round r every pending item bids its index for its cell with an
+// atomicMin, the smallest pending index of a cell wins the round and is kept.  Bids carry the round in their high half
+// ((0xFFFF - r) << 16 | index: later rounds bid lower values), so the two bid arrays (rounds alternate between them) never need a reset,
+// and one block barrier per round suffices: winners of round r - 1 are read from the array round r does not write.
+// (Round 1 ranked every item against its whole cell bucket: quadratic in the population of the crowded cells.)
+// Called by all 1024 threads; s_min: 2 * ncell words; item indices < 65536.
+__device__ __forceinline__ void grid_rank_keep(int n, const uint16_t *__restrict__ s_cell, uint8_t *__restrict__ s_keep, uint32_t *__restrict__ s_min,
+                                               int ncell, int max_per_cell) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * ncell; i += 1024) s_min[i] = 0xFFFFFFFFu;
+  for (int i = tid; i < n; i += 1024) s_keep[i] = 0;
+  __syncthreads();
+  max_per_cell = min(max_per_cell, n);                     // a cell never holds more than n items (keeps the round tag inside 16 bits)
+  for (int r = 0; r <= max_per_cell; ++r) {
+    uint32_t *cur = s_min + (r & 1) * ncell;
+    const uint32_t *prev = s_min + ((r & 1) ^ 1) * ncell;
+    const uint32_t tag = (uint32_t)(0xFFFF - r) << 16, tag_prev = (uint32_t)(0xFFFF - (r - 1)) << 16;
+    for (int i = tid; i < n; i += 1024) {
+      if (s_keep[i]) continue;
+      const int c = s_cell[i];
+      if (r > 0 && prev[c] == (tag_prev | (uint32_t)i)) { s_keep[i] = 1; continue; }
+      if (r < max_per_cell) atomicMin(&cur[c], tag | (uint32_t)i);
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------- select
 // Restates feature_match.cpp:68-81: walking keypoints in order, a keypoint is kept iff fewer than
 // max_per_cell earlier keypoints fell into its 16x16 cell, and the walk stops right after the
@@ -355,7 +383,6 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
     meta[f].n_cand = n;
     if (ovf) meta[f].n_sel = 0;
   }
-  for (int i = tid; i <= ncell; i += 1024) s_cellcnt[i] = 0;
   __syncthreads();
   const bool ovf = s_overflow != 0;
 
@@ -380,7 +407,6 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
           col = min(col, plan.grid_cols - 1);
           const int cell = row * plan.grid_cols + col;
           s_cell[o + i] = (uint16_t)cell;
-          atomicAdd(&s_cellcnt[cell], 1);
         }
       }
     }
@@ -388,42 +414,7 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
   __syncthreads();
   if (ovf) return;
 
-  // exclusive scan over cells (ncell <= 65535): chunked per thread
-  {
-    const int per = (ncell + 1023) >> 10;
-    const int b = tid * per, e = min(b + per, ncell);
-    int mine = 0;
-    for (int i = b; i < e; ++i) mine += s_cellcnt[i];
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    __syncthreads();
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int off = incl - mine;
-    for (int k = 0; k < warp; ++k) off += s_warp[k];
-    for (int i = b; i < e; ++i) {
-      const int c = s_cellcnt[i];
-      s_cellcnt[i] = off;
-      s_cursor[i] = off;
-      off += c;
-    }
-    if (tid == 1023) s_cellcnt[ncell] = n;
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += 1024) s_bucket[atomicAdd(&s_cursor[s_cell[i]], 1)] = (uint16_t)i;
-  __syncthreads();
-  // rank of candidate i inside its cell = number of smaller candidate ids in the same bucket
-  for (int i = tid; i < n; i += 1024) {
-    const int c = s_cell[i];
-    int rank = 0;
-    for (int k = s_cellcnt[c]; k < s_cellcnt[c + 1]; ++k) rank += (s_bucket[k] < i);
-    s_keep[i] = rank < plan.max_per_cell;
-  }
-  __syncthreads();
+  grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);     // s_cellcnt + s_cursor: 2 * ncell + 1 words
   // ordered prefix count of kept0 (contiguous chunk per thread), cut after max_kpts + 1
   {
     const int per = (n + 1023) >> 10;
@@ -481,7 +472,7 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
 // a prefix over the warps places them), shorter ones by warp 0 alone.
 constexpr int RET_MAX = 12288;       // candidates of one level the device path holds; more -> host path
 constexpr int RET_T = 256, RET_W = RET_T / 32;
-constexpr int RET_WARP_LEN = 768;
+constexpr int RET_WARP_LEN = 256;      // ranges from this length on are scanned by the whole CTA (round 2: 768; one warp needed ~100 cycles per 32 elements)
 
 struct RetBuf { float *key; uint16_t *idx, *Ls, *Rs; int *s_i; };   // s_i: 2 * RET_W + 8 ints of block scratch
 
@@ -499,15 +490,21 @@ __device__ __forceinline__ void ret_stop_lists(const RetBuf &b, int lo, int len,
   const unsigned below = (1u << lane) - 1u;
   if (!WHOLE) {
     nL = nR = 0;
-    for (int base = 0; base < len; base += 32) {
-      const int i = base + lane;
-      const bool inr = i < len;
-      const bool ls = inr && left(b.key[lo + i]), rs = inr && right(b.key[top - i]);
-      const unsigned bl = __ballot_sync(0xffffffffu, ls), br = __ballot_sync(0xffffffffu, rs);
-      if (ls) b.Ls[lo + nL + __popc(bl & below)] = (uint16_t)(lo + i);
-      if (rs) b.Rs[lo + nR + __popc(br & below)] = (uint16_t)(top - i);
-      nL += __popc(bl);
-      nR += __popc(br);
+    for (int base = 0; base < len; base += 64) {          // two 32-element groups per trip: four independent loads in flight
+      const int i0 = base + lane, i1 = i0 + 32;
+      const bool in0 = i0 < len, in1 = i1 < len;
+      const float kl0 = in0 ? b.key[lo + i0] : 0.f, kr0 = in0 ? b.key[top - i0] : 0.f;
+      const float kl1 = in1 ? b.key[lo + i1] : 0.f, kr1 = in1 ? b.key[top - i1] : 0.f;
+      const bool ls0 = in0 && left(kl0), rs0 = in0 && right(kr0), ls1 = in1 && left(kl1), rs1 = in1 && right(kr1);
+      const unsigned bl0 = __ballot_sync(0xffffffffu, ls0), br0 = __ballot_sync(0xffffffffu, rs0);
+      const unsigned bl1 = __ballot_sync(0xffffffffu, ls1), br1 = __ballot_sync(0xffffffffu, rs1);
+      const int cl0 = __popc(bl0), cr0 = __popc(br0);
+      if (ls0) b.Ls[lo + nL + __popc(bl0 & below)] = (uint16_t)(lo + i0);
+      if (rs0) b.Rs[lo + nR + __popc(br0 & below)] = (uint16_t)(top - i0);
+      if (ls1) b.Ls[lo + nL + cl0 + __popc(bl1 & below)] = (uint16_t)(lo + i1);
+      if (rs1) b.Rs[lo + nR + cr0 + __popc(br1 & below)] = (uint16_t)(top - i1);
+      nL += cl0 + __popc(bl1);
+      nR += cr0 + __popc(br1);
     }
     __syncwarp();
     return;
@@ -716,7 +713,6 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
     for (int l = 0; l < plan.nlevels; ++l) { s_off[l] = o; s_base[l] = bb; o += kept_cnt[f * plan.nlevels + l]; bb += meta[f].lvl_count[l]; }
     s_off[plan.nlevels] = o;
   }
-  for (int i = tid; i <= ncell; i += 1024) s_cellcnt[i] = 0;
   __syncthreads();
   const int n = s_off[plan.nlevels];
   if (n > scap) {                                                   // ties at the Harris cut beyond nfeatures: host path
@@ -736,34 +732,9 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
     col = min(col, plan.grid_cols - 1);
     const int cell = row * plan.grid_cols + col;
     s_pk[i] = p; s_lvl[i] = (uint8_t)l; s_cell[i] = (uint16_t)cell;
-    atomicAdd(&s_cellcnt[cell], 1);
   }
   __syncthreads();
-  {
-    const int per = (ncell + 1023) >> 10;
-    const int b = tid * per, e = min(b + per, ncell);
-    int mine = 0;
-    for (int i = b; i < e; ++i) mine += s_cellcnt[i];
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int off = incl - mine;
-    for (int k = 0; k < warp; ++k) off += s_warp[k];
-    for (int i = b; i < e; ++i) { const int c = s_cellcnt[i]; s_cellcnt[i] = off; s_cursor[i] = off; off += c; }
-    if (tid == 1023) s_cellcnt[ncell] = n;
-  }
-  __syncthreads();
-  for (int i = tid; i < n; i += 1024) s_bucket[atomicAdd(&s_cursor[s_cell[i]], 1)] = (uint16_t)i;
-  __syncthreads();
-  for (int i = tid; i < n; i += 1024) {
-    const int c = s_cell[i];
-    int rank = 0;
-    for (int k = s_cellcnt[c]; k < s_cellcnt[c + 1]; ++k) rank += (s_bucket[k] < i);
-    s_keep[i] = rank < plan.max_per_cell;
-  }
-  __syncthreads();
+  grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);
   {
     const int per = (n + 1023) >> 10;
     const int b = tid * per, e = min(b + per, n);
