@@ -1011,7 +1011,8 @@ int mvo_ba_pose_launch(mvo_ctx *ctx, int F, int E, int chunk, const int32_t *d_e
   a.i00 = info[0]; a.i01 = info[1]; a.i10 = info[2]; a.i11 = info[3];
   a.huber = huber; a.step_tol = step_tol;
   a.e_frame = d_eframe; a.X = d_X; a.obs = d_obs; a.poses = d_poses; a.stats = d_stats;
-  const int csz = pose_cluster_size();
+  static const int env_refit = getenv("MVO_REFIT_CLUSTER") ? atoi(getenv("MVO_REFIT_CLUSTER")) : 0;      // A/B hook for the one-frame problems
+  const int csz = (env_refit >= 1 && env_refit <= PF_MAXC) ? env_refit : pose_cluster_size();
   const bool cached = chunk >= 1 && chunk <= 4 && E / chunk <= csz * PF_T;
   const size_t smem = pose_smem_doubles(F, cached ? chunk : 0) * sizeof(double);
   void (*kern)(PoseArgs) = k_ba_pose<1, false, false>;
