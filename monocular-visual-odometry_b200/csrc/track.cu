@@ -228,7 +228,7 @@ int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f) {
     a.fcols = (float)f.cols; a.frows = (float)f.rows;
   }
   a.kpts = f.d_kpts; a.p3 = f.d_p3; a.p2 = f.d_p2;
-  const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 2 * ((size_t)cap / 16 + 2) * 4 + 64;
+  const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 3 * ((size_t)cap / 16 + 2) * 4 + ((size_t)cap / 16 + 2) + 64;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_match_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KTimer kt(ctx, KC_TRACK);
   MVO_CUDA(ctx, launch_pdl(ctx->stream, 1, MF_T, smem, 1, k_match_filter, a));

@@ -110,6 +110,125 @@ __device__ __forceinline__ void mf_heapsort(uint32_t *h, int len) {
   }
 }
 
+constexpr int MF_CTA_LEN = 384;      // segments from this length on are partitioned by the whole CTA
+constexpr int MF_DFS_LEN = 128;      // segments up to this length are finished (their whole subtree) by one warp, without block barriers
+constexpr int MF_STACK = 40;         // per-warp stack of the depth-first phase (>= 2 lg(MF_MAXN) + a margin)
+
+// std::__unguarded_partition_pivot(first, last, by keypoint index) evaluated by one warp; returns the cut (uniform over the warp).
+// The stop positions of the left scan (Lo) and of the right scan (Ro) are properties of the range before any swap, the k-th swap pairs
+// Lo[k] with Ro[k] while Lo[k] < Ro[k], the cut is min(Lo[K], Ro[K-1]).
+__device__ __forceinline__ int mf_partition_warp(uint32_t *arr, uint16_t *Ls, uint16_t *Rs, int first, int last) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {                         // __move_median_to_first(first, first+1, mid, last-1)
+    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+    const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
+    int pick;
+    if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+    else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+    const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
+  }
+  __syncwarp();
+  const uint32_t pivot = arr[first] >> 16;
+  const int lo = first + 1, len = last - lo;
+  const unsigned below = (1u << lane) - 1u;
+  int nL = 0, nR = 0;
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < len;
+    const bool ge = inr && (arr[lo + i] >> 16) >= pivot;              // !(x < pivot): the left scan stops here
+    const bool le = inr && (arr[last - 1 - i] >> 16) <= pivot;        // !(pivot < x): the right scan stops here
+    const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
+    if (ge) Ls[lo + nL + __popc(bg & below)] = (uint16_t)(lo + i);
+    if (le) Rs[lo + nR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
+    nL += __popc(bg);
+    nR += __popc(bl);
+  }
+  __syncwarp();
+  const int nmin = min(nL, nR);
+  int K = 0;
+  for (int base = 0; base < nmin; base += 32) {
+    const int j = base + lane;
+    const bool sw = j < nmin && Ls[lo + j] < Rs[lo + j];
+    const unsigned b = __ballot_sync(0xffffffffu, sw);
+    if (sw) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
+    const int c = __popc(b);
+    K += c;
+    if (c < 32) break;
+  }
+  __syncwarp();
+  int cut;
+  if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;                      // Lo[0] exists after the median step
+  else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
+  return cut;
+}
+
+// the same partition by the whole CTA (MF_T threads): every warp lists the stops of its chunk, a prefix over the warps places them.
+// s_scr: 2 * 32 + 2 ints.  Block barriers inside: called by all threads with uniform arguments.
+__device__ __forceinline__ int mf_partition_cta(uint32_t *arr, uint16_t *Ls, uint16_t *Rs, int first, int last, int *s_scr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+    const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
+    int pick;
+    if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
+    else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
+    const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
+    s_scr[64] = 0;
+  }
+  __syncthreads();
+  const uint32_t pivot = arr[first] >> 16;
+  const int lo = first + 1, len = last - lo;
+  const unsigned below = (1u << lane) - 1u;
+  const int chunk = ((len + MF_T - 1) / MF_T) * 32;                   // per warp, a multiple of 32
+  const int c0 = min(warp * chunk, len), c1 = min(c0 + chunk, len);
+  int cl = 0, cr = 0;
+  for (int base = c0; base < c1; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < c1;
+    cl += __popc(__ballot_sync(0xffffffffu, inr && (arr[lo + i] >> 16) >= pivot));
+    cr += __popc(__ballot_sync(0xffffffffu, inr && (arr[last - 1 - i] >> 16) <= pivot));
+  }
+  if (lane == 0) { s_scr[warp] = cl; s_scr[32 + warp] = cr; }
+  __syncthreads();
+  int oL = 0, oR = 0, nL = 0, nR = 0;
+  {
+    const int vl = s_scr[lane], vr = s_scr[32 + lane];
+    int il = vl, ir = vr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ul = __shfl_up_sync(0xffffffffu, il, o), ur = __shfl_up_sync(0xffffffffu, ir, o);
+      if (lane >= o) { il += ul; ir += ur; }
+    }
+    nL = __shfl_sync(0xffffffffu, il, 31); nR = __shfl_sync(0xffffffffu, ir, 31);
+    oL = __shfl_sync(0xffffffffu, il - vl, warp); oR = __shfl_sync(0xffffffffu, ir - vr, warp);
+  }
+  for (int base = c0; base < c1; base += 32) {
+    const int i = base + lane;
+    const bool inr = i < c1;
+    const bool ge = inr && (arr[lo + i] >> 16) >= pivot, le = inr && (arr[last - 1 - i] >> 16) <= pivot;
+    const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
+    if (ge) Ls[lo + oL + __popc(bg & below)] = (uint16_t)(lo + i);
+    if (le) Rs[lo + oR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
+    oL += __popc(bg);
+    oR += __popc(bl);
+  }
+  __syncthreads();
+  const int nmin = min(nL, nR);
+  int mine = 0;
+  for (int j = tid; j < nmin; j += MF_T)                              // Ls ascends, Rs descends: the condition holds on a prefix
+    if (Ls[lo + j] < Rs[lo + j]) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; ++mine; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0 && mine) atomicAdd(&s_scr[64], mine);
+  __syncthreads();
+  const int K = s_scr[64];
+  int cut;
+  if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;
+  else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
+  __syncthreads();                                                    // s_scr is free again
+  return cut;
+}
+
 __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   MVO_DYN_SMEM(uint8_t, smraw);
   const int cap = a.n_cap;
@@ -120,13 +239,17 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   uint16_t *Rs = Ls + cap;                              // [cap]
   uint32_t *segA = (uint32_t *)(Rs + cap);              // [cap/16 + 2] segments of the current level (first | last << 16)
   uint32_t *segB = segA + cap / 16 + 2;
+  uint32_t *dfs_seg = segB + cap / 16 + 2;              // [cap/16 + 2] segments of the depth-first phase
+  uint8_t *dfs_lvl = (uint8_t *)(dfs_seg + cap / 16 + 2);   // [cap/16 + 2] their partition depth
   __shared__ int s_warp[MF_T / 32];
   __shared__ unsigned s_min;
-  __shared__ int s_nseg[2], s_status, s_heap_segs, s_heap_max;
+  __shared__ int s_nseg[2], s_status, s_heap_segs, s_heap_max, s_ndfs, s_scr[66];
+  __shared__ uint32_t dfs_stack[(MF_T / 32) * MF_STACK];
+  __shared__ uint8_t dfs_stack_lvl[(MF_T / 32) * MF_STACK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmap = a.nmap;
   const bool sad = a.method == 3;
-  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; s_heap_segs = 0; s_heap_max = 0; }
+  if (tid == 0) { s_min = 0xFFFFFFFFu; s_status = 0; s_nseg[0] = s_nseg[1] = 0; s_heap_segs = 0; s_heap_max = 0; s_ndfs = 0; }
   pdl_wait();                       // first kernel of a tracked frame's chain (see launch_pdl.cuh)
   pdl_launch_dependents();
   long long tph = clock64();        // phase cycle counters (thread 0) -> info[4..8]: prologue, compaction, sort levels, epilogue
@@ -191,13 +314,24 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   if (tid == 0 && n > 16) { segA[0] = 0u | ((uint32_t)n << 16); s_nseg[0] = 1; }
   __syncthreads();
   MF_MARK(0);
-  // ---- quicksort phase of std::sort, level by level ----
+  // ---- quicksort phase of std::sort ----
+  // Level by level while segments are long (a list per level; segments of MF_CTA_LEN elements or more are partitioned by the whole
+  // CTA one after the other, the others by one warp each); a segment of at most MF_DFS_LEN elements goes to the list of the
+  // depth-first phase, where one warp finishes its whole subtree without a block barrier (round 2: every level cost two
+  // block barriers, ~1600 cycles even when all its segments were short; 10-13 levels per frame).
   int depth_limit = 0;
   for (int m = n; m > 1; m >>= 1) ++depth_limit;        // std::__lg(n)
   depth_limit *= 2;
   uint32_t *cur = segA, *nxt = segB;
   int level = 0, which = 0;
   long long tlev = clock64();
+  // [first, last) at partition depth lv: to the next level's list, to the depth-first list, or (<= 16) left to the final insertion sort
+  auto push = [&](int f, int l, int lv, int nxt_list) {
+    if (l - f <= 16) return;
+    const uint32_t seg = (uint32_t)f | ((uint32_t)l << 16);
+    if (l - f <= MF_DFS_LEN) { const int k = atomicAdd(&s_ndfs, 1); dfs_seg[k] = seg; dfs_lvl[k] = (uint8_t)min(lv, 255); }
+    else nxt[atomicAdd(&s_nseg[nxt_list], 1)] = seg;
+  };
   while (true) {
     const int nseg = s_nseg[which];
     if (nseg == 0) break;
@@ -209,63 +343,21 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
         big = max(big, last - first);
       }
       if (big) atomicMax(&s_heap_max, big);
-      if (tid == 0) s_heap_segs = nseg;
+      if (tid == 0) atomicAdd(&s_heap_segs, nseg);
       break;
     }
-    // __introsort_loop recurses on [cut, last) and continues with [first, cut): both go to the next level's lists
-    auto push = [&](int f, int l) {
-      if (l - f <= 16) return;                                              // left to the final insertion sort
-      const uint32_t seg = (uint32_t)f | ((uint32_t)l << 16);
-      nxt[atomicAdd(&s_nseg[which ^ 1], 1)] = seg;
-    };
-    // one warp per segment
-    for (int s = warp; s < nseg; s += MF_T / 32) {
-      const int first = (int)(cur[s] & 0xFFFFu), last = (int)(cur[s] >> 16);
-      // __move_median_to_first(first, first+1, mid, last-1)
-      if (lane == 0) {
-        const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
-        const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
-        int pick;
-        if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
-        else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
-        const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
-      }
-      __syncwarp();
-      const uint32_t pivot = arr[first] >> 16;
-      const int lo = first + 1, len = last - lo;
-      int nL = 0, nR = 0;
-      for (int base = 0; base < len; base += 32) {
-        const int i = base + lane;
-        const bool inr = i < len;
-        const bool ge = inr && (arr[lo + i] >> 16) >= pivot;              // !(x < pivot): the left scan stops here
-        const bool le = inr && (arr[last - 1 - i] >> 16) <= pivot;        // !(pivot < x): the right scan stops here
-        const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
-        const unsigned below = (1u << lane) - 1u;
-        if (ge) Ls[lo + nL + __popc(bg & below)] = (uint16_t)(lo + i);
-        if (le) Rs[lo + nR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
-        nL += __popc(bg);
-        nR += __popc(bl);
-      }
-      __syncwarp();
-      const int nmin = min(nL, nR);
-      int K = 0;
-      for (int base = 0; base < nmin; base += 32) {
-        const int j = base + lane;
-        const bool sw = j < nmin && Ls[lo + j] < Rs[lo + j];
-        const unsigned b = __ballot_sync(0xffffffffu, sw);
-        if (sw) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; }
-        const int c = __popc(b);
-        K += c;
-        if (c < 32) break;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        int cut;
-        if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;                    // Lo[0] exists after the median step
-        else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
-        push(cut, last);
-        push(first, cut);
-      }
+    // __introsort_loop recurses on [cut, last) and continues with [first, cut): both are pushed
+    for (int sg = 0; sg < nseg; ++sg) {                 // the long segments: whole CTA (uniform loop)
+      const int first = (int)(cur[sg] & 0xFFFFu), last = (int)(cur[sg] >> 16);
+      if (last - first < MF_CTA_LEN) continue;
+      const int cut = mf_partition_cta(arr, Ls, Rs, first, last, s_scr);
+      if (tid == 0) { push(cut, last, level + 1, which ^ 1); push(first, cut, level + 1, which ^ 1); }
+    }
+    for (int sg = warp; sg < nseg; sg += MF_T / 32) {   // the others: one warp per segment
+      const int first = (int)(cur[sg] & 0xFFFFu), last = (int)(cur[sg] >> 16);
+      if (last - first >= MF_CTA_LEN) continue;
+      const int cut = mf_partition_warp(arr, Ls, Rs, first, last);
+      if (lane == 0) { push(cut, last, level + 1, which ^ 1); push(first, cut, level + 1, which ^ 1); }
     }
     __syncthreads();
     if (tid == 0) {
@@ -276,6 +368,38 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
     uint32_t *t = cur; cur = nxt; nxt = t;
     ++level;
     __syncthreads();
+  }
+  __syncthreads();
+  // ---- depth-first phase: one warp per listed segment, explicit stack in shared memory ----
+  {
+    const int ndfs = s_ndfs;
+    uint32_t *stk = dfs_stack + warp * MF_STACK;
+    uint8_t *stl = dfs_stack_lvl + warp * MF_STACK;
+    int heap_segs = 0, heap_max = 0;
+    for (int sg = warp; sg < ndfs; sg += MF_T / 32) {
+      int sp = 0;
+      int first = (int)(dfs_seg[sg] & 0xFFFFu), last = (int)(dfs_seg[sg] >> 16), lv = dfs_lvl[sg];
+      while (true) {
+        // std::__introsort_loop(first, last, depth): while (last - first > 16) { depth limit -> heapsort; partition; recurse right; last = cut }
+        while (last - first > 16) {
+          if (lv >= depth_limit || sp >= MF_STACK) {   // (the stack bound cannot bind before the depth limit does)
+            if (lane == 0) mf_heapsort(arr + first, last - first);
+            __syncwarp();
+            ++heap_segs; heap_max = max(heap_max, last - first);
+            break;
+          }
+          const int cut = mf_partition_warp(arr, Ls, Rs, first, last);
+          ++lv;
+          if (last - cut > 16) { if (lane == 0) { stk[sp] = (uint32_t)cut | ((uint32_t)last << 16); stl[sp] = (uint8_t)min(lv, 255); } ++sp; }
+          last = cut;
+        }
+        if (sp == 0) break;
+        --sp;
+        __syncwarp();
+        first = (int)(stk[sp] & 0xFFFFu); last = (int)(stk[sp] >> 16); lv = stl[sp];
+      }
+    }
+    if (lane == 0 && heap_segs) { atomicAdd(&s_heap_segs, heap_segs); atomicMax(&s_heap_max, heap_max); }
   }
   __syncthreads();
   if (s_status != 0) {

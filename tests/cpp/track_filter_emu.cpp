@@ -33,7 +33,7 @@ int emu_match_filter(const uint32_t *keys, const uint8_t *vis, int nmap, int nk,
   a.keys = keys; a.vis = v.data(); a.nmap = nmap; a.nk = nk; a.method = method; a.n_cap = cap;
   a.xg_ratio = xiang_gao_ratio; a.lowe_ratio = lowe_ratio;
   a.pairs = (int2 *)pairs; a.info = info;
-  const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 2 * ((size_t)cap / 16 + 2) * 4 + 64;
+  const size_t smem = (size_t)cap * (4 + 4 + 2 + 2 + 2) + 3 * ((size_t)cap / 16 + 2) * 4 + ((size_t)cap / 16 + 2) + 64;
   run_grid(1, 1, 1, MF_T, smem, [&] { k_match_filter(a); });
   return 0;
 }
