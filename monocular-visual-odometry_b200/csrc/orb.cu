@@ -297,6 +297,14 @@ k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict
   }
 }
 
+// cell index = (int)coordinate / grid_size (feature_match.cpp:70): a shift when the grid size is a power of two (the coordinates are >= 0)
+__device__ __forceinline__ int orb_grid_shift(int g) {
+  if (g <= 0 || (g & (g - 1)) != 0) return -1;
+  int sh = 0;
+  while ((1 << sh) < g) ++sh;
+  return sh;
+}
+
 // keep[i] = 1 iff fewer than max_per_cell items j < i lie in item i's cell: the per-cell counter of selectUniformKptsByGrid
 // (feature_match.cpp:68-81) in closed form.  max_per_cell rounds: in round r every pending item bids its index for its cell with an
 // atomicMin, the smallest pending index of a cell wins the round and is kept.  Bids carry the round in their high half
@@ -387,6 +395,7 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
   const bool ovf = s_overflow != 0;
 
   // gather the band staging into the compact, level-major raster-ordered candidate array
+  const int gshift = orb_grid_shift(plan.grid_size);
   uint32_t *cf = cand + (size_t)f * cap;
   for (int b = warp; b < nb; b += 32) {
     const int o = s_boff[b], c = s_boff[b + 1] - o;
@@ -402,7 +411,7 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
           // feature_match.cpp:70: row = ((int)kpt.pt.y) / grid, col = ((int)kpt.pt.x) / grid
           const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
           const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
-          int row = ((int)fy) / plan.grid_size, col = ((int)fx) / plan.grid_size;
+          int row = gshift >= 0 ? ((int)fy) >> gshift : ((int)fy) / plan.grid_size, col = gshift >= 0 ? ((int)fx) >> gshift : ((int)fx) / plan.grid_size;
           row = min(row, plan.grid_rows - 1);
           col = min(col, plan.grid_cols - 1);
           const int cell = row * plan.grid_cols + col;
@@ -720,6 +729,7 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
     return;
   }
   const uint32_t *cf = cand + (size_t)f * plan.cand_cap;
+  const int gshift = orb_grid_shift(plan.grid_size);
   for (int i = tid; i < n; i += 1024) {
     int l = 0;
     while (l + 1 < plan.nlevels && i >= s_off[l + 1]) ++l;
@@ -727,7 +737,7 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
     const float scale = plan.lv[l].scale;
     const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
     const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
-    int row = ((int)fy) / plan.grid_size, col = ((int)fx) / plan.grid_size;
+    int row = gshift >= 0 ? ((int)fy) >> gshift : ((int)fy) / plan.grid_size, col = gshift >= 0 ? ((int)fx) >> gshift : ((int)fx) / plan.grid_size;
     row = min(row, plan.grid_rows - 1);
     col = min(col, plan.grid_cols - 1);
     const int cell = row * plan.grid_cols + col;

@@ -640,7 +640,15 @@ int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t s
     const int rc = dev_alloc(t);
     if (rc != MVO_OK) { wait_job(t, slot); job.state.store(0, std::memory_order_release); ++t->n_consume; return rc; }
   }
+  static const bool dbg_wait = getenv("MVO_TRACK_DEBUG") != nullptr;
+  const double tw0 = dbg_wait ? now_us() : 0;
   wait_job(t, slot);
+  if (dbg_wait) {                        // how long the tracking thread stood waiting for the extraction worker
+    static double acc_wait = 0;
+    static int n_wait = 0;
+    acc_wait += now_us() - tw0;
+    if (++n_wait % 50 == 0) { fprintf(stderr, "tracker: waited %.1f us/frame for the extraction of the frame\n", acc_wait / 50); acc_wait = 0; }
+  }
   ++t->n_consume;
   if (job.rc != MVO_OK) {
     const int rc = mvo_fail(ctx, job.rc, "tracker: %s", mvo_last_error(t->xctx[slot]));
