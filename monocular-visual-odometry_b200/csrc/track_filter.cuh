@@ -110,8 +110,7 @@ __device__ __forceinline__ void mf_heapsort(uint32_t *h, int len) {
   }
 }
 
-constexpr int MF_CTA_LEN = 384;      // segments from this length on are partitioned by the whole CTA
-constexpr int MF_DFS_LEN = 128;      // segments up to this length are finished (their whole subtree) by one warp, without block barriers
+constexpr int MF_DFS_LEN = 40;       // segments up to this length are finished (their whole subtree, <= 3 partitions) by one warp, without block barriers
 constexpr int MF_STACK = 40;         // per-warp stack of the depth-first phase (>= 2 lg(MF_MAXN) + a margin)
 
 // std::__unguarded_partition_pivot(first, last, by keypoint index) evaluated by one warp; returns the cut (uniform over the warp).
@@ -132,16 +131,22 @@ __device__ __forceinline__ int mf_partition_warp(uint32_t *arr, uint16_t *Ls, ui
   const int lo = first + 1, len = last - lo;
   const unsigned below = (1u << lane) - 1u;
   int nL = 0, nR = 0;
-  for (int base = 0; base < len; base += 32) {
-    const int i = base + lane;
-    const bool inr = i < len;
-    const bool ge = inr && (arr[lo + i] >> 16) >= pivot;              // !(x < pivot): the left scan stops here
-    const bool le = inr && (arr[last - 1 - i] >> 16) <= pivot;        // !(pivot < x): the right scan stops here
-    const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
-    if (ge) Ls[lo + nL + __popc(bg & below)] = (uint16_t)(lo + i);
-    if (le) Rs[lo + nR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
-    nL += __popc(bg);
-    nR += __popc(bl);
+  for (int base = 0; base < len; base += 64) {                         // two 32-element groups per trip: four independent loads in flight
+    const int i0 = base + lane, i1 = i0 + 32;
+    const bool in0 = i0 < len, in1 = i1 < len;
+    const uint32_t xl0 = in0 ? arr[lo + i0] >> 16 : 0u, xr0 = in0 ? arr[last - 1 - i0] >> 16 : 0u;
+    const uint32_t xl1 = in1 ? arr[lo + i1] >> 16 : 0u, xr1 = in1 ? arr[last - 1 - i1] >> 16 : 0u;
+    const bool ge0 = in0 && xl0 >= pivot, le0 = in0 && xr0 <= pivot;   // !(x < pivot): the left scan stops; !(pivot < x): the right scan stops
+    const bool ge1 = in1 && xl1 >= pivot, le1 = in1 && xr1 <= pivot;
+    const unsigned bg0 = __ballot_sync(0xffffffffu, ge0), bl0 = __ballot_sync(0xffffffffu, le0);
+    const unsigned bg1 = __ballot_sync(0xffffffffu, ge1), bl1 = __ballot_sync(0xffffffffu, le1);
+    const int cg0 = __popc(bg0), cl0 = __popc(bl0);
+    if (ge0) Ls[lo + nL + __popc(bg0 & below)] = (uint16_t)(lo + i0);
+    if (le0) Rs[lo + nR + __popc(bl0 & below)] = (uint16_t)(last - 1 - i0);
+    if (ge1) Ls[lo + nL + cg0 + __popc(bg1 & below)] = (uint16_t)(lo + i1);
+    if (le1) Rs[lo + nR + cl0 + __popc(bl1 & below)] = (uint16_t)(last - 1 - i1);
+    nL += cg0 + __popc(bg1);
+    nR += cl0 + __popc(bl1);
   }
   __syncwarp();
   const int nmin = min(nL, nR);
@@ -162,73 +167,6 @@ __device__ __forceinline__ int mf_partition_warp(uint32_t *arr, uint16_t *Ls, ui
   return cut;
 }
 
-// the same partition by the whole CTA (MF_T threads): every warp lists the stops of its chunk, a prefix over the warps places them.
-// s_scr: 2 * 32 + 2 ints.  Block barriers inside: called by all threads with uniform arguments.
-__device__ __forceinline__ int mf_partition_cta(uint32_t *arr, uint16_t *Ls, uint16_t *Rs, int first, int last, int *s_scr) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
-    const uint32_t ka = arr[ia] >> 16, kb = arr[ib] >> 16, kc = arr[ic] >> 16;
-    int pick;
-    if (ka < kb) pick = (kb < kc) ? ib : ((ka < kc) ? ic : ia);
-    else pick = (ka < kc) ? ia : ((kb < kc) ? ic : ib);
-    const uint32_t t = arr[first]; arr[first] = arr[pick]; arr[pick] = t;
-    s_scr[64] = 0;
-  }
-  __syncthreads();
-  const uint32_t pivot = arr[first] >> 16;
-  const int lo = first + 1, len = last - lo;
-  const unsigned below = (1u << lane) - 1u;
-  const int chunk = ((len + MF_T - 1) / MF_T) * 32;                   // per warp, a multiple of 32
-  const int c0 = min(warp * chunk, len), c1 = min(c0 + chunk, len);
-  int cl = 0, cr = 0;
-  for (int base = c0; base < c1; base += 32) {
-    const int i = base + lane;
-    const bool inr = i < c1;
-    cl += __popc(__ballot_sync(0xffffffffu, inr && (arr[lo + i] >> 16) >= pivot));
-    cr += __popc(__ballot_sync(0xffffffffu, inr && (arr[last - 1 - i] >> 16) <= pivot));
-  }
-  if (lane == 0) { s_scr[warp] = cl; s_scr[32 + warp] = cr; }
-  __syncthreads();
-  int oL = 0, oR = 0, nL = 0, nR = 0;
-  {
-    const int vl = s_scr[lane], vr = s_scr[32 + lane];
-    int il = vl, ir = vr;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int ul = __shfl_up_sync(0xffffffffu, il, o), ur = __shfl_up_sync(0xffffffffu, ir, o);
-      if (lane >= o) { il += ul; ir += ur; }
-    }
-    nL = __shfl_sync(0xffffffffu, il, 31); nR = __shfl_sync(0xffffffffu, ir, 31);
-    oL = __shfl_sync(0xffffffffu, il - vl, warp); oR = __shfl_sync(0xffffffffu, ir - vr, warp);
-  }
-  for (int base = c0; base < c1; base += 32) {
-    const int i = base + lane;
-    const bool inr = i < c1;
-    const bool ge = inr && (arr[lo + i] >> 16) >= pivot, le = inr && (arr[last - 1 - i] >> 16) <= pivot;
-    const unsigned bg = __ballot_sync(0xffffffffu, ge), bl = __ballot_sync(0xffffffffu, le);
-    if (ge) Ls[lo + oL + __popc(bg & below)] = (uint16_t)(lo + i);
-    if (le) Rs[lo + oR + __popc(bl & below)] = (uint16_t)(last - 1 - i);
-    oL += __popc(bg);
-    oR += __popc(bl);
-  }
-  __syncthreads();
-  const int nmin = min(nL, nR);
-  int mine = 0;
-  for (int j = tid; j < nmin; j += MF_T)                              // Ls ascends, Rs descends: the condition holds on a prefix
-    if (Ls[lo + j] < Rs[lo + j]) { const int x = Ls[lo + j], y = Rs[lo + j]; const uint32_t t = arr[x]; arr[x] = arr[y]; arr[y] = t; ++mine; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-  if (lane == 0 && mine) atomicAdd(&s_scr[64], mine);
-  __syncthreads();
-  const int K = s_scr[64];
-  int cut;
-  if (K == 0) cut = nL > 0 ? (int)Ls[lo] : last;
-  else { cut = (int)Rs[lo + K - 1]; if (K < nL) cut = min(cut, (int)Ls[lo + K]); }
-  __syncthreads();                                                    // s_scr is free again
-  return cut;
-}
-
 __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   MVO_DYN_SMEM(uint8_t, smraw);
   const int cap = a.n_cap;
@@ -243,7 +181,7 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   uint8_t *dfs_lvl = (uint8_t *)(dfs_seg + cap / 16 + 2);   // [cap/16 + 2] their partition depth
   __shared__ int s_warp[MF_T / 32];
   __shared__ unsigned s_min;
-  __shared__ int s_nseg[2], s_status, s_heap_segs, s_heap_max, s_ndfs, s_scr[66];
+  __shared__ int s_nseg[2], s_status, s_heap_segs, s_heap_max, s_ndfs;
   __shared__ uint32_t dfs_stack[(MF_T / 32) * MF_STACK];
   __shared__ uint8_t dfs_stack_lvl[(MF_T / 32) * MF_STACK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -315,10 +253,11 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   __syncthreads();
   MF_MARK(0);
   // ---- quicksort phase of std::sort ----
-  // Level by level while segments are long (a list per level; segments of MF_CTA_LEN elements or more are partitioned by the whole
-  // CTA one after the other, the others by one warp each); a segment of at most MF_DFS_LEN elements goes to the list of the
-  // depth-first phase, where one warp finishes its whole subtree without a block barrier (round 2: every level cost two
-  // block barriers, ~1600 cycles even when all its segments were short; 10-13 levels per frame).
+  // Level by level while segments are long (a list per level, one warp per segment); a segment of at most MF_DFS_LEN elements goes
+  // to the list of the depth-first phase, where one warp finishes its whole subtree without a block barrier: the stragglers of
+  // unbalanced partitions no longer cost a level (two block barriers, ~1600 cycles) each.  (Measured and dropped: whole-CTA
+  // partitions of the long segments — five block barriers, 3300 cycles for 700 elements against 2900 by one warp — and depth-first
+  // subtrees from 128 elements, which serialise ~12 partitions in one warp.)
   int depth_limit = 0;
   for (int m = n; m > 1; m >>= 1) ++depth_limit;        // std::__lg(n)
   depth_limit *= 2;
@@ -347,15 +286,8 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
       break;
     }
     // __introsort_loop recurses on [cut, last) and continues with [first, cut): both are pushed
-    for (int sg = 0; sg < nseg; ++sg) {                 // the long segments: whole CTA (uniform loop)
+    for (int sg = warp; sg < nseg; sg += MF_T / 32) {   // one warp per segment
       const int first = (int)(cur[sg] & 0xFFFFu), last = (int)(cur[sg] >> 16);
-      if (last - first < MF_CTA_LEN) continue;
-      const int cut = mf_partition_cta(arr, Ls, Rs, first, last, s_scr);
-      if (tid == 0) { push(cut, last, level + 1, which ^ 1); push(first, cut, level + 1, which ^ 1); }
-    }
-    for (int sg = warp; sg < nseg; sg += MF_T / 32) {   // the others: one warp per segment
-      const int first = (int)(cur[sg] & 0xFFFFu), last = (int)(cur[sg] >> 16);
-      if (last - first >= MF_CTA_LEN) continue;
       const int cut = mf_partition_warp(arr, Ls, Rs, first, last);
       if (lane == 0) { push(cut, last, level + 1, which ^ 1); push(first, cut, level + 1, which ^ 1); }
     }
