@@ -110,7 +110,24 @@ extern "C" {
 
 int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
                                  double *E, double *R, double *t, int32_t *inliers, int *n_inliers) {
+  return mvo_epi_essential_ex(ctx, pts1, pts2, n, K, threshold, E, R, t, inliers, n_inliers, 1, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+// estiMotionByEssential with the options of the keyframe branch (internal, mvo_internal.h):
+//   want_pose = 0   the caller only uses the RANSAC inliers (helperFindInlierMatchesByEpipolarCons, motion_estimation.cpp:180-196,
+//                   passes dummy R / t): recoverPose's cheirality vote is not launched, R / t are left untouched
+//   tri_*           doTriangulation (epipolar_geometry.cpp:130-175) of ALL n correspondences (normalised-plane points tri_np1 /
+//                   tri_np2, known motion tri_R / tri_t) in the same submission: the motion between two tracked frames is known
+//                   before the RANSAC runs, a point's triangulation does not depend on the inlier list, so the keyframe branch
+//                   needs one synchronisation for both stages; tri_out: n x 3 floats, the caller picks the inliers' rows
+int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
+                         double *E, double *R, double *t, int32_t *inliers, int *n_inliers, int want_pose,
+                         const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, float *tri_out) {
   if (!ctx) return MVO_ERR_INVALID_ARG;
+  const bool tri = tri_out != nullptr;
+  if (tri && (!tri_np1 || !tri_np2 || !tri_R || !tri_t)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null triangulation input");
   if (!pts1 || !pts2 || !K || !E || !R || !t || !n_inliers || (*n_inliers > 0 && !inliers))
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null pointer");
   if (n < 8) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "estiMotionByEssential: %d correspondences (< 8)", n);
@@ -124,14 +141,29 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   const int H = ctx->prm.epi_hypotheses;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_p1 = 0, o_p2 = al(o_p1 + (size_t)n * 8), o_inl = al(o_p2 + (size_t)n * 8), o_E = al(o_inl + (size_t)n * 4);
-  const size_t o_valid = al(o_E + (size_t)H * 72), o_cnt = al(o_valid + (size_t)H * 4), o_out = al(o_cnt + (size_t)H * 4), o_end = o_out + 512;
+  const size_t o_valid = al(o_E + (size_t)H * 72), o_cnt = al(o_valid + (size_t)H * 4), o_out = al(o_cnt + (size_t)H * 4);
+  // optional triangulation block: np1, np2 (n x 2 floats each), R | t (12 doubles), out (n x 3 floats)
+  const size_t o_t1 = al(o_out + 512), o_t2 = al(o_t1 + (size_t)n * 8), o_trt = al(o_t2 + (size_t)n * 8), o_tout = al(o_trt + 96);
+  const size_t o_end = tri ? o_tout + (size_t)n * 12 : o_out + 512;
+  // pinned staging: [p1 p2 | np1 np2 Rt] in, [out block 512 B + inliers | triangulated points] out
+  const size_t h_in = al((size_t)n * 16) + (tri ? al((size_t)n * 16) + 256 : 0), h_res = 512 + al((size_t)n * 4) + 256;
   MVO_TRY(mvo_reserve(ctx, ctx->d_a, o_end));
-  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, al((size_t)n * 16) + (size_t)n * 4 + 1024));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, h_in + h_res + (tri ? (size_t)n * 12 : 0) + 1024));
   uint8_t *d = (uint8_t *)ctx->d_a.p, *h = (uint8_t *)ctx->h_a.p;
   memcpy(h, pts1, (size_t)n * 8);
   memcpy(h + (size_t)n * 8, pts2, (size_t)n * 8);
   MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p1, h, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p2, h + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (tri) {
+    uint8_t *ht = h + al((size_t)n * 16);
+    memcpy(ht, tri_np1, (size_t)n * 8);
+    memcpy(ht + (size_t)n * 8, tri_np2, (size_t)n * 8);
+    memcpy(ht + al((size_t)n * 16), tri_R, 72);
+    memcpy(ht + al((size_t)n * 16) + 72, tri_t, 24);
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t1, ht, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t2, ht + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_trt, ht + al((size_t)n * 16), 96, cudaMemcpyHostToDevice, ctx->stream));
+  }
   const float *d1 = (const float *)(d + o_p1), *d2 = (const float *)(d + o_p2);
   double *dE = (double *)(d + o_E), *dout = (double *)(d + o_out);
   int32_t *dvalid = (int32_t *)(d + o_valid), *dcnt = (int32_t *)(d + o_cnt), *dinl = (int32_t *)(d + o_inl), *dout_i = (int32_t *)(d + o_out + 256);
@@ -148,14 +180,25 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   { KTimer kt(ctx, KC_EPI_FINISH);
     MVO_CUDA(ctx, launch_finish_cluster(ctx, sizeof(EpiFinSmem), k_epi_finish, d1, d2, n, cam, thr2, H, (const double *)dE, (const int32_t *)dcnt, dout, dout_i, dinl)); }
   MVO_CHECK_LAUNCH(ctx);
-  { KTimer kt(ctx, KC_EPI);
-  k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl); }
-  MVO_CHECK_LAUNCH(ctx);
-  double *h_out = (double *)(h + al((size_t)n * 16));
+  if (want_pose) {
+    KTimer kt(ctx, KC_EPI);
+    k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl);
+    MVO_CHECK_LAUNCH(ctx);
+  }
+  if (tri) {
+    KTimer kt(ctx, KC_EPI);
+    k_triangulate<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const float *)(d + o_t1), (const float *)(d + o_t2), nullptr, n, (const double *)(d + o_trt),
+                                                            (float *)(d + o_tout));
+    MVO_CHECK_LAUNCH(ctx);
+  }
+  double *h_out = (double *)(h + h_in);
   int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);
+  float *h_tri = (float *)(h + h_in + h_res);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, dinl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tri) MVO_CUDA(ctx, cudaMemcpyAsync(h_tri, d + o_tout, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (tri) memcpy(tri_out, h_tri, (size_t)n * 12);
   const int ni = h_i[0];
   if (getenv("MVO_EPI_DEBUG")) {
     std::vector<int32_t> hv(H), hc(H);
@@ -175,6 +218,12 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
                     h_i[3], h_i[4], ni);
   }
   if (ni > *n_inliers) return mvo_fail(ctx, MVO_ERR_CAPACITY, "inlier capacity %d < %d", *n_inliers, ni);
+  if (!want_pose) {
+    memcpy(E, h_out, 72);
+    memcpy(inliers, h_inl, (size_t)ni * 4);
+    *n_inliers = ni;
+    return MVO_OK;
+  }
   // recoverPose's choice among (R1,t) (R2,t) (R1,-t) (R2,-t), OpenCV's order: the first candidate whose vote count is a maximum
   const int32_t *g = h_i + 8;
   int pick = 3;
@@ -191,6 +240,8 @@ int mvo_esti_motion_by_essential(mvo_ctx *ctx, const float *pts1, const float *p
   *n_inliers = ni;
   return MVO_OK;
 }
+
+extern "C" {
 
 int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
                                   double *Hout, double *Rs, double *ts, double *normals, int *n_solutions, int32_t *inliers,

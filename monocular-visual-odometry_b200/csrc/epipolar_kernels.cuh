@@ -448,7 +448,7 @@ k_triangulate(const float *__restrict__ np1, const float *__restrict__ np2, cons
               const double *__restrict__ Rt /* 9 + 3 */, float *__restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_in) return;
-  const int i = inl[j];
+  const int i = inl ? inl[j] : j;                 // no list: every correspondence (mvo_epi_essential_ex)
   const double P0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   double P[12];
   for (int r = 0; r < 3; ++r) { P[4 * r] = Rt[3 * r]; P[4 * r + 1] = Rt[3 * r + 1]; P[4 * r + 2] = Rt[3 * r + 2]; P[4 * r + 3] = Rt[9 + r]; }

@@ -120,21 +120,12 @@ int mvo_match_features(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d
 
 }  // extern "C"
 
-int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
-                          int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out) {
-  const bool dev2 = d2_on_device != 0;
-  if (!ctx) return MVO_ERR_INVALID_ARG;
-  if (!n_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null n_out");
-  *n_out = 0;
-  if (method_index < 1 || method_index > 3)   // feature_match.cpp:225 throws
-    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "matchFeatures: wrong method index %d", method_index);
-  if (n1 > 0 && !out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
+// The tail of matchFeatures over the packed keys of the all-pairs kernel (one key per query for methods 1 / 3, two for method 2):
+// the distance thresholds (feature_match.cpp:179-196 / :210-217) and removeDuplicatedMatches (:229, :241-260)
+int mvo_match_filter_keys(mvo_ctx *ctx, int method_index, const uint32_t *k, int n1, mvo_dmatch *out, int *n_out) {
   int n = 0;
   if (method_index == 1 || method_index == 3) {
-    const uint32_t *k = nullptr;
     const bool sad = method_index == 3;
-    if (!sad && n2 == 0) return MVO_OK;   // BFMatcher on an empty train set returns no matches
-    MVO_TRY(run_match(ctx, sad ? 2 : 0, d1, xy1, n1, d2, xy2, n2, radius, &k, dev2));
     // feature_match.cpp:179-187
     double min_dis = 9999999, max_dis = 0;
     for (int i = 0; i < n1; ++i) {
@@ -150,9 +141,6 @@ int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t
       if (m.distance < thr) out[n++] = m;
     }
   } else {
-    if (n2 < 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "method 2 needs >= 2 train descriptors");
-    const uint32_t *k = nullptr;
-    MVO_TRY(run_match(ctx, 1, d1, nullptr, n1, d2, nullptr, n2, 0.f, &k, dev2));
     for (int i = 0; i < n1; ++i) {   // :210-217
       const mvo_dmatch m0 = unpack(i, k[2 * i], 0, false), m1 = unpack(i, k[2 * i + 1], 0, false);
       const double dist = m0.distance;
@@ -162,6 +150,27 @@ int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t
   mvo_remove_duplicated_matches(out, &n);   // :229
   *n_out = n;
   return MVO_OK;
+}
+
+int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
+                          int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out) {
+  const bool dev2 = d2_on_device != 0;
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!n_out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null n_out");
+  *n_out = 0;
+  if (method_index < 1 || method_index > 3)   // feature_match.cpp:225 throws
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "matchFeatures: wrong method index %d", method_index);
+  if (n1 > 0 && !out) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "null output");
+  const uint32_t *k = nullptr;
+  if (method_index == 1 || method_index == 3) {
+    const bool sad = method_index == 3;
+    if (!sad && n2 == 0) return MVO_OK;   // BFMatcher on an empty train set returns no matches
+    MVO_TRY(run_match(ctx, sad ? 2 : 0, d1, xy1, n1, d2, xy2, n2, radius, &k, dev2));
+  } else {
+    if (n2 < 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "method 2 needs >= 2 train descriptors");
+    MVO_TRY(run_match(ctx, 1, d1, nullptr, n1, d2, nullptr, n2, 0.f, &k, dev2));
+  }
+  return mvo_match_filter_keys(ctx, method_index, k, n1, out, n_out);
 }
 
 extern "C" {

@@ -197,6 +197,17 @@ int mvo_trk_push_frame(mvo_tracker *t, const double *T_w_c, const int32_t *ids, 
 int mvo_trk_append_links(mvo_tracker *t, int k, const int32_t *ids, const int32_t *kp_idx, const float *obs_xy, int n);
 int mvo_trk_links(mvo_tracker *t, int k, int32_t *ids, int32_t *kp_idx, int cap, int *n);
 int mvo_trk_counters(mvo_tracker *t, int32_t *visible, int32_t *matched, int n);
+// keyframe insertion in one submission / one synchronisation (tracker.cpp); the pointers address the context's pinned staging
+// buffer and stay valid until the next fetch
+struct MvoKfFetch {
+  int n_kpts;
+  const mvo_keypoint *kpts; const uint8_t *desc, *rgb;          // rgb: null unless asked for
+  const int32_t *link_ids, *link_kp; int n_links;              // inliers_to_mappt_connections_ of the frame, insertion order
+  const int32_t *vis, *matched; int n_counters;                // visible / matched increments per map position
+  const uint32_t *keys; int n_ref;                             // matcher keys reference keyframe x this frame; n_ref = 0: not available
+};
+int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out);
+int mvo_trk_set_ref_desc(mvo_tracker *t, int slot, int tag);
 int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
@@ -215,6 +226,13 @@ int mvo_orb_extract_end_dev(mvo_ctx *ctx, int *n_kpts, const mvo_keypoint **d_kp
 // mvo_match_features with the train descriptors optionally already on the device (match_host.cpp)
 int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
                           int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out);
+// the thresholds + removeDuplicatedMatches tail of matchFeatures over packed matcher keys (match_host.cpp)
+int mvo_match_filter_keys(mvo_ctx *ctx, int method_index, const uint32_t *keys, int n1, mvo_dmatch *out, int *n_out);
+// estiMotionByEssential with the keyframe branch's options: no recoverPose vote, triangulation of all correspondences in the same
+// submission (epipolar.cu)
+int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
+                         double *E, double *R, double *t, int32_t *inliers, int *n_inliers, int want_pose,
+                         const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, float *tri_out);
 
 // ---- stage entry points (host-side launchers, all asynchronous on ctx->stream) -----------
 // match.cu

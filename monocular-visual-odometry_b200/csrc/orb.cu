@@ -333,6 +333,53 @@ __device__ __forceinline__ void grid_rank_keep(int n, const uint16_t *__restrict
   }
 }
 
+// The same keep flags in two passes instead of max_per_cell rounds over all items (which cost 9 x 8000 item visits, 28 us, for an
+// above-cap frame): the 32 warps of the CTA take 32 contiguous segments of the item list.  Pass 1: a warp walks its segment 32 items
+// at a time; __match_any_sync groups the lanes by cell, rank inside the segment = the cell's count so far in this warp's private
+// table + the number of lower lanes of the group; the group's highest lane adds the group size to the table.  Pass 2: exclusive
+// prefix of the 32 tables per cell (one thread per cell).  Pass 3: keep = segment rank + prefix < max_per_cell.  Counts saturate
+// at 255, which is exact while max_per_cell <= 254 (the caller falls back to the round version otherwise).
+// s_tab: 32 x ncell bytes.  s_keep holds the segment ranks between the passes.
+__device__ __forceinline__ void grid_rank_keep_seg(int n, const uint16_t *__restrict__ s_cell, uint8_t *__restrict__ s_keep, uint8_t *__restrict__ s_tab,
+                                                   int ncell, int max_per_cell) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 8 * ncell; i += 1024) reinterpret_cast<uint32_t *>(s_tab)[i] = 0;       // 32 * ncell bytes, ncell-major per warp
+  __syncthreads();
+  const int seg = (((n + 31) >> 5) + 31) & ~31;               // items per warp: a multiple of 32
+  const int b = min(warp * seg, n), e = min(b + seg, n);
+  uint8_t *tab = s_tab + (size_t)warp * ncell;
+  const unsigned lt = lanemask_lt();
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < e;
+    const unsigned c = in ? (unsigned)s_cell[i] : 0xFFFF0000u + (unsigned)lane;      // lanes past the end: a group of their own
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int base = in ? (int)tab[c] : 0;
+    __syncwarp();                                             // every lane has read the count before the group leader moves it
+    if (in) {
+      s_keep[i] = (uint8_t)min(base + __popc(peers & lt), 255);
+      if ((peers >> lane) == 1u) tab[c] = (uint8_t)min(base + __popc(peers), 255);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += 1024) {
+    int run = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      const int v = s_tab[(size_t)w * ncell + c];
+      s_tab[(size_t)w * ncell + c] = (uint8_t)min(run, 255);
+      run += v;
+    }
+  }
+  __syncthreads();
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < e) s_keep[i] = (uint8_t)(((int)s_keep[i] + (int)tab[s_cell[i]]) < max_per_cell);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------- select
 // Restates feature_match.cpp:68-81: walking keypoints in order, a keypoint is kept iff fewer than
 // max_per_cell earlier keypoints fell into its 16x16 cell, and the walk stops right after the
@@ -340,7 +387,7 @@ __device__ __forceinline__ void grid_rank_keep(int n, const uint16_t *__restrict
 // kept = kept0 && (#kept0 before it) <= max_kpts.
 __global__ void __launch_bounds__(1024)
 k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *__restrict__ bandcnt,
-         uint32_t *__restrict__ cand, uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
+         uint32_t *__restrict__ cand, uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta, int seg_tab) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncell = plan.grid_rows * plan.grid_cols;
@@ -351,6 +398,7 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
   uint16_t *s_cell = reinterpret_cast<uint16_t *>(s_cursor + ncell);   // [cap] cell of candidate i
   uint16_t *s_bucket = s_cell + scap;                             // [cap] candidate ids grouped by cell
   uint8_t *s_keep = reinterpret_cast<uint8_t *>(s_bucket + scap);  // [cap]
+  uint8_t *s_tab = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_keep + scap) + 15) & ~(uintptr_t)15);   // [32 * ncell] per-warp cell counts (seg_tab != 0)
   __shared__ int s_lvl_off[MVO_MAX_LEVELS + 1];
   __shared__ int s_warp[32];
   __shared__ int s_overflow;
@@ -423,7 +471,8 @@ k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *_
   __syncthreads();
   if (ovf) return;
 
-  grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);     // s_cellcnt + s_cursor: 2 * ncell + 1 words
+  if (seg_tab) grid_rank_keep_seg(n, s_cell, s_keep, s_tab, ncell, plan.max_per_cell);
+  else grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);     // s_cellcnt + s_cursor: 2 * ncell + 1 words
   // ordered prefix count of kept0 (contiguous chunk per thread), cut after max_kpts + 1
   {
     const int per = (n + 1023) >> 10;
@@ -703,7 +752,7 @@ k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__rest
 // form of k_select (rank inside the 16 x 16 cell < max_per_cell, cut after max_kpts + 1 kept) in the retained ORDER.
 __global__ void __launch_bounds__(1024)
 k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t *__restrict__ kept, const int32_t *__restrict__ kept_cnt,
-              uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta) {
+              uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta, int seg_tab) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (meta[f].overflow != 1) return;
@@ -715,6 +764,7 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
   uint16_t *s_bucket = s_cell + scap;                               // [scap]
   uint8_t *s_keep = reinterpret_cast<uint8_t *>(s_bucket + scap);   // [scap]
   uint8_t *s_lvl = s_keep + scap;                                   // [scap]
+  uint8_t *s_tab = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(s_lvl + scap) + 15) & ~(uintptr_t)15);     // [32 * ncell] per-warp cell counts (seg_tab != 0)
   __shared__ int s_warp[32];
   __shared__ int s_off[MVO_MAX_LEVELS + 1], s_base[MVO_MAX_LEVELS + 1];
   if (tid == 0) {
@@ -744,7 +794,8 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
     s_pk[i] = p; s_lvl[i] = (uint8_t)l; s_cell[i] = (uint16_t)cell;
   }
   __syncthreads();
-  grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);
+  if (seg_tab) grid_rank_keep_seg(n, s_cell, s_keep, s_tab, ncell, plan.max_per_cell);
+  else grid_rank_keep(n, s_cell, s_keep, reinterpret_cast<uint32_t *>(s_cellcnt), ncell, plan.max_per_cell);
   {
     const int per = (n + 1023) >> 10;
     const int b = tid * per, e = min(b + per, n);
@@ -1167,16 +1218,25 @@ int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes,
   return MVO_OK;
 }
 
+// 1 when the two-pass grid selection (grid_rank_keep_seg) can run: its 32 count tables fit next to `smem` bytes and the per-cell
+// limit stays below the saturation value of a byte counter; MVO_GRID_ROUNDS=1 keeps the round version (A/B hook)
+static int orb_seg_tab(size_t smem, int ncell, int max_per_cell) {
+  static const bool rounds = getenv("MVO_GRID_ROUNDS") != nullptr && atoi(getenv("MVO_GRID_ROUNDS")) != 0;
+  return (!rounds && max_per_cell <= 254 && smem + (size_t)32 * ncell + 32 <= 220 * 1024) ? 1 : 0;
+}
+
 int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *staging, const int32_t *bandcnt,
                       uint32_t *cand, uint2 *sel, OrbFrameMeta *meta, int batch) {
   const int ncell = plan.grid_rows * plan.grid_cols;
-  const size_t smem = (size_t)(ORB_MAX_BANDS + 1) * 4 + (size_t)(ncell + 1) * 4 + (size_t)ncell * 4 +
-                      (size_t)plan.sel_cap * 2 * 2 + plan.sel_cap + 64;
+  size_t smem = (size_t)(ORB_MAX_BANDS + 1) * 4 + (size_t)(ncell + 1) * 4 + (size_t)ncell * 4 +
+                (size_t)plan.sel_cap * 2 * 2 + plan.sel_cap + 64;
   if (smem > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "selection grid too large");
+  const int seg_tab = orb_seg_tab(smem, ncell, plan.max_per_cell);      // the two-pass grid selection when its count tables fit
+  if (seg_tab) smem += (size_t)32 * ncell + 32;
   if (smem > 48 * 1024)
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KTimer kt(ctx, KC_SELECT);
-  k_select<<<batch, 1024, smem, ctx->stream>>>(plan, staging, bandcnt, cand, sel, meta);
+  k_select<<<batch, 1024, smem, ctx->stream>>>(plan, staging, bandcnt, cand, sel, meta, seg_tab);
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1222,11 +1282,13 @@ int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand
   k_retain<<<dim3(plan.nlevels, batch), RET_T, smem, ctx->stream>>>(plan, cand, harris, meta, kept, kept_cnt); }
   MVO_CHECK_LAUNCH(ctx);
   const int ncell = plan.grid_rows * plan.grid_cols;
-  const size_t smem2 = (size_t)(2 * ncell + 1) * 4 + (size_t)plan.sel_cap * (4 + 2 + 2 + 1 + 1) + 64;
+  size_t smem2 = (size_t)(2 * ncell + 1) * 4 + (size_t)plan.sel_cap * (4 + 2 + 2 + 1 + 1) + 64;
   if (smem2 > 220 * 1024) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "selection grid too large");
+  const int seg_tab = orb_seg_tab(smem2, ncell, plan.max_per_cell);
+  if (seg_tab) smem2 += (size_t)32 * ncell + 32;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_select_kept, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   { KTimer kt(ctx, KC_SELECT);
-  k_select_kept<<<batch, 1024, smem2, ctx->stream>>>(plan, cand, kept, kept_cnt, sel, meta); }
+  k_select_kept<<<batch, 1024, smem2, ctx->stream>>>(plan, cand, kept, kept_cnt, sel, meta, seg_tab); }
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

@@ -164,6 +164,11 @@ struct mvo_tracker {
   double *d_pose = nullptr, *d_res = nullptr, *d_stats = nullptr;
   uint8_t *h_pin = nullptr;            // pinned staging: [keys+vis][pairs][results]
   size_t h_pin_bytes = 0;
+  // descriptors of the reference keyframe (mvo_vo: ref_), kept on the device so that a keyframe insertion matches against them
+  // without an upload (mvo_trk_set_ref_desc / mvo_trk_keyframe_fetch)
+  uint8_t *d_ref_desc = nullptr;
+  int n_ref = 0, ref_tag = -1;
+  bool ref_copy_pending = false;       // a device-to-device copy out of an extraction slot is in flight: synchronise before the slot is released
 };
 
 namespace {
@@ -264,6 +269,7 @@ int dev_alloc(mvo_tracker *t) {
     const size_t o_flags = o; o = al256(o + 256);       // [0] BA skip flag, [8..] res_i (3), [16..] out_info (2 + 16)
     const size_t o_res = o;   o = al256(o + 256);       // res_d (12 doubles)
     const size_t o_stats = o; o = al256(o + 256);       // BA stats (16 doubles)
+    const size_t o_ref = o;   o = al256(o + (size_t)cap * 32);
     uint8_t *nd = nullptr;
     MVO_CUDA(ctx, cudaMalloc(&nd, o));
     MVO_CUDA(ctx, cudaMemsetAsync(nd, 0, o, ctx->stream));
@@ -274,6 +280,7 @@ int dev_alloc(mvo_tracker *t) {
     t->d_kxy = (float *)(nd + o_kxy); t->d_edge_map = (int32_t *)(nd + o_emap); t->d_edge_obs = (float *)(nd + o_eobs);
     t->d_edge_kp = (int32_t *)(nd + o_ekp); t->d_cnt = (int32_t *)(nd + o_cnt); t->d_pose = (double *)(nd + o_pose);
     t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res); t->d_stats = (double *)(nd + o_stats);
+    t->d_ref_desc = nd + o_ref; t->n_ref = 0; t->ref_tag = -1;
   }
   if (!map_ok) {
     int mcap = std::max(t->dev_mcap, 1024);
@@ -660,7 +667,100 @@ int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t s
   return MVO_OK;
 }
 
-void mvo_trk_release(mvo_tracker *t, int slot) { t->job[slot].state.store(0, std::memory_order_release); }
+void mvo_trk_release(mvo_tracker *t, int slot) {
+  if (t->ref_copy_pending) {             // the worker may overwrite the slot's buffers as soon as it is released
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    t->ref_copy_pending = false;
+  }
+  t->job[slot].state.store(0, std::memory_order_release);
+}
+
+// The acquired frame becomes the reference keyframe: its descriptors are kept on the device (asynchronous device-to-device
+// copy; completed by the next synchronisation of the tracking stream, at the latest when the slot is released).
+int mvo_trk_set_ref_desc(mvo_tracker *t, int slot, int tag) {
+  mvo_ctx *ctx = t->ctx;
+  ExtractJob &job = t->job[slot];
+  t->n_ref = 0; t->ref_tag = -1;
+  if (job.want_host || job.nk <= 0 || !job.d_d) return MVO_OK;
+  MVO_TRY(dev_alloc(t));
+  if (job.nk > t->dev_cap) return MVO_OK;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_CUDA(ctx, cudaMemcpyAsync(t->d_ref_desc, job.d_d, (size_t)job.nk * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  t->n_ref = job.nk; t->ref_tag = tag;
+  t->ref_copy_pending = true;
+  return MVO_OK;
+}
+
+// Keyframe insertion, device-resident mode: everything the host needs of the frame that was just tracked, in ONE submission
+// and ONE synchronisation — keypoints, descriptors, colours (gathered on the device for an image in device memory), the
+// connections PnP gave it (inliers_to_mappt_connections_), the visible / matched increments since the last call (reset like
+// mvo_trk_counters does), and the matcher keys of the reference keyframe's descriptors against this frame's (match_mode 0 =
+// nearest neighbour, 1 = two nearest; only when the descriptors kept by mvo_trk_set_ref_desc carry `ref_tag`).
+int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out) {
+  mvo_ctx *ctx = t->ctx;
+  ExtractJob &job = t->job[slot];
+  memset(out, 0, sizeof *out);
+  if (job.want_host) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "tracker: the frame was extracted for the host-array path");
+  if (t->frames.empty()) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: no frame in the buffer");
+  const int n = job.nk;
+  const TrackedFrame &f = t->frames.back();
+  const int nl = f.slot < 0 ? 0 : f.n_links;
+  const bool cnt_dev = n_counters > 0 && t->dev_nmap >= 0;
+  if (cnt_dev && n_counters != t->dev_nmap)
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: counters asked for %d points, the device map holds %d", n_counters, t->dev_nmap);
+  if (want_rgb && !job.on_device) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: the image of this frame is in host memory");
+  const bool do_match = match_mode >= 0 && match_mode <= 1 && t->n_ref > 0 && t->ref_tag == ref_tag && n > 0 && !(match_mode == 1 && n < 2);
+  const int W = match_mode == 1 ? 2 : 1;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t o = 0;
+  const size_t o_k = o;   o = al256(o + (size_t)n * sizeof(mvo_keypoint));
+  const size_t o_d = o;   o = al256(o + (size_t)n * 32);
+  const size_t o_c = o;   o = al256(o + (size_t)n * 3);
+  const size_t o_li = o;  o = al256(o + (size_t)nl * 4);
+  const size_t o_lk = o;  o = al256(o + (size_t)nl * 4);
+  const size_t o_v = o;   o = al256(o + (size_t)std::max(n_counters, 0) * 4);
+  const size_t o_m = o;   o = al256(o + (size_t)std::max(n_counters, 0) * 4);
+  const size_t o_key = o; o = al256(o + (do_match ? (size_t)t->n_ref * W * 4 : 0));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, o + 256));
+  uint8_t *h = (uint8_t *)ctx->h_b.p;
+  if (n > 0) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_k, job.d_k, (size_t)n * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_d, job.d_d, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_rgb) {
+      MVO_TRY(mvo_reserve(ctx, ctx->d_f, (size_t)n * 3 + 256));
+      MVO_TRY(mvo_track_kpt_colors(ctx, job.d_k, n, job.image, job.channels, job.stride, (uint8_t *)ctx->d_f.p));
+      MVO_CUDA(ctx, cudaMemcpyAsync(h + o_c, ctx->d_f.p, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  if (do_match) {
+    MVO_TRY(mvo_reserve(ctx, ctx->match_keys, (size_t)t->n_ref * W * 4 + 256));
+    MVO_TRY(mvo_match_launch(ctx, match_mode, t->d_ref_desc, nullptr, t->n_ref, job.d_d, nullptr, n, 0.f, (uint32_t *)ctx->match_keys.p));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_key, ctx->match_keys.p, (size_t)t->n_ref * W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (nl > 0) {
+    const size_t oe = (size_t)f.slot * t->dev_cap;
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_li, t->d_edge_map + oe, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_lk, t->d_edge_kp + oe, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (cnt_dev) {
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_v, t->d_vis_cnt, (size_t)n_counters * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_m, t->d_match_cnt, (size_t)n_counters * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MVO_CUDA(ctx, cudaMemsetAsync(t->d_vis_cnt, 0, (size_t)n_counters * 4, ctx->stream));
+    MVO_CUDA(ctx, cudaMemsetAsync(t->d_match_cnt, 0, (size_t)n_counters * 4, ctx->stream));
+  } else if (n_counters > 0) {          // no frame has been tracked against this map yet
+    memset(h + o_v, 0, (size_t)n_counters * 4);
+    memset(h + o_m, 0, (size_t)n_counters * 4);
+  }
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  t->ref_copy_pending = false;
+  out->n_kpts = n;
+  out->kpts = (const mvo_keypoint *)(h + o_k); out->desc = h + o_d; out->rgb = want_rgb ? h + o_c : nullptr;
+  out->link_ids = (const int32_t *)(h + o_li); out->link_kp = (const int32_t *)(h + o_lk); out->n_links = nl;
+  out->vis = (const int32_t *)(h + o_v); out->matched = (const int32_t *)(h + o_m); out->n_counters = std::max(n_counters, 0);
+  out->keys = do_match ? (const uint32_t *)(h + o_key) : nullptr; out->n_ref = do_match ? t->n_ref : 0;
+  return MVO_OK;
+}
 
 int mvo_trk_device_mode(const mvo_tracker *t) { return use_device_path(t) ? 1 : 0; }
 
@@ -773,6 +873,7 @@ int mvo_trk_append_links(mvo_tracker *t, int k, const int32_t *ids, const int32_
   MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_obs + 2 * o, obs_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(t->d_cnt + f.slot, &total, 4, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  t->ref_copy_pending = false;
   f.n_links = total;
   return MVO_OK;
 }

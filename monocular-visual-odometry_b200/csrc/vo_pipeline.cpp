@@ -162,7 +162,7 @@ struct mvo_vo {
   size_t cur_stride = 0;
   std::vector<uint8_t> img_scratch;
   std::vector<int32_t> new_ids, new_kp, cnt_vis, cnt_match;
-  std::vector<float> new_obs, up_pts;
+  std::vector<float> new_obs, up_pts, tri_all;
   std::vector<uint8_t> up_desc;
 };
 
@@ -282,6 +282,17 @@ int pull_counters(mvo_vo *v) {
     it->second.matched_times += v->cnt_match[(size_t)k];
   }
   return MVO_OK;
+}
+
+// the increments of one keyframe fetch (positions = the order of the last upload) folded into the map
+void fold_counters(mvo_vo *v, const int32_t *vis, const int32_t *matched, int n) {
+  for (int k = 0; k < n && k < (int)v->dev_order.size(); ++k) {
+    if (vis[k] == 0 && matched[k] == 0) continue;
+    auto it = v->map_points.find(v->dev_order[(size_t)k]);
+    if (it == v->map_points.end()) continue;
+    it->second.visible_times += vis[k];
+    it->second.matched_times += matched[k];
+  }
 }
 
 // device-resident mode: a frame that did not go through the tracking step enters the tracker's frame buffer
@@ -574,12 +585,45 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   VoFrame &c = *v->curr;
   const VoFrame &r = *v->ref;
   StageClock clk;
-  if (v->dev) {                                                  // the frame's keypoints and connections come to the host now
+  const int method = v->prm.track.match_method;
+  bool matched = false;
+  static const bool legacy = getenv("MVO_VO_LEGACY_KEYFRAME") != nullptr;      // A/B hook: the stage-by-stage path of round 1
+  const bool fused = v->dev && !legacy;
+  if (fused) {
+    // the frame's keypoints, descriptors, colours and connections, the visible / matched increments and the match against the
+    // reference keyframe (whose descriptors stayed on the device): one submission, one synchronisation
+    MvoKfFetch kf;
+    const bool cur = v->cur_image != nullptr;
+    MVO_TRY(mvo_trk_keyframe_fetch(v->trk, c.slot, cur && v->cur_on_device, (int)v->dev_order.size(), r.id,
+                                   method == 1 ? 0 : (method == 2 ? 1 : -1), &kf));
+    if (!c.host_ready) {
+      c.kpts.assign(kf.kpts, kf.kpts + kf.n_kpts);
+      c.desc.assign(kf.desc, kf.desc + (size_t)kf.n_kpts * 32);
+      c.xy.resize((size_t)kf.n_kpts * 2);
+      for (int i = 0; i < kf.n_kpts; ++i) { c.xy[2 * i] = c.kpts[(size_t)i].x; c.xy[2 * i + 1] = c.kpts[(size_t)i].y; }
+      if (kf.rgb) c.colors.assign(kf.rgb, kf.rgb + (size_t)kf.n_kpts * 3);
+      else { c.colors.assign((size_t)kf.n_kpts * 3, 0); if (cur) sample_colors(&c, v->cur_image, v->cur_channels, v->cur_stride); }
+      c.host_ready = true;
+    }
+    if (!c.conn_ready) {
+      for (int i = 0; i < kf.n_links; ++i) c.conn[kf.link_kp[i]] = PtConn{-1, kf.link_ids[i]};
+      c.conn_ready = true;
+    }
+    fold_counters(v, kf.vis, kf.matched, kf.n_counters);          // visible_times_ / matched_times_ as of this frame
+    clk.mark("fetch+match");
+    if (kf.n_ref > 0 && kf.n_ref == r.n()) {
+      c.matches_with_ref.resize((size_t)kf.n_ref);
+      int nm = 0;
+      MVO_TRY(mvo_match_filter_keys(v->ctx, method, kf.keys, kf.n_ref, c.matches_with_ref.data(), &nm));
+      c.matches_with_ref.resize((size_t)nm);
+      matched = true;
+    }
+  } else if (v->dev) {                                           // the frame's keypoints and connections come to the host now
     MVO_TRY(ensure_host(v, &c));
     MVO_TRY(ensure_conn(v, &c, 0));
+    clk.mark("fetch");
   }
-  clk.mark("fetch");
-  MVO_TRY(match_into(v, r.desc.data(), r.xy.data(), r.n(), c, v->prm.track.match_method, v->prm.max_match_dist_triangulation, &c.matches_with_ref));
+  if (!matched) MVO_TRY(match_into(v, r.desc.data(), r.xy.data(), r.n(), c, method, v->prm.max_match_dist_triangulation, &c.matches_with_ref));
   clk.mark("match");
   const int n = (int)c.matches_with_ref.size();
   info->kf_matches = n;
@@ -590,33 +634,50 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
     v->p1[2 * i] = r.xy[2 * m.query_idx]; v->p1[2 * i + 1] = r.xy[2 * m.query_idx + 1];
     v->p2[2 * i] = c.xy[2 * m.train_idx]; v->p2[2 * i + 1] = c.xy[2 * m.train_idx + 1];
   }
-  // helperFindInlierMatchesByEpipolarCons (motion_estimation.cpp:180-196): the inliers of the essential-matrix RANSAC
-  double E[9], Re[9], te[3];
-  v->inl.resize((size_t)n);
-  int ni = n;
-  const int rc = mvo_esti_motion_by_essential(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.essential_threshold, E, Re, te, v->inl.data(), &ni);
-  if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
-  if (rc != MVO_OK) return rc;
-  clk.mark("essential");
-  c.inliers_matches_with_ref.resize((size_t)ni);
-  v->np1.resize((size_t)ni * 2); v->np2.resize((size_t)ni * 2);
-  for (int i = 0; i < ni; ++i) {
-    mvo_dmatch m = c.matches_with_ref[(size_t)v->inl[i]];
-    m.img_idx = -1;
-    c.inliers_matches_with_ref[(size_t)i] = m;
-    // pixel2CamNormPlane (camera.cpp:10-15)
-    v->np1[2 * i] = (float)(((double)r.xy[2 * m.query_idx] - v->K[2]) / v->K[0]); v->np1[2 * i + 1] = (float)(((double)r.xy[2 * m.query_idx + 1] - v->K[5]) / v->K[4]);
-    v->np2[2 * i] = (float)(((double)c.xy[2 * m.train_idx] - v->K[2]) / v->K[0]); v->np2[2 * i + 1] = (float)(((double)c.xy[2 * m.train_idx + 1] - v->K[5]) / v->K[4]);
-  }
   // helperTriangulatePoints with the known motion getMotionFromFrame1to2(curr_, ref_) = curr^-1 * ref (vo_commons.cpp:9-15)
   double Tci[16], T[16], R[9], t[3];
   inv_rigid44(c.T_w_c, Tci);
   mul44(Tci, r.T_w_c, T);
   for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[i * 4 + j]; t[i] = T[i * 4 + 3]; }
-  std::vector<int32_t> all((size_t)ni);
-  for (int i = 0; i < ni; ++i) all[(size_t)i] = i;
+  auto to_norm_plane = [&](const mvo_dmatch &m, float *a, float *b) {        // pixel2CamNormPlane (camera.cpp:10-15)
+    a[0] = (float)(((double)r.xy[2 * m.query_idx] - v->K[2]) / v->K[0]); a[1] = (float)(((double)r.xy[2 * m.query_idx + 1] - v->K[5]) / v->K[4]);
+    b[0] = (float)(((double)c.xy[2 * m.train_idx] - v->K[2]) / v->K[0]); b[1] = (float)(((double)c.xy[2 * m.train_idx + 1] - v->K[5]) / v->K[4]);
+  };
+  // helperFindInlierMatchesByEpipolarCons (motion_estimation.cpp:180-196): the inliers of the essential-matrix RANSAC.  The
+  // reference passes dummy R / t here, so only the consensus set is computed; in the fused path the triangulation of every
+  // correspondence (its motion is known beforehand) rides in the same submission and the inliers' rows are picked below.
+  double E[9], Re[9], te[3];
+  v->inl.resize((size_t)n);
+  int ni = n;
+  int rc;
+  if (fused) {
+    v->np1.resize((size_t)n * 2); v->np2.resize((size_t)n * 2);
+    for (int i = 0; i < n; ++i) to_norm_plane(c.matches_with_ref[(size_t)i], &v->np1[2 * (size_t)i], &v->np2[2 * (size_t)i]);
+    v->tri_all.resize((size_t)n * 3);
+    rc = mvo_epi_essential_ex(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.essential_threshold, E, Re, te, v->inl.data(), &ni, 0,
+                              v->np1.data(), v->np2.data(), R, t, v->tri_all.data());
+  } else {
+    rc = mvo_esti_motion_by_essential(v->ctx, v->p1.data(), v->p2.data(), n, v->K, v->prm.essential_threshold, E, Re, te, v->inl.data(), &ni);
+  }
+  if (rc == MVO_ERR_DEGENERATE) return MVO_OK;
+  if (rc != MVO_OK) return rc;
+  clk.mark("essential");
+  c.inliers_matches_with_ref.resize((size_t)ni);
+  for (int i = 0; i < ni; ++i) {
+    mvo_dmatch m = c.matches_with_ref[(size_t)v->inl[i]];
+    m.img_idx = -1;
+    c.inliers_matches_with_ref[(size_t)i] = m;
+  }
   v->pts3d.resize((size_t)std::max(ni, 1) * 3);
-  if (ni > 0) MVO_TRY(mvo_do_triangulation(v->ctx, v->np1.data(), v->np2.data(), ni, R, t, all.data(), ni, v->pts3d.data()));
+  if (fused) {
+    for (int i = 0; i < ni; ++i) memcpy(&v->pts3d[3 * (size_t)i], &v->tri_all[3 * (size_t)v->inl[i]], 12);
+  } else {
+    v->np1.resize((size_t)ni * 2); v->np2.resize((size_t)ni * 2);
+    for (int i = 0; i < ni; ++i) to_norm_plane(c.inliers_matches_with_ref[(size_t)i], &v->np1[2 * (size_t)i], &v->np2[2 * (size_t)i]);
+    std::vector<int32_t> all((size_t)ni);
+    for (int i = 0; i < ni; ++i) all[(size_t)i] = i;
+    if (ni > 0) MVO_TRY(mvo_do_triangulation(v->ctx, v->np1.data(), v->np2.data(), ni, R, t, all.data(), ni, v->pts3d.data()));
+  }
   c.inliers_pts3d.resize((size_t)ni * 3);
   for (int i = 0; i < ni; ++i) trans_coord(&v->pts3d[3 * (size_t)i], R, t, &c.inliers_pts3d[3 * (size_t)i]);
   clk.mark("triangulate");
@@ -625,11 +686,12 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   v->new_ids.clear(); v->new_kp.clear(); v->new_obs.clear();
   push_curr_points_to_map(v);
   clk.mark("retain+push");
-  if (v->dev) MVO_TRY(pull_counters(v));                         // visible_times_ / matched_times_ as of this frame
+  if (v->dev && !fused) MVO_TRY(pull_counters(v));               // visible_times_ / matched_times_ as of this frame
   clk.mark("counters");
   optimize_map(v);
   clk.mark("optimize_map");
   if (v->dev) {
+    MVO_TRY(mvo_trk_set_ref_desc(v->trk, c.slot, c.id));         // this frame is the reference keyframe from now on
     MVO_TRY(upload_map(v));
     MVO_TRY(mvo_trk_append_links(v->trk, 0, v->new_ids.data(), v->new_kp.data(), v->new_obs.data(), (int)v->new_ids.size()));
   }
@@ -779,7 +841,8 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
       v->state = VO_DOING_INITIALIZATION;
       add_keyframe(v, frame);
       info.keyframe = 1;
-      if (v->dev) rc = push_frame_to_tracker(v, *frame);
+      if (v->dev) rc = mvo_trk_set_ref_desc(v->trk, slot, frame->id);
+      if (rc == MVO_OK && v->dev) rc = push_frame_to_tracker(v, *frame);
     }
   } else if (v->state == VO_DOING_INITIALIZATION) {              // :35-69
     const VoFrame &r = *v->ref;
@@ -795,7 +858,8 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
       add_keyframe(v, frame);
       v->state = VO_DOING_TRACKING;
       info.keyframe = 1;
-      if (v->dev) rc = upload_map(v);
+      if (v->dev) rc = mvo_trk_set_ref_desc(v->trk, slot, frame->id);
+      if (rc == MVO_OK && v->dev) rc = upload_map(v);
     } else {
       memcpy(frame->T_w_c, v->ref->T_w_c, sizeof frame->T_w_c);  // :64-68
     }

@@ -134,6 +134,16 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   pthread_barrier_wait(&g_warp_barrier[w]);
   return m;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned v) {            // lanes of the warp that hold the same value
+  const int w = threadIdx.x >> 5;
+  g_xchg[w][threadIdx.x & 31] = v;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  unsigned m = 0;
+  const unsigned lanes = std::min(32u, blockDim.x - 32u * (unsigned)w);
+  for (unsigned i = 0; i < lanes; ++i) m |= (unsigned)(g_xchg[w][i] == (unsigned long long)v) << i;
+  pthread_barrier_wait(&g_warp_barrier[w]);
+  return m;
+}
 static inline unsigned emu_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }     // %lanemask_lt (kernels read it through inline PTX)
 // atomics on shared or global memory: the GCC builtins on the same address
 template <class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

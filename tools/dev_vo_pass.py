@@ -14,6 +14,7 @@ ctx = mvo_b200.Context(0, max_keypoints=2000, ba_iterations=10)
 vo = mvo_b200.VisualOdometry(ctx, mvo_synth.K_DEFAULT, 480, 640)
 d = [torch.from_numpy(im).cuda() for im in imgs]
 torch.cuda.synchronize()
+sig = []
 for p in range(passes):
     vo.reset()
     t0 = time.perf_counter()
@@ -30,3 +31,8 @@ for p in range(passes):
     dt = time.perf_counter() - t0
     print("  " + ", ".join(f"{k} {len(v)} x {1e3 * sum(v) / max(len(v), 1):.3f} ms" for k, v in cls.items()), flush=True)
     print(f"pass {p}: {n} frames in {1e3 * dt:.1f} ms = {n / dt:.0f} fps, keyframes {kf}, state {info.state_out}, map {info.map_points}", flush=True)
+    if p == 0:
+        import hashlib
+        sig.append(np.asarray(T, dtype=np.float64).tobytes())
+        print("  result checksum (last pose + keyframes + map size of pass 0):", hashlib.sha1(b"".join(sig) + bytes([kf % 256]) + int(info.map_points).to_bytes(4, "little")).hexdigest()[:16],
+              "last pose t =", np.round(np.asarray(T)[:3, 3], 9).tolist(), flush=True)
