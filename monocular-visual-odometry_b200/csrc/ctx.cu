@@ -187,11 +187,12 @@ void mvo_destroy(mvo_ctx *ctx) {
                    &ctx->pnp_cnt, &ctx->pnp_out, &ctx->ba_buf};
   for (DevBuf *b : dbs)
     if (b->p) cudaFree(b->p);
-  PinBuf *pbs[] = {&ctx->h_a, &ctx->h_b, &ctx->orb_h, &ctx->match_h};
+  PinBuf *pbs[] = {&ctx->h_a, &ctx->h_b, &ctx->h_c, &ctx->orb_h, &ctx->match_h};
   for (PinBuf *b : pbs)
     if (b->p) cudaFreeHost(b->p);
   for (const MvoEvPair &p : ctx->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -233,3 +234,12 @@ int mvo_synchronize(mvo_ctx *ctx) {
 uint64_t mvo_kernel_launches(const mvo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"
+
+cudaStream_t mvo_side_stream(mvo_ctx *ctx) {
+  if (!ctx->side_stream) {
+    cudaSetDevice(ctx->device);
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->side_stream = nullptr; }
+  }
+  return ctx->side_stream;
+}
+

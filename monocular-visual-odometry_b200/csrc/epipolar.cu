@@ -126,10 +126,19 @@ int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int
                          double *E, double *R, double *t, int32_t *inliers, int *n_inliers, int want_pose,
                          const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, float *tri_out) {
   if (!ctx) return MVO_ERR_INVALID_ARG;
-  const bool tri = tri_out != nullptr;
+  if (!E || !R || !t || !n_inliers || (*n_inliers > 0 && !inliers)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null pointer");
+  MvoEpiJob job;
+  MVO_TRY(mvo_epi_essential_begin(ctx, pts1, pts2, n, K, threshold, want_pose, tri_np1, tri_np2, tri_R, tri_t, tri_out != nullptr, &job));
+  return mvo_epi_essential_end(ctx, &job, E, R, t, inliers, n_inliers, tri_out);
+}
+
+// first half: everything up to the device-to-host copies, enqueued on ctx->stream (the caller may have pointed that at a side
+// stream); no synchronisation
+int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, int want_pose,
+                            const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, bool tri, MvoEpiJob *job) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
   if (tri && (!tri_np1 || !tri_np2 || !tri_R || !tri_t)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null triangulation input");
-  if (!pts1 || !pts2 || !K || !E || !R || !t || !n_inliers || (*n_inliers > 0 && !inliers))
-    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null pointer");
+  if (!pts1 || !pts2 || !K || !job) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: null pointer");
   if (n < 8) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "estiMotionByEssential: %d correspondences (< 8)", n);
   if (!(threshold > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByEssential: threshold must be positive");
   EpiCam cam;
@@ -192,25 +201,35 @@ int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int
     MVO_CHECK_LAUNCH(ctx);
   }
   double *h_out = (double *)(h + h_in);
-  int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);
+  int32_t *h_inl = (int32_t *)((uint8_t *)h_out + 512);
   float *h_tri = (float *)(h + h_in + h_res);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, dinl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (tri) MVO_CUDA(ctx, cudaMemcpyAsync(h_tri, d + o_tout, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (tri) memcpy(tri_out, h_tri, (size_t)n * 12);
+  job->stream = ctx->stream; job->n = n; job->H = H; job->want_pose = want_pose != 0; job->tri = tri; job->thr2 = thr2; job->f = cam.f;
+  job->h_out = h_out; job->h_inl = h_inl; job->h_tri = h_tri; job->d_valid = dvalid; job->d_cnt = dcnt; job->d_model = dE;
+  return MVO_OK;
+}
+
+// second half: wait for the job's stream, recoverPose's pick, outputs
+int mvo_epi_essential_end(mvo_ctx *ctx, MvoEpiJob *job, double *E, double *R, double *t, int32_t *inliers, int *n_inliers, float *tri_out) {
+  MVO_CUDA(ctx, cudaStreamSynchronize(job->stream));
+  const int n = job->n, H = job->H;
+  double *h_out = job->h_out;
+  int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = job->h_inl;
+  if (job->tri && tri_out) memcpy(tri_out, job->h_tri, (size_t)n * 12);
   const int ni = h_i[0];
   if (getenv("MVO_EPI_DEBUG")) {
     std::vector<int32_t> hv(H), hc(H);
     std::vector<double> hE(9);
-    cudaMemcpy(hv.data(), dvalid, (size_t)H * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(hc.data(), dcnt, (size_t)H * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(hE.data(), dE, 72, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hv.data(), job->d_valid, (size_t)H * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hc.data(), job->d_cnt, (size_t)H * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hE.data(), job->d_model, 72, cudaMemcpyDeviceToHost);
     int nv = 0, mx = -2, why[4] = {0, 0, 0, 0};
     for (int h2 = 0; h2 < H; ++h2) { nv += hv[h2] > 0; if (hv[h2] <= 0 && hv[h2] > -4) why[-hv[h2]]++; if (hc[h2] > mx) mx = hc[h2]; }
     fprintf(stderr, "epi debug: rejected samples by reason 0..3: %d %d %d %d\n", why[0], why[1], why[2], why[3]);
     fprintf(stderr, "epi debug: H=%d valid=%d max count=%d | finish: inliers %d best %d votes %d minimal %d after LO %d | thr2 %.3e f %.1f | E[0]= %.4f %.4f %.4f %.4f %.4f %.4f %.4f %.4f %.4f\n",
-            H, nv, mx, h_i[0], h_i[1], h_i[2], h_i[3], h_i[4], thr2, cam.f, hE[0], hE[1], hE[2], hE[3], hE[4], hE[5], hE[6], hE[7], hE[8]);
+            H, nv, mx, h_i[0], h_i[1], h_i[2], h_i[3], h_i[4], job->thr2, job->f, hE[0], hE[1], hE[2], hE[3], hE[4], hE[5], hE[6], hE[7], hE[8]);
   }
   if (ni < 8) {
     *n_inliers = 0;
@@ -218,7 +237,7 @@ int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int
                     h_i[3], h_i[4], ni);
   }
   if (ni > *n_inliers) return mvo_fail(ctx, MVO_ERR_CAPACITY, "inlier capacity %d < %d", *n_inliers, ni);
-  if (!want_pose) {
+  if (!job->want_pose) {
     memcpy(E, h_out, 72);
     memcpy(inliers, h_inl, (size_t)ni * 4);
     *n_inliers = ni;
@@ -247,9 +266,20 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
                                   double *Hout, double *Rs, double *ts, double *normals, int *n_solutions, int32_t *inliers,
                                   int *n_inliers) {
   if (!ctx) return MVO_ERR_INVALID_ARG;
-  if (!pts1 || !pts2 || !K || !Hout || !Rs || !ts || !normals || !n_solutions || !n_inliers || (*n_inliers > 0 && !inliers))
+  if (!Hout || !Rs || !ts || !normals || !n_solutions || !n_inliers || (*n_inliers > 0 && !inliers))
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByHomography: null pointer");
   *n_solutions = 0;
+  MvoEpiJob job;
+  MVO_TRY(mvo_epi_homography_begin(ctx, pts1, pts2, n, K, threshold, &job));
+  return mvo_epi_homography_end(ctx, &job, K, Hout, Rs, ts, normals, n_solutions, inliers, n_inliers);
+}
+
+}  // extern "C"
+
+// first half (own device / pinned scratch, so that it can run next to an essential-matrix job on another stream)
+int mvo_epi_homography_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, MvoEpiJob *job) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (!pts1 || !pts2 || !K || !job) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByHomography: null pointer");
   if (n < 4) return mvo_fail(ctx, MVO_ERR_DEGENERATE, "estiMotionByHomography: %d correspondences (< 4)", n);
   if (!(threshold > 0)) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "estiMotionByHomography: threshold must be positive");
   HomoCam cam;
@@ -262,9 +292,9 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_p1 = 0, o_p2 = al(o_p1 + (size_t)n * 8), o_inl = al(o_p2 + (size_t)n * 8), o_H = al(o_inl + (size_t)n * 4);
   const size_t o_valid = al(o_H + (size_t)H * 72), o_cnt = al(o_valid + (size_t)H * 4), o_out = al(o_cnt + (size_t)H * 4), o_end = o_out + 512;
-  MVO_TRY(mvo_reserve(ctx, ctx->d_a, o_end));
-  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, al((size_t)n * 16) + (size_t)n * 4 + 1024));
-  uint8_t *d = (uint8_t *)ctx->d_a.p, *h = (uint8_t *)ctx->h_a.p;
+  MVO_TRY(mvo_reserve(ctx, ctx->d_e, o_end));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_c, al((size_t)n * 16) + (size_t)n * 4 + 1024));
+  uint8_t *d = (uint8_t *)ctx->d_e.p, *h = (uint8_t *)ctx->h_c.p;
   memcpy(h, pts1, (size_t)n * 8);
   memcpy(h + (size_t)n * 8, pts2, (size_t)n * 8);
   MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p1, h, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -287,10 +317,20 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
     MVO_CUDA(ctx, launch_finish_cluster(ctx, sizeof(HomoFinSmem), k_homo_finish, d1, d2, n, cam, thr2, H, (const double *)dH, (const int32_t *)dcnt, dout, dout_i, dinl)); }
   MVO_CHECK_LAUNCH(ctx);
   double *h_out = (double *)(h + al((size_t)n * 16));
-  int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = (int32_t *)((uint8_t *)h_out + 512);
+  int32_t *h_inl = (int32_t *)((uint8_t *)h_out + 512);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, dinl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memset(job, 0, sizeof *job);
+  job->stream = ctx->stream; job->n = n; job->H = H; job->thr2 = thr2; job->f = cam.f; job->h_out = h_out; job->h_inl = h_inl;
+  return MVO_OK;
+}
+
+int mvo_epi_homography_end(mvo_ctx *ctx, MvoEpiJob *job, const double *K, double *Hout, double *Rs, double *ts, double *normals, int *n_solutions,
+                           int32_t *inliers, int *n_inliers) {
+  MVO_CUDA(ctx, cudaStreamSynchronize(job->stream));
+  double *h_out = job->h_out;
+  int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = job->h_inl;
+  *n_solutions = 0;
   const int ni = h_i[0];
   if (ni < 4) {
     *n_inliers = 0;
@@ -315,6 +355,8 @@ int mvo_esti_motion_by_homography(mvo_ctx *ctx, const float *pts1, const float *
   *n_solutions = ns;
   return MVO_OK;
 }
+
+extern "C" {
 
 int mvo_remove_wrong_rt_of_homography(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, const int32_t *inliers, int n_inliers,
                                       double *Rs, double *ts, double *normals, int *n_solutions) {

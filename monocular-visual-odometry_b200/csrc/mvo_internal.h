@@ -81,7 +81,8 @@ struct mvo_ctx {
 
   // generic scratch
   DevBuf d_a, d_b, d_c, d_d, d_e, d_f;
-  PinBuf h_a, h_b;
+  PinBuf h_a, h_b, h_c;
+  cudaStream_t side_stream = nullptr;   // mvo_side_stream()
 
   // ORB workspace (sized for `orb_batch` frames of the current layout)
   OrbLayout orb;
@@ -165,6 +166,16 @@ struct MvoTrackGlue {
 int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,
                           int rows, int cols, uint8_t *d_vis, float *d_cxy);
 int mvo_track_kpt_xy(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, float *d_xy);
+// gather of several device arrays into one staging buffer (track.cu: k_pack_segments); lengths and offsets in 32-bit words
+#define MVO_PACK_SEGS 8
+struct MvoPackSegs {
+  int n;
+  const uint32_t *src[MVO_PACK_SEGS];
+  uint32_t first[MVO_PACK_SEGS + 1];       // running start of segment s in the concatenated index space; first[n] = total words
+  uint32_t dst_word[MVO_PACK_SEGS];        // where segment s starts in the destination
+  uint8_t zero_after[MVO_PACK_SEGS];       // clear the source behind the copy
+};
+int mvo_track_pack_segments(mvo_ctx *ctx, const MvoPackSegs &segs, uint32_t *d_dst);
 int mvo_track_kpt_colors(mvo_ctx *ctx, const mvo_keypoint *d_kpts, int n, const uint8_t *d_image, int channels, size_t stride, uint8_t *d_rgb);
 int mvo_track_gather_pairs(mvo_ctx *ctx, const int32_t *d_pairs, int n, const int32_t *d_n, const float *d_map_pts,
                            const mvo_keypoint *d_kpts, float *d_p3, float *d_p2);
@@ -206,7 +217,7 @@ struct MvoKfFetch {
   const int32_t *vis, *matched; int n_counters;                // visible / matched increments per map position
   const uint32_t *keys; int n_ref;                             // matcher keys reference keyframe x this frame; n_ref = 0: not available
 };
-int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out);
+int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int with_links, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out);
 int mvo_trk_set_ref_desc(mvo_tracker *t, int slot, int tag);
 int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res);
 
@@ -230,6 +241,21 @@ int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t
 int mvo_match_filter_keys(mvo_ctx *ctx, int method_index, const uint32_t *keys, int n1, mvo_dmatch *out, int *n_out);
 // estiMotionByEssential with the keyframe branch's options: no recoverPose vote, triangulation of all correspondences in the same
 // submission (epipolar.cu)
+// the same, and estiMotionByHomography, split at the synchronisation: _begin enqueues everything on ctx->stream (which the caller may
+// point at ctx's side stream for the duration of the call), _end waits for that stream and post-processes.  The two estimations use
+// separate scratch buffers, so the initialisation runs them side by side (two_view.cpp).
+struct MvoEpiJob {
+  cudaStream_t stream; int n, H; bool want_pose, tri; double thr2, f;
+  double *h_out; int32_t *h_inl; float *h_tri;
+  const void *d_valid, *d_cnt, *d_model;      // MVO_EPI_DEBUG
+};
+int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, int want_pose,
+                            const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, bool tri, MvoEpiJob *job);
+int mvo_epi_essential_end(mvo_ctx *ctx, MvoEpiJob *job, double *E, double *R, double *t, int32_t *inliers, int *n_inliers, float *tri_out);
+int mvo_epi_homography_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, MvoEpiJob *job);
+int mvo_epi_homography_end(mvo_ctx *ctx, MvoEpiJob *job, const double *K, double *Hout, double *Rs, double *ts, double *normals, int *n_solutions,
+                           int32_t *inliers, int *n_inliers);
+cudaStream_t mvo_side_stream(mvo_ctx *ctx);      // a second non-blocking stream of the context, created on first use (ctx.cu)
 int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
                          double *E, double *R, double *t, int32_t *inliers, int *n_inliers, int want_pose,
                          const float *tri_np1, const float *tri_np2, const double *tri_R, const double *tri_t, float *tri_out);

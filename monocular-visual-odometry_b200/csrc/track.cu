@@ -127,7 +127,32 @@ __global__ void __launch_bounds__(1024) k_track_glue(GlueArgs a) {
     for (int q = tid; q < a.nmap; q += blockDim.x) a.vis_cnt[q] += a.vis[q] != 0;
 }
 
+// Up to MVO_PACK_SEGS device arrays gathered into one staging buffer (32-bit words; a segment may be zeroed behind the copy: the
+// visible / matched counters are read and reset in one go), so that a keyframe fetch costs ONE device-to-host copy instead of seven
+// small ones queued behind each other.
+__global__ void __launch_bounds__(256) k_pack_segments(MvoPackSegs a, uint32_t *__restrict__ dst) {
+  const uint32_t total = a.first[a.n];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int s = 0;
+    while (s + 1 < a.n && i >= a.first[s + 1]) ++s;
+    const uint32_t k = i - a.first[s];
+    dst[a.dst_word[s] + k] = a.src[s][k];
+    if (a.zero_after[s]) const_cast<uint32_t *>(a.src[s])[k] = 0;
+  }
+}
+
 }  // namespace
+
+int mvo_track_pack_segments(mvo_ctx *ctx, const MvoPackSegs &segs, uint32_t *d_dst) {
+  if (segs.n <= 0 || segs.first[segs.n] == 0) return MVO_OK;
+  const uint32_t total = segs.first[segs.n];
+  int grid = (int)((total + 255) / 256);
+  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+  KTimer kt(ctx, KC_TRACK);
+  k_pack_segments<<<grid, 256, 0, ctx->stream>>>(segs, d_dst);
+  MVO_CHECK_LAUNCH(ctx);
+  return MVO_OK;
+}
 
 // ---- launchers (asynchronous on ctx->stream) ------------------------------------------------------------
 int mvo_track_project_map(mvo_ctx *ctx, const float *d_map_pts, int nmap, const double *Tcw12, const double *K,

@@ -695,17 +695,18 @@ int mvo_trk_set_ref_desc(mvo_tracker *t, int slot, int tag) {
 // Keyframe insertion, device-resident mode: everything the host needs of the frame that was just tracked, in ONE submission
 // and ONE synchronisation — keypoints, descriptors, colours (gathered on the device for an image in device memory), the
 // connections PnP gave it (inliers_to_mappt_connections_), the visible / matched increments since the last call (reset like
-// mvo_trk_counters does), and the matcher keys of the reference keyframe's descriptors against this frame's (match_mode 0 =
+// mvo_trk_counters does; with_links = 0 for a frame that has not been tracked: initialisation), and the matcher keys of the reference keyframe's descriptors against this frame's (match_mode 0 =
 // nearest neighbour, 1 = two nearest; only when the descriptors kept by mvo_trk_set_ref_desc carry `ref_tag`).
-int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out) {
+int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int with_links, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out) {
   mvo_ctx *ctx = t->ctx;
   ExtractJob &job = t->job[slot];
   memset(out, 0, sizeof *out);
   if (job.want_host) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "tracker: the frame was extracted for the host-array path");
-  if (t->frames.empty()) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: no frame in the buffer");
+  if (with_links && t->frames.empty()) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: no frame in the buffer");
   const int n = job.nk;
-  const TrackedFrame &f = t->frames.back();
-  const int nl = f.slot < 0 ? 0 : f.n_links;
+  static const TrackedFrame none = TrackedFrame();
+  const TrackedFrame &f = with_links ? t->frames.back() : none;       // with_links: the acquired frame is the newest buffered one
+  const int nl = (!with_links || f.slot < 0) ? 0 : f.n_links;
   const bool cnt_dev = n_counters > 0 && t->dev_nmap >= 0;
   if (cnt_dev && n_counters != t->dev_nmap)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: counters asked for %d points, the device map holds %d", n_counters, t->dev_nmap);
@@ -723,37 +724,53 @@ int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int n_counter
   const size_t o_m = o;   o = al256(o + (size_t)std::max(n_counters, 0) * 4);
   const size_t o_key = o; o = al256(o + (do_match ? (size_t)t->n_ref * W * 4 : 0));
   MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_b, o + 256));
+  MVO_TRY(mvo_reserve(ctx, ctx->d_d, o + 256));
   uint8_t *h = (uint8_t *)ctx->h_b.p;
+  // every piece is gathered into one device staging buffer by one kernel and comes back in one copy
+  MvoPackSegs segs;
+  memset(&segs, 0, sizeof segs);
+  uint32_t words = 0;
+  auto add = [&](const void *src, size_t bytes, size_t dst_off, bool zero) {
+    if (!bytes) return;
+    segs.src[segs.n] = (const uint32_t *)src; segs.first[segs.n] = words; segs.dst_word[segs.n] = (uint32_t)(dst_off / 4);
+    segs.zero_after[segs.n] = zero ? 1 : 0;
+    words += (uint32_t)((bytes + 3) / 4);
+    ++segs.n;
+  };
   if (n > 0) {
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_k, job.d_k, (size_t)n * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_d, job.d_d, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    add(job.d_k, (size_t)n * sizeof(mvo_keypoint), o_k, false);
+    add(job.d_d, (size_t)n * 32, o_d, false);
     if (want_rgb) {
       MVO_TRY(mvo_reserve(ctx, ctx->d_f, (size_t)n * 3 + 256));
       MVO_TRY(mvo_track_kpt_colors(ctx, job.d_k, n, job.image, job.channels, job.stride, (uint8_t *)ctx->d_f.p));
-      MVO_CUDA(ctx, cudaMemcpyAsync(h + o_c, ctx->d_f.p, (size_t)n * 3, cudaMemcpyDeviceToHost, ctx->stream));
+      add(ctx->d_f.p, (size_t)n * 3, o_c, false);
     }
   }
   if (do_match) {
     MVO_TRY(mvo_reserve(ctx, ctx->match_keys, (size_t)t->n_ref * W * 4 + 256));
     MVO_TRY(mvo_match_launch(ctx, match_mode, t->d_ref_desc, nullptr, t->n_ref, job.d_d, nullptr, n, 0.f, (uint32_t *)ctx->match_keys.p));
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_key, ctx->match_keys.p, (size_t)t->n_ref * W * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    add(ctx->match_keys.p, (size_t)t->n_ref * W * 4, o_key, false);
   }
   if (nl > 0) {
     const size_t oe = (size_t)f.slot * t->dev_cap;
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_li, t->d_edge_map + oe, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_lk, t->d_edge_kp + oe, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    add(t->d_edge_map + oe, (size_t)nl * 4, o_li, false);
+    add(t->d_edge_kp + oe, (size_t)nl * 4, o_lk, false);
   }
   if (cnt_dev) {
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_v, t->d_vis_cnt, (size_t)n_counters * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(h + o_m, t->d_match_cnt, (size_t)n_counters * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaMemsetAsync(t->d_vis_cnt, 0, (size_t)n_counters * 4, ctx->stream));
-    MVO_CUDA(ctx, cudaMemsetAsync(t->d_match_cnt, 0, (size_t)n_counters * 4, ctx->stream));
-  } else if (n_counters > 0) {          // no frame has been tracked against this map yet
-    memset(h + o_v, 0, (size_t)n_counters * 4);
-    memset(h + o_m, 0, (size_t)n_counters * 4);
+    add(t->d_vis_cnt, (size_t)n_counters * 4, o_v, true);
+    add(t->d_match_cnt, (size_t)n_counters * 4, o_m, true);
+  }
+  segs.first[segs.n] = words;
+  if (words) {
+    MVO_TRY(mvo_track_pack_segments(ctx, segs, (uint32_t *)ctx->d_d.p));
+    MVO_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_d.p, o, cudaMemcpyDeviceToHost, ctx->stream));
   }
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   t->ref_copy_pending = false;
+  if (!cnt_dev && n_counters > 0) {          // no frame has been tracked against this map yet: no increments
+    memset(h + o_v, 0, (size_t)n_counters * 4);
+    memset(h + o_m, 0, (size_t)n_counters * 4);
+  }
   out->n_kpts = n;
   out->kpts = (const mvo_keypoint *)(h + o_k); out->desc = h + o_d; out->rgb = want_rgb ? h + o_c : nullptr;
   out->link_ids = (const int32_t *)(h + o_li); out->link_kp = (const int32_t *)(h + o_lk); out->n_links = nl;

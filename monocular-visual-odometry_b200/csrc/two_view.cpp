@@ -23,16 +23,34 @@ extern "C" int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, 
   // ---- essential (:43-48); threshold = config findEssentialMat_threshold (mvo_params::essential_threshold) ----
   std::vector<int32_t> inl_e((size_t)n), inl_h((size_t)n);
   int n_e = n, n_h = 0;
-  MVO_TRY(mvo_esti_motion_by_essential(ctx, pts_img1, pts_img2, n, K, ctx->prm.essential_threshold, sol->E, sol->R[0], sol->t[0], inl_e.data(), &n_e));
-  // ---- homography + removeWrongRtOfHomography (:56-67) ----
+  // The two RANSACs are independent: the homography job is enqueued on the context's side stream while the essential-matrix job
+  // runs on the main one (separate scratch buffers); with per-kernel event timing enabled they run one after the other.
   double Rh[36], th[12], nh[12];
   int num_h = 0;
-  if (calc_homo) {
-    n_h = n;
-    const int rc = mvo_esti_motion_by_homography(ctx, pts_img1, pts_img2, n, K, ctx->prm.homography_threshold, sol->H, Rh, th, nh, &num_h, inl_h.data(), &n_h);
-    if (rc == MVO_ERR_DEGENERATE) { num_h = 0; n_h = 0; }
-    else if (rc != MVO_OK) return rc;
-    if (num_h > 0) MVO_TRY(mvo_remove_wrong_rt_of_homography(ctx, np1.data(), np2.data(), n, inl_h.data(), n_h, Rh, th, nh, &num_h));
+  {
+    MvoEpiJob je, jh;
+    bool h_running = false;
+    MVO_TRY(mvo_epi_essential_begin(ctx, pts_img1, pts_img2, n, K, ctx->prm.essential_threshold, 1, nullptr, nullptr, nullptr, nullptr, false, &je));
+    int rc_h = MVO_OK;
+    if (calc_homo) {
+      cudaStream_t main_stream = ctx->stream, side = ctx->timing_mask ? nullptr : mvo_side_stream(ctx);
+      if (side) ctx->stream = side;
+      rc_h = mvo_epi_homography_begin(ctx, pts_img1, pts_img2, n, K, ctx->prm.homography_threshold, &jh);
+      ctx->stream = main_stream;
+      h_running = rc_h == MVO_OK;
+    }
+    const int rc_e = mvo_epi_essential_end(ctx, &je, sol->E, sol->R[0], sol->t[0], inl_e.data(), &n_e, nullptr);
+    // ---- homography + removeWrongRtOfHomography (:56-67) ----
+    if (h_running) {
+      n_h = n;
+      rc_h = mvo_epi_homography_end(ctx, &jh, K, sol->H, Rh, th, nh, &num_h, inl_h.data(), &n_h);
+    }
+    if (rc_e != MVO_OK) return rc_e;
+    if (calc_homo) {
+      if (rc_h == MVO_ERR_DEGENERATE) { num_h = 0; n_h = 0; }
+      else if (rc_h != MVO_OK) return rc_h;
+      if (num_h > 0) MVO_TRY(mvo_remove_wrong_rt_of_homography(ctx, np1.data(), np2.data(), n, inl_h.data(), n_h, Rh, th, nh, &num_h));
+    }
   }
   // ---- combine (:75-89): solution 0 = essential, then the homography survivors, each with ITS inlier list ----
   sol->num_solutions = 1 + num_h;

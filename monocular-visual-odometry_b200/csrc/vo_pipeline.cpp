@@ -580,6 +580,19 @@ int call_bundle_adjustment(mvo_vo *v, mvo_vo_frame_info *info) {
   return MVO_OK;
 }
 
+// device-resident mode: keypoints / descriptors / colours of a one-submission fetch become the frame's host copy
+void adopt_fetched(mvo_vo *v, VoFrame *f, const MvoKfFetch &kf) {
+  if (f->host_ready) return;
+  const bool cur = f == v->curr.get() && v->cur_image;
+  f->kpts.assign(kf.kpts, kf.kpts + kf.n_kpts);
+  f->desc.assign(kf.desc, kf.desc + (size_t)kf.n_kpts * 32);
+  f->xy.resize((size_t)kf.n_kpts * 2);
+  for (int i = 0; i < kf.n_kpts; ++i) { f->xy[2 * i] = f->kpts[(size_t)i].x; f->xy[2 * i + 1] = f->kpts[(size_t)i].y; }
+  if (kf.rgb) f->colors.assign(kf.rgb, kf.rgb + (size_t)kf.n_kpts * 3);
+  else { f->colors.assign((size_t)kf.n_kpts * 3, 0); if (cur) sample_colors(f, v->cur_image, v->cur_channels, v->cur_stride); }
+  f->host_ready = true;
+}
+
 // the keyframe branch of addFrame (vo_addFrame.cpp:93-124)
 int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
   VoFrame &c = *v->curr;
@@ -594,17 +607,9 @@ int insert_keyframe(mvo_vo *v, mvo_vo_frame_info *info) {
     // reference keyframe (whose descriptors stayed on the device): one submission, one synchronisation
     MvoKfFetch kf;
     const bool cur = v->cur_image != nullptr;
-    MVO_TRY(mvo_trk_keyframe_fetch(v->trk, c.slot, cur && v->cur_on_device, (int)v->dev_order.size(), r.id,
+    MVO_TRY(mvo_trk_keyframe_fetch(v->trk, c.slot, cur && v->cur_on_device, 1, (int)v->dev_order.size(), r.id,
                                    method == 1 ? 0 : (method == 2 ? 1 : -1), &kf));
-    if (!c.host_ready) {
-      c.kpts.assign(kf.kpts, kf.kpts + kf.n_kpts);
-      c.desc.assign(kf.desc, kf.desc + (size_t)kf.n_kpts * 32);
-      c.xy.resize((size_t)kf.n_kpts * 2);
-      for (int i = 0; i < kf.n_kpts; ++i) { c.xy[2 * i] = c.kpts[(size_t)i].x; c.xy[2 * i + 1] = c.kpts[(size_t)i].y; }
-      if (kf.rgb) c.colors.assign(kf.rgb, kf.rgb + (size_t)kf.n_kpts * 3);
-      else { c.colors.assign((size_t)kf.n_kpts * 3, 0); if (cur) sample_colors(&c, v->cur_image, v->cur_channels, v->cur_stride); }
-      c.host_ready = true;
-    }
+    adopt_fetched(v, &c, kf);
     if (!c.conn_ready) {
       for (int i = 0; i < kf.n_links; ++i) c.conn[kf.link_kp[i]] = PtConn{-1, kf.link_ids[i]};
       c.conn_ready = true;
@@ -846,9 +851,27 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
     }
   } else if (v->state == VO_DOING_INITIALIZATION) {              // :35-69
     const VoFrame &r = *v->ref;
-    if (v->dev) rc = ensure_host(v, frame.get());
-    if (rc == MVO_OK)
-      rc = match_into(v, r.desc.data(), r.xy.data(), r.n(), *frame, v->prm.match_method_init, v->prm.max_match_dist_init, &frame->matches_with_ref);
+    bool matched = false;
+    static const bool legacy = getenv("MVO_VO_LEGACY_KEYFRAME") != nullptr;
+    const int mi = v->prm.match_method_init;
+    if (v->dev && !legacy) {            // the frame's host copy and its match against the first keyframe in one synchronisation
+      MvoKfFetch kf;
+      rc = mvo_trk_keyframe_fetch(v->trk, slot, v->cur_on_device, 0, 0, r.id, mi == 1 ? 0 : (mi == 2 ? 1 : -1), &kf);
+      if (rc == MVO_OK) {
+        adopt_fetched(v, frame.get(), kf);
+        if (kf.n_ref > 0 && kf.n_ref == r.n()) {
+          frame->matches_with_ref.resize((size_t)kf.n_ref);
+          int nm = 0;
+          rc = mvo_match_filter_keys(v->ctx, mi, kf.keys, kf.n_ref, frame->matches_with_ref.data(), &nm);
+          frame->matches_with_ref.resize((size_t)nm);
+          matched = rc == MVO_OK;
+        }
+      }
+    } else if (v->dev) {
+      rc = ensure_host(v, frame.get());
+    }
+    if (rc == MVO_OK && !matched)
+      rc = match_into(v, r.desc.data(), r.xy.data(), r.n(), *frame, mi, v->prm.max_match_dist_init, &frame->matches_with_ref);
     int usable = 0, good = 0;
     if (rc == MVO_OK) { info.n_matches = (int)frame->matches_with_ref.size(); rc = estimate_motion_and_3d_points(v, &info, &usable); }
     if (rc == MVO_OK && usable) rc = is_vo_good_to_init(v, &info, &good);

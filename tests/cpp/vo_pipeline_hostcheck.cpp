@@ -113,6 +113,31 @@ extern "C" const char *cudaGetErrorString(cudaError_t) { return "host check: no 
 int mvo_orb_extract_ex(mvo_ctx *, const uint8_t *image, int rows, int cols, int channels, size_t stride, int, mvo_keypoint *kpts, int *n_kpts, uint8_t *desc) {
   return g_stages.orb_extract(image, rows, cols, channels, stride, kpts, n_kpts, desc);
 }
+// csrc/two_view.cpp runs the two RANSACs as begin / end pairs (side by side on two streams in the product); here the pair forwards to the
+// installed stage when it is collected
+static struct { const float *p1, *p2; int n; const double *K; double thr; } g_e_job, g_h_job;
+cudaStream_t mvo_side_stream(mvo_ctx *) { return nullptr; }
+int mvo_epi_essential_begin(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, double threshold, int, const float *, const float *,
+                            const double *, const double *, bool, MvoEpiJob *) {
+  g_e_job = {p1, p2, n, K, threshold};
+  return MVO_OK;
+}
+int mvo_epi_essential_end(mvo_ctx *, MvoEpiJob *, double *E, double *R, double *t, int32_t *inliers, int *n_inliers, float *) {
+  return g_stages.esti_motion_by_essential(g_e_job.p1, g_e_job.p2, g_e_job.n, g_e_job.K, g_e_job.thr, E, R, t, inliers, n_inliers);
+}
+int mvo_epi_homography_begin(mvo_ctx *, const float *p1, const float *p2, int n, const double *K, double threshold, MvoEpiJob *) {
+  g_h_job = {p1, p2, n, K, threshold};
+  return MVO_OK;
+}
+int mvo_epi_homography_end(mvo_ctx *, MvoEpiJob *, const double *, double *H, double *Rs, double *ts, double *normals, int *n_solutions, int32_t *inliers,
+                           int *n_inliers) {
+  return g_stages.esti_motion_by_homography(g_h_job.p1, g_h_job.p2, g_h_job.n, g_h_job.K, g_h_job.thr, H, Rs, ts, normals, n_solutions, inliers, n_inliers);
+}
+int mvo_epi_essential_ex(mvo_ctx *, const float *, const float *, int, const double *, double, double *, double *, double *, int32_t *, int *, int, const float *,
+                         const float *, const double *, const double *, float *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_match_filter_keys(mvo_ctx *, int, const uint32_t *, int, mvo_dmatch *, int *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_keyframe_fetch(mvo_tracker *, int, int, int, int, int, int, MvoKfFetch *) { return MVO_ERR_UNSUPPORTED; }
+int mvo_trk_set_ref_desc(mvo_tracker *, int, int) { return MVO_ERR_UNSUPPORTED; }
 int mvo_trk_device_mode(const mvo_tracker *) { return 0; }
 void mvo_trk_configure(mvo_tracker *, int, int) {}
 int mvo_trk_acquire(mvo_tracker *, const uint8_t *, int, size_t, int, int *, int *) { return MVO_ERR_UNSUPPORTED; }
