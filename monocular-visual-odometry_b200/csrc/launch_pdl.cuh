@@ -46,3 +46,31 @@ static inline cudaError_t launch_pdl(cudaStream_t stream, unsigned grid, unsigne
   return emu_cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
 #endif
 }
+
+// the same for kernels with multi-dimensional grids (the extraction chain: gray -> pyramid -> FAST -> select -> Harris -> retainBest ->
+// grid selection -> blur -> describe -> pre-match); no clusters there
+template <class... P, class... A>
+static inline cudaError_t launch_pdl3(cudaStream_t stream, dim3 grid, dim3 block, size_t smem, void (*kernel)(P...), A &&...args) {
+#ifdef __CUDACC__
+  static const bool pdl_on = !(getenv("MVO_PDL") && atoi(getenv("MVO_PDL")) == 0) && !(getenv("MVO_PDL_ORB") && atoi(getenv("MVO_PDL_ORB")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  unsigned na = 0;
+  if (pdl_on) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+#else
+  (void)stream;
+  emu_launch(grid, block, smem, [&] { kernel(args...); });
+  return cudaSuccess;
+#endif
+}

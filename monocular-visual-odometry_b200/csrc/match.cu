@@ -19,6 +19,7 @@
 // + 1 pack + 1 min.  No tensor cores: integer/POPC-issue bound.
 #include <stdlib.h>
 #include "mvo_internal.h"
+#include "launch_pdl.cuh"
 
 namespace {
 
@@ -70,7 +71,12 @@ __global__ void __launch_bounds__(kQ)
 match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n1,
              const uint4 *__restrict__ d2, const float2 *__restrict__ xy2, int n2, int chunk,
              float r2, uint32_t *__restrict__ part, unsigned int *__restrict__ tickets,
-             uint32_t *__restrict__ keys, const uint8_t *__restrict__ qmask) {
+             uint32_t *__restrict__ keys, const uint8_t *__restrict__ qmask, const int32_t *__restrict__ n2_dev) {
+  pdl_wait();                              // the describe kernel wrote the train descriptors (and their count, n2_dev)
+  pdl_launch_dependents();
+  // n2_dev (optional): the number of train descriptors lives on the device (the extraction's keypoint count never visited the
+  // host); n2 is then its upper bound and the grid was sized for it — splits beyond the real count report "no match"
+  if (n2_dev) n2 = min(n2, *n2_dev);
   __shared__ uint4 s_t[kMaxChunk * 2];
   __shared__ float2 s_xy[MODE == 2 ? kMaxChunk : 1];
   __shared__ bool s_last;
@@ -78,7 +84,7 @@ match_kernel(const uint4 *__restrict__ d1, const float2 *__restrict__ xy1, int n
   const int q = blockIdx.x * kQ + threadIdx.x;
   const int split = blockIdx.y, nsplit = gridDim.y;
   const int j0 = split * chunk;
-  const int cnt = min(chunk, n2 - j0);
+  const int cnt = max(0, min(chunk, n2 - j0));
 
   for (int i = threadIdx.x; i < cnt * 2; i += kQ) s_t[i] = d2[(size_t)j0 * 2 + i];
   if (MODE == 2)
@@ -170,6 +176,13 @@ int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d
 int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
                             const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
                             uint32_t *d_keys, const uint8_t *d_qmask) {
+  return mvo_match_launch_ndev(ctx, mode, d_d1, d_xy1, n1, d_d2, d_xy2, n2, nullptr, radius, d_keys, d_qmask);
+}
+
+// d_n2 != nullptr: the train count is read on the device, n2 is its upper bound (mvo_internal.h)
+int mvo_match_launch_ndev(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                          const uint8_t *d_d2, const float *d_xy2, int n2, const int32_t *d_n2, float radius,
+                          uint32_t *d_keys, const uint8_t *d_qmask) {
   if (mode < 0 || mode > 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "match: bad mode %d", mode);
   if (n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535)
     return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "match: n1=%d n2=%d outside [0,65535]", n1, n2);
@@ -203,11 +216,11 @@ int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const f
   const float2 *xa = (const float2 *)d_xy1, *xb = (const float2 *)d_xy2;
   KTimer kt(ctx, KC_MATCH);
   if (mode == 0)
-    match_kernel<0><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, block, 0, match_kernel<0>, a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask, d_n2));
   else if (mode == 1)
-    match_kernel<1><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, block, 0, match_kernel<1>, a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask, d_n2));
   else
-    match_kernel<2><<<grid, block, 0, ctx->stream>>>(a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, block, 0, match_kernel<2>, a, xa, n1, b, xb, n2, chunk, r2, part, tickets, d_keys, d_qmask, d_n2));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

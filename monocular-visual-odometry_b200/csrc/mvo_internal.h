@@ -234,6 +234,9 @@ int mvo_orb_extract_end(mvo_ctx *ctx, mvo_keypoint *kpts, int *n_kpts, uint8_t *
 // the same with keypoints and descriptors left on the device (valid until the next begin on this context)
 int mvo_orb_extract_begin_dev(mvo_ctx *ctx, const uint8_t *image, int rows, int cols, int channels, size_t stride, int on_device);
 int mvo_orb_extract_end_dev(mvo_ctx *ctx, int *n_kpts, const mvo_keypoint **d_kpts, const uint8_t **d_desc);
+// between the two: the buffers being filled and the device address of the keypoint count (orb_host.cpp)
+int mvo_orb_extract_peek_dev(mvo_ctx *ctx, const mvo_keypoint **d_kpts, const uint8_t **d_desc, const int32_t **d_count, int *n_max);
+int mvo_orb_extract_used_host_path(mvo_ctx *ctx);
 // mvo_match_features with the train descriptors optionally already on the device (match_host.cpp)
 int mvo_match_features_ex(mvo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int d2_on_device,
                           int method_index, const float *xy1, const float *xy2, float radius, mvo_dmatch *out, int *n_out);
@@ -268,6 +271,10 @@ int mvo_match_launch(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d
 int mvo_match_launch_masked(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
                             const uint8_t *d_d2, const float *d_xy2, int n2, float radius,
                             uint32_t *d_keys, const uint8_t *d_qmask);
+// the train count on the device (d_n2; n2 = its upper bound, for which the grid is sized)
+int mvo_match_launch_ndev(mvo_ctx *ctx, int mode, const uint8_t *d_d1, const float *d_xy1, int n1,
+                          const uint8_t *d_d2, const float *d_xy2, int n2, const int32_t *d_n2, float radius,
+                          uint32_t *d_keys, const uint8_t *d_qmask);
 // pnp.cu: device-resident solvePnPRansac replacement (see there)
 int mvo_pnp_dev_buffers(mvo_ctx *ctx, int n, float **p3, float **p2, double **pose_io, int32_t **out_i, int32_t **inl);
 int mvo_pnp_dev_run(mvo_ctx *ctx, int n, const double *K, const int32_t *d_n);

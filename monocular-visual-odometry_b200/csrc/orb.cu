@@ -22,6 +22,7 @@
 #include <cuda.h>               // CUtensorMap: the FAST band tiles are staged by TMA (cp.async.bulk.tensor)
 #include <stdlib.h>
 #include "orb.cuh"
+#include "launch_pdl.cuh"   // the extraction chain is launched with programmatic dependent launch: every kernel starts with pdl_wait()
 
 namespace cg = cooperative_groups;
 
@@ -39,6 +40,8 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 __global__ void __launch_bounds__(128)
 k_gray(OrbPlanDev plan, const uint8_t *__restrict__ in, int channels, size_t stride, size_t frame_stride,
        uint8_t *__restrict__ planes) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int y = blockIdx.y, f = blockIdx.z;
   const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
   const int w = plan.lv[0].w, pitch = plan.lv[0].pitch;
@@ -66,6 +69,8 @@ k_gray(OrbPlanDev plan, const uint8_t *__restrict__ in, int channels, size_t str
 // ---------------------------------------------------------------------------------- resize
 __global__ void __launch_bounds__(128)
 k_resize(OrbPlanDev plan, int level, const int32_t *__restrict__ tables, uint8_t *__restrict__ planes) {
+  pdl_wait();
+  pdl_launch_dependents();
   const OrbLevelDev &L = plan.lv[level];
   const OrbLevelDev &S = plan.lv[level - 1];
   const int y = blockIdx.y, f = blockIdx.z;
@@ -140,6 +145,8 @@ template <bool TMA>
 __global__ void __launch_bounds__(256)
 k_fast(OrbPlanDev plan, const uint8_t *__restrict__ planes, uint32_t *__restrict__ staging,
        int32_t *__restrict__ bandcnt, const __grid_constant__ FastMaps maps) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   const int band = blockIdx.x, f = blockIdx.y;
   int l = 0;
@@ -388,6 +395,8 @@ __device__ __forceinline__ void grid_rank_keep_seg(int n, const uint16_t *__rest
 __global__ void __launch_bounds__(1024)
 k_select(OrbPlanDev plan, const uint32_t *__restrict__ staging, const int32_t *__restrict__ bandcnt,
          uint32_t *__restrict__ cand, uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta, int seg_tab) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncell = plan.grid_rows * plan.grid_cols;
@@ -704,6 +713,8 @@ __device__ int ret_retain_best(const RetBuf &b, int n, int npts) {
 __global__ void __launch_bounds__(RET_T)
 k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__restrict__ harris, OrbFrameMeta *__restrict__ meta,
          uint16_t *__restrict__ kept, int32_t *__restrict__ kept_cnt) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ int s_scratch[2 * RET_W + 8];
   const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -753,6 +764,8 @@ k_retain(OrbPlanDev plan, const uint32_t *__restrict__ cand, const float *__rest
 __global__ void __launch_bounds__(1024)
 k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t *__restrict__ kept, const int32_t *__restrict__ kept_cnt,
               uint2 *__restrict__ sel, OrbFrameMeta *__restrict__ meta, int seg_tab) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(128) uint8_t smem[];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (meta[f].overflow != 1) return;
@@ -832,6 +845,8 @@ struct BlurTiles { int first[MVO_MAX_LEVELS + 1]; int nx[MVO_MAX_LEVELS]; };
 
 __global__ void __launch_bounds__(256)
 k_blur(OrbPlanDev plan, BlurTiles tiles, uint8_t *__restrict__ planes) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ uint8_t s_in[BLUR_TH + 6][BLUR_TW + 8];
   __shared__ float s_row[BLUR_TH + 6][BLUR_TW + 1];
   int level = 0;
@@ -989,6 +1004,8 @@ k_describe(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__r
            const mvo_keypoint *__restrict__ kin, int n_in, mvo_keypoint *__restrict__ kout,
            uint8_t *__restrict__ desc, int32_t *__restrict__ counts, int out_cap, int with_desc,
            int32_t *__restrict__ bad_flag) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ char2 s_pat[512];
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_pat[i] = make_char2(kOrbPattern[i][0], kOrbPattern[i][1]);
@@ -1060,6 +1077,8 @@ k_describe(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__r
 __global__ void __launch_bounds__(128)
 k_harris_all(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint32_t *__restrict__ cand,
              const OrbFrameMeta *__restrict__ meta, float *__restrict__ harris) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.y;
   if (meta[f].overflow == 0) return;              // only retainBest needs the response of every candidate
   const int n = min(meta[f].n_cand, plan.cand_cap);
@@ -1122,7 +1141,7 @@ int orb_launch_gray(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, i
                     size_t frame_stride, uint8_t *planes, int batch) {
   dim3 grid((plan.lv[0].pitch / 4 + 127) / 128, plan.rows, batch);
   KTimer kt(ctx, KC_GRAY);
-  k_gray<<<grid, 128, 0, ctx->stream>>>(plan, d_in, channels, stride, frame_stride, planes);
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(128), 0, k_gray, plan, d_in, channels, stride, frame_stride, planes));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1131,7 +1150,7 @@ int orb_launch_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const int32_t *tabl
   for (int l = 1; l < plan.nlevels; ++l) {
     dim3 grid((plan.lv[l].pitch / 4 + 127) / 128, plan.lv[l].h, batch);
     KTimer kt(ctx, KC_RESIZE);
-    k_resize<<<grid, 128, 0, ctx->stream>>>(plan, l, tables, planes);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(128), 0, k_resize, plan, l, tables, planes));
     MVO_CHECK_LAUNCH(ctx);
   }
   return MVO_OK;
@@ -1208,11 +1227,11 @@ int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes,
   KTimer kt(ctx, KC_FAST);
   if (tma) {
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fast<true><<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt, *maps);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(256), smem, k_fast<true>, plan, planes, staging, bandcnt, *maps));
   } else {
     static const FastMaps none = {};
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fast<false><<<grid, 256, smem, ctx->stream>>>(plan, planes, staging, bandcnt, none);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(256), smem, k_fast<false>, plan, planes, staging, bandcnt, none));
   }
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
@@ -1236,7 +1255,7 @@ int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *stag
   if (smem > 48 * 1024)
     MVO_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   KTimer kt(ctx, KC_SELECT);
-  k_select<<<batch, 1024, smem, ctx->stream>>>(plan, staging, bandcnt, cand, sel, meta, seg_tab);
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, dim3(batch), dim3(1024), smem, k_select, plan, staging, bandcnt, cand, sel, meta, seg_tab));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1256,8 +1275,8 @@ int orb_launch_blur(mvo_ctx *ctx, const OrbPlanDev &plan, uint8_t *planes, int b
   // extraction on the B200 (gpurun_out/r2s1_orb_variants.jsonl), byte-identical output: default since round 2; MVO_BLUR2=0 = old kernel
   static const bool use_blur2 = getenv("MVO_BLUR2") == nullptr || atoi(getenv("MVO_BLUR2")) != 0;
   KTimer kt(ctx, KC_BLUR);
-  if (use_blur2) k_blur2<<<grid, 256, 0, ctx->stream>>>(plan, tiles, planes);
-  else k_blur<<<grid, 256, 0, ctx->stream>>>(plan, tiles, planes);
+  if (use_blur2) MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(256), 0, k_blur2, plan, tiles, planes));
+  else MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(256), 0, k_blur, plan, tiles, planes));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1266,7 +1285,7 @@ int orb_launch_harris_all(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *p
                           const OrbFrameMeta *meta, float *harris, int batch) {
   dim3 grid(ctx->sm_count, batch);
   KTimer kt(ctx, KC_HARRIS);
-  k_harris_all<<<grid, 128, 0, ctx->stream>>>(plan, planes, cand, meta, harris);
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(128), 0, k_harris_all, plan, planes, cand, meta, harris));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1279,7 +1298,7 @@ int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand
   const size_t smem = (size_t)RET_MAX * 10;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_retain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   { KTimer kt(ctx, KC_SELECT);
-  k_retain<<<dim3(plan.nlevels, batch), RET_T, smem, ctx->stream>>>(plan, cand, harris, meta, kept, kept_cnt); }
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, dim3(plan.nlevels, batch), dim3(RET_T), smem, k_retain, plan, cand, harris, meta, kept, kept_cnt)); }
   MVO_CHECK_LAUNCH(ctx);
   const int ncell = plan.grid_rows * plan.grid_cols;
   size_t smem2 = (size_t)(2 * ncell + 1) * 4 + (size_t)plan.sel_cap * (4 + 2 + 2 + 1 + 1) + 64;
@@ -1288,7 +1307,7 @@ int orb_launch_retain(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *cand
   if (seg_tab) smem2 += (size_t)32 * ncell + 32;
   MVO_CUDA(ctx, cudaFuncSetAttribute(k_select_kept, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   { KTimer kt(ctx, KC_SELECT);
-  k_select_kept<<<batch, 1024, smem2, ctx->stream>>>(plan, cand, kept, kept_cnt, sel, meta, seg_tab); }
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, dim3(batch), dim3(1024), smem2, k_select_kept, plan, cand, kept, kept_cnt, sel, meta, seg_tab)); }
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1301,10 +1320,10 @@ int orb_launch_describe_sel(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t 
   static const bool use_describe2 = getenv("MVO_DESCRIBE2") != nullptr && atoi(getenv("MVO_DESCRIBE2")) != 0;      // experimental variant
   KTimer kt(ctx, KC_DESCRIBE);
   if (use_describe2)
-    k_describe_sel2<<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, sel, meta, n_override, kpts, desc, counts, out_cap, with_desc);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe_sel2, plan, planes, sel, meta, n_override, kpts, desc, counts, out_cap, with_desc));
   else
-    k_describe<0><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, sel, meta, n_override, nullptr, 0, kpts,
-                                                             desc, counts, out_cap, with_desc, nullptr);
+    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe<0>, plan, planes, sel, meta, n_override, (const mvo_keypoint *)nullptr, 0, kpts,
+                              desc, counts, out_cap, with_desc, (int32_t *)nullptr));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
@@ -1314,8 +1333,8 @@ int orb_launch_describe_kpts(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t
   if (n <= 0) return MVO_OK;
   dim3 grid((n + DESC_WARPS - 1) / DESC_WARPS, 1);
   KTimer kt(ctx, KC_DESCRIBE);
-  k_describe<1><<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(plan, planes, nullptr, nullptr, nullptr, kpts, n, nullptr,
-                                                           desc, nullptr, 0, 1, bad_flag);
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe<1>, plan, planes, (const uint2 *)nullptr, (const OrbFrameMeta *)nullptr, (const int32_t *)nullptr, kpts, n,
+                            (mvo_keypoint *)nullptr, desc, (int32_t *)nullptr, 0, 1, bad_flag));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

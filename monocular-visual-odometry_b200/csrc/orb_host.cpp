@@ -432,6 +432,24 @@ int mvo_orb_extract_begin_dev(mvo_ctx *ctx, const uint8_t *image, int rows, int 
   return extract_begin(ctx, image, rows, cols, channels, stride, true, on_device != 0, false);
 }
 
+// Between begin_dev and end_dev: the device buffers the pending extraction is filling and the address of its keypoint count on the
+// device, so that a consumer kernel (the tracker's pre-match) can be queued behind the extraction without waiting for the count.
+// *host_path_possible: the count may still be replaced by the host retainBest path (overflow == 2, see extract_end) — the caller
+// checks mvo_orb_extract_used_host_path() after end_dev and redoes its kernel in that (adversarial-input) case.
+int mvo_orb_extract_peek_dev(mvo_ctx *ctx, const mvo_keypoint **d_kpts, const uint8_t **d_desc, const int32_t **d_count, int *n_max) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  OrbPending *pd = pending_of(ctx);
+  if (!pd->active) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "extract_peek: nothing pending");
+  if (d_kpts) *d_kpts = pd->d_k;
+  if (d_desc) *d_desc = pd->d_d;
+  if (d_count) *d_count = &pd->ws.meta[0].n_sel;
+  if (n_max) *n_max = pd->out_cap;
+  return MVO_OK;
+}
+int mvo_orb_extract_used_host_path(mvo_ctx *ctx) {
+  OrbPending *pd = pending_of(ctx);
+  return pd->h_meta && pd->h_meta->overflow == 2 ? 1 : 0;
+}
 int mvo_orb_extract_end_dev(mvo_ctx *ctx, int *n_kpts, const mvo_keypoint **d_kpts, const uint8_t **d_desc) {
   if (!ctx) return MVO_ERR_INVALID_ARG;
   return extract_end(ctx, nullptr, n_kpts, nullptr, d_desc, d_kpts);

@@ -70,6 +70,8 @@ constexpr int BLUR2_ROWF = BLUR_TW + 4;         // floats per row of the row-pas
 
 __global__ void __launch_bounds__(256)
 k_blur2(OrbPlanDev plan, BlurTiles tiles, uint8_t *__restrict__ planes) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ uint32_t s_in[BLUR_TH + 6][BLUR2_INW];
   __shared__ __align__(16) float s_row[BLUR_TH + 6][BLUR2_ROWF];
   int level = 0;
@@ -203,6 +205,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32)
 k_describe_sel2(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__restrict__ sel, const OrbFrameMeta *__restrict__ meta,
                 const int32_t *__restrict__ n_override, mvo_keypoint *__restrict__ kout, uint8_t *__restrict__ desc,
                 int32_t *__restrict__ counts, int out_cap, int with_desc) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float2 s_patf[512];
   const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 512; i += DESC_WARPS * 32) s_patf[i] = make_float2((float)kOrbPattern[i][0], (float)kOrbPattern[i][1]);

@@ -186,6 +186,9 @@ void worker_main(mvo_tracker *t) {
     }
     mvo_ctx *x = t->xctx[slot];
     int rc, nk = 0;
+    static const bool dbg_worker = getenv("MVO_TRACK_DEBUG") != nullptr;
+    const double tw0 = dbg_worker ? now_us() : 0;
+    double tw1 = 0;
     if (j->want_host) {
       const int cap = x->prm.max_keypoints + 1;
       j->kpts.resize(cap);
@@ -195,17 +198,42 @@ void worker_main(mvo_tracker *t) {
       if (rc == MVO_OK) rc = mvo_orb_extract_end(x, j->kpts.data(), &nk, j->desc.data(), &j->d_d);
     } else {
       rc = mvo_orb_extract_begin_dev(x, j->image, t->rows, t->cols, j->channels, j->stride, j->on_device);
-      if (rc == MVO_OK) rc = mvo_orb_extract_end_dev(x, &nk, &j->d_k, &j->d_d);
       j->matched = false;
-      if (rc == MVO_OK && j->prematch && nk > 0 && j->nmap > 0 && !(j->match_mode == 1 && nk < 2)) {
-        // all map descriptors x this frame's descriptors on the extraction stream: off the tracking chain
-        rc = mvo_match_launch_masked(x, j->match_mode, j->d_map_desc, nullptr, j->nmap, j->d_d, nullptr, nk, 0.f, j->d_keys, nullptr);
+      // All map descriptors x this frame's descriptors on the extraction stream, off the tracking chain — queued right behind
+      // the describe kernel: the keypoint count is read on the device (its upper bound sizes the grid), so the extraction
+      // chain of a frame is one submission and one synchronisation.
+      bool queued = false;
+      const bool want_match = j->prematch && j->nmap > 0;
+      if (rc == MVO_OK && want_match) {
+        const uint8_t *dd = nullptr;
+        const int32_t *dn = nullptr;
+        int n_max = 0;
+        rc = mvo_orb_extract_peek_dev(x, nullptr, &dd, &dn, &n_max);
+        if (rc == MVO_OK && n_max >= 2) {
+          rc = mvo_match_launch_ndev(x, j->match_mode, j->d_map_desc, nullptr, j->nmap, dd, nullptr, n_max, dn, 0.f, j->d_keys, nullptr);
+          queued = rc == MVO_OK;
+        }
+      }
+      if (dbg_worker) tw1 = now_us();
+      if (rc == MVO_OK) rc = mvo_orb_extract_end_dev(x, &nk, &j->d_k, &j->d_d);
+      if (rc == MVO_OK && want_match && nk > 0 && !(j->match_mode == 1 && nk < 2)) {
+        if (!queued || mvo_orb_extract_used_host_path(x))        // the host retainBest path replaced the keypoints: match again
+          rc = mvo_match_launch_masked(x, j->match_mode, j->d_map_desc, nullptr, j->nmap, j->d_d, nullptr, nk, 0.f, j->d_keys, nullptr);
         if (rc == MVO_OK && cudaStreamSynchronize(x->stream) != cudaSuccess) rc = MVO_ERR_CUDA;
         j->matched = rc == MVO_OK;
+      } else if (rc == MVO_OK && queued) {
+        if (cudaStreamSynchronize(x->stream) != cudaSuccess) rc = MVO_ERR_CUDA;      // the queued kernel must not outlive the job
       }
     }
     j->rc = rc;
     j->nk = nk;
+    if (dbg_worker) {                    // how long the extraction chain of one frame takes on the worker (enqueue / until everything has run)
+      static double acc_enq = 0, acc_all = 0;
+      static int n_w = 0;
+      const double t_end = now_us();
+      acc_enq += tw1 - tw0; acc_all += t_end - tw0;
+      if (++n_w % 50 == 0) { fprintf(stderr, "extraction worker: %.1f us/frame from job start to done (kernels enqueued after %.1f us)\n", acc_all / 50, acc_enq / 50); acc_enq = acc_all = 0; }
+    }
     {
       std::lock_guard<std::mutex> lk(t->mu);
       ++t->n_run;

@@ -8,6 +8,7 @@
 #include "cuda_emu.h"
 
 #include "orb.cuh"
+#include "pdl_device.cuh"   // pdl_wait / pdl_launch_dependents: no-ops on the CPU tier
 namespace {
 #include "orb_pattern.inc"
 float c_gauss7[7];
