@@ -15,6 +15,8 @@ pushCurrPointsToMap_, optimizeMap_.  Initialisation and keyframes are inside the
           the same state machine over cv2 (the OpenCV the reference calls) + oracle/ba_oracle.c (g2o restated); the
           reference binary itself cannot be built here (no OpenCV C++/g2o/...)
 
+A step is ONE call of mvo_vo_run_sequence (include/mvo.h: run_vo.cpp's main loop over frames in memory).
+
 One JSON line on stdout (rank 0).  Launch for N > 1:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port P bench.py --gpus N --steps K --warmup W
@@ -299,20 +301,12 @@ def run_gpu(args, rank, world, local_rank):
         return (p_np[i],), {}
 
     def run_pass(args_of):
-        """One step: the whole sequence from a BLANK state; frame i+1 is handed over (look-ahead) before frame i is added."""
+        """One step: the whole sequence from a BLANK state through mvo_vo_run_sequence — run_vo.cpp's main loop (for every image:
+        addFrame, record the pose) over frames in memory; frame i+1 is handed over (look-ahead) before frame i is added."""
         vo.reset()
-        poses, states, kf = [], [], 0
-        a, k = args_of(0)
-        vo.prefetch(*a, **k)
-        info = None
-        for i in range(N_FRAMES):
-            if i + 1 < N_FRAMES:
-                a2, k2 = args_of(i + 1)
-                vo.prefetch(*a2, **k2)
-            a, k = args_of(i)
-            T, info = vo.add_frame(*a, **k)
-            poses.append(T); states.append(info.state_out); kf += info.keyframe
-        return poses, states, kf, info
+        a = [args_of(i) for i in range(N_FRAMES)]
+        poses, infos = vo.run_sequence([x[0][0] for x in a], **a[0][1])
+        return list(poses), [inf.state_out for inf in infos], sum(inf.keyframe for inf in infos), infos[-1]
 
     def barrier():
         if dist is not None:
@@ -413,8 +407,8 @@ def run_gpu(args, rank, world, local_rank):
             "dtype": "u8/f32/f64", "data": "synthetic", "config": bench_config(),
             "detail": {"sequences": "one independent synthetic sequence per GPU (seed = rank)",
                        "ms_per_frame": ms / args.steps / N_FRAMES,
-                       "pipelining": "the next frame is handed over with mvo_vo_prefetch: its upload, ORB extraction and descriptor matching "
-                                     "overlap the current frame (2 streams); results identical",
+                       "pipelining": "one mvo_vo_run_sequence call per step (run_vo.cpp's main loop in C): the next frame is handed over with "
+                                     "mvo_vo_prefetch, its upload, ORB extraction and descriptor matching overlap the current frame (2 streams); results identical",
                        "device_resident": True, "tracking_ok": ok, "keyframes": int(kf),
                        "last_frame": {"keypoints": info_last.n_keypoints, "matches": info_last.n_matches,
                                       "inliers": info_last.n_inliers, "ba_frames": info_last.ba_frames, "map_points": info_last.map_points},

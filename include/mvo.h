@@ -469,6 +469,13 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
  * and descriptor matching against the map overlap the current frame (mvo_tracker_prefetch).  Frames must then be added in
  * the same order with the same image pointer; at most two frames in flight; results are identical. */
 int mvo_vo_prefetch(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device);
+/* The main loop of run_vo.cpp (:107-140: for every image: createFrame, vo->addFrame, cam_pose_history.push_back) over n_frames images
+ * that are already in memory, with the look-ahead of mvo_vo_prefetch applied to frame i + 1 while frame i is added.  images[i]:
+ * rows x cols x channels, host or device memory alike for all frames; T_w_c_out: n_frames x 16 doubles (the pose of every
+ * frame when its addFrame returned); infos: n_frames records or NULL; *n_done = frames added when the call returns (it stops at
+ * the first frame whose addFrame fails and returns that code).  Results equal n_frames calls of mvo_vo_add_frame_ex. */
+int mvo_vo_run_sequence(mvo_vo *v, const uint8_t *const *images, int n_frames, int channels, size_t stride, int images_on_device,
+                        double *T_w_c_out, mvo_vo_frame_info *infos, int *n_done);
 /* 1 when the tracking branch runs through the device-resident tracker (mvo_vo_params::track.device_resident, fixed map
  * points), 0 when every stage goes through its host-array entry point. */
 int mvo_vo_device_resident(const mvo_vo *v);

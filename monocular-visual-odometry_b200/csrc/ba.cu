@@ -82,9 +82,12 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // exp of a g2o SE3 update (omega, upsilon) applied on the left of (R, t): out = exp(d) * in
 __device__ void se3_update(const double *d, const double *in, double *out) {
   const double wx = d[0], wy = d[1], wz = d[2];
-  const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+  const double th2 = wx * wx + wy * wy + wz * wz;
   double a, b, c;
-  if (th < 0.00001) { a = 1; b = 1; c = 1; }        // g2o's small-angle branch: R = V = I + O + O^2
+  // g2o tests theta = sqrt(th2) < 0.00001; the square root is only taken where th2 is within rounding of that boundary (and on the
+  // large-angle path), not on the chain of every trial
+  const bool tiny = th2 < 0.99999e-10 ? true : (th2 > 1.00001e-10 ? false : sqrt(th2) < 0.00001);
+  if (tiny) { a = 1; b = 1; c = 1; }                // g2o's small-angle branch: R = V = I + O + O^2
   else if (th2 < 0.0625) {
     // sin(th)/th, (1-cos th)/th^2, (th-sin th)/th^3 as Taylor polynomials in th^2 (next term < 1e-24 relative for
     // th < 0.25): LM steps are small rotations, and this keeps sincos, a square root and three divisions off the
@@ -94,7 +97,7 @@ __device__ void se3_update(const double *d, const double *in, double *out) {
     b = 0.5 + x * (-1.0 / 24 + x * (1.0 / 720 + x * (-1.0 / 40320 + x * (1.0 / 3628800 + x * (-1.0 / 479001600 + x * (1.0 / 87178291200.0 + x * (-1.0 / 20922789888000.0 + x * (1.0 / 6402373705728000.0))))))));
     c = 1.0 / 6 + x * (-1.0 / 120 + x * (1.0 / 5040 + x * (-1.0 / 362880 + x * (1.0 / 39916800 + x * (-1.0 / 6227020800.0 + x * (1.0 / 1307674368000.0 + x * (-1.0 / 355687428096000.0 + x * (1.0 / 121645100408832000.0))))))));
   }
-  else { double sn, cs; sincos(th, &sn, &cs); const double ith = 1.0 / th; a = sn * ith; b = (1 - cs) * ith * ith; c = (th - sn) * ith * ith * ith; }
+  else { const double th = sqrt(th2); double sn, cs; sincos(th, &sn, &cs); const double ith = 1.0 / th; a = sn * ith; b = (1 - cs) * ith * ith; c = (th - sn) * ith * ith * ith; }
   const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
   double O2[9];
   for (int i = 0; i < 3; ++i)
@@ -103,7 +106,7 @@ __device__ void se3_update(const double *d, const double *in, double *out) {
   for (int i = 0; i < 9; ++i) {
     const double I = (i % 4 == 0) ? 1.0 : 0.0;
     Rd[i] = I + a * O[i] + b * O2[i];
-    V[i] = (th < 0.00001) ? Rd[i] : I + b * O[i] + c * O2[i];
+    V[i] = tiny ? Rd[i] : I + b * O[i] + c * O2[i];
   }
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) out[i * 3 + j] = Rd[i * 3] * in[j] + Rd[i * 3 + 1] * in[3 + j] + Rd[i * 3 + 2] * in[6 + j];
@@ -579,6 +582,21 @@ struct PoseArgs {
   MvoPoseStore st;          // STORE variant only: the tracker's device-resident frame buffer (F = listed slots)
 };
 
+// fast double reciprocal / reciprocal square root: float seed + Newton steps (<= 1 ulp), no fp64
+// division or sqrt on the dependent chain
+__device__ __forceinline__ double fast_rcp(double z) {
+  double r = (double)__frcp_rn((float)z);
+  r = r * (2.0 - z * r);
+  r = r * (2.0 - z * r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double c) {
+  double y = (double)rsqrtf((float)c);
+  y = y * (1.5 - 0.5 * c * y * y);
+  y = y * (1.5 - 0.5 * c * y * y);
+  return y;
+}
+
 __device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/, const double *g, double lambda, double *x) {
   // Cholesky with reciprocal diagonal (one rsqrt per column, no divisions on the dependent chain)
   double L[21], inv[6];     // lower triangle, row-major packed: L[i*(i+1)/2 + j]
@@ -597,8 +615,11 @@ __device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/,
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
     if (!(d > 0) || !isfinite(d)) { ok = false; d = 1; }
-    double id = rsqrt(d);
-    id = id * (1.5 - 0.5 * d * id * id);          // one Newton step: full double accuracy
+    // float seed + two Newton steps (<= 1 ulp) while the pivot is inside the float range: the library rsqrt(double) is a ~20-instruction
+    // dependent sequence, six of them sat on the chain of every LM trial
+    double id;
+    if (d > 1e-30 && d < 1e30) id = fast_rsqrt(d);
+    else { id = rsqrt(d); id = id * (1.5 - 0.5 * d * id * id); }
     inv[j] = id;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
@@ -624,21 +645,6 @@ __device__ __forceinline__ bool chol6_solve(const double *h /*21 packed upper*/,
     x[i] = s2 * inv[i];
   }
   return ok;
-}
-
-// fast double reciprocal / reciprocal square root: float seed + Newton steps (<= 1 ulp), no fp64
-// division or sqrt on the dependent chain
-__device__ __forceinline__ double fast_rcp(double z) {
-  double r = (double)__frcp_rn((float)z);
-  r = r * (2.0 - z * r);
-  r = r * (2.0 - z * r);
-  return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double c) {
-  double y = (double)rsqrtf((float)c);
-  y = y * (1.5 - 0.5 * c * y * y);
-  y = y * (1.5 - 0.5 * c * y * y);
-  return y;
 }
 
 // 28 contributions of one edge at pose Rt (chi2 in v[27]); v is ACCUMULATED
@@ -734,6 +740,14 @@ __device__ void pose_pass(const PoseArgs &a, int F, int nchunks, const double *P
     }
     // frame-segmented warp reduction: chunks are frame-major, so a warp spans one frame (rarely two)
     unsigned todo = __ballot_sync(0xffffffffu, f >= 0);
+    if (todo) {                                  // the usual case: every active lane of the warp holds edges of the same frame
+      const int fl = __shfl_sync(0xffffffffu, f, __ffs(todo) - 1);
+      if (__ballot_sync(0xffffffffu, f >= 0 && f != fl) == 0) {
+        const double tot = warp_fold32(v, lane);          // idle lanes contribute their zeros
+        if (lane < PF_V) s_wacc[warp * NV + fl * PF_V + lane] += tot;
+        todo = 0;
+      }
+    }
     while (todo) {
       const int leader = __ffs(todo) - 1;
       const int fl = __shfl_sync(0xffffffffu, f, leader);

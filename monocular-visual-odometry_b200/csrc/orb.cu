@@ -99,6 +99,104 @@ k_resize(OrbPlanDev plan, int level, const int32_t *__restrict__ tables, uint8_t
   *reinterpret_cast<uint32_t *>(slot + L.img_off + (size_t)y * L.pitch + x4) = out;
 }
 
+// ------------------------------------------------------------------- gray + pyramid, fused
+// k_gray and the k_resize chain in ONE launch: a CTA takes a horizontal band of the image, converts the rows of level 0 it has to
+// hold into shared memory, derives its rows of level 1 from those, level 2 from level 1, ... (each level is resized from the
+// ROUNDED level below, as OpenCV's pyramid is) and writes the rows it OWNS of every level (orb_host.cpp: band table; neighbouring
+// bands recompute the few rows they share).  Same arithmetic as k_gray / k_resize, so the planes are bit-identical; three
+// launches, their gaps and two round trips of the lower levels through L2 go away.
+constexpr int PYR_T = 256;
+
+__device__ __forceinline__ uint32_t gray4(const uint8_t *__restrict__ row, int x4, int w, int channels, bool aligned) {
+  if (x4 >= w) return 0;
+  if (channels == 3) {
+    if (aligned && x4 + 4 <= w) {
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(row + 3 * (size_t)x4);
+      const uint32_t a = p[0], b = p[1], c = p[2];                 // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      const uint32_t g0 = (3735u * (a & 0xFF) + 19235u * ((a >> 8) & 0xFF) + 9798u * ((a >> 16) & 0xFF) + 16384u) >> 15;
+      const uint32_t g1 = (3735u * (a >> 24) + 19235u * (b & 0xFF) + 9798u * ((b >> 8) & 0xFF) + 16384u) >> 15;
+      const uint32_t g2 = (3735u * ((b >> 16) & 0xFF) + 19235u * (b >> 24) + 9798u * (c & 0xFF) + 16384u) >> 15;
+      const uint32_t g3 = (3735u * ((c >> 8) & 0xFF) + 19235u * ((c >> 16) & 0xFF) + 9798u * (c >> 24) + 16384u) >> 15;
+      return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    }
+    uint32_t out = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int x = x4 + i;
+      if (x < w) {
+        const uint32_t b = row[3 * x], gg = row[3 * x + 1], r = row[3 * x + 2];
+        out |= ((3735u * b + 19235u * gg + 9798u * r + 16384u) >> 15) << (8 * i);
+      }
+    }
+    return out;
+  }
+  uint32_t out = 0;
+  for (int i = 0; i < 4; ++i)
+    if (x4 + i < w) out |= (uint32_t)row[x4 + i] << (8 * i);
+  return out;
+}
+
+__global__ void __launch_bounds__(PYR_T)
+k_pyramid(OrbPlanDev plan, const uint8_t *__restrict__ in, int channels, size_t stride, size_t frame_stride,
+          const int32_t *__restrict__ tables, uint8_t *__restrict__ planes) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int b = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const int nl = plan.nlevels;
+  const int32_t *bt = tables + plan.pyr_tab_off + (size_t)b * nl * 4;
+  uint8_t *slot = planes + (size_t)f * plan.slot_bytes;
+  // level 0
+  uint8_t *s_prev = smem;
+  int plo = bt[0];
+  {
+    const OrbLevelDev &L = plan.lv[0];
+    const int lo = bt[0], hi = bt[1], olo = bt[2], ohi = bt[3], wpr = L.pitch >> 2;
+    const uint8_t *base = in + (size_t)f * frame_stride;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(base) | stride) & 3) == 0;
+    for (int i = tid; i < (hi - lo) * wpr; i += PYR_T) {
+      const int r = i / wpr, x4 = (i - r * wpr) << 2, y = lo + r;
+      const uint32_t v = gray4(base + (size_t)y * stride, x4, L.w, channels, aligned);
+      *reinterpret_cast<uint32_t *>(s_prev + (size_t)r * L.pitch + x4) = v;
+      if (y >= olo && y < ohi) *reinterpret_cast<uint32_t *>(slot + L.img_off + (size_t)y * L.pitch + x4) = v;
+    }
+  }
+  __syncthreads();
+  for (int l = 1; l < nl; ++l) {
+    const OrbLevelDev &L = plan.lv[l];
+    const OrbLevelDev &S = plan.lv[l - 1];
+    const int32_t *e = bt + 4 * l;
+    const int lo = e[0], hi = e[1], olo = e[2], ohi = e[3], wpr = L.pitch >> 2;
+    const int32_t *xofs = tables + L.tab_off, *xw1 = xofs + L.w, *yofs = xw1 + L.w, *yw1 = yofs + L.h;
+    uint8_t *s_cur = s_prev + (size_t)plan.pyr_rows[l - 1] * S.pitch;
+    const bool keep = l + 1 < nl;                                  // the top level is not a source
+    for (int i = tid; i < (hi - lo) * wpr; i += PYR_T) {
+      const int r = i / wpr, x4 = (i - r * wpr) << 2, y = lo + r;
+      const int oy = yofs[y], wy1 = yw1[y], wy0 = 256 - wy1;
+      const int oy1 = min(oy + 1, S.h - 1);
+      const uint8_t *r0 = s_prev + (size_t)(oy - plo) * S.pitch, *r1 = s_prev + (size_t)(oy1 - plo) * S.pitch;
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        uint32_t v = 0;
+        if (x < L.w) {
+          const int ox = __ldg(xofs + x), wx1 = __ldg(xw1 + x), wx0 = 256 - wx1;
+          const int ox1 = min(ox + 1, S.w - 1);
+          const int h0 = r0[ox] * wx0 + r0[ox1] * wx1;
+          const int h1 = r1[ox] * wx0 + r1[ox1] * wx1;
+          v = (uint32_t)(h0 * wy0 + h1 * wy1 + 32768) >> 16;
+        }
+        out |= v << (8 * k);
+      }
+      if (keep) *reinterpret_cast<uint32_t *>(s_cur + (size_t)r * L.pitch + x4) = out;
+      if (y >= olo && y < ohi) *reinterpret_cast<uint32_t *>(slot + L.img_off + (size_t)y * L.pitch + x4) = out;
+    }
+    __syncthreads();
+    s_prev = s_cur;
+    plo = lo;
+  }
+}
+
 // ------------------------------------------------------------------------------------ FAST
 // cornerScore<16> (OpenCV fast_score.cpp) == max(t, A, B) - 1 with
 //   A = max over the 16 arcs of 9 contiguous ring pixels of min(d), B the same for -d,
@@ -1153,6 +1251,23 @@ int orb_launch_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const int32_t *tabl
     MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(128), 0, k_resize, plan, l, tables, planes));
     MVO_CHECK_LAUNCH(ctx);
   }
+  return MVO_OK;
+}
+
+int orb_launch_gray_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, int channels, size_t stride, size_t frame_stride,
+                            const int32_t *tables, uint8_t *planes, int batch) {
+  static const bool off = getenv("MVO_PYR_FUSED") != nullptr && atoi(getenv("MVO_PYR_FUSED")) == 0;      // A/B hook
+  size_t smem = 0;
+  for (int l = 0; l + 1 < plan.nlevels; ++l) smem += (size_t)plan.pyr_rows[l] * plan.lv[l].pitch;
+  smem += 16;
+  if (off || plan.pyr_nb < 1 || smem > 200 * 1024) {
+    MVO_TRY(orb_launch_gray(ctx, plan, d_in, channels, stride, frame_stride, planes, batch));
+    return orb_launch_pyramid(ctx, plan, tables, planes, batch);
+  }
+  if (smem > 48 * 1024) MVO_CUDA(ctx, cudaFuncSetAttribute(k_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KTimer kt(ctx, KC_GRAY);
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, dim3(plan.pyr_nb, batch), dim3(PYR_T), smem, k_pyramid, plan, d_in, channels, stride, frame_stride, tables, planes));
+  MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }
 

@@ -27,6 +27,11 @@ struct OrbPlanDev {
   int sel_cap;                         // fast-path bound on candidates (= nfeatures = sum of level caps)
   int fast_threshold;
   uint32_t slot_bytes;
+  // fused gray + pyramid kernel (k_pyramid): the image is cut into pyr_nb horizontal bands; per band and level the rows it has to
+  // hold in shared memory and the rows it owns (writes), 4 ints each, at tables + pyr_tab_off; pyr_rows[l] = most rows of level l a band holds
+  int pyr_nb;
+  uint32_t pyr_tab_off;
+  int pyr_rows[MVO_MAX_LEVELS];
   OrbLevelDev lv[MVO_MAX_LEVELS];
 };
 
@@ -51,6 +56,9 @@ __host__ __device__ inline int orb_ps(uint32_t p) { return p >> 24; }
 int orb_launch_gray(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, int channels, size_t stride,
                     size_t frame_stride, uint8_t *planes, int batch);
 int orb_launch_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const int32_t *tables, uint8_t *planes, int batch);
+// both in one launch (k_pyramid) when the bands fit in shared memory, else the two launchers above
+int orb_launch_gray_pyramid(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *d_in, int channels, size_t stride, size_t frame_stride,
+                            const int32_t *tables, uint8_t *planes, int batch);
 int orb_launch_fast(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t *planes, uint32_t *staging,
                     int32_t *bandcnt, int batch);
 int orb_launch_select(mvo_ctx *ctx, const OrbPlanDev &plan, const uint32_t *staging, const int32_t *bandcnt,

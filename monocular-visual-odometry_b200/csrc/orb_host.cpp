@@ -113,6 +113,35 @@ int build_plan(mvo_ctx *ctx, OrbState *st, int rows, int cols) {
     axis_table(pl.lv[l - 1].w, L.w, t, t + L.w);
     axis_table(pl.lv[l - 1].h, L.h, t + 2 * L.w, t + 2 * L.w + L.h);
   }
+  // band table of the fused gray + pyramid kernel: band b owns rows [b H_l / nb, (b + 1) H_l / nb) of every level; the rows of
+  // level l it must HOLD are those plus the source rows (INTER_LINEAR_EXACT reads rows yofs[y] and yofs[y] + 1) of the rows it
+  // holds of level l + 1
+  {
+    const int nb = std::max(1, rows / 8), nl = pl.nlevels;
+    pl.pyr_nb = nb;
+    pl.pyr_tab_off = (uint32_t)st->tables.size();
+    st->tables.resize(st->tables.size() + (size_t)nb * nl * 4, 0);
+    int32_t *bt = st->tables.data() + pl.pyr_tab_off;
+    for (int l = 0; l < nl; ++l) pl.pyr_rows[l] = 0;
+    for (int b = 0; b < nb; ++b) {
+      int lo = 0, hi = 0;                                        // rows held of the level above (none above the top level)
+      for (int l = nl - 1; l >= 0; --l) {
+        const int H = pl.lv[l].h, olo = (int)((long)b * H / nb), ohi = (int)((long)(b + 1) * H / nb);
+        int nlo = olo, nhi = ohi;
+        if (l + 1 < nl && hi > lo) {
+          const OrbLevelDev &U = pl.lv[l + 1];
+          const int32_t *yofs = st->tables.data() + U.tab_off + 2 * U.w;
+          const int slo = yofs[lo], shi = std::min(yofs[hi - 1] + 1, H - 1) + 1;
+          if (nhi > nlo) { nlo = std::min(nlo, slo); nhi = std::max(nhi, shi); }
+          else { nlo = slo; nhi = shi; }
+        }
+        int32_t *e = bt + ((size_t)b * nl + l) * 4;
+        e[0] = nlo; e[1] = nhi; e[2] = olo; e[3] = ohi;
+        pl.pyr_rows[l] = std::max(pl.pyr_rows[l], nhi - nlo);
+        lo = nlo; hi = nhi;
+      }
+    }
+  }
   st->valid = true;
   ctx->orb.rows = rows;
   ctx->orb.cols = cols;
@@ -264,8 +293,7 @@ int slow_path_frame(mvo_ctx *ctx, const OrbPlanDev &pl, const OrbWs &ws, int f, 
 int run_detect(mvo_ctx *ctx, OrbState *st, const OrbWs &ws, const uint8_t *d_in, int channels, size_t stride,
                size_t frame_stride, int batch) {
   const OrbPlanDev &pl = st->plan;
-  MVO_TRY(orb_launch_gray(ctx, pl, d_in, channels, stride, frame_stride, ws.planes, batch));
-  MVO_TRY(orb_launch_pyramid(ctx, pl, ws.tables, ws.planes, batch));
+  MVO_TRY(orb_launch_gray_pyramid(ctx, pl, d_in, channels, stride, frame_stride, ws.tables, ws.planes, batch));
   MVO_TRY(orb_launch_fast(ctx, pl, ws.planes, ws.staging, ws.bandcnt, batch));
   MVO_TRY(orb_launch_select(ctx, pl, ws.staging, ws.bandcnt, ws.cand, ws.sel, ws.meta, batch));
   // frames with a level above OpenCV's featuresPerLevel: Harris response of every candidate, retainBest (twice per level) and
@@ -510,8 +538,7 @@ int mvo_calc_descriptors(mvo_ctx *ctx, const uint8_t *image, int rows, int cols,
   uint8_t *d_d = (uint8_t *)ctx->orb_kpts.p + kb;
   MVO_CUDA(ctx, cudaMemcpyAsync(d_k, h, (size_t)n_kpts * sizeof(mvo_keypoint), cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemsetAsync(ws.bad_flag, 0, 4, ctx->stream));
-  MVO_TRY(orb_launch_gray(ctx, pl, d_in, channels, stride, 0, ws.planes, 1));
-  MVO_TRY(orb_launch_pyramid(ctx, pl, ws.tables, ws.planes, 1));
+  MVO_TRY(orb_launch_gray_pyramid(ctx, pl, d_in, channels, stride, 0, ws.tables, ws.planes, 1));
   MVO_TRY(orb_launch_blur(ctx, pl, ws.planes, 1));
   MVO_TRY(orb_launch_describe_kpts(ctx, pl, ws.planes, d_k, n_kpts, d_d, ws.bad_flag));
   int32_t *h_bad = (int32_t *)(h + kb);

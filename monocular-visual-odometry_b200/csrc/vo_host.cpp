@@ -39,8 +39,8 @@ int mvo_retain_good_triangulation(const float *pts3d_in_curr, int n, const doubl
     all[(size_t)i] = angle / 3.1415926 * 180.0;                  // :213 (the reference's truncated pi)
   }
   std::vector<double> sorted = all;
-  std::sort(sorted.begin(), sorted.end());
-  const double median = sorted[(size_t)(n / 2)];                 // :220
+  std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());      // the reference sorts and reads element n / 2 (:216-220): same value
+  const double median = sorted[(size_t)(n / 2)];
   int w = 0;
   for (int i = 0; i < n; ++i) {                                  // :236-244
     if (all[(size_t)i] < min_triang_angle || all[(size_t)i] / median > max_ratio_to_median) continue;

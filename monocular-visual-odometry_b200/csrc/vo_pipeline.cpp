@@ -461,8 +461,15 @@ void optimize_map(mvo_vo *v) {
     if (match_ratio < v->map_point_erase_ratio) { it = v->map_points.erase(it); continue; }
     double d[3] = {(double)mp.pos[0] - cam[0], (double)mp.pos[1] - cam[1], (double)mp.pos[2] - cam[2]};        // getViewAngle_ (vo.cpp:578-584)
     const double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    const double angle = acos(d[0] / len * mp.norm[0] + d[1] / len * mp.norm[1] + d[2] / len * mp.norm[2]);
-    if (angle > M_PI / 4.) { it = v->map_points.erase(it); continue; }
+    // angle = acos(x) > pi/4 (vo.cpp:515-519).  acos is monotonic, so the comparison is decided by x against cos(pi/4) except in a
+    // 1e-12 band around it (and for |x| > 1, where acos is NaN and the reference keeps the point): only there acos is evaluated
+    const double x = d[0] / len * mp.norm[0] + d[1] / len * mp.norm[1] + d[2] / len * mp.norm[2];
+    const double cq = 0.70710678118654752440;
+    bool too_oblique;
+    if (x >= -1.0 && x < cq - 1e-12) too_oblique = true;
+    else if (x > cq + 1e-12) too_oblique = false;
+    else too_oblique = acos(x) > M_PI / 4.;
+    if (too_oblique) { it = v->map_points.erase(it); continue; }
     ++it;
   }
   if (v->map_points.size() > 1000) v->map_point_erase_ratio += 0.05;
@@ -933,6 +940,23 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
   if (T_w_c_out) memcpy(T_w_c_out, frame->T_w_c, 16 * sizeof(double));
   if (info_out) *info_out = info;
   return rc;
+}
+
+// run_vo.cpp:107-140 over images in memory (see mvo.h)
+int mvo_vo_run_sequence(mvo_vo *v, const uint8_t *const *images, int n_frames, int channels, size_t stride, int images_on_device,
+                        double *T_w_c_out, mvo_vo_frame_info *infos, int *n_done) {
+  if (!v) return MVO_ERR_INVALID_ARG;
+  if (n_done) *n_done = 0;
+  if (n_frames < 0 || (n_frames > 0 && (!images || !T_w_c_out))) return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: bad sequence arguments");
+  for (int i = 0; i < n_frames; ++i)
+    if (!images[i]) return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: image %d is null", i);
+  if (n_frames > 0) MVO_TRY(mvo_vo_prefetch(v, images[0], channels, stride, images_on_device));
+  for (int i = 0; i < n_frames; ++i) {
+    if (i + 1 < n_frames) MVO_TRY(mvo_vo_prefetch(v, images[i + 1], channels, stride, images_on_device));
+    MVO_TRY(mvo_vo_add_frame_ex(v, images[i], channels, stride, images_on_device, T_w_c_out + 16 * (size_t)i, infos ? infos + i : nullptr));
+    if (n_done) *n_done = i + 1;
+  }
+  return MVO_OK;
 }
 
 int mvo_vo_is_initialized(const mvo_vo *v) { return v && v->state == VO_DOING_TRACKING; }      // vo.cpp:174-177

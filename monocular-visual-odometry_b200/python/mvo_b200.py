@@ -150,6 +150,7 @@ SIGNATURES = {
     "mvo_vo_num_keyframes": (_i, [_vp]),
     "mvo_vo_add_frame_ex": (_i, [_vp, _vp, _i, _sz, _i, _vp, C.POINTER(VoFrameInfo)]),
     "mvo_vo_prefetch": (_i, [_vp, _vp, _i, _sz, _i]),
+    "mvo_vo_run_sequence": (_i, [_vp, _vp, _i, _i, _sz, _i, _vp, _vp, _vp]),
     "mvo_vo_device_resident": (_i, [_vp]),
     "mvo_vo_reset": (_i, [_vp]),
     "mvo_vo_kernel_launches": (C.c_uint64, [_vp]),
@@ -487,6 +488,29 @@ class VisualOdometry:
         T, info = np.zeros(16), VoFrameInfo()
         self.ctx._chk(self.lib.mvo_vo_add_frame_ex(self.h, p, ch, st, 1 if on_device else 0, _ptr(T), C.byref(info)))
         return T.reshape(4, 4), info
+
+    def run_sequence(self, images, channels=None, stride=None, on_device=False):
+        """run_vo.cpp's main loop over frames in memory (mvo_vo_run_sequence): images = list of HxW(x3) uint8 arrays, or of device
+        pointers (ints) with channels / stride when on_device.  Returns (poses n x 4 x 4, list of VoFrameInfo)."""
+        n = len(images)
+        if on_device:
+            addrs, ch, st, keep = [int(im) for im in images], int(channels), int(stride), None
+        else:
+            keep = [im if (isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.flags.c_contiguous) else np.ascontiguousarray(im, np.uint8)
+                    for im in images]
+            shapes = {(1 if k.ndim == 2 else k.shape[2], k.shape[1]) for k in keep}
+            if len(shapes) > 1:
+                raise ValueError("run_sequence: all frames must share width and channels")
+            ch, w = next(iter(shapes)) if shapes else (3, 0)
+            st = w * ch
+            addrs = [k.ctypes.data for k in keep]
+        ptrs = (C.c_void_p * max(n, 1))(*addrs)
+        T = np.zeros((max(n, 1), 16))
+        infos = (VoFrameInfo * max(n, 1))()
+        done = C.c_int(0)
+        self.ctx._chk(self.lib.mvo_vo_run_sequence(self.h, ptrs, n, ch, st, 1 if on_device else 0, _ptr(T), infos, C.byref(done)))
+        del keep
+        return T[:n].reshape(n, 4, 4), [infos[i] for i in range(n)]
 
     def prefetch(self, image, channels=None, stride=None, on_device=False):
         """Hand the NEXT frame over (same array object / pointer as the later add_frame call)."""

@@ -134,6 +134,13 @@ for i in range(n):
     assert np.array_equal(T, ra[i][0]), (i, np.abs(T - ra[i][0]).max())
 i2, p2, d2, c2 = voA.get_map()
 assert np.array_equal(i2, ia) and np.array_equal(p2, pa) and np.array_equal(c2, ca)
+# mvo_vo_run_sequence (run_vo.cpp's main loop in one call) = the same calls in a loop: host images and device images
+for on_dev in (False, True):
+    voA.reset()
+    poses, infos = voA.run_sequence([t.data_ptr() for t in d], channels=3, stride=1920, on_device=True) if on_dev else voA.run_sequence(imgs)
+    for i in range(n):
+        assert [getattr(infos[i], f) for f in FIELDS] == ra[i][1], (on_dev, i)
+        assert np.array_equal(poses[i], ra[i][0]), (on_dev, i)
 print("vo modes child ok")
 '''
 
