@@ -112,6 +112,12 @@ static inline unsigned __vsadu4(unsigned a, unsigned b) {                   // s
   for (int i = 0; i < 4; ++i) { const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF; s += (unsigned)(x > y ? x - y : y - x); }
   return s;
 }
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {               // per-byte absolute difference
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) { const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF; r |= (unsigned)(x > y ? x - y : y - x) << (8 * i); }
+  return r;
+}
+static inline int __any_sync(unsigned, int pred);                           // defined with the other warp votes below
 template <class T> static inline T __ldcg(const T *p) { return *p; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -134,6 +140,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   pthread_barrier_wait(&g_warp_barrier[w]);
   return m;
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline unsigned __match_any_sync(unsigned, unsigned v) {            // lanes of the warp that hold the same value
   const int w = threadIdx.x >> 5;
   g_xchg[w][threadIdx.x & 31] = v;
