@@ -163,15 +163,31 @@ int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, 
   memcpy(h + (size_t)n * 8, pts2, (size_t)n * 8);
   MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p1, h, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(d + o_p2, h + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // the triangulation does not depend on the RANSAC: it runs on the context's side stream next to it (on the same stream when
+  // per-kernel event timing is on, or when this job itself was pointed at the side stream)
+  cudaStream_t tri_stream = ctx->stream;
+  float *h_tri = (float *)(h + h_in + h_res);
   if (tri) {
+    cudaStream_t side = ctx->timing_mask ? nullptr : mvo_side_stream(ctx);
+    if (side && side != ctx->stream) tri_stream = side;
     uint8_t *ht = h + al((size_t)n * 16);
     memcpy(ht, tri_np1, (size_t)n * 8);
     memcpy(ht + (size_t)n * 8, tri_np2, (size_t)n * 8);
     memcpy(ht + al((size_t)n * 16), tri_R, 72);
     memcpy(ht + al((size_t)n * 16) + 72, tri_t, 24);
-    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t1, ht, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t2, ht + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_trt, ht + al((size_t)n * 16), 96, cudaMemcpyHostToDevice, ctx->stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t1, ht, (size_t)n * 8, cudaMemcpyHostToDevice, tri_stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_t2, ht + (size_t)n * 8, (size_t)n * 8, cudaMemcpyHostToDevice, tri_stream));
+    MVO_CUDA(ctx, cudaMemcpyAsync(d + o_trt, ht + al((size_t)n * 16), 96, cudaMemcpyHostToDevice, tri_stream));
+    {
+      cudaStream_t keep = ctx->stream;
+      ctx->stream = tri_stream;              // KTimer records on ctx->stream
+      { KTimer kt(ctx, KC_EPI);
+      k_triangulate<<<(n + 127) / 128, 128, 0, tri_stream>>>((const float *)(d + o_t1), (const float *)(d + o_t2), nullptr, n, (const double *)(d + o_trt),
+                                                              (float *)(d + o_tout)); }
+      ctx->stream = keep;
+    }
+    MVO_CHECK_LAUNCH(ctx);
+    MVO_CUDA(ctx, cudaMemcpyAsync(h_tri, d + o_tout, (size_t)n * 12, cudaMemcpyDeviceToHost, tri_stream));
   }
   const float *d1 = (const float *)(d + o_p1), *d2 = (const float *)(d + o_p2);
   double *dE = (double *)(d + o_E), *dout = (double *)(d + o_out);
@@ -194,18 +210,11 @@ int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, 
     k_epi_vote<<<(n + 63) / 64, 256, 0, ctx->stream>>>(d1, d2, cam, dout, dout_i, dinl);
     MVO_CHECK_LAUNCH(ctx);
   }
-  if (tri) {
-    KTimer kt(ctx, KC_EPI);
-    k_triangulate<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const float *)(d + o_t1), (const float *)(d + o_t2), nullptr, n, (const double *)(d + o_trt),
-                                                            (float *)(d + o_tout));
-    MVO_CHECK_LAUNCH(ctx);
-  }
   double *h_out = (double *)(h + h_in);
   int32_t *h_inl = (int32_t *)((uint8_t *)h_out + 512);
-  float *h_tri = (float *)(h + h_in + h_res);
   MVO_CUDA(ctx, cudaMemcpyAsync(h_out, dout, 512, cudaMemcpyDeviceToHost, ctx->stream));
   MVO_CUDA(ctx, cudaMemcpyAsync(h_inl, dinl, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (tri) MVO_CUDA(ctx, cudaMemcpyAsync(h_tri, d + o_tout, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  job->tri_stream = tri_stream;
   job->stream = ctx->stream; job->n = n; job->H = H; job->want_pose = want_pose != 0; job->tri = tri; job->thr2 = thr2; job->f = cam.f;
   job->h_out = h_out; job->h_inl = h_inl; job->h_tri = h_tri; job->d_valid = dvalid; job->d_cnt = dcnt; job->d_model = dE;
   return MVO_OK;
@@ -214,6 +223,7 @@ int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, 
 // second half: wait for the job's stream, recoverPose's pick, outputs
 int mvo_epi_essential_end(mvo_ctx *ctx, MvoEpiJob *job, double *E, double *R, double *t, int32_t *inliers, int *n_inliers, float *tri_out) {
   MVO_CUDA(ctx, cudaStreamSynchronize(job->stream));
+  if (job->tri && job->tri_stream != job->stream) MVO_CUDA(ctx, cudaStreamSynchronize(job->tri_stream));
   const int n = job->n, H = job->H;
   double *h_out = job->h_out;
   int32_t *h_i = (int32_t *)((uint8_t *)h_out + 256), *h_inl = job->h_inl;
@@ -377,6 +387,57 @@ int mvo_remove_wrong_rt_of_homography(mvo_ctx *ctx, const float *pts_np1, const 
   *n_solutions = w;
   return MVO_OK;
 }
+
+}  // extern "C"
+
+// doTriangulation of several (R, t, inlier list) candidates over the same matched points (the initialisation triangulates the
+// essential-matrix solution and every surviving homography solution, motion_estimation.cpp:105-112): one upload of the points, one
+// launch per candidate, one download, ONE synchronisation
+int mvo_do_triangulation_multi(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, int nsol, const double *const *R,
+                               const double *const *t, const int32_t *const *inliers, const int *n_inliers, float *const *pts3d) {
+  if (!ctx) return MVO_ERR_INVALID_ARG;
+  if (n < 0 || nsol < 0 || nsol > 8 || (nsol > 0 && (!R || !t || !inliers || !n_inliers || !pts3d)) || (n > 0 && (!pts_np1 || !pts_np2)))
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "doTriangulation: bad arguments");
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = al(al((size_t)n * 8) + (size_t)n * 8), o_in_end = 0, total_out = 0;
+  size_t o_inl[8], o_rt[8], o_out[8];
+  for (int s = 0; s < nsol; ++s) {
+    if (n_inliers[s] < 0 || !R[s] || !t[s] || (n_inliers[s] > 0 && (!inliers[s] || !pts3d[s]))) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "doTriangulation: null pointer");
+    for (int j = 0; j < n_inliers[s]; ++j)
+      if (inliers[s][j] < 0 || inliers[s][j] >= n) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "doTriangulation: inlier index %d outside [0,%d)", inliers[s][j], n);
+    o_inl[s] = o; o = al(o + (size_t)n_inliers[s] * 4);
+    o_rt[s] = o;  o = al(o + 96);
+  }
+  o_in_end = o;
+  for (int s = 0; s < nsol; ++s) { o_out[s] = o; o = al(o + (size_t)n_inliers[s] * 12); total_out += (size_t)n_inliers[s]; }
+  if (total_out == 0) return MVO_OK;
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MVO_TRY(mvo_reserve(ctx, ctx->d_b, o + 256));
+  MVO_TRY(mvo_reserve_pinned(ctx, ctx->h_a, o + 256));
+  uint8_t *d = (uint8_t *)ctx->d_b.p, *h = (uint8_t *)ctx->h_a.p;
+  memcpy(h, pts_np1, (size_t)n * 8);
+  memcpy(h + al((size_t)n * 8), pts_np2, (size_t)n * 8);
+  for (int s = 0; s < nsol; ++s) {
+    memcpy(h + o_inl[s], inliers[s], (size_t)n_inliers[s] * 4);
+    memcpy(h + o_rt[s], R[s], 72);
+    memcpy(h + o_rt[s] + 72, t[s], 24);
+  }
+  MVO_CUDA(ctx, cudaMemcpyAsync(d, h, o_in_end, cudaMemcpyHostToDevice, ctx->stream));
+  for (int s = 0; s < nsol; ++s) {
+    if (n_inliers[s] == 0) continue;
+    { KTimer kt(ctx, KC_EPI);
+    k_triangulate<<<(n_inliers[s] + 127) / 128, 128, 0, ctx->stream>>>((const float *)d, (const float *)(d + al((size_t)n * 8)), (const int32_t *)(d + o_inl[s]),
+                                                                        n_inliers[s], (const double *)(d + o_rt[s]), (float *)(d + o_out[s])); }
+    MVO_CHECK_LAUNCH(ctx);
+  }
+  MVO_CUDA(ctx, cudaMemcpyAsync(h + o_in_end, d + o_in_end, o - o_in_end, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < nsol; ++s)
+    if (n_inliers[s] > 0) memcpy(pts3d[s], h + o_out[s], (size_t)n_inliers[s] * 12);
+  return MVO_OK;
+}
+
+extern "C" {
 
 int mvo_do_triangulation(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, const double *R, const double *t,
                          const int32_t *inliers, int n_inliers, float *pts3d) {

@@ -250,6 +250,7 @@ int mvo_match_filter_keys(mvo_ctx *ctx, int method_index, const uint32_t *keys, 
 struct MvoEpiJob {
   cudaStream_t stream; int n, H; bool want_pose, tri; double thr2, f;
   double *h_out; int32_t *h_inl; float *h_tri;
+  cudaStream_t tri_stream;                    // where the fused triangulation runs (the context's side stream when there is one)
   const void *d_valid, *d_cnt, *d_model;      // MVO_EPI_DEBUG
 };
 int mvo_epi_essential_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, int want_pose,
@@ -258,6 +259,8 @@ int mvo_epi_essential_end(mvo_ctx *ctx, MvoEpiJob *job, double *E, double *R, do
 int mvo_epi_homography_begin(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold, MvoEpiJob *job);
 int mvo_epi_homography_end(mvo_ctx *ctx, MvoEpiJob *job, const double *K, double *Hout, double *Rs, double *ts, double *normals, int *n_solutions,
                            int32_t *inliers, int *n_inliers);
+int mvo_do_triangulation_multi(mvo_ctx *ctx, const float *pts_np1, const float *pts_np2, int n, int nsol, const double *const *R,
+                               const double *const *t, const int32_t *const *inliers, const int *n_inliers, float *const *pts3d);
 cudaStream_t mvo_side_stream(mvo_ctx *ctx);      // a second non-blocking stream of the context, created on first use (ctx.cu)
 int mvo_epi_essential_ex(mvo_ctx *ctx, const float *pts1, const float *pts2, int n, const double *K, double threshold,
                          double *E, double *R, double *t, int32_t *inliers, int *n_inliers, int want_pose,

@@ -519,11 +519,13 @@ __device__ __forceinline__ void grid_rank_keep_seg(int n, const uint16_t *__rest
     const bool in = i < e;
     const unsigned c = in ? (unsigned)s_cell[i] : 0xFFFF0000u + (unsigned)lane;      // lanes past the end: a group of their own
     const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const int base = in ? (int)tab[c] : 0;
-    __syncwarp();                                             // every lane has read the count before the group leader moves it
+    const int leader = 31 - __clz((int)peers);               // only the group's highest lane touches the count: one warp barrier per step
+    int base = 0;
+    if (in && lane == leader) base = (int)tab[c];
+    base = __shfl_sync(0xffffffffu, base, leader);
     if (in) {
       s_keep[i] = (uint8_t)min(base + __popc(peers & lt), 255);
-      if ((peers >> lane) == 1u) tab[c] = (uint8_t)min(base + __popc(peers), 255);
+      if (lane == leader) tab[c] = (uint8_t)min(base + __popc(peers), 255);
     }
     __syncwarp();
   }
@@ -951,18 +953,39 @@ k_select_kept(OrbPlanDev plan, const uint32_t *__restrict__ cand, const uint16_t
   }
   const uint32_t *cf = cand + (size_t)f * plan.cand_cap;
   const int gshift = orb_grid_shift(plan.grid_size);
-  for (int i = tid; i < n; i += 1024) {
-    int l = 0;
-    while (l + 1 < plan.nlevels && i >= s_off[l + 1]) ++l;
-    const uint32_t p = cf[s_base[l] + kept[((size_t)f * plan.nlevels + l) * RET_MAX + (i - s_off[l])]];
-    const float scale = plan.lv[l].scale;
-    const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
-    const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
-    int row = gshift >= 0 ? ((int)fy) >> gshift : ((int)fy) / plan.grid_size, col = gshift >= 0 ? ((int)fx) >> gshift : ((int)fx) / plan.grid_size;
-    row = min(row, plan.grid_rows - 1);
-    col = min(col, plan.grid_cols - 1);
-    const int cell = row * plan.grid_cols + col;
-    s_pk[i] = p; s_lvl[i] = (uint8_t)l; s_cell[i] = (uint16_t)cell;
+  // two dependent gathers per item (retained index -> packed candidate): eight items per thread with all loads of one kind in flight
+  // together (one item at a time cost two L2 round trips each, a third of the kernel)
+  for (int i0 = tid; i0 < n; i0 += 8 * 1024) {
+    int lv[8];
+    uint32_t kk[8], pp[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 1024;
+      lv[u] = 0; kk[u] = 0;
+      if (i < n) {
+        int l = 0;
+        while (l + 1 < plan.nlevels && i >= s_off[l + 1]) ++l;
+        lv[u] = l;
+        kk[u] = kept[((size_t)f * plan.nlevels + l) * RET_MAX + (i - s_off[l])];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pp[u] = (i0 + u * 1024 < n) ? cf[s_base[lv[u]] + kk[u]] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 1024;
+      if (i >= n) continue;
+      const int l = lv[u];
+      const uint32_t p = pp[u];
+      const float scale = plan.lv[l].scale;
+      const float fx = l ? __fmul_rn((float)orb_px(p), scale) : (float)orb_px(p);
+      const float fy = l ? __fmul_rn((float)orb_py(p), scale) : (float)orb_py(p);
+      int row = gshift >= 0 ? ((int)fy) >> gshift : ((int)fy) / plan.grid_size, col = gshift >= 0 ? ((int)fx) >> gshift : ((int)fx) / plan.grid_size;
+      row = min(row, plan.grid_rows - 1);
+      col = min(col, plan.grid_cols - 1);
+      const int cell = row * plan.grid_cols + col;
+      s_pk[i] = p; s_lvl[i] = (uint8_t)l; s_cell[i] = (uint16_t)cell;
+    }
   }
   __syncthreads();
   if (seg_tab) grid_rank_keep_seg(n, s_cell, s_keep, s_tab, ncell, plan.max_per_cell);

@@ -64,9 +64,14 @@ extern "C" int mvo_estimate_relative_poses(mvo_ctx *ctx, const float *pts_img1, 
     memcpy(inliers + (size_t)(1 + s) * n, inl_h.data(), (size_t)n_h * 4);
   }
   // ---- triangulation of every solution (:105-112) ----
-  for (int s = 0; s < sol->num_solutions; ++s)
-    MVO_TRY(mvo_do_triangulation(ctx, np1.data(), np2.data(), n, sol->R[s], sol->t[s], inliers + (size_t)s * n, sol->n_inliers[s],
-                                 pts3d + (size_t)s * n * 3));
+  {
+    const double *Rs[8], *ts[8];
+    const int32_t *is[8];
+    float *ps[8];
+    int ns[8];
+    for (int s = 0; s < sol->num_solutions; ++s) { Rs[s] = sol->R[s]; ts[s] = sol->t[s]; is[s] = inliers + (size_t)s * n; ns[s] = sol->n_inliers[s]; ps[s] = pts3d + (size_t)s * n * 3; }
+    MVO_TRY(mvo_do_triangulation_multi(ctx, np1.data(), np2.data(), n, sol->num_solutions, Rs, ts, is, ns, ps));
+  }
   // ---- change of frame, after everything else (:114-118): basics::invRt ----
   if (!motion_cam2_to_cam1)
     for (int s = 0; s < sol->num_solutions; ++s) {

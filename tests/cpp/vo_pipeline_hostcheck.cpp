@@ -133,6 +133,14 @@ int mvo_epi_homography_end(mvo_ctx *, MvoEpiJob *, const double *, double *H, do
                            int *n_inliers) {
   return g_stages.esti_motion_by_homography(g_h_job.p1, g_h_job.p2, g_h_job.n, g_h_job.K, g_h_job.thr, H, Rs, ts, normals, n_solutions, inliers, n_inliers);
 }
+int mvo_do_triangulation_multi(mvo_ctx *, const float *np1, const float *np2, int n, int nsol, const double *const *R, const double *const *t,
+                               const int32_t *const *inliers, const int *n_inliers, float *const *pts3d) {
+  for (int s = 0; s < nsol; ++s) {
+    const int rc = g_stages.do_triangulation(np1, np2, n, R[s], t[s], inliers[s], n_inliers[s], pts3d[s]);
+    if (rc != MVO_OK) return rc;
+  }
+  return MVO_OK;
+}
 int mvo_epi_essential_ex(mvo_ctx *, const float *, const float *, int, const double *, double, double *, double *, double *, int32_t *, int *, int, const float *,
                          const float *, const double *, const double *, float *) { return MVO_ERR_UNSUPPORTED; }
 int mvo_match_filter_keys(mvo_ctx *, int, const uint32_t *, int, mvo_dmatch *, int *) { return MVO_ERR_UNSUPPORTED; }
