@@ -303,7 +303,7 @@ int mvo_tracker_track(mvo_tracker *t, const uint8_t *image, int channels, size_t
                       int image_on_device, double *T_w_c_out, mvo_track_result *res);
 /* Optional look-ahead: hand a FUTURE frame to the tracker's extraction worker (own host thread, own stream) so that
  * its upload, ORB extraction and — for match methods 1/2, which do not depend on the pose — its descriptor matching
- * against the map overlap the tracking of the current frame.  At most two frames in flight.  Frames must then be
+ * against the map overlap the tracking of the current frame.  At most two frames in flight next to the one being tracked.  Frames must then be
  * passed to mvo_tracker_track in the same order, with the same image pointer, and the image memory must stay valid
  * and unchanged until that mvo_tracker_track call returns (page-locked host images are copied from directly).  The
  * result is identical to tracking without prefetch. */
@@ -467,7 +467,8 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
                         mvo_vo_frame_info *info);
 /* Optional look-ahead (device-resident mode; a no-op otherwise): hand the NEXT frame over so that its upload, ORB extraction
  * and descriptor matching against the map overlap the current frame (mvo_tracker_prefetch).  Frames must then be added in
- * the same order with the same image pointer; at most two frames in flight; results are identical. */
+ * the same order with the same image pointer; at most two frames in flight next to the one being added (three between calls); results
+ * are identical. */
 int mvo_vo_prefetch(mvo_vo *v, const uint8_t *image, int channels, size_t stride, int image_on_device);
 /* The main loop of run_vo.cpp (:107-140: for every image: createFrame, vo->addFrame, cam_pose_history.push_back) over n_frames images
  * that are already in memory, with the look-ahead of mvo_vo_prefetch applied to frame i + 1 while frame i is added.  images[i]:

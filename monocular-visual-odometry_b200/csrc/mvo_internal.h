@@ -188,6 +188,7 @@ struct MvoTrackFilter {
   int nmap, nk, method;
   int32_t *d_pairs, *d_info;
   const double *Tcw12, *K;       // optional projection (methods 1/2)
+  const double *d_Tcw12;         // ... with the pose in device memory instead (K, rows, cols as above)
   int rows, cols;
   const float *d_map_pts;
   const mvo_keypoint *d_kpts;    // optional: write the PnP input arrays (d_p3, d_p2) as well
@@ -219,7 +220,10 @@ struct MvoKfFetch {
 };
 int mvo_trk_keyframe_fetch(mvo_tracker *t, int slot, int want_rgb, int with_links, int n_counters, int ref_tag, int match_mode, MvoKfFetch *out);
 int mvo_trk_set_ref_desc(mvo_tracker *t, int slot, int tag);
-int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res);
+// ref_k: the reference keyframe whose pose T_guess is = the ref_k-th newest buffered frame counting the frame being tracked as 0
+// (-1: not in the buffer); allow_spec: the head of the NEXT prefetched frame's chain (match filter + PnP) may be enqueued ahead of time
+int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res, int ref_k,
+                  int allow_spec);
 
 void orb_state_free(mvo_ctx *ctx);   // orb_host.cpp
 void orb_tma_free(mvo_ctx *ctx);     // orb.cu

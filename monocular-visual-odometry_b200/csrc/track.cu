@@ -245,10 +245,11 @@ int mvo_track_match_filter(mvo_ctx *ctx, const MvoTrackFilter &f) {
   a.keys = f.d_keys; a.vis = f.d_vis; a.nmap = f.nmap; a.nk = f.nk; a.method = f.method; a.n_cap = cap;
   a.xg_ratio = ctx->prm.xiang_gao_ratio; a.lowe_ratio = ctx->prm.lowe_ratio;
   a.pairs = (int2 *)f.d_pairs; a.info = f.d_info;
-  a.project = f.Tcw12 != nullptr;
+  a.project = f.Tcw12 != nullptr || f.d_Tcw12 != nullptr;
   a.map_pts = f.d_map_pts;
+  a.d_Tcw = f.d_Tcw12;
   if (a.project) {
-    for (int q = 0; q < 12; ++q) a.Tcw.v[q] = f.Tcw12[q];
+    if (f.Tcw12) for (int q = 0; q < 12; ++q) a.Tcw.v[q] = f.Tcw12[q];
     a.fx = f.K[0]; a.fy = f.K[4]; a.cx = f.K[2]; a.cy = f.K[5];
     a.fcols = (float)f.cols; a.frows = (float)f.rows;
   }

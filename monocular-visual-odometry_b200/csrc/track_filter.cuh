@@ -47,6 +47,7 @@ struct FilterArgs {
   int project;
   const float *map_pts;
   Rt12 Tcw;
+  const double *d_Tcw;      // optional: the guess pose is read from device memory (a slot of the tracker's pose ring) instead of Tcw
   double fx, fy, cx, cy;
   float fcols, frows;
   // optional (p3 != nullptr): the 3d-2d pairs of poseEstimationPnP_ (vo.cpp:293-301) go straight into the PnP input arrays
@@ -196,7 +197,12 @@ __global__ void __launch_bounds__(MF_T, 1) k_match_filter(FilterArgs a) {
   // ---- thresholds (feature_match.cpp:179-196 for methods 1/3, :210-217 for method 2), ordered compaction ----
   const int per = (nmap + MF_T - 1) / MF_T, q0 = min(tid * per, nmap), q1 = min(q0 + per, nmap);
   if (a.project) {          // every thread reads back only the flags it wrote itself
-    for (int q = q0; q < q1; ++q) { float2 uv; a.vis[q] = project_point(a.map_pts, q, a.Tcw, a.fx, a.fy, a.cx, a.cy, a.fcols, a.frows, uv) ? 1 : 0; }
+    Rt12 Tcw = a.Tcw;
+    if (a.d_Tcw) {          // enqueued ahead of time: the reference keyframe's pose as the bundle adjustment of the previous frame left it
+#pragma unroll
+      for (int q = 0; q < 12; ++q) Tcw.v[q] = a.d_Tcw[q];
+    }
+    for (int q = q0; q < q1; ++q) { float2 uv; a.vis[q] = project_point(a.map_pts, q, Tcw, a.fx, a.fy, a.cx, a.cy, a.fcols, a.frows, uv) ? 1 : 0; }
   }
   int nvis = 0;
   if (a.method != 2) {

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <stdlib.h>
 #include <math.h>
@@ -40,7 +41,10 @@ struct TrackedFrame {
   int n_links = 0;
 };
 
-// One extraction in flight per slot; the worker thread runs them in submission order.
+// One extraction in flight per slot, each slot with its own worker thread, context and stream.
+// Extraction slots (contexts, streams, worker threads): the frame being added holds one while two prefetched frames are extracted.
+constexpr int MVO_XSLOTS = 3;
+
 struct ExtractJob {
   std::atomic<int> state{0};           // 0 free, 1 queued, 2 done
   const uint8_t *image = nullptr;
@@ -140,10 +144,11 @@ struct mvo_tracker {
   int32_t ba_gen = 0;
   std::vector<MatchPair> pairs;      // device-resident path
   // extraction worker
-  mvo_ctx *xctx[2] = {nullptr, nullptr};
-  ExtractJob job[2];
+  mvo_ctx *xctx[MVO_XSLOTS] = {nullptr, nullptr, nullptr};
+  ExtractJob job[MVO_XSLOTS];
+  bool held = false;                 // an acquired slot has not been released yet
   unsigned n_submit = 0, n_consume = 0, n_submit_total = 0;
-  std::thread worker;
+  std::thread worker[MVO_XSLOTS];    // one per extraction slot / context: prefetched frames are extracted side by side
   std::mutex mu;
   std::condition_variable cv_job, cv_done;
   bool stop = false;
@@ -156,7 +161,7 @@ struct mvo_tracker {
   int32_t *d_map_ids = nullptr, *d_vis_cnt = nullptr, *d_match_cnt = nullptr, *d_edge_kp = nullptr;
   float *d_pos_by_id = nullptr;  uint8_t *d_alive = nullptr;
   bool count_stats = false;            // accumulate visible / matched counts per map point on the device
-  uint8_t *d_keysvis[2] = {nullptr, nullptr};   // per extraction slot: [keys nmap*2 u32][vis nmap u8] — one D2H after the match
+  uint8_t *d_keysvis[MVO_XSLOTS] = {nullptr, nullptr, nullptr};   // per extraction slot: [keys nmap*2 u32][vis nmap u8] — one D2H after the match
   int map_version = 0;                 // bumped by set_map: keys matched ahead of time against an older map are redone
   float *d_cxy = nullptr, *d_kxy = nullptr;
   int32_t *d_pairs = nullptr, *d_edge_map = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
@@ -169,19 +174,26 @@ struct mvo_tracker {
   uint8_t *d_ref_desc = nullptr;
   int n_ref = 0, ref_tag = -1;
   bool ref_copy_pending = false;       // a device-to-device copy out of an extraction slot is in flight: synchronise before the slot is released
+  // Speculative head of the next frame's chain.  The match filter and the PnP kernels of frame i + 1 only read the map, the keys the
+  // extraction worker left and the reference keyframe's pose, and only write scratch buffers: when frame i + 1 has been prefetched,
+  // they are enqueued right behind frame i's bundle adjustment (guess pose read from the device-side pose ring), so the GPU works
+  // on them while the host waits for frame i's results, decides about a keyframe and comes back with frame i + 1.  If anything they
+  // depended on changed in between (a keyframe replaced the map, another reference keyframe, a declined filter) they are redone.
+  struct Spec { bool valid = false; unsigned serial = 0; int map_version = 0, ref_slot = -1, nmap = 0, nk = 0, method = 0, n_upper = 0; } spec;
+  std::vector<double> ring_host;       // host mirror of the pose ring (world->camera [R|t] per slot), refreshed with every frame's read-back
+  cudaEvent_t ev_result = nullptr;     // recorded behind the device-to-host copy of a frame's result block
+  uint64_t spec_hits = 0, spec_issued = 0;
 };
 
 namespace {
 
-void worker_main(mvo_tracker *t) {
+void worker_main(mvo_tracker *t, int slot) {
   for (;;) {
     ExtractJob *j = nullptr;
-    int slot = 0;
     {
       std::unique_lock<std::mutex> lk(t->mu);
-      t->cv_job.wait(lk, [&] { return t->stop || t->job[t->n_run & 1].state.load(std::memory_order_acquire) == 1; });
+      t->cv_job.wait(lk, [&] { return t->stop || t->job[slot].state.load(std::memory_order_acquire) == 1; });
       if (t->stop) return;
-      slot = t->n_run & 1;
       j = &t->job[slot];
     }
     mvo_ctx *x = t->xctx[slot];
@@ -227,7 +239,7 @@ void worker_main(mvo_tracker *t) {
     }
     j->rc = rc;
     j->nk = nk;
-    if (dbg_worker) {                    // how long the extraction chain of one frame takes on the worker (enqueue / until everything has run)
+    if (dbg_worker && slot == 0) {       // how long the extraction chain of one frame takes on a worker (enqueue / until everything has run)
       static double acc_enq = 0, acc_all = 0;
       static int n_w = 0;
       const double t_end = now_us();
@@ -254,7 +266,7 @@ void wait_job(mvo_tracker *t, int slot) {
 
 void drain_jobs(mvo_tracker *t) {
   while (t->n_consume != t->n_submit) {
-    const int slot = t->n_consume & 1;
+    const int slot = (int)(t->n_consume % MVO_XSLOTS);
     wait_job(t, slot);
     t->job[slot].state.store(0, std::memory_order_release);
     ++t->n_consume;
@@ -284,7 +296,7 @@ int dev_alloc(mvo_tracker *t) {
   if (ring_ok && map_ok && ids_ok && t->dev_nmap == nmap) return MVO_OK;
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   // frames extracted (and matched) ahead of time hold pointers into the map arrays: let them finish first
-  for (unsigned k = t->n_consume; k != t->n_submit; ++k) wait_job(t, (int)(k & 1));
+  for (unsigned k = t->n_consume; k != t->n_submit; ++k) wait_job(t, (int)(k % MVO_XSLOTS));
   MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (!ring_ok) {
     size_t o = 0;
@@ -309,6 +321,8 @@ int dev_alloc(mvo_tracker *t) {
     t->d_edge_kp = (int32_t *)(nd + o_ekp); t->d_cnt = (int32_t *)(nd + o_cnt); t->d_pose = (double *)(nd + o_pose);
     t->d_flags = (int32_t *)(nd + o_flags); t->d_res = (double *)(nd + o_res); t->d_stats = (double *)(nd + o_stats);
     t->d_ref_desc = nd + o_ref; t->n_ref = 0; t->ref_tag = -1;
+    t->ring_host.assign((size_t)ring * 12, 0.0);
+    t->spec.valid = false;
   }
   if (!map_ok) {
     int mcap = std::max(t->dev_mcap, 1024);
@@ -316,8 +330,8 @@ int dev_alloc(mvo_tracker *t) {
     size_t o = 0;
     const size_t o_pts = o;   o = al256(o + (size_t)mcap * 12);
     const size_t o_desc = o;  o = al256(o + (size_t)mcap * 32);
-    const size_t o_kv = o;    o = al256(o + (size_t)mcap * 9);
-    const size_t o_kv2 = o;   o = al256(o + (size_t)mcap * 9);
+    size_t o_kv[MVO_XSLOTS];
+    for (int k = 0; k < MVO_XSLOTS; ++k) { o_kv[k] = o; o = al256(o + (size_t)mcap * 9); }
     const size_t o_cxy = o;   o = al256(o + (size_t)mcap * 8);
     const size_t o_pairs = o; o = al256(o + (size_t)mcap * 8);
     const size_t o_ids = o;   o = al256(o + (size_t)mcap * 4);
@@ -329,7 +343,8 @@ int dev_alloc(mvo_tracker *t) {
     MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (t->dev_map) cudaFree(t->dev_map);
     t->dev_map = nd; t->dev_mcap = mcap;
-    t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc; t->d_keysvis[0] = nd + o_kv; t->d_keysvis[1] = nd + o_kv2;
+    t->d_map_pts = (float *)(nd + o_pts); t->d_map_desc = nd + o_desc;
+    for (int k = 0; k < MVO_XSLOTS; ++k) t->d_keysvis[k] = nd + o_kv[k];
     t->d_cxy = (float *)(nd + o_cxy); t->d_pairs = (int32_t *)(nd + o_pairs); t->d_map_ids = (int32_t *)(nd + o_ids);
     t->d_vis_cnt = (int32_t *)(nd + o_vc); t->d_match_cnt = (int32_t *)(nd + o_mc);
     const size_t hb = al256((size_t)mcap * 9) + al256((size_t)mcap * 8 + 64) + al256((size_t)4096 * 96) + 1024;
@@ -470,8 +485,9 @@ extern "C" int mvo_test_match_filter_dev(mvo_ctx *ctx, const uint32_t *keys, con
 static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels, size_t stride, int image_on_device) {
   mvo_ctx *ctx = t->ctx;
   if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null image");
-  if (t->n_submit - t->n_consume >= 2) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: two frames are already in flight");
-  const int slot = t->n_submit & 1;
+  if ((int)(t->n_submit - t->n_consume) + (t->held ? 1 : 0) >= MVO_XSLOTS)
+    return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: %d frames are already in flight", (int)(t->n_submit - t->n_consume));
+  const int slot = (int)(t->n_submit % MVO_XSLOTS);
   ExtractJob &j = t->job[slot];
   mvo_ctx *x = t->xctx[slot];
   MVO_TRY(mvo_set_params(x, &ctx->prm));          // follow parameter changes made on the main context
@@ -492,7 +508,7 @@ static int submit_extraction(mvo_tracker *t, const uint8_t *image, int channels,
     std::lock_guard<std::mutex> lk(t->mu);
     j.state.store(1, std::memory_order_release);
   }
-  t->cv_job.notify_one();
+  t->cv_job.notify_all();
   ++t->n_submit;
   ++t->n_submit_total;
   return MVO_OK;
@@ -507,7 +523,7 @@ static void finish_frame(mvo_tracker *t, bool pnp_ok, double *T_w_c_out) {
   memcpy(T_w_c_out, t->frames.back().T_w_c, 16 * sizeof(double));
 }
 
-static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res);
+static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res, int ref_k = -1, int allow_spec = 0);
 static int track_host_arrays(mvo_tracker *t, ExtractJob &job, double *T_w_c_out, mvo_track_result *res);
 
 extern "C" {
@@ -548,30 +564,31 @@ int mvo_tracker_create(mvo_ctx *ctx, const double *K, int rows, int cols, const 
   }
   memset(t->T_ref, 0, sizeof t->T_ref);
   t->T_ref[0] = t->T_ref[5] = t->T_ref[10] = t->T_ref[15] = 1;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < MVO_XSLOTS; ++k) {
     const int rc = mvo_create(&t->xctx[k], ctx->device, &ctx->prm);
     if (rc != MVO_OK) {
       mvo_tracker_destroy(t);
       return mvo_fail(ctx, rc, "tracker: cannot create the extraction context");
     }
   }
-  t->worker = std::thread(worker_main, t);
+  for (int k = 0; k < MVO_XSLOTS; ++k) t->worker[k] = std::thread(worker_main, t, k);
   *out = t;
   return MVO_OK;
 }
 
 void mvo_tracker_destroy(mvo_tracker *t) {
   if (!t) return;
-  if (t->worker.joinable()) {
+  if (t->worker[0].joinable()) {
     drain_jobs(t);
     {
       std::lock_guard<std::mutex> lk(t->mu);
       t->stop = true;
     }
     t->cv_job.notify_all();
-    t->worker.join();
+    for (int k = 0; k < MVO_XSLOTS; ++k)
+      if (t->worker[k].joinable()) t->worker[k].join();
   }
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < MVO_XSLOTS; ++k)
     if (t->xctx[k]) mvo_destroy(t->xctx[k]);
   if (t->dev || t->dev_map || t->dev_ids) {
     cudaSetDevice(t->ctx->device);
@@ -606,6 +623,7 @@ int mvo_tracker_reset(mvo_tracker *t, const double *T_w_c_ref) {
   t->has_prev = false;
   t->frame_counter = 0;
   t->fused_holdoff = 0;
+  t->spec.valid = false;
   drain_jobs(t);                    // drop frames that were prefetched but never tracked
   t->n_submit = t->n_consume = 0;
   {
@@ -619,7 +637,7 @@ int mvo_tracker_timing_enable(mvo_tracker *t, uint32_t mask) {
   if (!t) return MVO_ERR_INVALID_ARG;
   if (t->n_submit != t->n_consume) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: timing calls need an idle tracker (frames are in flight)");
   MVO_TRY(mvo_timing_enable(t->ctx, mask));
-  for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_enable(t->xctx[k], mask));
+  for (int k = 0; k < MVO_XSLOTS; ++k) MVO_TRY(mvo_timing_enable(t->xctx[k], mask));
   return MVO_OK;
 }
 
@@ -627,13 +645,15 @@ int mvo_tracker_timing_read(mvo_tracker *t, double *ms, uint64_t *counts) {
   if (!t) return MVO_ERR_INVALID_ARG;
   if (t->n_submit != t->n_consume) return mvo_fail(t->ctx, MVO_ERR_INVALID_ARG, "tracker: timing calls need an idle tracker (frames are in flight)");
   MVO_TRY(mvo_timing_read(t->ctx, ms, counts));
-  for (int k = 0; k < 2; ++k) MVO_TRY(mvo_timing_read(t->xctx[k], ms, counts));
+  for (int k = 0; k < MVO_XSLOTS; ++k) MVO_TRY(mvo_timing_read(t->xctx[k], ms, counts));
   return MVO_OK;
 }
 
 uint64_t mvo_tracker_kernel_launches(const mvo_tracker *t) {
   if (!t) return 0;
-  return mvo_kernel_launches(t->ctx) + mvo_kernel_launches(t->xctx[0]) + mvo_kernel_launches(t->xctx[1]);
+  uint64_t n = mvo_kernel_launches(t->ctx);
+  for (int k = 0; k < MVO_XSLOTS; ++k) n += mvo_kernel_launches(t->xctx[k]);
+  return n;
 }
 
 int mvo_tracker_frame_pose(const mvo_tracker *t, int k, double *T_w_c) {
@@ -665,10 +685,10 @@ int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t s
   mvo_ctx *ctx = t->ctx;
   if (!image) return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: null pointer");
   // take the frame from the prefetch queue, or extract it now
-  if (t->n_submit != t->n_consume && t->job[t->n_consume & 1].image != image)
+  if (t->n_submit != t->n_consume && t->job[t->n_consume % MVO_XSLOTS].image != image)
     return mvo_fail(ctx, MVO_ERR_INVALID_ARG, "tracker: frames must be tracked in the order they were prefetched");
   if (t->n_submit == t->n_consume) MVO_TRY(submit_extraction(t, image, channels, stride, image_on_device));
-  const int slot = t->n_consume & 1;
+  const int slot = (int)(t->n_consume % MVO_XSLOTS);
   ExtractJob &job = t->job[slot];
   if (!job.want_host) {
     // the device copy of the map is refreshed while the extraction runs
@@ -692,6 +712,7 @@ int mvo_trk_acquire(mvo_tracker *t, const uint8_t *image, int channels, size_t s
   }
   *slot_out = slot;
   if (nk_out) *nk_out = job.nk;
+  t->held = true;
   return MVO_OK;
 }
 
@@ -702,6 +723,7 @@ void mvo_trk_release(mvo_tracker *t, int slot) {
     t->ref_copy_pending = false;
   }
   t->job[slot].state.store(0, std::memory_order_release);
+  t->held = false;
 }
 
 // The acquired frame becomes the reference keyframe: its descriptors are kept on the device (asynchronous device-to-device
@@ -871,6 +893,7 @@ int mvo_trk_set_map_ids(mvo_tracker *t, const float *pts3d, const uint8_t *desc,
   }
   t->dev_nmap = -1;                 // the device copy is refreshed by the next frame
   ++t->map_version;
+  t->spec.valid = false;
   return MVO_OK;
 }
 
@@ -891,6 +914,8 @@ int mvo_trk_push_frame(mvo_tracker *t, const double *T_w_c, const int32_t *ids, 
   const size_t o = (size_t)cur.slot * t->dev_cap;
   MVO_CUDA(ctx, cudaSetDevice(ctx->device));
   MVO_CUDA(ctx, cudaMemcpyAsync(t->d_pose + (size_t)cur.slot * 12, P, sizeof P, cudaMemcpyHostToDevice, ctx->stream));
+  if (t->ring_host.size() >= ((size_t)cur.slot + 1) * 12) memcpy(&t->ring_host[(size_t)cur.slot * 12], P, sizeof P);
+  t->spec.valid = false;
   MVO_CUDA(ctx, cudaMemcpyAsync(t->d_cnt + cur.slot, &n, 4, cudaMemcpyHostToDevice, ctx->stream));
   if (n > 0) {
     MVO_CUDA(ctx, cudaMemcpyAsync(t->d_edge_map + o, ids, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -959,13 +984,14 @@ int mvo_trk_counters(mvo_tracker *t, int32_t *visible, int32_t *matched, int n) 
 }
 
 // the tracking step of an acquired frame with the caller's guess (reference keyframe) and previous-frame poses
-int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res) {
+int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double *T_prev, double *T_w_c_out, mvo_track_result *res, int ref_k,
+                  int allow_spec) {
   ExtractJob &job = t->job[slot];
   if (job.want_host) return mvo_fail(t->ctx, MVO_ERR_UNSUPPORTED, "tracker: the frame was extracted for the host-array path");
   memcpy(t->T_ref, T_guess, sizeof t->T_ref);
   t->has_prev = T_prev != nullptr;
   if (T_prev) memcpy(t->T_prev, T_prev, sizeof t->T_prev);
-  return track_device(t, job, slot, T_w_c_out, res);
+  return track_device(t, job, slot, T_w_c_out, res, ref_k, allow_spec);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -975,8 +1001,12 @@ int mvo_trk_track(mvo_tracker *t, int slot, const double *T_guess, const double 
 //   int32 [0] BA skip flag   [8..10] model found, pnp_ok, inliers   [16..33] BA graph: frames, edges, slot of frame f
 //         [40..48] match filter: pairs, candidates, status, -, phase cycle counters
 //   +256: world->camera pose of the frame before BA (12 doubles)      +512: BA statistics (16 doubles)
-static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res) {
+static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c_out, mvo_track_result *res, int ref_k, int allow_spec) {
   mvo_ctx *ctx = t->ctx;
+  static const bool spec_off = getenv("MVO_TRACK_SPEC") != nullptr && atoi(getenv("MVO_TRACK_SPEC")) == 0;      // A/B hook
+  // ring slot of the reference keyframe (the frame whose pose is the initial guess), looked up before this frame enters the buffer
+  int ref_slot = -1;
+  if (ref_k >= 1 && ref_k <= (int)t->frames.size()) ref_slot = t->frames[t->frames.size() - (size_t)ref_k].slot;
   mvo_track_result r;
   memset(&r, 0, sizeof r);
   static const bool dbg = getenv("MVO_TRACK_DEBUG") != nullptr;
@@ -1013,6 +1043,15 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   int rc = MVO_OK;
   double Tcw[12];
   Twc_to_Rt12(cur.T_w_c, Tcw);
+  // When the guess is the pose of a buffered frame, its world->camera form is taken from the pose ring as it is (host mirror here,
+  // device memory for a chain head enqueued ahead of time: the same twelve doubles) instead of inverting the inverse again.
+  if (ref_slot >= 0 && t->ring_host.size() >= ((size_t)ref_slot + 1) * 12) {
+    const double *rp = &t->ring_host[(size_t)ref_slot * 12];
+    double dmax = 0;
+    for (int q = 0; q < 12; ++q) dmax = std::max(dmax, fabs(rp[q] - Tcw[q]));
+    if (dmax < 1e-9) memcpy(Tcw, rp, sizeof Tcw);
+    else ref_slot = -1;                      // the caller's guess is not that frame's pose: no ring pose, no speculation
+  } else ref_slot = -1;
   // methods 1/2: the matcher does not need the projections, so the in-view test is folded into the filter kernel
   // (the keys of points outside the view are simply ignored there); method 3 gates on the projected pixel
   const bool project_in_filter = method != 3 && !force_host_filter && t->fused_holdoff == 0;
@@ -1035,6 +1074,8 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   // d_n != nullptr: the pair count lives on the device (n = its upper bound); otherwise n pairs are in d_pairs
   MvoPoseStore st;
   bool counted = false;            // visible_times_ / matched_times_ are accumulated by the first tail only
+  bool pnp_enqueued = false;       // the PnP kernels of this frame were enqueued ahead of time (speculative chain head)
+  std::function<int()> speculate;  // set by the fused path: enqueues the next frame's chain head behind this frame's result copy
   auto enqueue_tail = [&](int n, const int32_t *d_n, bool gathered) -> int {
     MvoTrackGlue g;
     memset(&g, 0, sizeof g);
@@ -1059,7 +1100,8 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
       int32_t *d_out_i, *d_inl;
       rc2 = mvo_pnp_dev_buffers(ctx, n, &d_p3, &d_p2, &d_pose_io, &d_out_i, &d_inl);
       if (rc2 == MVO_OK && !gathered) rc2 = mvo_track_gather_pairs(ctx, t->d_pairs, n, d_n, t->d_map_pts, job.d_k, d_p3, d_p2);
-      if (rc2 == MVO_OK) rc2 = mvo_pnp_dev_run(ctx, n, t->K, d_n);
+      if (rc2 == MVO_OK && !pnp_enqueued) rc2 = mvo_pnp_dev_run(ctx, n, t->K, d_n);
+      pnp_enqueued = false;
       g.pose_io = d_pose_io; g.out_i = d_out_i; g.inl = d_inl;
     }
     if (rc2 == MVO_OK) rc2 = mvo_track_glue(ctx, g);
@@ -1085,7 +1127,10 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
     // one D2H: the result block + the pose ring
     MVO_CUDA(ctx, cudaMemcpyAsync(h_out, t->d_flags, 768, cudaMemcpyDeviceToHost, ctx->stream));
     MVO_CUDA(ctx, cudaMemcpyAsync(h_out + 768, t->d_pose, (size_t)t->dev_ring * 96, cudaMemcpyDeviceToHost, ctx->stream));
-    MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!t->ev_result) MVO_CUDA(ctx, cudaEventCreateWithFlags(&t->ev_result, cudaEventDisableTiming));
+    MVO_CUDA(ctx, cudaEventRecord(t->ev_result, ctx->stream));
+    if (speculate) { const int rcs = speculate(); if (rcs != MVO_OK) return rcs; }       // the next frame's chain head, behind this frame's results
+    MVO_CUDA(ctx, cudaEventSynchronize(t->ev_result));
     return MVO_OK;
   };
 
@@ -1117,26 +1162,68 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   // do that on every frame, so after a decline the next frames go straight to the host filter.
   bool fused = nmap > 0 && !force_host_filter && t->fused_holdoff == 0;
   if (t->fused_holdoff > 0) --t->fused_holdoff;
-  if (fused) {
-    const int n_upper = std::min(nmap, std::max(nk, 0));
+  // the head of a frame's chain: match filter (in-view test, thresholds, duplicate removal, PnP input arrays) + the PnP kernels;
+  // side-effect free apart from scratch buffers.  Tcw_host / d_Tcw: the guess pose as a kernel argument or in device memory.
+  auto enqueue_head = [&](const ExtractJob &jb, int jslot, const double *Tcw_host, const double *d_Tcw, int *n_upper_out) -> int {
+    uint8_t *kv = t->d_keysvis[jslot];
+    const int n_up = std::min(nmap, std::max(jb.nk, 0));
     MvoTrackFilter f;
     memset(&f, 0, sizeof f);
-    f.d_keys = d_keys; f.d_vis = d_vis; f.nmap = nmap; f.nk = nk; f.method = method;
+    f.d_keys = (uint32_t *)kv; f.d_vis = kv + (size_t)std::max(nmap, 1) * 8; f.nmap = nmap; f.nk = jb.nk; f.method = method;
     f.d_pairs = t->d_pairs; f.d_info = d_finfo;
-    if (project_in_filter) { f.Tcw12 = Tcw; f.K = t->K; f.rows = t->rows; f.cols = t->cols; }
+    if (Tcw_host || d_Tcw) { f.Tcw12 = Tcw_host; f.d_Tcw12 = d_Tcw; f.K = t->K; f.rows = t->rows; f.cols = t->cols; }
     f.d_map_pts = t->d_map_pts;
-    if (n_upper >= 4) {          // the filter writes the PnP input arrays itself
+    int rch = MVO_OK;
+    if (n_up >= 4) {             // the filter writes the PnP input arrays itself
       double *d_pose_io;
       int32_t *d_out_i, *d_inl;
-      rc = mvo_pnp_dev_buffers(ctx, n_upper, &f.d_p3, &f.d_p2, &d_pose_io, &d_out_i, &d_inl);
-      f.d_kpts = job.d_k;
+      rch = mvo_pnp_dev_buffers(ctx, n_up, &f.d_p3, &f.d_p2, &d_pose_io, &d_out_i, &d_inl);
+      f.d_kpts = jb.d_k;
     }
-    if (rc == MVO_OK) rc = mvo_track_match_filter(ctx, f);
+    if (rch == MVO_OK) rch = mvo_track_match_filter(ctx, f);
+    *n_upper_out = n_up;
+    return rch;
+  };
+  if (fused) {
+    int n_upper = 0;
+    const bool spec_ok = t->spec.valid && t->spec.serial == job.serial && t->spec.map_version == t->map_version && ref_slot >= 0 &&
+                         t->spec.ref_slot == ref_slot && t->spec.nmap == nmap && t->spec.nk == nk && t->spec.method == method && prematched &&
+                         project_in_filter && can_match;
+    t->spec.valid = false;
+    if (spec_ok) {               // the filter and the PnP kernels of this frame are already in the stream (or done)
+      n_upper = t->spec.n_upper;
+      pnp_enqueued = n_upper >= 4;
+      ++t->spec_hits;
+    } else {
+      rc = enqueue_head(job, slot, project_in_filter ? Tcw : nullptr, nullptr, &n_upper);
+    }
+    // next frame: its extraction and pre-match run on the worker while this frame is tracked; once they are done its chain head
+    // goes into the stream behind this frame's results, with the reference pose read from the ring slot this frame's BA may move
+    if (allow_spec && !spec_off && ref_slot >= 0 && project_in_filter && can_match && prematched && t->n_submit != t->n_consume && rc == MVO_OK) {
+      speculate = [&, ref_slot]() -> int {
+        const int ns = (int)(t->n_consume % MVO_XSLOTS);
+        ExtractJob &nj = t->job[ns];
+        if (nj.want_host) return MVO_OK;
+        wait_job(t, ns);
+        const int mode = method == 1 ? 0 : 1;
+        if (nj.rc != MVO_OK || !nj.matched || nj.map_version != t->map_version || nj.match_mode != mode || nj.nk <= 0 || (method == 2 && nj.nk < 2))
+          return MVO_OK;
+        int n_up = 0;
+        int rcs = enqueue_head(nj, ns, nullptr, t->d_pose + (size_t)ref_slot * 12, &n_up);
+        if (rcs == MVO_OK && n_up >= 4) rcs = mvo_pnp_dev_run(ctx, n_up, t->K, d_finfo);
+        if (rcs != MVO_OK) return rcs;
+        t->spec.valid = true; t->spec.serial = nj.serial; t->spec.map_version = t->map_version; t->spec.ref_slot = ref_slot;
+        t->spec.nmap = nmap; t->spec.nk = nj.nk; t->spec.method = method; t->spec.n_upper = n_up;
+        ++t->spec_issued;
+        return MVO_OK;
+      };
+    }
     if (rc == MVO_OK) rc = enqueue_tail(n_upper, d_finfo, true);
-    if (rc != MVO_OK) return fail(rc);
+    speculate = nullptr;
+    if (rc != MVO_OK) { t->spec.valid = false; return fail(rc); }
     TMARK(0);
     // the device filter declined: redo the tail through the host (its first pass saw zero pairs: only the in-view counts were taken)
-    if (h_flags[42] != 0) { fused = false; counted = true; t->fused_holdoff = 64; }
+    if (h_flags[42] != 0) { fused = false; counted = true; t->fused_holdoff = 64; t->spec.valid = false; }
   }
   if (!fused) {
     rc = host_filter_tail();
@@ -1147,6 +1234,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   const int32_t *h_res_i = h_flags + 8, *h_info = h_flags + 16;
   const double *h_res_d = (const double *)(h_out + 256), *h_stats = (const double *)(h_out + 512);
   const double *h_ring = (const double *)(h_out + 768);
+  if (t->ring_host.size() >= (size_t)t->dev_ring * 12) memcpy(t->ring_host.data(), h_ring, (size_t)t->dev_ring * 96);
   r.n_matches = h_flags[40];
   r.n_candidates = h_flags[41];
   const bool pnp_ok = h_res_i[1] != 0;
@@ -1175,6 +1263,7 @@ static int track_device(mvo_tracker *t, ExtractJob &job, int slot, double *T_w_c
   if (dbg && ++nacc % 50 == 0) {
     fprintf(stderr, "tracker(device) us/frame: fused frame (launch .. sync) %.1f host-filter redo %.1f finish %.1f | filter kernel cycles: prologue %d sort %d (%d levels, %d segments heapsorted, longest %d) epilogue %d\n",
             acc[0] / 50, acc[1] / 50, acc[2] / 50, h_flags[44], h_flags[45], h_flags[48], h_flags[43], h_flags[47], h_flags[46]);
+    fprintf(stderr, "  chain heads enqueued ahead of time: %llu issued, %llu used\n", (unsigned long long)t->spec_issued, (unsigned long long)t->spec_hits);
     fprintf(stderr, "  per level (cycles, nbig*1000+nsmall):");
     for (int l = 0; l < 7; ++l) fprintf(stderr, " %d/%d", h_flags[49 + 2 * l], h_flags[50 + 2 * l]);
     fprintf(stderr, "\n");

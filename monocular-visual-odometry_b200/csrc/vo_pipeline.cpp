@@ -897,7 +897,19 @@ int mvo_vo_add_frame_ex(mvo_vo *v, const uint8_t *image, int channels, size_t st
   } else if (v->state == VO_DOING_TRACKING && v->dev) {          // :70-125 through the device-resident tracker
     frame->conn_ready = false;
     mvo_track_result r;
-    rc = mvo_trk_track(v->trk, slot, v->ref->T_w_c, v->prev->T_w_c, frame->T_w_c, &r);
+    // where the reference keyframe sits in the frame buffer (this frame = 0), and whether this frame is likely to become a keyframe
+    // (then the tracker does not enqueue the next frame's chain head ahead of time: the keyframe would invalidate it)
+    int ref_k = -1;
+    for (int k = 1; k < (int)v->buff.size(); ++k)
+      if (v->buff[v->buff.size() - 1 - (size_t)k] == v->ref) { ref_k = k; break; }
+    int allow_spec = 0;
+    {
+      auto dist = [](const double *A, const double *B) { const double dx = A[3] - B[3], dy = A[7] - B[7], dz = A[11] - B[11]; return sqrt(dx * dx + dy * dy + dz * dz); };
+      const double d_prev = dist(v->prev->T_w_c, v->ref->T_w_c);
+      const double step = v->buff.size() >= 3 ? dist(v->prev->T_w_c, v->buff[v->buff.size() - 3]->T_w_c) : 0.0;
+      allow_spec = d_prev + 1.1 * step < v->prm.track.min_dist_keyframe;
+    }
+    rc = mvo_trk_track(v->trk, slot, v->ref->T_w_c, v->prev->T_w_c, frame->T_w_c, &r, ref_k, allow_spec);
     if (rc != MVO_OK) {                                          // the tracker has dropped the frame again: so do we
       v->buff.pop_back();
       v->curr = v->prev;
@@ -950,10 +962,13 @@ int mvo_vo_run_sequence(mvo_vo *v, const uint8_t *const *images, int n_frames, i
   if (n_frames < 0 || (n_frames > 0 && (!images || !T_w_c_out))) return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: bad sequence arguments");
   for (int i = 0; i < n_frames; ++i)
     if (!images[i]) return mvo_fail(v->ctx, MVO_ERR_INVALID_ARG, "vo: image %d is null", i);
-  if (n_frames > 0) MVO_TRY(mvo_vo_prefetch(v, images[0], channels, stride, images_on_device));
+  // two frames of look-ahead when the device-resident tracker extracts them (its extraction contexts work side by side): frame i
+  // is added while frames i + 1 and i + 2 are in flight (three extraction slots: one held by the frame being added)
+  const int ahead = v->dev ? 2 : 1;
+  for (int k = 0; k <= ahead && k < n_frames; ++k) MVO_TRY(mvo_vo_prefetch(v, images[k], channels, stride, images_on_device));
   for (int i = 0; i < n_frames; ++i) {
-    if (i + 1 < n_frames) MVO_TRY(mvo_vo_prefetch(v, images[i + 1], channels, stride, images_on_device));
     MVO_TRY(mvo_vo_add_frame_ex(v, images[i], channels, stride, images_on_device, T_w_c_out + 16 * (size_t)i, infos ? infos + i : nullptr));
+    if (i + ahead + 1 < n_frames) MVO_TRY(mvo_vo_prefetch(v, images[i + ahead + 1], channels, stride, images_on_device));
     if (n_done) *n_done = i + 1;
   }
   return MVO_OK;
