@@ -271,7 +271,19 @@ def run_gpu(args, rank, world, local_rank):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner off stdout: one JSON line there
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on the C-level stdout when the communicator is created (NCCL_DEBUG=VERSION/INFO in the
+        # environment): file descriptor 1 points at stderr until the first collective has run, so that stdout carries one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     stream = torch.cuda.Stream()       # non-blocking: no implicit coupling with the legacy default stream
     ctx = mvo_b200.Context(local_rank, max_keypoints=MAX_KPTS, ba_iterations=BA_ITERS)
     ctx.set_stream(stream.cuda_stream)
