@@ -1300,7 +1300,43 @@ k_harris_all(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint32_t
   }
 }
 
+// test hook: the keep flags of the first-come grid selection for a given cell list, by either formulation
+__global__ void __launch_bounds__(1024)
+k_test_grid_rank(const uint16_t *__restrict__ cells, int n, int ncell, int max_per_cell, int seg, uint8_t *__restrict__ keep_out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int npad = (n + 63) & ~63;
+  uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem);
+  uint8_t *s_keep = reinterpret_cast<uint8_t *>(s_cell + npad);
+  uint32_t *s_min = reinterpret_cast<uint32_t *>(s_keep + npad);
+  uint8_t *s_tab = reinterpret_cast<uint8_t *>(s_min + 2 * ncell + 4);
+  for (int i = threadIdx.x; i < n; i += 1024) s_cell[i] = cells[i];
+  __syncthreads();
+  if (seg) grid_rank_keep_seg(n, s_cell, s_keep, s_tab, ncell, max_per_cell);
+  else grid_rank_keep(n, s_cell, s_keep, s_min, ncell, max_per_cell);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) keep_out[i] = s_keep[i];
+}
+
 }  // namespace
+
+// test hook (not part of mvo.h): cells[i] < ncell, n <= 16384; seg = 1: grid_rank_keep_seg, 0: grid_rank_keep (rounds)
+extern "C" int mvo_test_grid_rank(mvo_ctx *ctx, const uint16_t *cells, int n, int ncell, int max_per_cell, int seg, uint8_t *keep) {
+  if (!ctx || !cells || !keep || n < 1 || n > 16384 || ncell < 1 || ncell > 4096 || max_per_cell < 0) return MVO_ERR_INVALID_ARG;
+  if (seg && max_per_cell > 254) return mvo_fail(ctx, MVO_ERR_UNSUPPORTED, "grid_rank_keep_seg: per-cell limit above the byte counters");
+  MVO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int npad = (n + 63) & ~63;
+  const size_t smem = (size_t)npad * 3 + (size_t)(2 * ncell + 4) * 4 + (size_t)32 * ncell + 256;
+  MVO_TRY(mvo_reserve(ctx, ctx->d_c, (size_t)npad * 3 + 256));
+  uint16_t *dc = (uint16_t *)ctx->d_c.p;
+  uint8_t *dk = (uint8_t *)ctx->d_c.p + (size_t)npad * 2;
+  MVO_CUDA(ctx, cudaMemcpyAsync(dc, cells, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->stream));
+  MVO_CUDA(ctx, cudaFuncSetAttribute(k_test_grid_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_test_grid_rank<<<1, 1024, smem, ctx->stream>>>(dc, n, ncell, max_per_cell, seg, dk);
+  MVO_CHECK_LAUNCH(ctx);
+  MVO_CUDA(ctx, cudaMemcpyAsync(keep, dk, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  MVO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MVO_OK;
+}
 
 // ------------------------------------------------------------------------------ launchers
 static bool g_gauss_uploaded[64] = {false};

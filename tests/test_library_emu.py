@@ -168,3 +168,10 @@ def test_emulated_estimate_relative_poses(lib, ctx, planar):
         finally:
             prm.eh_ratio_threshold = 0.5
             assert lib.mvo_set_params(ctx, C.byref(prm)) == 0
+
+
+def test_emulated_grid_selection_formulations(lib, ctx):
+    """The per-cell counter of selectUniformKptsByGrid in its two device formulations (csrc/orb.cu: grid_rank_keep_seg /
+    grid_rank_keep) against the sequential rule, executed on the CPU tier (cases of tests/test_orb_gpu.py)."""
+    from test_orb_gpu import check_grid_rank
+    check_grid_rank(lib, ctx)

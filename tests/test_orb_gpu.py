@@ -126,3 +126,49 @@ def test_errors(ctx):
     kp["x"], kp["y"], kp["octave"] = 5, 5, 0
     with pytest.raises(mvo_b200.MvoError):
         ctx.calc_descriptors(mvo_synth.rect_scene(0), kp)           # inside the border band
+
+
+def _grid_keep_reference(cells, max_per_cell):
+    """feature_match.cpp:68-81 without the total cut: an item is kept iff fewer than max_per_cell earlier items fell into its cell."""
+    cnt, keep = {}, np.zeros(len(cells), np.uint8)
+    for i, c in enumerate(cells.tolist()):
+        k = cnt.get(c, 0)
+        keep[i] = k < max_per_cell
+        cnt[c] = k + 1
+    return keep
+
+
+def grid_rank_cases():
+    rng = np.random.default_rng(7)
+    yield rng.integers(0, 1200, 8000).astype(np.uint16), 1200, 8            # the shipped shape: 40 x 30 cells, 8 per cell
+    yield rng.integers(0, 1200, 7999).astype(np.uint16), 1200, 1
+    crowd = rng.integers(0, 1200, 9000).astype(np.uint16)
+    crowd[rng.random(9000) < 0.7] = 17                                      # one cell with thousands of items: the byte counters saturate
+    yield crowd, 1200, 254
+    yield crowd[:4097], 1200, 8
+    for n in (1, 31, 32, 33, 1025):
+        yield rng.integers(0, 5, n).astype(np.uint16), 5, 3
+    yield np.zeros(300, np.uint16), 1, 0                                     # nothing may be kept
+
+
+def check_grid_rank(lib, ctx):
+    import ctypes as C
+    lib.mvo_test_grid_rank.restype = C.c_int
+    lib.mvo_test_grid_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    for cells, ncell, mpc in grid_rank_cases():
+        ref = _grid_keep_reference(cells, mpc)
+        for seg in (1, 0):
+            keep = np.full(len(cells), 7, np.uint8)
+            assert lib.mvo_test_grid_rank(ctx, cells.ctypes.data, len(cells), ncell, mpc, seg, keep.ctypes.data) == 0
+            assert np.array_equal(keep, ref), (len(cells), ncell, mpc, seg, int(np.count_nonzero(keep != ref)))
+
+
+def test_grid_selection_formulations_equal_the_sequential_rule():
+    """selectUniformKptsByGrid's per-cell counter (feature_match.cpp:68-81) as evaluated by k_select / k_select_kept: the two-pass
+    form over per-warp cell tables (__match_any_sync) and the round form, against the sequential rule, incl. saturating cells."""
+    import mvo_b200
+    ctx = mvo_b200.Context(0)
+    try:
+        check_grid_rank(mvo_b200.load_library(), ctx.h)
+    finally:
+        ctx.close()

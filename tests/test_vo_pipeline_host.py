@@ -204,7 +204,7 @@ def test_my_slam_visual_odometry_adapter(hostcheck, tmp_path):
 def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
     import mvo_b200
     from oracle import vo_pipeline_oracle as vp
-    oracle = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=max_kpts, ba_iterations=ba_iterations, **vo_cfg)
+    oracle = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=max_kpts, ba_iterations=ba_iterations, **{k: v for k, v in vo_cfg.items() if not k.startswith("_")})
     helper = vp.CpuVo(K, ROWS, COLS, max_number_of_keypoints=max_kpts)
     stages = Stages(helper, ba_iterations)
     hostcheck.hostcheck_set_stages(C.cast(stages.table, C.c_void_p))
@@ -233,6 +233,22 @@ def _run_both(hostcheck, frames, max_kpts, ba_iterations, **vo_cfg):
         assert hostcheck.mvo_vo_get_map(h, ids.ctypes.data, pts.ctypes.data, None, None, len(ids), C.byref(n)) == 0
         final = (ids[: n.value].copy(), pts[: n.value].copy(), hostcheck.mvo_vo_num_keyframes(h),
                  np.stack([_pose(hostcheck, h, k) for k in range(min(len(frames), 20))]))
+        if vo_cfg.get("_check_run_sequence"):
+            # mvo_vo_run_sequence (run_vo.cpp's main loop as one call) on a fresh instance = the calls above, frame by frame
+            h2 = C.c_void_p()
+            assert hostcheck.mvo_vo_create(ctx, Kc.ctypes.data, ROWS, COLS, C.byref(p), C.byref(h2)) == 0
+            try:
+                imgs = [np.ascontiguousarray(mvo_synth.gray_to_bgr(f)) for f in frames]
+                ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+                Ts, infos, done = np.zeros((len(imgs), 16)), (mvo_b200.VoFrameInfo * len(imgs))(), C.c_int(0)
+                hostcheck.mvo_vo_run_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                assert hostcheck.mvo_vo_run_sequence(h2, ptrs, len(imgs), 3, imgs[0].shape[1] * 3, 0, Ts.ctypes.data, infos, C.byref(done)) == 0
+                assert done.value == len(imgs)
+                for i, (_, _, T_p, info_p) in enumerate(rows):
+                    assert np.array_equal(Ts[i].reshape(4, 4), T_p), i
+                    assert (infos[i].state_out, infos[i].keyframe, infos[i].map_points, infos[i].n_inliers) == (info_p.state_out, info_p.keyframe, info_p.map_points, info_p.n_inliers), i
+            finally:
+                hostcheck.mvo_vo_destroy(h2)
     finally:
         hostcheck.mvo_vo_destroy(h)
         hostcheck.hostcheck_ctx_free(ctx)
@@ -338,7 +354,7 @@ def test_state_machine_through_blank_and_far_away_frames(hostcheck):
     far = truth[12].copy()
     far[:3, 3] += np.array([1.2, 0.0, 2.6])       # 2.9 m = 0.48 in the units of the normalised map (threshold 0.3)
     seq = frames[:3] + [blank] + frames[3:10] + [blank] + frames[10:12] + [mvo_synth.render_room(far, planes)] + frames[12:]
-    oracle, rows, (ids, pts, n_kf, _) = _run_both(hostcheck, seq, 2000, 10)
+    oracle, rows, (ids, pts, n_kf, _) = _run_both(hostcheck, seq, 2000, 10, _check_run_sequence=True)
     for i, (T_o, io, T_p, ip) in enumerate(rows):
         assert (io["state_out"], io["keyframe"], io["map_points"], io["n_keypoints"], io["n_matches"], io["n_inliers"], io["pnp_ok"]) == \
                (ip.state_out, ip.keyframe, ip.map_points, ip.n_keypoints, ip.n_matches, ip.n_inliers, ip.pnp_ok), i
