@@ -1249,7 +1249,7 @@ k_describe(OrbPlanDev plan, const uint8_t *__restrict__ planes, const uint2 *__r
   }
 }
 
-#include "orb_variants.cuh"   // experimental k_blur2 / k_describe_sel2 (MVO_BLUR2 / MVO_DESCRIBE2), host-emulated in tests
+#include "orb_variants.cuh"   // k_blur2 (the shipped descriptor blur; MVO_BLUR2=0: k_blur), host-emulated in tests
 
 // Harris response of every compact candidate of the frames whose levels overflow (retainBest needs them all).  One THREAD
 // per candidate: the 9 x 9 neighbourhood is read once into registers, the 49 Sobel-like gradients and the three integer sums
@@ -1551,13 +1551,9 @@ int orb_launch_describe_sel(mvo_ctx *ctx, const OrbPlanDev &plan, const uint8_t 
                             int32_t *counts, int out_cap, int with_desc, int batch) {
   const int blocks = (plan.max_kpts + 1 + DESC_WARPS - 1) / DESC_WARPS;
   dim3 grid(blocks < 1 ? 1 : blocks, batch);
-  static const bool use_describe2 = getenv("MVO_DESCRIBE2") != nullptr && atoi(getenv("MVO_DESCRIBE2")) != 0;      // experimental variant
   KTimer kt(ctx, KC_DESCRIBE);
-  if (use_describe2)
-    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe_sel2, plan, planes, sel, meta, n_override, kpts, desc, counts, out_cap, with_desc));
-  else
-    MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe<0>, plan, planes, sel, meta, n_override, (const mvo_keypoint *)nullptr, 0, kpts,
-                              desc, counts, out_cap, with_desc, (int32_t *)nullptr));
+  MVO_CUDA(ctx, launch_pdl3(ctx->stream, grid, dim3(DESC_WARPS * 32), 0, k_describe<0>, plan, planes, sel, meta, n_override, (const mvo_keypoint *)nullptr, 0, kpts,
+                            desc, counts, out_cap, with_desc, (int32_t *)nullptr));
   MVO_CHECK_LAUNCH(ctx);
   return MVO_OK;
 }

@@ -1,5 +1,5 @@
-// TEST INFRASTRUCTURE (CPU tier): csrc/orb_variants.cuh — the very text nvcc compiles for the experimental k_blur2 /
-// k_describe_sel2 kernels — compiled for the host and executed one OS thread per CUDA thread, one block at a time:
+// TEST INFRASTRUCTURE (CPU tier): csrc/orb_variants.cuh — the very text nvcc compiles for k_blur2, the shipped descriptor blur —
+// compiled for the host and executed one OS thread per CUDA thread, one block at a time:
 // threadIdx / blockIdx are thread-local, __shared__ arrays are function-local statics (one block runs at a time),
 // __syncthreads() is a barrier over the block's threads, __shfl_xor_sync an exchange through a per-warp buffer with two
 // warp barriers, and the round-to-nearest intrinsics are plain float operations (built with -ffp-contract=off).
@@ -69,30 +69,5 @@ int emu_blur2(int nlevels, const int *w, const int *h, const uint8_t *imgs, uint
   return 0;
 }
 
-// imgs / blurred: level images back to back; sel: n x (packed x | y << 12, level); outputs: n keypoints, n x 32 descriptor bytes
-int emu_describe_sel2(int nlevels, const int *w, const int *h, const float *scale, const uint8_t *imgs, const uint8_t *blurred,
-                      const uint32_t *sel_xy, const uint32_t *sel_level, int n, mvo_keypoint *kout, uint8_t *desc) {
-  std::vector<uint8_t> planes;
-  OrbPlanDev pl = make_plan(nlevels, w, h, scale, &planes);
-  pl.max_kpts = n;                                                 // selection rows are max_kpts + 1 apart
-  const uint8_t *a = imgs, *b = blurred;
-  for (int l = 0; l < nlevels; ++l) {
-    for (int y = 0; y < h[l]; ++y) {
-      memcpy(&planes[pl.lv[l].img_off + (size_t)y * pl.lv[l].pitch], a + (size_t)y * w[l], (size_t)w[l]);
-      memcpy(&planes[pl.lv[l].blur_off + (size_t)y * pl.lv[l].pitch], b + (size_t)y * w[l], (size_t)w[l]);
-    }
-    a += (size_t)w[l] * h[l]; b += (size_t)w[l] * h[l];
-  }
-  std::vector<uint2> sel((size_t)n + 1);
-  for (int i = 0; i < n; ++i) sel[(size_t)i] = make_uint2(sel_xy[i], sel_level[i]);
-  OrbFrameMeta meta;
-  memset(&meta, 0, sizeof meta);
-  meta.n_sel = n;
-  int32_t count = -1;
-  const int blocks = std::max(1, std::min(8, (n + DESC_WARPS - 1) / DESC_WARPS));      // grid-stride loop: any grid size covers all keypoints
-  const uint8_t *p = planes.data();
-  run_grid((unsigned)blocks, 1, 1, DESC_WARPS * 32, 0, [&] { k_describe_sel2(pl, p, sel.data(), &meta, nullptr, kout, desc, &count, n, 1); });
-  return count;
-}
 
 }  // extern "C"

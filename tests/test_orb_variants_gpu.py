@@ -1,7 +1,7 @@
-"""Experimental ORB kernel variants (csrc/orb.cu: k_blur2 under MVO_BLUR2=1, k_describe_sel2 under MVO_DESCRIBE2=1): same
-arithmetic as the shipped kernels with fewer instructions.  The switch is read once per process, so each configuration
-runs in its own child process; keypoints and descriptors must be byte-identical with the shipped kernels' (which are
-themselves bit-exact with cv2, tests/test_orb_gpu.py).  Passes on the B200 (GPUTEST_r01.json)."""
+"""The kernels the shipped ORB path replaced stay selectable (MVO_BLUR2=0: k_blur; MVO_PYR_FUSED=0: k_gray + k_resize; MVO_FAST_TMA=0:
+vector-load staging; MVO_GRID_ROUNDS=1: round-based grid selection; MVO_PDL=0: plain launches).  The switches are read once per
+process, so each configuration runs in its own child process; keypoints and descriptors must be byte-identical with the shipped
+kernels' (which are themselves bit-exact with cv2, tests/test_orb_gpu.py)."""
 import os
 import subprocess
 import sys
@@ -45,9 +45,9 @@ def _extract(tmp_path, name, env):
     return np.load(out)
 
 
-@pytest.mark.parametrize("env", [{"MVO_BLUR2": "1"}, {"MVO_DESCRIBE2": "1"}, {"MVO_BLUR2": "1", "MVO_DESCRIBE2": "1"}], ids=["blur2", "describe2", "both"])
+@pytest.mark.parametrize("env", [{"MVO_BLUR2": "0"}, {"MVO_PYR_FUSED": "0", "MVO_FAST_TMA": "0", "MVO_GRID_ROUNDS": "1", "MVO_PDL": "0"}], ids=["round1_blur", "round1_pyramid_fast_select"])
 def test_variant_is_byte_identical_with_the_shipped_kernels(built, tmp_path, env):
-    ref = _extract(tmp_path, "shipped", {"MVO_BLUR2": "0", "MVO_DESCRIBE2": "0"})
+    ref = _extract(tmp_path, "shipped", {})
     got = _extract(tmp_path, "variant", env)
     assert sorted(ref.files) == sorted(got.files)
     for k in ref.files:

@@ -8,7 +8,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-CONFIGS = [{}, {"MVO_BLUR2": "1"}, {"MVO_DESCRIBE2": "1"}, {"MVO_BLUR2": "1", "MVO_DESCRIBE2": "1"}]
+CONFIGS = [{}, {"MVO_BLUR2": "0"}, {"MVO_PYR_FUSED": "0"}, {"MVO_FAST_TMA": "0"}, {"MVO_GRID_ROUNDS": "1"}, {"MVO_PDL_ORB": "0"}]
 
 
 def child():
@@ -48,7 +48,7 @@ def child():
     for it in range(2):
         call((it % 2) * B)
     ms, cnt = mvo_b200.timing_read(ctx)
-    print(json.dumps({"config": {k: v for k, v in os.environ.items() if k in ("MVO_BLUR2", "MVO_DESCRIBE2")}, "us_per_frame": us / B,
+    print(json.dumps({"config": {k: v for k, v in os.environ.items() if k in ("MVO_BLUR2", "MVO_PYR_FUSED", "MVO_FAST_TMA", "MVO_GRID_ROUNDS", "MVO_PDL_ORB")}, "us_per_frame": us / B,
                       "frames_per_s": B / (us * 1e-6), "kernel_us_per_frame": {names[k]: round(1e3 * ms[k] / (2 * B), 3) for k in range(len(names)) if cnt[k]},
                       "checksum": int(d_d.to(torch.int64).sum().item())}))
 
@@ -59,7 +59,6 @@ if __name__ == "__main__":
     else:
         for cfg in CONFIGS:
             env = dict(os.environ)
-            env.update({"MVO_BLUR2": "0", "MVO_DESCRIBE2": "0"})
             env.update(cfg)
             r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
             print(r.stdout.strip() or json.dumps({"config": cfg, "error": r.stderr[-600:]}), flush=True)
