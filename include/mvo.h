@@ -474,7 +474,8 @@ int mvo_vo_prefetch(mvo_vo *v, const uint8_t *image, int channels, size_t stride
  * that are already in memory, with the look-ahead of mvo_vo_prefetch applied to frame i + 1 while frame i is added.  images[i]:
  * rows x cols x channels, host or device memory alike for all frames; T_w_c_out: n_frames x 16 doubles (the pose of every
  * frame when its addFrame returned); infos: n_frames records or NULL; *n_done = frames added when the call returns (it stops at
- * the first frame whose addFrame fails and returns that code).  Results equal n_frames calls of mvo_vo_add_frame_ex. */
+ * the first frame whose addFrame fails and returns that code; frames handed over ahead of it stay queued: add them in order or call
+ * mvo_vo_reset).  Results equal n_frames calls of mvo_vo_add_frame_ex. */
 int mvo_vo_run_sequence(mvo_vo *v, const uint8_t *const *images, int n_frames, int channels, size_t stride, int images_on_device,
                         double *T_w_c_out, mvo_vo_frame_info *infos, int *n_done);
 /* 1 when the tracking branch runs through the device-resident tracker (mvo_vo_params::track.device_resident, fixed map
