@@ -763,9 +763,15 @@ __device__ void pose_pass(const PoseArgs &a, int F, int nchunks, const double *P
   }
   __syncthreads();
   for (int i = tid; i < NV; i += PF_T) {
+    // all PF_NW loads first (independent, in flight together), then the clearing stores, then the sum in warp order
+    double part[PF_NW];
+#pragma unroll
+    for (int w = 0; w < PF_NW; ++w) part[w] = s_wacc[w * NV + i];
+#pragma unroll
+    for (int w = 0; w < PF_NW; ++w) s_wacc[w * NV + i] = 0;
     double s2 = 0;
 #pragma unroll
-    for (int w = 0; w < PF_NW; ++w) { s2 += s_wacc[w * NV + i]; s_wacc[w * NV + i] = 0; }
+    for (int w = 0; w < PF_NW; ++w) s2 += part[w];
     s_part[i] = s2;
   }
 }
