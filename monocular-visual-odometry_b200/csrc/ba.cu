@@ -702,6 +702,14 @@ __device__ __forceinline__ double warp_fold32(double (&v)[32], int lane) {
 // One pass over this CTA's chunks at poses `P` -> s_part[f*PF_V + q].  Thread (rank, tid) owns chunk
 // rank*PF_T + tid: CH consecutive edges of ONE frame (host pads each frame's run to a multiple of CH with
 // frame -1), cached in shared memory (s_ed, SoA) when CACHED, so the LM trials never touch global memory.
+// Which chunk thread (rank, tid) of the cluster owns when the chunks are cached in shared memory: consecutive WARPS of chunks go to
+// consecutive CTAs (warp w of CTA r takes chunks 32 (w csize + r) ..), so that a problem with fewer chunks than threads — the PnP refit
+// has ~500 edges for 4096 threads, the 5-frame BA ~2700 — keeps every SM of the cluster equally busy instead of filling CTA 0 first
+// (the fp64 pass of 16 full warps costs ~2.5 K cycles on one SM).  A warp still holds 32 consecutive chunks: one frame, rarely two.
+__device__ __forceinline__ int pf_chunk_of(unsigned rank, int tid, unsigned csize) {
+  return ((((tid >> 5) * (int)csize) + (int)rank) << 5) + (tid & 31);
+}
+
 template <int CH, bool CACHED>
 __device__ void pose_pass(const PoseArgs &a, int F, int nchunks, const double *P, const double *s_ed, const int *s_ef,
                           double *s_wacc /*[PF_NW][NV]*/, double *s_part, unsigned rank, unsigned csize) {
@@ -710,7 +718,7 @@ __device__ void pose_pass(const PoseArgs &a, int F, int nchunks, const double *P
   // s_wacc is all-zero on entry (cleared at kernel start and re-cleared by the reduction below)
   const int chunk = CACHED ? CH : a.chunk;
   const int stride = (int)csize * PF_T;
-  for (int cbase = (int)rank * PF_T; cbase < nchunks; cbase += stride) {      // one sweep when CACHED
+  for (int cbase = CACHED ? 0 : (int)rank * PF_T; cbase < (CACHED ? 1 : nchunks); cbase += CACHED ? 1 : stride) {      // one sweep when CACHED
     const int c = cbase + tid;
     double v[32];
 #pragma unroll
@@ -833,7 +841,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
   for (int i = tid; i < PF_NW * NV; i += PF_T) s_wacc[i] = 0;
   int my_edges = 0;
   if (STORE) {                               // this thread's chunk: gather the (fixed) map points of its observations
-    const int c = (int)rank * PF_T + tid;
+    const int c = pf_chunk_of(rank, tid, csize);
     int f = -1;
     if (c < nchunks) { f = 0; while (c >= s_cstart[f + 1]) ++f; }
     s_ef[tid] = f;
@@ -856,7 +864,7 @@ __global__ void __launch_bounds__(PF_T, 1) k_ba_pose(PoseArgs a) {
       ed[0] = X0; ed[PF_T] = X1; ed[2 * PF_T] = X2; ed[3 * PF_T] = ou; ed[4 * PF_T] = ov;
     }
   } else if (CACHED) {                       // this thread's chunk -> shared memory, once
-    const int c = (int)rank * PF_T + tid;
+    const int c = pf_chunk_of(rank, tid, csize);
     int f = -1;
     if (c < nchunks) f = a.e_frame[c * CH];
     s_ef[tid] = f;
