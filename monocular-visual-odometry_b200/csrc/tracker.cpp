@@ -7,14 +7,16 @@
 // Two implementations of the same step, selected by mvo_track_params::device_resident:
 //   * device-resident (default, shipped configuration = fixed map points): the map (points + descriptors),
 //     the frame buffer (pose + inlier connections of the newest kBuffSize_ frames) and the BA graph live in
-//     HBM.  Per frame the host synchronises twice: after the match kernel (the reference's duplicate removal
-//     is an unstable libstdc++ std::sort whose result has to be reproduced on the host) and at the end of the
-//     frame (poses and counters, ~3 KB).  Everything in between is launched back to back on one stream.
+//     HBM.  Per frame the host synchronises ONCE, at the end of the frame (result block and pose ring, ~3 KB): the
+//     reference's duplicate removal — an unstable libstdc++ std::sort — is restated on the device (track_filter.cuh;
+//     the host variant remains for the inputs on which libstdc++ would leave quicksort).  Everything is launched back
+//     to back on one stream with programmatic dependent launch, and the head of the NEXT frame's chain (match filter +
+//     PnP) is enqueued behind the current frame's bundle adjustment when that frame has been prefetched.
 //   * host-array: every stage through its public C-ABI entry point (mvo_match_features, mvo_solve_pnp_ransac,
 //     mvo_bundle_adjustment), as a maintainer who only swaps the bodies of the reference functions gets it.
-// ORB extraction does not depend on the VO state: a worker thread owns two extraction contexts
-// (own stream + workspace each) and runs frame i+1 — upload, kernels, the rare host retainBest path — while
-// frame i is tracked.
+// ORB extraction does not depend on the VO state: three extraction slots, each with its own context
+// (stream + workspace) and worker thread, run the prefetched frames i+1 and i+2 — upload, kernels, the pre-match against
+// the map, the rare host retainBest path — while frame i (which holds the third slot) is tracked.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
