@@ -592,6 +592,7 @@ void mvo_tracker_destroy(mvo_tracker *t) {
   }
   for (int k = 0; k < MVO_XSLOTS; ++k)
     if (t->xctx[k]) mvo_destroy(t->xctx[k]);
+  if (t->ev_result) { cudaSetDevice(t->ctx->device); cudaEventDestroy(t->ev_result); t->ev_result = nullptr; }
   if (t->dev || t->dev_map || t->dev_ids) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
